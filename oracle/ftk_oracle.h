@@ -1,0 +1,61 @@
+/* ORACLE (test infrastructure -- never shipped, never measured as the product).
+ *
+ * Plain-C, single-threaded CPU restatement of the reference hot path (pyramid, 3 KLT trackers x 3 methods,
+ * descriptor matching).  Every function in ftk_oracle.c cites the reference file:line it follows.
+ *
+ * Pinning: the reference has no golden vectors or assertions for this path, so this
+ * restatement is pinned against outputs of the reference itself: oracle/_ref/libftk_ref.so (the reference's
+ * own .cpp compiled in place against oracle/shim/) must agree BIT-FOR-BIT with this file on the bundled EuRoC
+ * pair and on seeded synthetic inputs (tests/test_oracle_vs_ref.py), and both must reproduce the committed
+ * golden dumps under tests/golden/.  The external dependencies the reference leans on (Eigen LDLT,
+ * Slam_Utility GrayImage / ImagePyramid) are absent from /root/reference; their semantics are frozen in
+ * oracle/shim/  and restated here identically.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may load this library. */
+#ifndef FTK_ORACLE_H_
+#define FTK_ORACLE_H_
+#include <stdint.h>
+
+#include "ftk_oracle_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ftko_pyramid_build(const uint8_t *image, int32_t rows, int32_t cols, int32_t levels, uint8_t *out);
+
+int ftko_klt_track(const ftko_klt_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                   const int32_t *rows, const int32_t *cols, int32_t n, const float *ref_uv, float *cur_uv, int32_t cur_uv_count, uint8_t *status,
+                   int32_t status_count, int32_t single_level);
+
+/* Same as ftko_klt_track, and additionally reports, per feature, how many Gauss-Newton iterations (calls of
+ * the per-patch accumulation routine) were executed over all levels: the "patch-iteration" unit of SURVEY.md
+ * section 8(d).  iterations may be NULL. */
+int ftko_klt_track_traced(const ftko_klt_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                          const int32_t *rows, const int32_t *cols, int32_t n, const float *ref_uv, float *cur_uv, int32_t cur_uv_count,
+                          uint8_t *status, int32_t status_count, int32_t single_level, int32_t *iterations);
+
+int ftko_pyramid_and_track(const ftko_klt_params *params, int32_t levels, const uint8_t *ref_image, const uint8_t *cur_image, int32_t rows,
+                           int32_t cols, int32_t n, const float *ref_uv, float *cur_uv, uint8_t *status);
+
+int ftko_match_brief_force(const uint8_t *ref_bits, int32_t n_ref, const uint8_t *cur_bits, int32_t n_cur, int32_t len, float max_dist, int32_t *idx,
+                           int32_t idx_count);
+int ftko_match_brief_nearby(const uint8_t *ref_bits, int32_t n_ref, const uint8_t *cur_bits, int32_t n_cur, int32_t len, const float *pred_uv,
+                            const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx, int32_t idx_count);
+int ftko_match_cosine_force(const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist, int32_t *idx,
+                            int32_t idx_count);
+int ftko_match_cosine_nearby(const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, const float *pred_uv, const float *cur_uv,
+                             int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx, int32_t idx_count);
+int ftko_match_brief_nearby_uv(const uint8_t *ref_bits, int32_t n_ref, const uint8_t *cur_bits, int32_t n_cur, int32_t len, const float *pred_uv,
+                               const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, float *matched_uv, uint8_t *status,
+                               int32_t status_count);
+int ftko_match_brief_force_uv(const uint8_t *ref_bits, int32_t n_ref, const uint8_t *cur_bits, int32_t n_cur, int32_t len, const float *cur_uv,
+                              float max_dist, float *matched_uv, uint8_t *status, int32_t status_count);
+
+/* Exposed for unit tests of the LDLT restatement: solves A x = b for n in {2,3,6}; A row-major n*n. */
+void ftko_ldlt_solve(int32_t n, const float *a, const float *b, float *x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

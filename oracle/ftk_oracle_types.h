@@ -1,0 +1,26 @@
+/* ORACLE (test infrastructure, never shipped or measured as product).
+ * Plain-C parameter block shared by the two CPU checkers in this directory:
+ *   - oracle/_ref/libftk_ref.so   : the reference's own .cpp files compiled in place against oracle/shim/
+ *   - oracle/_build/libftk_oracle.so : the plain-C restatement in ftk_oracle.c
+ * Field meaning follows the reference's OpticalFlowOptions (src/optical_flow_tracker/optical_flow.h:20-28),
+ * OpticalFlowMethod (:12-18) and the subclass extras (affine_klt/optical_flow_affine_klt.h:18,
+ * lssd_klt/optical_flow_lssd_klt.h:18-19).  The layout is deliberately identical to `ftk_klt_params` in
+ * include/ftk_c.h so one ctypes.Structure serves all three libraries. */
+#ifndef FTK_ORACLE_TYPES_H_
+#define FTK_ORACLE_TYPES_H_
+#include <stdint.h>
+
+typedef struct ftko_klt_params {
+    int32_t variant;                   /* 0 basic, 1 affine, 2 lssd */
+    int32_t method;                    /* 0 kInverse, 1 kDirect, 2 kFast (3,4 = kSse/kNeon fall to kFast) */
+    uint32_t max_track_points;         /* kMaxTrackPointsNumber */
+    uint32_t max_iteration;            /* kMaxIteration */
+    uint32_t max_tolerance_large_step; /* kMaxToleranceLargeStep */
+    int32_t patch_row_half;            /* kPatchRowHalfSize */
+    int32_t patch_col_half;            /* kPatchColHalfSize */
+    float max_converge_step;           /* kMaxConvergeStep (on the SQUARED step) */
+    float predict[4];                  /* row-major 2x2: predict_affine_ (affine) / predict_R_cr_ (lssd) */
+    int32_t consider_patch_luminance;  /* lssd fast only */
+} ftko_klt_params;
+
+#endif

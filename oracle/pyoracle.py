@@ -1,0 +1,281 @@
+"""ORACLE bindings (test infrastructure -- never imported by the product package).
+
+ctypes wrappers for the two CPU checkers:
+  * ``RefLib``    -> oracle/_ref/libftk_ref.so, the reference's own .cpp compiled in place (kind "reference")
+  * ``OracleLib`` -> oracle/_build/libftk_oracle.so, the plain-C restatement (kind "port")
+Both expose the same Python methods so tests can compare them with each other and with the CUDA path.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libftk_ref.so")
+ORACLE_SO = os.path.join(HERE, "_build", "libftk_oracle.so")
+REFERENCE_ROOT = "/root/reference"
+
+VARIANTS = {"basic": 0, "affine": 1, "lssd": 2}
+METHODS = {"inverse": 0, "direct": 1, "fast": 2}
+
+
+class KltParams(C.Structure):
+    """Mirror of ftko_klt_params / ftk_klt_params (same layout in all three libraries)."""
+
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("method", C.c_int32),
+        ("max_track_points", C.c_uint32),
+        ("max_iteration", C.c_uint32),
+        ("max_tolerance_large_step", C.c_uint32),
+        ("patch_row_half", C.c_int32),
+        ("patch_col_half", C.c_int32),
+        ("max_converge_step", C.c_float),
+        ("predict", C.c_float * 4),
+        ("consider_patch_luminance", C.c_int32),
+    ]
+
+
+def make_params(variant="basic", method="fast", half=6, half_col=None, max_points=500, max_iter=15, max_large=3,
+                converge=4e-2, predict=(1.0, 0.0, 0.0, 1.0), luminance=False):
+    """Defaults are the reference's OpticalFlowOptions defaults (optical_flow.h:20-28)."""
+    p = KltParams()
+    p.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    p.method = METHODS[method] if isinstance(method, str) else int(method)
+    p.max_track_points = max_points
+    p.max_iteration = max_iter
+    p.max_tolerance_large_step = max_large
+    p.patch_row_half = half
+    p.patch_col_half = half if half_col is None else half_col
+    p.max_converge_step = converge
+    for i in range(4):
+        p.predict[i] = predict[i]
+    p.consider_patch_luminance = 1 if luminance else 0
+    return p
+
+
+def build_ref(force=False):
+    """Compile the reference sources in place (only possible where /root/reference exists)."""
+    if os.path.exists(REF_SO) and not force:
+        return True
+    if not os.path.isdir(REFERENCE_ROOT):
+        return False
+    subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
+    return os.path.exists(REF_SO)
+
+
+def build_oracle(force=False):
+    if force and os.path.exists(ORACLE_SO):
+        os.remove(ORACLE_SO)
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    return os.path.exists(ORACLE_SO)
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _f32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def pyramid_level_shapes(rows, cols, levels):
+    return [(rows >> i, cols >> i) for i in range(levels)]
+
+
+class _CpuChecker:
+    """Common Python surface over a CPU checker library with symbol prefix ``self.prefix``."""
+
+    prefix = None
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.path = path
+
+    def _fn(self, name):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = C.c_int
+        return f
+
+    # -- pyramid -----------------------------------------------------------------------------------------------
+    def pyramid_build(self, image, levels):
+        """Returns the list of level images [level0(view), level1, ...] (uint8 2-D arrays)."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        rows, cols = image.shape
+        shapes = pyramid_level_shapes(rows, cols, levels)
+        total = sum(r * c for r, c in shapes[1:])
+        out = np.zeros(max(total, 1), dtype=np.uint8)
+        ok = self._fn("pyramid_build")(_u8p(image), C.c_int32(rows), C.c_int32(cols), C.c_int32(levels), _u8p(out))
+        assert ok == 1
+        res = [image]
+        off = 0
+        for r, c in shapes[1:]:
+            res.append(out[off:off + r * c].reshape(r, c).copy())
+            off += r * c
+        return res
+
+    # -- KLT ---------------------------------------------------------------------------------------------------
+    def klt_track(self, params, ref_levels, cur_levels, ref_uv, cur_uv=None, status=None, single_level=False):
+        """ref_levels/cur_levels: lists of uint8 2-D arrays.  cur_uv/status None == empty vectors on entry.
+        Returns (ok, cur_uv[n,2] float32, status[n] uint8)."""
+        levels = len(ref_levels)
+        ref_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in ref_levels]
+        cur_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in cur_levels]
+        rows = np.array([a.shape[0] for a in ref_levels], dtype=np.int32)
+        cols = np.array([a.shape[1] for a in ref_levels], dtype=np.int32)
+        PtrArr = C.POINTER(C.c_uint8) * levels
+        rp = PtrArr(*[_u8p(a) for a in ref_levels])
+        cp = PtrArr(*[_u8p(a) for a in cur_levels])
+        ref_uv = np.ascontiguousarray(ref_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        if cur_uv is None:
+            cur_buf, cur_count = np.zeros((max(n, 1), 2), np.float32), 0
+        else:
+            cur_in = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+            cur_count = cur_in.shape[0]
+            cur_buf = np.zeros((max(n, cur_count, 1), 2), np.float32)
+            cur_buf[:cur_count] = cur_in
+        if status is None:
+            st_buf, st_count = np.zeros(max(n, 1), np.uint8), 0
+        else:
+            st_in = np.ascontiguousarray(status, dtype=np.uint8).reshape(-1)
+            st_count = st_in.shape[0]
+            st_buf = np.zeros(max(n, st_count, 1), np.uint8)
+            st_buf[:st_count] = st_in
+        ok = self._fn("klt_track")(C.byref(params), C.c_int32(levels), rp, cp, _i32p(rows), _i32p(cols), C.c_int32(n), _f32p(ref_uv),
+                                    _f32p(cur_buf), C.c_int32(cur_count), _u8p(st_buf), C.c_int32(st_count),
+                                    C.c_int32(1 if single_level else 0))
+        return ok == 1, cur_buf[:n].copy(), st_buf[:n].copy()
+
+    def pyramid_and_track(self, params, levels, ref_image, cur_image, ref_uv):
+        ref_image = np.ascontiguousarray(ref_image, dtype=np.uint8)
+        cur_image = np.ascontiguousarray(cur_image, dtype=np.uint8)
+        rows, cols = ref_image.shape
+        ref_uv = np.ascontiguousarray(ref_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        cur = np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.uint8)
+        ok = self._fn("pyramid_and_track")(C.byref(params), C.c_int32(levels), _u8p(ref_image), _u8p(cur_image), C.c_int32(rows), C.c_int32(cols),
+                                            C.c_int32(n), _f32p(ref_uv), _f32p(cur), _u8p(st))
+        return ok == 1, cur, st
+
+    # -- matching ----------------------------------------------------------------------------------------------
+    @staticmethod
+    def _idx(idx, n_ref):
+        if idx is None:
+            return np.zeros(max(n_ref, 1), np.int32), 0
+        idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1)
+        buf = np.zeros(max(n_ref, idx.shape[0], 1), np.int32)
+        buf[:idx.shape[0]] = idx
+        return buf, idx.shape[0]
+
+    def match_brief_force(self, ref_bits, cur_bits, max_dist, idx=None):
+        """ref_bits/cur_bits: [n, len] uint8 arrays of 0/1.  idx None == empty index vector on entry."""
+        ref_bits = np.ascontiguousarray(ref_bits, dtype=np.uint8)
+        cur_bits = np.ascontiguousarray(cur_bits, dtype=np.uint8)
+        n_ref, ln = ref_bits.shape if ref_bits.ndim == 2 else (0, cur_bits.shape[1])
+        n_cur = cur_bits.shape[0]
+        buf, cnt = self._idx(idx, n_ref)
+        ok = self._fn("match_brief_force")(_u8p(ref_bits), C.c_int32(n_ref), _u8p(cur_bits), C.c_int32(n_cur), C.c_int32(ln), C.c_float(max_dist),
+                                            _i32p(buf), C.c_int32(cnt))
+        return ok == 1, buf[:n_ref].copy()
+
+    def match_brief_nearby(self, ref_bits, cur_bits, pred_uv, cur_uv, max_drow, max_dcol, max_dist, idx=None):
+        ref_bits = np.ascontiguousarray(ref_bits, dtype=np.uint8)
+        cur_bits = np.ascontiguousarray(cur_bits, dtype=np.uint8)
+        n_ref, ln = ref_bits.shape
+        n_cur = cur_bits.shape[0]
+        pred_uv = np.ascontiguousarray(pred_uv, dtype=np.float32).reshape(-1, 2)
+        cur_uv = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+        assert pred_uv.shape[0] == n_ref and cur_uv.shape[0] == n_cur
+        buf, cnt = self._idx(idx, n_ref)
+        ok = self._fn("match_brief_nearby")(_u8p(ref_bits), C.c_int32(n_ref), _u8p(cur_bits), C.c_int32(n_cur), C.c_int32(ln), _f32p(pred_uv),
+                                             _f32p(cur_uv), C.c_int32(max_drow), C.c_int32(max_dcol), C.c_float(max_dist), _i32p(buf), C.c_int32(cnt))
+        return ok == 1, buf[:n_ref].copy()
+
+    def match_cosine_force(self, ref, cur, max_dist, idx=None):
+        ref = np.ascontiguousarray(ref, dtype=np.float32)
+        cur = np.ascontiguousarray(cur, dtype=np.float32)
+        n_ref, dim = ref.shape
+        n_cur = cur.shape[0]
+        buf, cnt = self._idx(idx, n_ref)
+        ok = self._fn("match_cosine_force")(_f32p(ref), C.c_int32(n_ref), _f32p(cur), C.c_int32(n_cur), C.c_int32(dim), C.c_float(max_dist), _i32p(buf),
+                                             C.c_int32(cnt))
+        return ok == 1, buf[:n_ref].copy()
+
+    def match_cosine_nearby(self, ref, cur, pred_uv, cur_uv, max_drow, max_dcol, max_dist, idx=None):
+        ref = np.ascontiguousarray(ref, dtype=np.float32)
+        cur = np.ascontiguousarray(cur, dtype=np.float32)
+        n_ref, dim = ref.shape
+        n_cur = cur.shape[0]
+        pred_uv = np.ascontiguousarray(pred_uv, dtype=np.float32).reshape(-1, 2)
+        cur_uv = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+        buf, cnt = self._idx(idx, n_ref)
+        ok = self._fn("match_cosine_nearby")(_f32p(ref), C.c_int32(n_ref), _f32p(cur), C.c_int32(n_cur), C.c_int32(dim), _f32p(pred_uv), _f32p(cur_uv),
+                                              C.c_int32(max_drow), C.c_int32(max_dcol), C.c_float(max_dist), _i32p(buf), C.c_int32(cnt))
+        return ok == 1, buf[:n_ref].copy()
+
+    def match_brief_nearby_uv(self, ref_bits, cur_bits, pred_uv, cur_uv, max_drow, max_dcol, max_dist, status=None):
+        ref_bits = np.ascontiguousarray(ref_bits, dtype=np.uint8)
+        cur_bits = np.ascontiguousarray(cur_bits, dtype=np.uint8)
+        n_ref, ln = ref_bits.shape
+        n_cur = cur_bits.shape[0]
+        pred_uv = np.ascontiguousarray(pred_uv, dtype=np.float32).reshape(-1, 2)
+        cur_uv = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+        matched = np.zeros((n_ref, 2), np.float32)
+        if status is None:
+            st, cnt = np.zeros(max(n_ref, 1), np.uint8), 0
+        else:
+            s_in = np.ascontiguousarray(status, dtype=np.uint8)
+            cnt = s_in.shape[0]
+            st = np.zeros(max(n_ref, cnt, 1), np.uint8)
+            st[:cnt] = s_in
+        ok = self._fn("match_brief_nearby_uv")(_u8p(ref_bits), C.c_int32(n_ref), _u8p(cur_bits), C.c_int32(n_cur), C.c_int32(ln), _f32p(pred_uv),
+                                                _f32p(cur_uv), C.c_int32(max_drow), C.c_int32(max_dcol), C.c_float(max_dist), _f32p(matched), _u8p(st),
+                                                C.c_int32(cnt))
+        return ok == 1, matched, st[:n_ref].copy()
+
+    def match_brief_force_uv(self, ref_bits, cur_bits, cur_uv, max_dist, status=None):
+        ref_bits = np.ascontiguousarray(ref_bits, dtype=np.uint8)
+        cur_bits = np.ascontiguousarray(cur_bits, dtype=np.uint8)
+        n_ref, ln = ref_bits.shape
+        n_cur = cur_bits.shape[0]
+        cur_uv = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+        matched = np.zeros((n_ref, 2), np.float32)
+        if status is None:
+            st, cnt = np.zeros(max(n_ref, 1), np.uint8), 0
+        else:
+            s_in = np.ascontiguousarray(status, dtype=np.uint8)
+            cnt = s_in.shape[0]
+            st = np.zeros(max(n_ref, cnt, 1), np.uint8)
+            st[:cnt] = s_in
+        ok = self._fn("match_brief_force_uv")(_u8p(ref_bits), C.c_int32(n_ref), _u8p(cur_bits), C.c_int32(n_cur), C.c_int32(ln), _f32p(cur_uv),
+                                               C.c_float(max_dist), _f32p(matched), _u8p(st), C.c_int32(cnt))
+        return ok == 1, matched, st[:n_ref].copy()
+
+
+class RefLib(_CpuChecker):
+    prefix = "ftkref_"
+
+    def __init__(self):
+        if not build_ref():
+            raise FileNotFoundError("oracle/_ref/libftk_ref.so is absent and /root/reference is not available to build it")
+        super().__init__(REF_SO)
+
+
+class OracleLib(_CpuChecker):
+    prefix = "ftko_"
+
+    def __init__(self):
+        build_oracle()
+        super().__init__(ORACLE_SO)
+
+
+def have_ref():
+    return os.path.exists(REF_SO) or os.path.isdir(REFERENCE_ROOT)
