@@ -1,0 +1,87 @@
+"""ctypes binding of libftk_b200.so (the C ABI in include/ftk_c.h).
+
+The library is the product: hand-written sm_100a kernels behind a C ABI.  There is no CPU fallback -- importing this
+module without the built library raises, and creating a context without a B200 raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libftk_b200.so")
+
+OK = 0
+ERR_INVALID_ARGUMENT = -1
+ERR_EMPTY_INPUT = -2
+ERR_LEVEL_MISMATCH = -3
+ERR_SIZE_MISMATCH = -4
+ERR_CUDA = -5
+ERR_UNSUPPORTED = -6
+
+FLAG_DEVICE_POINTERS = 1
+FLAG_NO_PREDICTION = 2
+FLAG_NO_STATUS = 4
+FLAG_SINGLE_LEVEL = 8
+FLAG_NO_INDEX_INPUT = 16
+
+# Every symbol include/ftk_c.h declares (tests check that the library exports all of them).
+EXPORTED_SYMBOLS = [
+    "ftk_abi_version", "ftk_klt_params_default", "ftk_create", "ftk_destroy", "ftk_last_error", "ftk_synchronize", "ftk_stream",
+    "ftk_kernel_launches", "ftk_pyramid_create", "ftk_pyramid_destroy", "ftk_pyramid_set_images", "ftk_pyramid_build",
+    "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
+    "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched",
+]
+
+
+class KltParams(C.Structure):
+    """ftk_klt_params (include/ftk_c.h) == OpticalFlowOptions + subclass extras of the reference."""
+
+    _fields_ = [
+        ("variant", C.c_int32),
+        ("method", C.c_int32),
+        ("max_track_points", C.c_uint32),
+        ("max_iteration", C.c_uint32),
+        ("max_tolerance_large_step", C.c_uint32),
+        ("patch_row_half", C.c_int32),
+        ("patch_col_half", C.c_int32),
+        ("max_converge_step", C.c_float),
+        ("predict", C.c_float * 4),
+        ("consider_patch_luminance", C.c_int32),
+    ]
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make` (or __graft_entry__.build()); feature_tracker_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, u32, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_float
+    P = C.POINTER
+    sig = {
+        "ftk_abi_version": (C.c_int, []),
+        "ftk_klt_params_default": (None, [P(KltParams)]),
+        "ftk_create": (C.c_int, [C.c_int, P(vp)]),
+        "ftk_destroy": (None, [vp]),
+        "ftk_last_error": (C.c_char_p, [vp]),
+        "ftk_synchronize": (C.c_int, [vp]),
+        "ftk_stream": (vp, [vp]),
+        "ftk_kernel_launches": (C.c_uint64, [vp]),
+        "ftk_pyramid_create": (C.c_int, [vp, i32, i32, i32, i32, P(vp)]),
+        "ftk_pyramid_destroy": (None, [vp, vp]),
+        "ftk_pyramid_set_images": (C.c_int, [vp, vp, i32, i32, vp, u32]),
+        "ftk_pyramid_build": (C.c_int, [vp, vp, i32, i32]),
+        "ftk_pyramid_set_level": (C.c_int, [vp, vp, i32, i32, vp]),
+        "ftk_pyramid_get_level": (C.c_int, [vp, vp, i32, i32, vp]),
+        "ftk_pyramid_levels": (i32, [vp]),
+        "ftk_pyramid_images": (i32, [vp]),
+        "ftk_klt_track": (C.c_int, [vp, P(KltParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, u32]),
+        "ftk_match_hamming_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_hamming_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_cosine_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_fill_matched": (C.c_int, [vp, i32, vp, i32, vp, vp, i32]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib

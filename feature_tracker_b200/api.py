@@ -1,0 +1,413 @@
+"""Host-side mirror of the reference's tracker / matcher interface on top of the C ABI.
+
+Names, option fields, argument meaning and error behaviour follow the reference's C++ classes
+(src/optical_flow_tracker/optical_flow.h, the three subclasses, src/descriptor_matcher/descriptor_matcher.h); the C++
+facade with the same names lives in include/feature_tracker_b200/.  In/out std::vector arguments become "pass the
+current content (or None for an empty vector), get the new content back".
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import IntEnum
+
+import numpy as np
+
+from . import _capi
+
+
+class TrackStatus(IntEnum):
+    """src/feature_tracker.h:8-14"""
+    kNotTracked = 0
+    kTracked = 1
+    kLargeResidual = 2
+    kOutside = 3
+    kNumericError = 4
+
+
+class OpticalFlowMethod(IntEnum):
+    """src/optical_flow_tracker/optical_flow.h:12-18"""
+    kInverse = 0
+    kDirect = 1
+    kFast = 2
+    kSse = 3
+    kNeon = 4
+
+
+@dataclass
+class OpticalFlowOptions:
+    """src/optical_flow_tracker/optical_flow.h:20-28 (same defaults)."""
+    kMaxTrackPointsNumber: int = 500
+    kMaxIteration: int = 15
+    kMaxToleranceLargeStep: int = 3
+    kPatchRowHalfSize: int = 6
+    kPatchColHalfSize: int = 6
+    kMaxConvergeStep: float = 4e-2
+    kMethod: OpticalFlowMethod = OpticalFlowMethod.kFast
+
+
+class FtkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _capi.load_library()
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One GPU + one stream (ftk_context).  Not re-entrant, like the reference's tracker objects."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().ftk_create(int(device), C.byref(self._h))
+        if rc != _capi.OK:
+            self._h = None
+            raise FtkError(f"ftk_create(device={device}) failed with code {rc}: a B200 (sm_100) GPU is required; there is no CPU fallback")
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ftk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, soft=()):
+        """Raises on hard errors; returns False for the codes the reference maps to `return false`."""
+        if rc == _capi.OK:
+            return True
+        if rc in soft:
+            return False
+        raise FtkError(f"ftk error {rc}: {lib().ftk_last_error(self._h).decode()}")
+
+    def synchronize(self):
+        self.check(lib().ftk_synchronize(self._h))
+
+    @property
+    def stream(self):
+        return lib().ftk_stream(self._h)
+
+    @property
+    def kernel_launches(self):
+        return int(lib().ftk_kernel_launches(self._h))
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+class ImagePyramidBatch:
+    """Device-resident batch of same-sized image pyramids (ImagePyramid of the reference, batched)."""
+
+    def __init__(self, ctx, rows, cols, levels, n_images=1):
+        self.ctx = ctx
+        self.rows, self.cols, self.n_levels, self.n_images = int(rows), int(cols), int(levels), int(n_images)
+        self._h = C.c_void_p()
+        ctx.check(lib().ftk_pyramid_create(ctx._h, self.rows, self.cols, self.n_levels, self.n_images, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            lib().ftk_pyramid_destroy(self.ctx._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def level(self):
+        return self.n_levels
+
+    def SetRawImages(self, images, first=0):
+        """images: uint8 array [n, rows, cols] (host)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        if images.ndim == 2:
+            images = images[None]
+        assert images.shape[1:] == (self.rows, self.cols), images.shape
+        self.ctx.check(lib().ftk_pyramid_set_images(self.ctx._h, self._h, int(first), images.shape[0], _ptr(images), 0))
+        self.ctx.synchronize()  # the source array may be freed by the caller
+
+    def set_images_ptr(self, ptr, count, first=0, device=False):
+        """Raw pointer variant (pinned host memory or device memory) used by the benchmark; asynchronous."""
+        flags = _capi.FLAG_DEVICE_POINTERS if device else 0
+        self.ctx.check(lib().ftk_pyramid_set_images(self.ctx._h, self._h, int(first), int(count), C.c_void_p(ptr), flags))
+
+    def CreateImagePyramid(self, first=0, count=None):
+        count = self.n_images - first if count is None else count
+        self.ctx.check(lib().ftk_pyramid_build(self.ctx._h, self._h, int(first), int(count)))
+
+    def SetLevel(self, image, level, data):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        assert data.shape == (self.rows >> level, self.cols >> level), data.shape
+        self.ctx.check(lib().ftk_pyramid_set_level(self.ctx._h, self._h, int(image), int(level), _ptr(data)))
+
+    def GetLevel(self, image, level):
+        out = np.zeros((self.rows >> level, self.cols >> level), np.uint8)
+        if out.size:
+            self.ctx.check(lib().ftk_pyramid_get_level(self.ctx._h, self._h, int(image), int(level), _ptr(out)))
+        return out
+
+
+class OpticalFlow:
+    """Base of the three trackers (src/optical_flow_tracker/optical_flow.h:30-104)."""
+
+    _variant = None
+    _name = "None"
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = OpticalFlowOptions()
+        self._predict = np.eye(2, dtype=np.float32)
+        self._consider_patch_luminance = False
+
+    def OpticalFlowMethodName(self):
+        return self._name
+
+    def options(self):
+        return self._options
+
+    def _params(self):
+        o = self._options
+        p = _capi.KltParams()
+        p.variant = self._variant
+        p.method = int(o.kMethod)
+        p.max_track_points = int(o.kMaxTrackPointsNumber)
+        p.max_iteration = int(o.kMaxIteration)
+        p.max_tolerance_large_step = int(o.kMaxToleranceLargeStep)
+        p.patch_row_half = int(o.kPatchRowHalfSize)
+        p.patch_col_half = int(o.kPatchColHalfSize)
+        p.max_converge_step = float(o.kMaxConvergeStep)
+        pr = np.asarray(self._predict, dtype=np.float32).reshape(4)
+        for i in range(4):
+            p.predict[i] = float(pr[i])
+        p.consider_patch_luminance = 1 if self._consider_patch_luminance else 0
+        return p
+
+    def TrackFeatures(self, ref_pyramid, cur_pyramid, ref_pixel_uv, cur_pixel_uv=None, status=None, single_level=False, ref_image=0,
+                      cur_image=0):
+        """optical_flow.cpp:6-47.  ref_pixel_uv [n,2] float32; cur_pixel_uv / status = the vectors' content on entry (None or a
+        wrong length behaves like the reference: no prediction / all kNotTracked).  `single_level=True` is the GrayImage overload.
+        Returns (ok, cur_pixel_uv, status)."""
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        offsets = np.array([0, n], dtype=np.int32)
+        ok, cur, st = self.TrackFeaturesBatch(ref_pyramid, cur_pyramid, offsets, ref_uv, cur_pixel_uv, status, single_level,
+                                              np.array([ref_image], np.int32), np.array([cur_image], np.int32))
+        return ok, cur, st
+
+    def TrackFeaturesBatch(self, ref_pyramid, cur_pyramid, feat_offsets, ref_pixel_uv, cur_pixel_uv=None, status=None, single_level=False,
+                           ref_image=None, cur_image=None):
+        """Many independent frame pairs in one call (pair p owns features feat_offsets[p]:feat_offsets[p+1])."""
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        feat_offsets = np.ascontiguousarray(feat_offsets, dtype=np.int32)
+        n_pairs = feat_offsets.shape[0] - 1
+        flags = _capi.FLAG_SINGLE_LEVEL if single_level else 0
+        cur = np.zeros((max(n, 1), 2), np.float32)
+        if cur_pixel_uv is not None and np.asarray(cur_pixel_uv).reshape(-1, 2).shape[0] == n and n > 0:
+            cur[:n] = np.asarray(cur_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        else:
+            flags |= _capi.FLAG_NO_PREDICTION
+        st = np.zeros(max(n, 1), np.uint8)
+        if status is not None and np.asarray(status).reshape(-1).shape[0] == n and n > 0:
+            st[:n] = np.asarray(status, dtype=np.uint8).reshape(-1)
+        else:
+            flags |= _capi.FLAG_NO_STATUS
+        ri = None if ref_image is None else np.ascontiguousarray(ref_image, dtype=np.int32)
+        ci = None if cur_image is None else np.ascontiguousarray(cur_image, dtype=np.int32)
+        p = self._params()
+        rc = lib().ftk_klt_track(self.ctx._h, C.byref(p), ref_pyramid._h, cur_pyramid._h, n_pairs, _ptr(ri), _ptr(ci), _ptr(feat_offsets),
+                                 _ptr(ref_uv), _ptr(cur), _ptr(st), flags)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT, _capi.ERR_LEVEL_MISMATCH))
+        return ok, cur[:n], st[:n]
+
+
+class OpticalFlowBasicKlt(OpticalFlow):
+    """basic_klt/optical_flow_basic_klt.h:9-41"""
+    _variant = 0
+    _name = "Basic-Klt"
+
+
+class OpticalFlowAffineKlt(OpticalFlow):
+    """affine_klt/optical_flow_affine_klt.h:9-52"""
+    _variant = 1
+    _name = "Affine-Klt"
+
+    def predict_affine(self):
+        return self._predict
+
+
+class OpticalFlowLssdKlt(OpticalFlow):
+    """lssd_klt/optical_flow_lssd_klt.h:9-56"""
+    _variant = 2
+    _name = "Lssd-Klt"
+
+    def predict_R_cr(self):
+        return self._predict
+
+    @property
+    def consider_patch_luminance(self):
+        return self._consider_patch_luminance
+
+    @consider_patch_luminance.setter
+    def consider_patch_luminance(self, v):
+        self._consider_patch_luminance = bool(v)
+
+
+@dataclass
+class MatcherOptions:
+    """descriptor_matcher.h:16-20 (same defaults: nothing matches until kMaxValidDescriptorDistance is raised)."""
+    kMaxValidPredictRowDistance: int = 40
+    kMaxValidPredictColDistance: int = 40
+    kMaxValidDescriptorDistance: float = 0.0
+
+
+def pack_brief(bits):
+    """[n, len] array of 0/1 -> [n, ceil(len/32)] uint32, element k = bit k%32 of word k//32."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    n, ln = bits.shape
+    words = (ln + 31) // 32
+    padded = np.zeros((n, words * 32), np.uint8)
+    padded[:, :ln] = bits != 0
+    return np.packbits(padded.reshape(n, words, 32), axis=2, bitorder="little").view(np.uint32).reshape(n, words)
+
+
+class DescriptorMatcher:
+    """descriptor_matcher.h:12-52.  Subclasses fix the distance instead of overriding a per-pair virtual."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = MatcherOptions()
+
+    def options(self):
+        return self._options
+
+    def _idx(self, index_pairs_in_cur, n_ref):
+        buf = np.full(max(n_ref, 1), -1, np.int32)
+        flags = 0
+        if index_pairs_in_cur is not None and np.asarray(index_pairs_in_cur).reshape(-1).shape[0] == n_ref and n_ref > 0:
+            buf[:n_ref] = np.asarray(index_pairs_in_cur, dtype=np.int32).reshape(-1)
+        else:
+            flags = _capi.FLAG_NO_INDEX_INPUT
+        return buf, flags
+
+    def _force(self, ref, cur, idx, flags):
+        raise NotImplementedError
+
+    def _nearby(self, ref, cur, pred, pos, idx, flags):
+        raise NotImplementedError
+
+    def ForceMatch(self, descriptors_ref, descriptors_cur, index_pairs_in_cur=None):
+        """descriptor_matcher.h:55-79.  Returns (ok, index_pairs_in_cur)."""
+        ref, cur = self._prep(descriptors_ref), self._prep(descriptors_cur)
+        n_ref = ref.shape[0]
+        idx, flags = self._idx(index_pairs_in_cur, n_ref)
+        ok = self.ctx.check(self._force(ref, cur, idx, flags), soft=(_capi.ERR_EMPTY_INPUT,))
+        return ok, idx[:n_ref]
+
+    def NearbyMatch(self, descriptors_ref, descriptors_cur, pixel_uv_pred_in_cur, pixel_uv_cur, index_pairs_in_cur=None):
+        """descriptor_matcher.h:90-124.  Returns (ok, index_pairs_in_cur)."""
+        ref, cur = self._prep(descriptors_ref), self._prep(descriptors_cur)
+        n_ref, n_cur = ref.shape[0], cur.shape[0]
+        pred = np.ascontiguousarray(pixel_uv_pred_in_cur, dtype=np.float32).reshape(-1, 2)
+        pos = np.ascontiguousarray(pixel_uv_cur, dtype=np.float32).reshape(-1, 2)
+        idx, flags = self._idx(index_pairs_in_cur, n_ref)
+        if n_cur == 0 or pred.shape[0] != n_ref or pos.shape[0] != n_cur:  # :94-96
+            return False, idx[:n_ref]
+        ok = self.ctx.check(self._nearby(ref, cur, pred, pos, idx, flags), soft=(_capi.ERR_EMPTY_INPUT, _capi.ERR_SIZE_MISMATCH))
+        return ok, idx[:n_ref]
+
+    def FillMatchedPixelByPairIndices(self, index_pairs_in_cur, pixel_uv_cur, status=None):
+        """descriptor_matcher.h:135-157.  Returns (matched_pixel_uv_cur, status)."""
+        idx = np.ascontiguousarray(index_pairs_in_cur, dtype=np.int32)
+        pos = np.ascontiguousarray(pixel_uv_cur, dtype=np.float32).reshape(-1, 2)
+        n_ref = idx.shape[0]
+        matched = np.zeros((max(n_ref, 1), 2), np.float32)
+        st = np.zeros(max(n_ref, 1), np.uint8)
+        valid = 0
+        if status is not None and np.asarray(status).reshape(-1).shape[0] == n_ref:
+            st[:n_ref] = np.asarray(status, dtype=np.uint8)
+            valid = 1
+        rc = lib().ftk_fill_matched(_ptr(idx), n_ref, _ptr(pos), pos.shape[0], _ptr(matched), _ptr(st), valid)
+        self.ctx.check(rc)
+        return matched[:n_ref], st[:n_ref]
+
+    def ForceMatchUv(self, descriptors_ref, descriptors_cur, pixel_uv_cur, status=None):
+        """descriptor_matcher.h:81-88: returns (ok, matched_pixel_uv_cur, status)."""
+        ok, idx = self.ForceMatch(descriptors_ref, descriptors_cur, None)
+        if not ok:
+            return False, None, status
+        matched, st = self.FillMatchedPixelByPairIndices(idx, pixel_uv_cur, status)
+        return True, matched, st
+
+    def NearbyMatchUv(self, descriptors_ref, descriptors_cur, pixel_uv_pred_in_cur, pixel_uv_cur, status=None):
+        """descriptor_matcher.h:126-133: returns (ok, matched_pixel_uv_cur, status)."""
+        ok, idx = self.NearbyMatch(descriptors_ref, descriptors_cur, pixel_uv_pred_in_cur, pixel_uv_cur, None)
+        if not ok:
+            return False, None, status
+        matched, st = self.FillMatchedPixelByPairIndices(idx, pixel_uv_cur, status)
+        return True, matched, st
+
+
+class BriefMatcher(DescriptorMatcher):
+    """DescriptorMatcher<BriefType> with the Hamming ComputeDistance of test/test_descriptor_matcher_brief.cpp:33-45.
+    Descriptors are [n, words] uint32 (see pack_brief)."""
+
+    def _prep(self, d):
+        d = np.ascontiguousarray(d, dtype=np.uint32)
+        return d.reshape(d.shape[0], -1) if d.ndim == 2 else d.reshape(0, 8)
+
+    def _force(self, ref, cur, idx, flags):
+        o = self._options
+        words = cur.shape[1]
+        return lib().ftk_match_hamming_force(self.ctx._h, _ptr(ref), ref.shape[0], _ptr(cur), cur.shape[0], words,
+                                             float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
+
+    def _nearby(self, ref, cur, pred, pos, idx, flags):
+        o = self._options
+        words = cur.shape[1]
+        return lib().ftk_match_hamming_nearby(self.ctx._h, _ptr(ref), ref.shape[0], _ptr(cur), cur.shape[0], words, _ptr(pred), _ptr(pos),
+                                              int(o.kMaxValidPredictRowDistance), int(o.kMaxValidPredictColDistance),
+                                              float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
+
+
+class CosineMatcher(DescriptorMatcher):
+    """DescriptorMatcher<SuperpointDescriptorType / DiskDescriptorType> with the 0.5 - 0.5*cos ComputeDistance of
+    test/test_descriptor_matcher_superpoint.cpp:32-34.  Descriptors are [n, dim] float32."""
+
+    def _prep(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        return d.reshape(d.shape[0], -1) if d.ndim == 2 else d.reshape(0, 256)
+
+    def _force(self, ref, cur, idx, flags):
+        o = self._options
+        return lib().ftk_match_cosine_force(self.ctx._h, _ptr(ref), ref.shape[0], _ptr(cur), cur.shape[0], cur.shape[1],
+                                            float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
+
+    def _nearby(self, ref, cur, pred, pos, idx, flags):
+        o = self._options
+        return lib().ftk_match_cosine_nearby(self.ctx._h, _ptr(ref), ref.shape[0], _ptr(cur), cur.shape[0], cur.shape[1], _ptr(pred), _ptr(pos),
+                                             int(o.kMaxValidPredictRowDistance), int(o.kMaxValidPredictColDistance),
+                                             float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
+
+
+SuperpointMatcher = CosineMatcher
+DiskMatcher = CosineMatcher

@@ -1,0 +1,454 @@
+// C ABI of libftk_b200.so (declared in include/ftk_c.h): context, device-resident pyramid batches, and the host-side
+// marshalling (H2D / launch / D2H) around the kernels in pyramid.cu, klt.cu, klt_basic_fastpath.cu and match.cu.
+// There is deliberately no CPU fallback anywhere in this library.
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "ftk_internal.h"
+
+namespace ftk {
+
+int SetError(ftk_context *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = buf;
+    return code;
+}
+
+int EnsureDevice(ftk_context *ctx, FtkBuffer &buf, size_t bytes) {
+    if (bytes <= buf.bytes && buf.ptr) return FTK_OK;
+    if (buf.ptr) {
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaFree(buf.ptr));
+        buf.ptr = nullptr;
+        buf.bytes = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    want += want / 4;  // growth slack
+    FTK_CUDA_CHECK(ctx, cudaMalloc(&buf.ptr, want));
+    buf.bytes = want;
+    return FTK_OK;
+}
+
+}  // namespace ftk
+
+using ftk::EnsureDevice;
+using ftk::SetError;
+
+namespace {
+
+inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) {
+        cudaGetDevice(&prev);
+        if (prev != device) cudaSetDevice(device);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void FreeBuffer(FtkBuffer &b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+}
+
+// Host or device source -> device buffer owned by the context (or the caller's device pointer as is).
+template <typename T>
+int Stage(ftk_context *ctx, FtkBuffer &buf, const T *src, size_t count, bool on_device, const T **out) {
+    if (on_device) {
+        *out = src;
+        return FTK_OK;
+    }
+    if (int rc = EnsureDevice(ctx, buf, sizeof(T) * (count ? count : 1))) return rc;
+    if (count) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(buf.ptr, src, sizeof(T) * count, cudaMemcpyHostToDevice, ctx->stream));
+    *out = static_cast<const T *>(buf.ptr);
+    return FTK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ftk_abi_version(void) { return FTK_ABI_VERSION; }
+
+void ftk_klt_params_default(ftk_klt_params *p) {
+    if (!p) return;
+    p->variant = FTK_VARIANT_BASIC;
+    p->method = FTK_METHOD_FAST;
+    p->max_track_points = 500;
+    p->max_iteration = 15;
+    p->max_tolerance_large_step = 3;
+    p->patch_row_half = 6;
+    p->patch_col_half = 6;
+    p->max_converge_step = 4e-2f;
+    p->predict[0] = 1.0f, p->predict[1] = 0.0f, p->predict[2] = 0.0f, p->predict[3] = 1.0f;
+    p->consider_patch_luminance = 0;
+}
+
+int ftk_create(int device, ftk_context **out) {
+    if (!out) return FTK_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return FTK_ERR_CUDA;  // no GPU: fail loudly, never fall back
+    if (device < 0 || device >= count) return FTK_ERR_INVALID_ARGUMENT;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return FTK_ERR_CUDA;
+    if (prop.major != 10) return FTK_ERR_UNSUPPORTED;  // the library only carries sm_100a code
+    ftk_context *ctx = new ftk_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    DeviceGuard guard(device);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return FTK_ERR_CUDA;
+    }
+    *out = ctx;
+    return FTK_OK;
+}
+
+void ftk_destroy(ftk_context *ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
+                        &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_work2, &ctx->d_work3};
+    for (FtkBuffer *b : all) FreeBuffer(*b);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *ftk_last_error(const ftk_context *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+
+int ftk_synchronize(ftk_context *ctx) {
+    if (!ctx) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FTK_OK;
+}
+
+void *ftk_stream(ftk_context *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+uint64_t ftk_kernel_launches(const ftk_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- pyramids -------------------------------------------------------------------------------------------------
+
+int ftk_pyramid_create(ftk_context *ctx, int32_t rows, int32_t cols, int32_t levels, int32_t n_images, ftk_pyramid **out) {
+    if (!ctx || !out) return FTK_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (rows <= 0 || cols <= 0 || n_images <= 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pyramid needs positive rows/cols/n_images");
+    if (levels < 1 || levels > ftk::kMaxLevels) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "levels must be in [1, %d]", ftk::kMaxLevels);
+    DeviceGuard guard(ctx->device);
+    ftk_pyramid *pyr = new ftk_pyramid();
+    pyr->device = ctx->device;
+    ftk::PyramidView &v = pyr->view;
+    memset(&v, 0, sizeof(v));
+    v.levels = levels;
+    v.n_images = n_images;
+    size_t total = 0;
+    size_t offset[ftk::kMaxLevels];
+    for (int l = 0; l < levels; ++l) {
+        v.rows[l] = rows >> l;
+        v.cols[l] = cols >> l;
+        const int r = v.rows[l] > 0 ? v.rows[l] : 1, c = v.cols[l] > 0 ? v.cols[l] : 1;
+        v.pitch[l] = RoundUp(c, 16);
+        // one extra row + 16 bytes of slack per plane: the sampler's weight-0 "+1" neighbours stay inside it
+        v.image_stride[l] = static_cast<long long>(v.pitch[l]) * (r + 1) + 16;
+        offset[l] = total;
+        total += static_cast<size_t>(v.image_stride[l]) * n_images;
+        total = (total + 255) / 256 * 256;
+    }
+    total += 256;
+    if (cudaMalloc(&pyr->storage, total) != cudaSuccess) {
+        delete pyr;
+        return SetError(ctx, FTK_ERR_CUDA, "cudaMalloc of %zu bytes for the pyramid batch failed: %s", total, cudaGetErrorString(cudaGetLastError()));
+    }
+    pyr->storage_bytes = total;
+    cudaMemsetAsync(pyr->storage, 0, total, ctx->stream);
+    for (int l = 0; l < levels; ++l) v.base[l] = pyr->storage + offset[l];
+    *out = pyr;
+    return FTK_OK;
+}
+
+void ftk_pyramid_destroy(ftk_context *ctx, ftk_pyramid *pyr) {
+    if (!pyr) return;
+    DeviceGuard guard(pyr->device);
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (pyr->storage) cudaFree(pyr->storage);
+    delete pyr;
+}
+
+int32_t ftk_pyramid_levels(const ftk_pyramid *pyr) { return pyr ? pyr->view.levels : 0; }
+int32_t ftk_pyramid_images(const ftk_pyramid *pyr) { return pyr ? pyr->view.n_images : 0; }
+
+int ftk_pyramid_set_images(ftk_context *ctx, ftk_pyramid *pyr, int32_t first, int32_t count, const uint8_t *images, uint32_t flags) {
+    if (!ctx || !pyr || !images) return FTK_ERR_INVALID_ARGUMENT;
+    const ftk::PyramidView &v = pyr->view;
+    if (first < 0 || count <= 0 || first + count > v.n_images) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image range out of bounds");
+    DeviceGuard guard(ctx->device);
+    const cudaMemcpyKind kind = (flags & FTK_FLAG_DEVICE_POINTERS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    uint8_t *dst = const_cast<uint8_t *>(v.base[0]) + first * v.image_stride[0];
+    const size_t plane = static_cast<size_t>(v.rows[0]) * v.cols[0];
+    // One strided 2-D copy per image (rows of `cols` bytes into rows of `pitch` bytes).
+    for (int i = 0; i < count; ++i) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst + i * v.image_stride[0], v.pitch[0], images + i * plane, v.cols[0], v.cols[0], v.rows[0], kind, ctx->stream));
+    }
+    return FTK_OK;
+}
+
+int ftk_pyramid_build(ftk_context *ctx, ftk_pyramid *pyr, int32_t first, int32_t count) {
+    if (!ctx || !pyr) return FTK_ERR_INVALID_ARGUMENT;
+    if (first < 0 || count <= 0 || first + count > pyr->view.n_images) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image range out of bounds");
+    DeviceGuard guard(ctx->device);
+    for (int done = 0; done < count;) {
+        const int n = (count - done) < 32768 ? (count - done) : 32768;  // gridDim.z limit
+        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, first + done, n)) return rc;
+        done += n;
+    }
+    return FTK_OK;
+}
+
+int ftk_pyramid_set_level(ftk_context *ctx, ftk_pyramid *pyr, int32_t image, int32_t level, const uint8_t *data) {
+    if (!ctx || !pyr || !data) return FTK_ERR_INVALID_ARGUMENT;
+    const ftk::PyramidView &v = pyr->view;
+    if (image < 0 || image >= v.n_images || level < 0 || level >= v.levels) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image/level out of range");
+    if (v.rows[level] == 0 || v.cols[level] == 0) return FTK_OK;
+    DeviceGuard guard(ctx->device);
+    uint8_t *dst = const_cast<uint8_t *>(v.base[level]) + image * v.image_stride[level];
+    FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst, v.pitch[level], data, v.cols[level], v.cols[level], v.rows[level], cudaMemcpyHostToDevice, ctx->stream));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FTK_OK;
+}
+
+int ftk_pyramid_get_level(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, int32_t level, uint8_t *data) {
+    if (!ctx || !pyr || !data) return FTK_ERR_INVALID_ARGUMENT;
+    const ftk::PyramidView &v = pyr->view;
+    if (image < 0 || image >= v.n_images || level < 0 || level >= v.levels) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image/level out of range");
+    if (v.rows[level] == 0 || v.cols[level] == 0) return FTK_OK;
+    DeviceGuard guard(ctx->device);
+    const uint8_t *src = v.base[level] + image * v.image_stride[level];
+    FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(data, v.cols[level], src, v.pitch[level], v.cols[level], v.rows[level], cudaMemcpyDeviceToHost, ctx->stream));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FTK_OK;
+}
+
+// ---- KLT ------------------------------------------------------------------------------------------------------
+
+int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t n_pairs,
+                  const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv, uint8_t *status,
+                  uint32_t flags) {
+    if (!ctx || !params || !ref || !cur || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
+    // optical_flow.cpp:9: RETURN_FALSE_IF(cur_pyramid.level() != ref_pyramid.level())
+    if (ref->view.levels != cur->view.levels) return SetError(ctx, FTK_ERR_LEVEL_MISMATCH, "ref has %d levels, cur has %d", ref->view.levels, cur->view.levels);
+    if (ref->view.rows[0] != cur->view.rows[0] || ref->view.cols[0] != cur->view.cols[0])
+        return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "ref and cur pyramids differ in image size");
+    if (params->variant < 0 || params->variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params->variant);
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+
+    // Feature offsets are always needed on the host too (sizes, validation).
+    std::vector<int32_t> h_offsets(n_pairs + 1);
+    if (on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_offsets.data(), feat_offsets, sizeof(int32_t) * (n_pairs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(h_offsets.data(), feat_offsets, sizeof(int32_t) * (n_pairs + 1));
+    }
+    if (h_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
+    for (int p = 0; p < n_pairs; ++p)
+        if (h_offsets[p + 1] < h_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
+    const int n_features = h_offsets[n_pairs];
+    // optical_flow.cpp:8: RETURN_FALSE_IF(ref_pixel_uv.empty())
+    if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");
+    if (!on_device) {
+        for (int p = 0; p < n_pairs; ++p) {
+            const int ri = ref_image ? ref_image[p] : p, ci = cur_image ? cur_image[p] : p;
+            if (ri < 0 || ri >= ref->view.n_images || ci < 0 || ci >= cur->view.n_images)
+                return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pair %d references image %d/%d outside the pyramid batches", p, ri, ci);
+        }
+    }
+
+    ftk::KltLaunch a{};
+    a.p = *params;
+    a.ref = ref->view;
+    a.cur = cur->view;
+    a.n_pairs = n_pairs;
+    a.n_features = n_features;
+    a.has_prediction = (flags & FTK_FLAG_NO_PREDICTION) ? 0 : 1;
+    a.has_status = (flags & FTK_FLAG_NO_STATUS) ? 0 : 1;
+    a.single_level = (flags & FTK_FLAG_SINGLE_LEVEL) ? 1 : 0;
+
+    const float2 *d_ref_uv = nullptr;
+    if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(ref_uv), n_features, on_device, &d_ref_uv)) return rc;
+    a.ref_uv = d_ref_uv;
+    if (on_device) {
+        a.cur_uv = reinterpret_cast<float2 *>(cur_uv);
+        a.status = status;
+        a.feat_offsets = feat_offsets;
+        a.ref_image = ref_image;
+        a.cur_image = cur_image;
+    } else {
+        if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_features)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_status, n_features)) return rc;
+        a.cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr);
+        a.status = static_cast<uint8_t *>(ctx->d_status.ptr);
+        if (a.has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(a.cur_uv, cur_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ctx->stream));
+        if (a.has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(a.status, status, n_features, cudaMemcpyHostToDevice, ctx->stream));
+        const int32_t *d = nullptr;
+        if (int rc = Stage(ctx, ctx->d_offsets, feat_offsets, n_pairs + 1, false, &d)) return rc;
+        a.feat_offsets = d;
+        if (ref_image) {
+            if (int rc = Stage(ctx, ctx->d_ref_img, ref_image, n_pairs, false, &d)) return rc;
+            a.ref_image = d;
+        }
+        if (cur_image) {
+            if (int rc = Stage(ctx, ctx->d_cur_img, cur_image, n_pairs, false, &d)) return rc;
+            a.cur_image = d;
+        }
+    }
+    if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * n_features)) return rc;
+    int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr);
+    if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, n_pairs, n_features, d_feat_pair)) return rc;
+    a.feat_pair = d_feat_pair;
+
+    if (int rc = ftk::LaunchKltTrack(ctx, a)) return rc;
+
+    if (!on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, a.cur_uv, sizeof(float2) * n_features, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, a.status, n_features, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FTK_OK;
+}
+
+// ---- matching -------------------------------------------------------------------------------------------------
+
+namespace {
+
+// Common index-vector handling (descriptor_matcher.h:60-62, 98-100): a missing index vector starts at -1.
+int PrepareIndex(ftk_context *ctx, int32_t *idx, int n_ref, uint32_t flags, int **d_idx) {
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    if (on_device) {
+        *d_idx = idx;
+    } else {
+        if (int rc = EnsureDevice(ctx, ctx->d_idx, sizeof(int) * (n_ref ? n_ref : 1))) return rc;
+        *d_idx = static_cast<int *>(ctx->d_idx.ptr);
+    }
+    if (n_ref == 0) return FTK_OK;
+    if (flags & FTK_FLAG_NO_INDEX_INPUT) {
+        FTK_CUDA_CHECK(ctx, cudaMemsetAsync(*d_idx, 0xFF, sizeof(int) * n_ref, ctx->stream));  // -1
+    } else if (!on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(*d_idx, idx, sizeof(int) * n_ref, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return FTK_OK;
+}
+
+int FinishIndex(ftk_context *ctx, int32_t *idx, int n_ref, uint32_t flags, const int *d_idx) {
+    if (flags & FTK_FLAG_DEVICE_POINTERS) return FTK_OK;
+    if (n_ref) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(idx, d_idx, sizeof(int) * n_ref, cudaMemcpyDeviceToHost, ctx->stream));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return FTK_OK;
+}
+
+}  // namespace
+
+int ftk_match_hamming_force(ftk_context *ctx, const uint32_t *ref, int32_t n_ref, const uint32_t *cur, int32_t n_cur, int32_t words, float max_dist,
+                            int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_ref < 0 || words < 0 || words > 64) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_cur <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "descriptors_cur is empty");  // descriptor_matcher.h:58
+    if ((n_ref > 0 && !ref) || !cur) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const uint32_t *d_ref = nullptr, *d_cur = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * words, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * words, on_device, &d_cur)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (int rc = ftk::LaunchHammingForce(ctx, d_ref, n_ref, d_cur, n_cur, words, max_dist, d_idx)) return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_ref, const uint32_t *cur, int32_t n_cur, int32_t words,
+                             const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
+                             uint32_t flags) {
+    if (!ctx || !idx || n_ref < 0 || words < 0 || words > 64) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_cur <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "descriptors_cur is empty");  // descriptor_matcher.h:94
+    if ((n_ref > 0 && (!ref || !pred_uv)) || !cur || !cur_uv) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const uint32_t *d_ref = nullptr, *d_cur = nullptr;
+    const float2 *d_pred = nullptr, *d_pos = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * words, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * words, on_device, &d_cur)) return rc;
+    if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
+    if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (int rc = ftk::LaunchHammingNearby(ctx, d_ref, n_ref, d_cur, n_cur, words, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist,
+                           int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_ref < 0 || dim <= 0) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_cur <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "descriptors_cur is empty");
+    if ((n_ref > 0 && !ref) || !cur) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const float *d_ref = nullptr, *d_cur = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * dim, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * dim, on_device, &d_cur)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (int rc = ftk::LaunchCosineForce(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx)) return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, const float *pred_uv,
+                            const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_ref < 0 || dim <= 0) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_cur <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "descriptors_cur is empty");
+    if ((n_ref > 0 && (!ref || !pred_uv)) || !cur || !cur_uv) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const float *d_ref = nullptr, *d_cur = nullptr;
+    const float2 *d_pred = nullptr, *d_pos = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * dim, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * dim, on_device, &d_cur)) return rc;
+    if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
+    if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (int rc = ftk::LaunchCosineNearby(ctx, d_ref, n_ref, d_cur, n_cur, dim, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+// descriptor_matcher.h:135-157 FillMatchedPixelByPairIndices (negligible host work in the reference; kept on the host).
+int ftk_fill_matched(const int32_t *idx, int32_t n_ref, const float *cur_uv, int32_t n_cur, float *matched_uv, uint8_t *status, int32_t status_valid) {
+    if (n_ref < 0 || (n_ref > 0 && (!idx || !matched_uv || !status))) return FTK_ERR_INVALID_ARGUMENT;
+    if (!status_valid) memset(status, FTK_STATUS_NOT_TRACKED, n_ref);
+    for (int32_t i = 0; i < n_ref; ++i) {
+        if (status[i] > FTK_STATUS_TRACKED) continue;
+        const int32_t j = idx[i];
+        if (j >= 0 && j < n_cur) {
+            matched_uv[2 * i] = cur_uv[2 * j];
+            matched_uv[2 * i + 1] = cur_uv[2 * j + 1];
+            status[i] = FTK_STATUS_TRACKED;
+        } else {
+            status[i] = FTK_STATUS_LARGE_RESIDUAL;
+        }
+    }
+    return FTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// Internal declarations shared by the translation units of libftk_b200.so (not part of the public ABI).
+#ifndef FTK_INTERNAL_H_
+#define FTK_INTERNAL_H_
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "ftk_c.h"
+
+namespace ftk {
+
+constexpr int kMaxLevels = 10;  // oracle/shim/datatype_image_pyramid.h: kPyramidMaxLevel
+
+// Device-side view of one pyramid batch.  Level l of image i starts at base[l] + i * image_stride[l]; rows are
+// `pitch[l]` bytes apart (a multiple of 16) and every plane is followed by at least pitch[l] + 16 readable bytes,
+// so the bilinear sampler's weight-0 "+1" neighbour on the last row / column never leaves the allocation.
+struct PyramidView {
+    const uint8_t *base[kMaxLevels];
+    long long image_stride[kMaxLevels];
+    int rows[kMaxLevels];
+    int cols[kMaxLevels];
+    int pitch[kMaxLevels];
+    int levels;
+    int n_images;
+};
+
+}  // namespace ftk
+
+struct ftk_pyramid {
+    ftk::PyramidView view;
+    uint8_t *storage = nullptr;
+    size_t storage_bytes = 0;
+    int device = 0;
+};
+
+// Growable device / pinned-host scratch buffer owned by a context.
+struct FtkBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct ftk_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    // device scratch
+    FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
+    FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
+};
+
+namespace ftk {
+
+int SetError(ftk_context *ctx, int code, const char *fmt, ...);
+int EnsureDevice(ftk_context *ctx, FtkBuffer &buf, size_t bytes);
+
+#define FTK_CUDA_CHECK(ctx, expr)                                                                              \
+    do {                                                                                                       \
+        cudaError_t err__ = (expr);                                                                            \
+        if (err__ != cudaSuccess) {                                                                            \
+            return ftk::SetError((ctx), FTK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                                 __FILE__, __LINE__);                                                          \
+        }                                                                                                      \
+    } while (0)
+
+// pyramid.cu
+int LaunchPyramidBuild(ftk_context *ctx, ftk_pyramid *pyr, int first, int count);
+
+// klt.cu
+struct KltLaunch {
+    ftk_klt_params p;
+    PyramidView ref, cur;
+    int n_pairs;
+    int n_features;
+    const int *ref_image;   // device, may be null
+    const int *cur_image;   // device, may be null
+    const int *feat_offsets;  // device [n_pairs + 1]
+    const int *feat_pair;     // device [n_features]
+    const float2 *ref_uv;
+    float2 *cur_uv;
+    uint8_t *status;
+    int has_prediction;
+    int has_status;
+    int single_level;
+};
+int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int n_features, int *d_feat_pair);
+int LaunchKltTrack(ftk_context *ctx, const KltLaunch &launch);
+
+// match.cu
+int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);
+int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
+                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
+int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
+int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,
+                       const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
+
+}  // namespace ftk
+
+#endif

@@ -1,0 +1,1009 @@
+// K2-K4: pyramidal sparse Lucas-Kanade tracking on sm_100a -- basic (2-DoF), affine (6-DoF) and LSSD (SE(2) + mean
+// normalisation) trackers, each with the reference's kInverse / kDirect / kFast methods.
+//
+// Replaces (paths relative to the reference's src/optical_flow_tracker/):
+//   basic_klt/optical_flow_basic_klt.cpp:7-181, basic_klt/optical_flow_basic_klt_fast.cpp:7-195,
+//   affine_klt/optical_flow_affine_klt.cpp:6-273, affine_klt/optical_flow_affine_klt_fast.cpp:7-188,
+//   lssd_klt/optical_flow_lssd_klt.cpp:7-250, lssd_klt/optical_flow_lssd_klt_fast.cpp:7-229,
+//   optical_flow.cpp:49-102 (ExtractExtendPatchInReferenceImage).
+//
+// Mapping: a group of G lanes (G = 8 for the 2-DoF tracker, 32 for affine / LSSD) owns one feature for its whole
+// coarse-to-fine life; level and Gauss-Newton loops stay inside the kernel.  Patch pixels are processed in
+// row-major chunks of G: phase 1 evaluates the per-pixel terms of the normal equations on G lanes in parallel
+// (each term is a chain of correctly rounded fp32 operations identical to the reference's), phase 2 lets lane k
+// fold the chunk's k-th term into accumulator k in pixel order.  The sums are therefore bit-identical to the
+// sequential CPU loops while K accumulators x (32/G) features advance per warp instruction.
+// This file is the generic ("literal") implementation for every variant/method and any patch size; the
+// specialised kernels for the head-line configurations live in klt_basic_fastpath.cu.
+#include "klt_device.cuh"
+
+namespace ftk {
+
+namespace {
+
+constexpr int kInverse = FTK_METHOD_INVERSE;
+constexpr int kDirect = FTK_METHOD_DIRECT;
+constexpr int kFast = FTK_METHOD_FAST;
+
+// Patch geometry (optical_flow.cpp:104-124 PrepareForTracking).
+struct Geometry {
+    int hr, hc;          // half sizes
+    int pr, pc, psize;   // patch
+    int er, ec, esize;   // extended patch (+1 border)
+};
+
+// Per-group shared-memory carve-up (sizes decided on the host, see GroupSmemBytes()).
+struct Scratch {
+    float *term;
+    float *ex;         // extended ref patch (fast methods)
+    float *dx, *dy;    // ref gradients (fast methods)
+    float *curp;       // cur patch (lssd fast)
+    uint8_t *exv;      // ex patch validity
+    uint8_t *curv;     // cur patch validity (lssd fast)
+};
+
+struct SmemLayout {
+    int term_floats, ex_floats, p_floats, curp_floats, exv_bytes, curv_bytes, total_bytes;
+};
+
+__host__ __device__ inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
+
+__host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G, const Geometry &geo) {
+    SmemLayout l{};
+    const int kmax = variant == FTK_VARIANT_BASIC ? 5 : (variant == FTK_VARIANT_AFFINE ? 27 : 9);
+    l.term_floats = RoundUp(kmax * (G + 4), 4);
+    if (method == kFast) {
+        l.ex_floats = RoundUp(geo.esize, 4);
+        l.p_floats = RoundUp(geo.psize, 4);
+        l.curp_floats = variant == FTK_VARIANT_LSSD ? l.p_floats : 0;
+        l.exv_bytes = RoundUp(geo.esize, 16);
+        l.curv_bytes = variant == FTK_VARIANT_LSSD ? RoundUp(geo.psize, 16) : 0;
+    }
+    l.total_bytes = 4 * (l.term_floats + l.ex_floats + 2 * l.p_floats + l.curp_floats) + l.exv_bytes + l.curv_bytes;
+    l.total_bytes = RoundUp(l.total_bytes, 16);
+    return l;
+}
+
+__device__ __forceinline__ Scratch CarveScratch(unsigned char *base, const SmemLayout &l) {
+    Scratch s;
+    float *f = reinterpret_cast<float *>(base);
+    s.term = f;
+    f += l.term_floats;
+    s.ex = f;
+    f += l.ex_floats;
+    s.dx = f;
+    f += l.p_floats;
+    s.dy = f;
+    f += l.p_floats;
+    s.curp = f;
+    f += l.curp_floats;
+    uint8_t *b = reinterpret_cast<uint8_t *>(f);
+    s.exv = b;
+    b += l.exv_bytes;
+    s.curv = b;
+    return s;
+}
+
+// Everything a group needs while tracking one feature.
+template <int G>
+struct Ctx {
+    Group<G> g;
+    Chain<G> ch;
+    Scratch s;
+    Geometry geo;
+    const ftk_klt_params *p;
+};
+
+// ---- shared pieces of the fast methods ---------------------------------------------------------------------------
+
+// optical_flow.cpp:49-102 ExtractExtendPatchInReferenceImage: (2h+3)^2 integer-aligned window at floor(ref) with ONE
+// set of bilinear weights; valid iff 0<=row<=rows-2 && 0<=col<=cols-2.  Returns the valid count (group-uniform).
+template <int G>
+__device__ int ExtractExRefPatch(Ctx<G> &c, const Img &ref, float ref_x, float ref_y) {
+    const float int_row = floorf(ref_y), int_col = floorf(ref_x);
+    const float dec_row = fsub(ref_y, int_row), dec_col = fsub(ref_x, int_col);
+    const float w_tl = fmul(fsub(1.0f, dec_row), fsub(1.0f, dec_col));
+    const float w_tr = fmul(fsub(1.0f, dec_row), dec_col);
+    const float w_bl = fmul(dec_row, fsub(1.0f, dec_col));
+    const float w_br = fmul(dec_row, dec_col);
+    const int min_row = static_cast<int>(int_row) - c.geo.er / 2;
+    const int min_col = static_cast<int>(int_col) - c.geo.ec / 2;
+    int valid = 0;
+    for (int base = 0; base < c.geo.esize; base += G) {
+        const int e = base + c.g.lane;
+        bool ok = false;
+        if (e < c.geo.esize) {
+            const int row = min_row + e / c.geo.ec, col = min_col + e % c.geo.ec;
+            ok = !(row < 0 || row > ref.rows - 2 || col < 0 || col > ref.cols - 2);
+            float v = 0.0f;
+            if (ok) {
+                v = fadd(fadd(fadd(fmul(w_tl, PxI(ref, row, col)), fmul(w_tr, PxI(ref, row, col + 1))), fmul(w_bl, PxI(ref, row + 1, col))),
+                         fmul(w_br, PxI(ref, row + 1, col + 1)));
+            }
+            c.s.ex[e] = v;
+            c.s.exv[e] = ok ? 1 : 0;
+        }
+        valid += c.g.count(ok);
+    }
+    c.g.sync();
+    return valid;
+}
+
+// Gradient of the extended patch at interior pixel k (basic_klt_fast.cpp:71-94 and the affine / lssd twins).
+template <int G>
+__device__ __forceinline__ bool ExGradient(const Ctx<G> &c, int k, float *dx, float *dy) {
+    const int row = k / c.geo.pc, col = k % c.geo.pc;
+    const int e = (row + 1) * c.geo.ec + col + 1;
+    const int l = e - 1, r = e + 1, u = e - c.geo.ec, d = e + c.geo.ec;
+    if (c.s.exv[l] && c.s.exv[r] && c.s.exv[u] && c.s.exv[d]) {
+        *dx = fsub(c.s.ex[r], c.s.ex[l]);
+        *dy = fsub(c.s.ex[d], c.s.ex[u]);
+        return true;
+    }
+    *dx = 0.0f;
+    *dy = 0.0f;
+    return false;
+}
+
+// Step bookkeeping shared by the fast trackers (basic_klt_fast.cpp:48-60, affine_klt_fast.cpp:55-67,
+// lssd_klt_fast.cpp:101-112).  Returns true when the iteration loop must stop.
+__device__ __forceinline__ bool FastStepCheck(const ftk_klt_params &p, float squared_step, float &last_squared_step, uint32_t &large_step_cnt,
+                                              uint8_t &status) {
+    if (squared_step < last_squared_step) {
+        last_squared_step = squared_step;
+        large_step_cnt = 0;
+    } else {
+        ++large_step_cnt;
+        if (large_step_cnt >= p.max_tolerance_large_step) return true;
+    }
+    if (squared_step < p.max_converge_step) {
+        status = FTK_STATUS_TRACKED;
+        return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool IsNan(float v) { return v != v; }
+
+// Sequential sum (row-major) of the interior of a rows x cols float array in shared memory: one chain.
+template <int G>
+__device__ float InteriorSum(Ctx<G> &c, const float *vals, int rows, int cols) {
+    const int ir = rows - 2, ic = cols - 2;
+    const int n = ir > 0 && ic > 0 ? ir * ic : 0;
+    c.ch.reset();
+    for (int base = 0; base < n; base += G) {
+        const int q = base + c.g.lane;
+        float v = 0.0f;
+        if (q < n) v = vals[(q / ic + 1) * cols + q % ic + 1];
+        c.ch.put(c.g.lane, 0, v);
+        c.ch.template fold<1>(c.g);
+    }
+    return c.g.get(c.ch.acc, 0);
+}
+
+// ===================================================================================================================
+// BASIC KLT
+// ===================================================================================================================
+struct BasicState {
+    float cur_x, cur_y;
+};
+
+// basic_klt.cpp:118-181 ConstructIncrementalFunction.  H = {h00, h01, h11}.
+template <int METHOD, int G>
+__device__ int BasicConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, float cur_x, float cur_y, float (&H)[3],
+                              float (&b)[2]) {
+    int valid = 0;
+    c.ch.reset();
+    for (int base = 0; base < c.geo.psize; base += G) {
+        const int k = base + c.g.lane;
+        float t[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+        bool ok = false;
+        if (k < c.geo.psize) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            const float row_j = fadd(static_cast<float>(drow), cur_y), col_j = fadd(static_cast<float>(dcol), cur_x);
+            const Img &gi = METHOD == kInverse ? ref : cur;
+            const float gr = METHOD == kInverse ? row_i : row_j, gc = METHOD == kInverse ? col_i : col_j;
+            float v0, v1, v2, v3, v4, v5;
+            ok = PxChecked(gi, gr, fsub(gc, 1.0f), &v0) && PxChecked(gi, gr, fadd(gc, 1.0f), &v1) && PxChecked(gi, fsub(gr, 1.0f), gc, &v2) &&
+                 PxChecked(gi, fadd(gr, 1.0f), gc, &v3) && PxChecked(ref, row_i, col_i, &v4) && PxChecked(cur, row_j, col_j, &v5);
+            if (ok) {
+                const float fx = fsub(v1, v0), fy = fsub(v3, v2), ft = fsub(v5, v4);
+                t[0] = fmul(fx, fx);
+                t[1] = fmul(fx, fy);
+                t[2] = fmul(fy, fy);
+                t[3] = -fmul(fx, ft);
+                t[4] = -fmul(fy, ft);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) c.ch.put(c.g.lane, q, t[q]);
+        valid += c.g.count(ok);
+        c.ch.template fold<5>(c.g);
+    }
+    H[0] = c.g.get(c.ch.acc, 0);
+    H[1] = c.g.get(c.ch.acc, 1);
+    H[2] = c.g.get(c.ch.acc, 2);
+    b[0] = c.g.get(c.ch.acc, 3);
+    b[1] = c.g.get(c.ch.acc, 4);
+    return valid;
+}
+
+// basic_klt.cpp:88-116 TrackOneFeature.
+template <int METHOD, int G>
+__device__ void BasicTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status) {
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        float H[3], b[2];
+        if (BasicConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s.cur_x, s.cur_y, H, b) == 0) break;
+        const float A[2][2] = {{H[0], H[1]}, {H[1], H[2]}};
+        float v[2];
+        LdltSolve<2>(A, b, v);
+        if (IsNan(v[0]) || IsNan(v[1])) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        s.cur_x = fadd(s.cur_x, v[0]);
+        s.cur_y = fadd(s.cur_y, v[1]);
+        if (IsOutside(cur, s.cur_x, s.cur_y)) {
+            status = FTK_STATUS_OUTSIDE;
+            break;
+        }
+        if (fadd(fmul(v[0], v[0]), fmul(v[1], v[1])) < c.p->max_converge_step) {
+            status = FTK_STATUS_TRACKED;
+            break;
+        }
+    }
+}
+
+// basic_klt_fast.cpp:7-62 TrackOneFeatureFast (+ :64-99 PrecomputeJacobianAndHessian, :101-195 ComputeBias).
+template <int G>
+__device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status) {
+    if (ExtractExRefPatch(c, ref, ref_x, ref_y) == 0) {
+        status = FTK_STATUS_OUTSIDE;
+        return;
+    }
+    // gradients + Hessian (3 chains)
+    c.ch.reset();
+    for (int base = 0; base < c.geo.psize; base += G) {
+        const int k = base + c.g.lane;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+        if (k < c.geo.psize) {
+            float dx, dy;
+            if (ExGradient(c, k, &dx, &dy)) {
+                t0 = fmul(dx, dx);
+                t1 = fmul(dx, dy);
+                t2 = fmul(dy, dy);
+            }
+            c.s.dx[k] = dx;
+            c.s.dy[k] = dy;
+        }
+        c.ch.put(c.g.lane, 0, t0);
+        c.ch.put(c.g.lane, 1, t1);
+        c.ch.put(c.g.lane, 2, t2);
+        c.ch.template fold<3>(c.g);
+    }
+    const float h00 = c.g.get(c.ch.acc, 0), h01 = c.g.get(c.ch.acc, 1), h11 = c.g.get(c.ch.acc, 2);
+    const float A[2][2] = {{h00, h01}, {h01, h11}};
+
+    status = FTK_STATUS_LARGE_RESIDUAL;
+    float last_squared_step = INFINITY;
+    uint32_t large_step_cnt = 0;
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        // ComputeBias: integer-aligned window at floor(cur), one weight set.
+        const float int_row = floorf(s.cur_y), int_col = floorf(s.cur_x);
+        const float dec_row = fsub(s.cur_y, int_row), dec_col = fsub(s.cur_x, int_col);
+        const float w_tl = fmul(fsub(1.0f, dec_row), fsub(1.0f, dec_col));
+        const float w_tr = fmul(fsub(1.0f, dec_row), dec_col);
+        const float w_bl = fmul(dec_row, fsub(1.0f, dec_col));
+        const float w_br = fmul(dec_row, dec_col);
+        const int min_row = static_cast<int>(int_row) - c.geo.pr / 2;
+        const int min_col = static_cast<int>(int_col) - c.geo.pc / 2;
+        int valid = 0;
+        c.ch.reset();
+        for (int base = 0; base < c.geo.psize; base += G) {
+            const int k = base + c.g.lane;
+            float t0 = 0.0f, t1 = 0.0f;
+            bool ok = false;
+            if (k < c.geo.psize) {
+                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
+                const int row = min_row + prow, col = min_col + pcol;
+                const int e = (prow + 1) * c.geo.ec + pcol + 1;
+                ok = !(row < 0 || row > cur.rows - 2 || col < 0 || col > cur.cols - 2) && c.s.exv[e];
+                if (ok) {
+                    const float cur_value = fadd(fadd(fadd(fmul(w_tl, PxI(cur, row, col)), fmul(w_tr, PxI(cur, row, col + 1))), fmul(w_bl, PxI(cur, row + 1, col))),
+                                                 fmul(w_br, PxI(cur, row + 1, col + 1)));
+                    const float dt = fsub(cur_value, c.s.ex[e]);
+                    t0 = -fmul(c.s.dx[k], dt);
+                    t1 = -fmul(c.s.dy[k], dt);
+                }
+            }
+            c.ch.put(c.g.lane, 0, t0);
+            c.ch.put(c.g.lane, 1, t1);
+            valid += c.g.count(ok);
+            c.ch.template fold<2>(c.g);
+        }
+        if (valid == 0) break;
+        const float b[2] = {c.g.get(c.ch.acc, 0), c.g.get(c.ch.acc, 1)};
+        float v[2];
+        LdltSolve<2>(A, b, v);
+        if (IsNan(v[0]) || IsNan(v[1])) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        s.cur_x = fadd(s.cur_x, v[0]);
+        s.cur_y = fadd(s.cur_y, v[1]);
+        const float squared_step = fadd(fmul(v[0], v[0]), fmul(v[1], v[1]));
+        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) break;
+    }
+}
+
+// ===================================================================================================================
+// AFFINE KLT.  affine = {a00, a01, a10, a11} row-major.
+// ===================================================================================================================
+struct AffineState {
+    float cur_x, cur_y;
+    float a[4];
+};
+
+// Upper-triangle index pairs of the 21 accumulated Hessian entries, in the reference's order.
+__device__ const unsigned char kAffRow[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
+__device__ const unsigned char kAffCol[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
+
+// The 21 Hessian terms of one pixel (affine_klt.cpp:157-187; entry (3,4) accumulates yy*dxdy -- reproduced).
+__device__ __forceinline__ void AffineHessianTerms(float x, float y, float dx, float dy, float (&t)[27]) {
+    const float xx = fmul(x, x), yy = fmul(y, y), dxdx = fmul(dx, dx), dydy = fmul(dy, dy), xy = fmul(x, y), dxdy = fmul(dx, dy);
+    t[0] = fmul(xx, dxdx);
+    t[1] = fmul(xx, dxdy);
+    t[2] = fmul(xy, dxdx);
+    t[3] = fmul(xy, dxdy);
+    t[4] = fmul(x, dxdx);
+    t[5] = fmul(x, dxdy);
+    t[6] = fmul(xx, dydy);
+    t[7] = fmul(xy, dxdy);
+    t[8] = fmul(xy, dydy);
+    t[9] = fmul(x, dxdy);
+    t[10] = fmul(x, dydy);
+    t[11] = fmul(yy, dxdx);
+    t[12] = fmul(yy, dxdy);
+    t[13] = fmul(y, dxdx);
+    t[14] = fmul(y, dxdy);
+    t[15] = fmul(yy, dydy);
+    t[16] = fmul(yy, dxdy);
+    t[17] = fmul(y, dydy);
+    t[18] = dxdx;
+    t[19] = dxdy;
+    t[20] = dydy;
+}
+
+// The 6 bias terms of one pixel, negated because the reference subtracts them (affine_klt.cpp:189-194).
+__device__ __forceinline__ void AffineBiasTerms(float x, float y, float dx, float dy, float dt, float *t) {
+    t[0] = -fmul(fmul(dt, x), dx);
+    t[1] = -fmul(fmul(dt, x), dy);
+    t[2] = -fmul(fmul(dt, y), dx);
+    t[3] = -fmul(fmul(dt, y), dy);
+    t[4] = -fmul(dt, dx);
+    t[5] = -fmul(dt, dy);
+}
+
+template <int G>
+__device__ __forceinline__ void AffineGatherHessian(const Ctx<G> &c, float (&H)[6][6]) {
+#pragma unroll
+    for (int q = 0; q < 21; ++q) {
+        const float v = c.g.get(c.ch.acc, q);
+        H[kAffRow[q]][kAffCol[q]] = v;
+        H[kAffCol[q]][kAffRow[q]] = v;
+    }
+}
+
+// affine_klt.cpp:131-273 ConstructIncrementalFunction: 21 Hessian + 6 bias chains.
+template <int METHOD, int G>
+__device__ int AffineConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const AffineState &s, float (&H)[6][6],
+                               float (&b)[6]) {
+    static_assert(G >= 27, "affine needs 27 chains");
+    int valid = 0;
+    c.ch.reset();
+    for (int base = 0; base < c.geo.psize; base += G) {
+        const int k = base + c.g.lane;
+        float t[27];
+#pragma unroll
+        for (int q = 0; q < 27; ++q) t[q] = 0.0f;
+        bool ok = false;
+        if (k < c.geo.psize) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            const float ax = fadd(fmul(s.a[0], static_cast<float>(dcol)), fmul(s.a[1], static_cast<float>(drow)));
+            const float ay = fadd(fmul(s.a[2], static_cast<float>(dcol)), fmul(s.a[3], static_cast<float>(drow)));
+            const float row_j = fadd(ay, s.cur_y), col_j = fadd(ax, s.cur_x);
+            const Img &gi = METHOD == kDirect ? cur : ref;
+            const float gr = METHOD == kDirect ? row_j : row_i, gc = METHOD == kDirect ? col_j : col_i;
+            float v0, v1, v2, v3, v4, v5;
+            ok = PxChecked(gi, gr, fsub(gc, 1.0f), &v0) && PxChecked(gi, gr, fadd(gc, 1.0f), &v1) && PxChecked(gi, fsub(gr, 1.0f), gc, &v2) &&
+                 PxChecked(gi, fadd(gr, 1.0f), gc, &v3) && PxChecked(ref, row_i, col_i, &v4) && PxChecked(cur, row_j, col_j, &v5);
+            if (ok) {
+                const float dx = fsub(v1, v0), dy = fsub(v3, v2), dt = fsub(v5, v4);
+                AffineHessianTerms(col_j, row_j, dx, dy, t);
+                AffineBiasTerms(col_j, row_j, dx, dy, dt, &t[21]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
+        valid += c.g.count(ok);
+        c.ch.template fold<27>(c.g);
+    }
+    AffineGatherHessian(c, H);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) b[q] = c.g.get(c.ch.acc, 21 + q);
+    return valid;
+}
+
+__device__ __forceinline__ void AffineApply(AffineState &s, const float (&z)[6], float v0, float v1) {
+    s.cur_x = fadd(s.cur_x, v0);
+    s.cur_y = fadd(s.cur_y, v1);
+    s.a[0] = fadd(s.a[0], z[0]);  // col(0) += z.head<2>()
+    s.a[2] = fadd(s.a[2], z[1]);
+    s.a[1] = fadd(s.a[1], z[2]);  // col(1) += z.segment<2>(2)
+    s.a[3] = fadd(s.a[3], z[3]);
+}
+
+// affine_klt.cpp:93-129 TrackOneFeature.
+template <int METHOD, int G>
+__device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        float H[6][6], b[6], z[6];
+        if (AffineConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b) == 0) break;
+        LdltSolve<6>(H, b, z);
+        const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
+        const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);
+        if (IsNan(v0) || IsNan(v1)) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        AffineApply(s, z, v0, v1);
+        if (IsOutside(cur, s.cur_x, s.cur_y)) {
+            status = FTK_STATUS_OUTSIDE;
+            break;
+        }
+        if (fadd(fmul(v0, v0), fmul(v1, v1)) < c.p->max_converge_step) {
+            status = FTK_STATUS_TRACKED;
+            break;
+        }
+    }
+}
+
+// affine_klt_fast.cpp:7-69 TrackOneFeatureFast (+ :71-138 PrecomputeJacobianAndHessian, :140-188 ComputeBias).
+template <int G>
+__device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
+    if (ExtractExRefPatch(c, ref, ref_x, ref_y) == 0) {
+        status = FTK_STATUS_OUTSIDE;
+        return;
+    }
+    // Hessian at the level-entry cur position: 21 chains of which (1,2), (1,4), (3,4) are overwritten by copies.
+    c.ch.reset();
+    for (int base = 0; base < c.geo.psize; base += G) {
+        const int k = base + c.g.lane;
+        float t[27];
+#pragma unroll
+        for (int q = 0; q < 21; ++q) t[q] = 0.0f;
+        if (k < c.geo.psize) {
+            float dx, dy;
+            if (ExGradient(c, k, &dx, &dy)) {
+                const float x = fadd(static_cast<float>(k % c.geo.pc - c.geo.hc), s.cur_x);
+                const float y = fadd(static_cast<float>(k / c.geo.pc - c.geo.hr), s.cur_y);
+                AffineHessianTerms(x, y, dx, dy, t);
+            }
+            c.s.dx[k] = dx;
+            c.s.dy[k] = dy;
+        }
+#pragma unroll
+        for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
+        c.ch.template fold<21>(c.g);
+    }
+    float H[6][6];
+    AffineGatherHessian(c, H);
+    H[1][2] = H[2][1] = H[0][3];
+    H[1][4] = H[4][1] = H[0][5];
+    H[3][4] = H[4][3] = H[2][3];
+
+    float last_squared_step = INFINITY;
+    uint32_t large_step_cnt = 0;
+    status = FTK_STATUS_LARGE_RESIDUAL;
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        int valid = 0;
+        c.ch.reset();
+        for (int base = 0; base < c.geo.psize; base += G) {
+            const int k = base + c.g.lane;
+            float t[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            bool ok = false;
+            if (k < c.geo.psize) {
+                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
+                const int drow = prow - c.geo.hr, dcol = pcol - c.geo.hc;
+                const float ax = fadd(fmul(s.a[0], static_cast<float>(dcol)), fmul(s.a[1], static_cast<float>(drow)));
+                const float ay = fadd(fmul(s.a[2], static_cast<float>(dcol)), fmul(s.a[3], static_cast<float>(drow)));
+                const float row_c = fadd(ay, s.cur_y), col_c = fadd(ax, s.cur_x);
+                const int e = (prow + 1) * c.geo.ec + pcol + 1;
+                float cur_value;
+                ok = PxChecked(cur, row_c, col_c, &cur_value) && c.s.exv[e];
+                if (ok) {
+                    const float dt = fsub(cur_value, c.s.ex[e]);
+                    AffineBiasTerms(col_c, row_c, c.s.dx[k], c.s.dy[k], dt, t);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) c.ch.put(c.g.lane, q, t[q]);
+            valid += c.g.count(ok);
+            c.ch.template fold<6>(c.g);
+        }
+        if (valid == 0) break;
+        float b[6], z[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) b[q] = c.g.get(c.ch.acc, q);
+        LdltSolve<6>(H, b, z);
+        bool any_nan = false;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) any_nan = any_nan || IsNan(z[q]);
+        if (any_nan) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
+        const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);
+        AffineApply(s, z, v0, v1);
+        const float squared_step = fadd(fmul(v0, v0), fmul(v1, v1));
+        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) break;
+    }
+}
+
+// ===================================================================================================================
+// LSSD KLT.  R = {r00, r01, r10, r11} row-major, t = {tx, ty}.
+// ===================================================================================================================
+struct LssdState {
+    float R[4];
+    float t[2];
+};
+
+// lssd_klt.cpp:113-117 / lssd_klt_fast.cpp:95-99: R *= [1 -th; th 1]; R /= ||R.col(0)||; t += v.tail<2>().
+__device__ __forceinline__ void LssdUpdate(LssdState &s, const float (&v)[3]) {
+    const float th = v[0];
+    const float n00 = fadd(fmul(s.R[0], 1.0f), fmul(s.R[1], th));
+    const float n01 = fadd(fmul(s.R[0], -th), fmul(s.R[1], 1.0f));
+    const float n10 = fadd(fmul(s.R[2], 1.0f), fmul(s.R[3], th));
+    const float n11 = fadd(fmul(s.R[2], -th), fmul(s.R[3], 1.0f));
+    const float norm = __fsqrt_rn(fadd(fmul(n00, n00), fmul(n10, n10)));
+    s.R[0] = fdiv(n00, norm);
+    s.R[1] = fdiv(n01, norm);
+    s.R[2] = fdiv(n10, norm);
+    s.R[3] = fdiv(n11, norm);
+    s.t[0] = fadd(s.t[0], v[1]);
+    s.t[1] = fadd(s.t[1], v[2]);
+}
+
+__device__ __forceinline__ void LssdWarp(const LssdState &s, float col_i, float row_i, float *col_j, float *row_j) {
+    *col_j = fadd(fadd(fmul(s.R[0], col_i), fmul(s.R[1], row_i)), s.t[0]);
+    *row_j = fadd(fadd(fmul(s.R[2], col_i), fmul(s.R[3], row_i)), s.t[1]);
+}
+
+// 6 unique Hessian products + 3 negated bias products of one pixel (H += J^T J, b -= J^T r).
+__device__ __forceinline__ void LssdTerms(const float (&J)[3], float residual, float (&t)[9]) {
+    t[0] = fmul(J[0], J[0]);
+    t[1] = fmul(J[0], J[1]);
+    t[2] = fmul(J[0], J[2]);
+    t[3] = fmul(J[1], J[1]);
+    t[4] = fmul(J[1], J[2]);
+    t[5] = fmul(J[2], J[2]);
+    t[6] = -fmul(J[0], residual);
+    t[7] = -fmul(J[1], residual);
+    t[8] = -fmul(J[2], residual);
+}
+
+template <int G>
+__device__ __forceinline__ void LssdGather(const Ctx<G> &c, float (&H)[3][3], float (&b)[3]) {
+    const float h00 = c.g.get(c.ch.acc, 0), h01 = c.g.get(c.ch.acc, 1), h02 = c.g.get(c.ch.acc, 2);
+    const float h11 = c.g.get(c.ch.acc, 3), h12 = c.g.get(c.ch.acc, 4), h22 = c.g.get(c.ch.acc, 5);
+    H[0][0] = h00, H[0][1] = h01, H[0][2] = h02;
+    H[1][0] = h01, H[1][1] = h11, H[1][2] = h12;
+    H[2][0] = h02, H[2][1] = h12, H[2][2] = h22;
+    b[0] = c.g.get(c.ch.acc, 6);
+    b[1] = c.g.get(c.ch.acc, 7);
+    b[2] = c.g.get(c.ch.acc, 8);
+}
+
+// lssd_klt.cpp:127-250 ConstructIncrementalFunction: pass 1 = validity + patch means (2 chains), pass 2 = 9 chains.
+template <int METHOD, int G>
+__device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const LssdState &s, float (&H)[3][3], float (&b)[3]) {
+    int valid = 0;
+    unsigned long long ok_bits = 0ull;  // bit q: this lane's pixel of chunk q is valid (psize <= 64 * G, checked on the host)
+    c.ch.reset();
+    int chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        float t0 = 0.0f, t1 = 0.0f;
+        bool ok = false;
+        if (k < c.geo.psize) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            float row_j, col_j;
+            LssdWarp(s, col_i, row_i, &col_j, &row_j);
+            const Img &gi = METHOD == kInverse ? ref : cur;
+            const float gr = METHOD == kInverse ? row_i : row_j, gc = METHOD == kInverse ? col_i : col_j;
+            float v4, v5;
+            ok = PxInside(gi, gr, fsub(gc, 1.0f)) && PxInside(gi, gr, fadd(gc, 1.0f)) && PxInside(gi, fsub(gr, 1.0f), gc) &&
+                 PxInside(gi, fadd(gr, 1.0f), gc) && PxChecked(ref, row_i, col_i, &v4) && PxChecked(cur, row_j, col_j, &v5);
+            if (ok) {
+                t0 = v4;
+                t1 = v5;
+                ok_bits |= 1ull << chunk;
+            }
+        }
+        c.ch.put(c.g.lane, 0, t0);
+        c.ch.put(c.g.lane, 1, t1);
+        valid += c.g.count(ok);
+        c.ch.template fold<2>(c.g);
+    }
+    const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
+    const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
+
+    c.ch.reset();
+    chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        float t[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
+        if ((ok_bits >> chunk) & 1ull) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            float row_j, col_j;
+            LssdWarp(s, col_i, row_i, &col_j, &row_j);
+            const Img &gi = METHOD == kInverse ? ref : cur;
+            const float gr = METHOD == kInverse ? row_i : row_j, gc = METHOD == kInverse ? col_i : col_j;
+            const float v0 = PxF(gi, gr, fsub(gc, 1.0f));
+            const float v1 = PxF(gi, gr, fadd(gc, 1.0f));
+            const float v2 = PxF(gi, fsub(gr, 1.0f), gc);
+            const float v3 = PxF(gi, fadd(gr, 1.0f), gc);
+            const float v4 = PxF(ref, row_i, col_i);
+            const float v5 = PxF(cur, row_j, col_j);
+            const float avg = METHOD == kInverse ? ref_avg : cur_avg;
+            const float jp0 = fdiv(fsub(v1, v0), avg), jp1 = fdiv(fsub(v3, v2), avg);
+            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
+            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
+            float J[3];
+            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
+            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
+            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
+            const float residual = fsub(fdiv(v5, cur_avg), fdiv(v4, ref_avg));
+            LssdTerms(J, residual, t);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
+        c.ch.template fold<9>(c.g);
+    }
+    LssdGather(c, H, b);
+    return valid;
+}
+
+// lssd_klt.cpp:96-125 TrackOneFeature.
+template <int METHOD, int G>
+__device__ void LssdTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, LssdState &s, uint8_t &status) {
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        float H[3][3], b[3], v[3];
+        if (LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b) == 0) break;
+        LdltSolve<3>(H, b, v);
+        if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        LssdUpdate(s, v);
+        if (fadd(fadd(fmul(v[0], v[0]), fmul(v[1], v[1])), fmul(v[2], v[2])) < c.p->max_converge_step) {
+            status = FTK_STATUS_TRACKED;
+            break;
+        }
+    }
+}
+
+// lssd_klt_fast.cpp:7-114 TrackOneFeatureFast (+ :116-143, :145-195, :197-229).
+template <int G>
+__device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, LssdState &s, uint8_t &status) {
+    const int valid_ref = ExtractExRefPatch(c, ref, ref_x, ref_y);
+    if (valid_ref == 0) {
+        status = FTK_STATUS_OUTSIDE;
+        return;
+    }
+    for (int k = c.g.lane; k < c.geo.psize; k += G) {
+        float dx, dy;
+        ExGradient(c, k, &dx, &dy);
+        c.s.dx[k] = dx;
+        c.s.dy[k] = dy;
+    }
+    c.g.sync();
+    if (c.p->consider_patch_luminance) {
+        // :27-46: interior sum of the extended patch divided by the WHOLE extended patch's valid count.
+        const float ref_avg = fdiv(InteriorSum(c, c.s.ex, c.geo.er, c.geo.ec), static_cast<float>(valid_ref));
+        for (int k = c.g.lane; k < c.geo.psize; k += G) {
+            c.s.dx[k] = fdiv(c.s.dx[k], ref_avg);
+            c.s.dy[k] = fdiv(c.s.dy[k], ref_avg);
+        }
+        for (int e = c.g.lane; e < c.geo.esize; e += G) c.s.ex[e] = fdiv(c.s.ex[e], ref_avg);
+        c.g.sync();
+    }
+
+    status = FTK_STATUS_LARGE_RESIDUAL;
+    float last_squared_step = INFINITY;
+    uint32_t large_step_cnt = 0;
+    for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        // ExtractPatchInCurrentImage: the "inside" test truncates and uses a +-patch_rows/cols margin.
+        float cx, cy;
+        LssdWarp(s, ref_x, ref_y, &cx, &cy);
+        const int min_row = static_cast<int>(cy) - c.geo.pr, min_col = static_cast<int>(cx) - c.geo.pc;
+        const int max_row = min_row + c.geo.pr * 2, max_col = min_col + c.geo.pc * 2;
+        const bool partly_outside = min_row < 0 || max_row > cur.rows - 2 || min_col < 0 || max_col > cur.cols - 2;
+        int valid_cur = 0;
+        for (int base = 0; base < c.geo.psize; base += G) {
+            const int k = base + c.g.lane;
+            bool ok = false;
+            if (k < c.geo.psize) {
+                const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+                const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+                float row_j, col_j;
+                LssdWarp(s, col_i, row_i, &col_j, &row_j);
+                float value = 0.0f;
+                if (partly_outside) {
+                    ok = PxChecked(cur, row_j, col_j, &value);
+                    if (!ok) value = 0.0f;
+                } else {
+                    value = PxF(cur, row_j, col_j);
+                    ok = true;
+                }
+                c.s.curp[k] = value;
+                c.s.curv[k] = ok ? 1 : 0;
+            }
+            valid_cur += c.g.count(ok);
+        }
+        c.g.sync();
+        if (valid_cur == 0) break;
+        if (c.p->consider_patch_luminance) {
+            // :65-78: interior sum of the cur patch divided by the whole patch's valid count.
+            const float cur_avg = fdiv(InteriorSum(c, c.s.curp, c.geo.pr, c.geo.pc), static_cast<float>(valid_cur));
+            for (int k = c.g.lane; k < c.geo.psize; k += G) c.s.curp[k] = fdiv(c.s.curp[k], cur_avg);
+            c.g.sync();
+        }
+
+        // ComputeHessianAndBias: 9 chains.
+        int valid = 0;
+        c.ch.reset();
+        for (int base = 0; base < c.geo.psize; base += G) {
+            const int k = base + c.g.lane;
+            float t[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) t[q] = 0.0f;
+            bool ok = false;
+            if (k < c.geo.psize) {
+                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
+                const float row_i = fadd(static_cast<float>(prow - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(pcol - c.geo.hc), ref_x);
+                const int e = (prow + 1) * c.geo.ec + pcol + 1;
+                ok = c.s.exv[e] && c.s.curv[k];
+                if (ok) {
+                    const float s0 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
+                    const float s1 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
+                    float J[3];
+                    J[0] = fadd(fmul(c.s.dx[k], s0), fmul(c.s.dy[k], s1));
+                    J[1] = c.s.dx[k];
+                    J[2] = c.s.dy[k];
+                    LssdTerms(J, fsub(c.s.curp[k], c.s.ex[e]), t);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
+            valid += c.g.count(ok);
+            c.ch.template fold<9>(c.g);
+        }
+        if (valid == 0) break;
+        float H[3][3], b[3], v[3];
+        LssdGather(c, H, b);
+        LdltSolve<3>(H, b, v);
+        if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
+            status = FTK_STATUS_NUMERIC_ERROR;
+            break;
+        }
+        LssdUpdate(s, v);
+        const float squared_step = fadd(fadd(fmul(v[0], v[0]), fmul(v[1], v[1])), fmul(v[2], v[2]));
+        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) break;
+    }
+}
+
+// ===================================================================================================================
+// Kernel: one group per feature; TrackMultipleLevel / TrackSingleLevel of the three subclasses.
+// ===================================================================================================================
+template <int VARIANT, int METHOD, int G>
+__global__ void __launch_bounds__(128) KltKernel(KltLaunch a, SmemLayout layout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Ctx<G> c;
+    const int groups_per_block = blockDim.x / G;
+    const int group_in_block = threadIdx.x / G;
+    const int f = blockIdx.x * groups_per_block + group_in_block;
+    if (f >= a.n_features) return;
+
+    c.s = CarveScratch(smem_raw + static_cast<size_t>(group_in_block) * layout.total_bytes, layout);
+    c.ch.term = c.s.term;
+    c.p = &a.p;
+    c.geo.hr = a.p.patch_row_half;
+    c.geo.hc = a.p.patch_col_half;
+    c.geo.pr = 2 * c.geo.hr + 1;
+    c.geo.pc = 2 * c.geo.hc + 1;
+    c.geo.psize = c.geo.pr * c.geo.pc;
+    c.geo.er = c.geo.pr + 2;
+    c.geo.ec = c.geo.pc + 2;
+    c.geo.esize = c.geo.er * c.geo.ec;
+
+    const int pair = a.feat_pair[f];
+    const int local = f - a.feat_offsets[pair];
+    const float2 ref_uv = a.ref_uv[f];
+    float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;  // optical_flow.cpp:12-14
+    uint8_t status = a.has_status ? a.status[f] : static_cast<uint8_t>(FTK_STATUS_NOT_TRACKED);  // :17-19
+
+    // basic_klt.cpp:9,12,15: only the first kMaxTrackPointsNumber features, never re-track failed ones.
+    const bool tracked = static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
+    if (tracked) {
+        const int ref_image = a.ref_image ? a.ref_image[pair] : pair;
+        const int cur_image = a.cur_image ? a.cur_image[pair] : pair;
+        const Img cur0 = LevelImage(a.cur, cur_image, 0);
+        if (a.single_level) {
+            const Img ref0 = LevelImage(a.ref, ref_image, 0);
+            if constexpr (VARIANT == FTK_VARIANT_BASIC) {
+                // basic_klt.cpp:59-86
+                BasicState s{cur_uv.x, cur_uv.y};
+                if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                else BasicTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                cur_uv = make_float2(s.cur_x, s.cur_y);
+            } else if constexpr (VARIANT == FTK_VARIANT_AFFINE) {
+                // affine_klt.cpp:61-91: starts from predict_affine_
+                {
+                    AffineState s{cur_uv.x, cur_uv.y, {a.p.predict[0], a.p.predict[1], a.p.predict[2], a.p.predict[3]}};
+                    if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                    else AffineTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                    cur_uv = make_float2(s.cur_x, s.cur_y);
+                }
+            } else {
+                // lssd_klt.cpp:63-94: the result is never written back to cur_pixel_uv (reference quirk, kept).
+                const float *P = a.p.predict;
+                LssdState s;
+                s.R[0] = P[0], s.R[1] = P[1], s.R[2] = P[2], s.R[3] = P[3];
+                s.t[0] = fsub(cur_uv.x, fadd(fmul(P[0], ref_uv.x), fmul(P[1], ref_uv.y)));
+                s.t[1] = fsub(cur_uv.y, fadd(fmul(P[2], ref_uv.x), fmul(P[3], ref_uv.y)));
+                if constexpr (METHOD == kFast) LssdTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                else LssdTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+            }
+        } else {
+            const int levels = a.ref.levels;
+            const float scale = static_cast<float>(1 << (levels - 1));
+            float sref_x = fdiv(ref_uv.x, scale), sref_y = fdiv(ref_uv.y, scale);
+            const float scur_x = fdiv(cur_uv.x, scale), scur_y = fdiv(cur_uv.y, scale);
+            if constexpr (VARIANT == FTK_VARIANT_BASIC) {
+                // basic_klt.cpp:7-57
+                BasicState s{scur_x, scur_y};
+                for (int l = levels - 1; l > -1; --l) {
+                    const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
+                    if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
+                    else BasicTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                    if (l == 0) break;
+                    sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
+                    s.cur_x = fmul(s.cur_x, 2.0f), s.cur_y = fmul(s.cur_y, 2.0f);
+                }
+                cur_uv = make_float2(s.cur_x, s.cur_y);
+            } else if constexpr (VARIANT == FTK_VARIANT_AFFINE) {
+                // affine_klt.cpp:6-59: affine starts at identity and is carried across levels un-scaled.
+                {
+                    AffineState s{scur_x, scur_y, {1.0f, 0.0f, 0.0f, 1.0f}};
+                    for (int l = levels - 1; l > -1; --l) {
+                        const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
+                        if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
+                        else AffineTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                        if (l == 0) break;
+                        sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
+                        s.cur_x = fmul(s.cur_x, 2.0f), s.cur_y = fmul(s.cur_y, 2.0f);
+                    }
+                    cur_uv = make_float2(s.cur_x, s.cur_y);
+                }
+            } else {
+                // lssd_klt.cpp:7-61
+                const float *P = a.p.predict;
+                LssdState s;
+                s.R[0] = P[0], s.R[1] = P[1], s.R[2] = P[2], s.R[3] = P[3];
+                s.t[0] = fsub(scur_x, fadd(fmul(P[0], sref_x), fmul(P[1], sref_y)));
+                s.t[1] = fsub(scur_y, fadd(fmul(P[2], sref_x), fmul(P[3], sref_y)));
+                for (int l = levels - 1; l > -1; --l) {
+                    const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
+                    if constexpr (METHOD == kFast) LssdTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
+                    else LssdTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                    if (l == 0) break;
+                    sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
+                    s.t[0] = fmul(s.t[0], 2.0f), s.t[1] = fmul(s.t[1], 2.0f);
+                }
+                cur_uv.x = fadd(fadd(fmul(s.R[0], ref_uv.x), fmul(s.R[1], ref_uv.y)), s.t[0]);
+                cur_uv.y = fadd(fadd(fmul(s.R[2], ref_uv.x), fmul(s.R[3], ref_uv.y)), s.t[1]);
+            }
+        }
+        // final "outside" test on level-0 size (basic_klt.cpp:49-53 and twins)
+        if (IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;
+    }
+    if (c.g.lane == 0) {
+        a.cur_uv[f] = cur_uv;
+        a.status[f] = status;
+    }
+}
+
+__global__ void FeaturePairKernel(const int *offsets, int n_pairs, int n_features, int *feat_pair) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_features) return;
+    int lo = 0, hi = n_pairs - 1;  // last pair whose offset <= f
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (offsets[mid] <= f) lo = mid;
+        else hi = mid - 1;
+    }
+    feat_pair[f] = lo;
+}
+
+template <int VARIANT, int METHOD, int G>
+int LaunchOne(ftk_context *ctx, const KltLaunch &a, const Geometry &geo) {
+    const SmemLayout layout = MakeLayout(VARIANT, METHOD, G, geo);
+    const int threads = 128;
+    const int groups_per_block = threads / G;
+    const size_t smem = static_cast<size_t>(layout.total_bytes) * groups_per_block;
+    if (smem > 227 * 1024) return SetError(ctx, FTK_ERR_UNSUPPORTED, "patch %dx%d needs %zu bytes of shared memory per block", geo.pr, geo.pc, smem);
+    auto kernel = KltKernel<VARIANT, METHOD, G>;
+    if (smem > 48 * 1024) FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int blocks = (a.n_features + groups_per_block - 1) / groups_per_block;
+    kernel<<<blocks, threads, smem, ctx->stream>>>(a, layout);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+template <int VARIANT, int G>
+int LaunchMethod(ftk_context *ctx, const KltLaunch &a, const Geometry &geo) {
+    switch (a.p.method) {
+        case kInverse: return LaunchOne<VARIANT, kInverse, G>(ctx, a, geo);
+        case kDirect: return LaunchOne<VARIANT, kDirect, G>(ctx, a, geo);
+        default: return LaunchOne<VARIANT, kFast, G>(ctx, a, geo);  // kFast, kSse, kNeon (basic_klt.cpp:31-34 `default:`)
+    }
+}
+
+}  // namespace
+
+int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int n_features, int *d_feat_pair) {
+    const int threads = 256;
+    FeaturePairKernel<<<(n_features + threads - 1) / threads, threads, 0, ctx->stream>>>(d_offsets, n_pairs, n_features, d_feat_pair);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
+    Geometry geo;
+    geo.hr = a.p.patch_row_half;
+    geo.hc = a.p.patch_col_half;
+    geo.pr = 2 * geo.hr + 1;
+    geo.pc = 2 * geo.hc + 1;
+    geo.psize = geo.pr * geo.pc;
+    geo.er = geo.pr + 2;
+    geo.ec = geo.pc + 2;
+    geo.esize = geo.er * geo.ec;
+    if (geo.hr < 0 || geo.hc < 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "negative patch half size");
+    switch (a.p.variant) {
+        case FTK_VARIANT_BASIC:
+            if (geo.psize <= 8 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 8>(ctx, a, geo);
+            if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 32>(ctx, a, geo);
+            break;
+        case FTK_VARIANT_AFFINE:
+            if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
+            break;
+        case FTK_VARIANT_LSSD:
+            if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_LSSD, 32>(ctx, a, geo);
+            break;
+        default:
+            return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", a.p.variant);
+    }
+    return SetError(ctx, FTK_ERR_UNSUPPORTED, "patch of %d pixels is larger than this build supports (2048)", geo.psize);
+}
+
+}  // namespace ftk

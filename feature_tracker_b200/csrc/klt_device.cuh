@@ -1,0 +1,214 @@
+// Device-side building blocks shared by the KLT kernels.
+//
+// Arithmetic contract (DESIGN.md "Bit-exact parity"): every floating-point operation of the reference is executed
+// as the same IEEE-754 binary32 round-to-nearest operation, without FMA contraction (explicit __fmul_rn / __fadd_rn
+// / __fsub_rn / __fdiv_rn / __fsqrt_rn; the file is also compiled with -fmad=false), and every reduction over patch
+// pixels is accumulated in the reference's row-major pixel order.  The parallelism comes from (a) evaluating the
+// per-pixel terms of a chunk of pixels on different lanes and (b) giving every accumulator ("chain") of the normal
+// equations its own lane, which then folds the chunk's terms sequentially.
+#ifndef FTK_KLT_DEVICE_CUH_
+#define FTK_KLT_DEVICE_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "ftk_internal.h"
+
+namespace ftk {
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// ---- images ---------------------------------------------------------------------------------------------------
+struct Img {
+    const uint8_t *p;
+    int rows, cols, pitch;
+};
+
+__device__ __forceinline__ Img LevelImage(const PyramidView &v, int image, int level) {
+    Img im;
+    im.p = v.base[level] + image * v.image_stride[level];
+    im.rows = v.rows[level];
+    im.cols = v.cols[level];
+    im.pitch = v.pitch[level];
+    return im;
+}
+
+__device__ __forceinline__ float PxI(const Img &im, int row, int col) { return static_cast<float>(__ldg(im.p + row * im.pitch + col)); }
+
+// GrayImage::GetPixelValueNoCheck(float,float) (oracle/shim/datatype_image.h): base pixel by truncation, fractions by
+// floor, ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11.
+__device__ __forceinline__ float PxF(const Img &im, float row, float col) {
+    const uint8_t *v = im.p + static_cast<int>(row) * im.pitch + static_cast<int>(col);
+    const float sr = fsub(row, floorf(row));
+    const float sc = fsub(col, floorf(col));
+    const float ir = fsub(1.0f, sr);
+    const float ic = fsub(1.0f, sc);
+    const float p00 = static_cast<float>(__ldg(v));
+    const float p01 = static_cast<float>(__ldg(v + 1));
+    const float p10 = static_cast<float>(__ldg(v + im.pitch));
+    const float p11 = static_cast<float>(__ldg(v + im.pitch + 1));
+    return fadd(fadd(fadd(fmul(fmul(ic, ir), p00), fmul(fmul(sc, ir), p01)), fmul(fmul(ic, sr), p10)), fmul(fmul(sc, sr), p11));
+}
+
+// GrayImage::GetPixelValue(float,float,float*): fails iff outside [0, cols-1] x [0, rows-1].
+__device__ __forceinline__ bool PxInside(const Img &im, float row, float col) {
+    return !(col < 0.0f || row < 0.0f || col > static_cast<float>(im.cols - 1) || row > static_cast<float>(im.rows - 1));
+}
+__device__ __forceinline__ bool PxChecked(const Img &im, float row, float col, float *out) {
+    if (!PxInside(im, row, col)) return false;
+    *out = PxF(im, row, col);
+    return true;
+}
+
+__device__ __forceinline__ bool IsOutside(const Img &im, float x, float y) {
+    return x < 0.0f || x > static_cast<float>(im.cols - 1) || y < 0.0f || y > static_cast<float>(im.rows - 1);
+}
+
+// ---- lane groups: G lanes of a warp cooperate on one feature ---------------------------------------------------
+template <int G>
+struct Group {
+    int lane;       // 0..G-1
+    int base;       // first lane of the group inside the warp
+    unsigned mask;  // member mask of the group
+    __device__ __forceinline__ Group() {
+        const int l = threadIdx.x & 31;
+        lane = l % G;
+        base = l - lane;
+        mask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << base);
+    }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ int count(bool pred) const { return __popc(__ballot_sync(mask, pred)); }
+    __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(mask, v, base + src); }
+};
+
+// ---- chains: K accumulators, one per lane, folded sequentially over the G terms of a chunk -----------------------
+// Shared layout: term[k * (G + 4) + lane]; the +4 float padding keeps the float4 reads of lanes 0..K-1 on distinct
+// banks.
+template <int G>
+struct Chain {
+    static constexpr int kStride = G + 4;
+    float *term;
+    float acc;
+    __device__ __forceinline__ void reset() { acc = 0.0f; }
+    __device__ __forceinline__ void put(int lane, int k, float v) const { term[k * kStride + lane] = v; }
+    // All lanes call; lanes >= K idle during the fold.
+    template <int K>
+    __device__ __forceinline__ void fold(const Group<G> &g) {
+        g.sync();
+        if (g.lane < K) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(term + g.lane * kStride);
+#pragma unroll
+            for (int q = 0; q < G / 4; ++q) {
+                const float4 v = t4[q];
+                acc = fadd(acc, v.x);
+                acc = fadd(acc, v.y);
+                acc = fadd(acc, v.z);
+                acc = fadd(acc, v.w);
+            }
+        }
+        g.sync();
+    }
+};
+
+// ---- LDLT (Eigen LDLT<Lower> restated; oracle/shim/basic_type.h) ----------------------------------
+// Executed redundantly by every lane of a group on identical inputs (uniform control flow, no broadcast needed).
+template <int N>
+__device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&b)[N], float (&x)[N]) {
+    float a[N][N];
+    int tr[N];
+    float temp[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) a[i][j] = A[i][j];
+
+    bool zero_diag = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (zero_diag) break;
+        int p = k;
+        float best = fabsf(a[k][k]);
+        for (int i = k + 1; i < N; ++i) {
+            const float v = fabsf(a[i][i]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        tr[k] = p;
+        if (p != k) {
+            for (int j = 0; j < k; ++j) {
+                const float t = a[k][j];
+                a[k][j] = a[p][j];
+                a[p][j] = t;
+            }
+            for (int i = p + 1; i < N; ++i) {
+                const float t = a[i][k];
+                a[i][k] = a[i][p];
+                a[i][p] = t;
+            }
+            {
+                const float t = a[k][k];
+                a[k][k] = a[p][p];
+                a[p][p] = t;
+            }
+            for (int i = k + 1; i < p; ++i) {
+                const float t = a[i][k];
+                a[i][k] = a[p][i];
+                a[p][i] = t;
+            }
+        }
+        if (k > 0) {
+            for (int j = 0; j < k; ++j) temp[j] = fmul(a[j][j], a[k][j]);
+            float s = fmul(a[k][0], temp[0]);
+            for (int j = 1; j < k; ++j) s = fadd(s, fmul(a[k][j], temp[j]));
+            a[k][k] = fsub(a[k][k], s);
+            for (int i = k + 1; i < N; ++i) {
+                float t = fmul(a[i][0], temp[0]);
+                for (int j = 1; j < k; ++j) t = fadd(t, fmul(a[i][j], temp[j]));
+                a[i][k] = fsub(a[i][k], t);
+            }
+        }
+        const float akk = a[k][k];
+        const bool pivot_ok = fabsf(akk) > 0.0f;
+        if (k == 0 && !pivot_ok) {
+            for (int j = 0; j < N; ++j) tr[j] = j;
+            zero_diag = true;
+        } else if (pivot_ok) {
+            for (int i = k + 1; i < N; ++i) a[i][k] = fdiv(a[i][k], akk);
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = b[i];
+    for (int k = 0; k < N; ++k) {
+        const float t = x[k];
+        x[k] = x[tr[k]];
+        x[tr[k]] = t;
+    }
+    for (int i = 1; i < N; ++i) {
+        float s = fmul(a[i][0], x[0]);
+        for (int j = 1; j < i; ++j) s = fadd(s, fmul(a[i][j], x[j]));
+        x[i] = fsub(x[i], s);
+    }
+    for (int i = 0; i < N; ++i) x[i] = (fabsf(a[i][i]) > FLT_MIN) ? fdiv(x[i], a[i][i]) : 0.0f;
+    for (int i = N - 2; i >= 0; --i) {
+        float s = fmul(a[i + 1][i], x[i + 1]);
+        for (int j = i + 2; j < N; ++j) s = fadd(s, fmul(a[j][i], x[j]));
+        x[i] = fsub(x[i], s);
+    }
+    for (int k = N - 1; k >= 0; --k) {
+        const float t = x[k];
+        x[k] = x[tr[k]];
+        x[tr[k]] = t;
+    }
+}
+
+}  // namespace ftk
+
+#endif

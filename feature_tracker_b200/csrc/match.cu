@@ -1,0 +1,565 @@
+// K5-K7 (first generation): descriptor matching on sm_100a.
+//
+// Replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch (src/descriptor_matcher/descriptor_matcher.h:55-79,
+// 90-124) together with the user-supplied ComputeDistance bodies the reference's demos use:
+//   BRIEF   : number of differing elements      (test/test_descriptor_matcher_brief.cpp:33-45)
+//   float   : 0.5 - dot / |a| / |b| * 0.5       (test/test_descriptor_matcher_superpoint.cpp:32-34, ..._disk.cpp:32-34)
+//
+// Result contract (bit-exact): idx[i] = the LOWEST j minimising d(i, j) among the admissible j, provided that
+// minimum is < max_dist; otherwise idx[i] keeps its previous content.  "Admissible" is every j for ForceMatch and
+// the window-gated j for NearbyMatch.  The reference's `break` on d == 0 (descriptor_matcher.h:119) is honoured
+// exactly: candidates after the first admissible j with d == 0 are ignored (this only matters when a float
+// distance rounds below zero).
+//
+// Kernels:
+//   HammingForceKernel : XOR + POPC, ref descriptor in registers, cur descriptors streamed through shared memory as
+//                        warp-wide broadcasts; packed (distance << 20 | j) keys make "lowest j wins ties" a plain
+//                        integer min; the cur dimension is split across CTAs and merged with atomicMin.
+//   Nearby*            : cur features are bucketed into a uniform grid (count -> scan -> fill); one warp per ref
+//                        descriptor walks the cells overlapping its window, applies the reference's exact fp32 gate
+//                        and reduces (distance, j) lexicographically.
+//   CosineForceKernel  : exact fp32 distances with the reference's sequential k = 0..dim-1 summation order
+//                        (one chain per (ref, cur) pair, 4 independent pairs per thread for ILP).
+#include <cfloat>
+
+#include "ftk_internal.h"
+
+namespace ftk {
+
+namespace {
+
+constexpr unsigned kNoKey32 = 0xFFFFFFFFu;
+constexpr unsigned long long kNoKey64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr int kJBits = 20;  // packed 32-bit keys: j < 2^20, distance < 2^12
+
+__global__ void FillU32Kernel(unsigned *p, int n, unsigned v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void FillU64Kernel(unsigned long long *p, int n, unsigned long long v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Hamming force matching
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kHamThreads = 256;
+constexpr int kHamTile = 256;  // cur descriptors per shared-memory tile
+
+template <int W>
+__global__ void __launch_bounds__(kHamThreads) HammingForceKernel(const uint32_t *__restrict__ ref, int n_ref, const uint32_t *__restrict__ cur, int n_cur,
+                                                                 int cur_per_split, unsigned *__restrict__ best) {
+    __shared__ __align__(16) uint32_t tile[kHamTile * W];
+    const int i = blockIdx.x * kHamThreads + threadIdx.x;
+    const int j_begin = blockIdx.y * cur_per_split;
+    const int j_end = min(n_cur, j_begin + cur_per_split);
+
+    uint32_t r[W];
+    if (i < n_ref) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) r[w] = __ldg(ref + static_cast<size_t>(i) * W + w);
+    } else {
+#pragma unroll
+        for (int w = 0; w < W; ++w) r[w] = 0u;
+    }
+
+    unsigned key = kNoKey32;
+    for (int j0 = j_begin; j0 < j_end; j0 += kHamTile) {
+        const int n_tile = min(kHamTile, j_end - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n_tile * W; t += kHamThreads) tile[t] = __ldg(cur + static_cast<size_t>(j0) * W + t);
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < n_tile; ++t) {
+            unsigned d = 0;
+            if constexpr (W % 4 == 0) {
+#pragma unroll
+                for (int w = 0; w < W; w += 4) {
+                    const uint4 c = *reinterpret_cast<const uint4 *>(&tile[t * W + w]);
+                    d += __popc(r[w] ^ c.x) + __popc(r[w + 1] ^ c.y) + __popc(r[w + 2] ^ c.z) + __popc(r[w + 3] ^ c.w);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; ++w) d += __popc(r[w] ^ tile[t * W + w]);
+            }
+            key = min(key, (d << kJBits) | static_cast<unsigned>(j0 + t));
+        }
+    }
+    if (i < n_ref && key != kNoKey32) atomicMin(&best[i], key);
+}
+
+// Any descriptor length: ref words re-read from global (L1), 64-bit keys.
+__global__ void __launch_bounds__(kHamThreads) HammingForceGenericKernel(const uint32_t *__restrict__ ref, int n_ref, const uint32_t *__restrict__ cur,
+                                                                        int n_cur, int words, int cur_per_split, unsigned long long *__restrict__ best) {
+    const int i = blockIdx.x * kHamThreads + threadIdx.x;
+    if (i >= n_ref) return;
+    const int j_begin = blockIdx.y * cur_per_split;
+    const int j_end = min(n_cur, j_begin + cur_per_split);
+    unsigned long long key = kNoKey64;
+    for (int j = j_begin; j < j_end; ++j) {
+        unsigned d = 0;
+        for (int w = 0; w < words; ++w) d += __popc(__ldg(ref + static_cast<size_t>(i) * words + w) ^ __ldg(cur + static_cast<size_t>(j) * words + w));
+        const unsigned long long k = (static_cast<unsigned long long>(d) << 32) | static_cast<unsigned>(j);
+        key = k < key ? k : key;
+    }
+    if (key != kNoKey64) atomicMin(&best[i], key);
+}
+
+__global__ void HammingFinalize32Kernel(const unsigned *best, int n_ref, float max_dist, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const unsigned key = best[i];
+    if (key == kNoKey32) return;
+    const float d = static_cast<float>(key >> kJBits);
+    if (d < max_dist) idx[i] = static_cast<int>(key & ((1u << kJBits) - 1u));
+}
+
+__global__ void HammingFinalize64Kernel(const unsigned long long *best, int n_ref, float max_dist, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const unsigned long long key = best[i];
+    if (key == kNoKey64) return;
+    const float d = static_cast<float>(static_cast<unsigned>(key >> 32));
+    if (d < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Uniform grid over the cur feature positions (nearby matching)
+// ---------------------------------------------------------------------------------------------------------------
+struct GridDesc {
+    float x0, y0, inv_cw, inv_ch;
+    int gw, gh;
+};
+
+// bounds[0..3] = min x, min y, max x, max y over finite positions, as order-preserving integers.
+__device__ __forceinline__ int FloatToOrdered(float f) {
+    const int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7FFFFFFF;
+}
+__host__ __device__ inline float OrderedToFloat(int o) {
+    const int b = o >= 0 ? o : o ^ 0x7FFFFFFF;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, sizeof(f));
+    return f;
+#endif
+}
+
+__device__ __forceinline__ bool Finite2(float2 p) { return isfinite(p.x) && isfinite(p.y); }
+
+__global__ void BoundsKernel(const float2 *pos, int n, int *bounds) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float2 p = pos[j];
+    if (!Finite2(p)) return;
+    atomicMin(&bounds[0], FloatToOrdered(p.x));
+    atomicMin(&bounds[1], FloatToOrdered(p.y));
+    atomicMax(&bounds[2], FloatToOrdered(p.x));
+    atomicMax(&bounds[3], FloatToOrdered(p.y));
+}
+
+__device__ __forceinline__ int CellCoord(float v, float v0, float inv, int n) {
+    const float c = floorf((v - v0) * inv);
+    return c < 0.0f ? 0 : (c > static_cast<float>(n - 1) ? n - 1 : static_cast<int>(c));
+}
+
+// counts[cell] for finite positions; non-finite positions go to the "always a candidate" list.
+__global__ void CellCountKernel(const float2 *pos, int n, GridDesc g, int *counts, int *special, int *n_special) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float2 p = pos[j];
+    if (!Finite2(p)) {
+        special[atomicAdd(n_special, 1)] = j;
+        return;
+    }
+    atomicAdd(&counts[CellCoord(p.y, g.y0, g.inv_ch, g.gh) * g.gw + CellCoord(p.x, g.x0, g.inv_cw, g.gw)], 1);
+}
+
+// Exclusive scan of counts[0..n) into starts[0..n]; single block.
+__global__ void __launch_bounds__(1024) ScanKernel(const int *counts, int n, int *starts, int *cursor) {
+    __shared__ int partial[1024];
+    const int per = (n + 1023) / 1024;
+    const int begin = threadIdx.x * per, end = min(n, begin + per);
+    int sum = 0;
+    for (int i = begin; i < end; ++i) sum += counts[i];
+    partial[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int t = 0; t < 1024; ++t) {
+            const int v = partial[t];
+            partial[t] = acc;
+            acc += v;
+        }
+        starts[n] = acc;
+    }
+    __syncthreads();
+    int acc = partial[threadIdx.x];
+    for (int i = begin; i < end; ++i) {
+        starts[i] = acc;
+        cursor[i] = acc;
+        acc += counts[i];
+    }
+}
+
+__global__ void CellFillKernel(const float2 *pos, int n, GridDesc g, int *cursor, int *sorted) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const float2 p = pos[j];
+    if (!Finite2(p)) return;
+    const int cell = CellCoord(p.y, g.y0, g.inv_ch, g.gh) * g.gw + CellCoord(p.x, g.x0, g.inv_cw, g.gw);
+    sorted[atomicAdd(&cursor[cell], 1)] = j;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Distances for the nearby kernels
+// ---------------------------------------------------------------------------------------------------------------
+// Order-preserving key for a non-NaN float distance (with -0 canonicalised to +0).
+__device__ __forceinline__ unsigned FloatKey(float d) {
+    d = d + 0.0f;
+    const unsigned b = __float_as_uint(d);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float KeyFloat(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
+struct HammingDist {
+    const uint32_t *ref, *cur;
+    int words;
+    // returns false when the distance is not comparable (never for Hamming)
+    __device__ __forceinline__ bool operator()(int i, int j, float *d) const {
+        unsigned s = 0;
+        for (int w = 0; w < words; ++w) s += __popc(__ldg(ref + static_cast<size_t>(i) * words + w) ^ __ldg(cur + static_cast<size_t>(j) * words + w));
+        *d = words > 0 ? static_cast<float>(s) : 2147483647.0f;  // brief.cpp:34-36: empty descriptors -> kMaxInt32
+        return true;
+    }
+};
+
+// Sequential dot product, k ascending, no FMA: bit-identical to the reference's scalar evaluation order.
+__device__ __forceinline__ float SeqDot(const float *a, const float *b, int n) {
+    float s = __fmul_rn(__ldg(a), __ldg(b));
+    for (int k = 1; k < n; ++k) s = __fadd_rn(s, __fmul_rn(__ldg(a + k), __ldg(b + k)));
+    return s;
+}
+
+struct CosineDist {
+    const float *ref, *cur;
+    const float *ref_norm, *cur_norm;
+    int dim;
+    __device__ __forceinline__ bool operator()(int i, int j, float *d) const {
+        const float dot = SeqDot(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim);
+        const float v = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(dot, ref_norm[i]), cur_norm[j]), 0.5f));
+        *d = v;
+        return v == v;  // NaN never compares below anything in the reference
+    }
+};
+
+__global__ void NormKernel(const float *desc, int n, int dim, float *norm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *a = desc + static_cast<size_t>(i) * dim;
+    norm[i] = __fsqrt_rn(SeqDot(a, a, dim));
+}
+
+__device__ __forceinline__ unsigned long long WarpMin64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        v = other < v ? other : v;
+    }
+    return v;
+}
+__device__ __forceinline__ unsigned WarpMin32(unsigned v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+
+// One warp per ref descriptor.  `limit_j`: candidates with j > limit_j are ignored (used for the d == 0 break).
+template <typename Dist>
+__device__ void NearbyScan(const Dist &dist, int i, float2 pred, const float2 *pos, int n_cur, const GridDesc &g, const int *starts, const int *sorted,
+                           const int *special, int n_special, float max_dcol, float max_drow, unsigned limit_j, unsigned long long *best_out,
+                           unsigned *first_zero_out) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long best = kNoKey64;
+    unsigned first_zero = 0xFFFFFFFFu;
+
+    auto consider = [&](int j) {
+        if (static_cast<unsigned>(j) > limit_j) return;
+        const float2 q = pos[j];
+        // descriptor_matcher.h:108-111 (exact fp32 gate)
+        if (fabsf(__fsub_rn(pred.x, q.x)) > max_dcol || fabsf(__fsub_rn(pred.y, q.y)) > max_drow) return;
+        float d;
+        if (!dist(i, j, &d)) return;
+        const unsigned long long key = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+        best = key < best ? key : best;
+        if (d == 0.0f) first_zero = min(first_zero, static_cast<unsigned>(j));
+    };
+
+    if (Finite2(pred)) {
+        // Conservative cell range: one pixel (plus relative slack) wider than the window, cell mapping is monotonic.
+        const float mx = max_dcol + 1.0f + fabsf(pred.x) * 1e-6f, my = max_drow + 1.0f + fabsf(pred.y) * 1e-6f;
+        const int cx0 = CellCoord(pred.x - mx, g.x0, g.inv_cw, g.gw), cx1 = CellCoord(pred.x + mx, g.x0, g.inv_cw, g.gw);
+        const int cy0 = CellCoord(pred.y - my, g.y0, g.inv_ch, g.gh), cy1 = CellCoord(pred.y + my, g.y0, g.inv_ch, g.gh);
+        for (int cy = cy0; cy <= cy1; ++cy) {
+            const int begin = starts[cy * g.gw + cx0], end = starts[cy * g.gw + cx1 + 1];
+            for (int t = begin + lane; t < end; t += 32) consider(sorted[t]);
+        }
+        for (int t = lane; t < n_special; t += 32) consider(special[t]);
+    } else {
+        // A non-finite prediction makes every comparison of the gate false: all cur features are candidates.
+        for (int j = lane; j < n_cur; j += 32) consider(j);
+    }
+    *best_out = WarpMin64(best);
+    *first_zero_out = WarpMin32(first_zero);
+}
+
+template <typename Dist>
+__global__ void __launch_bounds__(128) NearbyKernel(Dist dist, int n_ref, const float2 *pred, const float2 *pos, int n_cur, GridDesc g, const int *starts,
+                                                    const int *sorted, const int *special, const int *n_special_ptr, float max_dcol, float max_drow,
+                                                    float max_dist, int *idx) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n_ref) return;
+    const int n_special = *n_special_ptr;
+    unsigned long long best;
+    unsigned first_zero;
+    NearbyScan(dist, i, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, 0xFFFFFFFFu, &best, &first_zero);
+    if (first_zero != 0xFFFFFFFFu && static_cast<unsigned>(best & 0xFFFFFFFFull) > first_zero) {
+        // A candidate after the reference's d == 0 break won: redo the scan over j <= first_zero only.
+        unsigned dummy;
+        NearbyScan(dist, i, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, first_zero, &best, &dummy);
+    }
+    if ((threadIdx.x & 31) == 0 && best != kNoKey64) {
+        const float d = KeyFloat(static_cast<unsigned>(best >> 32));
+        if (d < max_dist) idx[i] = static_cast<int>(best & 0xFFFFFFFFull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact fp32 cosine force matching
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCosThreads = 128;  // ref rows per CTA (one per thread)
+constexpr int kCosCurTile = 32;   // cur descriptors per shared tile
+constexpr int kCosK = 32;         // k-slice staged per step
+
+// best[i] packs (FloatKey(distance) << 32 | j); first_zero[i] = lowest j with distance == 0.
+__global__ void __launch_bounds__(kCosThreads) CosineForceKernel(const float *__restrict__ ref, int n_ref, const float *__restrict__ cur, int n_cur, int dim,
+                                                                const float *__restrict__ ref_norm, const float *__restrict__ cur_norm,
+                                                                int cur_per_split, unsigned long long *__restrict__ best) {
+    // ref slice transposed [k][thread] (conflict-free), cur slice [k][j] (broadcast float4 reads)
+    __shared__ float s_ref[kCosK][kCosThreads + 1];
+    __shared__ __align__(16) float s_cur[kCosK][kCosCurTile];
+    const int i0 = blockIdx.x * kCosThreads;
+    const int i = i0 + threadIdx.x;
+    const int j_begin = blockIdx.y * cur_per_split;
+    const int j_end = min(n_cur, j_begin + cur_per_split);
+    const float rn = i < n_ref ? ref_norm[i] : 1.0f;
+    unsigned long long key = kNoKey64;
+
+    for (int j0 = j_begin; j0 < j_end; j0 += kCosCurTile) {
+        float acc[kCosCurTile];
+#pragma unroll
+        for (int t = 0; t < kCosCurTile; ++t) acc[t] = 0.0f;
+        for (int k0 = 0; k0 < dim; k0 += kCosK) {
+            __syncthreads();
+            // stage ref[i0 .. i0+127][k0 .. k0+31]: consecutive threads read consecutive k of one row
+            for (int t = threadIdx.x; t < kCosThreads * kCosK; t += kCosThreads) {
+                const int r = t / kCosK, k = t % kCosK;
+                s_ref[k][r] = (i0 + r < n_ref && k0 + k < dim) ? __ldg(ref + static_cast<size_t>(i0 + r) * dim + k0 + k) : 0.0f;
+            }
+            for (int t = threadIdx.x; t < kCosCurTile * kCosK; t += kCosThreads) {
+                const int c = t / kCosK, k = t % kCosK;
+                s_cur[k][c] = (j0 + c < j_end && k0 + k < dim) ? __ldg(cur + static_cast<size_t>(j0 + c) * dim + k0 + k) : 0.0f;
+            }
+            __syncthreads();
+            const int kn = min(kCosK, dim - k0);
+            for (int k = 0; k < kn; ++k) {
+                const float a = s_ref[k][threadIdx.x];
+#pragma unroll
+                for (int t = 0; t < kCosCurTile; t += 4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(&s_cur[k][t]);
+                    if (k0 + k == 0) {  // the reference's sum starts from the first product, not from 0 + product
+                        acc[t] = __fmul_rn(a, b.x), acc[t + 1] = __fmul_rn(a, b.y), acc[t + 2] = __fmul_rn(a, b.z), acc[t + 3] = __fmul_rn(a, b.w);
+                    } else {
+                        acc[t] = __fadd_rn(acc[t], __fmul_rn(a, b.x));
+                        acc[t + 1] = __fadd_rn(acc[t + 1], __fmul_rn(a, b.y));
+                        acc[t + 2] = __fadd_rn(acc[t + 2], __fmul_rn(a, b.z));
+                        acc[t + 3] = __fadd_rn(acc[t + 3], __fmul_rn(a, b.w));
+                    }
+                }
+            }
+        }
+        const int n_tile = min(kCosCurTile, j_end - j0);
+#pragma unroll
+        for (int t = 0; t < kCosCurTile; ++t) {
+            if (t < n_tile) {
+                const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(acc[t], rn), cur_norm[j0 + t]), 0.5f));
+                if (d == d) {
+                    const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j0 + t);
+                    key = k64 < key ? k64 : key;
+                }
+            }
+        }
+    }
+    if (i < n_ref && key != kNoKey64) atomicMin(&best[i], key);
+}
+
+__global__ void CosineFinalizeKernel(const unsigned long long *best, int n_ref, float max_dist, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const unsigned long long key = best[i];
+    if (key == kNoKey64) return;
+    const float d = KeyFloat(static_cast<unsigned>(key >> 32));
+    if (d < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+}
+
+int Blocks(int n, int threads) { return (n + threads - 1) / threads; }
+
+// Number of cur splits so that the grid fills the GPU a few times over without making the tiles tiny.
+int CurSplits(const ftk_context *ctx, int ref_blocks, int n_cur, int tile) {
+    const int target = ctx->sm_count * 8;
+    int splits = (target + ref_blocks - 1) / ref_blocks;
+    const int max_splits = (n_cur + tile - 1) / tile;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    return splits;
+}
+
+template <typename Dist>
+int RunNearby(ftk_context *ctx, const Dist &dist, int n_ref, int n_cur, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol,
+              float max_dist, int *d_idx) {
+    cudaStream_t st = ctx->stream;
+    // 1. bounding box of the finite cur positions
+    int *d_bounds = nullptr;
+    if (int rc = EnsureDevice(ctx, ctx->d_work0, 64)) return rc;
+    d_bounds = static_cast<int *>(ctx->d_work0.ptr);
+    const int init[4] = {0x7FFFFFFF, 0x7FFFFFFF, static_cast<int>(0x80000000), static_cast<int>(0x80000000)};
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    BoundsKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, d_bounds);
+    ++ctx->launches;
+    int h_bounds[4];
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+
+    GridDesc g{};
+    g.gw = g.gh = 1;
+    g.x0 = g.y0 = 0.0f;
+    g.inv_cw = g.inv_ch = 0.0f;
+    if (h_bounds[0] != 0x7FFFFFFF) {
+        const float x0 = OrderedToFloat(h_bounds[0]), y0 = OrderedToFloat(h_bounds[1]);
+        const float x1 = OrderedToFloat(h_bounds[2]), y1 = OrderedToFloat(h_bounds[3]);
+        float cw = static_cast<float>(max_dcol > 1 ? max_dcol : 1), ch = static_cast<float>(max_drow > 1 ? max_drow : 1);
+        const float span_x = x1 - x0, span_y = y1 - y0;
+        if (span_x / cw > 255.0f) cw = span_x / 255.0f;
+        if (span_y / ch > 255.0f) ch = span_y / 255.0f;
+        g.x0 = x0;
+        g.y0 = y0;
+        g.inv_cw = 1.0f / cw;
+        g.inv_ch = 1.0f / ch;
+        g.gw = static_cast<int>(span_x / cw) + 1;
+        g.gh = static_cast<int>(span_y / ch) + 1;
+        if (g.gw > 256) g.gw = 256;
+        if (g.gh > 256) g.gh = 256;
+    }
+    const int n_cells = g.gw * g.gh;
+
+    // 2. count -> scan -> fill
+    if (int rc = EnsureDevice(ctx, ctx->d_work1, sizeof(int) * (3 * static_cast<size_t>(n_cells) + 8))) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work2, sizeof(int) * (2 * static_cast<size_t>(n_cur) + 8))) return rc;
+    int *d_counts = static_cast<int *>(ctx->d_work1.ptr);
+    int *d_starts = d_counts + n_cells;       // n_cells + 1
+    int *d_cursor = d_starts + n_cells + 1;   // n_cells
+    int *d_nspecial = d_cursor + n_cells;     // 1
+    int *d_sorted = static_cast<int *>(ctx->d_work2.ptr);
+    int *d_special = d_sorted + n_cur;
+    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (3 * static_cast<size_t>(n_cells) + 8), st));
+    CellCountKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, g, d_counts, d_special, d_nspecial);
+    ScanKernel<<<1, 1024, 0, st>>>(d_counts, n_cells, d_starts, d_cursor);
+    CellFillKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, g, d_cursor, d_sorted);
+    // 3. one warp per ref descriptor
+    NearbyKernel<Dist><<<Blocks(n_ref * 32, 128), 128, 0, st>>>(dist, n_ref, d_pred, d_pos, n_cur, g, d_starts, d_sorted, d_special, d_nspecial,
+                                                             static_cast<float>(max_dcol), static_cast<float>(max_drow), max_dist, d_idx);
+    ctx->launches += 4;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+int ComputeNorms(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float **ref_norm, float **cur_norm) {
+    if (int rc = EnsureDevice(ctx, ctx->d_work3, sizeof(float) * (static_cast<size_t>(n_ref) + n_cur + 8))) return rc;
+    *ref_norm = static_cast<float *>(ctx->d_work3.ptr);
+    *cur_norm = *ref_norm + n_ref;
+    NormKernel<<<Blocks(n_ref, 128), 128, 0, ctx->stream>>>(d_ref, n_ref, dim, *ref_norm);
+    NormKernel<<<Blocks(n_cur, 128), 128, 0, ctx->stream>>>(d_cur, n_cur, dim, *cur_norm);
+    ctx->launches += 2;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+}  // namespace
+
+int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx) {
+    if (n_ref == 0 || words == 0) return FTK_OK;  // empty descriptors: distance kMaxInt32 never beats a sane max_dist
+    cudaStream_t st = ctx->stream;
+    const int ref_blocks = Blocks(n_ref, kHamThreads);
+    const bool packed = (words == 4 || words == 8 || words == 16) && n_cur <= (1 << kJBits);
+    if (packed) {
+        if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned) * static_cast<size_t>(n_ref))) return rc;
+        unsigned *d_best = static_cast<unsigned *>(ctx->d_work0.ptr);
+        FillU32Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, kNoKey32);
+        const int splits = CurSplits(ctx, ref_blocks, n_cur, kHamTile);
+        const int per = ((n_cur + splits - 1) / splits + kHamTile - 1) / kHamTile * kHamTile;
+        const dim3 grid(ref_blocks, (n_cur + per - 1) / per);
+        if (words == 8) HammingForceKernel<8><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
+        else if (words == 4) HammingForceKernel<4><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
+        else HammingForceKernel<16><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
+        HammingFinalize32Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, max_dist, d_idx);
+    } else {
+        if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref))) return rc;
+        unsigned long long *d_best = static_cast<unsigned long long *>(ctx->d_work0.ptr);
+        FillU64Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, kNoKey64);
+        const int splits = CurSplits(ctx, ref_blocks, n_cur, 64);
+        const int per = (n_cur + splits - 1) / splits;
+        const dim3 grid(ref_blocks, (n_cur + per - 1) / per);
+        HammingForceGenericKernel<<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, words, per, d_best);
+        HammingFinalize64Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, max_dist, d_idx);
+    }
+    ctx->launches += 3;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
+                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx) {
+    if (n_ref == 0) return FTK_OK;
+    const HammingDist dist{d_ref, d_cur, words};
+    return RunNearby(ctx, dist, n_ref, n_cur, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx);
+}
+
+int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
+    if (n_ref == 0) return FTK_OK;
+    cudaStream_t st = ctx->stream;
+    float *ref_norm, *cur_norm;
+    if (int rc = ComputeNorms(ctx, d_ref, n_ref, d_cur, n_cur, dim, &ref_norm, &cur_norm)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref))) return rc;
+    unsigned long long *d_best = static_cast<unsigned long long *>(ctx->d_work0.ptr);
+    FillU64Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, kNoKey64);
+    const int ref_blocks = Blocks(n_ref, kCosThreads);
+    const int splits = CurSplits(ctx, ref_blocks, n_cur, kCosCurTile);
+    const int per = ((n_cur + splits - 1) / splits + kCosCurTile - 1) / kCosCurTile * kCosCurTile;
+    const dim3 grid(ref_blocks, (n_cur + per - 1) / per);
+    CosineForceKernel<<<grid, kCosThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, dim, ref_norm, cur_norm, per, d_best);
+    CosineFinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, max_dist, d_idx);
+    ctx->launches += 3;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,
+                       const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx) {
+    if (n_ref == 0) return FTK_OK;
+    float *ref_norm, *cur_norm;
+    if (int rc = ComputeNorms(ctx, d_ref, n_ref, d_cur, n_cur, dim, &ref_norm, &cur_norm)) return rc;
+    const CosineDist dist{d_ref, d_cur, ref_norm, cur_norm, dim};
+    return RunNearby(ctx, dist, n_ref, n_cur, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx);
+}
+
+}  // namespace ftk

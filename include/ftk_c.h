@@ -1,0 +1,149 @@
+/* ftk_c.h -- C ABI of the B200-native sparse feature tracking / descriptor matching library (libftk_b200.so).
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path (Horizon1026/Feature_Tracker):
+ * plain pointers and sizes, no C++ / torch types.  Every entry point cites the reference interface it replaces
+ * (paths relative to the reference root).  The reference has no FFI today (single-threaded C++ loops); the
+ * seam a maintainer would bind is shown in INTEGRATION.md, and include/feature_tracker_b200/ holds C++ facade
+ * classes with the reference's class names on top of this ABI.
+ *
+ * Conventions
+ *   - All functions return FTK_OK (0) or a negative error code; ftk_last_error() gives the text.  The facade maps
+ *     FTK_ERR_EMPTY_INPUT / FTK_ERR_LEVEL_MISMATCH / FTK_ERR_SIZE_MISMATCH to the reference's `return false`.
+ *   - uv arrays are interleaved float32 (x = column, y = row), like std::vector<Vec2>.
+ *   - status bytes are feature_tracker::TrackStatus values (src/feature_tracker.h:8-14).
+ *   - Pointers are HOST pointers unless FTK_FLAG_DEVICE_POINTERS is given; host calls are synchronous (results are
+ *     valid on return), device-pointer calls are asynchronous on the context's stream.
+ *   - A context is bound to one GPU and one stream; it is not re-entrant (the reference objects are not either:
+ *     src/optical_flow_tracker/optical_flow.h:94-103).  Use one context per host thread / per GPU.
+ *   - There is no CPU fallback: every call fails with FTK_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef FTK_C_H_
+#define FTK_C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTK_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------------------------ */
+#define FTK_OK 0
+#define FTK_ERR_INVALID_ARGUMENT (-1)
+#define FTK_ERR_EMPTY_INPUT (-2)    /* reference: RETURN_FALSE_IF(ref_pixel_uv.empty()) / descriptors_cur.empty() */
+#define FTK_ERR_LEVEL_MISMATCH (-3) /* reference: cur_pyramid.level() != ref_pyramid.level() */
+#define FTK_ERR_SIZE_MISMATCH (-4)  /* reference: descriptor/uv vector sizes differ (descriptor_matcher.h:95-96) */
+#define FTK_ERR_CUDA (-5)
+#define FTK_ERR_UNSUPPORTED (-6)
+
+/* ---- TrackStatus (src/feature_tracker.h:8-14) ---------------------------------------------------------------- */
+#define FTK_STATUS_NOT_TRACKED 0
+#define FTK_STATUS_TRACKED 1
+#define FTK_STATUS_LARGE_RESIDUAL 2
+#define FTK_STATUS_OUTSIDE 3
+#define FTK_STATUS_NUMERIC_ERROR 4
+
+/* ---- flags -------------------------------------------------------------------------------------------------- */
+#define FTK_FLAG_DEVICE_POINTERS 1u /* feature / descriptor / index arrays already live on the context's GPU */
+#define FTK_FLAG_NO_PREDICTION 2u   /* cur_uv holds no prediction: behave as cur_pixel_uv.size() != ref size (optical_flow.cpp:12-14) */
+#define FTK_FLAG_NO_STATUS 4u       /* status holds nothing: behave as status.size() != ref size (optical_flow.cpp:17-19) */
+#define FTK_FLAG_SINGLE_LEVEL 8u    /* the GrayImage overload: TrackSingleLevel on level 0 (optical_flow.cpp:28-47) */
+#define FTK_FLAG_NO_INDEX_INPUT 16u /* idx holds nothing: behave as index_pairs_in_cur.size() != ref size (descriptor_matcher.h:60-62) */
+
+/* ---- KLT parameters ------------------------------------------------------------------------------------------
+ * OpticalFlowOptions (src/optical_flow_tracker/optical_flow.h:20-28), OpticalFlowMethod (:12-18) and the subclass
+ * extras predict_affine() (affine_klt/optical_flow_affine_klt.h:18), predict_R_cr() / consider_patch_luminance()
+ * (lssd_klt/optical_flow_lssd_klt.h:18-19). */
+#define FTK_VARIANT_BASIC 0  /* OpticalFlowBasicKlt  */
+#define FTK_VARIANT_AFFINE 1 /* OpticalFlowAffineKlt */
+#define FTK_VARIANT_LSSD 2   /* OpticalFlowLssdKlt   */
+#define FTK_METHOD_INVERSE 0
+#define FTK_METHOD_DIRECT 1
+#define FTK_METHOD_FAST 2 /* kSse(3) / kNeon(4) take the reference's `default:` branch, i.e. kFast */
+
+typedef struct ftk_klt_params {
+    int32_t variant;
+    int32_t method;
+    uint32_t max_track_points;         /* kMaxTrackPointsNumber, applied per frame pair */
+    uint32_t max_iteration;            /* kMaxIteration */
+    uint32_t max_tolerance_large_step; /* kMaxToleranceLargeStep */
+    int32_t patch_row_half;            /* kPatchRowHalfSize */
+    int32_t patch_col_half;            /* kPatchColHalfSize */
+    float max_converge_step;           /* kMaxConvergeStep, compared with the SQUARED step */
+    float predict[4];                  /* row-major 2x2: predict_affine_ (affine, single level) / predict_R_cr_ (lssd) */
+    int32_t consider_patch_luminance;  /* lssd fast only */
+} ftk_klt_params;
+
+/* Fills the reference defaults (optical_flow.h:20-28; identity predictions; luminance off). */
+void ftk_klt_params_default(ftk_klt_params *params);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+typedef struct ftk_context ftk_context;
+
+int ftk_abi_version(void);
+int ftk_create(int device, ftk_context **out);
+void ftk_destroy(ftk_context *ctx);
+const char *ftk_last_error(const ftk_context *ctx);
+int ftk_synchronize(ftk_context *ctx);
+/* The context's cudaStream_t, for callers that time with CUDA events or enqueue their own work. */
+void *ftk_stream(ftk_context *ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+uint64_t ftk_kernel_launches(const ftk_context *ctx);
+
+/* ---- image pyramids (replaces ImagePyramid::SetRawImage / CreateImagePyramid, call sites
+ *      test/test_optical_flow.cpp:49-53,70-71; semantics: oracle/shim/datatype_image_pyramid.h) -------------------
+ * A pyramid batch holds n_images same-sized grayscale images, device resident, level-major. */
+typedef struct ftk_pyramid ftk_pyramid;
+
+int ftk_pyramid_create(ftk_context *ctx, int32_t rows, int32_t cols, int32_t levels, int32_t n_images, ftk_pyramid **out);
+void ftk_pyramid_destroy(ftk_context *ctx, ftk_pyramid *pyr);
+/* Copies `count` tightly packed rows*cols images into level 0 of images [first, first+count).
+ * `images` is a host pointer (pinned memory makes the copy asynchronous) or a device pointer with
+ * FTK_FLAG_DEVICE_POINTERS. */
+int ftk_pyramid_set_images(ftk_context *ctx, ftk_pyramid *pyr, int32_t first, int32_t count, const uint8_t *images, uint32_t flags);
+/* Builds levels 1..levels-1 of images [first, first+count) from their level 0 (asynchronous on the stream). */
+int ftk_pyramid_build(ftk_context *ctx, ftk_pyramid *pyr, int32_t first, int32_t count);
+/* Verbatim access to one level of one image (tightly packed (rows>>level)*(cols>>level) bytes, host memory). */
+int ftk_pyramid_set_level(ftk_context *ctx, ftk_pyramid *pyr, int32_t image, int32_t level, const uint8_t *data);
+int ftk_pyramid_get_level(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, int32_t level, uint8_t *data);
+int32_t ftk_pyramid_levels(const ftk_pyramid *pyr);
+int32_t ftk_pyramid_images(const ftk_pyramid *pyr);
+
+/* ---- sparse KLT tracking (replaces OpticalFlow::TrackFeatures, src/optical_flow_tracker/optical_flow.cpp:6-47,
+ *      and the TrackMultipleLevel / TrackSingleLevel overrides of the three subclasses) --------------------------
+ * Tracks n_pairs independent frame pairs in one call.  Pair p uses image ref_image[p] of `ref` and cur_image[p]
+ * of `cur` (NULL = image p) and owns features [feat_offsets[p], feat_offsets[p+1]).  `ref` and `cur` may be the
+ * same batch.  cur_uv is in/out (prediction in, result out), status is in/out (entries > kTracked are skipped
+ * untouched; only the first max_track_points features of each pair are tracked). */
+int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t n_pairs,
+                  const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
+                  uint8_t *status, uint32_t flags);
+
+/* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
+ *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of
+ *      test/test_descriptor_matcher_brief.cpp:33-45 and test/test_descriptor_matcher_superpoint.cpp:32-34) --------
+ * Binary descriptors are packed little-endian: element k of a BriefType is bit (k % 32) of word (k / 32).
+ * idx is in/out: idx[i] is overwritten only when ref descriptor i finds a match with distance < max_dist
+ * (strict <, lowest cur index wins ties). */
+int ftk_match_hamming_force(ftk_context *ctx, const uint32_t *ref, int32_t n_ref, const uint32_t *cur, int32_t n_cur, int32_t words,
+                            float max_dist, int32_t *idx, uint32_t flags);
+int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_ref, const uint32_t *cur, int32_t n_cur, int32_t words,
+                             const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
+                             uint32_t flags);
+/* Float descriptors, row-major n x dim, distance 0.5 - 0.5 * cos(ref, cur). */
+int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist,
+                           int32_t *idx, uint32_t flags);
+int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim,
+                            const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
+                            uint32_t flags);
+/* Host-side helper mirroring FillMatchedPixelByPairIndices (descriptor_matcher.h:135-157); status_valid == 0
+ * behaves as status.size() != idx.size(). */
+int ftk_fill_matched(const int32_t *idx, int32_t n_ref, const float *cur_uv, int32_t n_cur, float *matched_uv, uint8_t *status,
+                     int32_t status_valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTK_C_H_ */

@@ -1,0 +1,325 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle on identical seeded inputs and
+against the committed golden vectors (produced by the reference's own sources).
+
+Bar (BASELINE.json north_star): positions within 1e-3 px with identical status, Hamming distances / match indices
+bit-exact.  This implementation reproduces the reference's fp32 arithmetic and summation order, so the tests assert the
+stronger property: positions BIT-IDENTICAL, status identical, indices identical."""
+import numpy as np
+import pytest
+
+import feature_tracker_b200 as ft
+from conftest import bits_equal
+from feature_tracker_b200 import synthetic as S
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {"basic": ft.OpticalFlowBasicKlt, "affine": ft.OpticalFlowAffineKlt, "lssd": ft.OpticalFlowLssdKlt}
+METHODS = {"inverse": ft.OpticalFlowMethod.kInverse, "direct": ft.OpticalFlowMethod.kDirect, "fast": ft.OpticalFlowMethod.kFast}
+KLT_COMBOS = [(v, m, h) for v in ("basic", "affine", "lssd") for m in ("inverse", "direct", "fast") for h in (6, 7, 10)]
+POS_TOL_PX = 1e-3  # the stated tolerance; the assertions below demand exact equality
+
+
+def make_tracker(ctx, variant, method, half, half_col=None, max_points=500, predict=None, luminance=False):
+    klt = VARIANTS[variant](ctx)
+    o = klt.options()
+    o.kPatchRowHalfSize = half
+    o.kPatchColHalfSize = half if half_col is None else half_col
+    o.kMethod = METHODS[method]
+    o.kMaxTrackPointsNumber = max_points
+    if predict is not None:
+        klt._predict = np.array(predict, np.float32).reshape(2, 2)
+    if variant == "lssd":
+        klt.consider_patch_luminance = luminance
+    return klt
+
+
+def upload_levels(ctx, levels_list):
+    """Builds a device pyramid batch from host-built levels (one list of level arrays per image), verbatim."""
+    rows, cols = levels_list[0][0].shape
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, len(levels_list[0]), len(levels_list))
+    for i, lv in enumerate(levels_list):
+        for l, a in enumerate(lv):
+            pyr.SetLevel(i, l, a)
+    return pyr
+
+
+def assert_same(tag, got, exp):
+    ok_g, uv_g, st_g = got
+    ok_e, uv_e, st_e = exp
+    assert ok_g == ok_e, tag
+    bad_st = np.nonzero(st_g != st_e)[0]
+    assert bad_st.size == 0, f"{tag}: status differs at {bad_st[:10]} gpu={st_g[bad_st[:10]]} oracle={st_e[bad_st[:10]]}"
+    d = np.abs(uv_g.astype(np.float64) - uv_e.astype(np.float64))
+    d = np.where(np.isnan(d), 0 if np.array_equal(np.isnan(uv_g), np.isnan(uv_e)) else np.inf, d)
+    assert d.max() <= POS_TOL_PX, f"{tag}: max position error {d.max()} px"
+    assert bits_equal(uv_g, uv_e), f"{tag}: positions within tolerance ({d.max()} px) but not bit-identical"
+
+
+# ---- pyramid -------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,levels", [((480, 752), 4), ((720, 1280), 4), ((37, 53), 4), ((64, 64), 1), ((100, 131), 6), ((9, 9), 3)])
+def test_pyramid_bit_exact(ctx, oracle, shape, levels):
+    rng = np.random.default_rng(shape[0] * 7 + levels)
+    imgs = rng.integers(0, 256, (3,) + shape, dtype=np.uint8)
+    pyr = ft.ImagePyramidBatch(ctx, shape[0], shape[1], levels, 3)
+    pyr.SetRawImages(imgs)
+    pyr.CreateImagePyramid()
+    for i in range(3):
+        exp = oracle.pyramid_build(imgs[i], levels)
+        for l in range(levels):
+            assert (pyr.GetLevel(i, l) == exp[l]).all(), (i, l)
+
+
+def test_pyramid_matches_golden(ctx, euroc_golden):
+    g = euroc_golden
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([g["ref"], g["cur"]]))
+    pyr.CreateImagePyramid()
+    for l in range(1, 4):
+        assert (pyr.GetLevel(0, l) == g[f"ref_l{l}"]).all() and (pyr.GetLevel(1, l) == g[f"cur_l{l}"]).all()
+
+
+# ---- KLT vs golden (reference-produced) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("variant,method,half", KLT_COMBOS)
+def test_klt_matches_golden(ctx, euroc_golden, variant, method, half):
+    g = euroc_golden
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([g["ref"], g["cur"]]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, variant, method, half)
+    got = klt.TrackFeatures(pyr, pyr, g["pts"], ref_image=0, cur_image=1)
+    key = f"{variant}_{method}_h{half}"
+    assert_same(key, got, (True, g[key + "_uv"], g[key + "_st"]))
+
+
+def test_klt_golden_extras(ctx, euroc_golden):
+    g = euroc_golden
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([g["ref"], g["cur"]]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, "lssd", "fast", 6, luminance=True)
+    assert_same("lssd lum", klt.TrackFeatures(pyr, pyr, g["pts"], ref_image=0, cur_image=1), (True, g["lssd_fast_h6_lum_uv"], g["lssd_fast_h6_lum_st"]))
+    pred = g["pts"] + np.float32(3.0)
+    for v in ("basic", "affine", "lssd"):
+        klt = make_tracker(ctx, v, "fast", 6, predict=(0.9995, -0.03, 0.03, 0.9995))
+        got = klt.TrackFeatures(pyr, pyr, g["pts"], cur_pixel_uv=pred, single_level=True, ref_image=0, cur_image=1)
+        assert_same(v + " single", got, (True, g[f"{v}_fast_h6_single_uv"], g[f"{v}_fast_h6_single_st"]))
+
+
+# ---- KLT vs oracle on seeded synthetic pairs (interior + border + far-outside features) -------------------------------
+@pytest.mark.parametrize("variant", ["basic", "affine", "lssd"])
+@pytest.mark.parametrize("method", ["inverse", "direct", "fast"])
+def test_klt_synthetic_vs_oracle(ctx, oracle, variant, method):
+    ref, cur, uv, _ = S.make_pair(240, 320, 150, pair_id=11, border=12)
+    rng = np.random.default_rng(5)
+    uv = np.concatenate([uv, np.stack([rng.uniform(-6, 326, 60), rng.uniform(-6, 246, 60)], 1).astype(np.float32)])
+    rl, cl = oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3)
+    pyr = upload_levels(ctx, [rl, cl])
+    for half, half_col, lum, single in [(6, 6, False, False), (4, 5, True, False), (7, 7, False, True), (2, 9, False, False)]:
+        predict = (0.9995, -0.03, 0.03, 0.9995) if single else (1, 0, 0, 1)
+        p = po.make_params(variant, method, half=half, half_col=half_col, max_points=1000, luminance=lum, predict=predict)
+        exp = oracle.klt_track(p, rl, cl, uv, single_level=single)
+        klt = make_tracker(ctx, variant, method, half, half_col, max_points=1000, predict=predict, luminance=lum)
+        got = klt.TrackFeatures(pyr, pyr, uv, single_level=single, ref_image=0, cur_image=1)
+        assert_same(f"{variant}/{method}/h{half}x{half_col}/lum{lum}/single{single}", got, exp)
+
+
+def test_klt_entry_semantics(ctx, oracle):
+    ref, cur, uv, _ = S.make_pair(120, 160, 30, pair_id=5, border=10)
+    rl, cl = oracle.pyramid_build(ref, 2), oracle.pyramid_build(cur, 2)
+    pyr = upload_levels(ctx, [rl, cl])
+    klt = make_tracker(ctx, "basic", "fast", 4, max_points=10)
+    p = po.make_params("basic", "fast", half=4, max_points=10)
+    ok, _, _ = klt.TrackFeatures(pyr, pyr, np.zeros((0, 2), np.float32), ref_image=0, cur_image=1)
+    assert not ok  # optical_flow.cpp:8
+    assert_same("cap", klt.TrackFeatures(pyr, pyr, uv, cur_pixel_uv=uv[:5] + 1, status=np.full(3, 4, np.uint8), ref_image=0, cur_image=1),
+                oracle.klt_track(p, rl, cl, uv, cur_uv=uv[:5] + 1, status=np.full(3, 4, np.uint8)))
+    st_in = np.zeros(30, np.uint8)
+    st_in[2], st_in[4] = 3, 2
+    pred = uv + np.float32(0.5)
+    assert_same("skip", klt.TrackFeatures(pyr, pyr, uv, cur_pixel_uv=pred, status=st_in, ref_image=0, cur_image=1),
+                oracle.klt_track(p, rl, cl, uv, cur_uv=pred, status=st_in))
+    # level mismatch -> false (optical_flow.cpp:9)
+    other = ft.ImagePyramidBatch(ctx, 120, 160, 3, 1)
+    ok, _, _ = klt.TrackFeatures(pyr, other, uv, ref_image=0, cur_image=0)
+    assert not ok
+
+
+def test_klt_batch_of_pairs(ctx, oracle):
+    """Many frame pairs in one call (the sharding unit): ragged feature counts incl. an empty pair, device-built pyramids."""
+    n_pairs, rows, cols, levels = 5, 120, 160, 3
+    counts = [40, 0, 17, 64, 1]
+    refs, curs, uvs = [], [], []
+    for p in range(n_pairs):
+        r, c, uv, _ = S.make_pair(rows, cols, max(counts[p], 1), pair_id=40 + p, border=10)
+        refs.append(r), curs.append(c), uvs.append(uv[:counts[p]])
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 2 * n_pairs)
+    pyr.SetRawImages(np.stack(refs + curs))
+    pyr.CreateImagePyramid()
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    all_uv = np.concatenate(uvs)
+    for variant, method, half in [("basic", "inverse", 7), ("basic", "fast", 6), ("affine", "fast", 6), ("lssd", "inverse", 5)]:
+        klt = make_tracker(ctx, variant, method, half, max_points=50)
+        ok, cur_uv, st = klt.TrackFeaturesBatch(pyr, pyr, offsets, all_uv, ref_image=np.arange(n_pairs), cur_image=np.arange(n_pairs) + n_pairs)
+        assert ok
+        prm = po.make_params(variant, method, half=half, max_points=50)
+        for p in range(n_pairs):
+            if counts[p] == 0:
+                continue
+            exp = oracle.klt_track(prm, oracle.pyramid_build(refs[p], levels), oracle.pyramid_build(curs[p], levels), uvs[p])
+            sl = slice(offsets[p], offsets[p + 1])
+            assert_same(f"{variant}/{method} pair {p}", (True, cur_uv[sl], st[sl]), exp)
+
+
+def test_klt_north_star_config(ctx, oracle):
+    """BASELINE configs[0]: basic inverse, 4 levels, 15x15 patches, 200 features on a 752x480 pair."""
+    ref, cur, uv, fwd = S.make_pair(480, 752, 200, pair_id=0)
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, "basic", "inverse", 7)
+    got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    exp = oracle.klt_track(po.make_params("basic", "inverse", half=7), oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4), uv)
+    assert_same("north star", got, exp)
+    good = got[2] == 1
+    assert good.mean() > 0.9 and np.median(np.linalg.norm(got[1][good] - fwd(uv)[good], axis=1)) < 0.3
+
+
+def test_klt_lssd_c3_shape(ctx, oracle):
+    """BASELINE configs[2] at reduced count: LSSD inverse, 21x21 patches, 1280x720."""
+    ref, cur, uv, _ = S.make_pair(720, 1280, 300, pair_id=2)
+    pyr = ft.ImagePyramidBatch(ctx, 720, 1280, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, "lssd", "inverse", 10, max_points=10000)
+    got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    exp = oracle.klt_track(po.make_params("lssd", "inverse", half=10, max_points=10000), oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4), uv)
+    assert_same("lssd c3", got, exp)
+
+
+# ---- descriptor matching -----------------------------------------------------------------------------------------------
+def brief_matcher(ctx, max_dist, drow=40, dcol=40):
+    m = ft.BriefMatcher(ctx)
+    m.options().kMaxValidDescriptorDistance = max_dist
+    m.options().kMaxValidPredictRowDistance = drow
+    m.options().kMaxValidPredictColDistance = dcol
+    return m
+
+
+def test_matchers_match_golden(ctx, matcher_golden):
+    g = matcher_golden
+    m = brief_matcher(ctx, 60.0, 50, 50)
+    rb, cb = ft.pack_brief(g["brief_ref"]), ft.pack_brief(g["brief_cur"])
+    ok, idx = m.ForceMatch(rb, cb)
+    assert ok and (idx == g["brief_force_idx"]).all()
+    ok, idx = m.NearbyMatch(rb, cb, g["brief_pred"], g["brief_pos"])
+    assert ok and (idx == g["brief_nearby_idx"]).all()
+    ok, muv, mst = m.NearbyMatchUv(rb, cb, g["brief_pred"], g["brief_pos"])
+    assert ok and (mst == g["brief_nearby_st"]).all() and bits_equal(muv[mst == 1], g["brief_nearby_uv"][mst == 1])
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.1
+    ok, idx = c.ForceMatch(g["float_ref"], g["float_cur"])
+    assert ok and (idx == g["float_force_idx"]).all()
+    c.options().kMaxValidDescriptorDistance = 0.3
+    c.options().kMaxValidPredictRowDistance = c.options().kMaxValidPredictColDistance = 50
+    ok, idx = c.NearbyMatch(g["float_ref"], g["float_cur"], g["float_pred"], g["float_pos"])
+    assert ok and (idx == g["float_nearby_idx"]).all()
+
+
+@pytest.mark.parametrize("n_ref,n_cur,bits", [(1, 1, 256), (257, 300, 256), (1000, 777, 256), (300, 5000, 256), (64, 200, 128), (50, 60, 512), (40, 70, 96)])
+def test_hamming_force_vs_oracle(ctx, oracle, n_ref, n_cur, bits):
+    rb, cb, _, _, _ = S.make_brief_sets(n_ref, n_cur, bits=bits, seed=n_ref + n_cur)
+    for max_dist in (bits * 0.23, bits * 2.0, 0.0):
+        exp = oracle.match_brief_force(rb, cb, max_dist)
+        got = brief_matcher(ctx, max_dist).ForceMatch(ft.pack_brief(rb), ft.pack_brief(cb))
+        assert got[0] == exp[0] and (got[1] == exp[1]).all(), (n_ref, n_cur, bits, max_dist)
+
+
+def test_hamming_semantics(ctx, oracle):
+    rng = np.random.default_rng(4)
+    cur = rng.integers(0, 2, (6, 64), dtype=np.uint8)
+    cur[4] = cur[1]  # tie at distance 0: lowest j wins
+    ref = cur[[1, 3]].copy()
+    m = brief_matcher(ctx, 10.0)
+    assert list(m.ForceMatch(ft.pack_brief(ref), ft.pack_brief(cur))[1]) == [1, 3]
+    m0 = brief_matcher(ctx, 0.0)  # reference default: nothing matches
+    assert list(m0.ForceMatch(ft.pack_brief(ref), ft.pack_brief(cur))[1]) == [-1, -1]
+    assert list(m0.ForceMatch(ft.pack_brief(ref), ft.pack_brief(cur), np.array([5, 2], np.int32))[1]) == [5, 2]  # preset indices survive
+    ok, _ = m.ForceMatch(ft.pack_brief(ref), np.zeros((0, 2), np.uint32))
+    assert not ok  # descriptor_matcher.h:58
+    pos = np.array([[0, 0], [100, 100], [10, 10], [50, 50], [12, 12], [300, 300]], np.float32)
+    pred = np.array([[11, 11], [52, 52]], np.float32)
+    mn = brief_matcher(ctx, 64.0, 5, 5)
+    assert list(mn.NearbyMatch(ft.pack_brief(ref), ft.pack_brief(cur), pred, pos)[1]) == [4, 3]
+    ok, _ = mn.NearbyMatch(ft.pack_brief(ref), ft.pack_brief(cur), pred[:1], pos)
+    assert not ok  # descriptor_matcher.h:95
+
+
+@pytest.mark.parametrize("n_ref,n_cur,win", [(500, 600, (50, 50)), (1500, 1400, (30, 45)), (200, 3000, (5, 80)), (300, 300, (1000, 1000)), (100, 120, (0, 0))])
+def test_hamming_nearby_vs_oracle(ctx, oracle, n_ref, n_cur, win):
+    rb, cb, pred, pos, _ = S.make_brief_sets(n_ref, n_cur, seed=3 * n_ref + n_cur)
+    pos[::17] = np.round(pos[::17])  # exact window-edge cases
+    pred[::13] = np.round(pred[::13])
+    if n_ref == 500:  # non-finite coordinates follow the reference's comparison semantics (NaN passes the gate)
+        pos[5] = [np.nan, 100.0]
+        pos[6] = [np.inf, 50.0]
+        pred[9] = [np.nan, np.nan]
+        pred[10] = [200.0, np.nan]
+    exp = oracle.match_brief_nearby(rb, cb, pred, pos, win[0], win[1], 70.0)
+    got = brief_matcher(ctx, 70.0, win[0], win[1]).NearbyMatch(ft.pack_brief(rb), ft.pack_brief(cb), pred, pos)
+    assert got[0] == exp[0]
+    bad = np.nonzero(got[1] != exp[1])[0]
+    assert bad.size == 0, (bad[:10], got[1][bad[:10]], exp[1][bad[:10]])
+
+
+@pytest.mark.parametrize("n_ref,n_cur,dim", [(1, 1, 256), (130, 170, 256), (400, 333, 256), (60, 90, 64), (33, 40, 100)])
+def test_cosine_force_vs_oracle(ctx, oracle, n_ref, n_cur, dim):
+    rf, cf = S.make_float_sets(n_ref, n_cur, dim=dim, seed=dim + n_ref)
+    if n_ref > 100:
+        cf[7] = cf[3]          # exact tie: lowest j wins
+        rf[5] = 0.0            # zero-norm descriptor -> NaN distance -> never matches
+    for max_dist in (0.1, 0.6):
+        exp = oracle.match_cosine_force(rf, cf, max_dist)
+        c = ft.CosineMatcher(ctx)
+        c.options().kMaxValidDescriptorDistance = max_dist
+        got = c.ForceMatch(rf, cf)
+        assert got[0] == exp[0] and (got[1] == exp[1]).all(), (n_ref, n_cur, dim, max_dist, np.nonzero(got[1] != exp[1])[0][:10])
+
+
+def test_cosine_nearby_vs_oracle(ctx, oracle):
+    rf, cf = S.make_float_sets(300, 350, dim=256, seed=31)
+    rng = np.random.default_rng(8)
+    pos = np.stack([rng.uniform(0, 751, 350), rng.uniform(0, 479, 350)], 1).astype(np.float32)
+    pred = np.stack([rng.uniform(0, 751, 300), rng.uniform(0, 479, 300)], 1).astype(np.float32)
+    rf[10] = cf[20]  # exact duplicate -> distance that may round to exactly 0 (the `break` path)
+    pred[10] = pos[20]
+    exp = oracle.match_cosine_nearby(rf, cf, pred, pos, 120, 150, 0.45)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.45
+    c.options().kMaxValidPredictRowDistance, c.options().kMaxValidPredictColDistance = 120, 150
+    got = c.NearbyMatch(rf, cf, pred, pos)
+    assert got[0] == exp[0] and (got[1] == exp[1]).all()
+    assert (exp[1] >= 0).sum() > 50
+
+
+def test_hamming_c4_full_size_properties(ctx):
+    """BASELINE configs[3] at full size (10k x 10k): size-independent properties instead of the O(N*M) CPU oracle --
+    planted matches are recovered, results are idempotent, and a ref-row permutation permutes the result."""
+    rb, cb, pred, pos, truth = S.make_brief_sets(10000, 10000, seed=99)
+    pr, pc = ft.pack_brief(rb), ft.pack_brief(cb)
+    m = brief_matcher(ctx, 60.0, 50, 50)
+    ok, idx = m.ForceMatch(pr, pc)
+    has = truth >= 0
+    assert ok and (idx[has] == truth[has]).mean() > 0.999
+    ok, idx2 = m.ForceMatch(pr, pc, idx.copy())
+    assert (idx2 == idx).all()
+    perm = np.random.default_rng(0).permutation(10000)
+    ok, idx3 = m.ForceMatch(pr[perm], pc)
+    assert (idx3 == idx[perm]).all()
+    # distances of the reported matches really are the row minima (checked on a sample with numpy popcount)
+    sample = np.random.default_rng(1).integers(0, 10000, 64)
+    d = (rb[sample][:, None, :] != cb[None, :, :]).sum(2)
+    exp = np.where(d.min(1) < 60, d.argmin(1), -1)
+    assert (idx[sample] == exp).all()
+    ok, nidx = m.NearbyMatch(pr, pc, pred, pos)
+    assert ok and (nidx[has] == truth[has]).mean() > 0.95

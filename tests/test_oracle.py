@@ -1,0 +1,179 @@
+"""CPU tests of the oracle (plain-C restatement) against (a) the committed golden vectors, which were produced by the
+reference's own sources compiled in place, (b) that reference build itself when it is available, and (c) domain
+properties.  No GPU needed."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+from feature_tracker_b200 import synthetic as S
+from oracle import pyoracle as po
+
+KLT_COMBOS = [(v, m, h) for v in ("basic", "affine", "lssd") for m in ("inverse", "direct", "fast") for h in (6, 7, 10)]
+
+
+def golden_levels(g):
+    L = int(g["levels"])
+    return [g["ref"]] + [g[f"ref_l{l}"] for l in range(1, L)], [g["cur"]] + [g[f"cur_l{l}"] for l in range(1, L)]
+
+
+def test_pyramid_matches_golden(oracle, euroc_golden):
+    g = euroc_golden
+    lv = oracle.pyramid_build(g["ref"], int(g["levels"]))
+    for l in range(1, int(g["levels"])):
+        assert (lv[l] == g[f"ref_l{l}"]).all()
+        assert lv[l].shape == (480 >> l, 752 >> l)
+
+
+def test_pyramid_odd_sizes(oracle):
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    lv = oracle.pyramid_build(img, 4)
+    assert [a.shape for a in lv] == [(37, 53), (18, 26), (9, 13), (4, 6)]
+    a = img.astype(np.uint16)
+    exp = ((a[0:36:2, 0:52:2] + a[1:36:2, 0:52:2] + a[0:36:2, 1:52:2] + a[1:36:2, 1:52:2]) >> 2).astype(np.uint8)
+    assert (lv[1] == exp).all()
+
+
+@pytest.mark.parametrize("variant,method,half", KLT_COMBOS)
+def test_klt_matches_golden(oracle, euroc_golden, variant, method, half):
+    g = euroc_golden
+    rl, cl = golden_levels(g)
+    ok, uv, st = oracle.klt_track(po.make_params(variant, method, half=half), rl, cl, g["pts"])
+    assert ok
+    key = f"{variant}_{method}_h{half}"
+    assert (st == g[key + "_st"]).all()
+    assert bits_equal(uv, g[key + "_uv"])
+
+
+def test_klt_golden_extras(oracle, euroc_golden):
+    g = euroc_golden
+    rl, cl = golden_levels(g)
+    ok, uv, st = oracle.klt_track(po.make_params("lssd", "fast", half=6, luminance=True), rl, cl, g["pts"])
+    assert (st == g["lssd_fast_h6_lum_st"]).all() and bits_equal(uv, g["lssd_fast_h6_lum_uv"])
+    pred = g["pts"] + np.float32(3.0)
+    for v in ("basic", "affine", "lssd"):
+        p = po.make_params(v, "fast", half=6, predict=(0.9995, -0.03, 0.03, 0.9995))
+        ok, uv, st = oracle.klt_track(p, rl, cl, g["pts"], cur_uv=pred, single_level=True)
+        assert (st == g[f"{v}_fast_h6_single_st"]).all() and bits_equal(uv, g[f"{v}_fast_h6_single_uv"])
+
+
+@pytest.mark.parametrize("variant", ["basic", "affine", "lssd"])
+@pytest.mark.parametrize("method", ["inverse", "direct", "fast"])
+def test_klt_matches_reference_build_on_synthetic(oracle, reflib, variant, method):
+    """Bit-for-bit agreement with the reference's own .cpp on a seeded synthetic pair incl. border features."""
+    ref, cur, uv, _ = S.make_pair(240, 320, 120, pair_id=3, border=12)
+    rng = np.random.default_rng(9)
+    uv = np.concatenate([uv, np.stack([rng.uniform(-4, 324, 40), rng.uniform(-4, 244, 40)], 1).astype(np.float32)])
+    rl, cl = oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3)
+    for half, lum, single in [(6, False, False), (4, True, False), (7, False, True)]:
+        p = po.make_params(variant, method, half=half, half_col=half + 1, max_points=1000, luminance=lum,
+                           predict=(0.9995, -0.03, 0.03, 0.9995) if single else (1, 0, 0, 1))
+        a = reflib.klt_track(p, rl, cl, uv, single_level=single)
+        b = oracle.klt_track(p, rl, cl, uv, single_level=single)
+        assert a[0] == b[0] and (a[2] == b[2]).all() and bits_equal(a[1], b[1])
+
+
+def test_klt_entry_semantics(oracle):
+    """optical_flow.cpp:8-19 + basic_klt.cpp:9,15: empty input, size mismatches, skipped statuses, the point cap."""
+    ref, cur, uv, _ = S.make_pair(120, 160, 30, pair_id=5, border=10)
+    rl, cl = oracle.pyramid_build(ref, 2), oracle.pyramid_build(cur, 2)
+    p = po.make_params("basic", "fast", half=4, max_points=10)
+    ok, _, _ = oracle.klt_track(p, rl, cl, np.zeros((0, 2), np.float32))
+    assert not ok
+    # wrong-sized cur/status are reset; features beyond the cap keep cur = ref and kNotTracked
+    ok, out, st = oracle.klt_track(p, rl, cl, uv, cur_uv=uv[:5] + 1, status=np.full(3, 4, np.uint8))
+    assert ok and bits_equal(out[10:], uv[10:]) and (st[10:] == 0).all() and (st[:10] != 0).any()
+    # entries > kTracked are left untouched
+    st_in = np.zeros(30, np.uint8)
+    st_in[2], st_in[4] = 3, 2
+    pred = uv + np.float32(0.5)
+    ok, out, st = oracle.klt_track(p, rl, cl, uv, cur_uv=pred, status=st_in)
+    assert st[2] == 3 and st[4] == 2 and bits_equal(out[[2, 4]], pred[[2, 4]])
+
+
+def test_klt_recovers_known_shift(oracle):
+    """Property: a pure integer translation is recovered by every variant (status kTracked, error << 1 px)."""
+    ref = S.make_image(200, 260, seed=77)
+    cur = np.roll(np.roll(ref, 3, axis=0), -2, axis=1)
+    uv = S.detect_features(ref, 60, seed=1, border=40, border_fraction=0.0)
+    rl, cl = oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3)
+    for v in ("basic", "affine", "lssd"):
+        for m in ("inverse", "direct", "fast"):
+            ok, out, st = oracle.klt_track(po.make_params(v, m, half=7), rl, cl, uv)
+            good = st == 1
+            assert good.mean() > 0.8, (v, m, good.mean())
+            err = np.abs(out[good] - (uv[good] + np.array([-2.0, 3.0], np.float32)))
+            assert np.median(err) < 0.15, (v, m, np.median(err))
+
+
+def test_ldlt_restatement(oracle):
+    """SURVEY App. A.5 known answers: zero matrix -> 0, rank-1 [[4,2],[2,1]] b=(2,1) -> (0.5, 0); random SPD residuals."""
+    import ctypes as C
+    f = oracle.lib.ftko_ldlt_solve
+    f.restype = None
+
+    def solve(A, b):
+        A = np.ascontiguousarray(A, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        x = np.zeros(len(b), np.float32)
+        f(C.c_int32(len(b)), A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p))
+        return x
+
+    assert (solve(np.zeros((2, 2)), [1, 2]) == 0).all()
+    assert np.allclose(solve([[4, 2], [2, 1]], [2, 1]), [0.5, 0.0])
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 6):
+        for _ in range(200):
+            M = rng.normal(size=(n, n + 2)).astype(np.float32)
+            A = (M @ M.T).astype(np.float32)
+            b = rng.normal(size=n).astype(np.float32)
+            x = solve(A, b)
+            assert np.linalg.norm(A.astype(np.float64) @ x - b) <= 2e-3 * (1 + np.linalg.norm(b)) * np.linalg.cond(A.astype(np.float64)) ** 0.5
+
+
+def test_matchers_match_golden(oracle, matcher_golden):
+    m = matcher_golden
+    ok, idx = oracle.match_brief_force(m["brief_ref"], m["brief_cur"], 60.0)
+    assert ok and (idx == m["brief_force_idx"]).all()
+    ok, idx = oracle.match_brief_nearby(m["brief_ref"], m["brief_cur"], m["brief_pred"], m["brief_pos"], 50, 50, 60.0)
+    assert ok and (idx == m["brief_nearby_idx"]).all()
+    ok, muv, mst = oracle.match_brief_nearby_uv(m["brief_ref"], m["brief_cur"], m["brief_pred"], m["brief_pos"], 50, 50, 60.0)
+    assert (mst == m["brief_nearby_st"]).all() and bits_equal(muv[mst == 1], m["brief_nearby_uv"][mst == 1])
+    ok, idx = oracle.match_cosine_force(m["float_ref"], m["float_cur"], 0.1)
+    assert ok and (idx == m["float_force_idx"]).all()
+    ok, idx = oracle.match_cosine_nearby(m["float_ref"], m["float_cur"], m["float_pred"], m["float_pos"], 50, 50, 0.3)
+    assert ok and (idx == m["float_nearby_idx"]).all()
+
+
+def test_matchers_vs_reference_build(oracle, reflib):
+    rb, cb, pred, pos, _ = S.make_brief_sets(150, 170, seed=21)
+    for args in [(rb, cb, 60.0), (rb, cb, 200.0), (rb[:0], cb, 60.0)]:
+        if args[0].shape[0] == 0:
+            continue
+        assert (oracle.match_brief_force(*args)[1] == reflib.match_brief_force(*args)[1]).all()
+    a = oracle.match_brief_nearby(rb, cb, pred, pos, 30, 45, 70.0)
+    b = reflib.match_brief_nearby(rb, cb, pred, pos, 30, 45, 70.0)
+    assert a[0] == b[0] and (a[1] == b[1]).all()
+    rf, cf = S.make_float_sets(90, 100, dim=64, seed=2)
+    assert (oracle.match_cosine_force(rf, cf, 0.2)[1] == reflib.match_cosine_force(rf, cf, 0.2)[1]).all()
+
+
+def test_matcher_semantics(oracle):
+    """Strict '<' keeps the lowest j on ties; nothing matches at the default max distance 0; preset indices survive."""
+    rng = np.random.default_rng(4)
+    cur = rng.integers(0, 2, (6, 64), dtype=np.uint8)
+    cur[4] = cur[1]
+    ref = cur[[1, 3]].copy()
+    ok, idx = oracle.match_brief_force(ref, cur, 10.0)
+    assert ok and list(idx) == [1, 3]
+    ok, idx = oracle.match_brief_force(ref, cur, 0.0)
+    assert ok and list(idx) == [-1, -1]
+    ok, idx = oracle.match_brief_force(ref, cur, 0.0, idx=np.array([5, 2], np.int32))
+    assert list(idx) == [5, 2]
+    ok, _ = oracle.match_brief_force(ref, cur[:0].reshape(0, 64), 10.0)
+    assert not ok
+    # nearby: the window gate excludes the exact duplicate, a farther candidate inside the window wins
+    pos = np.array([[0, 0], [100, 100], [10, 10], [50, 50], [12, 12], [300, 300]], np.float32)
+    pred = np.array([[11, 11], [52, 52]], np.float32)
+    ok, idx = oracle.match_brief_nearby(ref, cur, pred, pos, 5, 5, 64.0)
+    assert list(idx) == [4, 3]
