@@ -373,7 +373,7 @@ class BriefMatcher(DescriptorMatcher):
 
     def _prep(self, d):
         d = np.ascontiguousarray(d, dtype=np.uint32)
-        return d.reshape(d.shape[0], -1) if d.ndim == 2 else d.reshape(0, 8)
+        return d if d.ndim == 2 else d.reshape(0, 8)
 
     def _force(self, ref, cur, idx, flags):
         o = self._options
@@ -395,7 +395,7 @@ class CosineMatcher(DescriptorMatcher):
 
     def _prep(self, d):
         d = np.ascontiguousarray(d, dtype=np.float32)
-        return d.reshape(d.shape[0], -1) if d.ndim == 2 else d.reshape(0, 256)
+        return d if d.ndim == 2 else d.reshape(0, 256)
 
     def _force(self, ref, cur, idx, flags):
         o = self._options
