@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+Metric (BASELINE.json): tracked features/sec (4-level KLT, 752x480), whole job over N GPUs.
+Workload: the batch shape of BASELINE configs[1] (1000 frame pairs x 2000 features per GPU, 752x480, 4 pyramid levels),
+tracked with the north-star tracker (basic KLT, kInverse, 15x15 patches).  One "step" = pyramid construction of all
+2000 images of the batch + tracking of all 2 000 000 features.  Frame pairs shard across GPUs with no collective on
+the data path (weak scaling: every rank owns its own 1000 pairs).
+
+  value : device-resident throughput (images + features already in HBM), CUDA-event timed on the library's stream
+  e2e   : same metric through the C ABI with HOST buffers (pinned): H2D of the images and features and D2H of the
+          results are inside the timed region
+  --impl reference : the reference's own CPU implementation (oracle/_ref, built from the reference's sources) on all
+          host cores, bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS, LEVELS = 480, 752, 4
+HALF = 7
+PAIRS_PER_GPU = 1000
+FEATURES_PER_PAIR = 2000
+UNIQUE_PAIRS = 8  # synthetic pairs generated; the batch tiles them (distinct HBM addresses, identical content)
+METRIC = "tracked features/sec (4-lvl KLT, 752x480)"
+UNIT = "features/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
+    ap.add_argument("--features", type=int, default=FEATURES_PER_PAIR)
+    ap.add_argument("--variant", default="basic")
+    ap.add_argument("--method", default="inverse")
+    ap.add_argument("--half", type=int, default=HALF)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (matchers, other trackers)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {
+        "workload": f"BASELINE configs[1] batch shape: {args.pairs} frame pairs/GPU x {args.features} features, {COLS}x{ROWS}, {LEVELS}-level pyramid; "
+                    f"tracker = {args.variant} KLT {args.method}, {2 * args.half + 1}x{2 * args.half + 1} patches (north-star target config); "
+                    "step = pyramid build of both frames + TrackFeatures for every pair",
+        "pairs_per_gpu": args.pairs, "features_per_pair": args.features, "image": [ROWS, COLS], "levels": LEVELS,
+        "patch": 2 * args.half + 1, "variant": args.variant, "method": args.method,
+        "l2_policy": "inputs larger than L2 (pyramid batch ~1 GB per GPU vs 126 MB L2)",
+        "sharding": "frame pairs split across ranks, no collective on the data path",
+    }
+
+
+def make_unique_pairs(n_unique, n_features):
+    from feature_tracker_b200 import synthetic as S
+    refs, curs, uvs = [], [], []
+    for p in range(n_unique):
+        ref, cur, uv, _ = S.make_pair(ROWS, COLS, n_features, pair_id=p)
+        refs.append(ref), curs.append(cur), uvs.append(uv)
+    return refs, curs, uvs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline (the only place bench.py touches oracle/): the reference's own code on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_checker():
+    from oracle import pyoracle as po
+    if os.path.exists(po.REF_SO) or os.path.isdir(po.REFERENCE_ROOT):
+        try:
+            return po.RefLib(), "reference"
+        except Exception:
+            pass
+    return po.OracleLib(), "port"
+
+
+def cpu_track_sample(lib, params, refs, curs, uvs, n_pairs, threads):
+    """Tracks n_pairs pairs (cycling over the unique ones) on `threads` host threads; returns (seconds, features)."""
+    jobs = list(range(n_pairs))
+    lock = threading.Lock()
+    done = [0]
+
+    def worker():
+        while True:
+            with lock:
+                if not jobs:
+                    return
+                p = jobs.pop()
+            u = p % len(refs)
+            ok, _, _ = lib.pyramid_and_track(params, LEVELS, refs[u], curs[u], uvs[u])
+            assert ok
+            with lock:
+                done[0] += len(uvs[u])
+
+    ts = [threading.Thread(target=worker) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return time.perf_counter() - t0, done[0]
+
+
+def run_reference(args):
+    from oracle import pyoracle as po
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind = cpu_checker()
+    cores = os.cpu_count() or 1
+    n_feat = args.features
+    refs, curs, uvs = make_unique_pairs(min(UNIQUE_PAIRS, 4), n_feat)
+    params = po.make_params(args.variant, args.method, half=args.half, max_points=max(500, n_feat))
+    # bounded sample: ~cores pairs per step (about cores * 0.3 s of CPU work for basic inverse 15x15 x 2000 features)
+    sample_pairs = max(1, min(cores, 64))
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_track_sample(lib, params, refs, curs, uvs, min(sample_pairs, cores), cores)
+    times, feats = [], 0
+    for _ in range(args.steps):
+        dt, nf = cpu_track_sample(lib, params, refs, curs, uvs, sample_pairs, cores)
+        times.append(dt)
+        feats = nf
+    total = sum(times)
+    value = feats * len(times) / total
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{sample_pairs} frame pairs x {n_feat} features per step (pyramid x2 + TrackFeatures), one tracker object per thread"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = the upper half of the samples (idle samples before/after the timed region drop out)
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import feature_tracker_b200 as ft
+    from feature_tracker_b200 import _capi
+    from feature_tracker_b200.api import lib as ftk_lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = ft.Context(local_rank)
+    L = ftk_lib()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    n_pairs, n_feat = args.pairs, args.features
+    refs, curs, uvs = make_unique_pairs(UNIQUE_PAIRS, n_feat)
+    # this rank's shard: pairs [rank*n_pairs, (rank+1)*n_pairs) of the global batch, cycling over the unique pairs
+    uniq = [(rank * n_pairs + p) % UNIQUE_PAIRS for p in range(n_pairs)]
+    plane = ROWS * COLS
+    host_images = torch.empty((2 * n_pairs, ROWS, COLS), dtype=torch.uint8).pin_memory()
+    hi = host_images.numpy()
+    for p, u in enumerate(uniq):
+        hi[p] = refs[u]
+        hi[n_pairs + p] = curs[u]
+    n_total = n_pairs * n_feat
+    host_ref_uv = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
+    host_cur_uv = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
+    host_status = torch.empty((n_total,), dtype=torch.uint8).pin_memory()
+    hr = host_ref_uv.numpy()
+    for p, u in enumerate(uniq):
+        hr[p * n_feat:(p + 1) * n_feat] = uvs[u]
+    offsets = (np.arange(n_pairs + 1, dtype=np.int32) * n_feat)
+    ref_idx = np.arange(n_pairs, dtype=np.int32)
+    cur_idx = ref_idx + n_pairs
+
+    pyr = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, 2 * n_pairs)
+    klt = {"basic": ft.OpticalFlowBasicKlt, "affine": ft.OpticalFlowAffineKlt, "lssd": ft.OpticalFlowLssdKlt}[args.variant](ctx)
+    o = klt.options()
+    o.kPatchRowHalfSize = o.kPatchColHalfSize = args.half
+    o.kMethod = {"inverse": ft.OpticalFlowMethod.kInverse, "direct": ft.OpticalFlowMethod.kDirect, "fast": ft.OpticalFlowMethod.kFast}[args.method]
+    o.kMaxTrackPointsNumber = max(500, n_feat)
+    params = klt._params()
+
+    # device-resident inputs for `value`
+    d_ref_uv = torch.from_numpy(hr).to(f"cuda:{local_rank}")
+    d_cur_uv = torch.empty_like(d_ref_uv)
+    d_status = torch.empty((n_total,), dtype=torch.uint8, device=d_ref_uv.device)
+    d_offsets = torch.from_numpy(offsets).to(d_ref_uv.device)
+    d_ref_idx = torch.from_numpy(ref_idx).to(d_ref_uv.device)
+    d_cur_idx = torch.from_numpy(cur_idx).to(d_ref_uv.device)
+    pyr.set_images_ptr(host_images.data_ptr(), 2 * n_pairs)
+    ctx.synchronize()
+    vp = C.c_void_p
+
+    def step_resident():
+        ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
+        flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(d_ref_idx.data_ptr()), vp(d_cur_idx.data_ptr()),
+                                  vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(d_cur_uv.data_ptr()), vp(d_status.data_ptr()), flags))
+
+    def step_e2e():
+        pyr.set_images_ptr(host_images.data_ptr(), 2 * n_pairs)
+        ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
+        flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(ref_idx.ctypes.data), vp(cur_idx.ctypes.data),
+                                  vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()), vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, per_kernel=False):
+        """Times `steps` calls with CUDA events on the library's stream, bracketed by barrier + synchronize; max over ranks."""
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ctx.kernel_launches
+        ev0.record(stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=d_ref_uv.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.kernel_launches - launches0
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    tracked_per_step = n_total * world
+    value = tracked_per_step * args.steps / (ms * 1e-3)
+
+    # per-kernel split (CUDA events around each stage, same stream), for the roofline objects
+    def pyramid_only():
+        ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
+
+    def klt_only():
+        flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(d_ref_idx.data_ptr()), vp(d_cur_idx.data_ptr()),
+                                  vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(d_cur_uv.data_ptr()), vp(d_status.data_ptr()), flags))
+
+    ms_pyr, _ = timed(pyramid_only, args.steps)
+    ms_klt, _ = timed(klt_only, args.steps)
+    status_host = d_status.cpu().numpy()
+
+    # end to end through the C ABI with host buffers
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    e2e_value = tracked_per_step * args.steps / (ms_e2e * 1e-3)
+    h2d = 2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4
+    d2h = n_total * 9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    # pyramid: algorithmic bytes = read H*W + write H*W*(1/4+1/16+1/64) per image (479 400 B per 752x480 image)
+    pyr_bytes = sum((ROWS >> l) * (COLS >> l) for l in range(LEVELS)) * 2 * n_pairs
+    pyr_gbs = pyr_bytes / (ms_pyr / args.steps * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "tracked_fraction": float((status_host == 1).mean()),
+        "kernel_ms": {"pyramid": ms_pyr / args.steps, "klt": ms_klt / args.steps},
+        "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak, "traffic": None,
+                             "peak_source": hbm_src, "algorithmic_bytes_per_launch": pyr_bytes},
+    }
+
+    if not args.no_cpu_baseline:
+        from oracle import pyoracle as po
+        lib_cpu, kind = cpu_checker()
+        cores = os.cpu_count() or 1
+        cparams = po.make_params(args.variant, args.method, half=args.half, max_points=max(500, n_feat))
+        sample_pairs = max(1, min(cores, 64))
+        cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, min(sample_pairs, cores), cores)
+        dt, nf = cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, sample_pairs, cores)
+        dt1, nf1 = cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, 1, 1)
+        line["cpu_baseline"] = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                                "sample": f"{sample_pairs} frame pairs x {n_feat} features (pyramid x2 + TrackFeatures), one tracker object per thread",
+                                "single_thread_value": nf1 / dt1}
+        # KLT roofline: algorithmic flops from the oracle's iteration trace on the unique pairs (the batch tiles them)
+        oracle = po.OracleLib()
+        iters = 0
+        for u in range(UNIQUE_PAIRS):
+            rl, cl = oracle.pyramid_build(refs[u], LEVELS), oracle.pyramid_build(curs[u], LEVELS)
+            it = np.zeros(n_feat, np.int32)
+            levels = len(rl)
+            rows = np.array([a.shape[0] for a in rl], np.int32)
+            cols = np.array([a.shape[1] for a in rl], np.int32)
+            PtrArr = C.POINTER(C.c_uint8) * levels
+            rp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in rl])
+            cp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in cl])
+            cu = np.zeros((n_feat, 2), np.float32)
+            st = np.zeros(n_feat, np.uint8)
+            f = oracle.lib.ftko_klt_track_traced
+            f.restype = C.c_int
+            f(C.byref(cparams), C.c_int32(levels), rp, cp, rows.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), C.c_int32(n_feat),
+              uvs[u].ctypes.data_as(C.c_void_p), cu.ctypes.data_as(C.c_void_p), C.c_int32(0), st.ctypes.data_as(C.c_void_p), C.c_int32(0), C.c_int32(0),
+              it.ctypes.data_as(C.c_void_p))
+            iters += int(it.sum()) * sum(1 for x in uniq if x == u)
+            # at-scale parity spot check: the GPU's results for the first tile of this unique pair
+            p0 = uniq.index(u)
+            got_st = status_host[p0 * n_feat:(p0 + 1) * n_feat]
+            got_uv = d_cur_uv[p0 * n_feat:(p0 + 1) * n_feat].cpu().numpy()
+            line.setdefault("parity_check", {"pairs": 0, "status_mismatch": 0, "position_bits_mismatch": 0})
+            line["parity_check"]["pairs"] += 1
+            line["parity_check"]["status_mismatch"] += int((got_st != st).sum())
+            line["parity_check"]["position_bits_mismatch"] += int((got_uv.view(np.uint32) != cu.view(np.uint32)).any(1).sum())
+        P = (2 * args.half + 1) ** 2
+        # SURVEY 8(d), basic hoisted form: per iteration 20*P flop, per feature-level setup ((2h+3)^2-4)*15 + 8*P flop
+        flops = iters * 20.0 * P + n_total * LEVELS * ((((2 * args.half + 3) ** 2) - 4) * 15.0 + 8.0 * P)
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        tfs = flops / (ms_klt / args.steps * 1e-3) / 1e12
+        line["roofline"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
+                            "frac": tfs / fp32_peak, "traffic": None,
+                            "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
+                            "algorithmic_flops_per_launch": flops, "patch_iterations_per_feature": iters / n_total, "kernel": "KltKernel"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,9 @@ __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G,
     }
     l.total_bytes = 4 * (l.term_floats + l.ex_floats + 2 * l.p_floats + l.curp_floats) + l.exv_bytes + l.curv_bytes;
     l.total_bytes = RoundUp(l.total_bytes, 16);
+    // Groups of one warp must start on different banks: make the group stride (in words) congruent to G modulo 32.
+    if (G < 32)
+        while ((l.total_bytes / 4) % 32 != G % 32) l.total_bytes += 16;
     return l;
 }
 
