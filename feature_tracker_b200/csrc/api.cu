@@ -2,6 +2,7 @@
 // marshalling (H2D / launch / D2H) around the kernels in pyramid.cu, klt.cu, klt_basic_fastpath.cu and match.cu.
 // There is deliberately no CPU fallback anywhere in this library.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -106,6 +107,10 @@ int ftk_create(int device, ftk_context **out) {
     ftk_context *ctx = new ftk_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    {
+        const char *e = getenv("FTK_DISABLE_FASTPATH");
+        ctx->use_fast_paths = !(e && e[0] == '1');
+    }
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
@@ -198,9 +203,15 @@ int ftk_pyramid_set_images(ftk_context *ctx, ftk_pyramid *pyr, int32_t first, in
     const cudaMemcpyKind kind = (flags & FTK_FLAG_DEVICE_POINTERS) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     uint8_t *dst = const_cast<uint8_t *>(v.base[0]) + first * v.image_stride[0];
     const size_t plane = static_cast<size_t>(v.rows[0]) * v.cols[0];
-    // One strided 2-D copy per image (rows of `cols` bytes into rows of `pitch` bytes).
-    for (int i = 0; i < count; ++i) {
-        FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst + i * v.image_stride[0], v.pitch[0], images + i * plane, v.cols[0], v.cols[0], v.rows[0], kind, ctx->stream));
+    if (v.pitch[0] == v.cols[0]) {
+        // Rows are already pitch-sized: one 2-D copy whose "rows" are whole images (src stride = plane, dst stride = image_stride).
+        FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst, v.image_stride[0], images, plane, plane, count, kind, ctx->stream));
+    } else {
+        // One strided 2-D copy per image (rows of `cols` bytes into rows of `pitch` bytes).
+        for (int i = 0; i < count; ++i) {
+            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst + i * v.image_stride[0], v.pitch[0], images + i * plane, v.cols[0], v.cols[0], v.rows[0], kind,
+                                                  ctx->stream));
+        }
     }
     return FTK_OK;
 }

@@ -48,6 +48,7 @@ struct ftk_context {
     std::string error;
     uint64_t launches = 0;
     int sm_count = 0;
+    bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
     FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
@@ -89,6 +90,8 @@ struct KltLaunch {
 };
 int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int n_features, int *d_feat_pair);
 int LaunchKltTrack(ftk_context *ctx, const KltLaunch &launch);
+// klt_basic_fastpath.cu: FTK_ERR_UNSUPPORTED when no specialisation covers the configuration
+int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &launch);
 
 // match.cu
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);

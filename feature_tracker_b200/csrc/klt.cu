@@ -992,6 +992,10 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
     geo.ec = geo.pc + 2;
     geo.esize = geo.er * geo.ec;
     if (geo.hr < 0 || geo.hc < 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "negative patch half size");
+    if (ctx->use_fast_paths) {
+        const int rc = LaunchKltBasicFastPath(ctx, a);
+        if (rc != FTK_ERR_UNSUPPORTED) return rc;
+    }
     switch (a.p.variant) {
         case FTK_VARIANT_BASIC:
             if (geo.psize <= 8 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 8>(ctx, a, geo);

@@ -1,0 +1,369 @@
+// K2 fast path: basic (2-DoF) KLT, kInverse method, patches up to 16 columns wide (13x13, 15x15 instantiated).
+// Same results, bit for bit, as the generic kernel in klt.cu and as the reference
+// (src/optical_flow_tracker/basic_klt/optical_flow_basic_klt.cpp:7-181); only the work decomposition differs.
+//
+// Mapping on sm_100a
+//   * 16 lanes per feature, lane = patch column; two features per warp; the row loop is fully unrolled.
+//   * The reference recomputes, every Gauss-Newton iteration, five bilinear samples of the REFERENCE image per pixel
+//     (:127-134).  They do not depend on the iteration, so they are evaluated once per pyramid level and kept in
+//     registers (fx, fy, I_ref per row).  The 2x2 Hessian over the "all reference samples valid" mask is also built
+//     once per level; it is rebuilt only in iterations whose current-image validity mask differs (border features),
+//     which reproduces the reference's per-iteration Hessian exactly because the summands and their order are equal.
+//   * floor / fraction / bounds test of a sample position are separable in row and column: each lane keeps its column
+//     entries in registers and the row entries of the level live in a small shared table, so a bilinear sample costs
+//     4 weight products + 4 products + 3 sums.  Every product and sum is the same fp32 operation the reference
+//     performs, in the same order.
+//   * Pixel bytes are fetched once into a register strip that rolls down the patch (2 new bytes per pixel for the
+//     current image, 4 for the reference image) whenever the integer bases advance regularly, which is the case unless
+//     a coordinate rounds across an integer or the patch touches the image border; otherwise the group falls back to
+//     loading every sample's four bytes directly.
+//   * Normal-equation sums use the chain scheme of klt_device.cuh: lane k of a group folds the k-th term of the 16
+//     pixels of a row in pixel order, so the sums equal the reference's sequential sums bit for bit.
+#include "klt_device.cuh"
+
+namespace ftk {
+
+namespace {
+
+constexpr int kG = 16;
+constexpr int kThreads = 128;
+constexpr int kGroupsPerBlock = kThreads / kG;
+
+// Separable part of a bilinear sample along one axis.
+struct __align__(16) Entry {
+    int off;   // clamped integer base (columns) or clamped integer base * pitch (rows): always addressable
+    float s;   // fraction  (x - floor(x))
+    float i;   // 1 - fraction
+    int ok;    // !(x < 0 || x > n - 1)   (GrayImage::GetPixelValue bounds test)
+};
+
+__device__ __forceinline__ Entry MakeEntry(float x, int n, int scale) {
+    Entry e;
+    const float f = floorf(x);
+    e.s = fsub(x, f);
+    e.i = fsub(1.0f, e.s);
+    e.ok = !(x < 0.0f || x > static_cast<float>(n - 1));
+    int b = static_cast<int>(f);  // for in-bounds x: truncation == floor == the reference's static_cast<int32_t>
+    b = min(max(b, 0), n - 1);
+    e.off = b * scale;
+    return e;
+}
+
+// ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11 -- GrayImage::GetPixelValueNoCheck(float, float).
+__device__ __forceinline__ float Bilerp(const Entry &R, const Entry &C, float p00, float p01, float p10, float p11) {
+    return fadd(fadd(fadd(fmul(fmul(C.i, R.i), p00), fmul(fmul(C.s, R.i), p01)), fmul(fmul(C.i, R.s), p10)), fmul(fmul(C.s, R.s), p11));
+}
+
+__device__ __forceinline__ float LoadPx(const uint8_t *p) {
+    // cvt.rn.f32.s32 keeps the conversion on the ALU pipe (I2FP) instead of the quarter-rate XU pipe (I2F.U16).
+    const int v = __ldg(p);
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(v));
+    return f;
+}
+
+// A sample addressed through (row entry, column entry): loads its four bytes directly.
+__device__ __forceinline__ float SampleDirect(const uint8_t *img, int pitch, const Entry &R, const Entry &C) {
+    const uint8_t *p = img + R.off + C.off;
+    return Bilerp(R, C, LoadPx(p), LoadPx(p + 1), LoadPx(p + pitch), LoadPx(p + pitch + 1));
+}
+
+template <int PR, int PC>
+struct GroupSmem {
+    float term[5 * (kG + 4)];
+    Entry rows[3 * PR];  // setup: {R0, Rm, Rp} per patch row; iteration: the first PR entries
+    float fx[PR][kG], fy[PR][kG], iref[PR][kG];  // per-level reference gradients / samples, [patch row][lane]
+    static constexpr int kRawWords = 5 * (kG + 4) + 4 * 3 * PR + 3 * PR * kG;
+    // pad the group stride to 16 (mod 32) words so the two groups of a warp hit different banks
+    static constexpr int kPad = ((16 - kRawWords % 32) + 32) % 32;
+    float pad[kPad == 0 ? 32 : kPad];
+};
+
+// The two 16-lane groups of a warp always execute the same instruction stream (a finished or idle group keeps
+// computing on clamped, addressable data and simply discards its results), so every vote / shuffle / barrier below is
+// a cheap full-warp one.
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct Lanes {
+    int lane;            // 0..15 inside the group
+    int base;            // 0 or 16
+    unsigned mask;       // the group's 16 lanes
+    __device__ __forceinline__ int count(bool pred) const { return __popc(__ballot_sync(kFull, pred) & mask); }
+    __device__ __forceinline__ bool any(bool pred) const { return (__ballot_sync(kFull, pred) & mask) != 0u; }
+    __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(kFull, v, base + src); }
+};
+
+// Lane k < K of each group folds the k-th term of the group's 16 pixels in pixel order (see klt_device.cuh Chain).
+template <int K>
+__device__ __forceinline__ void Fold(float *term, const Lanes &g, float &acc) {
+    __syncwarp();
+    if (g.lane < K) {
+        const float4 *t4 = reinterpret_cast<const float4 *>(term + g.lane * (kG + 4));
+#pragma unroll
+        for (int q = 0; q < kG / 4; ++q) {
+            const float4 v = t4[q];
+            acc = fadd(acc, v.x);
+            acc = fadd(acc, v.y);
+            acc = fadd(acc, v.z);
+            acc = fadd(acc, v.w);
+        }
+    }
+    __syncwarp();
+}
+
+// Reference samples of one pyramid level -> fx, fy, I_ref per patch row (shared), validity mask, 3 Hessian chains.
+// The row loops are deliberately NOT unrolled: the fully unrolled kernel overflowed the instruction cache
+// (ncu: 12 "no_instruction" stall cycles per issued instruction).
+template <int PR, bool REGULAR, typename Smem>
+__device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes &g, const Entry &C0, const Entry &Cm, const Entry &Cp,
+                                          bool cols_ok, unsigned &refmask, float &acc) {
+    // strip rows s0..s3: pixels (rb + j, cb + i), rb = base(Rm of the current patch row), cb = base(Cm)
+    float s0[4], s1[4], s2[4], s3[4];
+    const uint8_t *p = ref.p + Cm.off + sm.rows[1].off;  // row rb of patch row 0
+    if (REGULAR) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s0[i] = LoadPx(p + i);
+        p += ref.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s1[i] = LoadPx(p + i);
+        p += ref.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
+    }
+#pragma unroll 1
+    for (int r = 0; r < PR; ++r) {
+        const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
+        float v0, v1, v2, v3, v4;
+        if (REGULAR) {
+            p += ref.pitch;  // the new bottom row of the strip: base(Rp) + 1
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s3[i] = LoadPx(p + i);
+            v0 = Bilerp(R0, Cm, s1[0], s1[1], s2[0], s2[1]);  // (row_i, col_i - 1)
+            v1 = Bilerp(R0, Cp, s1[2], s1[3], s2[2], s2[3]);  // (row_i, col_i + 1)
+            v2 = Bilerp(Rm, C0, s0[1], s0[2], s1[1], s1[2]);  // (row_i - 1, col_i)
+            v3 = Bilerp(Rp, C0, s2[1], s2[2], s3[1], s3[2]);  // (row_i + 1, col_i)
+            v4 = Bilerp(R0, C0, s1[1], s1[2], s2[1], s2[2]);  // (row_i, col_i)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s0[i] = s1[i];
+                s1[i] = s2[i];
+                s2[i] = s3[i];
+            }
+        } else {
+            v0 = SampleDirect(ref.p, ref.pitch, R0, Cm);
+            v1 = SampleDirect(ref.p, ref.pitch, R0, Cp);
+            v2 = SampleDirect(ref.p, ref.pitch, Rm, C0);
+            v3 = SampleDirect(ref.p, ref.pitch, Rp, C0);
+            v4 = SampleDirect(ref.p, ref.pitch, R0, C0);
+        }
+        const bool ok = cols_ok && R0.ok && Rm.ok && Rp.ok;
+        const float fx = fsub(v1, v0), fy = fsub(v3, v2);
+        sm.fx[r][g.lane] = fx;
+        sm.fy[r][g.lane] = fy;
+        sm.iref[r][g.lane] = v4;
+        refmask |= ok ? (1u << r) : 0u;
+        sm.term[0 * (kG + 4) + g.lane] = ok ? fmul(fx, fx) : 0.0f;
+        sm.term[1 * (kG + 4) + g.lane] = ok ? fmul(fx, fy) : 0.0f;
+        sm.term[2 * (kG + 4) + g.lane] = ok ? fmul(fy, fy) : 0.0f;
+        Fold<3>(sm.term, g, acc);
+    }
+}
+
+// One Gauss-Newton iteration's pass over the patch: current-image sample, residual, 2 bias chains.
+template <int PR, bool REGULAR, typename Smem>
+__device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lanes &g, const Entry &Cj, unsigned refmask, unsigned &okmask,
+                                            int &valid, float &acc) {
+    const uint8_t *p = cur.p + Cj.off + sm.rows[0].off;
+    float top0 = 0.0f, top1 = 0.0f;
+    if (REGULAR) {
+        top0 = LoadPx(p);
+        top1 = LoadPx(p + 1);
+    }
+#pragma unroll 1
+    for (int r = 0; r < PR; ++r) {
+        const Entry Rj = sm.rows[r];
+        if (!REGULAR) {
+            p = cur.p + Cj.off + Rj.off;
+            top0 = LoadPx(p);
+            top1 = LoadPx(p + 1);
+        }
+        p += cur.pitch;
+        const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
+        const float v5 = Bilerp(Rj, Cj, top0, top1, bot0, bot1);
+        top0 = bot0;
+        top1 = bot1;
+        const bool ok = ((refmask >> r) & 1u) && Rj.ok && Cj.ok;
+        const float ft = fsub(v5, sm.iref[r][g.lane]);
+        okmask |= ok ? (1u << r) : 0u;
+        sm.term[0 * (kG + 4) + g.lane] = ok ? -fmul(sm.fx[r][g.lane], ft) : 0.0f;
+        sm.term[1 * (kG + 4) + g.lane] = ok ? -fmul(sm.fy[r][g.lane], ft) : 0.0f;
+        valid += g.count(ok);
+        Fold<2>(sm.term, g, acc);
+    }
+}
+
+template <int PR, int PC>
+__global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) {
+    static_assert(PC <= kG && PR <= 32, "patch must fit one 16-lane group / one 32-bit row mask");
+    constexpr int HR = PR / 2, HC = PC / 2;
+    __shared__ GroupSmem<PR, PC> smem_all[kGroupsPerBlock];
+
+    Lanes g;
+    g.lane = threadIdx.x & (kG - 1);
+    g.base = (threadIdx.x & 31) - g.lane;
+    g.mask = 0xFFFFu << g.base;
+    const int group_in_block = threadIdx.x / kG;
+    const int f_raw = blockIdx.x * kGroupsPerBlock + group_in_block;
+    const bool exists = f_raw < a.n_features;
+    const int f = exists ? f_raw : a.n_features - 1;  // idle groups shadow the last feature and write nothing
+    GroupSmem<PR, PC> &sm = smem_all[group_in_block];
+    float *term = sm.term;
+
+    const int lane = g.lane;
+    const bool col_active = lane < PC;
+    const float dcol = static_cast<float>(lane - HC);
+
+    const int pair = a.feat_pair[f];
+    const int local = f - a.feat_offsets[pair];
+    const float2 ref_uv = a.ref_uv[f];
+    float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;
+    uint8_t status = a.has_status ? a.status[f] : static_cast<uint8_t>(FTK_STATUS_NOT_TRACKED);
+    // basic_klt.cpp:9,12,15: only the first kMaxTrackPointsNumber features, never re-track failed ones
+    const bool tracked = exists && static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
+
+    if (__any_sync(kFull, tracked)) {
+        const int ref_image = a.ref_image ? a.ref_image[pair] : pair;
+        const int cur_image = a.cur_image ? a.cur_image[pair] : pair;
+        const int levels = a.single_level ? 1 : a.ref.levels;  // TrackSingleLevel (basic_klt.cpp:59-86) == one level, scale 1
+        const float scale = static_cast<float>(1 << (levels - 1));
+        float ref_x = fdiv(ref_uv.x, scale), ref_y = fdiv(ref_uv.y, scale);
+        float cur_x = fdiv(cur_uv.x, scale), cur_y = fdiv(cur_uv.y, scale);
+
+        for (int level = levels - 1; level > -1; --level) {
+            const Img ref = LevelImage(a.ref, ref_image, level), cur = LevelImage(a.cur, cur_image, level);
+
+            // ================= per-level setup: reference samples, gradients, full-mask Hessian =================
+            unsigned refmask = 0;  // bit r: all five reference samples of my pixel in patch row r are inside the image
+            float acc = 0.0f;
+            {
+                const float col_i = fadd(dcol, ref_x);
+                const Entry C0 = MakeEntry(col_i, ref.cols, 1);
+                const Entry Cm = MakeEntry(fsub(col_i, 1.0f), ref.cols, 1);
+                const Entry Cp = MakeEntry(fadd(col_i, 1.0f), ref.cols, 1);
+                __syncwarp();
+                if (lane < PR) {
+                    const float row_i = fadd(static_cast<float>(lane - HR), ref_y);
+                    sm.rows[3 * lane + 0] = MakeEntry(row_i, ref.rows, ref.pitch);
+                    sm.rows[3 * lane + 1] = MakeEntry(fsub(row_i, 1.0f), ref.rows, ref.pitch);
+                    sm.rows[3 * lane + 2] = MakeEntry(fadd(row_i, 1.0f), ref.rows, ref.pitch);
+                }
+                __syncwarp();
+                // Do the integer bases advance regularly?  (lane r checks patch row r; every lane its own three columns)
+                bool regular = Cm.off == C0.off - 1 && Cp.off == C0.off + 1;
+                if (lane < PR) {
+                    const int r0 = sm.rows[3 * lane].off;
+                    regular = regular && sm.rows[3 * lane + 1].off == r0 - ref.pitch && sm.rows[3 * lane + 2].off == r0 + ref.pitch;
+                    if (lane + 1 < PR) regular = regular && sm.rows[3 * (lane + 1)].off == r0 + ref.pitch;
+                }
+                const bool cols_ok = C0.ok && Cm.ok && Cp.ok && col_active;
+                if (__all_sync(kFull, regular)) SetupRows<PR, true>(ref, sm, g, C0, Cm, Cp, cols_ok, refmask, acc);
+                else SetupRows<PR, false>(ref, sm, g, C0, Cm, Cp, cols_ok, refmask, acc);
+            }
+            const float hfull00 = g.get(acc, 0), hfull01 = g.get(acc, 1), hfull11 = g.get(acc, 2);
+
+            // ================= Gauss-Newton iterations (basic_klt.cpp:88-116) =================
+            bool running = tracked;
+            for (uint32_t iter = 0; iter < a.p.max_iteration && __any_sync(kFull, running); ++iter) {
+                const Entry Cj = MakeEntry(fadd(dcol, cur_x), cur.cols, 1);
+                __syncwarp();
+                if (lane < PR) sm.rows[lane] = MakeEntry(fadd(static_cast<float>(lane - HR), cur_y), cur.rows, cur.pitch);
+                __syncwarp();
+                bool regular = true;
+                if (lane + 1 < PR) regular = sm.rows[lane + 1].off == sm.rows[lane].off + cur.pitch;
+
+                unsigned okmask = 0;
+                int valid = 0;
+                acc = 0.0f;
+                if (__all_sync(kFull, regular)) IterateRows<PR, true>(cur, sm, g, Cj, refmask, okmask, valid, acc);
+                else IterateRows<PR, false>(cur, sm, g, Cj, refmask, okmask, valid, acc);
+                const float b[2] = {g.get(acc, 0), g.get(acc, 1)};
+
+                float h00 = hfull00, h01 = hfull01, h11 = hfull11;
+                const bool mask_changed = g.any(okmask != refmask);
+                if (__any_sync(kFull, mask_changed && running)) {
+                    // Some reference-valid pixel left the current image: this iteration's Hessian runs over fewer pixels.
+                    acc = 0.0f;
+#pragma unroll 1
+                    for (int r = 0; r < PR; ++r) {
+                        const bool ok = (okmask >> r) & 1u;
+                        const float fx = sm.fx[r][lane], fy = sm.fy[r][lane];
+                        term[0 * (kG + 4) + lane] = ok ? fmul(fx, fx) : 0.0f;
+                        term[1 * (kG + 4) + lane] = ok ? fmul(fx, fy) : 0.0f;
+                        term[2 * (kG + 4) + lane] = ok ? fmul(fy, fy) : 0.0f;
+                        Fold<3>(term, g, acc);
+                    }
+                    const float n00 = g.get(acc, 0), n01 = g.get(acc, 1), n11 = g.get(acc, 2);
+                    if (mask_changed) h00 = n00, h01 = n01, h11 = n11;
+                }
+
+                if (running) {
+                    if (valid == 0) {
+                        running = false;  // BREAK_IF(ConstructIncrementalFunction(...) == 0)
+                    } else {
+                        const float A[2][2] = {{h00, h01}, {h01, h11}};
+                        float v[2];
+                        LdltSolve<2>(A, b, v);
+                        if (v[0] != v[0] || v[1] != v[1]) {
+                            status = FTK_STATUS_NUMERIC_ERROR;
+                            running = false;
+                        } else {
+                            cur_x = fadd(cur_x, v[0]);
+                            cur_y = fadd(cur_y, v[1]);
+                            if (IsOutside(cur, cur_x, cur_y)) {
+                                status = FTK_STATUS_OUTSIDE;
+                                running = false;
+                            } else if (fadd(fmul(v[0], v[0]), fmul(v[1], v[1])) < a.p.max_converge_step) {
+                                status = FTK_STATUS_TRACKED;
+                                running = false;
+                            }
+                        }
+                    }
+                }
+            }
+
+            if (level == 0) break;
+            ref_x = fmul(ref_x, 2.0f), ref_y = fmul(ref_y, 2.0f);
+            cur_x = fmul(cur_x, 2.0f), cur_y = fmul(cur_y, 2.0f);
+        }
+        if (tracked) {
+            cur_uv = make_float2(cur_x, cur_y);
+            const Img cur0 = LevelImage(a.cur, cur_image, 0);
+            if (IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;  // basic_klt.cpp:49-53
+        }
+    }
+    if (exists && g.lane == 0) {
+        a.cur_uv[f] = cur_uv;
+        a.status[f] = status;
+    }
+}
+
+template <int PR, int PC>
+int Launch(ftk_context *ctx, const KltLaunch &a) {
+    const int blocks = (a.n_features + kGroupsPerBlock - 1) / kGroupsPerBlock;
+    BasicInverseFastKernel<PR, PC><<<blocks, kThreads, 0, ctx->stream>>>(a);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+}  // namespace
+
+// Returns FTK_ERR_UNSUPPORTED when no specialisation covers the configuration (the caller then uses the generic kernel).
+int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &a) {
+    if (a.p.variant != FTK_VARIANT_BASIC || a.p.method != FTK_METHOD_INVERSE) return FTK_ERR_UNSUPPORTED;
+    if (a.p.patch_row_half == 7 && a.p.patch_col_half == 7) return Launch<15, 15>(ctx, a);
+    if (a.p.patch_row_half == 6 && a.p.patch_col_half == 6) return Launch<13, 13>(ctx, a);
+    return FTK_ERR_UNSUPPORTED;
+}
+
+}  // namespace ftk
