@@ -31,23 +31,23 @@ constexpr int kGroupsPerBlock = kThreads / kG;
 
 // Separable part of a bilinear sample along one axis.
 struct __align__(16) Entry {
-    int off;   // clamped integer base (columns) or clamped integer base * pitch (rows): always addressable
+    int base;  // floor(x) as an integer (limited to [-64, n + 64]); for in-bounds x it is the reference's static_cast<int32_t>(x)
     float s;   // fraction  (x - floor(x))
     float i;   // 1 - fraction
     int ok;    // !(x < 0 || x > n - 1)   (GrayImage::GetPixelValue bounds test)
 };
 
-__device__ __forceinline__ Entry MakeEntry(float x, int n, int scale) {
+__device__ __forceinline__ Entry MakeEntry(float x, int n) {
     Entry e;
     const float f = floorf(x);
     e.s = fsub(x, f);
     e.i = fsub(1.0f, e.s);
     e.ok = !(x < 0.0f || x > static_cast<float>(n - 1));
-    int b = static_cast<int>(f);  // for in-bounds x: truncation == floor == the reference's static_cast<int32_t>
-    b = min(max(b, 0), n - 1);
-    e.off = b * scale;
+    e.base = min(max(static_cast<int>(f), -64), n + 64);
     return e;
 }
+
+__device__ __forceinline__ int Clamp(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11 -- GrayImage::GetPixelValueNoCheck(float, float).
 __device__ __forceinline__ float Bilerp(const Entry &R, const Entry &C, float p00, float p01, float p10, float p11) {
@@ -62,10 +62,11 @@ __device__ __forceinline__ float LoadPx(const uint8_t *p) {
     return f;
 }
 
-// A sample addressed through (row entry, column entry): loads its four bytes directly.
-__device__ __forceinline__ float SampleDirect(const uint8_t *img, int pitch, const Entry &R, const Entry &C) {
-    const uint8_t *p = img + R.off + C.off;
-    return Bilerp(R, C, LoadPx(p), LoadPx(p + 1), LoadPx(p + pitch), LoadPx(p + pitch + 1));
+// A sample addressed through (row entry, column entry): loads its four bytes directly.  Out-of-image entries are
+// clamped to an addressable pixel; their value is never used (the sample's `ok` is false).
+__device__ __forceinline__ float SampleDirect(const Img &im, const Entry &R, const Entry &C) {
+    const uint8_t *p = im.p + Clamp(R.base, 0, im.rows - 1) * im.pitch + Clamp(C.base, 0, im.cols - 1);
+    return Bilerp(R, C, LoadPx(p), LoadPx(p + 1), LoadPx(p + im.pitch), LoadPx(p + im.pitch + 1));
 }
 
 template <int PR, int PC>
@@ -117,25 +118,30 @@ __device__ __forceinline__ void Fold(float *term, const Lanes &g, float &acc) {
 template <int PR, bool REGULAR, typename Smem>
 __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes &g, const Entry &C0, const Entry &Cm, const Entry &Cp,
                                           bool cols_ok, unsigned &refmask, float &acc) {
-    // strip rows s0..s3: pixels (rb + j, cb + i), rb = base(Rm of the current patch row), cb = base(Cm)
+    // strip rows s0..s3: pixels (rb + j, cb + i), rb = base(Rm of the current patch row), cb = base(Cm).  Rows / columns
+    // outside the image are clamped to addressable ones: they only feed samples whose `ok` is false.
     float s0[4], s1[4], s2[4], s3[4];
-    const uint8_t *p = ref.p + Cm.off + sm.rows[1].off;  // row rb of patch row 0
+    const uint8_t *colp = ref.p + Clamp(Cm.base, 0, ref.cols - 3);
+    int rr = sm.rows[1].base;  // image row of strip row s0
     if (REGULAR) {
+        const uint8_t *p = colp + Clamp(rr, 0, ref.rows) * ref.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s0[i] = LoadPx(p + i);
-        p += ref.pitch;
+        p = colp + Clamp(rr + 1, 0, ref.rows) * ref.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s1[i] = LoadPx(p + i);
-        p += ref.pitch;
+        p = colp + Clamp(rr + 2, 0, ref.rows) * ref.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
+        rr += 3;
     }
 #pragma unroll 1
     for (int r = 0; r < PR; ++r) {
         const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
         float v0, v1, v2, v3, v4;
         if (REGULAR) {
-            p += ref.pitch;  // the new bottom row of the strip: base(Rp) + 1
+            const uint8_t *p = colp + Clamp(rr, 0, ref.rows) * ref.pitch;  // the new bottom row of the strip: base(Rp) + 1
+            ++rr;
 #pragma unroll
             for (int i = 0; i < 4; ++i) s3[i] = LoadPx(p + i);
             v0 = Bilerp(R0, Cm, s1[0], s1[1], s2[0], s2[1]);  // (row_i, col_i - 1)
@@ -150,11 +156,11 @@ __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes 
                 s2[i] = s3[i];
             }
         } else {
-            v0 = SampleDirect(ref.p, ref.pitch, R0, Cm);
-            v1 = SampleDirect(ref.p, ref.pitch, R0, Cp);
-            v2 = SampleDirect(ref.p, ref.pitch, Rm, C0);
-            v3 = SampleDirect(ref.p, ref.pitch, Rp, C0);
-            v4 = SampleDirect(ref.p, ref.pitch, R0, C0);
+            v0 = SampleDirect(ref, R0, Cm);
+            v1 = SampleDirect(ref, R0, Cp);
+            v2 = SampleDirect(ref, Rm, C0);
+            v3 = SampleDirect(ref, Rp, C0);
+            v4 = SampleDirect(ref, R0, C0);
         }
         const bool ok = cols_ok && R0.ok && Rm.ok && Rp.ok;
         const float fx = fsub(v1, v0), fy = fsub(v3, v2);
@@ -173,25 +179,28 @@ __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes 
 template <int PR, bool REGULAR, typename Smem>
 __device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lanes &g, const Entry &Cj, unsigned refmask, unsigned &okmask,
                                             int &valid, float &acc) {
-    const uint8_t *p = cur.p + Cj.off + sm.rows[0].off;
+    const uint8_t *colp = cur.p + Clamp(Cj.base, 0, cur.cols - 1);
+    int rr = sm.rows[0].base;  // image row of the strip's top row
     float top0 = 0.0f, top1 = 0.0f;
     if (REGULAR) {
+        const uint8_t *p = colp + Clamp(rr, 0, cur.rows) * cur.pitch;
         top0 = LoadPx(p);
         top1 = LoadPx(p + 1);
     }
 #pragma unroll 1
     for (int r = 0; r < PR; ++r) {
         const Entry Rj = sm.rows[r];
-        if (!REGULAR) {
-            p = cur.p + Cj.off + Rj.off;
-            top0 = LoadPx(p);
-            top1 = LoadPx(p + 1);
+        float v5;
+        if (REGULAR) {
+            ++rr;
+            const uint8_t *p = colp + Clamp(rr, 0, cur.rows) * cur.pitch;
+            const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
+            v5 = Bilerp(Rj, Cj, top0, top1, bot0, bot1);
+            top0 = bot0;
+            top1 = bot1;
+        } else {
+            v5 = SampleDirect(cur, Rj, Cj);
         }
-        p += cur.pitch;
-        const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
-        const float v5 = Bilerp(Rj, Cj, top0, top1, bot0, bot1);
-        top0 = bot0;
-        top1 = bot1;
         const bool ok = ((refmask >> r) & 1u) && Rj.ok && Cj.ok;
         const float ft = fsub(v5, sm.iref[r][g.lane]);
         okmask |= ok ? (1u << r) : 0u;
@@ -247,23 +256,23 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
             float acc = 0.0f;
             {
                 const float col_i = fadd(dcol, ref_x);
-                const Entry C0 = MakeEntry(col_i, ref.cols, 1);
-                const Entry Cm = MakeEntry(fsub(col_i, 1.0f), ref.cols, 1);
-                const Entry Cp = MakeEntry(fadd(col_i, 1.0f), ref.cols, 1);
+                const Entry C0 = MakeEntry(col_i, ref.cols);
+                const Entry Cm = MakeEntry(fsub(col_i, 1.0f), ref.cols);
+                const Entry Cp = MakeEntry(fadd(col_i, 1.0f), ref.cols);
                 __syncwarp();
                 if (lane < PR) {
                     const float row_i = fadd(static_cast<float>(lane - HR), ref_y);
-                    sm.rows[3 * lane + 0] = MakeEntry(row_i, ref.rows, ref.pitch);
-                    sm.rows[3 * lane + 1] = MakeEntry(fsub(row_i, 1.0f), ref.rows, ref.pitch);
-                    sm.rows[3 * lane + 2] = MakeEntry(fadd(row_i, 1.0f), ref.rows, ref.pitch);
+                    sm.rows[3 * lane + 0] = MakeEntry(row_i, ref.rows);
+                    sm.rows[3 * lane + 1] = MakeEntry(fsub(row_i, 1.0f), ref.rows);
+                    sm.rows[3 * lane + 2] = MakeEntry(fadd(row_i, 1.0f), ref.rows);
                 }
                 __syncwarp();
                 // Do the integer bases advance regularly?  (lane r checks patch row r; every lane its own three columns)
-                bool regular = Cm.off == C0.off - 1 && Cp.off == C0.off + 1;
+                bool regular = Cm.base == C0.base - 1 && Cp.base == C0.base + 1 && ref.cols >= 4 && ref.rows >= 4;
                 if (lane < PR) {
-                    const int r0 = sm.rows[3 * lane].off;
-                    regular = regular && sm.rows[3 * lane + 1].off == r0 - ref.pitch && sm.rows[3 * lane + 2].off == r0 + ref.pitch;
-                    if (lane + 1 < PR) regular = regular && sm.rows[3 * (lane + 1)].off == r0 + ref.pitch;
+                    const int r0 = sm.rows[3 * lane].base;
+                    regular = regular && sm.rows[3 * lane + 1].base == r0 - 1 && sm.rows[3 * lane + 2].base == r0 + 1;
+                    if (lane + 1 < PR) regular = regular && sm.rows[3 * (lane + 1)].base == r0 + 1;
                 }
                 const bool cols_ok = C0.ok && Cm.ok && Cp.ok && col_active;
                 if (__all_sync(kFull, regular)) SetupRows<PR, true>(ref, sm, g, C0, Cm, Cp, cols_ok, refmask, acc);
@@ -274,12 +283,12 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
             // ================= Gauss-Newton iterations (basic_klt.cpp:88-116) =================
             bool running = tracked;
             for (uint32_t iter = 0; iter < a.p.max_iteration && __any_sync(kFull, running); ++iter) {
-                const Entry Cj = MakeEntry(fadd(dcol, cur_x), cur.cols, 1);
+                const Entry Cj = MakeEntry(fadd(dcol, cur_x), cur.cols);
                 __syncwarp();
-                if (lane < PR) sm.rows[lane] = MakeEntry(fadd(static_cast<float>(lane - HR), cur_y), cur.rows, cur.pitch);
+                if (lane < PR) sm.rows[lane] = MakeEntry(fadd(static_cast<float>(lane - HR), cur_y), cur.rows);
                 __syncwarp();
                 bool regular = true;
-                if (lane + 1 < PR) regular = sm.rows[lane + 1].off == sm.rows[lane].off + cur.pitch;
+                if (lane + 1 < PR) regular = sm.rows[lane + 1].base == sm.rows[lane].base + 1;
 
                 unsigned okmask = 0;
                 int valid = 0;
