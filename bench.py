@@ -192,6 +192,93 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+def run_extras(ctx, L, torch, local_rank, steps):
+    """Secondary workloads of BASELINE.json configs[1..4] (device-resident, CUDA-event timed).  Not the headline."""
+    import feature_tracker_b200 as ft
+    from feature_tracker_b200 import _capi, synthetic as S
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    vp = C.c_void_p
+    out = {}
+
+    def timeit(fn, n):
+        fn()
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            fn()
+        e1.record(stream)
+        ctx.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # ---- KLT variants on a reduced batch (100 pairs x 2000 features; 8 pairs for the heavy LSSD shape) ----
+    def klt_case(name, variant, method, half, rows, cols, n_pairs, n_feat, unique=4):
+        pairs = [S.make_pair(rows, cols, n_feat, pair_id=100 + p) for p in range(unique)]
+        imgs = np.stack([pairs[p % unique][0] for p in range(n_pairs)] + [pairs[p % unique][1] for p in range(n_pairs)])
+        pyr = ft.ImagePyramidBatch(ctx, rows, cols, LEVELS, 2 * n_pairs)
+        pyr.SetRawImages(imgs)
+        pyr.CreateImagePyramid()
+        uv = np.concatenate([pairs[p % unique][2] for p in range(n_pairs)])
+        d_ref = torch.from_numpy(uv).to(dev)
+        d_cur = torch.empty_like(d_ref)
+        d_st = torch.empty((uv.shape[0],), dtype=torch.uint8, device=dev)
+        d_off = torch.from_numpy(np.arange(n_pairs + 1, dtype=np.int32) * n_feat).to(dev)
+        d_ri = torch.arange(n_pairs, dtype=torch.int32, device=dev)
+        d_ci = d_ri + n_pairs
+        klt = {"basic": ft.OpticalFlowBasicKlt, "affine": ft.OpticalFlowAffineKlt, "lssd": ft.OpticalFlowLssdKlt}[variant](ctx)
+        o = klt.options()
+        o.kPatchRowHalfSize = o.kPatchColHalfSize = half
+        o.kMethod = {"inverse": ft.OpticalFlowMethod.kInverse, "direct": ft.OpticalFlowMethod.kDirect, "fast": ft.OpticalFlowMethod.kFast}[method]
+        o.kMaxTrackPointsNumber = max(500, n_feat)
+        prm = klt._params()
+        flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+
+        def fn():
+            ctx.check(L.ftk_klt_track(ctx._h, C.byref(prm), pyr._h, pyr._h, n_pairs, vp(d_ri.data_ptr()), vp(d_ci.data_ptr()), vp(d_off.data_ptr()),
+                                      vp(d_ref.data_ptr()), vp(d_cur.data_ptr()), vp(d_st.data_ptr()), flags))
+        ms = timeit(fn, steps)
+        out[name] = {"features_per_s": uv.shape[0] / (ms * 1e-3), "ms": ms, "pairs": n_pairs, "features_per_pair": n_feat,
+                     "tracked_fraction": float((d_st.cpu().numpy() == 1).mean())}
+        pyr.close()
+
+    klt_case("C2_affine_direct_13x13", "affine", "direct", 6, ROWS, COLS, 100, 2000)
+    klt_case("C2_affine_fast_13x13", "affine", "fast", 6, ROWS, COLS, 100, 2000)
+    klt_case("basic_fast_13x13_reference_default", "basic", "fast", 6, ROWS, COLS, 100, 2000)
+    klt_case("basic_direct_15x15", "basic", "direct", 7, ROWS, COLS, 100, 2000)
+    klt_case("C3_lssd_inverse_21x21_1280x720", "lssd", "inverse", 10, 720, 1280, 4, 10000, unique=2)
+
+    # ---- C4: BRIEF-256 force 10k x 10k + nearby ----
+    rb, cb, pred, pos, truth = S.make_brief_sets(10000, 10000, seed=99)
+    d_r = torch.from_numpy(ft.pack_brief(rb).view(np.int32)).to(dev)
+    d_c = torch.from_numpy(ft.pack_brief(cb).view(np.int32)).to(dev)
+    d_idx = torch.full((10000,), -1, dtype=torch.int32, device=dev)
+    d_pred = torch.from_numpy(pred).to(dev)
+    d_pos = torch.from_numpy(pos).to(dev)
+    fl = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_INDEX_INPUT
+    ms = timeit(lambda: ctx.check(L.ftk_match_hamming_force(ctx._h, vp(d_r.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, 60.0, vp(d_idx.data_ptr()), fl)), steps * 4)
+    idx = d_idx.cpu().numpy()
+    has = truth >= 0
+    popc_peak_pairs = 148 * 16 * 1.965e9 / 8  # measured POPC rate: 16 lanes/clk/SM (profiles/r1_microbench_pipe_rates.txt), 8 POPC per 256-bit pair
+    out["C4_brief256_force_10k_x_10k"] = {"pairs_per_s": 1e8 / (ms * 1e-3), "ms": ms, "recovered_planted_matches": float((idx[has] == truth[has]).mean()),
+                                          "popc_peak_pairs_per_s": popc_peak_pairs, "frac_of_popc_peak": 1e8 / (ms * 1e-3) / popc_peak_pairs}
+    ms = timeit(lambda: ctx.check(L.ftk_match_hamming_nearby(ctx._h, vp(d_r.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, vp(d_pred.data_ptr()),
+                                                             vp(d_pos.data_ptr()), 50, 50, 60.0, vp(d_idx.data_ptr()), fl)), steps * 4)
+    out["C4_brief256_nearby_10k_window50"] = {"ref_rows_per_s": 1e4 / (ms * 1e-3), "ms": ms}
+
+    # ---- C5: float-256 force 20k x 20k ----
+    rf, cf = S.make_float_sets(20000, 20000, seed=5)
+    d_rf = torch.from_numpy(rf).to(dev)
+    d_cf = torch.from_numpy(cf).to(dev)
+    d_idx2 = torch.full((20000,), -1, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_rf.data_ptr()), 20000, vp(d_cf.data_ptr()), 20000, 256, 0.1, vp(d_idx2.data_ptr()), fl)), max(2, steps // 2))
+    flop = 2.0 * 20000 * 20000 * 256
+    out["C5_float256_force_20k_x_20k"] = {"pairs_per_s": 4e8 / (ms * 1e-3), "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12,
+                                          "matched": int((d_idx2.cpu().numpy() >= 0).sum())}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -395,6 +482,11 @@ def run_b200(args):
                             "frac": tfs / fp32_peak, "traffic": None,
                             "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
                             "algorithmic_flops_per_launch": flops, "patch_iterations_per_feature": iters / n_total, "kernel": "KltKernel"}
+    if not args.no_extras and world == 1:
+        try:
+            line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps)
+        except Exception as e:  # the headline must survive a failure in the extras
+            line["other_workloads"] = {"error": repr(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
