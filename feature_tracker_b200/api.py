@@ -409,5 +409,10 @@ class CosineMatcher(DescriptorMatcher):
                                              float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
 
 
+    def last_exact_scan_items(self):
+        """Diagnostics: rows x splits the last ForceMatch re-scanned exactly (0 = the tensor-core pass decided everything)."""
+        return int(lib().ftk_last_cosine_exact_scan_items(self.ctx._h))
+
+
 SuperpointMatcher = CosineMatcher
 DiskMatcher = CosineMatcher

@@ -444,6 +444,16 @@ int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, c
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 
+int ftk_last_cosine_exact_scan_items(ftk_context *ctx) {
+    if (!ctx) return FTK_ERR_INVALID_ARGUMENT;
+    if (!ctx->d_last_scan_items) return -1;
+    DeviceGuard guard(ctx->device);
+    int n = 0;
+    if (cudaMemcpyAsync(&n, ctx->d_last_scan_items, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return n;
+}
+
 // descriptor_matcher.h:135-157 FillMatchedPixelByPairIndices (negligible host work in the reference; kept on the host).
 int ftk_fill_matched(const int32_t *idx, int32_t n_ref, const float *cur_uv, int32_t n_cur, float *matched_uv, uint8_t *status, int32_t status_valid) {
     if (n_ref < 0 || (n_ref > 0 && (!idx || !matched_uv || !status))) return FTK_ERR_INVALID_ARGUMENT;

@@ -48,6 +48,7 @@ struct ftk_context {
     std::string error;
     uint64_t launches = 0;
     int sm_count = 0;
+    const int *d_last_scan_items = nullptr;  // device counter of the last tensor-core cosine match (nullptr: path not used)
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
@@ -98,6 +99,8 @@ int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const
 int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
                         const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
+// match_cosine_tc.cu: tcgen05 GEMM + exact re-rank; FTK_ERR_UNSUPPORTED for dim > 256
+int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
 int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,
                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
 

@@ -536,6 +536,11 @@ int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, cons
 
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
     if (n_ref == 0) return FTK_OK;
+    ctx->d_last_scan_items = nullptr;
+    if (ctx->use_fast_paths) {
+        const int rc = LaunchCosineForceTensor(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx);
+        if (rc != FTK_ERR_UNSUPPORTED) return rc;
+    }
     cudaStream_t st = ctx->stream;
     float *ref_norm, *cur_norm;
     if (int rc = ComputeNorms(ctx, d_ref, n_ref, d_cur, n_cur, dim, &ref_norm, &cur_norm)) return rc;

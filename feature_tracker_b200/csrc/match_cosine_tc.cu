@@ -1,0 +1,472 @@
+// K7: force matching of dense float descriptors (SuperPoint / DISK, up to 256-d) on the 5th-generation tensor cores.
+//
+// Replaces DescriptorMatcher<T>::ForceMatch (src/descriptor_matcher/descriptor_matcher.h:55-79) with the cosine
+// ComputeDistance of test/test_descriptor_matcher_superpoint.cpp:32-34 (d = 0.5 - dot / |a| / |b| * 0.5).
+//
+// The result is still EXACT (same indices as the reference's fp32 evaluation, lowest j on ties):
+//   1. PrepKernel      : unit-normalised BF16 copies of both descriptor sets (K padded to a multiple of 64).
+//   2. CosineTcKernel  : C = A_hat * B_hat^T with tcgen05.mma (BF16 in, FP32 accumulate in TMEM); operands arrive by TMA
+//                        (128B-swizzled boxes), the 128 x K reference tile stays resident in shared memory while
+//                        128-column tiles of the current set stream through a 2-stage mbarrier pipeline; the score
+//                        matrix is never written: the epilogue warps read the accumulator with tcgen05.ld and keep a
+//                        running top-2 (largest approximate dot, lowest j first) per reference row in registers.
+//   3. RerankKernel    : |approximate dot - exact dot| <= kEpsDot for unit vectors, so only candidates within
+//                        2 * kEpsDot of the row's best approximate dot can be the exact arg-min.  Those (usually one)
+//                        are re-evaluated with the reference's own sequential fp32 arithmetic; rows whose top-2 are
+//                        both inside the margin (a third candidate could hide) go to an exact scan (ExactScanKernel).
+// Warp roles in CosineTcKernel (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
+// epilogue (one TMEM lane quarter each).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "ftk_internal.h"
+
+namespace ftk {
+
+namespace {
+
+constexpr int kTileM = 128;      // reference rows per CTA (TMEM lanes)
+constexpr int kTileN = 128;      // current descriptors per MMA tile (TMEM columns)
+constexpr int kKBlock = 64;      // BF16 elements per 128-byte swizzle row
+constexpr int kMaxKBlocks = 4;   // K <= 256
+constexpr int kStages = 2;
+constexpr int kBoxBytes = kTileM * kKBlock * 2;  // 16 KiB: one TMA box (128 rows x 128 B)
+constexpr int kTcThreads = 192;
+constexpr int kTmemCols = 256;   // two 128-column fp32 accumulators
+constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytes * (1 + kStages) + 256;
+
+// |dot(bf16(a_hat), bf16(b_hat)) - exact dot of the unit vectors| <= 2 * 2^-9 + 2^-18 (Cauchy-Schwarz), plus fp32
+// accumulation slack on both sides.
+constexpr float kEpsDot = 0.0041f;
+
+constexpr unsigned long long kNoKey64 = 0xFFFFFFFFFFFFFFFFull;
+
+struct __align__(16) Top2 {
+    float b1;
+    int j1;
+    float b2;
+    int j2;
+};
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t SmemU32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void MbarInit(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemU32(bar)), "r"(count));
+}
+__device__ __forceinline__ void MbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemU32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemU32(bar)) : "memory");
+}
+__device__ __forceinline__ void MbarWait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(SmemU32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void TmaLoad2D(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(SmemU32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(SmemU32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void UmmaBf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void UmmaCommit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemU32(bar)) : "memory");
+}
+__device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor for a K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row groups 1024 B
+// apart): start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 B, version 1 (Blackwell), SWIZZLE_128B.
+__device__ __forceinline__ uint64_t MakeSmemDesc(const void *tile) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((SmemU32(tile) >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+
+// ---- kernels -----------------------------------------------------------------------------------------------------
+
+// norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA).
+__global__ void NormPrepKernel(const float *desc, int n, int dim, int k_pad, float *norm, __nv_bfloat16 *unit) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *a = desc + static_cast<size_t>(i) * dim;
+    float s = __fmul_rn(a[0], a[0]);
+    for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
+    const float nrm = __fsqrt_rn(s);
+    norm[i] = nrm;
+    // A descriptor without a usable norm has NaN distances to everything in the reference: NaN rows keep it out of every top-2.
+    const bool usable = nrm > 0.0f && isfinite(nrm);
+    __nv_bfloat16 *u = unit + static_cast<size_t>(i) * k_pad;
+    for (int k = 0; k < k_pad; ++k) {
+        float v = 0.0f;
+        if (k < dim) v = usable ? a[k] / nrm : __int_as_float(0x7FC00000);
+        u[k] = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks,
+               int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages * kMaxKBlocks * kBoxBytes);
+    uint64_t *bar_a = &bars[0];
+    uint64_t *bar_full = &bars[1];        // [kStages]
+    uint64_t *bar_empty = &bars[3];       // [kStages]
+    uint64_t *bar_acc_full = &bars[5];    // [2]
+    uint64_t *bar_acc_empty = &bars[7];   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[9]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int t_begin = blockIdx.y * tiles_per_split;
+    const int t_end = min(n_tiles, t_begin + tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        MbarInit(bar_a, 1);
+        for (int s = 0; s < kStages; ++s) {
+            MbarInit(&bar_full[s], 1);
+            MbarInit(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            MbarInit(&bar_acc_full[a], 1);
+            MbarInit(&bar_acc_empty[a], 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    TcFenceBefore();
+    __syncthreads();
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            MbarExpectTx(bar_a, static_cast<uint32_t>(k_blocks) * kBoxBytes);
+            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2D(smem_a + kb * kBoxBytes, &map_ref, bar_a, kb * kKBlock, m_tile * kTileM);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                MbarWait(&bar_empty[stage], phase ^ 1u);
+                MbarExpectTx(&bar_full[stage], static_cast<uint32_t>(k_blocks) * kBoxBytes);
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    TmaLoad2D(smem_b + (stage * kMaxKBlocks + kb) * kBoxBytes, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            MbarWait(bar_a, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
+                MbarWait(&bar_full[stage], phase);
+                TcFenceAfter();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytes);
+                    const uint64_t bdesc = MakeSmemDesc(smem_b + (stage * kMaxKBlocks + kb) * kBoxBytes);
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        // each UMMA consumes K = 16 BF16 = 32 bytes of the 128-byte swizzle row: advance the start address by 32 B
+                        UmmaBf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                }
+                UmmaCommit(&bar_empty[stage]);     // the stage's operands may be overwritten once these MMAs retire
+                UmmaCommit(&bar_acc_full[acc]);    // ... and the accumulator is complete
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue: running top-2 per reference row =====================
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = m_tile * kTileM + quarter * 32 + lane;
+        float b1 = -INFINITY, b2 = -INFINITY;
+        int j1 = -1, j2 = -1;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            MbarWait(&bar_acc_full[acc], acc_phase);
+            TcFenceAfter();
+            const int n0 = t * kTileN;
+            const bool partial = n0 + kTileN > n_cur;
+#pragma unroll 1
+            for (int chunk = 0; chunk < kTileN / 32; ++chunk) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN + chunk * 32);
+                TmemLoad32(taddr, r);
+                const int c0 = n0 + chunk * 32;
+                if (partial) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c0 + c >= n_cur) r[c] = 0xFF800000u;  // -inf: zero-filled columns past the end never win
+                }
+                float m = __uint_as_float(r[0]);
+#pragma unroll
+                for (int c = 1; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));  // fmaxf drops NaN
+                if (m > b2) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = __uint_as_float(r[c]);
+                        if (v > b1) {
+                            b2 = b1, j2 = j1;
+                            b1 = v, j1 = c0 + c;
+                        } else if (v > b2) {
+                            b2 = v, j2 = c0 + c;
+                        }
+                    }
+                }
+            }
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArrive(&bar_acc_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (row < n_ref) {
+            Top2 o;
+            o.b1 = b1, o.j1 = j1, o.b2 = b2, o.j2 = j2;
+            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
+        }
+    }
+
+    TcFenceBefore();
+    __syncthreads();
+    if (warp == 1) {
+        TcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// Order-preserving key for a non-NaN float distance (with -0 canonicalised to +0).
+__device__ __forceinline__ unsigned FloatKey(float d) {
+    d = d + 0.0f;
+    const unsigned b = __float_as_uint(d);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float KeyFloat(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
+
+// The reference's distance, bit for bit: sequential dot (k ascending, no FMA), 0.5 - dot / |a| / |b| * 0.5.
+__device__ __forceinline__ float ExactDistance(const float *a, const float *b, int dim, float na, float nb) {
+    float s = __fmul_rn(__ldg(a), __ldg(b));
+    for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(__ldg(a + k), __ldg(b + k)));
+    return __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
+}
+
+// One thread per reference row: exact re-evaluation of the candidates inside the error margin.
+__global__ void RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm, const float *cur_norm, const Top2 *top,
+                             int n_splits, int n_ref_pad, unsigned long long *best, int2 *work, int *n_work) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    float gmax = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) gmax = fmaxf(gmax, top[static_cast<size_t>(s) * n_ref_pad + i].b1);
+    unsigned long long key = kNoKey64;
+    if (gmax > -INFINITY) {
+        const float thr = gmax - 2.0f * kEpsDot;
+        const float *a = ref + static_cast<size_t>(i) * dim;
+        const float na = ref_norm[i];
+        for (int s = 0; s < n_splits; ++s) {
+            const Top2 t = top[static_cast<size_t>(s) * n_ref_pad + i];
+            if (t.j1 < 0 || !(t.b1 >= thr)) continue;
+            if (t.j2 >= 0 && t.b2 >= thr) {
+                // both of this split's best are inside the margin: a third candidate could hide behind them
+                const int slot = atomicAdd(n_work, 1);
+                work[slot] = make_int2(i, s);
+                continue;
+            }
+            const float d = ExactDistance(a, cur + static_cast<size_t>(t.j1) * dim, dim, na, cur_norm[t.j1]);
+            if (d == d) {
+                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(t.j1);
+                key = k < key ? k : key;
+            }
+        }
+    }
+    if (key != kNoKey64) atomicMin(&best[i], key);
+}
+
+// One block per flagged (row, split): exact scan of the split's column range.
+__global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const float *cur, int n_cur, int dim, const float *ref_norm, const float *cur_norm,
+                                                      const int2 *work, const int *n_work, int cols_per_split, unsigned long long *best) {
+    const int n = *n_work;
+    for (int w = blockIdx.x; w < n; w += gridDim.x) {
+        const int i = work[w].x, s = work[w].y;
+        const int j_begin = s * cols_per_split, j_end = min(n_cur, j_begin + cols_per_split);
+        const float *a = ref + static_cast<size_t>(i) * dim;
+        const float na = ref_norm[i];
+        unsigned long long key = kNoKey64;
+        for (int j = j_begin + threadIdx.x; j < j_end; j += blockDim.x) {
+            const float d = ExactDistance(a, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j]);
+            if (d == d) {
+                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+                key = k < key ? k : key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = other < key ? other : key;
+        }
+        if ((threadIdx.x & 31) == 0 && key != kNoKey64) atomicMin(&best[i], key);
+    }
+}
+
+__global__ void FinalizeKernel(const unsigned long long *best, int n_ref, float max_dist, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const unsigned long long key = best[i];
+    if (key == kNoKey64) return;
+    const float d = KeyFloat(static_cast<unsigned>(key >> 32));
+    if (d < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+}
+
+__global__ void FillKeysKernel(unsigned long long *p, int n, int *counter) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = kNoKey64;
+    if (i == 0) *counter = 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn GetEncodeTiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows][k_pad] BF16, K-major; box = 64 elements x 128 rows, 128B swizzle, out-of-range rows read as zero.
+bool MakeMap(CUtensorMap *map, const __nv_bfloat16 *base, int rows, int k_pad) {
+    EncodeTiledFn encode = GetEncodeTiled();
+    if (!encode) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_pad) * 2};
+    const cuuint32_t box[2] = {kKBlock, kTileM};
+    const cuuint32_t elem[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int Blocks(int n, int threads) { return (n + threads - 1) / threads; }
+
+}  // namespace
+
+// Returns FTK_ERR_UNSUPPORTED when the tensor-core path does not cover the shape (dim > 256): the caller then runs the
+// exact CUDA-core kernel of match.cu.
+int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
+    if (dim > kMaxKBlocks * kKBlock) return FTK_ERR_UNSUPPORTED;
+    if (n_ref == 0) return FTK_OK;
+    cudaStream_t st = ctx->stream;
+    const int k_blocks = (dim + kKBlock - 1) / kKBlock, k_pad = k_blocks * kKBlock;
+    const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + kTileN - 1) / kTileN;
+    // split the current set across CTAs until the grid covers the GPU about once
+    int splits = (ctx->sm_count + m_tiles - 1) / m_tiles;
+    if (splits > n_tiles) splits = n_tiles;
+    if (splits < 1) splits = 1;
+    const int tiles_per_split = (n_tiles + splits - 1) / splits;
+    splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+    const int n_ref_pad = m_tiles * kTileM;
+
+    // scratch: norms | unit bf16 copies | top-2 | best keys | work list
+    const size_t bytes_norm = sizeof(float) * (static_cast<size_t>(n_ref) + n_cur);
+    const size_t bytes_unit = sizeof(__nv_bfloat16) * static_cast<size_t>(k_pad) * (static_cast<size_t>(n_ref) + n_cur);
+    if (int rc = EnsureDevice(ctx, ctx->d_work3, bytes_norm + 256)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work1, bytes_unit + 1024)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work2, sizeof(Top2) * static_cast<size_t>(splits) * n_ref_pad + 256)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref) + sizeof(int2) * static_cast<size_t>(n_ref) * splits + 256))
+        return rc;
+    float *ref_norm = static_cast<float *>(ctx->d_work3.ptr), *cur_norm = ref_norm + n_ref;
+    __nv_bfloat16 *ref_unit = static_cast<__nv_bfloat16 *>(ctx->d_work1.ptr);
+    __nv_bfloat16 *cur_unit = ref_unit + static_cast<size_t>(n_ref) * k_pad;
+    Top2 *top = static_cast<Top2 *>(ctx->d_work2.ptr);
+    unsigned long long *best = static_cast<unsigned long long *>(ctx->d_work0.ptr);
+    int *n_work = reinterpret_cast<int *>(best + n_ref);
+    int2 *work = reinterpret_cast<int2 *>(n_work + 2);
+
+    CUtensorMap map_ref, map_cur;
+    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad))
+        return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
+
+    NormPrepKernel<<<Blocks(n_ref, 128), 128, 0, st>>>(d_ref, n_ref, dim, k_pad, ref_norm, ref_unit);
+    NormPrepKernel<<<Blocks(n_cur, 128), 128, 0, st>>>(d_cur, n_cur, dim, k_pad, cur_norm, cur_unit);
+    FillKeysKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, n_work);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
+        attr_set = true;
+    }
+    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad);
+    RerankKernel<<<Blocks(n_ref, 128), 128, 0, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, n_work);
+    ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
+    FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
+    ctx->launches += 7;
+    ctx->d_last_scan_items = n_work;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+}  // namespace ftk

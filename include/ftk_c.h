@@ -138,6 +138,10 @@ int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, co
 int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim,
                             const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
                             uint32_t flags);
+/* Diagnostics: number of (reference row, column split) items the last ftk_match_cosine_force call had to hand to the exact
+ * fall-back scan because the tensor-core pass could not separate the candidates (0 when the fast path decided every row;
+ * -1 when the call did not use the tensor-core path).  Synchronises the context. */
+int ftk_last_cosine_exact_scan_items(ftk_context *ctx);
 /* Host-side helper mirroring FillMatchedPixelByPairIndices (descriptor_matcher.h:135-157); status_valid == 0
  * behaves as status.size() != idx.size(). */
 int ftk_fill_matched(const int32_t *idx, int32_t n_ref, const float *cur_uv, int32_t n_cur, float *matched_uv, uint8_t *status,

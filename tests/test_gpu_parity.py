@@ -286,6 +286,28 @@ def test_cosine_force_vs_oracle(ctx, oracle, n_ref, n_cur, dim):
         assert got[0] == exp[0] and (got[1] == exp[1]).all(), (n_ref, n_cur, dim, max_dist, np.nonzero(got[1] != exp[1])[0][:10])
 
 
+def test_cosine_tensor_path_decides_without_fallback(ctx, oracle):
+    """The tcgen05 GEMM + top-2 must itself find the matches: on well-separated data no row may need the exact fall-back scan
+    (otherwise a broken GEMM could hide behind it), and the result still equals the oracle's."""
+    rf, cf = S.make_float_sets(700, 900, dim=256, seed=77)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.1
+    ok, idx = c.ForceMatch(rf, cf)
+    assert ok and c.last_exact_scan_items() == 0
+    assert (idx == oracle.match_cosine_force(rf, cf, 0.1)[1]).all() and (idx >= 0).mean() > 0.95
+    # near-duplicates inside the error margin force the exact path for those rows only
+    cf2 = cf.copy()
+    cf2[10] = cf2[3] * np.float32(1.0001)
+    ok, idx2 = c.ForceMatch(rf, cf2)
+    assert 0 < c.last_exact_scan_items() < 20
+    assert (idx2 == oracle.match_cosine_force(rf, cf2, 0.1)[1]).all()
+    # dims that are not a multiple of 64, tiny problems, a dim above the tensor-path limit
+    for n_ref, n_cur, dim in [(5, 3, 200), (129, 257, 65), (50, 60, 300)]:
+        a, b = S.make_float_sets(n_ref, n_cur, dim=dim, seed=dim)
+        ok, got = c.ForceMatch(a, b)
+        assert (got == oracle.match_cosine_force(a, b, 0.1)[1]).all(), (n_ref, n_cur, dim)
+
+
 def test_cosine_nearby_vs_oracle(ctx, oracle):
     rf, cf = S.make_float_sets(300, 350, dim=256, seed=31)
     rng = np.random.default_rng(8)
