@@ -1,0 +1,388 @@
+// C++ facade over the C ABI (include/ftk_c.h) with the reference's class names, option structs and method signatures
+// (namespace feature_tracker; src/feature_tracker.h, src/optical_flow_tracker/optical_flow.h and the three KLT subclasses,
+// src/descriptor_matcher/descriptor_matcher.h), so application code that holds `OpticalFlowBasicKlt klt;` or a
+// `DescriptorMatcher<T>` subclass recompiles against this header and runs on the B200 instead of the CPU loops.
+//
+// Differences a maintainer has to know about (all dictated by where the data lives):
+//   * ImagePyramid is device resident: SetRawImage() + CreateImagePyramid() upload level 0 and build the levels on the GPU.
+//   * DescriptorMatcher<T> no longer calls a per-pair virtual ComputeDistance (one virtual call per pair cannot feed a GPU);
+//     the distance is selected by DescriptorTraits<T>: Hamming for element-wise boolean containers (BriefType), the
+//     0.5 - 0.5 * cos distance for float vectors (Superpoint / Disk descriptors), exactly the demos' ComputeDistance bodies.
+//   * Vec2 is any type with x() / y() accessors and a (float, float) constructor (Eigen::Vector2f qualifies); define
+//     FTK_VEC2_TYPE before including this header to use the application's own type.
+// Header only; link with libftk_b200.so.
+#ifndef FEATURE_TRACKER_B200_FEATURE_TRACKER_H_
+#define FEATURE_TRACKER_B200_FEATURE_TRACKER_H_
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "ftk_c.h"
+
+#ifndef FTK_VEC2_TYPE
+namespace feature_tracker {
+struct Vec2f {
+    float v[2];
+    Vec2f() : v{0.0f, 0.0f} {}
+    Vec2f(float x, float y) : v{x, y} {}
+    float &x() { return v[0]; }
+    float &y() { return v[1]; }
+    const float &x() const { return v[0]; }
+    const float &y() const { return v[1]; }
+};
+}  // namespace feature_tracker
+#define FTK_VEC2_TYPE ::feature_tracker::Vec2f
+#endif
+
+namespace feature_tracker {
+
+using Vec2 = FTK_VEC2_TYPE;
+
+// src/feature_tracker.h:8-14
+enum class TrackStatus : uint8_t {
+    kNotTracked = 0,
+    kTracked = 1,
+    kLargeResidual = 2,
+    kOutside = 3,
+    kNumericError = 4,
+};
+
+// One GPU context shared by the facade objects of a thread (the reference objects are not re-entrant either).
+class Device {
+public:
+    static ftk_context *Get(int device = 0) {
+        static thread_local std::unique_ptr<Device> instance;
+        if (!instance || instance->device_ != device) instance.reset(new Device(device));
+        return instance->ctx_;
+    }
+    ~Device() { ftk_destroy(ctx_); }
+
+private:
+    explicit Device(int device) : device_(device) {
+        if (ftk_create(device, &ctx_) != FTK_OK) throw std::runtime_error("feature_tracker_b200: no usable B200 (sm_100) device; there is no CPU fallback");
+    }
+    int device_ = 0;
+    ftk_context *ctx_ = nullptr;
+};
+
+// Device-resident stand-in for Slam_Utility's ImagePyramid (call sites: test/test_optical_flow.cpp:49-53,70-71).
+class ImagePyramid {
+public:
+    ImagePyramid() = default;
+    ~ImagePyramid() { Release(); }
+    ImagePyramid(const ImagePyramid &) = delete;
+    ImagePyramid &operator=(const ImagePyramid &) = delete;
+
+    void SetPyramidBuff(uint8_t *, bool) {}  // levels live in HBM; kept for source compatibility
+    void SetRawImage(const uint8_t *data, int32_t rows, int32_t cols) {
+        raw_ = data;
+        rows_ = rows;
+        cols_ = cols;
+    }
+    bool CreateImagePyramid(uint32_t level) {
+        if (raw_ == nullptr || level == 0) return false;
+        ftk_context *ctx = Device::Get();
+        if (pyr_ == nullptr || ftk_pyramid_levels(pyr_) != static_cast<int32_t>(level) || built_rows_ != rows_ || built_cols_ != cols_) {
+            Release();
+            if (ftk_pyramid_create(ctx, rows_, cols_, static_cast<int32_t>(level), 1, &pyr_) != FTK_OK) return false;
+            built_rows_ = rows_;
+            built_cols_ = cols_;
+        }
+        if (ftk_pyramid_set_images(ctx, pyr_, 0, 1, raw_, 0) != FTK_OK) return false;
+        return ftk_pyramid_build(ctx, pyr_, 0, 1) == FTK_OK && ftk_synchronize(ctx) == FTK_OK;
+    }
+    uint32_t level() const { return pyr_ ? static_cast<uint32_t>(ftk_pyramid_levels(pyr_)) : 0u; }
+    int32_t rows() const { return rows_; }
+    int32_t cols() const { return cols_; }
+    const ftk_pyramid *handle() const { return pyr_; }
+
+private:
+    void Release() {
+        if (pyr_) ftk_pyramid_destroy(Device::Get(), pyr_);
+        pyr_ = nullptr;
+    }
+    const uint8_t *raw_ = nullptr;
+    int32_t rows_ = 0, cols_ = 0, built_rows_ = 0, built_cols_ = 0;
+    ftk_pyramid *pyr_ = nullptr;
+};
+
+// src/optical_flow_tracker/optical_flow.h:12-18
+enum class OpticalFlowMethod : uint8_t {
+    kInverse = 0,
+    kDirect = 1,
+    kFast = 2,
+    kSse = 3,
+    kNeon = 4,
+};
+
+// src/optical_flow_tracker/optical_flow.h:20-28
+struct OpticalFlowOptions {
+    uint32_t kMaxTrackPointsNumber = 500;
+    uint32_t kMaxIteration = 15;
+    uint32_t kMaxToleranceLargeStep = 3;
+    int32_t kPatchRowHalfSize = 6;
+    int32_t kPatchColHalfSize = 6;
+    float kMaxConvergeStep = 4e-2f;
+    OpticalFlowMethod kMethod = OpticalFlowMethod::kFast;
+};
+
+// src/optical_flow_tracker/optical_flow.h:30-104
+class OpticalFlow {
+public:
+    OpticalFlow() = default;
+    virtual ~OpticalFlow() = default;
+    virtual std::string OpticalFlowMethodName() const { return "None"; }
+
+    // optical_flow.cpp:6-26
+    bool TrackFeatures(const ImagePyramid &ref_pyramid, const ImagePyramid &cur_pyramid, const std::vector<Vec2> &ref_pixel_uv,
+                       std::vector<Vec2> &cur_pixel_uv, std::vector<uint8_t> &status) {
+        if (ref_pixel_uv.empty()) return false;
+        if (cur_pyramid.level() != ref_pyramid.level()) return false;
+        return Track(ref_pyramid, cur_pyramid, ref_pixel_uv, cur_pixel_uv, status, 0u);
+    }
+    // optical_flow.cpp:28-47 (the GrayImage overload): level 0 of the two pyramids, TrackSingleLevel semantics.
+    bool TrackFeaturesSingleLevel(const ImagePyramid &ref_image, const ImagePyramid &cur_image, const std::vector<Vec2> &ref_pixel_uv,
+                                  std::vector<Vec2> &cur_pixel_uv, std::vector<uint8_t> &status) {
+        if (ref_pixel_uv.empty()) return false;
+        return Track(ref_image, cur_image, ref_pixel_uv, cur_pixel_uv, status, FTK_FLAG_SINGLE_LEVEL);
+    }
+
+    OpticalFlowOptions &options() { return options_; }
+    const OpticalFlowOptions &options() const { return options_; }
+
+protected:
+    virtual void FillParams(ftk_klt_params &p) const = 0;
+
+private:
+    bool Track(const ImagePyramid &ref, const ImagePyramid &cur, const std::vector<Vec2> &ref_uv, std::vector<Vec2> &cur_uv, std::vector<uint8_t> &status,
+               uint32_t flags) {
+        if (!ref.handle() || !cur.handle()) return false;
+        const int32_t n = static_cast<int32_t>(ref_uv.size());
+        ftk_klt_params p;
+        ftk_klt_params_default(&p);
+        p.max_track_points = options_.kMaxTrackPointsNumber;
+        p.max_iteration = options_.kMaxIteration;
+        p.max_tolerance_large_step = options_.kMaxToleranceLargeStep;
+        p.patch_row_half = options_.kPatchRowHalfSize;
+        p.patch_col_half = options_.kPatchColHalfSize;
+        p.max_converge_step = options_.kMaxConvergeStep;
+        p.method = static_cast<int32_t>(options_.kMethod);
+        FillParams(p);
+        std::vector<float> ref_flat(2 * static_cast<size_t>(n)), cur_flat(2 * static_cast<size_t>(n), 0.0f);
+        for (int32_t i = 0; i < n; ++i) ref_flat[2 * i] = ref_uv[i].x(), ref_flat[2 * i + 1] = ref_uv[i].y();
+        if (cur_uv.size() == ref_uv.size()) {
+            for (int32_t i = 0; i < n; ++i) cur_flat[2 * i] = cur_uv[i].x(), cur_flat[2 * i + 1] = cur_uv[i].y();
+        } else {
+            flags |= FTK_FLAG_NO_PREDICTION;  // optical_flow.cpp:12-14
+        }
+        if (status.size() != ref_uv.size()) {
+            flags |= FTK_FLAG_NO_STATUS;  // optical_flow.cpp:17-19
+            status.assign(ref_uv.size(), static_cast<uint8_t>(TrackStatus::kNotTracked));
+        }
+        const int32_t offsets[2] = {0, n};
+        const int32_t image0 = 0;
+        const int rc = ftk_klt_track(Device::Get(), &p, ref.handle(), cur.handle(), 1, &image0, &image0, offsets, ref_flat.data(), cur_flat.data(), status.data(), flags);
+        if (rc != FTK_OK) return false;
+        cur_uv.resize(ref_uv.size());
+        for (int32_t i = 0; i < n; ++i) cur_uv[i] = Vec2(cur_flat[2 * i], cur_flat[2 * i + 1]);
+        return true;
+    }
+    OpticalFlowOptions options_;
+};
+
+// basic_klt/optical_flow_basic_klt.h:9-41
+class OpticalFlowBasicKlt : public OpticalFlow {
+public:
+    std::string OpticalFlowMethodName() const override { return "Basic-Klt"; }
+
+protected:
+    void FillParams(ftk_klt_params &p) const override { p.variant = FTK_VARIANT_BASIC; }
+};
+
+// Row-major 2x2 float matrix with Eigen-like (i, j) access for the prediction accessors.
+struct Mat2f {
+    float m[4] = {1.0f, 0.0f, 0.0f, 1.0f};
+    float &operator()(int i, int j) { return m[2 * i + j]; }
+    const float &operator()(int i, int j) const { return m[2 * i + j]; }
+};
+
+// affine_klt/optical_flow_affine_klt.h:9-52
+class OpticalFlowAffineKlt : public OpticalFlow {
+public:
+    std::string OpticalFlowMethodName() const override { return "Affine-Klt"; }
+    Mat2f &predict_affine() { return predict_affine_; }
+    const Mat2f &predict_affine() const { return predict_affine_; }
+
+protected:
+    void FillParams(ftk_klt_params &p) const override {
+        p.variant = FTK_VARIANT_AFFINE;
+        std::memcpy(p.predict, predict_affine_.m, sizeof(p.predict));
+    }
+
+private:
+    Mat2f predict_affine_;
+};
+
+// lssd_klt/optical_flow_lssd_klt.h:9-56
+class OpticalFlowLssdKlt : public OpticalFlow {
+public:
+    std::string OpticalFlowMethodName() const override { return "Lssd-Klt"; }
+    Mat2f &predict_R_cr() { return predict_R_cr_; }
+    const Mat2f &predict_R_cr() const { return predict_R_cr_; }
+    bool &consider_patch_luminance() { return consider_patch_luminance_; }
+    const bool &consider_patch_luminance() const { return consider_patch_luminance_; }
+
+protected:
+    void FillParams(ftk_klt_params &p) const override {
+        p.variant = FTK_VARIANT_LSSD;
+        std::memcpy(p.predict, predict_R_cr_.m, sizeof(p.predict));
+        p.consider_patch_luminance = consider_patch_luminance_ ? 1 : 0;
+    }
+
+private:
+    Mat2f predict_R_cr_;
+    bool consider_patch_luminance_ = false;
+};
+
+// ---- descriptor matching (src/descriptor_matcher/descriptor_matcher.h) --------------------------------------------
+
+// How a descriptor type is flattened for the GPU.  kBinary: element-wise boolean container -> packed little-endian
+// bits, Hamming distance (test/test_descriptor_matcher_brief.cpp:33-45).  Otherwise: float vector, 0.5 - 0.5 * cos
+// (test/test_descriptor_matcher_superpoint.cpp:32-34).
+template <typename DescriptorType, typename Enable = void>
+struct DescriptorTraits {
+    static constexpr bool kBinary = false;
+    static size_t Size(const DescriptorType &d) { return static_cast<size_t>(d.size()); }
+    static float At(const DescriptorType &d, size_t k) { return static_cast<float>(d[k]); }
+};
+template <typename DescriptorType>
+struct DescriptorTraits<DescriptorType, typename std::enable_if<std::is_integral<typename DescriptorType::value_type>::value>::type> {
+    static constexpr bool kBinary = true;
+    static size_t Size(const DescriptorType &d) { return static_cast<size_t>(d.size()); }
+    static bool At(const DescriptorType &d, size_t k) { return d[k] != 0; }
+};
+
+template <typename DescriptorType>
+class DescriptorMatcher {
+public:
+    // descriptor_matcher.h:16-20
+    struct Options {
+        int32_t kMaxValidPredictRowDistance = 40;
+        int32_t kMaxValidPredictColDistance = 40;
+        float kMaxValidDescriptorDistance = 0.0f;
+    };
+
+    DescriptorMatcher() = default;
+    virtual ~DescriptorMatcher() = default;
+
+    // descriptor_matcher.h:55-79
+    bool ForceMatch(const std::vector<DescriptorType> &descriptors_ref, const std::vector<DescriptorType> &descriptors_cur,
+                    std::vector<int32_t> &index_pairs_in_cur) {
+        if (descriptors_cur.empty()) return false;
+        uint32_t flags = PrepareIndex(descriptors_ref.size(), index_pairs_in_cur);
+        return Run(descriptors_ref, descriptors_cur, nullptr, nullptr, index_pairs_in_cur, flags);
+    }
+    // descriptor_matcher.h:81-88
+    bool ForceMatch(const std::vector<DescriptorType> &descriptors_ref, const std::vector<DescriptorType> &descriptors_cur,
+                    const std::vector<Vec2> &pixel_uv_cur, std::vector<Vec2> &matched_pixel_uv_cur, std::vector<uint8_t> &status) {
+        std::vector<int32_t> index_pairs_in_cur;
+        if (!ForceMatch(descriptors_ref, descriptors_cur, index_pairs_in_cur)) return false;
+        return FillMatchedPixelByPairIndices(index_pairs_in_cur, pixel_uv_cur, matched_pixel_uv_cur, status);
+    }
+    // descriptor_matcher.h:90-124
+    bool NearbyMatch(const std::vector<DescriptorType> &descriptors_ref, const std::vector<DescriptorType> &descriptors_cur,
+                     const std::vector<Vec2> &pixel_uv_pred_in_cur, const std::vector<Vec2> &pixel_uv_cur, std::vector<int32_t> &index_pairs_in_cur) {
+        if (descriptors_cur.empty()) return false;
+        if (descriptors_ref.size() != pixel_uv_pred_in_cur.size()) return false;
+        if (descriptors_cur.size() != pixel_uv_cur.size()) return false;
+        uint32_t flags = PrepareIndex(descriptors_ref.size(), index_pairs_in_cur);
+        return Run(descriptors_ref, descriptors_cur, &pixel_uv_pred_in_cur, &pixel_uv_cur, index_pairs_in_cur, flags);
+    }
+    // descriptor_matcher.h:126-133
+    bool NearbyMatch(const std::vector<DescriptorType> &descriptors_ref, const std::vector<DescriptorType> &descriptors_cur,
+                     const std::vector<Vec2> &pixel_uv_pred_in_cur, const std::vector<Vec2> &pixel_uv_cur, std::vector<Vec2> &matched_pixel_uv_cur,
+                     std::vector<uint8_t> &status) {
+        std::vector<int32_t> index_pairs_in_cur;
+        if (!NearbyMatch(descriptors_ref, descriptors_cur, pixel_uv_pred_in_cur, pixel_uv_cur, index_pairs_in_cur)) return false;
+        return FillMatchedPixelByPairIndices(index_pairs_in_cur, pixel_uv_cur, matched_pixel_uv_cur, status);
+    }
+
+    Options &options() { return options_; }
+    const Options &options() const { return options_; }
+
+private:
+    static uint32_t PrepareIndex(size_t n_ref, std::vector<int32_t> &idx) {
+        if (idx.size() == n_ref) return 0u;
+        idx.assign(n_ref, -1);  // descriptor_matcher.h:60-62, 98-100
+        return FTK_FLAG_NO_INDEX_INPUT;
+    }
+    static std::vector<float> Flatten(const std::vector<Vec2> &uv) {
+        std::vector<float> out(2 * uv.size());
+        for (size_t i = 0; i < uv.size(); ++i) out[2 * i] = uv[i].x(), out[2 * i + 1] = uv[i].y();
+        return out;
+    }
+    bool Run(const std::vector<DescriptorType> &ref, const std::vector<DescriptorType> &cur, const std::vector<Vec2> *pred, const std::vector<Vec2> *pos,
+             std::vector<int32_t> &idx, uint32_t flags) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        ftk_context *ctx = Device::Get();
+        const int32_t n_ref = static_cast<int32_t>(ref.size()), n_cur = static_cast<int32_t>(cur.size());
+        const size_t len = Traits::Size(cur[0]);
+        std::vector<float> pred_flat, pos_flat;
+        if (pred) pred_flat = Flatten(*pred), pos_flat = Flatten(*pos);
+        int rc;
+        if constexpr (Traits::kBinary) {
+            const int32_t words = static_cast<int32_t>((len + 31) / 32);
+            std::vector<uint32_t> r(static_cast<size_t>(n_ref) * words, 0u), c(static_cast<size_t>(n_cur) * words, 0u);
+            for (int32_t i = 0; i < n_ref; ++i)
+                for (size_t k = 0; k < len && k < Traits::Size(ref[i]); ++k)
+                    if (Traits::At(ref[i], k)) r[static_cast<size_t>(i) * words + k / 32] |= 1u << (k % 32);
+            for (int32_t j = 0; j < n_cur; ++j)
+                for (size_t k = 0; k < len && k < Traits::Size(cur[j]); ++k)
+                    if (Traits::At(cur[j], k)) c[static_cast<size_t>(j) * words + k / 32] |= 1u << (k % 32);
+            rc = pred ? ftk_match_hamming_nearby(ctx, r.data(), n_ref, c.data(), n_cur, words, pred_flat.data(), pos_flat.data(),
+                                                 options_.kMaxValidPredictRowDistance, options_.kMaxValidPredictColDistance,
+                                                 options_.kMaxValidDescriptorDistance, idx.data(), flags)
+                      : ftk_match_hamming_force(ctx, r.data(), n_ref, c.data(), n_cur, words, options_.kMaxValidDescriptorDistance, idx.data(), flags);
+        } else {
+            const int32_t dim = static_cast<int32_t>(len);
+            std::vector<float> r(static_cast<size_t>(n_ref) * dim), c(static_cast<size_t>(n_cur) * dim);
+            for (int32_t i = 0; i < n_ref; ++i)
+                for (int32_t k = 0; k < dim; ++k) r[static_cast<size_t>(i) * dim + k] = Traits::At(ref[i], k);
+            for (int32_t j = 0; j < n_cur; ++j)
+                for (int32_t k = 0; k < dim; ++k) c[static_cast<size_t>(j) * dim + k] = Traits::At(cur[j], k);
+            rc = pred ? ftk_match_cosine_nearby(ctx, r.data(), n_ref, c.data(), n_cur, dim, pred_flat.data(), pos_flat.data(),
+                                                options_.kMaxValidPredictRowDistance, options_.kMaxValidPredictColDistance,
+                                                options_.kMaxValidDescriptorDistance, idx.data(), flags)
+                      : ftk_match_cosine_force(ctx, r.data(), n_ref, c.data(), n_cur, dim, options_.kMaxValidDescriptorDistance, idx.data(), flags);
+        }
+        return rc == FTK_OK;
+    }
+    // descriptor_matcher.h:135-157
+    bool FillMatchedPixelByPairIndices(const std::vector<int32_t> &idx, const std::vector<Vec2> &pixel_uv_cur, std::vector<Vec2> &matched, std::vector<uint8_t> &status) {
+        int32_t valid = 1;
+        if (idx.size() != status.size()) {
+            status.assign(idx.size(), static_cast<uint8_t>(TrackStatus::kNotTracked));
+            valid = 0;
+        }
+        const std::vector<float> pos = Flatten(pixel_uv_cur);
+        std::vector<float> out(2 * idx.size(), 0.0f);
+        for (size_t i = 0; i < matched.size() && i < idx.size(); ++i) out[2 * i] = matched[i].x(), out[2 * i + 1] = matched[i].y();
+        if (ftk_fill_matched(idx.data(), static_cast<int32_t>(idx.size()), pos.data(), static_cast<int32_t>(pixel_uv_cur.size()), out.data(), status.data(), valid) != FTK_OK)
+            return false;
+        matched.resize(idx.size());
+        for (size_t i = 0; i < idx.size(); ++i) matched[i] = Vec2(out[2 * i], out[2 * i + 1]);
+        return true;
+    }
+
+    Options options_;
+};
+
+}  // namespace feature_tracker
+
+#endif

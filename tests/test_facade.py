@@ -1,0 +1,74 @@
+"""The C++ facade (include/feature_tracker_b200/feature_tracker.h) keeps the reference's class names and signatures on top of
+the C ABI.  CPU: it compiles and links against libftk_b200.so.  GPU: a C++ program written like the reference's demos
+(tests/cpp/facade_test.cpp) produces results identical to the oracle."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_facade_test(tmp_path):
+    exe = str(tmp_path / "facade_test")
+    libdir = os.path.join(ROOT, "feature_tracker_b200")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"),
+           "-o", exe, "-L" + libdir, "-lftk_b200", "-Wl,-rpath," + libdir]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_facade_compiles_and_links(tmp_path):
+    exe = build_facade_test(tmp_path)
+    assert os.path.exists(exe)
+    # reference names are all there
+    text = open(os.path.join(ROOT, "include", "feature_tracker_b200", "feature_tracker.h")).read()
+    for name in ["namespace feature_tracker", "enum class TrackStatus", "struct OpticalFlowOptions", "class OpticalFlowBasicKlt", "class OpticalFlowAffineKlt",
+                 "class OpticalFlowLssdKlt", "class DescriptorMatcher", "predict_affine", "predict_R_cr", "consider_patch_luminance", "ForceMatch",
+                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber"]:
+        assert name in text, name
+
+
+@pytest.mark.gpu
+def test_facade_matches_oracle(tmp_path, oracle):
+    from feature_tracker_b200 import synthetic as S
+    from oracle import pyoracle as po
+    exe = build_facade_test(tmp_path)
+    rows, cols, levels, n = 240, 320, 4, 120
+    ref, cur, uv, _ = S.make_pair(rows, cols, n, pair_id=21, border=12)
+    rb, cb, pred, pos, _ = S.make_brief_sets(200, 230, seed=9, rows=rows, cols=cols)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("8i", rows, cols, levels, n, rb.shape[0], cb.shape[0], rb.shape[1], 0))
+        for a in (ref, cur, uv, rb, cb, pred, pos):
+            f.write(np.ascontiguousarray(a).tobytes())
+    subprocess.check_call([exe, fin, fout], timeout=120)
+    data = open(fout, "rb").read()
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a
+
+    rl, cl = oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels)
+    cases = [po.make_params("basic", "fast", half=6), po.make_params("basic", "inverse", half=7), po.make_params("affine", "fast", half=6),
+             po.make_params("lssd", "fast", half=6)]
+    for p in cases:
+        ok = take(np.int32, 1)[0]
+        got_uv = take(np.float32, 2 * n).reshape(n, 2)
+        got_st = take(np.uint8, n)
+        _, exp_uv, exp_st = oracle.klt_track(p, rl, cl, uv)
+        assert ok == 1 and (got_st == exp_st).all() and (got_uv.view(np.uint32) == exp_uv.view(np.uint32)).all()
+    assert list(take(np.int32, 2)) == [0, 0]  # empty input / level mismatch -> false
+    ok = take(np.int32, 1)[0]
+    idx = take(np.int32, rb.shape[0])
+    assert ok == 1 and (idx == oracle.match_brief_force(rb, cb, 60.0)[1]).all()
+    ok = take(np.int32, 1)[0]
+    muv = take(np.float32, 2 * rb.shape[0]).reshape(-1, 2)
+    mst = take(np.uint8, rb.shape[0])
+    _, euv, est = oracle.match_brief_nearby_uv(rb, cb, pred, pos, 50, 50, 60.0)
+    assert ok == 1 and (mst == est).all() and (muv[mst == 1].view(np.uint32) == euv[est == 1].view(np.uint32)).all()
