@@ -344,11 +344,11 @@ def run_b200(args):
                                   vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(d_cur_uv.data_ptr()), vp(d_status.data_ptr()), flags))
 
     def step_e2e():
-        pyr.set_images_ptr(host_images.data_ptr(), 2 * n_pairs)
-        ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
+        # the user-facing call: host images + host features in, host results out (H2D of chunk k+1 overlaps compute of chunk k)
         flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(ref_idx.ctypes.data), vp(cur_idx.ctypes.data),
-                                  vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()), vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+        ctx.check(L.ftk_track_image_pairs(ctx._h, C.byref(params), ROWS, COLS, LEVELS, n_pairs, vp(host_images.data_ptr()),
+                                          vp(host_images.data_ptr() + n_pairs * plane), vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()),
+                                          vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
 
     def barrier():
         ctx.synchronize()

@@ -240,6 +240,33 @@ class OpticalFlow:
         return ok, cur[:n], st[:n]
 
 
+    def TrackImagePairs(self, levels, ref_images, cur_images, feat_offsets, ref_pixel_uv, cur_pixel_uv=None, status=None):
+        """The reference demo's timed region (CreateImagePyramid x2 + TrackFeatures, test/test_optical_flow.cpp:69-73) for a batch of
+        frame pairs given as host images [n_pairs, rows, cols]; H2D copies overlap compute (ftk_track_image_pairs)."""
+        ref_images = np.ascontiguousarray(ref_images, dtype=np.uint8)
+        cur_images = np.ascontiguousarray(cur_images, dtype=np.uint8)
+        n_pairs, rows, cols = ref_images.shape
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        feat_offsets = np.ascontiguousarray(feat_offsets, dtype=np.int32)
+        flags = 0
+        cur = np.zeros((max(n, 1), 2), np.float32)
+        if cur_pixel_uv is not None and np.asarray(cur_pixel_uv).reshape(-1, 2).shape[0] == n and n > 0:
+            cur[:n] = np.asarray(cur_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        else:
+            flags |= _capi.FLAG_NO_PREDICTION
+        st = np.zeros(max(n, 1), np.uint8)
+        if status is not None and np.asarray(status).reshape(-1).shape[0] == n and n > 0:
+            st[:n] = np.asarray(status, dtype=np.uint8).reshape(-1)
+        else:
+            flags |= _capi.FLAG_NO_STATUS
+        p = self._params()
+        rc = lib().ftk_track_image_pairs(self.ctx._h, C.byref(p), rows, cols, int(levels), n_pairs, _ptr(ref_images), _ptr(cur_images),
+                                         _ptr(feat_offsets), _ptr(ref_uv), _ptr(cur), _ptr(st), flags)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
+        return ok, cur[:n], st[:n]
+
+
 class OpticalFlowBasicKlt(OpticalFlow):
     """basic_klt/optical_flow_basic_klt.h:9-41"""
     _variant = 0

@@ -125,9 +125,18 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
+    for (int b = 0; b < 2; ++b) {
+        if (ctx->stage_pyr[b]) {
+            if (ctx->stage_pyr[b]->storage) cudaFree(ctx->stage_pyr[b]->storage);
+            delete ctx->stage_pyr[b];
+        }
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -339,6 +348,126 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, a.status, n_features, cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return FTK_OK;
+}
+
+int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
+                          const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
+                          uint8_t *status, uint32_t flags) {
+    if (!ctx || !params || !ref_images || !cur_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
+    if (flags & (FTK_FLAG_DEVICE_POINTERS | FTK_FLAG_SINGLE_LEVEL)) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "host images, multi-level only");
+    if (params->variant < 0 || params->variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params->variant);
+    if (feat_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
+    for (int p = 0; p < n_pairs; ++p)
+        if (feat_offsets[p + 1] < feat_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
+    const int n_features = feat_offsets[n_pairs];
+    if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");  // optical_flow.cpp:8
+    DeviceGuard guard(ctx->device);
+
+    // chunking: about 8 chunks per call, double-buffered staging pyramids (2 * chunk_pairs images each: refs then curs)
+    const int chunk_pairs = n_pairs < 16 ? n_pairs : (n_pairs + 7) / 8;
+    const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+    if (!ctx->copy_stream) {
+        FTK_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            FTK_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+            FTK_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->stage_rows != rows || ctx->stage_cols != cols || ctx->stage_levels != levels || ctx->stage_pairs < chunk_pairs) {
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        for (int b = 0; b < 2; ++b) {
+            if (ctx->stage_pyr[b]) ftk_pyramid_destroy(ctx, ctx->stage_pyr[b]);
+            ctx->stage_pyr[b] = nullptr;
+            if (int rc = ftk_pyramid_create(ctx, rows, cols, levels, 2 * chunk_pairs, &ctx->stage_pyr[b])) return rc;
+        }
+        ctx->stage_rows = rows, ctx->stage_cols = cols, ctx->stage_levels = levels, ctx->stage_pairs = chunk_pairs;
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the pyramids' memset
+    }
+    const int stage_pairs = ctx->stage_pairs;
+
+    // features up front (small), chunk-local offset tables, the "cur image = stage_pairs + p" map
+    if (int rc = EnsureDevice(ctx, ctx->d_ref_uv, sizeof(float2) * n_features)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_features)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_status, n_features)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * n_features)) return rc;
+    std::vector<int32_t> h_offsets;
+    h_offsets.reserve(n_pairs + n_chunks);
+    std::vector<int> chunk_table_start(n_chunks);
+    for (int c = 0; c < n_chunks; ++c) {
+        const int p_lo = c * chunk_pairs, p_hi = p_lo + chunk_pairs < n_pairs ? p_lo + chunk_pairs : n_pairs;
+        chunk_table_start[c] = static_cast<int>(h_offsets.size());
+        for (int p = p_lo; p <= p_hi; ++p) h_offsets.push_back(feat_offsets[p] - feat_offsets[p_lo]);
+    }
+    std::vector<int32_t> h_curmap(stage_pairs);
+    for (int p = 0; p < stage_pairs; ++p) h_curmap[p] = stage_pairs + p;
+    if (int rc = EnsureDevice(ctx, ctx->d_chunk_offsets, sizeof(int32_t) * h_offsets.size())) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_chunk_curmap, sizeof(int32_t) * h_curmap.size())) return rc;
+    const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);
+    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_uv.ptr, ref_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ks));
+    if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_cur_uv.ptr, cur_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ks));
+    if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_status.ptr, status, n_features, cudaMemcpyHostToDevice, ks));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_offsets.ptr, h_offsets.data(), sizeof(int32_t) * h_offsets.size(), cudaMemcpyHostToDevice, ks));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_curmap.ptr, h_curmap.data(), sizeof(int32_t) * h_curmap.size(), cudaMemcpyHostToDevice, ks));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));  // the host vectors above go out of scope; the copy stream may start
+
+    const size_t plane = static_cast<size_t>(rows) * cols;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        const int p_lo = c * chunk_pairs, p_hi = p_lo + chunk_pairs < n_pairs ? p_lo + chunk_pairs : n_pairs;
+        const int np = p_hi - p_lo;
+        ftk_pyramid *pyr = ctx->stage_pyr[b];
+        const ftk::PyramidView &v = pyr->view;
+        // ---- copy stream: images of this chunk into staging buffer b (after its previous user finished computing)
+        if (c >= 2) FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(cs, ctx->ev_computed[b], 0));
+        uint8_t *dst_ref = const_cast<uint8_t *>(v.base[0]);
+        uint8_t *dst_cur = dst_ref + static_cast<size_t>(stage_pairs) * v.image_stride[0];
+        if (v.pitch[0] == cols) {
+            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_ref, v.image_stride[0], ref_images + p_lo * plane, plane, plane, np, cudaMemcpyHostToDevice, cs));
+            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_cur, v.image_stride[0], cur_images + p_lo * plane, plane, plane, np, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int i = 0; i < np; ++i) {
+                FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_ref + i * v.image_stride[0], v.pitch[0], ref_images + (p_lo + i) * plane, cols, cols, rows,
+                                                      cudaMemcpyHostToDevice, cs));
+                FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_cur + i * v.image_stride[0], v.pitch[0], cur_images + (p_lo + i) * plane, cols, cols, rows,
+                                                      cudaMemcpyHostToDevice, cs));
+            }
+        }
+        FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
+        // ---- compute stream: pyramids of the 2 * np images, then the chunk's features
+        FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ks, ctx->ev_copied[b], 0));
+        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, 0, np)) return rc;
+        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, stage_pairs, np)) return rc;
+        const int f_lo = feat_offsets[p_lo], f_hi = feat_offsets[p_hi];
+        if (f_hi > f_lo) {
+            ftk::KltLaunch a{};
+            a.p = *params;
+            a.ref = v;
+            a.cur = v;
+            a.n_pairs = np;
+            a.n_features = f_hi - f_lo;
+            a.has_prediction = has_prediction ? 1 : 0;
+            a.has_status = has_status ? 1 : 0;
+            a.single_level = 0;
+            a.ref_uv = static_cast<const float2 *>(ctx->d_ref_uv.ptr) + f_lo;
+            a.cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr) + f_lo;
+            a.status = static_cast<uint8_t *>(ctx->d_status.ptr) + f_lo;
+            a.feat_offsets = static_cast<const int *>(ctx->d_chunk_offsets.ptr) + chunk_table_start[c];
+            a.ref_image = nullptr;  // image p of the staging batch
+            a.cur_image = static_cast<const int *>(ctx->d_chunk_curmap.ptr);
+            int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr) + f_lo;
+            if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, np, a.n_features, d_feat_pair)) return rc;
+            a.feat_pair = d_feat_pair;
+            if (int rc = ftk::LaunchKltTrack(ctx, a)) return rc;
+        }
+        FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_computed[b], ks));
+    }
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, ctx->d_cur_uv.ptr, sizeof(float2) * n_features, cudaMemcpyDeviceToHost, ks));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, ctx->d_status.ptr, n_features, cudaMemcpyDeviceToHost, ks));
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));
     return FTK_OK;
 }
 

@@ -45,6 +45,11 @@ struct FtkBuffer {
 struct ftk_context {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // H2D of the next chunk while the current one computes (ftk_track_image_pairs)
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_computed[2] = {nullptr, nullptr};
+    ftk_pyramid *stage_pyr[2] = {nullptr, nullptr};  // double-buffered pyramid storage for the pipelined entry point
+    int stage_rows = 0, stage_cols = 0, stage_levels = 0, stage_pairs = 0;
     std::string error;
     uint64_t launches = 0;
     int sm_count = 0;
@@ -52,6 +57,7 @@ struct ftk_context {
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
+    FtkBuffer d_chunk_offsets, d_chunk_curmap;
     FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
 };
 

@@ -121,6 +121,15 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
                   const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
                   uint8_t *status, uint32_t flags);
 
+/* One call for the reference demo's whole timed region -- CreateImagePyramid x2 + TrackFeatures
+ * (test/test_optical_flow.cpp:69-73) -- over a batch of frame pairs given as HOST images (n_pairs tightly packed rows*cols
+ * images each; pinned memory recommended).  The batch is processed in chunks on two streams so the host-to-device copy of
+ * chunk k+1 overlaps pyramid construction and tracking of chunk k.  ref_uv / cur_uv / status / feat_offsets are host arrays
+ * with the semantics of ftk_klt_track (FTK_FLAG_NO_PREDICTION / FTK_FLAG_NO_STATUS apply; multi-level only). */
+int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
+                          const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
+                          uint8_t *status, uint32_t flags);
+
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of
  *      test/test_descriptor_matcher_brief.cpp:33-45 and test/test_descriptor_matcher_superpoint.cpp:32-34) --------

@@ -171,6 +171,37 @@ def test_klt_batch_of_pairs(ctx, oracle):
             assert_same(f"{variant}/{method} pair {p}", (True, cur_uv[sl], st[sl]), exp)
 
 
+def test_track_image_pairs_pipelined(ctx, oracle):
+    """ftk_track_image_pairs: host images in, chunked two-stream pipeline (40 pairs -> 8 chunks of 5), ragged feature counts."""
+    n_pairs, rows, cols, levels = 40, 96, 128, 3
+    rng = np.random.default_rng(12)
+    uniq = [S.make_pair(rows, cols, 24, pair_id=80 + p, border=8) for p in range(5)]
+    counts = rng.integers(0, 25, n_pairs)
+    counts[3] = 0
+    refs = np.stack([uniq[p % 5][0] for p in range(n_pairs)])
+    curs = np.stack([uniq[p % 5][1] for p in range(n_pairs)])
+    uvs = [uniq[p % 5][2][:counts[p]] for p in range(n_pairs)]
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    all_uv = np.concatenate(uvs)
+    for variant, method, half in [("basic", "inverse", 7), ("basic", "fast", 6), ("lssd", "fast", 4)]:
+        klt = make_tracker(ctx, variant, method, half)
+        ok, cur_uv, st = klt.TrackImagePairs(levels, refs, curs, offsets, all_uv)
+        assert ok
+        prm = po.make_params(variant, method, half=half)
+        cache = {}
+        for p in range(n_pairs):
+            if counts[p] == 0:
+                continue
+            u = p % 5
+            if u not in cache:
+                cache[u] = (oracle.pyramid_build(uniq[u][0], levels), oracle.pyramid_build(uniq[u][1], levels))
+            exp = oracle.klt_track(prm, cache[u][0], cache[u][1], uvs[p])
+            sl = slice(offsets[p], offsets[p + 1])
+            assert_same(f"pipelined {variant}/{method} pair {p}", (True, cur_uv[sl], st[sl]), exp)
+    ok, _, _ = klt.TrackImagePairs(levels, refs, curs, np.zeros(n_pairs + 1, np.int32), np.zeros((0, 2), np.float32))
+    assert not ok
+
+
 def test_klt_north_star_config(ctx, oracle):
     """BASELINE configs[0]: basic inverse, 4 levels, 15x15 patches, 200 features on a 752x480 pair."""
     ref, cur, uv, fwd = S.make_pair(480, 752, 200, pair_id=0)
