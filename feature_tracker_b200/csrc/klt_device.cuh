@@ -38,20 +38,35 @@ __device__ __forceinline__ Img LevelImage(const PyramidView &v, int image, int l
     return im;
 }
 
-__device__ __forceinline__ float PxI(const Img &im, int row, int col) { return static_cast<float>(__ldg(im.p + row * im.pitch + col)); }
+// uint8 pixel -> float.  cvt.rn.f32.s32 (I2FP, ALU pipe, 64 lanes/clk/SM) instead of the I2F.U16 (XU pipe, 16 lanes/clk/SM)
+// the compiler picks for a byte source: profiles/r1_microbench_pipe_rates.txt.
+__device__ __forceinline__ float PxToFloat(const uint8_t *p) {
+    const int v = __ldg(p);
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(v));
+    return f;
+}
+
+__device__ __forceinline__ float PxI(const Img &im, int row, int col) { return PxToFloat(im.p + row * im.pitch + col); }
 
 // GrayImage::GetPixelValueNoCheck(float,float) (oracle/shim/datatype_image.h): base pixel by truncation, fractions by
 // floor, ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11.
 __device__ __forceinline__ float PxF(const Img &im, float row, float col) {
-    const uint8_t *v = im.p + static_cast<int>(row) * im.pitch + static_cast<int>(col);
-    const float sr = fsub(row, floorf(row));
-    const float sc = fsub(col, floorf(col));
+    // Callers only sample positions inside the image (0 <= row, col < 2^24): there truncation == floor, so one F2I.FLOOR per
+    // axis yields both the base pixel and (converted back on the ALU pipe) the value floor() would return.
+    const int r = __float2int_rd(row), c = __float2int_rd(col);
+    const uint8_t *v = im.p + r * im.pitch + c;
+    float fr, fc;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(fr) : "r"(r));
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(fc) : "r"(c));
+    const float sr = fsub(row, fr);
+    const float sc = fsub(col, fc);
     const float ir = fsub(1.0f, sr);
     const float ic = fsub(1.0f, sc);
-    const float p00 = static_cast<float>(__ldg(v));
-    const float p01 = static_cast<float>(__ldg(v + 1));
-    const float p10 = static_cast<float>(__ldg(v + im.pitch));
-    const float p11 = static_cast<float>(__ldg(v + im.pitch + 1));
+    const float p00 = PxToFloat(v);
+    const float p01 = PxToFloat(v + 1);
+    const float p10 = PxToFloat(v + im.pitch);
+    const float p11 = PxToFloat(v + im.pitch + 1);
     return fadd(fadd(fadd(fmul(fmul(ic, ir), p00), fmul(fmul(sc, ir), p01)), fmul(fmul(ic, sr), p10)), fmul(fmul(sc, sr), p11));
 }
 

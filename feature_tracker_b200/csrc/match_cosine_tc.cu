@@ -26,14 +26,16 @@ namespace ftk {
 namespace {
 
 constexpr int kTileM = 128;      // reference rows per CTA (TMEM lanes)
-constexpr int kTileN = 128;      // current descriptors per MMA tile (TMEM columns)
+constexpr int kTileN = 256;      // current descriptors per MMA tile (TMEM columns); N = 256 keeps the smem operand reads (A 4 KB + B 8 KB per
+                                 // UMMA) under the 128 B/clk shared-memory bandwidth, N = 128 would sit exactly on it
 constexpr int kKBlock = 64;      // BF16 elements per 128-byte swizzle row
 constexpr int kMaxKBlocks = 4;   // K <= 256
-constexpr int kStages = 2;
-constexpr int kBoxBytes = kTileM * kKBlock * 2;  // 16 KiB: one TMA box (128 rows x 128 B)
+constexpr int kStages = 4;       // pipeline stage = one K block (64 wide) of a 256-row tile of the current set
+constexpr int kBoxBytesA = kTileM * kKBlock * 2;  // 16 KiB: one TMA box of the reference tile (128 rows x 128 B)
+constexpr int kBoxBytesB = kTileN * kKBlock * 2;  // 32 KiB: one TMA box of the current set (256 rows x 128 B)
 constexpr int kTcThreads = 192;
-constexpr int kTmemCols = 256;   // two 128-column fp32 accumulators
-constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytes * (1 + kStages) + 256;
+constexpr int kTmemCols = 512;   // two 256-column fp32 accumulators (all of TMEM)
+constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytesA + static_cast<size_t>(kStages) * kBoxBytesB + 256;
 
 // |dot(bf16(a_hat), bf16(b_hat)) - exact dot of the unit vectors| <= 2 * 2^-9 + 2^-18 (Cauchy-Schwarz), plus fp32
 // accumulation slack on both sides.
@@ -125,22 +127,36 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 
 // ---- kernels -----------------------------------------------------------------------------------------------------
 
-// norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA).
-__global__ void NormPrepKernel(const float *desc, int n, int dim, int k_pad, float *norm, __nv_bfloat16 *unit) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *a = desc + static_cast<size_t>(i) * dim;
-    float s = __fmul_rn(a[0], a[0]);
-    for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
-    const float nrm = __fsqrt_rn(s);
-    norm[i] = nrm;
-    // A descriptor without a usable norm has NaN distances to everything in the reference: NaN rows keep it out of every top-2.
-    const bool usable = nrm > 0.0f && isfinite(nrm);
-    __nv_bfloat16 *u = unit + static_cast<size_t>(i) * k_pad;
-    for (int k = 0; k < k_pad; ++k) {
-        float v = 0.0f;
-        if (k < dim) v = usable ? a[k] / nrm : __int_as_float(0x7FC00000);
-        u[k] = __float2bfloat16_rn(v);
+// norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA) -- and the
+// unit-normalised BF16 copy.  32 descriptors per block: rows are staged through shared memory so global reads and writes are
+// coalesced while each row's sum of squares is still accumulated by one thread in ascending k.
+constexpr int kPrepRows = 32;
+constexpr int kPrepThreads = 128;
+__global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *desc, int n, int dim, int k_pad, float *norm, __nv_bfloat16 *unit) {
+    extern __shared__ float prep_smem[];  // [kPrepRows][dim + 1] + [kPrepRows]
+    const int stride = dim + 1;
+    float *s_norm = prep_smem + kPrepRows * stride;
+    const int row0 = blockIdx.x * kPrepRows;
+    const int rows = min(kPrepRows, n - row0);
+    for (int t = threadIdx.x; t < rows * dim; t += kPrepThreads) {
+        const int r = t / dim, k = t - r * dim;
+        prep_smem[r * stride + k] = __ldg(desc + static_cast<size_t>(row0) * dim + t);
+    }
+    __syncthreads();
+    if (threadIdx.x < rows) {
+        const float *a = prep_smem + threadIdx.x * stride;
+        float s = __fmul_rn(a[0], a[0]);
+        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
+        const float nrm = __fsqrt_rn(s);
+        norm[row0 + threadIdx.x] = nrm;
+        // A descriptor without a usable norm has NaN distances to everything in the reference: NaN rows keep it out of every top-2.
+        s_norm[threadIdx.x] = (nrm > 0.0f && isfinite(nrm)) ? nrm : __int_as_float(0x7FC00000);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < rows * k_pad; t += kPrepThreads) {
+        const int r = t / k_pad, k = t - r * k_pad;
+        const float v = k < dim ? prep_smem[r * stride + k] / s_norm[r] : 0.0f;  // x / NaN = NaN
+        unit[static_cast<size_t>(row0) * k_pad + t] = __float2bfloat16_rn(v);
     }
 }
 
@@ -150,14 +166,14 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages * kMaxKBlocks * kBoxBytes);
+    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytesA;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages * kBoxBytesB);
     uint64_t *bar_a = &bars[0];
-    uint64_t *bar_full = &bars[1];        // [kStages]
-    uint64_t *bar_empty = &bars[3];       // [kStages]
-    uint64_t *bar_acc_full = &bars[5];    // [2]
-    uint64_t *bar_acc_empty = &bars[7];   // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[9]);
+    uint64_t *bar_full = &bars[1];                     // [kStages]
+    uint64_t *bar_empty = &bars[1 + kStages];          // [kStages]
+    uint64_t *bar_acc_full = &bars[1 + 2 * kStages];   // [2]
+    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages];  // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x;
@@ -188,18 +204,19 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            MbarExpectTx(bar_a, static_cast<uint32_t>(k_blocks) * kBoxBytes);
-            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2D(smem_a + kb * kBoxBytes, &map_ref, bar_a, kb * kKBlock, m_tile * kTileM);
+            MbarExpectTx(bar_a, static_cast<uint32_t>(k_blocks) * kBoxBytesA);
+            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2D(smem_a + kb * kBoxBytesA, &map_ref, bar_a, kb * kKBlock, m_tile * kTileM);
             int stage = 0;
             uint32_t phase = 0;
             for (int t = t_begin; t < t_end; ++t) {
-                MbarWait(&bar_empty[stage], phase ^ 1u);
-                MbarExpectTx(&bar_full[stage], static_cast<uint32_t>(k_blocks) * kBoxBytes);
-                for (int kb = 0; kb < k_blocks; ++kb)
-                    TmaLoad2D(smem_b + (stage * kMaxKBlocks + kb) * kBoxBytes, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN);
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1u;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    MbarWait(&bar_empty[stage], phase ^ 1u);
+                    MbarExpectTx(&bar_full[stage], kBoxBytesB);
+                    TmaLoad2D(smem_b + stage * kBoxBytesB, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
             }
         }
@@ -212,24 +229,25 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
             uint32_t phase = 0, acc_phase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
-                MbarWait(&bar_full[stage], phase);
                 TcFenceAfter();
                 const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytes);
-                    const uint64_t bdesc = MakeSmemDesc(smem_b + (stage * kMaxKBlocks + kb) * kBoxBytes);
+                    MbarWait(&bar_full[stage], phase);
+                    TcFenceAfter();
+                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytesA);
+                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB);
 #pragma unroll
                     for (int k = 0; k < kKBlock / 16; ++k) {
                         // each UMMA consumes K = 16 BF16 = 32 bytes of the 128-byte swizzle row: advance the start address by 32 B
                         UmmaBf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
                     }
+                    UmmaCommit(&bar_empty[stage]);  // the stage's operands may be overwritten once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
-                UmmaCommit(&bar_empty[stage]);     // the stage's operands may be overwritten once these MMAs retire
-                UmmaCommit(&bar_acc_full[acc]);    // ... and the accumulator is complete
-                if (++stage == kStages) {
-                    stage = 0;
-                    phase ^= 1u;
-                }
+                UmmaCommit(&bar_acc_full[acc]);  // the accumulator is complete
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -240,7 +258,7 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int row = m_tile * kTileM + quarter * 32 + lane;
         float b1 = -INFINITY, b2 = -INFINITY;
-        int j1 = -1, j2 = -1;
+        int j1 = -1;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = t_begin; t < t_end; ++t) {
@@ -259,20 +277,34 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
                     for (int c = 0; c < 32; ++c)
                         if (c0 + c >= n_cur) r[c] = 0xFF800000u;  // -inf: zero-filled columns past the end never win
                 }
-                float m = __uint_as_float(r[0]);
+                // chunk maximum with a shallow tree (fmaxf drops NaN)
+                float m4[8];
 #pragma unroll
-                for (int c = 1; c < 32; ++c) m = fmaxf(m, __uint_as_float(r[c]));  // fmaxf drops NaN
-                if (m > b2) {
+                for (int q = 0; q < 8; ++q)
+                    m4[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                if (m > b1) {
+                    // A new best lives in this chunk (rare per lane): locate it (lowest column on ties) and the chunk's runner-up.
+                    // Only the VALUE of the overall second best is needed later (rows whose two best are both inside the
+                    // error margin are re-scanned exactly), so no index is kept for it.
+                    float cb1 = -INFINITY, cb2 = -INFINITY;
+                    int cj = 0;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const float v = __uint_as_float(r[c]);
-                        if (v > b1) {
-                            b2 = b1, j2 = j1;
-                            b1 = v, j1 = c0 + c;
-                        } else if (v > b2) {
-                            b2 = v, j2 = c0 + c;
+                        if (v > cb1) {
+                            cb2 = cb1;
+                            cb1 = v;
+                            cj = c;
+                        } else {
+                            cb2 = fmaxf(cb2, v);
                         }
                     }
+                    b2 = fmaxf(b1, cb2);  // old best and the chunk's runner-up compete for second place (old b2 <= old b1)
+                    b1 = cb1;
+                    j1 = c0 + cj;
+                } else {
+                    b2 = fmaxf(b2, m);  // m <= b1: the chunk can only improve the second place
                 }
             }
             TcFenceBefore();
@@ -283,7 +315,7 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         }
         if (row < n_ref) {
             Top2 o;
-            o.b1 = b1, o.j1 = j1, o.b2 = b2, o.j2 = j2;
+            o.b1 = b1, o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;  // j2 only says whether a second candidate exists
             out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
         }
     }
@@ -311,35 +343,57 @@ __device__ __forceinline__ float ExactDistance(const float *a, const float *b, i
     return __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
 }
 
-// One thread per reference row: exact re-evaluation of the candidates inside the error margin.
-__global__ void RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm, const float *cur_norm, const Top2 *top,
-                             int n_splits, int n_ref_pad, unsigned long long *best, int2 *work, int *n_work) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ref) return;
-    float gmax = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) gmax = fmaxf(gmax, top[static_cast<size_t>(s) * n_ref_pad + i].b1);
-    unsigned long long key = kNoKey64;
-    if (gmax > -INFINITY) {
+// Exact distance evaluated by a warp: the lanes load both descriptors coalesced and form the 256 products in parallel (each
+// product is one correctly rounded operation, exactly the reference's), lane 0 then adds them in ascending k -- the
+// reference's summation order -- so the value is bit-identical to ExactDistance().  `prod` = dim floats of shared memory.
+__device__ __forceinline__ float WarpExactDistance(const float *a, const float *b, int dim, float na, float nb, float *prod) {
+    const int lane = threadIdx.x & 31;
+    for (int k = lane; k < dim; k += 32) prod[k] = __fmul_rn(__ldg(a + k), __ldg(b + k));
+    __syncwarp();
+    float d = 0.0f;
+    if (lane == 0) {
+        float s = prod[0];
+        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);
+        d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
+    }
+    __syncwarp();
+    return __shfl_sync(0xFFFFFFFFu, d, 0);
+}
+
+// One warp per reference row: exact re-evaluation of the candidates inside the error margin.
+constexpr int kRerankWarps = 4;
+__global__ void __launch_bounds__(kRerankWarps * 32) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
+                                                                 const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
+                                                                 unsigned long long *best, int2 *work, int *n_work) {
+    extern __shared__ float rerank_smem[];  // [kRerankWarps][dim]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *prod = rerank_smem + warp * dim;
+    for (int i = blockIdx.x * kRerankWarps + warp; i < n_ref; i += gridDim.x * kRerankWarps) {
+        float gmax = -INFINITY;
+        for (int s = lane; s < n_splits; s += 32) gmax = fmaxf(gmax, top[static_cast<size_t>(s) * n_ref_pad + i].b1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+        if (!(gmax > -INFINITY)) continue;
         const float thr = gmax - 2.0f * kEpsDot;
         const float *a = ref + static_cast<size_t>(i) * dim;
         const float na = ref_norm[i];
-        for (int s = 0; s < n_splits; ++s) {
+        unsigned long long key = kNoKey64;
+        for (int s = 0; s < n_splits; ++s) {  // warp-uniform loop
             const Top2 t = top[static_cast<size_t>(s) * n_ref_pad + i];
             if (t.j1 < 0 || !(t.b1 >= thr)) continue;
             if (t.j2 >= 0 && t.b2 >= thr) {
                 // both of this split's best are inside the margin: a third candidate could hide behind them
-                const int slot = atomicAdd(n_work, 1);
-                work[slot] = make_int2(i, s);
+                if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, s);
                 continue;
             }
-            const float d = ExactDistance(a, cur + static_cast<size_t>(t.j1) * dim, dim, na, cur_norm[t.j1]);
+            const float d = WarpExactDistance(a, cur + static_cast<size_t>(t.j1) * dim, dim, na, cur_norm[t.j1], prod);
             if (d == d) {
                 const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(t.j1);
                 key = k < key ? k : key;
             }
         }
+        if (lane == 0 && key != kNoKey64) atomicMin(&best[i], key);
     }
-    if (key != kNoKey64) atomicMin(&best[i], key);
 }
 
 // One block per flagged (row, split): exact scan of the split's column range.
@@ -398,13 +452,13 @@ EncodeTiledFn GetEncodeTiled() {
     return fn;
 }
 
-// [rows][k_pad] BF16, K-major; box = 64 elements x 128 rows, 128B swizzle, out-of-range rows read as zero.
-bool MakeMap(CUtensorMap *map, const __nv_bfloat16 *base, int rows, int k_pad) {
+// [rows][k_pad] BF16, K-major; box = 64 elements x box_rows rows, 128B swizzle, out-of-range rows read as zero.
+bool MakeMap(CUtensorMap *map, const __nv_bfloat16 *base, int rows, int k_pad, int box_rows) {
     EncodeTiledFn encode = GetEncodeTiled();
     if (!encode) return false;
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_pad) * 2};
-    const cuuint32_t box[2] = {kKBlock, kTileM};
+    const cuuint32_t box[2] = {kKBlock, static_cast<cuuint32_t>(box_rows)};
     const cuuint32_t elem[2] = {1, 1};
     return encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(base), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -422,10 +476,25 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     cudaStream_t st = ctx->stream;
     const int k_blocks = (dim + kKBlock - 1) / kKBlock, k_pad = k_blocks * kKBlock;
     const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + kTileN - 1) / kTileN;
-    // split the current set across CTAs until the grid covers the GPU about once
-    int splits = (ctx->sm_count + m_tiles - 1) / m_tiles;
-    if (splits > n_tiles) splits = n_tiles;
-    if (splits < 1) splits = 1;
+    // Split the current set across CTAs: one CTA per SM at a time (192 KB of shared memory), so pick the split count whose
+    // grid fills whole waves best (ties: fewer splits = more reuse of the resident reference tile).
+    int splits = 1;
+    {
+        double best_eff = -1.0;
+        const int max_splits = n_tiles < 16 ? n_tiles : 16;
+        for (int sp = 1; sp <= max_splits; ++sp) {
+            const int per = (n_tiles + sp - 1) / sp, real = (n_tiles + per - 1) / per;
+            const long long ctas = static_cast<long long>(m_tiles) * real;
+            const long long waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
+            // time ~ waves * tiles per CTA (+ one tile-equivalent for loading the reference tile)
+            const double cost = static_cast<double>(waves) * (per + 1.0);
+            const double eff = 1.0 / cost;
+            if (eff > best_eff * 1.02) {
+                best_eff = eff;
+                splits = real;
+            }
+        }
+    }
     const int tiles_per_split = (n_tiles + splits - 1) / splits;
     splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_ref_pad = m_tiles * kTileM;
@@ -447,11 +516,12 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     int2 *work = reinterpret_cast<int2 *>(n_work + 2);
 
     CUtensorMap map_ref, map_cur;
-    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad))
+    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, kTileN))
         return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
 
-    NormPrepKernel<<<Blocks(n_ref, 128), 128, 0, st>>>(d_ref, n_ref, dim, k_pad, ref_norm, ref_unit);
-    NormPrepKernel<<<Blocks(n_cur, 128), 128, 0, st>>>(d_cur, n_cur, dim, k_pad, cur_norm, cur_unit);
+    const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * (dim + 1) + kPrepRows);
+    NormPrepKernel<<<Blocks(n_ref, kPrepRows), kPrepThreads, prep_smem, st>>>(d_ref, n_ref, dim, k_pad, ref_norm, ref_unit);
+    NormPrepKernel<<<Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_cur, n_cur, dim, k_pad, cur_norm, cur_unit);
     FillKeysKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, n_work);
 
     static bool attr_set = false;
@@ -460,7 +530,8 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
         attr_set = true;
     }
     CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad);
-    RerankKernel<<<Blocks(n_ref, 128), 128, 0, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, n_work);
+    RerankKernel<<<ctx->sm_count * 8, kRerankWarps * 32, sizeof(float) * kRerankWarps * dim, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
+                                                                                                  n_ref_pad, best, work, n_work);
     ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
     FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
     ctx->launches += 7;
