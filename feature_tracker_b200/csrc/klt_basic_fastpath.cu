@@ -34,16 +34,18 @@ struct __align__(16) Entry {
     int base;  // floor(x) as an integer (limited to [-64, n + 64]); for in-bounds x it is the reference's static_cast<int32_t>(x)
     float s;   // fraction  (x - floor(x))
     float i;   // 1 - fraction
-    int ok;    // !(x < 0 || x > n - 1)   (GrayImage::GetPixelValue bounds test)
+    int off;   // row tables: byte offset (clamped, always addressable) of the image row the rolling strip loads next
 };
 
-__device__ __forceinline__ Entry MakeEntry(float x, int n) {
+// ok = !(x < 0 || x > n - 1): the GrayImage::GetPixelValue bounds test.
+__device__ __forceinline__ Entry MakeEntry(float x, int n, bool *ok) {
     Entry e;
     const float f = floorf(x);
     e.s = fsub(x, f);
     e.i = fsub(1.0f, e.s);
-    e.ok = !(x < 0.0f || x > static_cast<float>(n - 1));
+    *ok = !(x < 0.0f || x > static_cast<float>(n - 1));
     e.base = min(max(static_cast<int>(f), -64), n + 64);
+    e.off = 0;
     return e;
 }
 
@@ -63,7 +65,7 @@ __device__ __forceinline__ float LoadPx(const uint8_t *p) {
 }
 
 // A sample addressed through (row entry, column entry): loads its four bytes directly.  Out-of-image entries are
-// clamped to an addressable pixel; their value is never used (the sample's `ok` is false).
+// clamped to an addressable pixel; their value is never used (the pixel's validity bit is clear).
 __device__ __forceinline__ float SampleDirect(const Img &im, const Entry &R, const Entry &C) {
     const uint8_t *p = im.p + Clamp(R.base, 0, im.rows - 1) * im.pitch + Clamp(C.base, 0, im.cols - 1);
     return Bilerp(R, C, LoadPx(p), LoadPx(p + 1), LoadPx(p + im.pitch), LoadPx(p + im.pitch + 1));
@@ -89,13 +91,20 @@ struct Lanes {
     int lane;            // 0..15 inside the group
     int base;            // 0 or 16
     unsigned mask;       // the group's 16 lanes
-    __device__ __forceinline__ int count(bool pred) const { return __popc(__ballot_sync(kFull, pred) & mask); }
+    // bit r of the result = pred of group lane r
+    __device__ __forceinline__ unsigned bits(bool pred) const { return (__ballot_sync(kFull, pred) >> base) & 0xFFFFu; }
     __device__ __forceinline__ bool any(bool pred) const { return (__ballot_sync(kFull, pred) & mask) != 0u; }
     __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(kFull, v, base + src); }
+    __device__ __forceinline__ int sum(int v) const {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        return v;
+    }
 };
 
 // Lane k < K of each group folds the k-th term of the group's 16 pixels in pixel order (see klt_device.cuh Chain).
-template <int K>
+// SUBTRACT: acc -= term (the reference's `bias -= ...`), which equals acc += (-term) bit for bit.
+template <int K, bool SUBTRACT>
 __device__ __forceinline__ void Fold(float *term, const Lanes &g, float &acc) {
     __syncwarp();
     if (g.lane < K) {
@@ -103,27 +112,34 @@ __device__ __forceinline__ void Fold(float *term, const Lanes &g, float &acc) {
 #pragma unroll
         for (int q = 0; q < kG / 4; ++q) {
             const float4 v = t4[q];
-            acc = fadd(acc, v.x);
-            acc = fadd(acc, v.y);
-            acc = fadd(acc, v.z);
-            acc = fadd(acc, v.w);
+            if (SUBTRACT) {
+                acc = fsub(acc, v.x);
+                acc = fsub(acc, v.y);
+                acc = fsub(acc, v.z);
+                acc = fsub(acc, v.w);
+            } else {
+                acc = fadd(acc, v.x);
+                acc = fadd(acc, v.y);
+                acc = fadd(acc, v.z);
+                acc = fadd(acc, v.w);
+            }
         }
     }
     __syncwarp();
 }
 
-// Reference samples of one pyramid level -> fx, fy, I_ref per patch row (shared), validity mask, 3 Hessian chains.
+// Reference samples of one pyramid level -> fx, fy, I_ref per patch row (shared), 3 Hessian chains over the pixels of `okbits`.
 // The row loops are deliberately NOT unrolled: the fully unrolled kernel overflowed the instruction cache
 // (ncu: 12 "no_instruction" stall cycles per issued instruction).
 template <int PR, bool REGULAR, typename Smem>
 __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes &g, const Entry &C0, const Entry &Cm, const Entry &Cp,
-                                          bool cols_ok, unsigned &refmask, float &acc) {
+                                          unsigned okbits, float &acc) {
     // strip rows s0..s3: pixels (rb + j, cb + i), rb = base(Rm of the current patch row), cb = base(Cm).  Rows / columns
-    // outside the image are clamped to addressable ones: they only feed samples whose `ok` is false.
+    // outside the image are clamped to addressable ones: they only feed pixels whose validity bit is clear.
     float s0[4], s1[4], s2[4], s3[4];
     const uint8_t *colp = ref.p + Clamp(Cm.base, 0, ref.cols - 3);
-    int rr = sm.rows[1].base;  // image row of strip row s0
     if (REGULAR) {
+        const int rr = sm.rows[1].base;  // image row of strip row s0
         const uint8_t *p = colp + Clamp(rr, 0, ref.rows) * ref.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s0[i] = LoadPx(p + i);
@@ -133,15 +149,13 @@ __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes 
         p = colp + Clamp(rr + 2, 0, ref.rows) * ref.pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
-        rr += 3;
     }
 #pragma unroll 1
     for (int r = 0; r < PR; ++r) {
         const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
         float v0, v1, v2, v3, v4;
         if (REGULAR) {
-            const uint8_t *p = colp + Clamp(rr, 0, ref.rows) * ref.pitch;  // the new bottom row of the strip: base(Rp) + 1
-            ++rr;
+            const uint8_t *p = colp + R0.off;  // the new bottom row of the strip: base(Rp) + 1, clamped (precomputed)
 #pragma unroll
             for (int i = 0; i < 4; ++i) s3[i] = LoadPx(p + i);
             v0 = Bilerp(R0, Cm, s1[0], s1[1], s2[0], s2[1]);  // (row_i, col_i - 1)
@@ -162,28 +176,25 @@ __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes 
             v3 = SampleDirect(ref, Rp, C0);
             v4 = SampleDirect(ref, R0, C0);
         }
-        const bool ok = cols_ok && R0.ok && Rm.ok && Rp.ok;
+        const bool ok = (okbits >> r) & 1u;
         const float fx = fsub(v1, v0), fy = fsub(v3, v2);
         sm.fx[r][g.lane] = fx;
         sm.fy[r][g.lane] = fy;
         sm.iref[r][g.lane] = v4;
-        refmask |= ok ? (1u << r) : 0u;
         sm.term[0 * (kG + 4) + g.lane] = ok ? fmul(fx, fx) : 0.0f;
         sm.term[1 * (kG + 4) + g.lane] = ok ? fmul(fx, fy) : 0.0f;
         sm.term[2 * (kG + 4) + g.lane] = ok ? fmul(fy, fy) : 0.0f;
-        Fold<3>(sm.term, g, acc);
+        Fold<3, false>(sm.term, g, acc);
     }
 }
 
-// One Gauss-Newton iteration's pass over the patch: current-image sample, residual, 2 bias chains.
+// One Gauss-Newton iteration's pass over the patch: current-image sample, residual, 2 bias chains (acc -= g * ft).
 template <int PR, bool REGULAR, typename Smem>
-__device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lanes &g, const Entry &Cj, unsigned refmask, unsigned &okmask,
-                                            int &valid, float &acc) {
+__device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lanes &g, const Entry &Cj, unsigned okbits, float &acc) {
     const uint8_t *colp = cur.p + Clamp(Cj.base, 0, cur.cols - 1);
-    int rr = sm.rows[0].base;  // image row of the strip's top row
     float top0 = 0.0f, top1 = 0.0f;
     if (REGULAR) {
-        const uint8_t *p = colp + Clamp(rr, 0, cur.rows) * cur.pitch;
+        const uint8_t *p = colp + Clamp(sm.rows[0].base, 0, cur.rows) * cur.pitch;
         top0 = LoadPx(p);
         top1 = LoadPx(p + 1);
     }
@@ -192,8 +203,7 @@ __device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lane
         const Entry Rj = sm.rows[r];
         float v5;
         if (REGULAR) {
-            ++rr;
-            const uint8_t *p = colp + Clamp(rr, 0, cur.rows) * cur.pitch;
+            const uint8_t *p = colp + Rj.off;  // row base + 1, clamped (precomputed)
             const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
             v5 = Bilerp(Rj, Cj, top0, top1, bot0, bot1);
             top0 = bot0;
@@ -201,19 +211,17 @@ __device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lane
         } else {
             v5 = SampleDirect(cur, Rj, Cj);
         }
-        const bool ok = ((refmask >> r) & 1u) && Rj.ok && Cj.ok;
+        const bool ok = (okbits >> r) & 1u;
         const float ft = fsub(v5, sm.iref[r][g.lane]);
-        okmask |= ok ? (1u << r) : 0u;
-        sm.term[0 * (kG + 4) + g.lane] = ok ? -fmul(sm.fx[r][g.lane], ft) : 0.0f;
-        sm.term[1 * (kG + 4) + g.lane] = ok ? -fmul(sm.fy[r][g.lane], ft) : 0.0f;
-        valid += g.count(ok);
-        Fold<2>(sm.term, g, acc);
+        sm.term[0 * (kG + 4) + g.lane] = ok ? fmul(sm.fx[r][g.lane], ft) : 0.0f;
+        sm.term[1 * (kG + 4) + g.lane] = ok ? fmul(sm.fy[r][g.lane], ft) : 0.0f;
+        Fold<2, true>(sm.term, g, acc);
     }
 }
 
 template <int PR, int PC>
 __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) {
-    static_assert(PC <= kG && PR <= 32, "patch must fit one 16-lane group / one 32-bit row mask");
+    static_assert(PC <= kG && PR <= kG, "patch must fit one 16-lane group (lane = column; lane r also builds row r's table entry)");
     constexpr int HR = PR / 2, HC = PC / 2;
     __shared__ GroupSmem<PR, PC> smem_all[kGroupsPerBlock];
 
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
     const int lane = g.lane;
     const bool col_active = lane < PC;
     const float dcol = static_cast<float>(lane - HC);
+    constexpr unsigned kRowMask = (1u << PR) - 1u;
 
     const int pair = a.feat_pair[f];
     const int local = f - a.feat_offsets[pair];
@@ -256,60 +265,79 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
             float acc = 0.0f;
             {
                 const float col_i = fadd(dcol, ref_x);
-                const Entry C0 = MakeEntry(col_i, ref.cols);
-                const Entry Cm = MakeEntry(fsub(col_i, 1.0f), ref.cols);
-                const Entry Cp = MakeEntry(fadd(col_i, 1.0f), ref.cols);
+                bool c0_ok, cm_ok, cp_ok;
+                const Entry C0 = MakeEntry(col_i, ref.cols, &c0_ok);
+                const Entry Cm = MakeEntry(fsub(col_i, 1.0f), ref.cols, &cm_ok);
+                const Entry Cp = MakeEntry(fadd(col_i, 1.0f), ref.cols, &cp_ok);
+                // lane r builds the three row entries of patch row r
+                bool rows_ok = false, regular = Cm.base == C0.base - 1 && Cp.base == C0.base + 1 && ref.cols >= 4 && ref.rows >= 4;
+                int my_base = 0;
                 __syncwarp();
                 if (lane < PR) {
                     const float row_i = fadd(static_cast<float>(lane - HR), ref_y);
-                    sm.rows[3 * lane + 0] = MakeEntry(row_i, ref.rows);
-                    sm.rows[3 * lane + 1] = MakeEntry(fsub(row_i, 1.0f), ref.rows);
-                    sm.rows[3 * lane + 2] = MakeEntry(fadd(row_i, 1.0f), ref.rows);
+                    bool r0_ok, rm_ok, rp_ok;
+                    Entry R0 = MakeEntry(row_i, ref.rows, &r0_ok);
+                    const Entry Rm = MakeEntry(fsub(row_i, 1.0f), ref.rows, &rm_ok);
+                    const Entry Rp = MakeEntry(fadd(row_i, 1.0f), ref.rows, &rp_ok);
+                    R0.off = Clamp(Rp.base + 1, 0, ref.rows) * ref.pitch;  // the strip's new bottom row while processing this patch row
+                    sm.rows[3 * lane + 0] = R0;
+                    sm.rows[3 * lane + 1] = Rm;
+                    sm.rows[3 * lane + 2] = Rp;
+                    rows_ok = r0_ok && rm_ok && rp_ok;
+                    regular = regular && Rm.base == R0.base - 1 && Rp.base == R0.base + 1;
+                    my_base = R0.base;
                 }
+                // Do the integer bases advance regularly from one patch row to the next?
+                const int next_base = __shfl_down_sync(kFull, my_base, 1);
+                if (lane + 1 < PR) regular = regular && next_base == my_base + 1;
                 __syncwarp();
-                // Do the integer bases advance regularly?  (lane r checks patch row r; every lane its own three columns)
-                bool regular = Cm.base == C0.base - 1 && Cp.base == C0.base + 1 && ref.cols >= 4 && ref.rows >= 4;
-                if (lane < PR) {
-                    const int r0 = sm.rows[3 * lane].base;
-                    regular = regular && sm.rows[3 * lane + 1].base == r0 - 1 && sm.rows[3 * lane + 2].base == r0 + 1;
-                    if (lane + 1 < PR) regular = regular && sm.rows[3 * (lane + 1)].base == r0 + 1;
-                }
-                const bool cols_ok = C0.ok && Cm.ok && Cp.ok && col_active;
-                if (__all_sync(kFull, regular)) SetupRows<PR, true>(ref, sm, g, C0, Cm, Cp, cols_ok, refmask, acc);
-                else SetupRows<PR, false>(ref, sm, g, C0, Cm, Cp, cols_ok, refmask, acc);
+                const unsigned rows_ok_bits = g.bits(rows_ok) & kRowMask;
+                refmask = (c0_ok && cm_ok && cp_ok && col_active) ? rows_ok_bits : 0u;
+                if (__all_sync(kFull, regular)) SetupRows<PR, true>(ref, sm, g, C0, Cm, Cp, refmask, acc);
+                else SetupRows<PR, false>(ref, sm, g, C0, Cm, Cp, refmask, acc);
             }
             const float hfull00 = g.get(acc, 0), hfull01 = g.get(acc, 1), hfull11 = g.get(acc, 2);
 
             // ================= Gauss-Newton iterations (basic_klt.cpp:88-116) =================
             bool running = tracked;
             for (uint32_t iter = 0; iter < a.p.max_iteration && __any_sync(kFull, running); ++iter) {
-                const Entry Cj = MakeEntry(fadd(dcol, cur_x), cur.cols);
+                bool cj_ok;
+                const Entry Cj = MakeEntry(fadd(dcol, cur_x), cur.cols, &cj_ok);
+                bool row_ok = false, regular = true;
+                int my_base = 0;
                 __syncwarp();
-                if (lane < PR) sm.rows[lane] = MakeEntry(fadd(static_cast<float>(lane - HR), cur_y), cur.rows);
+                if (lane < PR) {
+                    Entry Rj = MakeEntry(fadd(static_cast<float>(lane - HR), cur_y), cur.rows, &row_ok);
+                    Rj.off = Clamp(Rj.base + 1, 0, cur.rows) * cur.pitch;
+                    sm.rows[lane] = Rj;
+                    my_base = Rj.base;
+                }
+                const int next_base = __shfl_down_sync(kFull, my_base, 1);
+                if (lane + 1 < PR) regular = next_base == my_base + 1;
                 __syncwarp();
-                bool regular = true;
-                if (lane + 1 < PR) regular = sm.rows[lane + 1].base == sm.rows[lane].base + 1;
+                // pixels that pass all six bounds tests this iteration; their count is the reference's num_of_valid_pixel
+                const unsigned rows_ok_bits = g.bits(row_ok);  // every lane votes (full-warp ballot)
+                const unsigned okbits = (cj_ok && col_active) ? (refmask & rows_ok_bits) : 0u;
+                const int valid = g.sum(__popc(okbits));
 
-                unsigned okmask = 0;
-                int valid = 0;
                 acc = 0.0f;
-                if (__all_sync(kFull, regular)) IterateRows<PR, true>(cur, sm, g, Cj, refmask, okmask, valid, acc);
-                else IterateRows<PR, false>(cur, sm, g, Cj, refmask, okmask, valid, acc);
+                if (__all_sync(kFull, regular)) IterateRows<PR, true>(cur, sm, g, Cj, okbits, acc);
+                else IterateRows<PR, false>(cur, sm, g, Cj, okbits, acc);
                 const float b[2] = {g.get(acc, 0), g.get(acc, 1)};
 
                 float h00 = hfull00, h01 = hfull01, h11 = hfull11;
-                const bool mask_changed = g.any(okmask != refmask);
+                const bool mask_changed = g.any(okbits != refmask);
                 if (__any_sync(kFull, mask_changed && running)) {
                     // Some reference-valid pixel left the current image: this iteration's Hessian runs over fewer pixels.
                     acc = 0.0f;
 #pragma unroll 1
                     for (int r = 0; r < PR; ++r) {
-                        const bool ok = (okmask >> r) & 1u;
+                        const bool ok = (okbits >> r) & 1u;
                         const float fx = sm.fx[r][lane], fy = sm.fy[r][lane];
                         term[0 * (kG + 4) + lane] = ok ? fmul(fx, fx) : 0.0f;
                         term[1 * (kG + 4) + lane] = ok ? fmul(fx, fy) : 0.0f;
                         term[2 * (kG + 4) + lane] = ok ? fmul(fy, fy) : 0.0f;
-                        Fold<3>(term, g, acc);
+                        Fold<3, false>(term, g, acc);
                     }
                     const float n00 = g.get(acc, 0), n01 = g.get(acc, 1), n11 = g.get(acc, 2);
                     if (mask_changed) h00 = n00, h01 = n01, h11 = n11;
