@@ -159,7 +159,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -429,7 +429,8 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "tracked_fraction": float((status_host == 1).mean()),
         "kernel_ms": {"pyramid": ms_pyr / args.steps, "klt": ms_klt / args.steps},
-        "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak, "traffic": None,
+        "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
+                             "traffic": (72.85e6 + 6.28e6) / 200 * 2 * n_pairs,  # ncu dram bytes per image (profiles/r1_ncu_traffic.json) x images
                              "peak_source": hbm_src, "algorithmic_bytes_per_launch": pyr_bytes},
     }
 
@@ -478,10 +479,18 @@ def run_b200(args):
         flops = iters * 20.0 * P + n_total * LEVELS * ((((2 * args.half + 3) ** 2) - 4) * 15.0 + 8.0 * P)
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
         tfs = flops / (ms_klt / args.steps * 1e-3) / 1e12
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["BasicInverseFastKernel"]
+            if args.variant == "basic" and args.method == "inverse" and args.half in (6, 7):
+                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["features_per_launch"] * n_total  # ncu capture scaled to this launch
+        except Exception:
+            pass
         line["roofline"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
-                            "frac": tfs / fp32_peak, "traffic": None,
+                            "frac": tfs / fp32_peak, "traffic": traffic,
                             "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
-                            "algorithmic_flops_per_launch": flops, "patch_iterations_per_feature": iters / n_total, "kernel": "KltKernel"}
+                            "algorithmic_flops_per_launch": flops, "patch_iterations_per_feature": iters / n_total,
+                            "kernel": "BasicInverseFastKernel<15,15>" if (args.variant, args.method, args.half) == ("basic", "inverse", 7) else "KltKernel"}
     if not args.no_extras and world == 1:
         try:
             line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps)

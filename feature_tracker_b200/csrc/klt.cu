@@ -38,12 +38,13 @@ struct Scratch {
     float *ex;         // extended ref patch (fast methods)
     float *dx, *dy;    // ref gradients (fast methods)
     float *curp;       // cur patch (lssd fast)
+    float *hoist;      // lssd inverse: per-level reference gradients / samples + this iteration's cur samples: 4 x p_floats
     uint8_t *exv;      // ex patch validity
     uint8_t *curv;     // cur patch validity (lssd fast)
 };
 
 struct SmemLayout {
-    int term_floats, ex_floats, p_floats, curp_floats, exv_bytes, curv_bytes, total_bytes;
+    int term_floats, ex_floats, p_floats, curp_floats, hoist_floats, exv_bytes, curv_bytes, total_bytes;
 };
 
 __host__ __device__ inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
@@ -59,7 +60,12 @@ __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G,
         l.exv_bytes = RoundUp(geo.esize, 16);
         l.curv_bytes = variant == FTK_VARIANT_LSSD ? RoundUp(geo.psize, 16) : 0;
     }
-    l.total_bytes = 4 * (l.term_floats + l.ex_floats + 2 * l.p_floats + l.curp_floats) + l.exv_bytes + l.curv_bytes;
+    int pair_floats = 2 * l.p_floats;  // dx, dy of the fast methods
+    if (variant == FTK_VARIANT_LSSD && method == kInverse) {
+        pair_floats = 0;
+        l.hoist_floats = 4 * RoundUp(geo.psize, 4);
+    }
+    l.total_bytes = 4 * (l.term_floats + l.ex_floats + pair_floats + l.curp_floats + l.hoist_floats) + l.exv_bytes + l.curv_bytes;
     l.total_bytes = RoundUp(l.total_bytes, 16);
     // Groups of one warp must start on different banks: make the group stride (in words) congruent to G modulo 32.
     if (G < 32)
@@ -80,6 +86,8 @@ __device__ __forceinline__ Scratch CarveScratch(unsigned char *base, const SmemL
     f += l.p_floats;
     s.curp = f;
     f += l.curp_floats;
+    s.hoist = f;
+    f += l.hoist_floats;
     uint8_t *b = reinterpret_cast<uint8_t *>(f);
     s.exv = b;
     b += l.exv_bytes;
@@ -684,12 +692,108 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
     return valid;
 }
 
+// kInverse only: the five reference samples of a pixel (lssd_klt.cpp:152-155, 202-206) do not depend on the iteration.  They are
+// evaluated once per level: gradients fx, fy and the centre sample go to shared memory, the "all five inside the image" bit to
+// a per-lane mask (bit q = this lane's pixel of chunk q).  Same values, same order of use as the reference's per-iteration
+// recomputation.
+template <int G>
+__device__ unsigned long long LssdHoistRef(Ctx<G> &c, const Img &ref, float ref_x, float ref_y) {
+    const int pf = RoundUp(c.geo.psize, 4);
+    float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf;
+    unsigned long long ref_bits = 0ull;
+    int chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        if (k < c.geo.psize) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            const float cm = fsub(col_i, 1.0f), cp = fadd(col_i, 1.0f), rm = fsub(row_i, 1.0f), rp = fadd(row_i, 1.0f);
+            if (PxInside(ref, row_i, cm) && PxInside(ref, row_i, cp) && PxInside(ref, rm, col_i) && PxInside(ref, rp, col_i) && PxInside(ref, row_i, col_i)) {
+                hfx[k] = fsub(PxF(ref, row_i, cp), PxF(ref, row_i, cm));
+                hfy[k] = fsub(PxF(ref, rp, col_i), PxF(ref, rm, col_i));
+                hv4[k] = PxF(ref, row_i, col_i);
+                ref_bits |= 1ull << chunk;
+            }
+        }
+    }
+    return ref_bits;
+}
+
+// lssd_klt.cpp:127-250 ConstructIncrementalFunction, kInverse, on top of the hoisted reference samples.
+template <int G>
+__device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ref_bits,
+                                    float (&H)[3][3], float (&b)[3]) {
+    const int pf = RoundUp(c.geo.psize, 4);
+    const float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf;
+    float *hv5 = c.s.hoist + 3 * pf;
+    int valid = 0;
+    unsigned long long ok_bits = 0ull;
+    c.ch.reset();
+    int chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        float t0 = 0.0f, t1 = 0.0f;
+        bool ok = false;
+        if ((ref_bits >> chunk) & 1ull) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            float row_j, col_j, v5;
+            LssdWarp(s, col_i, row_i, &col_j, &row_j);
+            ok = PxChecked(cur, row_j, col_j, &v5);
+            if (ok) {
+                t0 = hv4[k];
+                t1 = v5;
+                hv5[k] = v5;
+                ok_bits |= 1ull << chunk;
+            }
+        }
+        c.ch.put(c.g.lane, 0, t0);
+        c.ch.put(c.g.lane, 1, t1);
+        valid += c.g.count(ok);
+        c.ch.template fold<2>(c.g);
+    }
+    const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
+    const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
+
+    c.ch.reset();
+    chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        float t[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
+        if ((ok_bits >> chunk) & 1ull) {
+            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            const float jp0 = fdiv(hfx[k], ref_avg), jp1 = fdiv(hfy[k], ref_avg);
+            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
+            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
+            float J[3];
+            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
+            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
+            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
+            const float residual = fsub(fdiv(hv5[k], cur_avg), fdiv(hv4[k], ref_avg));
+            LssdTerms(J, residual, t);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
+        c.ch.template fold<9>(c.g);
+    }
+    LssdGather(c, H, b);
+    return valid;
+}
+
 // lssd_klt.cpp:96-125 TrackOneFeature.
 template <int METHOD, int G>
 __device__ void LssdTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, LssdState &s, uint8_t &status) {
+    unsigned long long ref_bits = 0ull;
+    if constexpr (METHOD == kInverse) ref_bits = LssdHoistRef<G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
         float H[3][3], b[3], v[3];
-        if (LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b) == 0) break;
+        int valid;
+        if constexpr (METHOD == kInverse) valid = LssdConstructHoisted<G>(c, cur, ref_x, ref_y, s, ref_bits, H, b);
+        else valid = LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b);
+        if (valid == 0) break;
         LdltSolve<3>(H, b, v);
         if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
             status = FTK_STATUS_NUMERIC_ERROR;
