@@ -426,7 +426,8 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
+                "api": "ftk_track_image_pairs (pinned host images + features in, host results out; H2D of chunk k+1 overlaps compute of chunk k)"},
         "tracked_fraction": float((status_host == 1).mean()),
         "kernel_ms": {"pyramid": ms_pyr / args.steps, "klt": ms_klt / args.steps},
         "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,

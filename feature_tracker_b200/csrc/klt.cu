@@ -295,6 +295,8 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
     }
     const float h00 = c.g.get(c.ch.acc, 0), h01 = c.g.get(c.ch.acc, 1), h11 = c.g.get(c.ch.acc, 2);
     const float A[2][2] = {{h00, h01}, {h01, h11}};
+    LdltFactors<2> factors;
+    LdltFactor<2>(A, factors);
 
     status = FTK_STATUS_LARGE_RESIDUAL;
     float last_squared_step = INFINITY;
@@ -336,7 +338,7 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
         if (valid == 0) break;
         const float b[2] = {c.g.get(c.ch.acc, 0), c.g.get(c.ch.acc, 1)};
         float v[2];
-        LdltSolve<2>(A, b, v);
+        LdltSolveFactored<2>(factors, b, v);
         if (IsNan(v[0]) || IsNan(v[1])) {
             status = FTK_STATUS_NUMERIC_ERROR;
             break;
@@ -514,6 +516,8 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
     H[1][2] = H[2][1] = H[0][3];
     H[1][4] = H[4][1] = H[0][5];
     H[3][4] = H[4][3] = H[2][3];
+    LdltFactors<6> factors;  // the Hessian is fixed for the level: factorise once (identical factors every iteration)
+    LdltFactor<6>(H, factors);
 
     float last_squared_step = INFINITY;
     uint32_t large_step_cnt = 0;
@@ -548,7 +552,7 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
         float b[6], z[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) b[q] = c.g.get(c.ch.acc, q);
-        LdltSolve<6>(H, b, z);
+        LdltSolveFactored<6>(factors, b, z);
         bool any_nan = false;
 #pragma unroll
         for (int q = 0; q < 6; ++q) any_nan = any_nan || IsNan(z[q]);

@@ -132,10 +132,18 @@ struct Chain {
 
 // ---- LDLT (Eigen LDLT<Lower> restated; oracle/shim/basic_type.h) ----------------------------------
 // Executed redundantly by every lane of a group on identical inputs (uniform control flow, no broadcast needed).
+// Factorisation and solve are separate so that a Hessian that stays constant over the iterations of a level (the fast
+// methods) is factorised once; the reference calls hessian.ldlt() every iteration, which yields the same factors each time.
 template <int N>
-__device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&b)[N], float (&x)[N]) {
+struct LdltFactors {
     float a[N][N];
     int tr[N];
+};
+
+template <int N>
+__device__ __forceinline__ void LdltFactor(const float (&A)[N][N], LdltFactors<N> &f) {
+    float(&a)[N][N] = f.a;
+    int(&tr)[N] = f.tr;
     float temp[N];
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -198,7 +206,12 @@ __device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&
             for (int i = k + 1; i < N; ++i) a[i][k] = fdiv(a[i][k], akk);
         }
     }
+}
 
+template <int N>
+__device__ __forceinline__ void LdltSolveFactored(const LdltFactors<N> &f, const float (&b)[N], float (&x)[N]) {
+    const float(&a)[N][N] = f.a;
+    const int(&tr)[N] = f.tr;
 #pragma unroll
     for (int i = 0; i < N; ++i) x[i] = b[i];
     for (int k = 0; k < N; ++k) {
@@ -222,6 +235,13 @@ __device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&
         x[k] = x[tr[k]];
         x[tr[k]] = t;
     }
+}
+
+template <int N>
+__device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&b)[N], float (&x)[N]) {
+    LdltFactors<N> f;
+    LdltFactor<N>(A, f);
+    LdltSolveFactored<N>(f, b, x);
 }
 
 }  // namespace ftk

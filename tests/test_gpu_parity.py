@@ -202,6 +202,30 @@ def test_track_image_pairs_pipelined(ctx, oracle):
     assert not ok
 
 
+def test_klt_temporal_sequence_shares_pyramids(ctx, oracle):
+    """in a sequence the cur frame of pair k is the ref frame of pair k+1.  One pyramid per frame, pairs
+    (k, k+1) addressed through the ref_image / cur_image maps; results equal tracking each pair on its own."""
+    rows, cols, levels, n_frames = 120, 160, 3, 4
+    base = S.make_image(rows, cols, seed=500)
+    frames = [base]
+    for k in range(1, n_frames):
+        frames.append(S.warp_image(frames[-1], seed=600 + k, max_shift=3.0, max_rot_deg=1.0)[0])
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, n_frames)
+    pyr.SetRawImages(np.stack(frames))
+    pyr.CreateImagePyramid()
+    uvs = [S.detect_features(frames[k], 30, seed=k, border=12) for k in range(n_frames - 1)]
+    offsets = np.arange(n_frames) * 30
+    klt = make_tracker(ctx, "basic", "inverse", 6)
+    ok, cur_uv, st = klt.TrackFeaturesBatch(pyr, pyr, offsets.astype(np.int32), np.concatenate(uvs), ref_image=np.arange(n_frames - 1),
+                                            cur_image=np.arange(1, n_frames))
+    assert ok
+    prm = po.make_params("basic", "inverse", half=6)
+    lv = [oracle.pyramid_build(f, levels) for f in frames]
+    for k in range(n_frames - 1):
+        exp = oracle.klt_track(prm, lv[k], lv[k + 1], uvs[k])
+        assert_same(f"sequence pair {k}", (True, cur_uv[30 * k:30 * (k + 1)], st[30 * k:30 * (k + 1)]), exp)
+
+
 def test_klt_north_star_config(ctx, oracle):
     """BASELINE configs[0]: basic inverse, 4 levels, 15x15 patches, 200 features on a 752x480 pair."""
     ref, cur, uv, fwd = S.make_pair(480, 752, 200, pair_id=0)
