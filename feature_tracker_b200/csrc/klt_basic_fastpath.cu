@@ -384,6 +384,227 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
     }
 }
 
+// =====================================================================================================================
+// kFast method (basic_klt_fast.cpp:7-195 + optical_flow.cpp:49-102), patches up to 14 columns wide (the reference's default
+// 13x13 instantiated).  The reference's fast method is integer-aligned by construction: the extended reference patch
+// ((2h+3)^2 samples) and every iteration's current patch use ONE set of bilinear weights over a window at floor(position),
+// and a sample is valid iff 0 <= row <= rows-2 && 0 <= col <= cols-2 -- separable in row and column.  Mapping: lane = column of
+// the extended patch (15 of 16 lanes for 13x13), two features per warp, rolling 2-byte strips, row validity as bit masks,
+// gradients from the neighbouring lanes (shuffles) and the previous / next extended rows (registers).
+// =====================================================================================================================
+template <int PR, int PC>
+struct FastSmem {
+    static constexpr int ER = PR + 2;
+    float term[5 * (kG + 4)];
+    float ex[ER][kG];            // extended reference patch, [row][lane]
+    float dx[PR][kG], dy[PR][kG];  // reference gradients of patch pixel (row, lane - 1)
+    static constexpr int kRawWords = 5 * (kG + 4) + ER * kG + 2 * PR * kG;
+    static constexpr int kPad = ((16 - kRawWords % 32) + 32) % 32;
+    float pad[kPad == 0 ? 32 : kPad];
+};
+
+// One weight set for a whole integer-aligned window (optical_flow.cpp:53-60, basic_klt_fast.cpp:109-116).
+struct WindowWeights {
+    float tl, tr, bl, br;
+    int int_row, int_col;
+};
+__device__ __forceinline__ WindowWeights MakeWindowWeights(float x, float y) {
+    WindowWeights w;
+    const float fr = floorf(y), fc = floorf(x);
+    const float dr = fsub(y, fr), dc = fsub(x, fc);
+    w.tl = fmul(fsub(1.0f, dr), fsub(1.0f, dc));
+    w.tr = fmul(fsub(1.0f, dr), dc);
+    w.bl = fmul(dr, fsub(1.0f, dc));
+    w.br = fmul(dr, dc);
+    w.int_row = min(max(static_cast<int>(fr), -(1 << 24)), 1 << 24);
+    w.int_col = min(max(static_cast<int>(fc), -(1 << 24)), 1 << 24);
+    return w;
+}
+__device__ __forceinline__ float WindowSample(const WindowWeights &w, float p00, float p01, float p10, float p11) {
+    return fadd(fadd(fadd(fmul(w.tl, p00), fmul(w.tr, p01)), fmul(w.bl, p10)), fmul(w.br, p11));
+}
+// bit r = (0 <= first + r <= limit) for r in [0, n)
+__device__ __forceinline__ unsigned RangeBits(int first, int n, int limit) {
+    unsigned bits = 0;
+#pragma unroll 1
+    for (int r = 0; r < n; ++r) bits |= (first + r >= 0 && first + r <= limit) ? (1u << r) : 0u;
+    return bits;
+}
+
+template <int PR, int PC>
+__global__ void __launch_bounds__(kThreads) BasicFastMethodKernel(KltLaunch a) {
+    constexpr int ER = PR + 2, EC = PC + 2;
+    static_assert(EC <= kG && ER <= 32, "extended patch must fit one 16-lane group");
+    __shared__ FastSmem<PR, PC> smem_all[kGroupsPerBlock];
+
+    Lanes g;
+    g.lane = threadIdx.x & (kG - 1);
+    g.base = (threadIdx.x & 31) - g.lane;
+    g.mask = 0xFFFFu << g.base;
+    const int group_in_block = threadIdx.x / kG;
+    const int f_raw = blockIdx.x * kGroupsPerBlock + group_in_block;
+    const bool exists = f_raw < a.n_features;
+    const int f = exists ? f_raw : a.n_features - 1;
+    FastSmem<PR, PC> &sm = smem_all[group_in_block];
+    float *term = sm.term;
+    const int lane = g.lane;
+
+    const int pair = a.feat_pair[f];
+    const int local = f - a.feat_offsets[pair];
+    const float2 ref_uv = a.ref_uv[f];
+    float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;
+    uint8_t status = a.has_status ? a.status[f] : static_cast<uint8_t>(FTK_STATUS_NOT_TRACKED);
+    const bool tracked = exists && static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
+
+    if (__any_sync(kFull, tracked)) {
+        const int ref_image = a.ref_image ? a.ref_image[pair] : pair;
+        const int cur_image = a.cur_image ? a.cur_image[pair] : pair;
+        const int levels = a.single_level ? 1 : a.ref.levels;
+        const float scale = static_cast<float>(1 << (levels - 1));
+        float ref_x = fdiv(ref_uv.x, scale), ref_y = fdiv(ref_uv.y, scale);
+        float cur_x = fdiv(cur_uv.x, scale), cur_y = fdiv(cur_uv.y, scale);
+
+        for (int level = levels - 1; level > -1; --level) {
+            const Img ref = LevelImage(a.ref, ref_image, level), cur = LevelImage(a.cur, cur_image, level);
+
+            // ============ ExtractExtendPatchInReferenceImage + PrecomputeJacobianAndHessian ============
+            const WindowWeights wr = MakeWindowWeights(ref_x, ref_y);
+            const int ex_row0 = wr.int_row - ER / 2, ex_col0 = wr.int_col - EC / 2;
+            const unsigned ex_rows_ok = RangeBits(ex_row0, ER, ref.rows - 2);                   // bit er
+            const int my_col = ex_col0 + lane;
+            const bool ex_col_ok = lane < EC && my_col >= 0 && my_col <= ref.cols - 2;
+            const unsigned ex_cols_ok = g.bits(ex_col_ok);                                       // bit lane
+            const int ex_valid = __popc(ex_rows_ok) * __popc(ex_cols_ok);                        // valid_pixel_num
+            // gradient of patch column (lane - 1) needs the extended columns lane - 1, lane, lane + 1
+            const bool grad_cols_ok = lane >= 1 && lane <= PC && ((ex_cols_ok >> (lane - 1)) & 7u) == 7u;
+
+            float acc = 0.0f;
+            {
+                const uint8_t *colp = ref.p + Clamp(my_col, 0, ref.cols - 1);
+                const uint8_t *p = colp + Clamp(ex_row0, 0, ref.rows) * ref.pitch;
+                float top0 = LoadPx(p), top1 = LoadPx(p + 1);
+                float e_prev2 = 0.0f, e_prev1 = 0.0f;  // extended rows er - 2, er - 1 of my column
+#pragma unroll 1
+                for (int er = 0; er < ER; ++er) {
+                    p = colp + Clamp(ex_row0 + er + 1, 0, ref.rows) * ref.pitch;
+                    const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
+                    const bool ok = ex_col_ok && ((ex_rows_ok >> er) & 1u);
+                    const float e = ok ? WindowSample(wr, top0, top1, bot0, bot1) : 0.0f;
+                    top0 = bot0;
+                    top1 = bot1;
+                    sm.ex[er][lane] = e;
+                    // horizontal neighbours of the PREVIOUS extended row (the centre row of patch row er - 2)
+                    const float left = __shfl_sync(kFull, e_prev1, (threadIdx.x & 31) - 1);
+                    const float right = __shfl_sync(kFull, e_prev1, (threadIdx.x & 31) + 1);
+                    if (er >= 2) {
+                        const int pr = er - 2;
+                        const bool gok = grad_cols_ok && ((ex_rows_ok >> pr) & 7u) == 7u;
+                        const float dx = gok ? fsub(right, left) : 0.0f;
+                        const float dy = gok ? fsub(e, e_prev2) : 0.0f;
+                        sm.dx[pr][lane] = dx;
+                        sm.dy[pr][lane] = dy;
+                        term[0 * (kG + 4) + lane] = gok ? fmul(dx, dx) : 0.0f;
+                        term[1 * (kG + 4) + lane] = gok ? fmul(dx, dy) : 0.0f;
+                        term[2 * (kG + 4) + lane] = gok ? fmul(dy, dy) : 0.0f;
+                        Fold<3, false>(term, g, acc);
+                    }
+                    e_prev2 = e_prev1;
+                    e_prev1 = e;
+                }
+            }
+            const float h00 = g.get(acc, 0), h01 = g.get(acc, 1), h11 = g.get(acc, 2);
+            const float A[2][2] = {{h00, h01}, {h01, h11}};
+            LdltFactors<2> factors;
+            LdltFactor<2>(A, factors);
+
+            // ============ iterations (basic_klt_fast.cpp:29-61) ============
+            bool running = tracked;
+            if (running && ex_valid == 0) {  // :16-19
+                status = FTK_STATUS_OUTSIDE;
+                running = false;
+            }
+            if (running) status = FTK_STATUS_LARGE_RESIDUAL;
+            float last_squared_step = INFINITY;
+            uint32_t large_step_cnt = 0;
+            for (uint32_t iter = 0; iter < a.p.max_iteration && __any_sync(kFull, running); ++iter) {
+                // ComputeBias: integer window at floor(cur), one weight set; my patch column is lane - 1
+                const WindowWeights wc = MakeWindowWeights(cur_x, cur_y);
+                const int row0 = wc.int_row - PR / 2, col = wc.int_col - PC / 2 + lane - 1;
+                const unsigned rows_ok = RangeBits(row0, PR, cur.rows - 2) & (ex_rows_ok >> 1);   // cur row valid && centre row of ex valid
+                const bool col_ok = lane >= 1 && lane <= PC && col >= 0 && col <= cur.cols - 2 && ex_col_ok;
+                const int valid = __popc(rows_ok) * __popc(g.bits(col_ok));
+                const uint8_t *colp = cur.p + Clamp(col, 0, cur.cols - 1);
+                const uint8_t *p = colp + Clamp(row0, 0, cur.rows) * cur.pitch;
+                float top0 = LoadPx(p), top1 = LoadPx(p + 1);
+                acc = 0.0f;
+#pragma unroll 1
+                for (int pr = 0; pr < PR; ++pr) {
+                    p = colp + Clamp(row0 + pr + 1, 0, cur.rows) * cur.pitch;
+                    const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
+                    const float cur_value = WindowSample(wc, top0, top1, bot0, bot1);
+                    top0 = bot0;
+                    top1 = bot1;
+                    const bool ok = col_ok && ((rows_ok >> pr) & 1u);
+                    const float dt = fsub(cur_value, sm.ex[pr + 1][lane]);
+                    term[0 * (kG + 4) + lane] = ok ? fmul(sm.dx[pr][lane], dt) : 0.0f;
+                    term[1 * (kG + 4) + lane] = ok ? fmul(sm.dy[pr][lane], dt) : 0.0f;
+                    Fold<2, true>(term, g, acc);
+                }
+                const float b[2] = {g.get(acc, 0), g.get(acc, 1)};
+                if (running) {
+                    if (valid == 0) {
+                        running = false;  // BREAK_IF(ComputeBias(...) == 0)
+                    } else {
+                        float v[2];
+                        LdltSolveFactored<2>(factors, b, v);
+                        if (v[0] != v[0] || v[1] != v[1]) {
+                            status = FTK_STATUS_NUMERIC_ERROR;
+                            running = false;
+                        } else {
+                            cur_x = fadd(cur_x, v[0]);
+                            cur_y = fadd(cur_y, v[1]);
+                            const float squared_step = fadd(fmul(v[0], v[0]), fmul(v[1], v[1]));
+                            if (squared_step < last_squared_step) {
+                                last_squared_step = squared_step;
+                                large_step_cnt = 0;
+                            } else {
+                                ++large_step_cnt;
+                                if (large_step_cnt >= a.p.max_tolerance_large_step) running = false;
+                            }
+                            if (running && squared_step < a.p.max_converge_step) {
+                                status = FTK_STATUS_TRACKED;
+                                running = false;
+                            }
+                        }
+                    }
+                }
+            }
+
+            if (level == 0) break;
+            ref_x = fmul(ref_x, 2.0f), ref_y = fmul(ref_y, 2.0f);
+            cur_x = fmul(cur_x, 2.0f), cur_y = fmul(cur_y, 2.0f);
+        }
+        if (tracked) {
+            cur_uv = make_float2(cur_x, cur_y);
+            const Img cur0 = LevelImage(a.cur, cur_image, 0);
+            if (IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;  // basic_klt.cpp:49-53
+        }
+    }
+    if (exists && g.lane == 0) {
+        a.cur_uv[f] = cur_uv;
+        a.status[f] = status;
+    }
+}
+
+template <int PR, int PC>
+int LaunchFastMethod(ftk_context *ctx, const KltLaunch &a) {
+    const int blocks = (a.n_features + kGroupsPerBlock - 1) / kGroupsPerBlock;
+    BasicFastMethodKernel<PR, PC><<<blocks, kThreads, 0, ctx->stream>>>(a);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
 template <int PR, int PC>
 int Launch(ftk_context *ctx, const KltLaunch &a) {
     const int blocks = (a.n_features + kGroupsPerBlock - 1) / kGroupsPerBlock;
@@ -397,7 +618,14 @@ int Launch(ftk_context *ctx, const KltLaunch &a) {
 
 // Returns FTK_ERR_UNSUPPORTED when no specialisation covers the configuration (the caller then uses the generic kernel).
 int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &a) {
-    if (a.p.variant != FTK_VARIANT_BASIC || a.p.method != FTK_METHOD_INVERSE) return FTK_ERR_UNSUPPORTED;
+    if (a.p.variant != FTK_VARIANT_BASIC) return FTK_ERR_UNSUPPORTED;
+    if (a.p.method >= FTK_METHOD_FAST || a.p.method < 0) {  // kFast, and kSse / kNeon which take the reference's `default:` branch
+        if (a.p.patch_row_half == 6 && a.p.patch_col_half == 6) return LaunchFastMethod<13, 13>(ctx, a);
+        if (a.p.patch_row_half == 5 && a.p.patch_col_half == 5) return LaunchFastMethod<11, 11>(ctx, a);
+        if (a.p.patch_row_half == 4 && a.p.patch_col_half == 4) return LaunchFastMethod<9, 9>(ctx, a);
+        return FTK_ERR_UNSUPPORTED;
+    }
+    if (a.p.method != FTK_METHOD_INVERSE) return FTK_ERR_UNSUPPORTED;
     if (a.p.patch_row_half == 7 && a.p.patch_col_half == 7) return Launch<15, 15>(ctx, a);
     if (a.p.patch_row_half == 6 && a.p.patch_col_half == 6) return Launch<13, 13>(ctx, a);
     return FTK_ERR_UNSUPPORTED;

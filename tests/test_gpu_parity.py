@@ -115,7 +115,8 @@ def test_klt_synthetic_vs_oracle(ctx, oracle, variant, method):
     uv = np.concatenate([uv, np.stack([rng.uniform(-6, 326, 60), rng.uniform(-6, 246, 60)], 1).astype(np.float32)])
     rl, cl = oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3)
     pyr = upload_levels(ctx, [rl, cl])
-    for half, half_col, lum, single in [(6, 6, False, False), (4, 5, True, False), (7, 7, False, True), (2, 9, False, False)]:
+    for half, half_col, lum, single in [(6, 6, False, False), (4, 5, True, False), (7, 7, False, True), (2, 9, False, False), (5, 5, False, False),
+                                        (4, 4, False, True), (6, 6, False, True), (7, 7, False, False)]:
         predict = (0.9995, -0.03, 0.03, 0.9995) if single else (1, 0, 0, 1)
         p = po.make_params(variant, method, half=half, half_col=half_col, max_points=1000, luminance=lum, predict=predict)
         exp = oracle.klt_track(p, rl, cl, uv, single_level=single)
