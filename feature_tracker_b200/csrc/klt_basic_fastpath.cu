@@ -385,6 +385,242 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
 }
 
 // =====================================================================================================================
+// kDirect method (basic_klt.cpp:151-177): the gradient comes from the CURRENT image at the moving position, so the five-sample
+// pass of SetupRows runs every iteration on `cur`; only the reference centre sample (and its bounds bit) is per-level work.
+// =====================================================================================================================
+
+// Reference centre sample of every patch pixel -> sm.iref (per level).
+template <int PR, bool REGULAR, typename Smem>
+__device__ __forceinline__ void RefCentreRows(const Img &ref, Smem &sm, const Lanes &g, const Entry &C0) {
+    const uint8_t *colp = ref.p + Clamp(C0.base, 0, ref.cols - 1);
+    float top0 = 0.0f, top1 = 0.0f;
+    if (REGULAR) {
+        const uint8_t *p = colp + Clamp(sm.rows[0].base, 0, ref.rows) * ref.pitch;
+        top0 = LoadPx(p);
+        top1 = LoadPx(p + 1);
+    }
+#pragma unroll 1
+    for (int r = 0; r < PR; ++r) {
+        const Entry R0 = sm.rows[r];
+        float v;
+        if (REGULAR) {
+            const uint8_t *p = colp + R0.off;
+            const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
+            v = Bilerp(R0, C0, top0, top1, bot0, bot1);
+            top0 = bot0;
+            top1 = bot1;
+        } else {
+            v = SampleDirect(ref, R0, C0);
+        }
+        sm.iref[r][g.lane] = v;
+    }
+}
+
+// One iteration: five current-image samples per pixel, 3 Hessian + 2 bias chains (bias terms stored negated).
+template <int PR, bool REGULAR, typename Smem>
+__device__ __forceinline__ void DirectRows(const Img &cur, Smem &sm, const Lanes &g, const Entry &C0, const Entry &Cm, const Entry &Cp, unsigned okbits,
+                                           float &acc) {
+    float s0[4], s1[4], s2[4], s3[4];
+    const uint8_t *colp = cur.p + Clamp(Cm.base, 0, cur.cols - 3);
+    if (REGULAR) {
+        const int rr = sm.rows[1].base;
+        const uint8_t *p = colp + Clamp(rr, 0, cur.rows) * cur.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s0[i] = LoadPx(p + i);
+        p = colp + Clamp(rr + 1, 0, cur.rows) * cur.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s1[i] = LoadPx(p + i);
+        p = colp + Clamp(rr + 2, 0, cur.rows) * cur.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
+    }
+#pragma unroll 1
+    for (int r = 0; r < PR; ++r) {
+        const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
+        float v0, v1, v2, v3, v5;
+        if (REGULAR) {
+            const uint8_t *p = colp + R0.off;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s3[i] = LoadPx(p + i);
+            v0 = Bilerp(R0, Cm, s1[0], s1[1], s2[0], s2[1]);
+            v1 = Bilerp(R0, Cp, s1[2], s1[3], s2[2], s2[3]);
+            v2 = Bilerp(Rm, C0, s0[1], s0[2], s1[1], s1[2]);
+            v3 = Bilerp(Rp, C0, s2[1], s2[2], s3[1], s3[2]);
+            v5 = Bilerp(R0, C0, s1[1], s1[2], s2[1], s2[2]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                s0[i] = s1[i];
+                s1[i] = s2[i];
+                s2[i] = s3[i];
+            }
+        } else {
+            v0 = SampleDirect(cur, R0, Cm);
+            v1 = SampleDirect(cur, R0, Cp);
+            v2 = SampleDirect(cur, Rm, C0);
+            v3 = SampleDirect(cur, Rp, C0);
+            v5 = SampleDirect(cur, R0, C0);
+        }
+        const bool ok = (okbits >> r) & 1u;
+        const float fx = fsub(v1, v0), fy = fsub(v3, v2), ft = fsub(v5, sm.iref[r][g.lane]);
+        sm.term[0 * (kG + 4) + g.lane] = ok ? fmul(fx, fx) : 0.0f;
+        sm.term[1 * (kG + 4) + g.lane] = ok ? fmul(fx, fy) : 0.0f;
+        sm.term[2 * (kG + 4) + g.lane] = ok ? fmul(fy, fy) : 0.0f;
+        sm.term[3 * (kG + 4) + g.lane] = ok ? -fmul(fx, ft) : 0.0f;
+        sm.term[4 * (kG + 4) + g.lane] = ok ? -fmul(fy, ft) : 0.0f;
+        Fold<5, false>(sm.term, g, acc);
+    }
+}
+
+template <int PR, int PC>
+__global__ void __launch_bounds__(kThreads) BasicDirectFastKernel(KltLaunch a) {
+    static_assert(PC <= kG && PR <= kG, "patch must fit one 16-lane group");
+    constexpr int HR = PR / 2, HC = PC / 2;
+    __shared__ GroupSmem<PR, PC> smem_all[kGroupsPerBlock];
+
+    Lanes g;
+    g.lane = threadIdx.x & (kG - 1);
+    g.base = (threadIdx.x & 31) - g.lane;
+    g.mask = 0xFFFFu << g.base;
+    const int group_in_block = threadIdx.x / kG;
+    const int f_raw = blockIdx.x * kGroupsPerBlock + group_in_block;
+    const bool exists = f_raw < a.n_features;
+    const int f = exists ? f_raw : a.n_features - 1;
+    GroupSmem<PR, PC> &sm = smem_all[group_in_block];
+    const int lane = g.lane;
+    const bool col_active = lane < PC;
+    const float dcol = static_cast<float>(lane - HC);
+    constexpr unsigned kRowMask = (1u << PR) - 1u;
+
+    const int pair = a.feat_pair[f];
+    const int local = f - a.feat_offsets[pair];
+    const float2 ref_uv = a.ref_uv[f];
+    float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;
+    uint8_t status = a.has_status ? a.status[f] : static_cast<uint8_t>(FTK_STATUS_NOT_TRACKED);
+    const bool tracked = exists && static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
+
+    if (__any_sync(kFull, tracked)) {
+        const int ref_image = a.ref_image ? a.ref_image[pair] : pair;
+        const int cur_image = a.cur_image ? a.cur_image[pair] : pair;
+        const int levels = a.single_level ? 1 : a.ref.levels;
+        const float scale = static_cast<float>(1 << (levels - 1));
+        float ref_x = fdiv(ref_uv.x, scale), ref_y = fdiv(ref_uv.y, scale);
+        float cur_x = fdiv(cur_uv.x, scale), cur_y = fdiv(cur_uv.y, scale);
+
+        for (int level = levels - 1; level > -1; --level) {
+            const Img ref = LevelImage(a.ref, ref_image, level), cur = LevelImage(a.cur, cur_image, level);
+
+            // ---- per level: reference centre samples and their bounds bits ----
+            unsigned ref_rows_ok;
+            bool ref_col_ok;
+            {
+                const Entry C0 = MakeEntry(fadd(dcol, ref_x), ref.cols, &ref_col_ok);
+                bool row_ok = false, regular = true;
+                int my_base = 0;
+                __syncwarp();
+                if (lane < PR) {
+                    Entry R0 = MakeEntry(fadd(static_cast<float>(lane - HR), ref_y), ref.rows, &row_ok);
+                    R0.off = Clamp(R0.base + 1, 0, ref.rows) * ref.pitch;
+                    sm.rows[lane] = R0;
+                    my_base = R0.base;
+                }
+                const int next_base = __shfl_down_sync(kFull, my_base, 1);
+                if (lane + 1 < PR) regular = next_base == my_base + 1;
+                __syncwarp();
+                ref_rows_ok = g.bits(row_ok) & kRowMask;
+                if (__all_sync(kFull, regular)) RefCentreRows<PR, true>(ref, sm, g, C0);
+                else RefCentreRows<PR, false>(ref, sm, g, C0);
+            }
+
+            // ---- Gauss-Newton iterations (basic_klt.cpp:88-116 with the kDirect branch of :151-177) ----
+            bool running = tracked;
+            for (uint32_t iter = 0; iter < a.p.max_iteration && __any_sync(kFull, running); ++iter) {
+                const float col_j = fadd(dcol, cur_x);
+                bool c0_ok, cm_ok, cp_ok;
+                const Entry C0 = MakeEntry(col_j, cur.cols, &c0_ok);
+                const Entry Cm = MakeEntry(fsub(col_j, 1.0f), cur.cols, &cm_ok);
+                const Entry Cp = MakeEntry(fadd(col_j, 1.0f), cur.cols, &cp_ok);
+                bool rows_ok = false, regular = Cm.base == C0.base - 1 && Cp.base == C0.base + 1 && cur.cols >= 4 && cur.rows >= 4;
+                int my_base = 0;
+                __syncwarp();
+                if (lane < PR) {
+                    const float row_j = fadd(static_cast<float>(lane - HR), cur_y);
+                    bool r0_ok, rm_ok, rp_ok;
+                    Entry R0 = MakeEntry(row_j, cur.rows, &r0_ok);
+                    const Entry Rm = MakeEntry(fsub(row_j, 1.0f), cur.rows, &rm_ok);
+                    const Entry Rp = MakeEntry(fadd(row_j, 1.0f), cur.rows, &rp_ok);
+                    R0.off = Clamp(Rp.base + 1, 0, cur.rows) * cur.pitch;
+                    sm.rows[3 * lane + 0] = R0;
+                    sm.rows[3 * lane + 1] = Rm;
+                    sm.rows[3 * lane + 2] = Rp;
+                    rows_ok = r0_ok && rm_ok && rp_ok;
+                    regular = regular && Rm.base == R0.base - 1 && Rp.base == R0.base + 1;
+                    my_base = R0.base;
+                }
+                const int next_base = __shfl_down_sync(kFull, my_base, 1);
+                if (lane + 1 < PR) regular = regular && next_base == my_base + 1;
+                __syncwarp();
+                const unsigned row_bits = g.bits(rows_ok) & ref_rows_ok;
+                const bool lane_gate = ref_col_ok && c0_ok && cm_ok && cp_ok && col_active;
+                const unsigned okbits = lane_gate ? row_bits : 0u;
+                const int valid = __popc(row_bits) * __popc(g.bits(lane_gate));  // the six bounds tests are separable in row and column
+
+                float acc = 0.0f;
+                if (__all_sync(kFull, regular)) DirectRows<PR, true>(cur, sm, g, C0, Cm, Cp, okbits, acc);
+                else DirectRows<PR, false>(cur, sm, g, C0, Cm, Cp, okbits, acc);
+                const float h00 = g.get(acc, 0), h01 = g.get(acc, 1), h11 = g.get(acc, 2);
+                const float b[2] = {g.get(acc, 3), g.get(acc, 4)};
+
+                if (running) {
+                    if (valid == 0) {
+                        running = false;
+                    } else {
+                        const float A[2][2] = {{h00, h01}, {h01, h11}};
+                        float v[2];
+                        LdltSolve<2>(A, b, v);
+                        if (v[0] != v[0] || v[1] != v[1]) {
+                            status = FTK_STATUS_NUMERIC_ERROR;
+                            running = false;
+                        } else {
+                            cur_x = fadd(cur_x, v[0]);
+                            cur_y = fadd(cur_y, v[1]);
+                            if (IsOutside(cur, cur_x, cur_y)) {
+                                status = FTK_STATUS_OUTSIDE;
+                                running = false;
+                            } else if (fadd(fmul(v[0], v[0]), fmul(v[1], v[1])) < a.p.max_converge_step) {
+                                status = FTK_STATUS_TRACKED;
+                                running = false;
+                            }
+                        }
+                    }
+                }
+            }
+
+            if (level == 0) break;
+            ref_x = fmul(ref_x, 2.0f), ref_y = fmul(ref_y, 2.0f);
+            cur_x = fmul(cur_x, 2.0f), cur_y = fmul(cur_y, 2.0f);
+        }
+        if (tracked) {
+            cur_uv = make_float2(cur_x, cur_y);
+            const Img cur0 = LevelImage(a.cur, cur_image, 0);
+            if (IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;
+        }
+    }
+    if (exists && g.lane == 0) {
+        a.cur_uv[f] = cur_uv;
+        a.status[f] = status;
+    }
+}
+
+template <int PR, int PC>
+int LaunchDirect(ftk_context *ctx, const KltLaunch &a) {
+    const int blocks = (a.n_features + kGroupsPerBlock - 1) / kGroupsPerBlock;
+    BasicDirectFastKernel<PR, PC><<<blocks, kThreads, 0, ctx->stream>>>(a);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+// =====================================================================================================================
 // kFast method (basic_klt_fast.cpp:7-195 + optical_flow.cpp:49-102), patches up to 14 columns wide (the reference's default
 // 13x13 instantiated).  The reference's fast method is integer-aligned by construction: the extended reference patch
 // ((2h+3)^2 samples) and every iteration's current patch use ONE set of bilinear weights over a window at floor(position),
@@ -625,7 +861,11 @@ int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &a) {
         if (a.p.patch_row_half == 4 && a.p.patch_col_half == 4) return LaunchFastMethod<9, 9>(ctx, a);
         return FTK_ERR_UNSUPPORTED;
     }
-    if (a.p.method != FTK_METHOD_INVERSE) return FTK_ERR_UNSUPPORTED;
+    if (a.p.method == FTK_METHOD_DIRECT) {
+        if (a.p.patch_row_half == 7 && a.p.patch_col_half == 7) return LaunchDirect<15, 15>(ctx, a);
+        if (a.p.patch_row_half == 6 && a.p.patch_col_half == 6) return LaunchDirect<13, 13>(ctx, a);
+        return FTK_ERR_UNSUPPORTED;
+    }
     if (a.p.patch_row_half == 7 && a.p.patch_col_half == 7) return Launch<15, 15>(ctx, a);
     if (a.p.patch_row_half == 6 && a.p.patch_col_half == 6) return Launch<13, 13>(ctx, a);
     return FTK_ERR_UNSUPPORTED;
