@@ -247,6 +247,7 @@ def run_extras(ctx, L, torch, local_rank, steps):
     klt_case("C2_affine_fast_13x13", "affine", "fast", 6, ROWS, COLS, 100, 2000)
     klt_case("basic_fast_13x13_reference_default", "basic", "fast", 6, ROWS, COLS, 100, 2000)
     klt_case("basic_direct_15x15", "basic", "direct", 7, ROWS, COLS, 100, 2000)
+    klt_case("basic_inverse_15x15_100pairs", "basic", "inverse", 7, ROWS, COLS, 100, 2000)
     klt_case("C3_lssd_inverse_21x21_1280x720", "lssd", "inverse", 10, 720, 1280, 4, 10000, unique=2)
 
     # ---- C4: BRIEF-256 force 10k x 10k + nearby ----

@@ -140,6 +140,13 @@ def test_klt_entry_semantics(ctx, oracle):
     pred = uv + np.float32(0.5)
     assert_same("skip", klt.TrackFeatures(pyr, pyr, uv, cur_pixel_uv=pred, status=st_in, ref_image=0, cur_image=1),
                 oracle.klt_track(p, rl, cl, uv, cur_uv=pred, status=st_in))
+    # kSse / kNeon take the reference's `default:` branch, i.e. behave exactly like kFast (basic_klt.cpp:31-34)
+    for half in (4, 7):
+        fast = make_tracker(ctx, "basic", "fast", half)
+        sse = make_tracker(ctx, "basic", "fast", half)
+        sse.options().kMethod = ft.OpticalFlowMethod.kSse
+        a, b = fast.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1), sse.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+        assert (a[2] == b[2]).all() and bits_equal(a[1], b[1])
     # level mismatch -> false (optical_flow.cpp:9)
     other = ft.ImagePyramidBatch(ctx, 120, 160, 3, 1)
     ok, _, _ = klt.TrackFeatures(pyr, other, uv, ref_image=0, cur_image=0)
