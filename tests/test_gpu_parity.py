@@ -408,3 +408,70 @@ def test_hamming_c4_full_size_properties(ctx):
     assert (idx[sample] == exp).all()
     ok, nidx = m.NearbyMatch(pr, pc, pred, pos)
     assert ok and (nidx[has] == truth[has]).mean() > 0.95
+
+
+# ---- BASELINE.json full sizes ---------------------------------------------------------------------------------------------
+def test_klt_c2_full_batch_properties(ctx, oracle):
+    """BASELINE configs[1] batch shape at full size (1000 frame pairs x 2000 features, 752x480, 4 levels) for the north-star tracker
+    and the affine fast tracker: size-independent properties (identical pairs give identical results wherever they sit in the
+    batch) + the first copy of every unique pair checked against the oracle."""
+    n_pairs, n_feat, unique = 1000, 2000, 4
+    pairs = [S.make_pair(480, 752, n_feat, pair_id=300 + u) for u in range(unique)]
+    refs = np.stack([pairs[p % unique][0] for p in range(n_pairs)])
+    curs = np.stack([pairs[p % unique][1] for p in range(n_pairs)])
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2 * n_pairs)
+    pyr.SetRawImages(refs, first=0)
+    pyr.SetRawImages(curs, first=n_pairs)
+    del refs, curs
+    pyr.CreateImagePyramid()
+    uv = np.concatenate([pairs[p % unique][2] for p in range(n_pairs)])
+    offsets = (np.arange(n_pairs + 1) * n_feat).astype(np.int32)
+    lv = [(oracle.pyramid_build(pairs[u][0], 4), oracle.pyramid_build(pairs[u][1], 4)) for u in range(unique)]
+    for variant, method, half, check in [("basic", "inverse", 7, n_feat), ("affine", "fast", 6, 300)]:
+        klt = make_tracker(ctx, variant, method, half, max_points=n_feat)
+        ok, cur_uv, st = klt.TrackFeaturesBatch(pyr, pyr, offsets, uv, ref_image=np.arange(n_pairs), cur_image=np.arange(n_pairs) + n_pairs)
+        assert ok
+        cur_uv = cur_uv.reshape(n_pairs, n_feat, 2)
+        st = st.reshape(n_pairs, n_feat)
+        for u in range(unique):  # every copy of a unique pair equals the first copy, bit for bit
+            assert (cur_uv[u::unique].view(np.uint32) == cur_uv[u].view(np.uint32)).all() and (st[u::unique] == st[u]).all()
+            prm = po.make_params(variant, method, half=half, max_points=n_feat)
+            exp = oracle.klt_track(prm, lv[u][0], lv[u][1], pairs[u][2][:check])
+            assert_same(f"C2 full batch {variant}/{method} pair {u}", (True, cur_uv[u][:check], st[u][:check]), exp)
+        assert (st == 1).mean() > 0.95
+    pyr.close()
+
+
+def test_klt_c3_full_size(ctx, oracle):
+    """BASELINE configs[2] at full size: LSSD inverse, 21x21 patches, 10 000 features on a 1280x720 pair; the oracle needs a few
+    seconds for the 2 000 features that are compared one to one, the rest is covered by a permutation property."""
+    ref, cur, uv, _ = S.make_pair(720, 1280, 10000, pair_id=7)
+    pyr = ft.ImagePyramidBatch(ctx, 720, 1280, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, "lssd", "inverse", 10, max_points=10000)
+    ok, cur_uv, st = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    assert ok and (st == 1).mean() > 0.9
+    exp = oracle.klt_track(po.make_params("lssd", "inverse", half=10, max_points=10000), oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4), uv[:2000])
+    assert_same("C3 full size", (True, cur_uv[:2000], st[:2000]), exp)
+    perm = np.random.default_rng(3).permutation(10000)
+    ok, cur2, st2 = klt.TrackFeatures(pyr, pyr, uv[perm], ref_image=0, cur_image=1)
+    assert bits_equal(cur2, cur_uv[perm]) and (st2 == st[perm]).all()  # features are independent: order does not matter
+
+
+def test_cosine_c5_full_size_properties(ctx):
+    """BASELINE configs[4] at full size (20k x 20k x 256): planted matches recovered without the exact fall-back, idempotence,
+    row-permutation equivariance, and a sampled check of the reported arg-min against float64 numpy."""
+    rf, cf = S.make_float_sets(20000, 20000, seed=5)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.1
+    ok, idx = c.ForceMatch(rf, cf)
+    assert ok and (idx >= 0).all() and c.last_exact_scan_items() == 0
+    ok, idx2 = c.ForceMatch(rf, cf, idx.copy())
+    assert (idx2 == idx).all()
+    perm = np.random.default_rng(0).permutation(20000)
+    ok, idx3 = c.ForceMatch(rf[perm], cf)
+    assert (idx3 == idx[perm]).all()
+    sample = np.random.default_rng(1).integers(0, 20000, 128)
+    d = 0.5 - 0.5 * (rf[sample].astype(np.float64) @ cf.astype(np.float64).T)
+    assert (d.argmin(1) == idx[sample]).all() and (d.min(1) < 0.1).all()
