@@ -21,6 +21,7 @@
 //   CosineForceKernel  : exact fp32 distances with the reference's sequential k = 0..dim-1 summation order
 //                        (one chain per (ref, cur) pair, 4 independent pairs per thread for ILP).
 #include <cfloat>
+#include <cstring>
 
 #include "ftk_internal.h"
 
@@ -161,13 +162,37 @@ __global__ void BoundsKernel(const float2 *pos, int n, int *bounds) {
     atomicMax(&bounds[3], FloatToOrdered(p.y));
 }
 
+// Grid geometry from the bounding box of the finite positions: cells about one search window wide, at most 256 x 256.
+__global__ void GridSetupKernel(const int *bounds, int max_dcol, int max_drow, GridDesc *out) {
+    GridDesc g;
+    g.gw = g.gh = 1;
+    g.x0 = g.y0 = 0.0f;
+    g.inv_cw = g.inv_ch = 0.0f;
+    if (bounds[0] != 0x7FFFFFFF) {
+        const float x0 = OrderedToFloat(bounds[0]), y0 = OrderedToFloat(bounds[1]);
+        const float x1 = OrderedToFloat(bounds[2]), y1 = OrderedToFloat(bounds[3]);
+        float cw = static_cast<float>(max_dcol > 1 ? max_dcol : 1), ch = static_cast<float>(max_drow > 1 ? max_drow : 1);
+        const float span_x = x1 - x0, span_y = y1 - y0;
+        if (span_x / cw > 255.0f) cw = span_x / 255.0f;
+        if (span_y / ch > 255.0f) ch = span_y / 255.0f;
+        g.x0 = x0;
+        g.y0 = y0;
+        g.inv_cw = 1.0f / cw;
+        g.inv_ch = 1.0f / ch;
+        g.gw = min(static_cast<int>(span_x / cw) + 1, 256);
+        g.gh = min(static_cast<int>(span_y / ch) + 1, 256);
+    }
+    *out = g;
+}
+
 __device__ __forceinline__ int CellCoord(float v, float v0, float inv, int n) {
     const float c = floorf((v - v0) * inv);
     return c < 0.0f ? 0 : (c > static_cast<float>(n - 1) ? n - 1 : static_cast<int>(c));
 }
 
 // counts[cell] for finite positions; non-finite positions go to the "always a candidate" list.
-__global__ void CellCountKernel(const float2 *pos, int n, GridDesc g, int *counts, int *special, int *n_special) {
+__global__ void CellCountKernel(const float2 *pos, int n, const GridDesc *gp, int *counts, int *special, int *n_special) {
+    const GridDesc g = *gp;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float2 p = pos[j];
@@ -179,7 +204,8 @@ __global__ void CellCountKernel(const float2 *pos, int n, GridDesc g, int *count
 }
 
 // Exclusive scan of counts[0..n) into starts[0..n]; single block.
-__global__ void __launch_bounds__(1024) ScanKernel(const int *counts, int n, int *starts, int *cursor) {
+__global__ void __launch_bounds__(1024) ScanKernel(const int *counts, const GridDesc *gp, int *starts, int *cursor) {
+    const int n = gp->gw * gp->gh;
     __shared__ int partial[1024];
     const int per = (n + 1023) / 1024;
     const int begin = threadIdx.x * per, end = min(n, begin + per);
@@ -205,7 +231,8 @@ __global__ void __launch_bounds__(1024) ScanKernel(const int *counts, int n, int
     }
 }
 
-__global__ void CellFillKernel(const float2 *pos, int n, GridDesc g, int *cursor, int *sorted) {
+__global__ void CellFillKernel(const float2 *pos, int n, const GridDesc *gp, int *cursor, int *sorted) {
+    const GridDesc g = *gp;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const float2 p = pos[j];
@@ -313,12 +340,13 @@ __device__ void NearbyScan(const Dist &dist, int i, float2 pred, const float2 *p
 }
 
 template <typename Dist>
-__global__ void __launch_bounds__(128) NearbyKernel(Dist dist, int n_ref, const float2 *pred, const float2 *pos, int n_cur, GridDesc g, const int *starts,
+__global__ void __launch_bounds__(128) NearbyKernel(Dist dist, int n_ref, const float2 *pred, const float2 *pos, int n_cur, const GridDesc *gp, const int *starts,
                                                     const int *sorted, const int *special, const int *n_special_ptr, float max_dcol, float max_drow,
                                                     float max_dist, int *idx) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= n_ref) return;
     const int n_special = *n_special_ptr;
+    const GridDesc g = *gp;
     unsigned long long best;
     unsigned first_zero;
     NearbyScan(dist, i, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, 0xFFFFFFFFu, &best, &first_zero);
@@ -428,56 +456,33 @@ template <typename Dist>
 int RunNearby(ftk_context *ctx, const Dist &dist, int n_ref, int n_cur, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol,
               float max_dist, int *d_idx) {
     cudaStream_t st = ctx->stream;
-    // 1. bounding box of the finite cur positions
-    int *d_bounds = nullptr;
-    if (int rc = EnsureDevice(ctx, ctx->d_work0, 64)) return rc;
-    d_bounds = static_cast<int *>(ctx->d_work0.ptr);
+    // 1. bounding box of the finite cur positions -> grid geometry, all on the device (no host round trip)
+    constexpr int kMaxCells = 256 * 256;
+    if (int rc = EnsureDevice(ctx, ctx->d_work0, 256)) return rc;
+    int *d_bounds = static_cast<int *>(ctx->d_work0.ptr);
+    GridDesc *d_grid = reinterpret_cast<GridDesc *>(d_bounds + 8);
     const int init[4] = {0x7FFFFFFF, 0x7FFFFFFF, static_cast<int>(0x80000000), static_cast<int>(0x80000000)};
     FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, st));
     BoundsKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, d_bounds);
-    ++ctx->launches;
-    int h_bounds[4];
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
-    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-
-    GridDesc g{};
-    g.gw = g.gh = 1;
-    g.x0 = g.y0 = 0.0f;
-    g.inv_cw = g.inv_ch = 0.0f;
-    if (h_bounds[0] != 0x7FFFFFFF) {
-        const float x0 = OrderedToFloat(h_bounds[0]), y0 = OrderedToFloat(h_bounds[1]);
-        const float x1 = OrderedToFloat(h_bounds[2]), y1 = OrderedToFloat(h_bounds[3]);
-        float cw = static_cast<float>(max_dcol > 1 ? max_dcol : 1), ch = static_cast<float>(max_drow > 1 ? max_drow : 1);
-        const float span_x = x1 - x0, span_y = y1 - y0;
-        if (span_x / cw > 255.0f) cw = span_x / 255.0f;
-        if (span_y / ch > 255.0f) ch = span_y / 255.0f;
-        g.x0 = x0;
-        g.y0 = y0;
-        g.inv_cw = 1.0f / cw;
-        g.inv_ch = 1.0f / ch;
-        g.gw = static_cast<int>(span_x / cw) + 1;
-        g.gh = static_cast<int>(span_y / ch) + 1;
-        if (g.gw > 256) g.gw = 256;
-        if (g.gh > 256) g.gh = 256;
-    }
-    const int n_cells = g.gw * g.gh;
+    GridSetupKernel<<<1, 1, 0, st>>>(d_bounds, max_dcol, max_drow, d_grid);
 
     // 2. count -> scan -> fill
-    if (int rc = EnsureDevice(ctx, ctx->d_work1, sizeof(int) * (3 * static_cast<size_t>(n_cells) + 8))) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_work1, sizeof(int) * (3 * static_cast<size_t>(kMaxCells) + 8))) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work2, sizeof(int) * (2 * static_cast<size_t>(n_cur) + 8))) return rc;
     int *d_counts = static_cast<int *>(ctx->d_work1.ptr);
-    int *d_starts = d_counts + n_cells;       // n_cells + 1
-    int *d_cursor = d_starts + n_cells + 1;   // n_cells
-    int *d_nspecial = d_cursor + n_cells;     // 1
+    int *d_starts = d_counts + kMaxCells;       // kMaxCells + 1
+    int *d_cursor = d_starts + kMaxCells + 1;   // kMaxCells
+    int *d_nspecial = d_cursor + kMaxCells;     // 1
     int *d_sorted = static_cast<int *>(ctx->d_work2.ptr);
     int *d_special = d_sorted + n_cur;
-    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (3 * static_cast<size_t>(n_cells) + 8), st));
-    CellCountKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, g, d_counts, d_special, d_nspecial);
-    ScanKernel<<<1, 1024, 0, st>>>(d_counts, n_cells, d_starts, d_cursor);
-    CellFillKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, g, d_cursor, d_sorted);
+    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(int) * (3 * static_cast<size_t>(kMaxCells) + 8), st));
+    CellCountKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, d_grid, d_counts, d_special, d_nspecial);
+    ScanKernel<<<1, 1024, 0, st>>>(d_counts, d_grid, d_starts, d_cursor);
+    CellFillKernel<<<Blocks(n_cur, 256), 256, 0, st>>>(d_pos, n_cur, d_grid, d_cursor, d_sorted);
     // 3. one warp per ref descriptor
-    NearbyKernel<Dist><<<Blocks(n_ref * 32, 128), 128, 0, st>>>(dist, n_ref, d_pred, d_pos, n_cur, g, d_starts, d_sorted, d_special, d_nspecial,
+    NearbyKernel<Dist><<<Blocks(n_ref * 32, 128), 128, 0, st>>>(dist, n_ref, d_pred, d_pos, n_cur, d_grid, d_starts, d_sorted, d_special, d_nspecial,
                                                              static_cast<float>(max_dcol), static_cast<float>(max_drow), max_dist, d_idx);
+    ctx->launches += 2;
     ctx->launches += 4;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
