@@ -110,6 +110,8 @@ int ftk_create(int device, ftk_context **out) {
     {
         const char *e = getenv("FTK_DISABLE_FASTPATH");
         ctx->use_fast_paths = !(e && e[0] == '1');
+        const char *e2 = getenv("FTK_ENABLE_POOLED");
+        ctx->use_pooled = e2 && e2[0] == '1';
     }
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {

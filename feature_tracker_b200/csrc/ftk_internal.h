@@ -54,6 +54,7 @@ struct ftk_context {
     uint64_t launches = 0;
     int sm_count = 0;
     const int *d_last_scan_items = nullptr;  // device counter of the last tensor-core cosine match (nullptr: path not used)
+    bool use_pooled = false;     // FTK_ENABLE_POOLED=1 routes basic kInverse to the CTA-pooled-fold kernel (experiment; slower)
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
@@ -99,6 +100,8 @@ int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int 
 int LaunchKltTrack(ftk_context *ctx, const KltLaunch &launch);
 // klt_basic_fastpath.cu: FTK_ERR_UNSUPPORTED when no specialisation covers the configuration
 int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &launch);
+// klt_basic_pooled.cu: basic kInverse with CTA-pooled folds; FTK_ERR_UNSUPPORTED when not covered
+int LaunchKltBasicPooled(ftk_context *ctx, const KltLaunch &launch);
 
 // match.cu
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);

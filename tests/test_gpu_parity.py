@@ -248,6 +248,21 @@ def test_klt_north_star_config(ctx, oracle):
     assert good.mean() > 0.9 and np.median(np.linalg.norm(got[1][good] - fwd(uv)[good], axis=1)) < 0.3
 
 
+def test_klt_pooled_fold_kernel_opt_in(oracle, monkeypatch):
+    """The CTA-pooled-fold kernel (FTK_ENABLE_POOLED=1, read by ftk_create) stays bit-identical although it is not the default."""
+    monkeypatch.setenv("FTK_ENABLE_POOLED", "1")
+    pooled_ctx = ft.Context(0)
+    ref, cur, uv, _ = S.make_pair(480, 752, 700, pair_id=5)
+    pyr = ft.ImagePyramidBatch(pooled_ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    for half in (7, 6):
+        klt = make_tracker(pooled_ctx, "basic", "inverse", half, max_points=1000)
+        got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+        exp = oracle.klt_track(po.make_params("basic", "inverse", half=half, max_points=1000), oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4), uv)
+        assert_same(f"pooled h={half}", got, exp)
+
+
 def test_klt_lssd_c3_shape(ctx, oracle):
     """BASELINE configs[2] at reduced count: LSSD inverse, 21x21 patches, 1280x720."""
     ref, cur, uv, _ = S.make_pair(720, 1280, 300, pair_id=2)
