@@ -405,6 +405,26 @@ def run_b200(args):
     h2d = 2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4
     d2h = n_total * 9
 
+    # the temporal form: n_pairs + 1 host frames alternating the two images of one unique pair, each uploaded once
+    seq_u = rank % UNIQUE_PAIRS
+    host_seq = torch.empty((n_pairs + 1, ROWS, COLS), dtype=torch.uint8).pin_memory()
+    hs = host_seq.numpy()
+    hs[0::2] = refs[seq_u]
+    hs[1::2] = curs[seq_u]
+    host_seq_uv = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
+    host_seq_uv.numpy().reshape(n_pairs, n_feat, 2)[:] = uvs[seq_u]
+
+    def step_e2e_sequence():
+        flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+        ctx.check(L.ftk_track_image_sequence(ctx._h, C.byref(params), ROWS, COLS, LEVELS, n_pairs + 1, vp(host_seq.data_ptr()), vp(offsets.ctypes.data),
+                                             vp(host_seq_uv.data_ptr()), vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+
+    for _ in range(2):
+        step_e2e_sequence()
+    ms_seq, _ = timed(step_e2e_sequence, args.steps)
+    seq_value = tracked_per_step * args.steps / (ms_seq * 1e-3)
+    seq_tracked = float((host_status.numpy() == 1).mean())
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -429,6 +449,9 @@ def run_b200(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
                 "api": "ftk_track_image_pairs (pinned host images + features in, host results out; H2D of chunk k+1 overlaps compute of chunk k)"},
+        "e2e_sequence": {"value": seq_value, "unit": UNIT, "ms_per_step": ms_seq / args.steps, "h2d_bytes_per_step": ((n_pairs + 1) * plane + n_total * 8) * world,
+                         "tracked_fraction": seq_tracked,
+                         "api": "ftk_track_image_sequence (n_pairs + 1 host frames, pair k = frame k -> k+1; every frame uploaded and its pyramid built once)"},
         "tracked_fraction": float((status_host == 1).mean()),
         "kernel_ms": {"pyramid": ms_pyr / args.steps, "klt": ms_klt / args.steps},
         "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,

@@ -177,6 +177,8 @@ class OpticalFlow:
         self._options = OpticalFlowOptions()
         self._predict = np.eye(2, dtype=np.float32)
         self._consider_patch_luminance = False
+        # > 0: forward-backward consistency pass (not in the reference; see ftk_klt_params::forward_backward_max_error)
+        self.forward_backward_max_error = 0.0
 
     def OpticalFlowMethodName(self):
         return self._name
@@ -199,6 +201,7 @@ class OpticalFlow:
         for i in range(4):
             p.predict[i] = float(pr[i])
         p.consider_patch_luminance = 1 if self._consider_patch_luminance else 0
+        p.forward_backward_max_error = float(self.forward_backward_max_error)
         return p
 
     def TrackFeatures(self, ref_pyramid, cur_pyramid, ref_pixel_uv, cur_pixel_uv=None, status=None, single_level=False, ref_image=0,
@@ -263,6 +266,32 @@ class OpticalFlow:
         p = self._params()
         rc = lib().ftk_track_image_pairs(self.ctx._h, C.byref(p), rows, cols, int(levels), n_pairs, _ptr(ref_images), _ptr(cur_images),
                                          _ptr(feat_offsets), _ptr(ref_uv), _ptr(cur), _ptr(st), flags)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
+        return ok, cur[:n], st[:n]
+
+    def TrackImageSequence(self, levels, frames, feat_offsets, ref_pixel_uv, cur_pixel_uv=None, status=None):
+        """Temporal form of TrackImagePairs: host frames [n_frames, rows, cols]; pair k tracks features
+        feat_offsets[k]:feat_offsets[k+1] from frame k to frame k+1; every frame is uploaded and its pyramid built once
+        (ftk_track_image_sequence)."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint8)
+        n_frames, rows, cols = frames.shape
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        feat_offsets = np.ascontiguousarray(feat_offsets, dtype=np.int32)
+        flags = 0
+        cur = np.zeros((max(n, 1), 2), np.float32)
+        if cur_pixel_uv is not None and np.asarray(cur_pixel_uv).reshape(-1, 2).shape[0] == n and n > 0:
+            cur[:n] = np.asarray(cur_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        else:
+            flags |= _capi.FLAG_NO_PREDICTION
+        st = np.zeros(max(n, 1), np.uint8)
+        if status is not None and np.asarray(status).reshape(-1).shape[0] == n and n > 0:
+            st[:n] = np.asarray(status, dtype=np.uint8).reshape(-1)
+        else:
+            flags |= _capi.FLAG_NO_STATUS
+        p = self._params()
+        rc = lib().ftk_track_image_sequence(self.ctx._h, C.byref(p), rows, cols, int(levels), n_frames, _ptr(frames), _ptr(feat_offsets),
+                                            _ptr(ref_uv), _ptr(cur), _ptr(st), flags)
         ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
         return ok, cur[:n], st[:n]
 

@@ -93,6 +93,7 @@ void ftk_klt_params_default(ftk_klt_params *p) {
     p->max_converge_step = 4e-2f;
     p->predict[0] = 1.0f, p->predict[1] = 0.0f, p->predict[2] = 0.0f, p->predict[3] = 1.0f;
     p->consider_patch_luminance = 0;
+    p->forward_backward_max_error = 0.0f;
 }
 
 int ftk_create(int device, ftk_context **out) {
@@ -127,7 +128,7 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < 2; ++b) {
@@ -343,7 +344,7 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
     if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, n_pairs, n_features, d_feat_pair)) return rc;
     a.feat_pair = d_feat_pair;
 
-    if (int rc = ftk::LaunchKltTrack(ctx, a)) return rc;
+    if (int rc = ftk::LaunchKltTrackChecked(ctx, a)) return rc;
 
     if (!on_device) {
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, a.cur_uv, sizeof(float2) * n_features, cudaMemcpyDeviceToHost, ctx->stream));
@@ -353,10 +354,13 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
     return FTK_OK;
 }
 
-int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
-                          const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
-                          uint8_t *status, uint32_t flags) {
-    if (!ctx || !params || !ref_images || !cur_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
+// The chunked two-stream pipeline behind ftk_track_image_pairs (cur_images != nullptr: pair p = ref_images[p] -> cur_images[p])
+// and ftk_track_image_sequence (cur_images == nullptr: ref_images holds n_pairs + 1 frames, pair p = frame p -> frame p + 1).
+static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
+                                const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
+                                uint8_t *status, uint32_t flags) {
+    const bool sequence = cur_images == nullptr;
+    if (!ctx || !params || !ref_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
     if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
     if (flags & (FTK_FLAG_DEVICE_POINTERS | FTK_FLAG_SINGLE_LEVEL)) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "host images, multi-level only");
     if (params->variant < 0 || params->variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params->variant);
@@ -367,7 +371,8 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
     if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");  // optical_flow.cpp:8
     DeviceGuard guard(ctx->device);
 
-    // chunking: about 8 chunks per call, double-buffered staging pyramids (2 * chunk_pairs images each: refs then curs)
+    // chunking: about 8 chunks per call, double-buffered staging pyramids (2 * chunk_pairs images each: refs then curs; a
+    // sequence chunk uses the first chunk_pairs + 1 of them and re-uploads the frame it shares with the previous chunk)
     const int chunk_pairs = n_pairs < 16 ? n_pairs : (n_pairs + 7) / 8;
     const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
     if (!ctx->copy_stream) {
@@ -395,6 +400,10 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
     if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_features)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_status, n_features)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * n_features)) return rc;
+    if (params->forward_backward_max_error > 0.0f) {  // backward-pass scratch for the whole batch, so no chunk reallocates it
+        if (int rc = EnsureDevice(ctx, ctx->d_back_uv, sizeof(float2) * n_features)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_back_status, n_features)) return rc;
+    }
     std::vector<int32_t> h_offsets;
     h_offsets.reserve(n_pairs + n_chunks);
     std::vector<int> chunk_table_start(n_chunks);
@@ -404,7 +413,7 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
         for (int p = p_lo; p <= p_hi; ++p) h_offsets.push_back(feat_offsets[p] - feat_offsets[p_lo]);
     }
     std::vector<int32_t> h_curmap(stage_pairs);
-    for (int p = 0; p < stage_pairs; ++p) h_curmap[p] = stage_pairs + p;
+    for (int p = 0; p < stage_pairs; ++p) h_curmap[p] = sequence ? p + 1 : stage_pairs + p;
     if (int rc = EnsureDevice(ctx, ctx->d_chunk_offsets, sizeof(int32_t) * h_offsets.size())) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_chunk_curmap, sizeof(int32_t) * h_curmap.size())) return rc;
     const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);
@@ -427,22 +436,25 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
         if (c >= 2) FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(cs, ctx->ev_computed[b], 0));
         uint8_t *dst_ref = const_cast<uint8_t *>(v.base[0]);
         uint8_t *dst_cur = dst_ref + static_cast<size_t>(stage_pairs) * v.image_stride[0];
+        const int n_first = sequence ? np + 1 : np;  // images copied into staging slots [0, n_first)
         if (v.pitch[0] == cols) {
-            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_ref, v.image_stride[0], ref_images + p_lo * plane, plane, plane, np, cudaMemcpyHostToDevice, cs));
-            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_cur, v.image_stride[0], cur_images + p_lo * plane, plane, plane, np, cudaMemcpyHostToDevice, cs));
+            FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_ref, v.image_stride[0], ref_images + p_lo * plane, plane, plane, n_first, cudaMemcpyHostToDevice, cs));
+            if (!sequence)
+                FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_cur, v.image_stride[0], cur_images + p_lo * plane, plane, plane, np, cudaMemcpyHostToDevice, cs));
         } else {
-            for (int i = 0; i < np; ++i) {
+            for (int i = 0; i < n_first; ++i)
                 FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_ref + i * v.image_stride[0], v.pitch[0], ref_images + (p_lo + i) * plane, cols, cols, rows,
                                                       cudaMemcpyHostToDevice, cs));
+            for (int i = 0; i < np && !sequence; ++i)
                 FTK_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst_cur + i * v.image_stride[0], v.pitch[0], cur_images + (p_lo + i) * plane, cols, cols, rows,
                                                       cudaMemcpyHostToDevice, cs));
-            }
         }
         FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
         // ---- compute stream: pyramids of the 2 * np images, then the chunk's features
         FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ks, ctx->ev_copied[b], 0));
-        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, 0, np)) return rc;
-        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, stage_pairs, np)) return rc;
+        if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, 0, n_first)) return rc;
+        if (!sequence)
+            if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, stage_pairs, np)) return rc;
         const int f_lo = feat_offsets[p_lo], f_hi = feat_offsets[p_hi];
         if (f_hi > f_lo) {
             ftk::KltLaunch a{};
@@ -463,7 +475,7 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
             int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr) + f_lo;
             if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, np, a.n_features, d_feat_pair)) return rc;
             a.feat_pair = d_feat_pair;
-            if (int rc = ftk::LaunchKltTrack(ctx, a)) return rc;
+            if (int rc = ftk::LaunchKltTrackChecked(ctx, a, f_lo)) return rc;
         }
         FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_computed[b], ks));
     }
@@ -471,6 +483,19 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
     FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, ctx->d_status.ptr, n_features, cudaMemcpyDeviceToHost, ks));
     FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));
     return FTK_OK;
+}
+
+int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
+                          const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
+                          uint8_t *status, uint32_t flags) {
+    if (!cur_images) return FTK_ERR_INVALID_ARGUMENT;
+    return TrackImagesPipelined(ctx, params, rows, cols, levels, n_pairs, ref_images, cur_images, feat_offsets, ref_uv, cur_uv, status, flags);
+}
+
+int ftk_track_image_sequence(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_frames,
+                             const uint8_t *frames, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv, uint8_t *status, uint32_t flags) {
+    if (ctx && n_frames < 2) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "a sequence needs at least two frames");
+    return TrackImagesPipelined(ctx, params, rows, cols, levels, n_frames - 1, frames, nullptr, feat_offsets, ref_uv, cur_uv, status, flags);
 }
 
 // ---- matching -------------------------------------------------------------------------------------------------

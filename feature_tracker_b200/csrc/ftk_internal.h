@@ -59,6 +59,7 @@ struct ftk_context {
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
     FtkBuffer d_chunk_offsets, d_chunk_curmap;
+    FtkBuffer d_back_uv, d_back_status;  // forward-backward pass scratch
     FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
 };
 
@@ -98,6 +99,9 @@ struct KltLaunch {
 };
 int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int n_features, int *d_feat_pair);
 int LaunchKltTrack(ftk_context *ctx, const KltLaunch &launch);
+// Forward pass, then (p.forward_backward_max_error > 0) the backward pass and the consistency test; scratch is indexed like the
+// launch's feature arrays starting at scratch_offset.
+int LaunchKltTrackChecked(ftk_context *ctx, const KltLaunch &launch, size_t scratch_offset = 0);
 // klt_basic_fastpath.cu: FTK_ERR_UNSUPPORTED when no specialisation covers the configuration
 int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &launch);
 // klt_basic_pooled.cu: basic kInverse with CTA-pooled folds; FTK_ERR_UNSUPPORTED when not covered

@@ -1125,4 +1125,50 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
     return SetError(ctx, FTK_ERR_UNSUPPORTED, "patch of %d pixels is larger than this build supports (2048)", geo.psize);
 }
 
+namespace {
+
+// Forward-backward consistency test (ftk_klt_params::forward_backward_max_error): see include/ftk_c.h.
+__global__ void ForwardBackwardCheckKernel(int n_features, const float2 *ref_uv, const float2 *back_uv, const uint8_t *back_status, uint8_t *status,
+                                           float max_sq) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_features || status[f] != FTK_STATUS_TRACKED) return;
+    const float dx = fsub(back_uv[f].x, ref_uv[f].x), dy = fsub(back_uv[f].y, ref_uv[f].y);
+    const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+    if (!(back_status[f] == FTK_STATUS_TRACKED && d2 <= max_sq)) status[f] = FTK_STATUS_LARGE_RESIDUAL;
+}
+
+}  // namespace
+
+int LaunchKltTrackChecked(ftk_context *ctx, const KltLaunch &a, size_t scratch_offset) {
+    if (int rc = LaunchKltTrack(ctx, a)) return rc;
+    const float max_error = a.p.forward_backward_max_error;
+    if (!(max_error > 0.0f)) return FTK_OK;
+    const size_t n = static_cast<size_t>(a.n_features);
+    if (int rc = EnsureDevice(ctx, ctx->d_back_uv, sizeof(float2) * (scratch_offset + n))) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_back_status, scratch_offset + n)) return rc;
+    float2 *back_uv = static_cast<float2 *>(ctx->d_back_uv.ptr) + scratch_offset;
+    uint8_t *back_status = static_cast<uint8_t *>(ctx->d_back_status.ptr) + scratch_offset;
+    // TrackFeatures(cur_pyramid, ref_pyramid, ref := forward result, cur := reference position (prediction), status := forward status)
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(back_uv, a.ref_uv, sizeof(float2) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(back_status, a.status, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    KltLaunch b = a;
+    b.ref = a.cur;
+    b.cur = a.ref;
+    b.ref_image = a.cur_image;
+    b.cur_image = a.ref_image;
+    b.ref_uv = a.cur_uv;
+    b.cur_uv = back_uv;
+    b.status = back_status;
+    b.has_prediction = 1;
+    b.has_status = 1;
+    b.p.predict[0] = 1.0f, b.p.predict[1] = 0.0f, b.p.predict[2] = 0.0f, b.p.predict[3] = 1.0f;
+    if (int rc = LaunchKltTrack(ctx, b)) return rc;
+    const int threads = 256;
+    ForwardBackwardCheckKernel<<<(a.n_features + threads - 1) / threads, threads, 0, ctx->stream>>>(a.n_features, a.ref_uv, back_uv, back_status, a.status,
+                                                                                                   max_error * max_error);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
 }  // namespace ftk

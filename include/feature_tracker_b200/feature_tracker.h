@@ -156,6 +156,10 @@ public:
     OpticalFlowOptions &options() { return options_; }
     const OpticalFlowOptions &options() const { return options_; }
 
+    // Not in the reference: > 0 adds the forward-backward consistency pass of ftk_klt_params::forward_backward_max_error.
+    float &forward_backward_max_error() { return forward_backward_max_error_; }
+    const float &forward_backward_max_error() const { return forward_backward_max_error_; }
+
 protected:
     virtual void FillParams(ftk_klt_params &p) const = 0;
 
@@ -173,6 +177,7 @@ private:
         p.patch_col_half = options_.kPatchColHalfSize;
         p.max_converge_step = options_.kMaxConvergeStep;
         p.method = static_cast<int32_t>(options_.kMethod);
+        p.forward_backward_max_error = forward_backward_max_error_;
         FillParams(p);
         std::vector<float> ref_flat(2 * static_cast<size_t>(n)), cur_flat(2 * static_cast<size_t>(n), 0.0f);
         for (int32_t i = 0; i < n; ++i) ref_flat[2 * i] = ref_uv[i].x(), ref_flat[2 * i + 1] = ref_uv[i].y();
@@ -194,6 +199,7 @@ private:
         return true;
     }
     OpticalFlowOptions options_;
+    float forward_backward_max_error_ = 0.0f;
 };
 
 // basic_klt/optical_flow_basic_klt.h:9-41

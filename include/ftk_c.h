@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTK_ABI_VERSION 1
+#define FTK_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------------------------ */
 #define FTK_OK 0
@@ -74,6 +74,12 @@ typedef struct ftk_klt_params {
     float max_converge_step;           /* kMaxConvergeStep, compared with the SQUARED step */
     float predict[4];                  /* row-major 2x2: predict_affine_ (affine, single level) / predict_R_cr_ (lssd) */
     int32_t consider_patch_luminance;  /* lssd fast only */
+    /* Not in the reference (SURVEY 8(f) "next" row): > 0 adds a forward-backward consistency pass.  Every feature the forward
+     * pass left kTracked is tracked back from its result in the current frame into the reference frame -- exactly
+     * TrackFeatures(cur_pyramid, ref_pyramid, result, prediction = its reference position) with identity `predict` -- and is
+     * downgraded to kLargeResidual unless the backward track is kTracked and ends within this many pixels of the
+     * reference position (dx*dx + dy*dy <= max*max in fp32).  0 (default) = the reference's behaviour. */
+    float forward_backward_max_error;
 } ftk_klt_params;
 
 /* Fills the reference defaults (optical_flow.h:20-28; identity predictions; luminance off). */
@@ -129,6 +135,15 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
 int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
                           const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
                           uint8_t *status, uint32_t flags);
+
+/* The temporal form of the same pipeline (SURVEY 8(f) "next" row: the current frame of pair k is the reference frame of pair
+ * k+1, but the reference's callers rebuild both pyramids for every pair, test/test_optical_flow.cpp:70-71).  `frames` holds
+ * n_frames >= 2 tightly packed HOST images; pair k = (frame k -> frame k+1), k = 0 .. n_frames-2, owns features
+ * [feat_offsets[k], feat_offsets[k+1]).  Every frame is uploaded once and its pyramid is built once, which halves the
+ * host-to-device traffic and the pyramid work of ftk_track_image_pairs; results are identical to it. */
+int ftk_track_image_sequence(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_frames,
+                             const uint8_t *frames, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv, uint8_t *status,
+                             uint32_t flags);
 
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of

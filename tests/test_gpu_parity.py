@@ -234,6 +234,76 @@ def test_klt_temporal_sequence_shares_pyramids(ctx, oracle):
         assert_same(f"sequence pair {k}", (True, cur_uv[30 * k:30 * (k + 1)], st[30 * k:30 * (k + 1)]), exp)
 
 
+def forward_backward_oracle(oracle, prm, ref_levels, cur_levels, uv, max_error):
+    """The composition ftk_klt_params::forward_backward_max_error documents, out of two reference TrackFeatures calls."""
+    ok, fwd_uv, fwd_st = oracle.klt_track(prm, ref_levels, cur_levels, uv)
+    _, back_uv, back_st = oracle.klt_track(prm, cur_levels, ref_levels, fwd_uv, cur_uv=uv, status=fwd_st)
+    d = back_uv - uv.astype(np.float32)
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32)
+    good = (back_st == 1) & (d2 <= np.float32(max_error) * np.float32(max_error))
+    st = fwd_st.copy()
+    st[(fwd_st == 1) & ~good] = 2
+    return ok, fwd_uv, st
+
+
+def test_track_image_sequence_pipelined(ctx, oracle):
+    """ftk_track_image_sequence: 41 host frames -> 40 pairs in 8 chunks; every frame uploaded once; equals pair-by-pair tracking."""
+    rows, cols, levels, n_frames = 96, 128, 3, 41
+    base = S.make_image(rows, cols, seed=900)
+    frames = [base]
+    for k in range(1, 6):
+        frames.append(S.warp_image(frames[-1], seed=910 + k, max_shift=2.5, max_rot_deg=1.0)[0])
+    cycle = frames + frames[-2:0:-1]  # 0 1 2 3 4 5 4 3 2 1 | 0 1 ...: consecutive frames always differ by one small warp
+    seq = np.stack([cycle[k % len(cycle)] for k in range(n_frames)])
+    rng = np.random.default_rng(3)
+    counts = rng.integers(0, 20, n_frames - 1)
+    counts[7] = 0
+    uvs = [S.detect_features(seq[k], 20, seed=k % len(cycle), border=10)[:counts[k]] for k in range(n_frames - 1)]
+    counts = np.array([u.shape[0] for u in uvs])
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    all_uv = np.concatenate(uvs)
+    lv = {}
+    for variant, method, half, fb in [("basic", "inverse", 7, 0.0), ("basic", "fast", 6, 0.5), ("affine", "direct", 5, 0.0)]:
+        klt = make_tracker(ctx, variant, method, half)
+        klt.forward_backward_max_error = fb
+        ok, cur_uv, st = klt.TrackImageSequence(levels, seq, offsets, all_uv)
+        assert ok
+        prm = po.make_params(variant, method, half=half)
+        for k in range(n_frames - 1):
+            if counts[k] == 0:
+                continue
+            for f in (k, k + 1):
+                if f % len(cycle) not in lv:
+                    lv[f % len(cycle)] = oracle.pyramid_build(seq[f], levels)
+            a, b = lv[k % len(cycle)], lv[(k + 1) % len(cycle)]
+            exp = forward_backward_oracle(oracle, prm, a, b, uvs[k], fb) if fb > 0 else oracle.klt_track(prm, a, b, uvs[k])
+            sl = slice(offsets[k], offsets[k + 1])
+            assert_same(f"sequence {variant}/{method} fb={fb} pair {k}", (True, cur_uv[sl], st[sl]), exp)
+    ok, _, _ = klt.TrackImageSequence(levels, seq[:1], np.zeros(1, np.int32), np.zeros((0, 2), np.float32))
+    assert not ok  # fewer than two frames == empty input
+
+
+@pytest.mark.parametrize("variant,method,half", [("basic", "inverse", 7), ("basic", "direct", 6), ("affine", "fast", 6), ("lssd", "inverse", 5)])
+def test_klt_forward_backward_check(ctx, oracle, variant, method, half):
+    """forward_backward_max_error: the backward pass and the consistency test equal the composition of two reference calls."""
+    ref, cur, uv, _ = S.make_pair(240, 320, 300, pair_id=31)
+    cur = cur.copy()
+    cur[60:140, 100:220] = np.random.default_rng(5).integers(0, 255, (80, 120), dtype=np.uint8)  # an occluder: forward tracks land on noise
+    pyr = ft.ImagePyramidBatch(ctx, 240, 320, 3, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    klt = make_tracker(ctx, variant, method, half)
+    plain = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    klt.forward_backward_max_error = 0.7
+    got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    prm = po.make_params(variant, method, half=half)
+    exp = forward_backward_oracle(oracle, prm, oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3), uv, 0.7)
+    assert_same(f"forward-backward {variant}/{method}", got, exp)
+    rejected = (plain[2] == 1) & (got[2] == 2)
+    assert rejected.sum() > 0 and (got[2] == 1).sum() > 100  # the test rejects something and keeps the bulk
+    assert bits_equal(got[1], plain[1])  # positions are the forward pass's
+
+
 def test_klt_north_star_config(ctx, oracle):
     """BASELINE configs[0]: basic inverse, 4 levels, 15x15 patches, 200 features on a 752x480 pair."""
     ref, cur, uv, fwd = S.make_pair(480, 752, 200, pair_id=0)
