@@ -277,6 +277,14 @@ def run_extras(ctx, L, torch, local_rank, steps):
     flop = 2.0 * 20000 * 20000 * 256
     out["C5_float256_force_20k_x_20k"] = {"pairs_per_s": 4e8 / (ms * 1e-3), "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12,
                                           "matched": int((d_idx2.cpu().numpy() >= 0).sum())}
+
+    # ---- score-matrix mutual arg-max (NNFeatureMatcher post-processing): HBM bound, 4 B per matrix element ----
+    for n in (2048, 12288):  # LightGlue's usual size (16 MB, L2 resident) and a matrix far larger than L2 (604 MB)
+        d_s = torch.randn((n, n), dtype=torch.float32, device=dev) * 2.0 - 6.0
+        d_i = torch.empty((n,), dtype=torch.int32, device=dev)
+        ms = timeit(lambda: ctx.check(L.ftk_match_mutual_scores(ctx._h, vp(d_s.data_ptr()), n, n, -3.0, vp(d_i.data_ptr()), _capi.FLAG_DEVICE_POINTERS)), steps * 2)
+        out[f"mutual_scores_{n}x{n}"] = {"ms": ms, "gb_per_s": 4.0 * n * n / (ms * 1e-3) / 1e9, "algorithmic_bytes": 4 * n * n}
+        del d_s
     return out
 
 

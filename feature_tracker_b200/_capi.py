@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
     "ftk_track_image_pairs", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
+    "ftk_match_mutual_scores", "ftk_match_cross_check",
 ]
 
 
@@ -82,6 +83,8 @@ def load_library():
         "ftk_match_hamming_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_mutual_scores": (C.c_int, [vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_cross_check": (C.c_int, [vp, vp, i32, vp, i32, u32]),
         "ftk_fill_matched": (C.c_int, [vp, i32, vp, i32, vp, vp, i32]),
         "ftk_last_cosine_exact_scan_items": (C.c_int, [vp]),
     }

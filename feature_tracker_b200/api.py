@@ -391,6 +391,18 @@ class DescriptorMatcher:
         ok = self.ctx.check(self._nearby(ref, cur, pred, pos, idx, flags), soft=(_capi.ERR_EMPTY_INPUT, _capi.ERR_SIZE_MISMATCH))
         return ok, idx[:n_ref]
 
+    def CrossCheckForceMatch(self, descriptors_ref, descriptors_cur):
+        """Not in the reference: ForceMatch in both directions, keeping ref i -> cur j only when cur j -> ref i too
+        (ftk_match_cross_check).  Returns (ok, index_pairs_in_cur)."""
+        ok_f, fwd = self.ForceMatch(descriptors_ref, descriptors_cur)
+        ok_b, bwd = self.ForceMatch(descriptors_cur, descriptors_ref)
+        if not (ok_f and ok_b):
+            return False, fwd
+        fwd = np.ascontiguousarray(fwd, dtype=np.int32)
+        bwd = np.ascontiguousarray(bwd, dtype=np.int32)
+        self.ctx.check(lib().ftk_match_cross_check(self.ctx._h, _ptr(fwd), fwd.shape[0], _ptr(bwd), bwd.shape[0], 0))
+        return True, fwd
+
     def FillMatchedPixelByPairIndices(self, index_pairs_in_cur, pixel_uv_cur, status=None):
         """descriptor_matcher.h:135-157.  Returns (matched_pixel_uv_cur, status)."""
         idx = np.ascontiguousarray(index_pairs_in_cur, dtype=np.int32)
@@ -472,3 +484,47 @@ class CosineMatcher(DescriptorMatcher):
 
 SuperpointMatcher = CosineMatcher
 DiskMatcher = CosineMatcher
+
+
+class NNFeatureMatcherOptions:
+    """nn_feature_matcher.h:23-27 (the fields the score-matrix post-processing uses)."""
+
+    def __init__(self):
+        self.kMinValidMatchScore = -3.0
+
+
+class NNFeatureMatcher:
+    """The score-matrix post-processing of NNFeatureMatcher::Match (src/nn_feature_matcher/nn_feature_matcher.cpp:154-216):
+    mutual row / column arg-max with a minimum score.  The LightGlue network itself (ONNX Runtime in the reference) is out of
+    scope; its output matrix is the input here."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = NNFeatureMatcherOptions()
+
+    def options(self):
+        return self._options
+
+    def MatchScores(self, scores):
+        """scores [n_ref, n_cur] float32 -> index_pairs_in_cur [n_ref] (-1 = no mutual match)."""
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        n_ref, n_cur = scores.shape
+        idx = np.full(max(n_ref, 1), -1, np.int32)
+        rc = lib().ftk_match_mutual_scores(self.ctx._h, _ptr(scores), n_ref, n_cur, float(self._options.kMinValidMatchScore), _ptr(idx), 0)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
+        return ok, idx[:n_ref]
+
+    def Match(self, scores, pixel_uv_ref, pixel_uv_cur):
+        """nn_feature_matcher.cpp:154-216 after InferenceSession: returns (ok, matched_pixel_uv_cur [n_ref, 2], status [n_ref]) with
+        status kLargeResidual for unmatched rows (:157) and kTracked for matched ones (:213).  (The reference copies
+        pixel_uv_cur into matched_pixel_uv_cur first, :158; unmatched rows here keep their own reference position.)"""
+        ok, idx = self.MatchScores(scores)
+        ref = np.ascontiguousarray(pixel_uv_ref, dtype=np.float32).reshape(-1, 2)
+        cur = np.ascontiguousarray(pixel_uv_cur, dtype=np.float32).reshape(-1, 2)
+        matched = ref.copy()
+        status = np.full(ref.shape[0], 2, np.uint8)
+        if ok:
+            good = idx >= 0
+            matched[good] = cur[idx[good]]
+            status[good] = 1
+        return ok, matched, status

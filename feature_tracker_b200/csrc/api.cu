@@ -565,6 +565,32 @@ int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_re
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 
+int ftk_match_mutual_scores(ftk_context *ctx, const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_ref < 0) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_cur <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "the score matrix has no columns");
+    if (n_ref > 0 && !scores) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const float *d_scores = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, scores, static_cast<size_t>(n_ref) * n_cur, on_device, &d_scores)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags | FTK_FLAG_NO_INDEX_INPUT, &d_idx)) return rc;  // every entry is written
+    if (int rc = ftk::LaunchMutualScores(ctx, d_scores, n_ref, n_cur, min_score, d_idx)) return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_match_cross_check(ftk_context *ctx, int32_t *idx_ref_to_cur, int32_t n_ref, const int32_t *idx_cur_to_ref, int32_t n_cur, uint32_t flags) {
+    if (!ctx || !idx_ref_to_cur || n_ref < 0 || n_cur < 0 || (n_cur > 0 && !idx_cur_to_ref)) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    int *d_fwd = nullptr;
+    if (int rc = PrepareIndex(ctx, idx_ref_to_cur, n_ref, flags & ~FTK_FLAG_NO_INDEX_INPUT, &d_fwd)) return rc;
+    const int32_t *d_bwd = nullptr;
+    if (int rc = Stage(ctx, ctx->d_work2, idx_cur_to_ref, static_cast<size_t>(n_cur), on_device, &d_bwd)) return rc;
+    if (int rc = ftk::LaunchCrossCheck(ctx, d_fwd, n_ref, d_bwd, n_cur)) return rc;
+    return FinishIndex(ctx, idx_ref_to_cur, n_ref, flags, d_fwd);
+}
+
 int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist,
                            int32_t *idx, uint32_t flags) {
     if (!ctx || !idx || n_ref < 0 || dim <= 0) return FTK_ERR_INVALID_ARGUMENT;

@@ -112,6 +112,9 @@ int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const
 int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
                         const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
+// match_mutual.cu: mutual arg-max of a score matrix; cross-check filter
+int LaunchMutualScores(ftk_context *ctx, const float *d_scores, int n_ref, int n_cur, float min_score, int *d_idx);
+int LaunchCrossCheck(ftk_context *ctx, int *d_idx_fwd, int n_ref, const int *d_idx_bwd, int n_cur);
 // match_cosine_tc.cu: tcgen05 GEMM + exact re-rank; FTK_ERR_UNSUPPORTED for dim > 256
 int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
 int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,

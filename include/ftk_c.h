@@ -166,6 +166,16 @@ int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, c
  * fall-back scan because the tensor-core pass could not separate the candidates (0 when the fast path decided every row;
  * -1 when the call did not use the tensor-core path).  Synchronises the context. */
 int ftk_last_cosine_exact_scan_items(ftk_context *ctx);
+/* ---- mutual arg-max of a score matrix (SURVEY 8(f) "next" row; replaces the score-matrix post-processing of
+ *      NNFeatureMatcher::Match, src/nn_feature_matcher/nn_feature_matcher.cpp:180-216) ---------------------------------
+ * scores = n_ref x n_cur row-major floats (LightGlue log-assignment).  idx[i] = j when j is the FIRST maximum of row i
+ * (`scores(j) > max_score`, :205), scores[i][j] is not < min_score (kMinValidMatchScore, :210) and the first maximum of
+ * column j is row i (:211); -1 otherwise.  Every idx entry is written.  Matched positions / status then follow from
+ * ftk_fill_matched.  NaN entries behave as in the reference's comparisons. */
+int ftk_match_mutual_scores(ftk_context *ctx, const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx, uint32_t flags);
+/* Cross-check filter for the descriptor matchers: idx_ref_to_cur[i] (from a Force / NearbyMatch ref -> cur) is reset to -1
+ * unless idx_cur_to_ref[idx_ref_to_cur[i]] == i (from the same call with the two sets swapped). */
+int ftk_match_cross_check(ftk_context *ctx, int32_t *idx_ref_to_cur, int32_t n_ref, const int32_t *idx_cur_to_ref, int32_t n_cur, uint32_t flags);
 /* Host-side helper mirroring FillMatchedPixelByPairIndices (descriptor_matcher.h:135-157); status_valid == 0
  * behaves as status.size() != idx.size(). */
 int ftk_fill_matched(const int32_t *idx, int32_t n_ref, const float *cur_uv, int32_t n_cur, float *matched_uv, uint8_t *status,

@@ -1092,3 +1092,40 @@ int ftko_match_brief_force_uv(const uint8_t *ref_bits, int32_t n_ref, const uint
     free(idx);
     return ok;
 }
+
+/* src/nn_feature_matcher/nn_feature_matcher.cpp:180-216, the score-matrix branch of NNFeatureMatcher::Match after the network
+ * has run (the network itself needs ONNX Runtime and is outside the path; so is a compiled-in-place check of these lines --
+ * this restatement is unpinned).  scores is the n_ref x n_cur row-major matrix; idx[i] = matched column or -1
+ * (status kTracked / kLargeResidual in the reference). */
+int ftko_mutual_scores(const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx) {
+    if (n_cur <= 0) return 0;
+    int32_t *max_scores_in_cols_index = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_cur);
+    for (int32_t j = 0; j < n_cur; ++j) { /* :187-198 */
+        int32_t max_score_index = 0;
+        float max_score = n_ref > 0 ? scores[j] : 0.0f;
+        for (int32_t i = 1; i < n_ref; ++i) {
+            if (scores[(size_t)i * n_cur + j] > max_score) {
+                max_score = scores[(size_t)i * n_cur + j];
+                max_score_index = i;
+            }
+        }
+        max_scores_in_cols_index[j] = max_score_index;
+    }
+    for (int32_t idx_ref = 0; idx_ref < n_ref; ++idx_ref) { /* :200-214 */
+        const float *row = scores + (size_t)idx_ref * n_cur;
+        int32_t max_score_index = 0;
+        float max_score = row[0];
+        for (int32_t j = 1; j < n_cur; ++j) {
+            if (row[j] > max_score) {
+                max_score = row[j];
+                max_score_index = j;
+            }
+        }
+        idx[idx_ref] = -1;
+        if (max_score < min_score) continue;
+        if (max_scores_in_cols_index[max_score_index] != idx_ref) continue;
+        idx[idx_ref] = max_score_index;
+    }
+    free(max_scores_in_cols_index);
+    return 1;
+}

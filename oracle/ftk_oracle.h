@@ -53,6 +53,9 @@ int ftko_match_brief_force_uv(const uint8_t *ref_bits, int32_t n_ref, const uint
                               float max_dist, float *matched_uv, uint8_t *status, int32_t status_count);
 
 /* Exposed for unit tests of the LDLT restatement: solves A x = b for n in {2,3,6}; A row-major n*n. */
+/* nn_feature_matcher.cpp:180-216: mutual row / column arg-max of a score matrix (restatement only; needs no network). */
+int ftko_mutual_scores(const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx);
+
 void ftko_ldlt_solve(int32_t n, const float *a, const float *b, float *x);
 
 #ifdef __cplusplus

@@ -276,6 +276,14 @@ class OracleLib(_CpuChecker):
         build_oracle()
         super().__init__(ORACLE_SO)
 
+    def mutual_scores(self, scores, min_score):
+        """nn_feature_matcher.cpp:180-216 (C restatement only: the reference file needs ONNX Runtime to compile)."""
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        n_ref, n_cur = scores.shape
+        idx = np.full(max(n_ref, 1), -1, np.int32)
+        ok = self._fn("mutual_scores")(_f32p(scores), C.c_int32(n_ref), C.c_int32(n_cur), C.c_float(min_score), _i32p(idx))
+        return ok == 1, idx[:n_ref].copy()
+
 
 def have_ref():
     return os.path.exists(REF_SO) or os.path.isdir(REFERENCE_ROOT)

@@ -472,6 +472,64 @@ def test_cosine_nearby_vs_oracle(ctx, oracle):
     assert (exp[1] >= 0).sum() > 50
 
 
+def lightglue_like_scores(n_ref, n_cur, seed):
+    """Log-assignment-like matrix: a planted partial permutation of strong scores over weak background, ties, -inf, NaN."""
+    rng = np.random.default_rng(seed)
+    s = rng.normal(-8.0, 2.0, (n_ref, n_cur)).astype(np.float32)
+    n_match = min(n_ref, n_cur) * 2 // 3
+    rows, cols = rng.permutation(n_ref)[:n_match], rng.permutation(n_cur)[:n_match]
+    s[rows, cols] = rng.uniform(-4.0, -0.01, n_match).astype(np.float32)  # some below the -3 threshold
+    s[rng.random(s.shape) < 0.3 / n_cur] = np.float32(-0.5)  # ties between strong entries (about every third row)
+    if n_ref > 8 and n_cur > 8:
+        s[1, :] = -np.inf
+        s[:, 2] = -np.inf
+        s[3, 0] = np.nan
+        s[0, 5] = np.nan
+        s[6, 7] = np.nan
+        s[4, 4] = -0.0
+        s[4, 6] = 0.0
+    return s
+
+
+@pytest.mark.parametrize("n_ref,n_cur", [(1, 1), (5, 3), (300, 257), (512, 2048), (2048, 2048), (1000, 4099), (3000, 130)])
+def test_mutual_scores_vs_oracle(ctx, oracle, n_ref, n_cur):
+    """ftk_match_mutual_scores == the reference's score-matrix post-processing (nn_feature_matcher.cpp:180-216), index for index."""
+    s = lightglue_like_scores(n_ref, n_cur, seed=n_ref * 7 + n_cur)
+    m = ft.NNFeatureMatcher(ctx)
+    counts = []
+    for thr in (-1.0, -100.0, -3.0):
+        m.options().kMinValidMatchScore = thr
+        ok, idx = m.MatchScores(s)
+        ok_e, exp = oracle.mutual_scores(s, thr)
+        assert ok and ok_e
+        bad = np.nonzero(idx != exp)[0]
+        assert bad.size == 0, f"rows {bad[:10]}: gpu {idx[bad[:10]]} oracle {exp[bad[:10]]}"
+        counts.append(int((exp >= 0).sum()))
+    if n_ref > 8:
+        assert counts[1] > min(n_ref, n_cur) // 4 and counts[0] <= counts[1]  # planted matches found; the threshold only removes
+    uv_ref = np.zeros((n_ref, 2), np.float32)
+    uv_cur = np.arange(2 * n_cur, dtype=np.float32).reshape(n_cur, 2)
+    ok, matched, st = m.Match(s, uv_ref, uv_cur)
+    assert ok and np.array_equal(st == 1, exp >= 0) and np.array_equal(matched[exp >= 0], uv_cur[exp[exp >= 0]])
+    ok, _ = m.MatchScores(np.zeros((4, 0), np.float32))
+    assert not ok
+
+
+def test_cross_check_force_match(ctx, oracle):
+    """Cross-check matching = two ForceMatch calls (reference semantics each) + the mutual filter."""
+    rng = np.random.default_rng(9)
+    ref_bits = rng.integers(0, 2, (700, 256), dtype=np.uint8)
+    cur_bits = ref_bits[rng.permutation(700)[:600]].copy()
+    cur_bits[rng.random(cur_bits.shape) < 0.08] ^= 1
+    cur_bits = np.concatenate([cur_bits, rng.integers(0, 2, (150, 256), dtype=np.uint8)])
+    m = brief_matcher(ctx, 60.0)
+    ok, idx = m.CrossCheckForceMatch(ft.pack_brief(ref_bits), ft.pack_brief(cur_bits))
+    _, fwd = oracle.match_brief_force(ref_bits, cur_bits, 60.0)
+    _, bwd = oracle.match_brief_force(cur_bits, ref_bits, 60.0)
+    exp = np.where((fwd >= 0) & (bwd[np.clip(fwd, 0, None)] == np.arange(700)), fwd, -1)
+    assert ok and np.array_equal(idx, exp) and (exp >= 0).sum() > 500
+
+
 def test_hamming_c4_full_size_properties(ctx):
     """BASELINE configs[3] at full size (10k x 10k): size-independent properties instead of the O(N*M) CPU oracle --
     planted matches are recovered, results are idempotent, and a ref-row permutation permutes the result."""

@@ -177,3 +177,44 @@ def test_matcher_semantics(oracle):
     pred = np.array([[11, 11], [52, 52]], np.float32)
     ok, idx = oracle.match_brief_nearby(ref, cur, pred, pos, 5, 5, 64.0)
     assert list(idx) == [4, 3]
+
+
+def _mutual_scores_python(scores, min_score):
+    """Pure-Python transcription of nn_feature_matcher.cpp:187-214 (small cases only)."""
+    n_ref, n_cur = scores.shape
+    col_best = []
+    for j in range(n_cur):
+        best, best_i = scores[0, j], 0
+        for i in range(1, n_ref):
+            if scores[i, j] > best:
+                best, best_i = scores[i, j], i
+        col_best.append(best_i)
+    idx = np.full(n_ref, -1, np.int32)
+    for i in range(n_ref):
+        best, best_j = scores[i, 0], 0
+        for j in range(1, n_cur):
+            if scores[i, j] > best:
+                best, best_j = scores[i, j], j
+        if best < min_score or col_best[best_j] != i:
+            continue
+        idx[i] = best_j
+    return idx
+
+
+def test_mutual_scores_restatement(oracle):
+    """The C restatement of the score-matrix post-processing against a literal Python loop, ties / NaN / -inf included."""
+    rng = np.random.default_rng(77)
+    for n_ref, n_cur in [(1, 1), (7, 5), (40, 61), (64, 64)]:
+        s = rng.normal(-4, 3, (n_ref, n_cur)).astype(np.float32)
+        s[rng.random(s.shape) < 0.1] = np.float32(-1.5)  # ties
+        if n_ref > 5:
+            s[2, :] = -np.inf
+            s[3, 0] = np.nan
+            s[0, 2] = np.nan
+            s[5, 3] = np.nan
+        ok, idx = oracle.mutual_scores(s, -3.0)
+        assert ok
+        with np.errstate(invalid="ignore"):
+            assert np.array_equal(idx, _mutual_scores_python(s, np.float32(-3.0)))
+    ok, _ = oracle.mutual_scores(np.zeros((3, 0), np.float32), -3.0)
+    assert not ok
