@@ -65,6 +65,10 @@ __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G,
         pair_floats = 0;
         l.hoist_floats = 4 * RoundUp(geo.psize, 4);
     }
+    if (variant == FTK_VARIANT_AFFINE && method != kFast) {
+        pair_floats = 0;
+        l.hoist_floats = (method == kInverse ? 3 : 1) * RoundUp(geo.psize, 4);  // per level: [fx, fy,] reference centre sample
+    }
     l.total_bytes = 4 * (l.term_floats + l.ex_floats + pair_floats + l.curp_floats + l.hoist_floats) + l.exv_bytes + l.curv_bytes;
     l.total_bytes = RoundUp(l.total_bytes, 16);
     // Groups of one warp must start on different banks: make the group stride (in words) congruent to G modulo 32.
@@ -408,32 +412,77 @@ __device__ __forceinline__ void AffineGatherHessian(const Ctx<G> &c, float (&H)[
     }
 }
 
-// affine_klt.cpp:131-273 ConstructIncrementalFunction: 21 Hessian + 6 bias chains.
+// The reference samples of affine_klt.cpp:131-273 do not depend on the iteration: the centre sample I_ref(row_i, col_i)
+// (both methods) and, for kInverse, the gradient stencil of the reference image are evaluated once per level into the
+// group's shared scratch.  Bit q of the result = this lane's pixel of chunk q has all its reference samples inside.
 template <int METHOD, int G>
-__device__ int AffineConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const AffineState &s, float (&H)[6][6],
-                               float (&b)[6]) {
+__device__ unsigned long long AffineHoistRef(Ctx<G> &c, const Img &ref, float ref_x, float ref_y) {
+    const int pf = RoundUp(c.geo.psize, 4);
+    float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;  // hfx / hfy exist for kInverse only
+    unsigned long long ref_bits = 0ull;
+    int prow = c.g.lane / c.geo.pc, pcol = c.g.lane - prow * c.geo.pc;
+    const int step_r = G / c.geo.pc, step_c = G - step_r * c.geo.pc;
+    int chunk = 0;
+    c.g.sync();  // the previous level has finished reading the scratch
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        if (k < c.geo.psize) {
+            const float row_i = fadd(static_cast<float>(prow - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(pcol - c.geo.hc), ref_x);
+            if constexpr (METHOD == kInverse) {
+                float v0, v1, v2, v3, v4;
+                if (PxStencil5(ref, row_i, col_i, &v0, &v1, &v2, &v3, &v4)) {
+                    hfx[k] = fsub(v1, v0);
+                    hfy[k] = fsub(v3, v2);
+                    hv4[k] = v4;
+                    ref_bits |= 1ull << chunk;
+                }
+            } else {
+                float v4;
+                if (PxChecked(ref, row_i, col_i, &v4)) {
+                    hv4[k] = v4;
+                    ref_bits |= 1ull << chunk;
+                }
+            }
+        }
+        pcol += step_c, prow += step_r;
+        if (pcol >= c.geo.pc) pcol -= c.geo.pc, ++prow;
+    }
+    return ref_bits;  // each lane reads back only what it wrote: no barrier needed
+}
+
+// affine_klt.cpp:131-273 ConstructIncrementalFunction: 21 Hessian + 6 bias chains, on top of the hoisted reference samples.
+template <int METHOD, int G>
+__device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, unsigned long long ref_bits, float (&H)[6][6], float (&b)[6]) {
     static_assert(G >= 27, "affine needs 27 chains");
+    const int pf = RoundUp(c.geo.psize, 4);
+    const float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;
     int valid = 0;
     c.ch.reset();
-    for (int base = 0; base < c.geo.psize; base += G) {
+    int prow = c.g.lane / c.geo.pc, pcol = c.g.lane - prow * c.geo.pc;
+    const int step_r = G / c.geo.pc, step_c = G - step_r * c.geo.pc;
+    int chunk = 0;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t[27];
 #pragma unroll
         for (int q = 0; q < 27; ++q) t[q] = 0.0f;
         bool ok = false;
-        if (k < c.geo.psize) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
-            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
-            const float ax = fadd(fmul(s.a[0], static_cast<float>(dcol)), fmul(s.a[1], static_cast<float>(drow)));
-            const float ay = fadd(fmul(s.a[2], static_cast<float>(dcol)), fmul(s.a[3], static_cast<float>(drow)));
+        if ((ref_bits >> chunk) & 1ull) {  // implies k < psize
+            const float fdrow = static_cast<float>(prow - c.geo.hr), fdcol = static_cast<float>(pcol - c.geo.hc);
+            const float ax = fadd(fmul(s.a[0], fdcol), fmul(s.a[1], fdrow));
+            const float ay = fadd(fmul(s.a[2], fdcol), fmul(s.a[3], fdrow));
             const float row_j = fadd(ay, s.cur_y), col_j = fadd(ax, s.cur_x);
-            const Img &gi = METHOD == kDirect ? cur : ref;
-            const float gr = METHOD == kDirect ? row_j : row_i, gc = METHOD == kDirect ? col_j : col_i;
-            float v0, v1, v2, v3, v4, v5;
-            ok = PxChecked(gi, gr, fsub(gc, 1.0f), &v0) && PxChecked(gi, gr, fadd(gc, 1.0f), &v1) && PxChecked(gi, fsub(gr, 1.0f), gc, &v2) &&
-                 PxChecked(gi, fadd(gr, 1.0f), gc, &v3) && PxChecked(ref, row_i, col_i, &v4) && PxChecked(cur, row_j, col_j, &v5);
+            float dx, dy, v5;
+            if constexpr (METHOD == kDirect) {
+                float v0, v1, v2, v3;
+                ok = PxStencil5(cur, row_j, col_j, &v0, &v1, &v2, &v3, &v5);
+                dx = fsub(v1, v0), dy = fsub(v3, v2);
+            } else {
+                ok = PxChecked(cur, row_j, col_j, &v5);
+                dx = hfx[k], dy = hfy[k];
+            }
             if (ok) {
-                const float dx = fsub(v1, v0), dy = fsub(v3, v2), dt = fsub(v5, v4);
+                const float dt = fsub(v5, hv4[k]);
                 AffineHessianTerms(col_j, row_j, dx, dy, t);
                 AffineBiasTerms(col_j, row_j, dx, dy, dt, &t[21]);
             }
@@ -442,6 +491,8 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float 
         for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
         c.ch.template fold<27>(c.g);
+        pcol += step_c, prow += step_r;
+        if (pcol >= c.geo.pc) pcol -= c.geo.pc, ++prow;
     }
     AffineGatherHessian(c, H);
 #pragma unroll
@@ -461,9 +512,10 @@ __device__ __forceinline__ void AffineApply(AffineState &s, const float (&z)[6],
 // affine_klt.cpp:93-129 TrackOneFeature.
 template <int METHOD, int G>
 __device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
+    const unsigned long long ref_bits = AffineHoistRef<METHOD, G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
         float H[6][6], b[6], z[6];
-        if (AffineConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b) == 0) break;
+        if (AffineConstruct<METHOD, G>(c, cur, s, ref_bits, H, b) == 0) break;
         LdltSolve<6>(H, b, z);
         const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
         const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);

@@ -80,6 +80,40 @@ __device__ __forceinline__ bool PxChecked(const Img &im, float row, float col, f
     return true;
 }
 
+// The gradient stencil of the direct / inverse methods: five GetPixelValue calls at (row, col -/+ 1), (row -/+ 1, col) and
+// (row, col) (basic_klt.cpp:127-134, affine_klt.cpp:140-147, lssd_klt.cpp:202-207).  False when any of them is outside.
+// col - 1 and row - 1 are exact for coordinates >= 1 (guaranteed once their bounds tests pass); when col + 1 and row + 1 are
+// exact too (always, except where the coordinate crosses a binade) the five positions have the same fractions, hence the
+// same four weight products, and overlap in 12 distinct pixels.  Every sample is still the reference's own sequence of
+// rounded operations, ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11; only the common sub-expressions are shared.
+__device__ __forceinline__ bool PxStencil5(const Img &im, float row, float col, float *left, float *right, float *up, float *down, float *centre) {
+    const float cm = fsub(col, 1.0f), cp = fadd(col, 1.0f), rm = fsub(row, 1.0f), rp = fadd(row, 1.0f);
+    if (!(PxInside(im, row, cm) && PxInside(im, row, cp) && PxInside(im, rm, col) && PxInside(im, rp, col) && PxInside(im, row, col))) return false;
+    const int r = __float2int_rd(row), c = __float2int_rd(col);
+    float fr, fc;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(fr) : "r"(r));
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(fc) : "r"(c));
+    const float sr = fsub(row, fr), sc = fsub(col, fc);
+    const float ir = fsub(1.0f, sr), ic = fsub(1.0f, sc);
+    const float w00 = fmul(ic, ir), w01 = fmul(sc, ir), w10 = fmul(ic, sr), w11 = fmul(sc, sr);
+    const uint8_t *v = im.p + r * im.pitch + c;
+    const uint8_t *vm = v - im.pitch, *vp = v + im.pitch, *vq = vp + im.pitch;
+    const float a0 = PxToFloat(vm), a1 = PxToFloat(vm + 1);
+    const float b0 = PxToFloat(v - 1), b1 = PxToFloat(v), b2 = PxToFloat(v + 1), b3 = PxToFloat(v + 2);
+    const float c0 = PxToFloat(vp - 1), c1 = PxToFloat(vp), c2 = PxToFloat(vp + 1), c3 = PxToFloat(vp + 2);
+    const float d0 = PxToFloat(vq), d1 = PxToFloat(vq + 1);
+    *left = fadd(fadd(fadd(fmul(w00, b0), fmul(w01, b1)), fmul(w10, c0)), fmul(w11, c1));
+    *up = fadd(fadd(fadd(fmul(w00, a0), fmul(w01, a1)), fmul(w10, b1)), fmul(w11, b2));
+    *centre = fadd(fadd(fadd(fmul(w00, b1), fmul(w01, b2)), fmul(w10, c1)), fmul(w11, c2));
+    float rv = fadd(fadd(fadd(fmul(w00, b2), fmul(w01, b3)), fmul(w10, c2)), fmul(w11, c3));
+    float dv = fadd(fadd(fadd(fmul(w00, c1), fmul(w01, c2)), fmul(w10, d0)), fmul(w11, d1));
+    if (fsub(cp, 1.0f) != col) rv = PxF(im, row, cp);  // col + 1 was rounded: its own fraction (and possibly base pixel)
+    if (fsub(rp, 1.0f) != row) dv = PxF(im, rp, col);
+    *right = rv;
+    *down = dv;
+    return true;
+}
+
 __device__ __forceinline__ bool IsOutside(const Img &im, float x, float y) {
     return x < 0.0f || x > static_cast<float>(im.cols - 1) || y < 0.0f || y > static_cast<float>(im.rows - 1);
 }
