@@ -99,9 +99,22 @@ __device__ __forceinline__ Scratch CarveScratch(unsigned char *base, const SmemL
     return s;
 }
 
+// Position of a lane's pixel inside the patch while the row-major pixel index advances by G per chunk: replaces k / pc and
+// k % pc (a ~20-instruction integer division each) in the per-iteration loops.
+struct PatchWalk {
+    int row, col;          // k / pc, k % pc for k = chunk * G + lane
+    int step_row, step_col, pc;
+    __device__ __forceinline__ void next() {
+        col += step_col;
+        row += step_row;
+        if (col >= pc) col -= pc, ++row;
+    }
+};
+
 // Everything a group needs while tracking one feature.
 template <int G>
 struct Ctx {
+    PatchWalk walk;  // chunk 0 of this lane
     Group<G> g;
     Chain<G> ch;
     Scratch s;
@@ -209,12 +222,13 @@ __device__ int BasicConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float r
                               float (&b)[2]) {
     int valid = 0;
     c.ch.reset();
+    PatchWalk w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G) {
         const int k = base + c.g.lane;
         float t[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
         bool ok = false;
         if (k < c.geo.psize) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
             const float row_j = fadd(static_cast<float>(drow), cur_y), col_j = fadd(static_cast<float>(dcol), cur_x);
             const Img &gi = METHOD == kInverse ? ref : cur;
@@ -235,6 +249,7 @@ __device__ int BasicConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float r
         for (int q = 0; q < 5; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
         c.ch.template fold<5>(c.g);
+        w.next();
     }
     H[0] = c.g.get(c.ch.acc, 0);
     H[1] = c.g.get(c.ch.acc, 1);
@@ -317,12 +332,13 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
         const int min_col = static_cast<int>(int_col) - c.geo.pc / 2;
         int valid = 0;
         c.ch.reset();
+        PatchWalk w = c.walk;
         for (int base = 0; base < c.geo.psize; base += G) {
             const int k = base + c.g.lane;
             float t0 = 0.0f, t1 = 0.0f;
             bool ok = false;
             if (k < c.geo.psize) {
-                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
+                const int prow = w.row, pcol = w.col;
                 const int row = min_row + prow, col = min_col + pcol;
                 const int e = (prow + 1) * c.geo.ec + pcol + 1;
                 ok = !(row < 0 || row > cur.rows - 2 || col < 0 || col > cur.cols - 2) && c.s.exv[e];
@@ -338,6 +354,7 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
             c.ch.put(c.g.lane, 1, t1);
             valid += c.g.count(ok);
             c.ch.template fold<2>(c.g);
+            w.next();
         }
         if (valid == 0) break;
         const float b[2] = {c.g.get(c.ch.acc, 0), c.g.get(c.ch.acc, 1)};
@@ -420,14 +437,13 @@ __device__ unsigned long long AffineHoistRef(Ctx<G> &c, const Img &ref, float re
     const int pf = RoundUp(c.geo.psize, 4);
     float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;  // hfx / hfy exist for kInverse only
     unsigned long long ref_bits = 0ull;
-    int prow = c.g.lane / c.geo.pc, pcol = c.g.lane - prow * c.geo.pc;
-    const int step_r = G / c.geo.pc, step_c = G - step_r * c.geo.pc;
+    PatchWalk w = c.walk;
     int chunk = 0;
     c.g.sync();  // the previous level has finished reading the scratch
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         if (k < c.geo.psize) {
-            const float row_i = fadd(static_cast<float>(prow - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(pcol - c.geo.hc), ref_x);
+            const float row_i = fadd(static_cast<float>(w.row - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(w.col - c.geo.hc), ref_x);
             if constexpr (METHOD == kInverse) {
                 float v0, v1, v2, v3, v4;
                 if (PxStencil5(ref, row_i, col_i, &v0, &v1, &v2, &v3, &v4)) {
@@ -444,8 +460,7 @@ __device__ unsigned long long AffineHoistRef(Ctx<G> &c, const Img &ref, float re
                 }
             }
         }
-        pcol += step_c, prow += step_r;
-        if (pcol >= c.geo.pc) pcol -= c.geo.pc, ++prow;
+        w.next();
     }
     return ref_bits;  // each lane reads back only what it wrote: no barrier needed
 }
@@ -458,8 +473,7 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
     const float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;
     int valid = 0;
     c.ch.reset();
-    int prow = c.g.lane / c.geo.pc, pcol = c.g.lane - prow * c.geo.pc;
-    const int step_r = G / c.geo.pc, step_c = G - step_r * c.geo.pc;
+    PatchWalk w = c.walk;
     int chunk = 0;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
@@ -468,7 +482,7 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
         for (int q = 0; q < 27; ++q) t[q] = 0.0f;
         bool ok = false;
         if ((ref_bits >> chunk) & 1ull) {  // implies k < psize
-            const float fdrow = static_cast<float>(prow - c.geo.hr), fdcol = static_cast<float>(pcol - c.geo.hc);
+            const float fdrow = static_cast<float>(w.row - c.geo.hr), fdcol = static_cast<float>(w.col - c.geo.hc);
             const float ax = fadd(fmul(s.a[0], fdcol), fmul(s.a[1], fdrow));
             const float ay = fadd(fmul(s.a[2], fdcol), fmul(s.a[3], fdrow));
             const float row_j = fadd(ay, s.cur_y), col_j = fadd(ax, s.cur_x);
@@ -491,8 +505,7 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
         for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
         c.ch.template fold<27>(c.g);
-        pcol += step_c, prow += step_r;
-        if (pcol >= c.geo.pc) pcol -= c.geo.pc, ++prow;
+        w.next();
     }
     AffineGatherHessian(c, H);
 #pragma unroll
@@ -544,6 +557,7 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
     }
     // Hessian at the level-entry cur position: 21 chains of which (1,2), (1,4), (3,4) are overwritten by copies.
     c.ch.reset();
+    PatchWalk w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G) {
         const int k = base + c.g.lane;
         float t[27];
@@ -552,8 +566,8 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
         if (k < c.geo.psize) {
             float dx, dy;
             if (ExGradient(c, k, &dx, &dy)) {
-                const float x = fadd(static_cast<float>(k % c.geo.pc - c.geo.hc), s.cur_x);
-                const float y = fadd(static_cast<float>(k / c.geo.pc - c.geo.hr), s.cur_y);
+                const float x = fadd(static_cast<float>(w.col - c.geo.hc), s.cur_x);
+                const float y = fadd(static_cast<float>(w.row - c.geo.hr), s.cur_y);
                 AffineHessianTerms(x, y, dx, dy, t);
             }
             c.s.dx[k] = dx;
@@ -562,6 +576,7 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
 #pragma unroll
         for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
         c.ch.template fold<21>(c.g);
+        w.next();
     }
     float H[6][6];
     AffineGatherHessian(c, H);
@@ -577,12 +592,13 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
         int valid = 0;
         c.ch.reset();
+        PatchWalk w = c.walk;
         for (int base = 0; base < c.geo.psize; base += G) {
             const int k = base + c.g.lane;
             float t[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
             bool ok = false;
             if (k < c.geo.psize) {
-                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
+                const int prow = w.row, pcol = w.col;
                 const int drow = prow - c.geo.hr, dcol = pcol - c.geo.hc;
                 const float ax = fadd(fmul(s.a[0], static_cast<float>(dcol)), fmul(s.a[1], static_cast<float>(drow)));
                 const float ay = fadd(fmul(s.a[2], static_cast<float>(dcol)), fmul(s.a[3], static_cast<float>(drow)));
@@ -599,6 +615,7 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
             for (int q = 0; q < 6; ++q) c.ch.put(c.g.lane, q, t[q]);
             valid += c.g.count(ok);
             c.ch.template fold<6>(c.g);
+            w.next();
         }
         if (valid == 0) break;
         float b[6], z[6];
@@ -681,12 +698,13 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
     unsigned long long ok_bits = 0ull;  // bit q: this lane's pixel of chunk q is valid (psize <= 64 * G, checked on the host)
     c.ch.reset();
     int chunk = 0;
+    PatchWalk w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t0 = 0.0f, t1 = 0.0f;
         bool ok = false;
         if (k < c.geo.psize) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
             float row_j, col_j;
             LssdWarp(s, col_i, row_i, &col_j, &row_j);
@@ -705,19 +723,21 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
         c.ch.put(c.g.lane, 1, t1);
         valid += c.g.count(ok);
         c.ch.template fold<2>(c.g);
+        w.next();
     }
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
 
     c.ch.reset();
     chunk = 0;
+    w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) t[q] = 0.0f;
         if ((ok_bits >> chunk) & 1ull) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
             float row_j, col_j;
             LssdWarp(s, col_i, row_i, &col_j, &row_j);
@@ -743,6 +763,7 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
 #pragma unroll
         for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
         c.ch.template fold<9>(c.g);
+        w.next();
     }
     LssdGather(c, H, b);
     return valid;
@@ -758,19 +779,21 @@ __device__ unsigned long long LssdHoistRef(Ctx<G> &c, const Img &ref, float ref_
     float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf;
     unsigned long long ref_bits = 0ull;
     int chunk = 0;
+    PatchWalk w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         if (k < c.geo.psize) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
-            const float cm = fsub(col_i, 1.0f), cp = fadd(col_i, 1.0f), rm = fsub(row_i, 1.0f), rp = fadd(row_i, 1.0f);
-            if (PxInside(ref, row_i, cm) && PxInside(ref, row_i, cp) && PxInside(ref, rm, col_i) && PxInside(ref, rp, col_i) && PxInside(ref, row_i, col_i)) {
-                hfx[k] = fsub(PxF(ref, row_i, cp), PxF(ref, row_i, cm));
-                hfy[k] = fsub(PxF(ref, rp, col_i), PxF(ref, rm, col_i));
-                hv4[k] = PxF(ref, row_i, col_i);
+            float v0, v1, v2, v3, v4;
+            if (PxStencil5(ref, row_i, col_i, &v0, &v1, &v2, &v3, &v4)) {
+                hfx[k] = fsub(v1, v0);
+                hfy[k] = fsub(v3, v2);
+                hv4[k] = v4;
                 ref_bits |= 1ull << chunk;
             }
         }
+        w.next();
     }
     return ref_bits;
 }
@@ -786,12 +809,13 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
     unsigned long long ok_bits = 0ull;
     c.ch.reset();
     int chunk = 0;
+    PatchWalk w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t0 = 0.0f, t1 = 0.0f;
         bool ok = false;
         if ((ref_bits >> chunk) & 1ull) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
             float row_j, col_j, v5;
             LssdWarp(s, col_i, row_i, &col_j, &row_j);
@@ -807,19 +831,21 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
         c.ch.put(c.g.lane, 1, t1);
         valid += c.g.count(ok);
         c.ch.template fold<2>(c.g);
+        w.next();
     }
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
 
     c.ch.reset();
     chunk = 0;
+    w = c.walk;
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t[9];
 #pragma unroll
         for (int q = 0; q < 9; ++q) t[q] = 0.0f;
         if ((ok_bits >> chunk) & 1ull) {
-            const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
             const float jp0 = fdiv(hfx[k], ref_avg), jp1 = fdiv(hfy[k], ref_avg);
             const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
@@ -834,6 +860,7 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
 #pragma unroll
         for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
         c.ch.template fold<9>(c.g);
+        w.next();
     }
     LssdGather(c, H, b);
     return valid;
@@ -900,11 +927,12 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
         const int max_row = min_row + c.geo.pr * 2, max_col = min_col + c.geo.pc * 2;
         const bool partly_outside = min_row < 0 || max_row > cur.rows - 2 || min_col < 0 || max_col > cur.cols - 2;
         int valid_cur = 0;
+        PatchWalk w = c.walk;
         for (int base = 0; base < c.geo.psize; base += G) {
             const int k = base + c.g.lane;
             bool ok = false;
             if (k < c.geo.psize) {
-                const int drow = k / c.geo.pc - c.geo.hr, dcol = k % c.geo.pc - c.geo.hc;
+                const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
                 const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
                 float row_j, col_j;
                 LssdWarp(s, col_i, row_i, &col_j, &row_j);
@@ -920,6 +948,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
                 c.s.curv[k] = ok ? 1 : 0;
             }
             valid_cur += c.g.count(ok);
+            w.next();
         }
         c.g.sync();
         if (valid_cur == 0) break;
@@ -933,6 +962,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
         // ComputeHessianAndBias: 9 chains.
         int valid = 0;
         c.ch.reset();
+        w = c.walk;
         for (int base = 0; base < c.geo.psize; base += G) {
             const int k = base + c.g.lane;
             float t[9];
@@ -940,8 +970,8 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
             for (int q = 0; q < 9; ++q) t[q] = 0.0f;
             bool ok = false;
             if (k < c.geo.psize) {
-                const int prow = k / c.geo.pc, pcol = k % c.geo.pc;
-                const float row_i = fadd(static_cast<float>(prow - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(pcol - c.geo.hc), ref_x);
+                const int prow = w.row, pcol = w.col;
+                const float row_i = fadd(static_cast<float>(w.row - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(w.col - c.geo.hc), ref_x);
                 const int e = (prow + 1) * c.geo.ec + pcol + 1;
                 ok = c.s.exv[e] && c.s.curv[k];
                 if (ok) {
@@ -958,6 +988,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
             for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
             valid += c.g.count(ok);
             c.ch.template fold<9>(c.g);
+            w.next();
         }
         if (valid == 0) break;
         float H[3][3], b[3], v[3];
@@ -996,6 +1027,11 @@ __global__ void __launch_bounds__(128) KltKernel(KltLaunch a, SmemLayout layout)
     c.geo.er = c.geo.pr + 2;
     c.geo.ec = c.geo.pc + 2;
     c.geo.esize = c.geo.er * c.geo.ec;
+    c.walk.pc = c.geo.pc;
+    c.walk.row = c.g.lane / c.geo.pc;
+    c.walk.col = c.g.lane - c.walk.row * c.geo.pc;
+    c.walk.step_row = G / c.geo.pc;
+    c.walk.step_col = G - c.walk.step_row * c.geo.pc;
 
     const int pair = a.feat_pair[f];
     const int local = f - a.feat_offsets[pair];
