@@ -2,16 +2,19 @@
 """bench.py -- headline benchmark of the hot path (contract: see the task statement / DESIGN.md "Measurement").
 
 Metric (BASELINE.json): tracked features/sec (4-level KLT, 752x480), whole job over N GPUs.
-Workload: the batch shape of BASELINE configs[1] (1000 frame pairs x 2000 features per GPU, 752x480, 4 pyramid levels),
-tracked with the north-star tracker (basic KLT, kInverse, 15x15 patches).  One "step" = pyramid construction of all
-2000 images of the batch + tracking of all 2 000 000 features.  Frame pairs shard across GPUs with no collective on
-the data path (weak scaling: every rank owns its own 1000 pairs).
+Workload (default, --workload configs1): BASELINE configs[1] -- affine KLT, kDirect AND kFast, 4-level pyramid, 2000
+features per frame, a batch of 1000 frame pairs per GPU, 13x13 patches (the reference's default half size 6).  One "step" =
+pyramid construction of all 2000 images of the batch + TrackFeatures with kDirect + TrackFeatures with kFast on every pair,
+i.e. 2 x 2 000 000 tracked features per step and GPU.  Frame pairs shard across GPUs with no collective on the data path
+(weak scaling: every rank owns its own 1000 pairs).
 
-  value : device-resident throughput (images + features already in HBM), CUDA-event timed on the library's stream
-  e2e   : same metric through the C ABI with HOST buffers (pinned): H2D of the images and features and D2H of the
-          results are inside the timed region
+  value      : device-resident throughput (images + features already in HBM), CUDA-event timed on the library's stream
+  e2e        : same metric through the C ABI with HOST buffers (pinned): H2D of the images and features and D2H of the
+               results are inside the timed region (one ftk_track_image_pairs call per method)
+  north_star : the same batch tracked with the tracker BASELINE's north_star sets its target on (basic KLT, kInverse, 15x15):
+               value / e2e / roofline of that configuration (--workload north_star makes it the headline instead)
   --impl reference : the reference's own CPU implementation (oracle/_ref, built from the reference's sources) on all
-          host cores, bounded sample of the same workload.
+               host cores, bounded sample of the same workload.
 """
 import argparse
 import ctypes as C
@@ -29,12 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ROWS, COLS, LEVELS = 480, 752, 4
-HALF = 7
 PAIRS_PER_GPU = 1000
 FEATURES_PER_PAIR = 2000
 UNIQUE_PAIRS = 8  # synthetic pairs generated; the batch tiles them (distinct HBM addresses, identical content)
 METRIC = "tracked features/sec (4-lvl KLT, 752x480)"
 UNIT = "features/s"
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "configs1": [("affine", "direct", 6), ("affine", "fast", 6)],
+    # BASELINE.json north_star target: >= 1e8 features/s/GPU for 4-level inverse basic KLT with 15x15 patches
+    "north_star": [("basic", "inverse", 7)],
+}
 
 
 def parse():
@@ -43,23 +51,39 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS))
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--features", type=int, default=FEATURES_PER_PAIR)
-    ap.add_argument("--variant", default="basic")
-    ap.add_argument("--method", default="inverse")
-    ap.add_argument("--half", type=int, default=HALF)
+    ap.add_argument("--variant", default=None, help="with --method / --half: time one tracker instead of a named workload (profiling)")
+    ap.add_argument("--method", default=None)
+    ap.add_argument("--half", type=int, default=None)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (matchers, other trackers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the north_star object of the configs1 workload")
     return ap.parse_args()
 
 
+def trackers_of(args):
+    if args.variant or args.method or args.half is not None:
+        return [(args.variant or "basic", args.method or "inverse", 7 if args.half is None else args.half)]
+    return WORKLOADS[args.workload]
+
+
+def tracker_name(t):
+    return f"{t[0]} KLT {t[1]} {2 * t[2] + 1}x{2 * t[2] + 1}"
+
+
 def workload_config(args):
+    trackers = trackers_of(args)
+    what = "BASELINE configs[1]" if trackers == WORKLOADS["configs1"] else ("BASELINE north_star target configuration on the configs[1] batch shape"
+                                                                            if trackers == WORKLOADS["north_star"] else "single tracker on the configs[1] batch shape")
     return {
-        "workload": f"BASELINE configs[1] batch shape: {args.pairs} frame pairs/GPU x {args.features} features, {COLS}x{ROWS}, {LEVELS}-level pyramid; "
-                    f"tracker = {args.variant} KLT {args.method}, {2 * args.half + 1}x{2 * args.half + 1} patches (north-star target config); "
-                    "step = pyramid build of both frames + TrackFeatures for every pair",
+        "workload": f"{what}: {args.pairs} frame pairs/GPU x {args.features} features/frame, {COLS}x{ROWS}, {LEVELS}-level pyramid; trackers = "
+                    + " + ".join(tracker_name(t) for t in trackers)
+                    + "; step = pyramid build of both frames of every pair + one TrackFeatures per tracker and pair",
         "pairs_per_gpu": args.pairs, "features_per_pair": args.features, "image": [ROWS, COLS], "levels": LEVELS,
-        "patch": 2 * args.half + 1, "variant": args.variant, "method": args.method,
+        "trackers": [{"variant": t[0], "method": t[1], "patch": 2 * t[2] + 1} for t in trackers],
+        "tracked_features_per_step_per_gpu": len(trackers) * args.pairs * args.features,
         "l2_policy": "inputs larger than L2 (pyramid batch ~1 GB per GPU vs 126 MB L2)",
         "sharding": "frame pairs split across ranks, no collective on the data path",
     }
@@ -87,8 +111,9 @@ def cpu_checker():
     return po.OracleLib(), "port"
 
 
-def cpu_track_sample(lib, params, refs, curs, uvs, n_pairs, threads):
-    """Tracks n_pairs pairs (cycling over the unique ones) on `threads` host threads; returns (seconds, features)."""
+def cpu_track_sample(lib, params_list, refs, curs, uvs, n_pairs, threads):
+    """Runs the workload's trackers on n_pairs pairs (cycling over the unique ones) on `threads` host threads; a pair's pyramids
+    are built once per tracker call, as the reference's demo does (test/test_optical_flow.cpp:69-73).  Returns (seconds, features)."""
     jobs = list(range(n_pairs))
     lock = threading.Lock()
     done = [0]
@@ -100,10 +125,11 @@ def cpu_track_sample(lib, params, refs, curs, uvs, n_pairs, threads):
                     return
                 p = jobs.pop()
             u = p % len(refs)
-            ok, _, _ = lib.pyramid_and_track(params, LEVELS, refs[u], curs[u], uvs[u])
-            assert ok
+            for params in params_list:
+                ok, _, _ = lib.pyramid_and_track(params, LEVELS, refs[u], curs[u], uvs[u])
+                assert ok
             with lock:
-                done[0] += len(uvs[u])
+                done[0] += len(uvs[u]) * len(params_list)
 
     ts = [threading.Thread(target=worker) for _ in range(threads)]
     t0 = time.perf_counter()
@@ -114,23 +140,28 @@ def cpu_track_sample(lib, params, refs, curs, uvs, n_pairs, threads):
     return time.perf_counter() - t0, done[0]
 
 
-def run_reference(args):
+def cpu_params(trackers, n_feat):
     from oracle import pyoracle as po
+    return [po.make_params(v, m, half=h, max_points=max(500, n_feat)) for v, m, h in trackers]
+
+
+def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     lib, kind = cpu_checker()
     cores = os.cpu_count() or 1
     n_feat = args.features
+    trackers = trackers_of(args)
     refs, curs, uvs = make_unique_pairs(min(UNIQUE_PAIRS, 4), n_feat)
-    params = po.make_params(args.variant, args.method, half=args.half, max_points=max(500, n_feat))
-    # bounded sample: ~cores pairs per step (about cores * 0.3 s of CPU work for basic inverse 15x15 x 2000 features)
+    params_list = cpu_params(trackers, n_feat)
+    # bounded sample: one frame pair per host core and step (a few seconds of CPU work per step)
     sample_pairs = max(1, min(cores, 64))
     for _ in range(max(args.warmup, 0) and 1):
-        cpu_track_sample(lib, params, refs, curs, uvs, min(sample_pairs, cores), cores)
+        cpu_track_sample(lib, params_list, refs, curs, uvs, min(sample_pairs, cores), cores)
     times, feats = [], 0
     for _ in range(args.steps):
-        dt, nf = cpu_track_sample(lib, params, refs, curs, uvs, sample_pairs, cores)
+        dt, nf = cpu_track_sample(lib, params_list, refs, curs, uvs, sample_pairs, cores)
         times.append(dt)
         feats = nf
     total = sum(times)
@@ -140,7 +171,8 @@ def run_reference(args):
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": "reference", "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{sample_pairs} frame pairs x {n_feat} features per step (pyramid x2 + TrackFeatures), one tracker object per thread"},
+                         "sample": f"{sample_pairs} frame pairs x {n_feat} features per step, per pair and tracker: CreateImagePyramid x2 + TrackFeatures; "
+                                   "one tracker object per host thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -288,6 +320,37 @@ def run_extras(ctx, L, torch, local_rank, steps):
     return out
 
 
+def oracle_trace(oracle, cparams, refs, curs, uvs, u, n_feat):
+    """The oracle's results and per-feature patch-iteration counts (SURVEY 8(d) unit) for unique pair u."""
+    rl, cl = oracle.pyramid_build(refs[u], LEVELS), oracle.pyramid_build(curs[u], LEVELS)
+    it = np.zeros(n_feat, np.int32)
+    levels = len(rl)
+    rows = np.array([a.shape[0] for a in rl], np.int32)
+    cols = np.array([a.shape[1] for a in rl], np.int32)
+    PtrArr = C.POINTER(C.c_uint8) * levels
+    rp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in rl])
+    cp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in cl])
+    cu = np.zeros((n_feat, 2), np.float32)
+    st = np.zeros(n_feat, np.uint8)
+    f = oracle.lib.ftko_klt_track_traced
+    f.restype = C.c_int
+    f(C.byref(cparams), C.c_int32(levels), rp, cp, rows.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), C.c_int32(n_feat),
+      uvs[u].ctypes.data_as(C.c_void_p), cu.ctypes.data_as(C.c_void_p), C.c_int32(0), st.ctypes.data_as(C.c_void_p), C.c_int32(0), C.c_int32(0),
+      it.ctypes.data_as(C.c_void_p))
+    return cu, st, it
+
+
+def algorithmic_flops(tracker, iters, n_total):
+    """SURVEY 8(d) per-unit figures x executed units (patch iterations from the oracle's trace, feature-levels)."""
+    v, m, h = tracker
+    P = (2 * h + 1) ** 2
+    if v == "basic":  # hoisted form: 20*P flop per iteration + ((2h+3)^2-4)*15 + 8*P flop per feature-level
+        return iters * 20.0 * P + n_total * LEVELS * ((((2 * h + 3) ** 2) - 4) * 15.0 + 8.0 * P), "20*P flop/iteration + ((2h+3)^2-4)*15 + 8*P flop/feature-level"
+    if v == "affine":  # ~90*P flop per iteration + 6x6 LDLT ~250 flop
+        return iters * (90.0 * P + 250.0), "90*P + 250 flop/iteration"
+    return iters * 60.0 * P, "60*P flop/iteration (hoisted form)"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -304,8 +367,11 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ft.Context(local_rank)
     L = ftk_lib()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    vp = C.c_void_p
 
+    trackers = trackers_of(args)
     n_pairs, n_feat = args.pairs, args.features
     refs, curs, uvs = make_unique_pairs(UNIQUE_PAIRS, n_feat)
     # this rank's shard: pairs [rank*n_pairs, (rank+1)*n_pairs) of the global batch, cycling over the unique pairs
@@ -324,40 +390,23 @@ def run_b200(args):
     for p, u in enumerate(uniq):
         hr[p * n_feat:(p + 1) * n_feat] = uvs[u]
     offsets = (np.arange(n_pairs + 1, dtype=np.int32) * n_feat)
-    ref_idx = np.arange(n_pairs, dtype=np.int32)
-    cur_idx = ref_idx + n_pairs
 
     pyr = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, 2 * n_pairs)
-    klt = {"basic": ft.OpticalFlowBasicKlt, "affine": ft.OpticalFlowAffineKlt, "lssd": ft.OpticalFlowLssdKlt}[args.variant](ctx)
-    o = klt.options()
-    o.kPatchRowHalfSize = o.kPatchColHalfSize = args.half
-    o.kMethod = {"inverse": ft.OpticalFlowMethod.kInverse, "direct": ft.OpticalFlowMethod.kDirect, "fast": ft.OpticalFlowMethod.kFast}[args.method]
-    o.kMaxTrackPointsNumber = max(500, n_feat)
-    params = klt._params()
-
-    # device-resident inputs for `value`
-    d_ref_uv = torch.from_numpy(hr).to(f"cuda:{local_rank}")
-    d_cur_uv = torch.empty_like(d_ref_uv)
-    d_status = torch.empty((n_total,), dtype=torch.uint8, device=d_ref_uv.device)
-    d_offsets = torch.from_numpy(offsets).to(d_ref_uv.device)
-    d_ref_idx = torch.from_numpy(ref_idx).to(d_ref_uv.device)
-    d_cur_idx = torch.from_numpy(cur_idx).to(d_ref_uv.device)
+    d_ref_uv = torch.from_numpy(hr).to(dev)
+    d_offsets = torch.from_numpy(offsets).to(dev)
+    d_ref_idx = torch.arange(n_pairs, dtype=torch.int32, device=dev)
+    d_cur_idx = d_ref_idx + n_pairs
     pyr.set_images_ptr(host_images.data_ptr(), 2 * n_pairs)
     ctx.synchronize()
-    vp = C.c_void_p
 
-    def step_resident():
-        ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
-        flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(d_ref_idx.data_ptr()), vp(d_cur_idx.data_ptr()),
-                                  vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(d_cur_uv.data_ptr()), vp(d_status.data_ptr()), flags))
-
-    def step_e2e():
-        # the user-facing call: host images + host features in, host results out (H2D of chunk k+1 overlaps compute of chunk k)
-        flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-        ctx.check(L.ftk_track_image_pairs(ctx._h, C.byref(params), ROWS, COLS, LEVELS, n_pairs, vp(host_images.data_ptr()),
-                                          vp(host_images.data_ptr() + n_pairs * plane), vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()),
-                                          vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+    def klt_params(tracker):
+        v, m, h = tracker
+        klt = {"basic": ft.OpticalFlowBasicKlt, "affine": ft.OpticalFlowAffineKlt, "lssd": ft.OpticalFlowLssdKlt}[v](ctx)
+        o = klt.options()
+        o.kPatchRowHalfSize = o.kPatchColHalfSize = h
+        o.kMethod = {"inverse": ft.OpticalFlowMethod.kInverse, "direct": ft.OpticalFlowMethod.kDirect, "fast": ft.OpticalFlowMethod.kFast}[m]
+        o.kMaxTrackPointsNumber = max(500, n_feat)
+        return klt._params()
 
     def barrier():
         ctx.synchronize()
@@ -366,7 +415,7 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def timed(fn, steps, per_kernel=False):
+    def timed(fn, steps):
         """Times `steps` calls with CUDA events on the library's stream, bracketed by barrier + synchronize; max over ranks."""
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -378,60 +427,130 @@ def run_b200(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
-            t = torch.tensor([ms], device=d_ref_uv.device)
+            t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, ctx.kernel_launches - launches0
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms, launches = timed(step_resident, args.steps)
-    clocks = sampler.stop()
-    tracked_per_step = n_total * world
-    value = tracked_per_step * args.steps / (ms * 1e-3)
-
-    # per-kernel split (CUDA events around each stage, same stream), for the roofline objects
     def pyramid_only():
         ctx.check(L.ftk_pyramid_build(ctx._h, pyr._h, 0, 2 * n_pairs))
 
-    def klt_only():
-        flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-        ctx.check(L.ftk_klt_track(ctx._h, C.byref(params), pyr._h, pyr._h, n_pairs, vp(d_ref_idx.data_ptr()), vp(d_cur_idx.data_ptr()),
-                                  vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(d_cur_uv.data_ptr()), vp(d_status.data_ptr()), flags))
+    class Run:
+        """One tracker list on the resident batch: device outputs per tracker, the resident step, the end-to-end step."""
 
-    ms_pyr, _ = timed(pyramid_only, args.steps)
-    ms_klt, _ = timed(klt_only, args.steps)
-    status_host = d_status.cpu().numpy()
+        def __init__(self, tracker_list):
+            self.trackers = tracker_list
+            self.params = [klt_params(t) for t in tracker_list]
+            self.d_cur = [torch.empty_like(d_ref_uv) for _ in tracker_list]
+            self.d_st = [torch.empty((n_total,), dtype=torch.uint8, device=dev) for _ in tracker_list]
 
-    # end to end through the C ABI with host buffers
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
-    e2e_value = tracked_per_step * args.steps / (ms_e2e * 1e-3)
-    h2d = 2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4
-    d2h = n_total * 9
+        def klt_only(self, i):
+            flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+            ctx.check(L.ftk_klt_track(ctx._h, C.byref(self.params[i]), pyr._h, pyr._h, n_pairs, vp(d_ref_idx.data_ptr()), vp(d_cur_idx.data_ptr()),
+                                      vp(d_offsets.data_ptr()), vp(d_ref_uv.data_ptr()), vp(self.d_cur[i].data_ptr()), vp(self.d_st[i].data_ptr()), flags))
 
-    # the temporal form: n_pairs + 1 host frames alternating the two images of one unique pair, each uploaded once
-    seq_u = rank % UNIQUE_PAIRS
-    host_seq = torch.empty((n_pairs + 1, ROWS, COLS), dtype=torch.uint8).pin_memory()
-    hs = host_seq.numpy()
-    hs[0::2] = refs[seq_u]
-    hs[1::2] = curs[seq_u]
-    host_seq_uv = torch.empty((n_total, 2), dtype=torch.float32).pin_memory()
-    host_seq_uv.numpy().reshape(n_pairs, n_feat, 2)[:] = uvs[seq_u]
+        def step_resident(self):
+            pyramid_only()
+            for i in range(len(self.trackers)):
+                self.klt_only(i)
 
-    def step_e2e_sequence():
-        flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-        ctx.check(L.ftk_track_image_sequence(ctx._h, C.byref(params), ROWS, COLS, LEVELS, n_pairs + 1, vp(host_seq.data_ptr()), vp(offsets.ctypes.data),
-                                             vp(host_seq_uv.data_ptr()), vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+        def step_e2e(self):
+            # the user-facing call, once per tracker: host images + host features in, host results out (H2D of chunk k+1 overlaps
+            # compute of chunk k)
+            flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+            for prm in self.params:
+                ctx.check(L.ftk_track_image_pairs(ctx._h, C.byref(prm), ROWS, COLS, LEVELS, n_pairs, vp(host_images.data_ptr()),
+                                                  vp(host_images.data_ptr() + n_pairs * plane), vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()),
+                                                  vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
 
-    for _ in range(2):
-        step_e2e_sequence()
-    ms_seq, _ = timed(step_e2e_sequence, args.steps)
-    seq_value = tracked_per_step * args.steps / (ms_seq * 1e-3)
-    seq_tracked = float((host_status.numpy() == 1).mean())
+        def measure(self, steps, warmup, sample_clocks):
+            n_track = len(self.trackers)
+            for _ in range(max(warmup, 3)):
+                self.step_resident()
+            sampler = ClockSampler(local_rank) if sample_clocks else None
+            if sampler:
+                sampler.start()
+            ms, launches = timed(self.step_resident, steps)
+            clocks = sampler.stop() if sampler else None
+            per_step = n_track * n_total * world
+            res = {"value": per_step * steps / (ms * 1e-3), "ms_per_step": ms / steps, "launches": launches, "clocks": clocks}
+            ms_pyr, _ = timed(pyramid_only, steps)
+            res["kernel_ms"] = {"pyramid": ms_pyr / steps}
+            for i, t in enumerate(self.trackers):
+                ms_k, _ = timed(lambda i=i: self.klt_only(i), steps)
+                res["kernel_ms"][f"klt_{t[0]}_{t[1]}"] = ms_k / steps
+            res["tracked_fraction"] = {f"{t[0]}_{t[1]}": float((self.d_st[i] == 1).float().mean().item()) for i, t in enumerate(self.trackers)}
+            for _ in range(2):
+                self.step_e2e()
+            ms_e2e, _ = timed(self.step_e2e, steps)
+            h2d = n_track * (2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4)
+            d2h = n_track * n_total * 9
+            res["e2e"] = {"value": per_step * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                          "ms_per_step": ms_e2e / steps,
+                          "api": "ftk_track_image_pairs, one call per tracker (pinned host images + features in, host results out; H2D of chunk k+1 "
+                                 "overlaps compute of chunk k)"}
+            return res
+
+        def rooflines(self, res, oracle):
+            """Per tracker: algorithmic flops (oracle iteration trace) / kernel time, against the derived fp32 issue peak; plus the
+            at-scale parity spot check of the timed run's outputs against the oracle."""
+            from oracle import pyoracle as po
+            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+            out, parity = {}, {"pairs": 0, "status_mismatch": 0, "position_bits_mismatch": 0}
+            for i, t in enumerate(self.trackers):
+                cparams = po.make_params(t[0], t[1], half=t[2], max_points=max(500, n_feat))
+                st_host = self.d_st[i].cpu().numpy()
+                uv_host = self.d_cur[i].cpu().numpy()
+                iters = 0
+                for u in range(UNIQUE_PAIRS):
+                    if u not in uniq:
+                        continue
+                    cu, st, it = oracle_trace(oracle, cparams, refs, curs, uvs, u, n_feat)
+                    iters += int(it.sum()) * sum(1 for x in uniq if x == u)
+                    p0 = uniq.index(u)
+                    sl = slice(p0 * n_feat, (p0 + 1) * n_feat)
+                    parity["pairs"] += 1
+                    parity["status_mismatch"] += int((st_host[sl] != st).sum())
+                    same = (uv_host[sl].view(np.uint32) == cu.view(np.uint32)) | (np.isnan(uv_host[sl]) & np.isnan(cu))
+                    parity["position_bits_mismatch"] += int((~same).any(1).sum())
+                flops, formula = algorithmic_flops(t, iters, n_total)
+                ms_k = res["kernel_ms"][f"klt_{t[0]}_{t[1]}"]
+                tfs = flops / (ms_k * 1e-3) / 1e12
+                out[f"{t[0]}_{t[1]}"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
+                                         "frac": tfs / fp32_peak, "traffic": None,
+                                         "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
+                                         "algorithmic_flops_per_launch": flops, "algorithmic_flops_formula": formula,
+                                         "patch_iterations_per_feature": iters / n_total, "launch_ms": ms_k,
+                                         "kernel": "BasicInverseFastKernel<15,15>" if t == ("basic", "inverse", 7) else f"KltKernel ({tracker_name(t)})"}
+            return out, parity
+
+    head = Run(trackers)
+    res = head.measure(args.steps, args.warmup, sample_clocks=True)
+
+    north = north_res = None
+    if trackers == WORKLOADS["configs1"] and not args.no_north_star:
+        north = Run(WORKLOADS["north_star"])
+        north_res = north.measure(args.steps, args.warmup, sample_clocks=False)
+        # the temporal form (SURVEY 8(f)): n_pairs + 1 host frames alternating the two images of one unique pair, each uploaded once
+        seq_u = rank % UNIQUE_PAIRS
+        hs = host_images.numpy()[:n_pairs + 1]  # reuse the pinned buffer: the resident pyramids are not needed any more
+        hs[0::2] = refs[seq_u]
+        hs[1::2] = curs[seq_u]
+        host_ref_uv.numpy().reshape(n_pairs, n_feat, 2)[:] = uvs[seq_u]
+
+        def step_e2e_sequence():
+            flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+            ctx.check(L.ftk_track_image_sequence(ctx._h, C.byref(north.params[0]), ROWS, COLS, LEVELS, n_pairs + 1, vp(host_images.data_ptr()),
+                                                 vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()), vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+
+        for _ in range(2):
+            step_e2e_sequence()
+        ms_seq, _ = timed(step_e2e_sequence, args.steps)
+        north_res["e2e_sequence"] = {"value": n_total * world * args.steps / (ms_seq * 1e-3), "unit": UNIT, "ms_per_step": ms_seq / args.steps,
+                                     "h2d_bytes_per_step": ((n_pairs + 1) * plane + n_total * 8) * world,
+                                     "tracked_fraction": float((host_status.numpy() == 1).mean()),
+                                     "api": "ftk_track_image_sequence (n_pairs + 1 host frames, pair k = frame k -> k+1; every frame uploaded and its pyramid "
+                                            "built once)"}
 
     if rank != 0:
         if world > 1:
@@ -445,23 +564,18 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-
     # pyramid: algorithmic bytes = read H*W + write H*W*(1/4+1/16+1/64) per image (479 400 B per 752x480 image)
     pyr_bytes = sum((ROWS >> l) * (COLS >> l) for l in range(LEVELS)) * 2 * n_pairs
-    pyr_gbs = pyr_bytes / (ms_pyr / args.steps * 1e-3) / 1e9
+    pyr_gbs = pyr_bytes / (res["kernel_ms"]["pyramid"] * 1e-3) / 1e9
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
-        "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
-                "api": "ftk_track_image_pairs (pinned host images + features in, host results out; H2D of chunk k+1 overlaps compute of chunk k)"},
-        "e2e_sequence": {"value": seq_value, "unit": UNIT, "ms_per_step": ms_seq / args.steps, "h2d_bytes_per_step": ((n_pairs + 1) * plane + n_total * 8) * world,
-                         "tracked_fraction": seq_tracked,
-                         "api": "ftk_track_image_sequence (n_pairs + 1 host frames, pair k = frame k -> k+1; every frame uploaded and its pyramid built once)"},
-        "tracked_fraction": float((status_host == 1).mean()),
-        "kernel_ms": {"pyramid": ms_pyr / args.steps, "klt": ms_klt / args.steps},
+        "clocks": res["clocks"], "gpu_launches": res["launches"],
+        "e2e": res["e2e"],
+        "tracked_fraction": res["tracked_fraction"],
+        "kernel_ms": res["kernel_ms"],
         "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
                              "traffic": (72.85e6 + 6.28e6) / 200 * 2 * n_pairs,  # ncu dram bytes per image (profiles/r1_ncu_traffic.json) x images
                              "peak_source": hbm_src, "algorithmic_bytes_per_launch": pyr_bytes},
@@ -471,59 +585,40 @@ def run_b200(args):
         from oracle import pyoracle as po
         lib_cpu, kind = cpu_checker()
         cores = os.cpu_count() or 1
-        cparams = po.make_params(args.variant, args.method, half=args.half, max_points=max(500, n_feat))
+        plist = cpu_params(trackers, n_feat)
         sample_pairs = max(1, min(cores, 64))
-        cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, min(sample_pairs, cores), cores)
-        dt, nf = cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, sample_pairs, cores)
-        dt1, nf1 = cpu_track_sample(lib_cpu, cparams, refs, curs, uvs, 1, 1)
+        cpu_track_sample(lib_cpu, plist, refs, curs, uvs, min(sample_pairs, cores), cores)
+        dt, nf = cpu_track_sample(lib_cpu, plist, refs, curs, uvs, sample_pairs, cores)
+        dt1, nf1 = cpu_track_sample(lib_cpu, plist, refs, curs, uvs, 1, 1)
         line["cpu_baseline"] = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                                "sample": f"{sample_pairs} frame pairs x {n_feat} features (pyramid x2 + TrackFeatures), one tracker object per thread",
+                                "sample": f"{sample_pairs} frame pairs x {n_feat} features, per pair and tracker: CreateImagePyramid x2 + TrackFeatures; one "
+                                          "tracker object per host thread",
                                 "single_thread_value": nf1 / dt1}
-        # KLT roofline: algorithmic flops from the oracle's iteration trace on the unique pairs (the batch tiles them)
         oracle = po.OracleLib()
-        iters = 0
-        for u in range(UNIQUE_PAIRS):
-            rl, cl = oracle.pyramid_build(refs[u], LEVELS), oracle.pyramid_build(curs[u], LEVELS)
-            it = np.zeros(n_feat, np.int32)
-            levels = len(rl)
-            rows = np.array([a.shape[0] for a in rl], np.int32)
-            cols = np.array([a.shape[1] for a in rl], np.int32)
-            PtrArr = C.POINTER(C.c_uint8) * levels
-            rp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in rl])
-            cp = PtrArr(*[a.ctypes.data_as(C.POINTER(C.c_uint8)) for a in cl])
-            cu = np.zeros((n_feat, 2), np.float32)
-            st = np.zeros(n_feat, np.uint8)
-            f = oracle.lib.ftko_klt_track_traced
-            f.restype = C.c_int
-            f(C.byref(cparams), C.c_int32(levels), rp, cp, rows.ctypes.data_as(C.c_void_p), cols.ctypes.data_as(C.c_void_p), C.c_int32(n_feat),
-              uvs[u].ctypes.data_as(C.c_void_p), cu.ctypes.data_as(C.c_void_p), C.c_int32(0), st.ctypes.data_as(C.c_void_p), C.c_int32(0), C.c_int32(0),
-              it.ctypes.data_as(C.c_void_p))
-            iters += int(it.sum()) * sum(1 for x in uniq if x == u)
-            # at-scale parity spot check: the GPU's results for the first tile of this unique pair
-            p0 = uniq.index(u)
-            got_st = status_host[p0 * n_feat:(p0 + 1) * n_feat]
-            got_uv = d_cur_uv[p0 * n_feat:(p0 + 1) * n_feat].cpu().numpy()
-            line.setdefault("parity_check", {"pairs": 0, "status_mismatch": 0, "position_bits_mismatch": 0})
-            line["parity_check"]["pairs"] += 1
-            line["parity_check"]["status_mismatch"] += int((got_st != st).sum())
-            line["parity_check"]["position_bits_mismatch"] += int((got_uv.view(np.uint32) != cu.view(np.uint32)).any(1).sum())
-        P = (2 * args.half + 1) ** 2
-        # SURVEY 8(d), basic hoisted form: per iteration 20*P flop, per feature-level setup ((2h+3)^2-4)*15 + 8*P flop
-        flops = iters * 20.0 * P + n_total * LEVELS * ((((2 * args.half + 3) ** 2) - 4) * 15.0 + 8.0 * P)
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        tfs = flops / (ms_klt / args.steps * 1e-3) / 1e12
-        traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["BasicInverseFastKernel"]
-            if args.variant == "basic" and args.method == "inverse" and args.half in (6, 7):
-                traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["features_per_launch"] * n_total  # ncu capture scaled to this launch
-        except Exception:
-            pass
-        line["roofline"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
-                            "frac": tfs / fp32_peak, "traffic": traffic,
-                            "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
-                            "algorithmic_flops_per_launch": flops, "patch_iterations_per_feature": iters / n_total,
-                            "kernel": "BasicInverseFastKernel<15,15>" if (args.variant, args.method, args.half) == ("basic", "inverse", 7) else "KltKernel"}
+        roofs, parity = head.rooflines(res, oracle)
+        # the dominant kernel of the step = the tracker kernel with the longest launch
+        dominant = max(roofs, key=lambda k: roofs[k]["launch_ms"])
+        line["roofline"] = roofs[dominant]
+        line["roofline_by_tracker"] = roofs
+        line["parity_check"] = parity
+        if north is not None:
+            nroofs, nparity = north.rooflines(north_res, oracle)
+            tr = None
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["BasicInverseFastKernel"]
+                tr = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["features_per_launch"] * n_total  # ncu capture scaled to this launch
+            except Exception:
+                pass
+            nroofs["basic_inverse"]["traffic"] = tr
+            dt, nf = cpu_track_sample(lib_cpu, cpu_params(WORKLOADS["north_star"], n_feat), refs, curs, uvs, sample_pairs, cores)
+            north_res["roofline"] = nroofs["basic_inverse"]
+            north_res["parity_check"] = nparity
+            north_res["cpu_baseline"] = {"value": nf / dt, "unit": UNIT, "cores": cores, "kind": kind, "sample": f"{sample_pairs} frame pairs x {n_feat} features"}
+    if north_res is not None:
+        north_res.pop("clocks", None)
+        north_res["config"] = "BASELINE north_star target: basic KLT kInverse 15x15, 4 levels, the same 1000 x 2000 batch; target >= 1e8 features/s/GPU"
+        north_res["unit"] = UNIT
+        line["north_star"] = north_res
     if not args.no_extras and world == 1:
         try:
             line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps)

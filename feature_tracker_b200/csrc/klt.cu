@@ -137,11 +137,17 @@ __device__ int ExtractExRefPatch(Ctx<G> &c, const Img &ref, float ref_x, float r
     const int min_row = static_cast<int>(int_row) - c.geo.er / 2;
     const int min_col = static_cast<int>(int_col) - c.geo.ec / 2;
     int valid = 0;
-    for (int base = 0; base < c.geo.esize; base += G) {
+    PatchWalk w;  // over the extended patch (two divisions per call instead of two per chunk)
+    w.pc = c.geo.ec;
+    w.row = c.g.lane / c.geo.ec;
+    w.col = c.g.lane - w.row * c.geo.ec;
+    w.step_row = G / c.geo.ec;
+    w.step_col = G - w.step_row * c.geo.ec;
+    for (int base = 0; base < c.geo.esize; base += G, w.next()) {
         const int e = base + c.g.lane;
         bool ok = false;
         if (e < c.geo.esize) {
-            const int row = min_row + e / c.geo.ec, col = min_col + e % c.geo.ec;
+            const int row = min_row + w.row, col = min_col + w.col;
             ok = !(row < 0 || row > ref.rows - 2 || col < 0 || col > ref.cols - 2);
             float v = 0.0f;
             if (ok) {
@@ -159,8 +165,7 @@ __device__ int ExtractExRefPatch(Ctx<G> &c, const Img &ref, float ref_x, float r
 
 // Gradient of the extended patch at interior pixel k (basic_klt_fast.cpp:71-94 and the affine / lssd twins).
 template <int G>
-__device__ __forceinline__ bool ExGradient(const Ctx<G> &c, int k, float *dx, float *dy) {
-    const int row = k / c.geo.pc, col = k % c.geo.pc;
+__device__ __forceinline__ bool ExGradient(const Ctx<G> &c, int row, int col, float *dx, float *dy) {
     const int e = (row + 1) * c.geo.ec + col + 1;
     const int l = e - 1, r = e + 1, u = e - c.geo.ec, d = e + c.geo.ec;
     if (c.s.exv[l] && c.s.exv[r] && c.s.exv[u] && c.s.exv[d]) {
@@ -294,12 +299,13 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
     }
     // gradients + Hessian (3 chains)
     c.ch.reset();
-    for (int base = 0; base < c.geo.psize; base += G) {
+    PatchWalk wg = c.walk;
+    for (int base = 0; base < c.geo.psize; base += G, wg.next()) {
         const int k = base + c.g.lane;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
         if (k < c.geo.psize) {
             float dx, dy;
-            if (ExGradient(c, k, &dx, &dy)) {
+            if (ExGradient(c, wg.row, wg.col, &dx, &dy)) {
                 t0 = fmul(dx, dx);
                 t1 = fmul(dx, dy);
                 t2 = fmul(dy, dy);
@@ -478,9 +484,8 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
     for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
         const int k = base + c.g.lane;
         float t[27];
-#pragma unroll
-        for (int q = 0; q < 27; ++q) t[q] = 0.0f;
         bool ok = false;
+        float tx = 0.0f, ty = 0.0f, tdx = 0.0f, tdy = 0.0f, tdt = 0.0f;  // invalid pixels: all 27 terms become +-0 (no-ops in the chains)
         if ((ref_bits >> chunk) & 1ull) {  // implies k < psize
             const float fdrow = static_cast<float>(w.row - c.geo.hr), fdcol = static_cast<float>(w.col - c.geo.hc);
             const float ax = fadd(fmul(s.a[0], fdcol), fmul(s.a[1], fdrow));
@@ -495,12 +500,10 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
                 ok = PxChecked(cur, row_j, col_j, &v5);
                 dx = hfx[k], dy = hfy[k];
             }
-            if (ok) {
-                const float dt = fsub(v5, hv4[k]);
-                AffineHessianTerms(col_j, row_j, dx, dy, t);
-                AffineBiasTerms(col_j, row_j, dx, dy, dt, &t[21]);
-            }
+            if (ok) tx = col_j, ty = row_j, tdx = dx, tdy = dy, tdt = fsub(v5, hv4[k]);
         }
+        AffineHessianTerms(tx, ty, tdx, tdy, t);
+        AffineBiasTerms(tx, ty, tdx, tdy, tdt, &t[21]);
 #pragma unroll
         for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
@@ -561,18 +564,18 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
     for (int base = 0; base < c.geo.psize; base += G) {
         const int k = base + c.g.lane;
         float t[27];
-#pragma unroll
-        for (int q = 0; q < 21; ++q) t[q] = 0.0f;
+        // Pixels without a gradient (or past the patch) run the same products on zeros: every term is then +0, and adding
+        // +0 leaves a chain unchanged -- no zero-fill, no divergent branch around the 21 products.
+        float dx = 0.0f, dy = 0.0f, x = 0.0f, y = 0.0f;
         if (k < c.geo.psize) {
-            float dx, dy;
-            if (ExGradient(c, k, &dx, &dy)) {
-                const float x = fadd(static_cast<float>(w.col - c.geo.hc), s.cur_x);
-                const float y = fadd(static_cast<float>(w.row - c.geo.hr), s.cur_y);
-                AffineHessianTerms(x, y, dx, dy, t);
+            if (ExGradient(c, w.row, w.col, &dx, &dy)) {
+                x = fadd(static_cast<float>(w.col - c.geo.hc), s.cur_x);
+                y = fadd(static_cast<float>(w.row - c.geo.hr), s.cur_y);
             }
             c.s.dx[k] = dx;
             c.s.dy[k] = dy;
         }
+        AffineHessianTerms(x, y, dx, dy, t);
 #pragma unroll
         for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
         c.ch.template fold<21>(c.g);
@@ -595,8 +598,9 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
         PatchWalk w = c.walk;
         for (int base = 0; base < c.geo.psize; base += G) {
             const int k = base + c.g.lane;
-            float t[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            float t[6];
             bool ok = false;
+            float bx = 0.0f, by = 0.0f, bdx = 0.0f, bdy = 0.0f, bdt = 0.0f;  // invalid pixels: products of zeros, i.e. -0 terms (no-ops)
             if (k < c.geo.psize) {
                 const int prow = w.row, pcol = w.col;
                 const int drow = prow - c.geo.hr, dcol = pcol - c.geo.hc;
@@ -607,10 +611,11 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
                 float cur_value;
                 ok = PxChecked(cur, row_c, col_c, &cur_value) && c.s.exv[e];
                 if (ok) {
-                    const float dt = fsub(cur_value, c.s.ex[e]);
-                    AffineBiasTerms(col_c, row_c, c.s.dx[k], c.s.dy[k], dt, t);
+                    bdt = fsub(cur_value, c.s.ex[e]);
+                    bx = col_c, by = row_c, bdx = c.s.dx[k], bdy = c.s.dy[k];
                 }
             }
+            AffineBiasTerms(bx, by, bdx, bdy, bdt, t);
 #pragma unroll
             for (int q = 0; q < 6; ++q) c.ch.put(c.g.lane, q, t[q]);
             valid += c.g.count(ok);
@@ -898,9 +903,10 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
         status = FTK_STATUS_OUTSIDE;
         return;
     }
-    for (int k = c.g.lane; k < c.geo.psize; k += G) {
+    PatchWalk wg = c.walk;
+    for (int k = c.g.lane; k < c.geo.psize; k += G, wg.next()) {
         float dx, dy;
-        ExGradient(c, k, &dx, &dy);
+        ExGradient(c, wg.row, wg.col, &dx, &dy);
         c.s.dx[k] = dx;
         c.s.dy[k] = dy;
     }
