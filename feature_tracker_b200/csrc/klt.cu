@@ -429,7 +429,7 @@ template <int G>
 __device__ __forceinline__ void AffineGatherHessian(const Ctx<G> &c, float (&H)[6][6]) {
 #pragma unroll
     for (int q = 0; q < 21; ++q) {
-        const float v = c.g.get(c.ch.acc, q);
+        const float v = c.ch.value(c.g, q);
         H[kAffRow[q]][kAffCol[q]] = v;
         H[kAffCol[q]][kAffRow[q]] = v;
     }
@@ -474,7 +474,7 @@ __device__ unsigned long long AffineHoistRef(Ctx<G> &c, const Img &ref, float re
 // affine_klt.cpp:131-273 ConstructIncrementalFunction: 21 Hessian + 6 bias chains, on top of the hoisted reference samples.
 template <int METHOD, int G>
 __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, unsigned long long ref_bits, float (&H)[6][6], float (&b)[6]) {
-    static_assert(G >= 27, "affine needs 27 chains");
+    static_assert(2 * G >= 27, "affine needs 27 chains, at most two per lane");
     const int pf = RoundUp(c.geo.psize, 4);
     const float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;
     int valid = 0;
@@ -507,12 +507,12 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
 #pragma unroll
         for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
-        c.ch.template fold<27>(c.g);
+        c.ch.template fold_wide<27>(c.g);
         w.next();
     }
     AffineGatherHessian(c, H);
 #pragma unroll
-    for (int q = 0; q < 6; ++q) b[q] = c.g.get(c.ch.acc, 21 + q);
+    for (int q = 0; q < 6; ++q) b[q] = c.ch.value(c.g, 21 + q);
     return valid;
 }
 
@@ -578,7 +578,7 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
         AffineHessianTerms(x, y, dx, dy, t);
 #pragma unroll
         for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
-        c.ch.template fold<21>(c.g);
+        c.ch.template fold_wide<21>(c.g);
         w.next();
     }
     float H[6][6];
@@ -1208,6 +1208,9 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_AFFINE:
+            // kDirect with 16 lanes per feature: two features share a warp's 6x6 LDLT instructions and 13x13 patches fill 11 chunks of
+            // 16 to 96 % (measured 47.4 ms vs 50.9 ms per 2 M features; kFast is slower that way, 49.4 ms vs 43.9 ms)
+            if (geo.psize <= 16 * 64 && a.p.method == kDirect) return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo);
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_LSSD:

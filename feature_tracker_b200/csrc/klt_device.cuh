@@ -142,8 +142,11 @@ template <int G>
 struct Chain {
     static constexpr int kStride = G + 4;
     float *term;
-    float acc;
-    __device__ __forceinline__ void reset() { acc = 0.0f; }
+    float acc;     // chain `lane`
+    float acc_hi;  // chain `G + lane` when a pass has more chains than the group has lanes (fold_wide)
+    __device__ __forceinline__ void reset() { acc = 0.0f, acc_hi = 0.0f; }
+    // value of chain q after the folds (any lane may ask)
+    __device__ __forceinline__ float value(const Group<G> &g, int q) const { return q < G ? g.get(acc, q) : g.get(acc_hi, q - G); }
     __device__ __forceinline__ void put(int lane, int k, float v) const { term[k * kStride + lane] = v; }
     // All lanes call; lanes >= K idle during the fold.
     template <int K>
@@ -161,6 +164,39 @@ struct Chain {
             }
         }
         g.sync();
+    }
+    // K chains with G < K <= 2 G: lanes fold chains 0..G-1, then lanes 0..K-G-1 fold chains G..K-1.
+    template <int K>
+    __device__ __forceinline__ void fold_wide(const Group<G> &g) {
+        if constexpr (K <= G) {
+            fold<K>(g);
+        } else {
+            static_assert(K <= 2 * G, "at most two chains per lane");
+            g.sync();
+            {
+                const float4 *t4 = reinterpret_cast<const float4 *>(term + g.lane * kStride);
+#pragma unroll
+                for (int q = 0; q < G / 4; ++q) {
+                    const float4 v = t4[q];
+                    acc = fadd(acc, v.x);
+                    acc = fadd(acc, v.y);
+                    acc = fadd(acc, v.z);
+                    acc = fadd(acc, v.w);
+                }
+            }
+            if (g.lane < K - G) {
+                const float4 *t4 = reinterpret_cast<const float4 *>(term + (G + g.lane) * kStride);
+#pragma unroll
+                for (int q = 0; q < G / 4; ++q) {
+                    const float4 v = t4[q];
+                    acc_hi = fadd(acc_hi, v.x);
+                    acc_hi = fadd(acc_hi, v.y);
+                    acc_hi = fadd(acc_hi, v.z);
+                    acc_hi = fadd(acc_hi, v.w);
+                }
+            }
+            g.sync();
+        }
     }
 };
 
