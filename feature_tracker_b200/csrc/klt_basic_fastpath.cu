@@ -86,7 +86,7 @@ __device__ __forceinline__ void SetupRows(const Img &ref, Smem &sm, const Lanes 
 #pragma unroll
         for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
     }
-#pragma unroll 1
+#pragma unroll 3
     for (int r = 0; r < PR; ++r) {
         const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
         float v0, v1, v2, v3, v4;
@@ -134,7 +134,7 @@ __device__ __forceinline__ void IterateRows(const Img &cur, Smem &sm, const Lane
         top0 = LoadPx(p);
         top1 = LoadPx(p + 1);
     }
-#pragma unroll 1
+#pragma unroll 15
     for (int r = 0; r < PR; ++r) {
         const Entry Rj = sm.rows[r];
         float v5;
@@ -335,7 +335,7 @@ __device__ __forceinline__ void RefCentreRows(const Img &ref, Smem &sm, const La
         top0 = LoadPx(p);
         top1 = LoadPx(p + 1);
     }
-#pragma unroll 1
+#pragma unroll 5
     for (int r = 0; r < PR; ++r) {
         const Entry R0 = sm.rows[r];
         float v;
@@ -370,7 +370,7 @@ __device__ __forceinline__ void DirectRows(const Img &cur, Smem &sm, const Lanes
 #pragma unroll
         for (int i = 0; i < 4; ++i) s2[i] = LoadPx(p + i);
     }
-#pragma unroll 1
+#pragma unroll 3
     for (int r = 0; r < PR; ++r) {
         const Entry R0 = sm.rows[3 * r], Rm = sm.rows[3 * r + 1], Rp = sm.rows[3 * r + 2];
         float v0, v1, v2, v3, v5;
@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(kThreads) BasicFastMethodKernel(KltLaunch a) {
                 const uint8_t *p = colp + Clamp(ex_row0, 0, ref.rows) * ref.pitch;
                 float top0 = LoadPx(p), top1 = LoadPx(p + 1);
                 float e_prev2 = 0.0f, e_prev1 = 0.0f;  // extended rows er - 2, er - 1 of my column
-#pragma unroll 1
+#pragma unroll 3
                 for (int er = 0; er < ER; ++er) {
                     p = colp + Clamp(ex_row0 + er + 1, 0, ref.rows) * ref.pitch;
                     const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kThreads) BasicFastMethodKernel(KltLaunch a) {
                 const uint8_t *p = colp + Clamp(row0, 0, cur.rows) * cur.pitch;
                 float top0 = LoadPx(p), top1 = LoadPx(p + 1);
                 acc = 0.0f;
-#pragma unroll 1
+#pragma unroll
                 for (int pr = 0; pr < PR; ++pr) {
                     p = colp + Clamp(row0 + pr + 1, 0, cur.rows) * cur.pitch;
                     const float bot0 = LoadPx(p), bot1 = LoadPx(p + 1);
