@@ -364,6 +364,7 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner out of stdout (the JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = ft.Context(local_rank)
     L = ftk_lib()
@@ -514,10 +515,18 @@ def run_b200(args):
                     same = (uv_host[sl].view(np.uint32) == cu.view(np.uint32)) | (np.isnan(uv_host[sl]) & np.isnan(cu))
                     parity["position_bits_mismatch"] += int((~same).any(1).sum())
                 flops, formula = algorithmic_flops(t, iters, n_total)
+                traffic = None
+                try:  # dram bytes of one ncu --set full capture of this kernel, scaled from its 200 000-feature launch to this launch
+                    key = {("basic", "inverse"): "BasicInverseFastKernel", ("affine", "direct"): "KltKernel_affine_direct",
+                           ("affine", "fast"): "KltKernel_affine_fast"}[(t[0], t[1])]
+                    tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[key]
+                    traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["features_per_launch"] * n_total
+                except Exception:
+                    pass
                 ms_k = res["kernel_ms"][f"klt_{t[0]}_{t[1]}"]
                 tfs = flops / (ms_k * 1e-3) / 1e12
                 out[f"{t[0]}_{t[1]}"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
-                                         "frac": tfs / fp32_peak, "traffic": None,
+                                         "frac": tfs / fp32_peak, "traffic": traffic,
                                          "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
                                          "algorithmic_flops_per_launch": flops, "algorithmic_flops_formula": formula,
                                          "patch_iterations_per_feature": iters / n_total, "launch_ms": ms_k,
@@ -603,13 +612,6 @@ def run_b200(args):
         line["parity_check"] = parity
         if north is not None:
             nroofs, nparity = north.rooflines(north_res, oracle)
-            tr = None
-            try:
-                t = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))["BasicInverseFastKernel"]
-                tr = (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["features_per_launch"] * n_total  # ncu capture scaled to this launch
-            except Exception:
-                pass
-            nroofs["basic_inverse"]["traffic"] = tr
             dt, nf = cpu_track_sample(lib_cpu, cpu_params(WORKLOADS["north_star"], n_feat), refs, curs, uvs, sample_pairs, cores)
             north_res["roofline"] = nroofs["basic_inverse"]
             north_res["parity_check"] = nparity
