@@ -177,3 +177,14 @@ def make_float_sets(n_ref, n_cur, dim=256, noise=0.2, seed=11):
     cur /= np.linalg.norm(cur, axis=1, keepdims=True)
     order = rng.permutation(n_cur)
     return ref, np.ascontiguousarray(cur[order])
+
+
+def make_direct_method_scene(rows, cols, n_features, pair_id, depth=5.0, focal=400.0, **kw):
+    """A frame pair for the direct-method pose tracker: the similarity-warped pair of make_pair() read as a camera moving in
+    front of a fronto-parallel plane at `depth` (translation ~ image shift * depth / focal, roll ~ image rotation).  Returns
+    (ref, cur, ref_uv, K = (fx, fy, cx, cy), p_c_in_ref [n, 3])."""
+    ref, cur, uv, _ = make_pair(rows, cols, n_features, pair_id, **kw)
+    K = np.array([focal, focal, cols / 2.0, rows / 2.0], np.float32)
+    z = np.full(uv.shape[0], depth, np.float32)
+    pts = np.stack([(uv[:, 0] - K[2]) / K[0] * z, (uv[:, 1] - K[3]) / K[1] * z, z], axis=1).astype(np.float32)
+    return ref, cur, uv, K, pts

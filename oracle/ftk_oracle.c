@@ -1129,3 +1129,137 @@ int ftko_mutual_scores(const float *scores, int32_t n_ref, int32_t n_cur, float 
     free(max_scores_in_cols_index);
     return 1;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Direct-method pose tracker: src/direct_method_tracker/direct_method_tracker.cpp.
+ * Quaternion / camera arithmetic is external (Eigen::Quaternionf, Sensor_Model CameraPinhole); its semantics are frozen in
+ * oracle/shim/basic_type.h (Quat) and oracle/shim/camera_pinhole.h and restated here.  q = (w, x, y, z).
+ * ---------------------------------------------------------------------------------------------------------- */
+static void quat_rotate(const float *q, const float *v, float *out) { /* Quat::operator*(Vec3) */
+    const float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+    float ux = qy * v[2] - qz * v[1], uy = qz * v[0] - qx * v[2], uz = qx * v[1] - qy * v[0];
+    ux = ux + ux, uy = uy + uy, uz = uz + uz;
+    out[0] = v[0] + qw * ux + (qy * uz - qz * uy);
+    out[1] = v[1] + qw * uy + (qz * ux - qx * uz);
+    out[2] = v[2] + qw * uz + (qx * uy - qy * ux);
+}
+static void quat_inverse(const float *q, float *out) {
+    const float n2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0];
+    if (n2 > 0.0f) out[0] = q[0] / n2, out[1] = -q[1] / n2, out[2] = -q[2] / n2, out[3] = -q[3] / n2;
+    else out[0] = out[1] = out[2] = out[3] = 0.0f;
+}
+static void quat_normalize(float *q) {
+    const float n = sqrtf(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0]);
+    q[0] = q[0] / n, q[1] = q[1] / n, q[2] = q[2] / n, q[3] = q[3] / n;
+}
+static void quat_mul(const float *a, const float *b, float *out) {
+    const float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    const float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    const float y = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+    const float z = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+    out[0] = w, out[1] = x, out[2] = y, out[3] = z;
+}
+
+#define FTKO_ZERO_FLOAT 1e-6f /* kZeroFloat, oracle/shim/basic_type.h */
+
+/* direct_method_tracker.cpp:115-192 TrackAllFeaturesDirect on one level. */
+static void direct_track_level(const ftko_direct_params *o, const image_t *ref, const image_t *cur, const float *K, int32_t n, const float *p_c_in_ref,
+                               const float *ref_uv, float *cur_uv, float *q_rc, float *p_rc) {
+    const float fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    for (uint32_t iter = 0; iter < o->max_iteration; ++iter) {
+        float H[36], b[6];
+        for (int k = 0; k < 36; ++k) H[k] = 0.0f;
+        for (int k = 0; k < 6; ++k) b[k] = 0.0f;
+        const uint32_t max_id = (uint32_t)n < o->max_track_points ? (uint32_t)n : o->max_track_points;
+        float q_inv[4];
+        quat_inverse(q_rc, q_inv);
+        for (uint32_t i = 0; i < max_id; ++i) {
+            const float *pr = &p_c_in_ref[3 * i];
+            if (pr[2] < FTKO_ZERO_FLOAT) continue; /* :129 */
+            const float x = pr[0], y = pr[1], z = pr[2];
+            const float z_inv = 1.0f / z;
+            const float z2_inv = z_inv * z_inv;
+            const float d[3] = {pr[0] - p_rc[0], pr[1] - p_rc[1], pr[2] - p_rc[2]};
+            float pc[3];
+            quat_rotate(q_inv, d, pc); /* :139 */
+            if (pc[2] < FTKO_ZERO_FLOAT) continue; /* :140 */
+            const float nx = pc[0] / pc[2], ny = pc[1] / pc[2]; /* :142 */
+            cur_uv[2 * i] = fx * nx + cx;                       /* :143 */
+            cur_uv[2 * i + 1] = fy * ny + cy;
+            /* :146-150, row-major 2x6; every product chain runs left to right */
+            const float J[12] = {fx * z_inv, 0.0f, -fx * x * z2_inv, -fx * x * y * z2_inv, fx + fx * x * x * z2_inv, -fx * y * z_inv,
+                                 0.0f, fy * z_inv, -fy * y * z2_inv, -fy - fy * y * y * z2_inv, fy * x * y * z2_inv, fy * x * z_inv};
+            for (int32_t drow = -o->patch_row_half; drow <= o->patch_row_half; ++drow) {
+                for (int32_t dcol = -o->patch_col_half; dcol <= o->patch_col_half; ++dcol) {
+                    const float row_i = (float)drow + ref_uv[2 * i + 1], col_i = (float)dcol + ref_uv[2 * i];
+                    const float row_j = (float)drow + cur_uv[2 * i + 1], col_j = (float)dcol + cur_uv[2 * i];
+                    float t[6];
+                    if (px_checked(cur, row_j, col_j - 1.0f, &t[0]) && px_checked(cur, row_j, col_j + 1.0f, &t[1]) &&
+                        px_checked(cur, row_j - 1.0f, col_j, &t[2]) && px_checked(cur, row_j + 1.0f, col_j, &t[3]) &&
+                        px_checked(ref, row_i, col_i, &t[4]) && px_checked(cur, row_j, col_j, &t[5])) {
+                        const float gx = (t[1] - t[0]) * 0.5f, gy = (t[3] - t[2]) * 0.5f; /* :165 */
+                        const float residual = t[5] - t[4];
+                        float jac[6];
+                        for (int k = 0; k < 6; ++k) jac[k] = gx * J[k] + gy * J[6 + k]; /* :169 */
+                        for (int r = 0; r < 6; ++r)
+                            for (int c = 0; c < 6; ++c) H[6 * r + c] = H[6 * r + c] + jac[r] * jac[c]; /* :170 */
+                        for (int k = 0; k < 6; ++k) b[k] = b[k] + residual * jac[k];                  /* :171 */
+                    }
+                }
+            }
+        }
+        float dx[6];
+        ldlt_solve(6, H, b, dx); /* :178 */
+        int any_nan = 0;
+        for (int k = 0; k < 6; ++k) any_nan = any_nan || isnan(dx[k]);
+        if (any_nan) break;
+        p_rc[0] = p_rc[0] + dx[0], p_rc[1] = p_rc[1] + dx[1], p_rc[2] = p_rc[2] + dx[2]; /* :182 */
+        float dq[4] = {1.0f, dx[3] * 0.5f, dx[4] * 0.5f, dx[5] * 0.5f}, qn[4];
+        quat_normalize(dq);
+        quat_mul(dq, q_rc, qn); /* :183 */
+        q_rc[0] = qn[0], q_rc[1] = qn[1], q_rc[2] = qn[2], q_rc[3] = qn[3];
+        quat_normalize(q_rc); /* :184 */
+        float sq = dx[0] * dx[0];
+        for (int k = 1; k < 6; ++k) sq = sq + dx[k] * dx[k];
+        if (sq < o->max_converge_step) break; /* :187 */
+    }
+}
+
+/* direct_method_tracker.cpp:41-95 TrackFeatures (camera-frame overload). */
+int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                             const int32_t *rows, const int32_t *cols, const float *K, int32_t n, const float *p_c_in_ref, const float *ref_uv,
+                             float *cur_uv, int32_t cur_uv_count, float *q_rc, float *p_rc, uint8_t *status, int32_t status_count) {
+    if (n <= 0) return 0;                    /* :44 */
+    if (levels < 1 || levels > 16) return 0; /* :45 equal depth is implied by the shared `levels` */
+    if (cur_uv_count != n) memcpy(cur_uv, ref_uv, sizeof(float) * 2 * (size_t)n); /* :48-50 */
+    image_t ref_pyr[16], cur_pyr[16];
+    uint8_t *store[32];
+    for (int32_t l = 0; l < levels; ++l) {
+        const size_t npx = (size_t)rows[l] * cols[l];
+        store[2 * l] = (uint8_t *)calloc(npx + cols[l] + 2, 1);
+        store[2 * l + 1] = (uint8_t *)calloc(npx + cols[l] + 2, 1);
+        memcpy(store[2 * l], ref_levels[l], npx);
+        memcpy(store[2 * l + 1], cur_levels[l], npx);
+        ref_pyr[l].d = store[2 * l], ref_pyr[l].rows = rows[l], ref_pyr[l].cols = cols[l];
+        cur_pyr[l].d = store[2 * l + 1], cur_pyr[l].rows = rows[l], cur_pyr[l].cols = cols[l];
+    }
+    const float scale = (float)(1 << (levels - 1));
+    float *scaled_ref = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+    for (int32_t i = 0; i < 2 * n; ++i) scaled_ref[i] = ref_uv[i] / scale; /* :56-58 */
+    float sK[4] = {K[0] / scale, K[1] / scale, K[2] / scale, K[3] / scale};
+    for (int32_t l = levels - 1; l > -1; --l) {
+        if (params->method == 1) direct_track_level(params, &ref_pyr[l], &cur_pyr[l], sK, n, p_c_in_ref, scaled_ref, cur_uv, q_rc, p_rc);
+        /* kInverse (:107-113) and kFast (:194-199) are empty upstream: they return true without touching anything */
+        if (l == 0) break;
+        for (int32_t i = 0; i < 2 * n; ++i) scaled_ref[i] = scaled_ref[i] * 2.0f;
+        for (int k = 0; k < 4; ++k) sK[k] = sK[k] * 2.0f;
+    }
+    if (status_count != n) memset(status, ST_TRACKED, (size_t)n); /* :82-84 */
+    for (int32_t i = 0; i < n; ++i) {                             /* :86-91 (bounds of the REFERENCE pyramid's level 0) */
+        if (cur_uv[2 * i] < 0 || cur_uv[2 * i] > (float)(cols[0] - 1) || cur_uv[2 * i + 1] < 0 || cur_uv[2 * i + 1] > (float)(rows[0] - 1))
+            status[i] = ST_OUTSIDE;
+    }
+    free(scaled_ref);
+    for (int32_t l = 0; l < 2 * levels; ++l) free(store[l]);
+    return 1;
+}

@@ -56,6 +56,11 @@ int ftko_match_brief_force_uv(const uint8_t *ref_bits, int32_t n_ref, const uint
 /* nn_feature_matcher.cpp:180-216: mutual row / column arg-max of a score matrix (restatement only; needs no network). */
 int ftko_mutual_scores(const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx);
 
+/* direct_method_tracker.cpp:41-95 (camera-frame TrackFeatures) + :115-192.  q_rc = (w, x, y, z), in/out like p_rc. */
+int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                             const int32_t *rows, const int32_t *cols, const float *K, int32_t n, const float *p_c_in_ref, const float *ref_uv,
+                             float *cur_uv, int32_t cur_uv_count, float *q_rc, float *p_rc, uint8_t *status, int32_t status_count);
+
 void ftko_ldlt_solve(int32_t n, const float *a, const float *b, float *x);
 
 #ifdef __cplusplus

@@ -23,4 +23,15 @@ typedef struct ftko_klt_params {
     int32_t consider_patch_luminance;  /* lssd fast only */
 } ftko_klt_params;
 
+/* DirectMethodOptions (src/direct_method_tracker/direct_method_tracker.h:20-28); same layout as ftk_direct_params. */
+typedef struct ftko_direct_params {
+    uint32_t max_track_points;   /* kMaxTrackPointsNumber = 500 */
+    uint32_t max_iteration;      /* kMaxIteration = 15 */
+    int32_t patch_row_half;      /* kPatchRowHalfSize = 6 */
+    int32_t patch_col_half;      /* kPatchColHalfSize = 6 */
+    float max_converge_step;     /* kMaxConvergeStep = 1e-6 (on the squared step) */
+    float max_converge_residual; /* kMaxConvergeResidual = 2.0 (unused by the reference) */
+    int32_t method;              /* DirectMethodMethod: 0 kInverse, 1 kDirect (default), 2 kFast; only kDirect does work upstream */
+} ftko_direct_params;
+
 #endif

@@ -38,6 +38,32 @@ class KltParams(C.Structure):
     ]
 
 
+class DirectParams(C.Structure):
+    """ftko_direct_params == DirectMethodOptions (src/direct_method_tracker/direct_method_tracker.h:20-28)."""
+
+    _fields_ = [
+        ("max_track_points", C.c_uint32),
+        ("max_iteration", C.c_uint32),
+        ("patch_row_half", C.c_int32),
+        ("patch_col_half", C.c_int32),
+        ("max_converge_step", C.c_float),
+        ("max_converge_residual", C.c_float),
+        ("method", C.c_int32),
+    ]
+
+
+def make_direct_params(half=6, half_col=None, max_points=500, max_iter=15, converge=1e-6, method="direct"):
+    p = DirectParams()
+    p.max_track_points = max_points
+    p.max_iteration = max_iter
+    p.patch_row_half = half
+    p.patch_col_half = half if half_col is None else half_col
+    p.max_converge_step = converge
+    p.max_converge_residual = 2.0
+    p.method = {"inverse": 0, "direct": 1, "fast": 2}[method]
+    return p
+
+
 def make_params(variant="basic", method="fast", half=6, half_col=None, max_points=500, max_iter=15, max_large=3,
                 converge=4e-2, predict=(1.0, 0.0, 0.0, 1.0), luminance=False):
     """Defaults are the reference's OpticalFlowOptions defaults (optical_flow.h:20-28)."""
@@ -152,6 +178,42 @@ class _CpuChecker:
                                     _f32p(cur_buf), C.c_int32(cur_count), _u8p(st_buf), C.c_int32(st_count),
                                     C.c_int32(1 if single_level else 0))
         return ok == 1, cur_buf[:n].copy(), st_buf[:n].copy()
+
+    def direct_method_track(self, params, ref_levels, cur_levels, K, p_c_in_ref, ref_uv, q_rc, p_rc, cur_uv=None, status=None):
+        """DirectMethod::TrackFeatures, camera-frame overload (direct_method_tracker.cpp:41-95).  q_rc = (w, x, y, z).
+        Returns (ok, cur_uv, q_rc, p_rc, status)."""
+        levels = len(ref_levels)
+        ref_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in ref_levels]
+        cur_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in cur_levels]
+        rows = np.array([a.shape[0] for a in ref_levels], dtype=np.int32)
+        cols = np.array([a.shape[1] for a in ref_levels], dtype=np.int32)
+        PtrArr = C.POINTER(C.c_uint8) * levels
+        rp = PtrArr(*[_u8p(a) for a in ref_levels])
+        cp = PtrArr(*[_u8p(a) for a in cur_levels])
+        ref_uv = np.ascontiguousarray(ref_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        pts = np.ascontiguousarray(p_c_in_ref, dtype=np.float32).reshape(-1, 3)
+        assert pts.shape[0] == n
+        Kc = np.ascontiguousarray(K, dtype=np.float32).reshape(4)
+        q = np.ascontiguousarray(q_rc, dtype=np.float32).reshape(4).copy()
+        p = np.ascontiguousarray(p_rc, dtype=np.float32).reshape(3).copy()
+        if cur_uv is None:
+            cur_buf, cur_count = np.zeros((max(n, 1), 2), np.float32), 0
+        else:
+            cur_in = np.ascontiguousarray(cur_uv, dtype=np.float32).reshape(-1, 2)
+            cur_count = cur_in.shape[0]
+            cur_buf = np.zeros((max(n, cur_count, 1), 2), np.float32)
+            cur_buf[:cur_count] = cur_in
+        if status is None:
+            st_buf, st_count = np.zeros(max(n, 1), np.uint8), 0
+        else:
+            st_in = np.ascontiguousarray(status, dtype=np.uint8).reshape(-1)
+            st_count = st_in.shape[0]
+            st_buf = np.zeros(max(n, st_count, 1), np.uint8)
+            st_buf[:st_count] = st_in
+        ok = self._fn("direct_method_track")(C.byref(params), C.c_int32(levels), rp, cp, _i32p(rows), _i32p(cols), _f32p(Kc), C.c_int32(n), _f32p(pts),
+                                              _f32p(ref_uv), _f32p(cur_buf), C.c_int32(cur_count), _f32p(q), _f32p(p), _u8p(st_buf), C.c_int32(st_count))
+        return ok == 1, cur_buf[:n].copy(), q, p, st_buf[:n].copy()
 
     def pyramid_and_track(self, params, levels, ref_image, cur_image, ref_uv):
         ref_image = np.ascontiguousarray(ref_image, dtype=np.uint8)

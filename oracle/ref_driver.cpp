@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "descriptor_matcher.h"
+#include "direct_method_tracker.h"
 #include "optical_flow_affine_klt.h"
 #include "optical_flow_basic_klt.h"
 #include "optical_flow_lssd_klt.h"
@@ -115,6 +116,7 @@ std::vector<Vec2> WrapUv(const float *uv, int32_t n) {
 }
 
 }  // namespace
+
 
 extern "C" {
 
@@ -264,6 +266,45 @@ int ftkref_match_brief_force_uv(const uint8_t *ref_bits, int32_t n_ref, const ui
         matched_uv[2 * i + 1] = matched[i].y();
         status[i] = st[i];
     }
+    return 1;
+}
+
+// DirectMethod::TrackFeatures, camera-frame overload (direct_method_tracker.cpp:41-95).  p_c_in_ref: n x 3; q_rc = (w, x, y, z)
+// and p_rc in/out; cur_uv_count / status_count = the sizes of the caller's vectors on entry.
+int ftkref_direct_method_track(const ftko_direct_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                               const int32_t *rows, const int32_t *cols, const float *K, int32_t n, const float *p_c_in_ref, const float *ref_uv,
+                               float *cur_uv, int32_t cur_uv_count, float *q_rc, float *p_rc, uint8_t *status, int32_t status_count) {
+    feature_tracker::DirectMethod solver;
+    solver.options().kMaxTrackPointsNumber = params->max_track_points;
+    solver.options().kMaxIteration = params->max_iteration;
+    solver.options().kPatchRowHalfSize = params->patch_row_half;
+    solver.options().kPatchColHalfSize = params->patch_col_half;
+    solver.options().kMaxConvergeStep = params->max_converge_step;
+    solver.options().kMaxConvergeResidual = params->max_converge_residual;
+    solver.options().kMethod = static_cast<feature_tracker::DirectMethodMethod>(params->method);
+    PaddedLevels ref_store, cur_store;
+    ref_store.Adopt(levels, ref_levels, rows, cols);
+    cur_store.Adopt(levels, cur_levels, rows, cols);
+    ImagePyramid ref_pyr, cur_pyr;
+    ref_pyr.SetLevels(levels, ref_store.ptr.data(), rows, cols);
+    cur_pyr.SetLevels(levels, cur_store.ptr.data(), rows, cols);
+    std::vector<Vec2> ref_vec = WrapUv(ref_uv, n);
+    std::vector<Vec2> cur_vec = WrapUv(cur_uv, cur_uv_count);
+    std::vector<uint8_t> status_vec(status, status + status_count);
+    std::vector<Vec3> points(n);
+    for (int32_t i = 0; i < n; ++i) points[i] << p_c_in_ref[3 * i], p_c_in_ref[3 * i + 1], p_c_in_ref[3 * i + 2];
+    const std::array<float, 4> Kc = {K[0], K[1], K[2], K[3]};
+    Quat q(q_rc[0], q_rc[1], q_rc[2], q_rc[3]);
+    Vec3 p;
+    p << p_rc[0], p_rc[1], p_rc[2];
+    if (!solver.TrackFeatures(ref_pyr, cur_pyr, Kc, points, ref_vec, cur_vec, q, p, status_vec)) return 0;
+    for (int32_t i = 0; i < n; ++i) {
+        cur_uv[2 * i] = cur_vec[i].x();
+        cur_uv[2 * i + 1] = cur_vec[i].y();
+        status[i] = status_vec[i];
+    }
+    q_rc[0] = q.w(), q_rc[1] = q.x(), q_rc[2] = q.y(), q_rc[3] = q.z();
+    p_rc[0] = p(0), p_rc[1] = p(1), p_rc[2] = p(2);
     return 1;
 }
 

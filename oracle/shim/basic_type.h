@@ -118,6 +118,8 @@ struct Mat {
     const float &x() const { return (&d[0][0])[0]; }
     float &y() { return (&d[0][0])[1]; }
     const float &y() const { return (&d[0][0])[1]; }
+    float &z() { return (&d[0][0])[2]; }
+    const float &z() const { return (&d[0][0])[2]; }
 
     Mat operator+(const Mat &o) const {
         Mat r;
@@ -324,6 +326,58 @@ Ldlt<R> Mat<R, C>::ldlt() const {
     return Ldlt<R>(*this);
 }
 
+// scalar * matrix (direct_method_tracker.cpp:176 `residual * jacobian`): each coefficient s * m(i,j).
+template <int R, int C>
+inline Mat<R, C> operator*(float s, const Mat<R, C> &m) {
+    Mat<R, C> r;
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < C; ++j) r.d[i][j] = s * m.d[i][j];
+    return r;
+}
+
+// Stand-in for Eigen::Quaternionf (direct_method_tracker.cpp only).  Restates Eigen 3.3/3.4's scalar code paths:
+//   product            quat_product<..., false>::run
+//   quat * vec3        QuaternionBase::_transformVector: uv = vec x v; uv += uv; v + w * uv + vec x uv
+//   inverse            conjugate / squaredNorm (a zero quaternion stays zero)
+//   normalize(d)       coeffs / norm, norm = sqrt(x*x + y*y + z*z + w*w) summed in coefficient order (x, y, z, w)
+// Sums run left to right as everywhere in this shim.
+struct Quat {
+    float qw, qx, qy, qz;
+    Quat() {}
+    Quat(float w, float x, float y, float z) : qw(w), qx(x), qy(y), qz(z) {}
+    static Quat Identity() { return Quat(1.0f, 0.0f, 0.0f, 0.0f); }
+    float w() const { return qw; }
+    float x() const { return qx; }
+    float y() const { return qy; }
+    float z() const { return qz; }
+    float squaredNorm() const { return qx * qx + qy * qy + qz * qz + qw * qw; }
+    float norm() const { return std::sqrt(squaredNorm()); }
+    Quat inverse() const {
+        const float n2 = squaredNorm();
+        if (n2 > 0.0f) return Quat(qw / n2, -qx / n2, -qy / n2, -qz / n2);
+        return Quat(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    Quat normalized() const {
+        const float n = norm();
+        return Quat(qw / n, qx / n, qy / n, qz / n);
+    }
+    void normalize() { *this = normalized(); }
+    Quat operator*(const Quat &b) const {
+        return Quat(qw * b.qw - qx * b.qx - qy * b.qy - qz * b.qz, qw * b.qx + qx * b.qw + qy * b.qz - qz * b.qy,
+                    qw * b.qy + qy * b.qw + qz * b.qx - qx * b.qz, qw * b.qz + qz * b.qw + qx * b.qy - qy * b.qx);
+    }
+    Mat<3, 1> operator*(const Mat<3, 1> &v) const {
+        const float vx = v.d[0][0], vy = v.d[1][0], vz = v.d[2][0];
+        float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;  // vec x v
+        ux = ux + ux, uy = uy + uy, uz = uz + uz;
+        Mat<3, 1> r;
+        r.d[0][0] = vx + qw * ux + (qy * uz - qz * uy);
+        r.d[1][0] = vy + qw * uy + (qz * ux - qx * uz);
+        r.d[2][0] = vz + qw * uz + (qx * uy - qy * ux);
+        return r;
+    }
+};
+
 // Dynamic int matrix (only setConstant + element access are used, lssd_klt.cpp:136-137).
 struct MatIntDyn {
     std::vector<int32_t> v;
@@ -359,6 +413,10 @@ using Mat6 = shim::Mat<6, 6>;
 using Mat2x3 = shim::Mat<2, 3>;
 using Mat1x2 = shim::Mat<1, 2>;
 using Mat1x3 = shim::Mat<1, 3>;
+using Mat2x6 = shim::Mat<2, 6>;
+using Quat = shim::Quat;
+// Slam_Utility's "treat as zero" threshold (direct_method_tracker.cpp:129,140 depth tests).  Frozen here, like the rest of the shim.
+constexpr float kZeroFloat = 1e-6f;
 using MatInt = shim::MatIntDyn;
 
 #endif

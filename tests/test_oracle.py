@@ -218,3 +218,34 @@ def test_mutual_scores_restatement(oracle):
             assert np.array_equal(idx, _mutual_scores_python(s, np.float32(-3.0)))
     ok, _ = oracle.mutual_scores(np.zeros((3, 0), np.float32), -3.0)
     assert not ok
+
+
+@pytest.mark.parametrize("levels,half,max_points", [(4, 6, 500), (3, 4, 40), (1, 7, 500), (5, 6, 25)])
+def test_direct_method_restatement_vs_reference_build(oracle, reflib, levels, half, max_points):
+    """SURVEY 8(f) rank 3: the C restatement of DirectMethod::TrackFeatures equals the reference's own
+    direct_method_tracker.cpp compiled in place, bit for bit (pose, projected positions, status)."""
+    from feature_tracker_b200 import synthetic as S
+    ref, cur, uv, K, pts = S.make_direct_method_scene(240, 320, 60, pair_id=40 + levels, border=10)
+    pts = pts.copy()
+    pts[3, 2] = -1.0     # behind the reference camera: skipped (:129)
+    pts[7, 2] = 1e-7     # below kZeroFloat
+    pts[11] = (50.0, 0.0, 1.0)  # projects far outside the image: status kOutside, contributes nothing
+    rl, cl = oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels)
+    q0 = np.array([0.9999, 0.002, -0.003, 0.004], np.float32)
+    p0 = np.array([0.01, -0.02, 0.005], np.float32)
+    for method in ("direct", "inverse", "fast"):
+        prm = po.make_direct_params(half=half, max_points=max_points, method=method)
+        for kwargs in ({}, {"cur_uv": uv + 0.5, "status": np.full(60, 2, np.uint8)}):
+            a = oracle.direct_method_track(prm, rl, cl, K, pts, uv, q0, p0, **kwargs)
+            b = reflib.direct_method_track(prm, rl, cl, K, pts, uv, q0, p0, **kwargs)
+            assert a[0] and b[0]
+            for x, y, name in zip(a[1:], b[1:], ("cur_uv", "q_rc", "p_rc", "status")):
+                if x.dtype == np.uint8:
+                    assert np.array_equal(x, y), (method, name)
+                else:
+                    assert bits_equal(x, y), (method, name, x[:4], y[:4])
+    # the pose actually moved and most projections stay inside
+    prm = po.make_direct_params(half=half, max_points=max_points)
+    ok, cur_uv, q, p, st = oracle.direct_method_track(prm, rl, cl, K, pts, uv, [1, 0, 0, 0], [0, 0, 0])
+    assert ok and (st == 1).sum() > 40 and np.abs(p).max() > 1e-3
+    assert not oracle.direct_method_track(prm, rl, cl, K, np.zeros((0, 3)), np.zeros((0, 2)), [1, 0, 0, 0], [0, 0, 0])[0]
