@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
     "ftk_track_image_pairs", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
-    "ftk_match_mutual_scores", "ftk_match_cross_check",
+    "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track",
 ]
 
 
@@ -49,6 +49,20 @@ class KltParams(C.Structure):
         ("predict", C.c_float * 4),
         ("consider_patch_luminance", C.c_int32),
         ("forward_backward_max_error", C.c_float),
+    ]
+
+
+class DirectParams(C.Structure):
+    """ftk_direct_params (include/ftk_c.h) == DirectMethodOptions of the reference."""
+
+    _fields_ = [
+        ("max_track_points", C.c_uint32),
+        ("max_iteration", C.c_uint32),
+        ("patch_row_half", C.c_int32),
+        ("patch_col_half", C.c_int32),
+        ("max_converge_step", C.c_float),
+        ("max_converge_residual", C.c_float),
+        ("method", C.c_int32),
     ]
 
 
@@ -83,6 +97,8 @@ def load_library():
         "ftk_match_hamming_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_direct_params_default": (None, [P(DirectParams)]),
+        "ftk_direct_method_track": (C.c_int, [vp, P(DirectParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]),
         "ftk_match_mutual_scores": (C.c_int, [vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cross_check": (C.c_int, [vp, vp, i32, vp, i32, u32]),
         "ftk_fill_matched": (C.c_int, [vp, i32, vp, i32, vp, vp, i32]),

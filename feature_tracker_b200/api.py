@@ -528,3 +528,87 @@ class NNFeatureMatcher:
             matched[good] = cur[idx[good]]
             status[good] = 1
         return ok, matched, status
+
+
+class DirectMethodMethod:
+    """direct_method_tracker.h:14-18"""
+    kInverse = 0
+    kDirect = 1
+    kFast = 2
+
+
+class DirectMethodOptions:
+    """direct_method_tracker.h:20-28"""
+
+    def __init__(self):
+        self.kMaxTrackPointsNumber = 500
+        self.kMaxIteration = 15
+        self.kPatchRowHalfSize = 6
+        self.kPatchColHalfSize = 6
+        self.kMaxConvergeStep = 1e-6
+        self.kMaxConvergeResidual = 2.0
+        self.kMethod = DirectMethodMethod.kDirect
+
+
+class DirectMethod:
+    """DirectMethod (src/direct_method_tracker/direct_method_tracker.h:30-77): one 6-DoF pose of the current frame relative to the
+    reference frame from all features of a frame pair.  Quaternions are (w, x, y, z)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = DirectMethodOptions()
+
+    def options(self):
+        return self._options
+
+    def _params(self):
+        o = self._options
+        p = _capi.DirectParams()
+        p.max_track_points = int(o.kMaxTrackPointsNumber)
+        p.max_iteration = int(o.kMaxIteration)
+        p.patch_row_half = int(o.kPatchRowHalfSize)
+        p.patch_col_half = int(o.kPatchColHalfSize)
+        p.max_converge_step = float(o.kMaxConvergeStep)
+        p.max_converge_residual = float(o.kMaxConvergeResidual)
+        p.method = int(o.kMethod)
+        return p
+
+    def TrackFeaturesBatch(self, ref_pyramid, cur_pyramid, feat_offsets, K, p_c_in_ref, ref_pixel_uv, q_rc, p_rc, cur_pixel_uv=None, status=None,
+                           ref_image=None, cur_image=None):
+        """n_pairs independent problems in one call (ftk_direct_method_track).  K [n_pairs, 4], q_rc [n_pairs, 4], p_rc [n_pairs, 3].
+        Returns (ok, cur_pixel_uv, q_rc, p_rc, status)."""
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        feat_offsets = np.ascontiguousarray(feat_offsets, dtype=np.int32)
+        n_pairs = feat_offsets.shape[0] - 1
+        pts = np.ascontiguousarray(p_c_in_ref, dtype=np.float32).reshape(-1, 3)
+        Kc = np.ascontiguousarray(K, dtype=np.float32).reshape(n_pairs, 4)
+        q = np.ascontiguousarray(q_rc, dtype=np.float32).reshape(n_pairs, 4).copy()
+        p = np.ascontiguousarray(p_rc, dtype=np.float32).reshape(n_pairs, 3).copy()
+        flags = 0
+        cur = np.zeros((max(n, 1), 2), np.float32)
+        if cur_pixel_uv is not None and np.asarray(cur_pixel_uv).reshape(-1, 2).shape[0] == n and n > 0:
+            cur[:n] = np.asarray(cur_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        else:
+            flags |= _capi.FLAG_NO_PREDICTION
+        st = np.zeros(max(n, 1), np.uint8)
+        if status is not None and np.asarray(status).reshape(-1).shape[0] == n and n > 0:
+            st[:n] = np.asarray(status, dtype=np.uint8).reshape(-1)
+        else:
+            flags |= _capi.FLAG_NO_STATUS
+        ri = None if ref_image is None else np.ascontiguousarray(ref_image, dtype=np.int32)
+        ci = None if cur_image is None else np.ascontiguousarray(cur_image, dtype=np.int32)
+        prm = self._params()
+        rc = lib().ftk_direct_method_track(self.ctx._h, C.byref(prm), ref_pyramid._h, cur_pyramid._h, n_pairs, _ptr(ri), _ptr(ci), _ptr(feat_offsets),
+                                           _ptr(Kc), _ptr(pts), _ptr(ref_uv), _ptr(cur), _ptr(q), _ptr(p), _ptr(st), flags)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT, _capi.ERR_LEVEL_MISMATCH))
+        return ok, cur[:n], q, p, st[:n]
+
+    def TrackFeatures(self, ref_pyramid, cur_pyramid, K, p_c_in_ref, ref_pixel_uv, q_rc, p_rc, cur_pixel_uv=None, status=None, ref_image=0,
+                      cur_image=0):
+        """direct_method_tracker.cpp:41-95 (camera-frame overload) for one frame pair."""
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        ok, cur, q, p, st = self.TrackFeaturesBatch(ref_pyramid, cur_pyramid, np.array([0, ref_uv.shape[0]], np.int32), np.asarray(K).reshape(1, 4),
+                                                    p_c_in_ref, ref_uv, np.asarray(q_rc).reshape(1, 4), np.asarray(p_rc).reshape(1, 3), cur_pixel_uv,
+                                                    status, np.array([ref_image], np.int32), np.array([cur_image], np.int32))
+        return ok, cur, q[0], p[0], st

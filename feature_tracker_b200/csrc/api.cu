@@ -96,6 +96,17 @@ void ftk_klt_params_default(ftk_klt_params *p) {
     p->forward_backward_max_error = 0.0f;
 }
 
+void ftk_direct_params_default(ftk_direct_params *p) {
+    if (!p) return;
+    p->max_track_points = 500;  // direct_method_tracker.h:20-28
+    p->max_iteration = 15;
+    p->patch_row_half = 6;
+    p->patch_col_half = 6;
+    p->max_converge_step = 1e-6f;
+    p->max_converge_residual = 2.0f;
+    p->method = FTK_DIRECT_METHOD_DIRECT;
+}
+
 int ftk_create(int device, ftk_context **out) {
     if (!out) return FTK_ERR_INVALID_ARGUMENT;
     *out = nullptr;
@@ -128,7 +139,7 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < 2; ++b) {
@@ -563,6 +574,78 @@ int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_re
     if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
     if (int rc = ftk::LaunchHammingNearby(ctx, d_ref, n_ref, d_cur, n_cur, words, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t n_pairs,
+                            const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *K, const float *p_c_in_ref,
+                            const float *ref_uv, float *cur_uv, float *q_rc, float *p_rc, uint8_t *status, uint32_t flags) {
+    if (!ctx || !params || !ref || !cur || !feat_offsets || !K || !p_c_in_ref || !ref_uv || !cur_uv || !q_rc || !p_rc || !status)
+        return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
+    if (ref->view.levels != cur->view.levels)  // direct_method_tracker.cpp:45
+        return SetError(ctx, FTK_ERR_LEVEL_MISMATCH, "ref has %d levels, cur has %d", ref->view.levels, cur->view.levels);
+    if (ref->view.rows[0] != cur->view.rows[0] || ref->view.cols[0] != cur->view.cols[0])
+        return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "ref and cur pyramids differ in image size");
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    std::vector<int32_t> h_offsets(n_pairs + 1);
+    if (on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_offsets.data(), feat_offsets, sizeof(int32_t) * (n_pairs + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(h_offsets.data(), feat_offsets, sizeof(int32_t) * (n_pairs + 1));
+    }
+    if (h_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
+    for (int p = 0; p < n_pairs; ++p) {
+        if (h_offsets[p + 1] < h_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
+        if (h_offsets[p + 1] == h_offsets[p]) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "pair %d has no features", p);  // :44
+        if (!on_device) {
+            const int ri = ref_image ? ref_image[p] : p, ci = cur_image ? cur_image[p] : p;
+            if (ri < 0 || ri >= ref->view.n_images || ci < 0 || ci >= cur->view.n_images)
+                return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pair %d references image %d/%d outside the pyramid batches", p, ri, ci);
+        }
+    }
+    const int n = h_offsets[n_pairs];
+    const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);
+    const int32_t *d_offsets = nullptr, *d_ri = nullptr, *d_ci = nullptr;
+    const float *d_K = nullptr, *d_points = nullptr;
+    const float2 *d_ref_uv = nullptr;
+    float2 *d_cur_uv = reinterpret_cast<float2 *>(cur_uv);
+    float *d_q = q_rc, *d_p = p_rc;
+    uint8_t *d_status = status;
+    if (int rc = Stage(ctx, ctx->d_offsets, feat_offsets, n_pairs + 1, on_device, &d_offsets)) return rc;
+    if (ref_image)
+        if (int rc = Stage(ctx, ctx->d_ref_img, ref_image, n_pairs, on_device, &d_ri)) return rc;
+    if (cur_image)
+        if (int rc = Stage(ctx, ctx->d_cur_img, cur_image, n_pairs, on_device, &d_ci)) return rc;
+    if (int rc = Stage(ctx, ctx->d_dm_K, K, static_cast<size_t>(n_pairs) * 4, on_device, &d_K)) return rc;
+    if (int rc = Stage(ctx, ctx->d_dm_points, p_c_in_ref, static_cast<size_t>(n) * 3, on_device, &d_points)) return rc;
+    if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(ref_uv), n, on_device, &d_ref_uv)) return rc;
+    if (!on_device) {
+        if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_status, n)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_dm_q, sizeof(float) * 4 * n_pairs)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_dm_p, sizeof(float) * 3 * n_pairs)) return rc;
+        d_cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr);
+        d_status = static_cast<uint8_t *>(ctx->d_status.ptr);
+        d_q = static_cast<float *>(ctx->d_dm_q.ptr);
+        d_p = static_cast<float *>(ctx->d_dm_p.ptr);
+        if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cur_uv, cur_uv, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+        if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_status, status, n, cudaMemcpyHostToDevice, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_q, q_rc, sizeof(float) * 4 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_p, p_rc, sizeof(float) * 3 * n_pairs, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (int rc = ftk::LaunchDirectMethod(ctx, *params, ref->view, cur->view, n_pairs, d_ri, d_ci, d_offsets, d_K, d_points, d_ref_uv, d_cur_uv, d_q, d_p,
+                                         d_status, n, has_prediction, has_status))
+        return rc;
+    if (!on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, d_cur_uv, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(q_rc, d_q, sizeof(float) * 4 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(p_rc, d_p, sizeof(float) * 3 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FTK_OK;
 }
 
 int ftk_match_mutual_scores(ftk_context *ctx, const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx, uint32_t flags) {

@@ -145,6 +145,34 @@ int ftk_track_image_sequence(ftk_context *ctx, const ftk_klt_params *params, int
                              const uint8_t *frames, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv, uint8_t *status,
                              uint32_t flags);
 
+/* ---- direct-method pose tracker (SURVEY 8(f) "next" row; replaces DirectMethod::TrackFeatures, camera-frame overload,
+ *      src/direct_method_tracker/direct_method_tracker.cpp:41-95, and TrackAllFeaturesDirect, :115-192) --------------------
+ * DirectMethodOptions (direct_method_tracker.h:20-28).  Only kDirect does work upstream; kInverse / kFast are empty there
+ * (:107-113, :194-199) and leave pose and positions untouched here too. */
+#define FTK_DIRECT_METHOD_INVERSE 0
+#define FTK_DIRECT_METHOD_DIRECT 1
+#define FTK_DIRECT_METHOD_FAST 2
+typedef struct ftk_direct_params {
+    uint32_t max_track_points;   /* kMaxTrackPointsNumber (per frame pair) */
+    uint32_t max_iteration;      /* kMaxIteration (per pyramid level) */
+    int32_t patch_row_half;      /* kPatchRowHalfSize */
+    int32_t patch_col_half;      /* kPatchColHalfSize */
+    float max_converge_step;     /* kMaxConvergeStep, compared with the squared 6-vector step */
+    float max_converge_residual; /* kMaxConvergeResidual (unused by the reference) */
+    int32_t method;              /* DirectMethodMethod */
+} ftk_direct_params;
+void ftk_direct_params_default(ftk_direct_params *params);
+/* One 6-DoF pose per frame pair, estimated from ALL features of the pair (n_pairs independent problems per call).  Pair p
+ * uses image ref_image[p] / cur_image[p] (NULL = image p), features [feat_offsets[p], feat_offsets[p+1]), intrinsics
+ * K[4p..4p+3] = (fx, fy, cx, cy), and updates q_rc[4p..] = (w, x, y, z) and p_rc[3p..] (current frame in the reference frame)
+ * in place.  p_c_in_ref: feature positions in the reference camera frame (n x 3).  cur_uv (in/out; out = the projection with
+ * the pose of the last linearisation) and status follow the reference: FTK_FLAG_NO_PREDICTION = cur_pixel_uv.size() differs
+ * (:48-50), FTK_FLAG_NO_STATUS = status.size() differs => all kTracked (:82-84); features projecting outside become
+ * kOutside (:86-91).  q_rc and K must be 16-byte aligned when passed as device pointers. */
+int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t n_pairs,
+                            const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *K, const float *p_c_in_ref,
+                            const float *ref_uv, float *cur_uv, float *q_rc, float *p_rc, uint8_t *status, uint32_t flags);
+
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of
  *      test/test_descriptor_matcher_brief.cpp:33-45 and test/test_descriptor_matcher_superpoint.cpp:32-34) --------

@@ -472,6 +472,71 @@ def test_cosine_nearby_vs_oracle(ctx, oracle):
     assert (exp[1] >= 0).sum() > 50
 
 
+def assert_pose_same(tag, got, exp):
+    ok_g, uv_g, q_g, p_g, st_g = got
+    ok_e, uv_e, q_e, p_e, st_e = exp
+    assert ok_g == ok_e, tag
+    assert np.array_equal(st_g, st_e), f"{tag}: status differs at {np.nonzero(st_g != st_e)[0][:10]}"
+    assert bits_equal(q_g, q_e) and bits_equal(p_g, p_e), f"{tag}: pose differs: gpu q={q_g} p={p_g} oracle q={q_e} p={p_e}"
+    assert bits_equal(uv_g, uv_e), f"{tag}: projected positions differ (max {np.abs(uv_g - uv_e).max()} px)"
+
+
+@pytest.mark.parametrize("shape,levels,half,n_feat,max_points", [((240, 320), 4, 6, 60, 500), ((240, 320), 3, 4, 150, 40), ((480, 752), 4, 6, 300, 500),
+                                                                   ((120, 160), 1, 7, 25, 500), ((240, 320), 5, 3, 80, 500)])
+def test_direct_method_vs_oracle(ctx, oracle, shape, levels, half, n_feat, max_points):
+    """SURVEY 8(f) rank 3: ftk_direct_method_track == DirectMethod::TrackFeatures of the reference, bit for bit."""
+    rows, cols = shape
+    ref, cur, uv, K, pts = S.make_direct_method_scene(rows, cols, n_feat, pair_id=60 + levels, border=10)
+    n = uv.shape[0]
+    pts = pts.copy()
+    pts[1, 2] = -1.0
+    pts[2, 2] = 1e-7
+    pts[4] = (50.0, 0.0, 1.0)
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    rl, cl = oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels)
+    dm = ft.DirectMethod(ctx)
+    dm.options().kPatchRowHalfSize = dm.options().kPatchColHalfSize = half
+    dm.options().kMaxTrackPointsNumber = max_points
+    q0 = np.array([0.9999, 0.002, -0.003, 0.004], np.float32)
+    p0 = np.array([0.01, -0.02, 0.005], np.float32)
+    for method in ("direct", "inverse", "fast"):
+        dm.options().kMethod = {"direct": 1, "inverse": 0, "fast": 2}[method]
+        prm = po.make_direct_params(half=half, max_points=max_points, method=method)
+        for kwargs in ({}, {"cur_uv": uv + 0.5, "status": np.full(n, 2, np.uint8)}):
+            got = dm.TrackFeatures(pyr, pyr, K, pts, uv, q0, p0, cur_pixel_uv=kwargs.get("cur_uv"), status=kwargs.get("status"), ref_image=0, cur_image=1)
+            exp = oracle.direct_method_track(prm, rl, cl, K, pts, uv, q0, p0, **kwargs)
+            assert_pose_same(f"direct method {method} {sorted(kwargs)}", got, exp)
+    dm.options().kMethod = 1
+    ok, cur_uv, q, p, st = dm.TrackFeatures(pyr, pyr, K, pts, uv, [1, 0, 0, 0], [0, 0, 0], ref_image=0, cur_image=1)
+    assert ok and (st == 1).mean() > 0.7 and np.abs(p).max() > 1e-3  # the pose moved, most projections stay inside
+
+
+def test_direct_method_batch_of_pairs(ctx, oracle):
+    """Several independent pose problems in one launch (one CTA per frame pair), ragged feature counts, image maps."""
+    rows, cols, levels = 240, 320, 4
+    scenes = [S.make_direct_method_scene(rows, cols, 40 + 15 * p, pair_id=70 + p, border=10) for p in range(5)]
+    imgs = np.stack([s[0] for s in scenes] + [s[1] for s in scenes])
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 10)
+    pyr.SetRawImages(imgs)
+    pyr.CreateImagePyramid()
+    counts = [s[2].shape[0] for s in scenes]
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    dm = ft.DirectMethod(ctx)
+    K = np.stack([s[3] for s in scenes])
+    q0 = np.tile(np.array([1, 0, 0, 0], np.float32), (5, 1))
+    p0 = np.zeros((5, 3), np.float32)
+    ok, cur_uv, q, p, st = dm.TrackFeaturesBatch(pyr, pyr, offsets, K, np.concatenate([s[4] for s in scenes]), np.concatenate([s[2] for s in scenes]), q0, p0,
+                                                 ref_image=np.arange(5), cur_image=np.arange(5, 10))
+    assert ok
+    prm = po.make_direct_params()
+    for i, s in enumerate(scenes):
+        exp = oracle.direct_method_track(prm, oracle.pyramid_build(s[0], levels), oracle.pyramid_build(s[1], levels), s[3], s[4], s[2], q0[i], p0[i])
+        sl = slice(offsets[i], offsets[i + 1])
+        assert_pose_same(f"pair {i}", (True, cur_uv[sl], q[i], p[i], st[sl]), exp)
+
+
 def lightglue_like_scores(n_ref, n_cur, seed):
     """Log-assignment-like matrix: a planted partial permutation of strong scores over weak background, ties, -inf, NaN."""
     rng = np.random.default_rng(seed)
