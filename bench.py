@@ -310,6 +310,39 @@ def run_extras(ctx, L, torch, local_rank, steps):
     out["C5_float256_force_20k_x_20k"] = {"pairs_per_s": 4e8 / (ms * 1e-3), "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12,
                                           "matched": int((d_idx2.cpu().numpy() >= 0).sum())}
 
+    # ---- direct-method pose tracker: one 6-DoF pose per frame pair from 300 features, 13x13 patches, 4 levels ----
+    n_dm, f_dm = 600, 300
+    scenes = [S.make_direct_method_scene(ROWS, COLS, f_dm, pair_id=200 + p) for p in range(4)]
+    pyr_dm = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, 2 * n_dm)
+    pyr_dm.SetRawImages(np.stack([scenes[p % 4][0] for p in range(n_dm)] + [scenes[p % 4][1] for p in range(n_dm)]))
+    pyr_dm.CreateImagePyramid()
+    counts = [scenes[p % 4][2].shape[0] for p in range(n_dm)]
+    d_off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)).to(dev)
+    d_uv = torch.from_numpy(np.concatenate([scenes[p % 4][2] for p in range(n_dm)])).to(dev)
+    d_pts = torch.from_numpy(np.concatenate([scenes[p % 4][4] for p in range(n_dm)])).to(dev)
+    d_K = torch.from_numpy(np.stack([scenes[p % 4][3] for p in range(n_dm)])).to(dev)
+    d_cur = torch.empty_like(d_uv)
+    d_st = torch.empty((d_uv.shape[0],), dtype=torch.uint8, device=dev)
+    d_ri = torch.arange(n_dm, dtype=torch.int32, device=dev)
+    d_ci = d_ri + n_dm
+    q_init = torch.tensor([1.0, 0.0, 0.0, 0.0], device=dev).repeat(n_dm, 1).contiguous()
+    d_q, d_p = q_init.clone(), torch.zeros((n_dm, 3), device=dev)
+    dprm = ft.DirectMethod(ctx)._params()
+    fl_dm = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
+
+    def dm_fn():
+        d_q.copy_(q_init)  # every run starts from the identity pose (tiny device copies on torch's stream, ordered by the syncs of timeit)
+        d_p.zero_()
+        torch.cuda.current_stream().synchronize()
+        ctx.check(L.ftk_direct_method_track(ctx._h, C.byref(dprm), pyr_dm._h, pyr_dm._h, n_dm, vp(d_ri.data_ptr()), vp(d_ci.data_ptr()), vp(d_off.data_ptr()),
+                                            vp(d_K.data_ptr()), vp(d_pts.data_ptr()), vp(d_uv.data_ptr()), vp(d_cur.data_ptr()), vp(d_q.data_ptr()),
+                                            vp(d_p.data_ptr()), vp(d_st.data_ptr()), fl_dm))
+    ms = timeit(dm_fn, max(2, steps // 2))
+    out["direct_method_600_pairs_x_300_features"] = {"ms": ms, "pairs_per_s": n_dm / (ms * 1e-3), "features_per_s": int(d_uv.shape[0]) / (ms * 1e-3),
+                                                     "tracked_fraction": float((d_st.cpu().numpy() == 1).mean()),
+                                                     "pose_translation_of_pair_0": [float(x) for x in d_p[0].cpu().numpy()]}
+    pyr_dm.close()
+
     # ---- score-matrix mutual arg-max (NNFeatureMatcher post-processing): HBM bound, 4 B per matrix element ----
     for n in (2048, 12288):  # LightGlue's usual size (16 MB, L2 resident) and a matrix far larger than L2 (604 MB)
         d_s = torch.randn((n, n), dtype=torch.float32, device=dev) * 2.0 - 6.0

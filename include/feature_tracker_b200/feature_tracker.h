@@ -389,6 +389,77 @@ private:
     Options options_;
 };
 
+// src/direct_method_tracker/direct_method_tracker.h:14-77.  Quaternions are passed as (w, x, y, z) arrays and 3-vectors as
+// std::array<float, 3> (the reference's Quat / Vec3 are Eigen types of the absent Slam_Utility; an application that has them
+// converts with q.w(), q.x(), ... / v.data()).  Only the camera-frame overload is offered: the world-frame one
+// (direct_method_tracker.cpp:8-39) is eight lines of quaternion algebra around it.
+enum DirectMethodMethod : uint8_t { kDirectMethodInverse = 0, kDirectMethodDirect = 1, kDirectMethodFast = 2 };
+
+struct DirectMethodOptions {
+    uint32_t kMaxTrackPointsNumber = 500;
+    uint32_t kMaxIteration = 15;
+    int32_t kPatchRowHalfSize = 6;
+    int32_t kPatchColHalfSize = 6;
+    float kMaxConvergeStep = 1e-6f;
+    float kMaxConvergeResidual = 2.0f;
+    DirectMethodMethod kMethod = kDirectMethodDirect;
+};
+
+class DirectMethod {
+public:
+    DirectMethod() = default;
+    virtual ~DirectMethod() = default;
+    DirectMethod(const DirectMethod &) = delete;
+
+    // direct_method_tracker.cpp:41-95
+    bool TrackFeatures(const ImagePyramid &ref_pyramid, const ImagePyramid &cur_pyramid, const std::array<float, 4> &K,
+                       const std::vector<std::array<float, 3>> &p_c_in_ref, const std::vector<Vec2> &ref_pixel_uv, std::vector<Vec2> &cur_pixel_uv,
+                       std::array<float, 4> &q_rc, std::array<float, 3> &p_rc, std::vector<uint8_t> &status) {
+        if (ref_pixel_uv.empty()) return false;
+        if (cur_pyramid.level() != ref_pyramid.level()) return false;
+        if (!ref_pyramid.handle() || !cur_pyramid.handle() || p_c_in_ref.size() != ref_pixel_uv.size()) return false;
+        const int32_t n = static_cast<int32_t>(ref_pixel_uv.size());
+        ftk_direct_params p;
+        ftk_direct_params_default(&p);
+        p.max_track_points = options_.kMaxTrackPointsNumber;
+        p.max_iteration = options_.kMaxIteration;
+        p.patch_row_half = options_.kPatchRowHalfSize;
+        p.patch_col_half = options_.kPatchColHalfSize;
+        p.max_converge_step = options_.kMaxConvergeStep;
+        p.max_converge_residual = options_.kMaxConvergeResidual;
+        p.method = static_cast<int32_t>(options_.kMethod);
+        uint32_t flags = 0;
+        std::vector<float> ref_flat(2 * static_cast<size_t>(n)), cur_flat(2 * static_cast<size_t>(n), 0.0f), pts(3 * static_cast<size_t>(n));
+        for (int32_t i = 0; i < n; ++i) {
+            ref_flat[2 * i] = ref_pixel_uv[i].x(), ref_flat[2 * i + 1] = ref_pixel_uv[i].y();
+            pts[3 * i] = p_c_in_ref[i][0], pts[3 * i + 1] = p_c_in_ref[i][1], pts[3 * i + 2] = p_c_in_ref[i][2];
+        }
+        if (cur_pixel_uv.size() == ref_pixel_uv.size()) {
+            for (int32_t i = 0; i < n; ++i) cur_flat[2 * i] = cur_pixel_uv[i].x(), cur_flat[2 * i + 1] = cur_pixel_uv[i].y();
+        } else {
+            flags |= FTK_FLAG_NO_PREDICTION;  // :48-50
+        }
+        if (status.size() != ref_pixel_uv.size()) {
+            flags |= FTK_FLAG_NO_STATUS;  // :82-84
+            status.assign(ref_pixel_uv.size(), static_cast<uint8_t>(TrackStatus::kTracked));
+        }
+        const int32_t offsets[2] = {0, n};
+        const int32_t image0 = 0;
+        const int rc = ftk_direct_method_track(Device::Get(), &p, ref_pyramid.handle(), cur_pyramid.handle(), 1, &image0, &image0, offsets, K.data(), pts.data(),
+                                               ref_flat.data(), cur_flat.data(), q_rc.data(), p_rc.data(), status.data(), flags);
+        if (rc != FTK_OK) return false;
+        cur_pixel_uv.resize(ref_pixel_uv.size());
+        for (int32_t i = 0; i < n; ++i) cur_pixel_uv[i] = Vec2(cur_flat[2 * i], cur_flat[2 * i + 1]);
+        return true;
+    }
+
+    DirectMethodOptions &options() { return options_; }
+    const DirectMethodOptions &options() const { return options_; }
+
+private:
+    DirectMethodOptions options_;
+};
+
 }  // namespace feature_tracker
 
 #endif

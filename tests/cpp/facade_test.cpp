@@ -97,6 +97,27 @@ int main(int argc, char **argv) {
         fwrite(xy, sizeof(float), 2, out);
     }
     fwrite(status.data(), 1, n_ref, out);
+
+    // Direct-method pose tracker, as in test_direct_method.cpp: the KLT features read as points of a plane 5 m in front of the camera
+    {
+        const std::array<float, 4> K = {400.0f, 400.0f, cols / 2.0f, rows / 2.0f};
+        std::vector<std::array<float, 3>> p_c_in_ref(n);
+        for (int i = 0; i < n; ++i) p_c_in_ref[i] = {(uv[2 * i] - K[2]) / K[0] * 5.0f, (uv[2 * i + 1] - K[3]) / K[1] * 5.0f, 5.0f};
+        DirectMethod solver;
+        std::vector<Vec2> cur_pixel_uv;
+        std::vector<uint8_t> st;
+        std::array<float, 4> q_rc = {1.0f, 0.0f, 0.0f, 0.0f};
+        std::array<float, 3> p_rc = {0.0f, 0.0f, 0.0f};
+        okv = solver.TrackFeatures(ref_pyramid, cur_pyramid, K, p_c_in_ref, ref_pixel_uv, cur_pixel_uv, q_rc, p_rc, st) ? 1 : 0;
+        fwrite(&okv, sizeof(okv), 1, out);
+        fwrite(q_rc.data(), sizeof(float), 4, out);
+        fwrite(p_rc.data(), sizeof(float), 3, out);
+        for (int i = 0; i < n; ++i) {
+            const float xy[2] = {cur_pixel_uv[i].x(), cur_pixel_uv[i].y()};
+            fwrite(xy, sizeof(float), 2, out);
+        }
+        fwrite(st.data(), 1, n, out);
+    }
     fclose(in);
     fclose(out);
     return 0;

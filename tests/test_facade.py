@@ -27,7 +27,7 @@ def test_facade_compiles_and_links(tmp_path):
     text = open(os.path.join(ROOT, "include", "feature_tracker_b200", "feature_tracker.h")).read()
     for name in ["namespace feature_tracker", "enum class TrackStatus", "struct OpticalFlowOptions", "class OpticalFlowBasicKlt", "class OpticalFlowAffineKlt",
                  "class OpticalFlowLssdKlt", "class DescriptorMatcher", "predict_affine", "predict_R_cr", "consider_patch_luminance", "ForceMatch",
-                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber"]:
+                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber", "class DirectMethod", "struct DirectMethodOptions"]:
         assert name in text, name
 
 
@@ -72,3 +72,17 @@ def test_facade_matches_oracle(tmp_path, oracle):
     mst = take(np.uint8, rb.shape[0])
     _, euv, est = oracle.match_brief_nearby_uv(rb, cb, pred, pos, 50, 50, 60.0)
     assert ok == 1 and (mst == est).all() and (muv[mst == 1].view(np.uint32) == euv[est == 1].view(np.uint32)).all()
+    # direct-method pose tracker through the facade
+    ok = take(np.int32, 1)[0]
+    q = take(np.float32, 4)
+    pr = take(np.float32, 3)
+    duv = take(np.float32, 2 * n).reshape(n, 2)
+    dst = take(np.uint8, n)
+    K = np.array([400.0, 400.0, cols / 2.0, rows / 2.0], np.float32)
+    five = np.float32(5.0)
+    pts = np.stack([(uv[:, 0] - K[2]) / K[0] * five, (uv[:, 1] - K[3]) / K[1] * five, np.full(n, five, np.float32)], axis=1).astype(np.float32)
+    eok, euv, eq, ep, est = oracle.direct_method_track(po.make_direct_params(), rl, cl, K, pts, uv, [1, 0, 0, 0], [0, 0, 0])
+    assert ok == 1 and eok and (dst == est).all()
+    assert (q.view(np.uint32) == eq.view(np.uint32)).all() and (pr.view(np.uint32) == ep.view(np.uint32)).all()
+    assert (duv.view(np.uint32) == euv.view(np.uint32)).all()
+
