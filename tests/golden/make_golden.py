@@ -77,6 +77,36 @@ def main():
           "force matched", int((m["brief_force_idx"] >= 0).sum()), "nearby matched", int((m["brief_nearby_idx"] >= 0).sum()),
           "float force", int((m["float_force_idx"] >= 0).sum()), "float nearby", int((m["float_nearby_idx"] >= 0).sum()))
 
+    # ---- direct-method pose tracker on the reference's own KITTI fixture (test/test_direct_method.cpp) ------------------------
+    dm_dir = "/root/reference/example/direct_method"
+    left = np.array(Image.open(os.path.join(dm_dir, "left.png")).convert("L"))
+    disparity = np.array(Image.open(os.path.join(dm_dir, "disparity.png")).convert("L"))
+    curs = [np.array(Image.open(os.path.join(dm_dir, f"00000{i}.png")).convert("L")) for i in (1, 2)]
+    fx = fy = np.float32(718.856)
+    cx, cy, baseline = np.float32(607.1928), np.float32(185.2157), np.float32(0.573)  # test_direct_method.cpp:15-20
+    rng = np.random.default_rng(7)  # the demo draws 300 rand() pixels (:44-48); seeded here, zero-disparity pixels skipped
+    uv = []
+    while len(uv) < 300:
+        c, r = int(rng.integers(0, left.shape[1])), int(rng.integers(0, left.shape[0]))
+        if disparity[r, c] > 0:
+            uv.append((c, r))
+    uv = np.array(uv, np.float32)
+    depth = (fx * baseline / disparity[uv[:, 1].astype(int), uv[:, 0].astype(int)].astype(np.float32)).astype(np.float32)
+    p_w = (np.stack([(uv[:, 0] - cx) / fx, (uv[:, 1] - cy) / fy, np.ones(300, np.float32)], 1).astype(np.float32) * depth[:, None]).astype(np.float32)
+    dm_levels = 5  # :39, :76
+    d = {"left": left, "cur1": curs[0], "cur2": curs[1], "uv": uv, "p_c_in_ref": p_w, "K": np.array([fx, fy, cx, cy], np.float32),
+         "levels": np.int32(dm_levels)}
+    ll = R.pyramid_build(left, dm_levels)
+    q, p = np.array([1, 0, 0, 0], np.float32), np.zeros(3, np.float32)  # q_ref = identity, p_ref = 0: world frame == reference camera frame
+    cur_uv, st = None, None
+    for i, cur_img in enumerate(curs, 1):  # the demo carries pose, positions and status from frame to frame (:69-86)
+        ok, cur_uv, q, p, st = R.direct_method_track(po.make_direct_params(), ll, R.pyramid_build(cur_img, dm_levels), d["K"], p_w, uv, q, p,
+                                                     cur_uv=cur_uv, status=st)
+        assert ok
+        d[f"q_{i}"], d[f"p_{i}"], d[f"uv_{i}"], d[f"st_{i}"] = q, p, cur_uv, st
+        print(f"direct method frame {i}: q_rc = {q}, p_rc = {p}, inside = {int((st == 1).sum())}")
+    np.savez_compressed(os.path.join(HERE, "direct_method_golden.npz"), **d)
+
 
 if __name__ == "__main__":
     main()

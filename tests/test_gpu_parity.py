@@ -513,6 +513,24 @@ def test_direct_method_vs_oracle(ctx, oracle, shape, levels, half, n_feat, max_p
     assert ok and (st == 1).mean() > 0.7 and np.abs(p).max() > 1e-3  # the pose moved, most projections stay inside
 
 
+def test_direct_method_matches_golden(ctx):
+    """The CUDA path against the committed outputs of the reference itself on its own KITTI fixture (1241x376, 5 levels, 300 features,
+    pose / positions / status carried over two frames like test/test_direct_method.cpp:69-86)."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "direct_method_golden.npz")))
+    levels = int(g["levels"])
+    rows, cols = g["left"].shape
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 3)
+    pyr.SetRawImages(np.stack([g["left"], g["cur1"], g["cur2"]]))
+    pyr.CreateImagePyramid()
+    dm = ft.DirectMethod(ctx)
+    q, p, cur_uv, st = np.array([1, 0, 0, 0], np.float32), np.zeros(3, np.float32), None, None
+    for i in (1, 2):
+        ok, cur_uv, q, p, st = dm.TrackFeatures(pyr, pyr, g["K"], g["p_c_in_ref"], g["uv"], q, p, cur_pixel_uv=cur_uv, status=st, ref_image=0, cur_image=i)
+        assert_pose_same(f"golden frame {i}", (ok, cur_uv, q, p, st), (True, g[f"uv_{i}"], g[f"q_{i}"], g[f"p_{i}"], g[f"st_{i}"]))
+
+
 def test_direct_method_batch_of_pairs(ctx, oracle):
     """Several independent pose problems in one launch (one CTA per frame pair), ragged feature counts, image maps."""
     rows, cols, levels = 240, 320, 4

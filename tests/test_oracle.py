@@ -1,10 +1,12 @@
 """CPU tests of the oracle (plain-C restatement) against (a) the committed golden vectors, which were produced by the
 reference's own sources compiled in place, (b) that reference build itself when it is available, and (c) domain
 properties.  No GPU needed."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import bits_equal
+from conftest import GOLDEN, bits_equal
 from feature_tracker_b200 import synthetic as S
 from oracle import pyoracle as po
 
@@ -249,3 +251,17 @@ def test_direct_method_restatement_vs_reference_build(oracle, reflib, levels, ha
     ok, cur_uv, q, p, st = oracle.direct_method_track(prm, rl, cl, K, pts, uv, [1, 0, 0, 0], [0, 0, 0])
     assert ok and (st == 1).sum() > 40 and np.abs(p).max() > 1e-3
     assert not oracle.direct_method_track(prm, rl, cl, K, np.zeros((0, 3)), np.zeros((0, 2)), [1, 0, 0, 0], [0, 0, 0])[0]
+
+
+def test_direct_method_matches_golden(oracle):
+    """The restatement against outputs of the reference itself (direct_method_tracker.cpp compiled in place) on the reference's
+    own KITTI fixture, two frames with pose / positions / status carried over like test/test_direct_method.cpp:69-86."""
+    g = dict(np.load(os.path.join(GOLDEN, "direct_method_golden.npz")))
+    levels = int(g["levels"])
+    ll = oracle.pyramid_build(g["left"], levels)
+    q, p, cur_uv, st = np.array([1, 0, 0, 0], np.float32), np.zeros(3, np.float32), None, None
+    for i in (1, 2):
+        ok, cur_uv, q, p, st = oracle.direct_method_track(po.make_direct_params(), ll, oracle.pyramid_build(g[f"cur{i}"], levels), g["K"], g["p_c_in_ref"],
+                                                          g["uv"], q, p, cur_uv=cur_uv, status=st)
+        assert ok and bits_equal(q, g[f"q_{i}"]) and bits_equal(p, g[f"p_{i}"]) and bits_equal(cur_uv, g[f"uv_{i}"]) and np.array_equal(st, g[f"st_{i}"])
+    assert 0.5 < p[2] / 2 < 1.0  # the car drives forward ~0.7 m per frame
