@@ -558,7 +558,7 @@ def run_b200(args):
                     pass
                 ms_k = res["kernel_ms"][f"klt_{t[0]}_{t[1]}"]
                 tfs = flops / (ms_k * 1e-3) / 1e12
-                out[f"{t[0]}_{t[1]}"] = {"bound": "fp32 CUDA-core issue (not HBM, not tensor: SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
+                out[f"{t[0]}_{t[1]}"] = {"bound": "fp32", "bound_note": "FP32 CUDA-core issue + L1/shared bandwidth; neither HBM nor tensor (SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
                                          "frac": tfs / fp32_peak, "traffic": traffic,
                                          "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
                                          "algorithmic_flops_per_launch": flops, "algorithmic_flops_formula": formula,
