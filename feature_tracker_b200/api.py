@@ -612,3 +612,21 @@ class DirectMethod:
                                                     p_c_in_ref, ref_uv, np.asarray(q_rc).reshape(1, 4), np.asarray(p_rc).reshape(1, 3), cur_pixel_uv,
                                                     status, np.array([ref_image], np.int32), np.array([cur_image], np.int32))
         return ok, cur, q[0], p[0], st
+
+    def TrackFeaturesWorld(self, ref_pyramid, cur_pyramid, K, ref_q_wc, ref_p_wc, p_w, ref_pixel_uv, cur_q_wc, cur_p_wc, cur_pixel_uv=None,
+                           status=None, ref_image=0, cur_image=0):
+        """direct_method_tracker.cpp:8-39 (world-frame overload): lifts the points and the predicted pose into the reference camera
+        frame, runs the camera-frame overload and maps the pose back.  Returns (ok, cur_pixel_uv, cur_q_wc, cur_p_wc, status)."""
+        from . import quat
+        ref_q_wc = np.asarray(ref_q_wc, np.float32).reshape(4)
+        ref_p_wc = np.asarray(ref_p_wc, np.float32).reshape(3)
+        ref_q_cw = quat.inverse(ref_q_wc)
+        p_c_in_ref = quat.rotate(ref_q_cw, np.asarray(p_w, np.float32).reshape(-1, 3) - ref_p_wc)
+        q_rc = quat.multiply(ref_q_cw, cur_q_wc)
+        p_rc = quat.rotate(ref_q_cw, np.asarray(cur_p_wc, np.float32).reshape(3) - ref_p_wc)
+        ok, cur, q_rc, p_rc, st = self.TrackFeatures(ref_pyramid, cur_pyramid, K, p_c_in_ref, ref_pixel_uv, q_rc, p_rc, cur_pixel_uv, status, ref_image,
+                                                     cur_image)
+        if not ok:  # RETURN_FALSE_IF_FALSE: the caller's pose stays untouched
+            return False, cur, np.asarray(cur_q_wc, np.float32).reshape(4), np.asarray(cur_p_wc, np.float32).reshape(3), st
+        return True, cur, quat.multiply(ref_q_wc, q_rc), quat.rotate(ref_q_wc, p_rc) + ref_p_wc, st
+

@@ -330,6 +330,27 @@ class RefLib(_CpuChecker):
             raise FileNotFoundError("oracle/_ref/libftk_ref.so is absent and /root/reference is not available to build it")
         super().__init__(REF_SO)
 
+    def direct_method_track_world(self, params, ref_levels, cur_levels, K, ref_q_wc, ref_p_wc, p_w, ref_uv, cur_q_wc, cur_p_wc):
+        """The world-frame overload (direct_method_tracker.cpp:8-39); empty cur_pixel_uv / status vectors on entry."""
+        levels = len(ref_levels)
+        ref_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in ref_levels]
+        cur_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in cur_levels]
+        rows = np.array([a.shape[0] for a in ref_levels], dtype=np.int32)
+        cols = np.array([a.shape[1] for a in ref_levels], dtype=np.int32)
+        PtrArr = C.POINTER(C.c_uint8) * levels
+        rp = PtrArr(*[_u8p(a) for a in ref_levels])
+        cp = PtrArr(*[_u8p(a) for a in cur_levels])
+        ref_uv = np.ascontiguousarray(ref_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        pts = np.ascontiguousarray(p_w, dtype=np.float32).reshape(n, 3)
+        f = lambda a, k: np.ascontiguousarray(a, dtype=np.float32).reshape(k).copy()
+        Kc, rq, rpw, q, p = f(K, 4), f(ref_q_wc, 4), f(ref_p_wc, 3), f(cur_q_wc, 4), f(cur_p_wc, 3)
+        cur_buf, st_buf = np.zeros((n, 2), np.float32), np.zeros(n, np.uint8)
+        ok = self._fn("direct_method_track_world")(C.byref(params), C.c_int32(levels), rp, cp, _i32p(rows), _i32p(cols), _f32p(Kc), _f32p(rq), _f32p(rpw),
+                                                    C.c_int32(n), _f32p(pts), _f32p(ref_uv), _f32p(cur_buf), C.c_int32(0), _f32p(q), _f32p(p), _u8p(st_buf),
+                                                    C.c_int32(0))
+        return ok == 1, cur_buf, q, p, st_buf
+
 
 class OracleLib(_CpuChecker):
     prefix = "ftko_"

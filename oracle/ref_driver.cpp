@@ -308,4 +308,45 @@ int ftkref_direct_method_track(const ftko_direct_params *params, int32_t levels,
     return 1;
 }
 
+// The world-frame overload (direct_method_tracker.cpp:8-39): ref pose, world points, current pose in/out.
+int ftkref_direct_method_track_world(const ftko_direct_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                                     const int32_t *rows, const int32_t *cols, const float *K, const float *ref_q_wc, const float *ref_p_wc, int32_t n,
+                                     const float *p_w, const float *ref_uv, float *cur_uv, int32_t cur_uv_count, float *cur_q_wc, float *cur_p_wc,
+                                     uint8_t *status, int32_t status_count) {
+    feature_tracker::DirectMethod solver;
+    solver.options().kMaxTrackPointsNumber = params->max_track_points;
+    solver.options().kMaxIteration = params->max_iteration;
+    solver.options().kPatchRowHalfSize = params->patch_row_half;
+    solver.options().kPatchColHalfSize = params->patch_col_half;
+    solver.options().kMaxConvergeStep = params->max_converge_step;
+    solver.options().kMaxConvergeResidual = params->max_converge_residual;
+    solver.options().kMethod = static_cast<feature_tracker::DirectMethodMethod>(params->method);
+    PaddedLevels ref_store, cur_store;
+    ref_store.Adopt(levels, ref_levels, rows, cols);
+    cur_store.Adopt(levels, cur_levels, rows, cols);
+    ImagePyramid ref_pyr, cur_pyr;
+    ref_pyr.SetLevels(levels, ref_store.ptr.data(), rows, cols);
+    cur_pyr.SetLevels(levels, cur_store.ptr.data(), rows, cols);
+    std::vector<Vec2> ref_vec = WrapUv(ref_uv, n);
+    std::vector<Vec2> cur_vec = WrapUv(cur_uv, cur_uv_count);
+    std::vector<uint8_t> status_vec(status, status + status_count);
+    std::vector<Vec3> points(n);
+    for (int32_t i = 0; i < n; ++i) points[i] << p_w[3 * i], p_w[3 * i + 1], p_w[3 * i + 2];
+    const std::array<float, 4> Kc = {K[0], K[1], K[2], K[3]};
+    const Quat q_ref(ref_q_wc[0], ref_q_wc[1], ref_q_wc[2], ref_q_wc[3]);
+    Quat q_cur(cur_q_wc[0], cur_q_wc[1], cur_q_wc[2], cur_q_wc[3]);
+    Vec3 p_ref, p_cur;
+    p_ref << ref_p_wc[0], ref_p_wc[1], ref_p_wc[2];
+    p_cur << cur_p_wc[0], cur_p_wc[1], cur_p_wc[2];
+    if (!solver.TrackFeatures(ref_pyr, cur_pyr, Kc, q_ref, p_ref, points, ref_vec, cur_vec, q_cur, p_cur, status_vec)) return 0;
+    for (int32_t i = 0; i < n; ++i) {
+        cur_uv[2 * i] = cur_vec[i].x();
+        cur_uv[2 * i + 1] = cur_vec[i].y();
+        status[i] = status_vec[i];
+    }
+    cur_q_wc[0] = q_cur.w(), cur_q_wc[1] = q_cur.x(), cur_q_wc[2] = q_cur.y(), cur_q_wc[3] = q_cur.z();
+    cur_p_wc[0] = p_cur(0), cur_p_wc[1] = p_cur(1), cur_p_wc[2] = p_cur(2);
+    return 1;
+}
+
 }  // extern "C"

@@ -531,6 +531,28 @@ def test_direct_method_matches_golden(ctx):
         assert_pose_same(f"golden frame {i}", (ok, cur_uv, q, p, st), (True, g[f"uv_{i}"], g[f"q_{i}"], g[f"p_{i}"], g[f"st_{i}"]))
 
 
+def test_direct_method_world_frame_overload(ctx, reflib):
+    """direct_method_tracker.cpp:8-39: the world-frame overload (host-side quaternion algebra around the kernel) against the
+    reference's own overload, bit for bit."""
+    rows, cols, levels = 240, 320, 4
+    ref, cur, uv, K, pts = S.make_direct_method_scene(rows, cols, 70, pair_id=90, border=10)
+    ref_q = np.array([0.96, 0.1, -0.2, 0.15], np.float32)
+    ref_q /= np.float32(np.linalg.norm(ref_q))
+    ref_p = np.array([1.5, -0.7, 3.0], np.float32)
+    from feature_tracker_b200 import quat
+    p_w = quat.rotate(ref_q, pts) + ref_p  # world points that the reference camera sees at `pts`
+    cur_q, cur_p = ref_q.copy(), ref_p.copy()  # prediction: the camera did not move
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    dm = ft.DirectMethod(ctx)
+    got = dm.TrackFeaturesWorld(pyr, pyr, K, ref_q, ref_p, p_w, uv, cur_q, cur_p, ref_image=0, cur_image=1)
+    exp = reflib.direct_method_track_world(po.make_direct_params(), reflib.pyramid_build(ref, levels), reflib.pyramid_build(cur, levels), K, ref_q, ref_p,
+                                           p_w, uv, cur_q, cur_p)
+    assert_pose_same("world-frame overload", got, exp)
+    assert np.abs(got[3] - ref_p).max() > 1e-3
+
+
 def test_direct_method_batch_of_pairs(ctx, oracle):
     """Several independent pose problems in one launch (one CTA per frame pair), ragged feature counts, image maps."""
     rows, cols, levels = 240, 320, 4

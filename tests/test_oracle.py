@@ -265,3 +265,24 @@ def test_direct_method_matches_golden(oracle):
                                                           g["uv"], q, p, cur_uv=cur_uv, status=st)
         assert ok and bits_equal(q, g[f"q_{i}"]) and bits_equal(p, g[f"p_{i}"]) and bits_equal(cur_uv, g[f"uv_{i}"]) and np.array_equal(st, g[f"st_{i}"])
     assert 0.5 < p[2] / 2 < 1.0  # the car drives forward ~0.7 m per frame
+
+
+def test_direct_method_world_frame_algebra(oracle, reflib):
+    """The host-side quaternion algebra of the world-frame overload (feature_tracker_b200/quat.py, used by the product's
+    DirectMethod.TrackFeaturesWorld) around the camera-frame core == the reference's own world-frame overload
+    (direct_method_tracker.cpp:8-39), bit for bit."""
+    from feature_tracker_b200 import quat
+    ref, cur, uv, K, pts = S.make_direct_method_scene(240, 320, 70, pair_id=90, border=10)
+    ref_q = np.array([0.96, 0.1, -0.2, 0.15], np.float32)
+    ref_q /= np.float32(np.linalg.norm(ref_q))
+    ref_p = np.array([1.5, -0.7, 3.0], np.float32)
+    p_w = quat.rotate(ref_q, pts) + ref_p
+    rl, cl = oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4)
+    exp = reflib.direct_method_track_world(po.make_direct_params(), rl, cl, K, ref_q, ref_p, p_w, uv, ref_q, ref_p)
+    q_cw = quat.inverse(ref_q)
+    ok, cu, q, p, st = oracle.direct_method_track(po.make_direct_params(), rl, cl, K, quat.rotate(q_cw, p_w - ref_p), uv, quat.multiply(q_cw, ref_q),
+                                                  quat.rotate(q_cw, ref_p - ref_p))
+    assert ok and exp[0]
+    assert bits_equal(quat.multiply(ref_q, q), exp[2]) and bits_equal(quat.rotate(ref_q, p) + ref_p, exp[3])
+    assert bits_equal(cu, exp[1]) and np.array_equal(st, exp[4])
+
