@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
     "ftk_track_image_pairs", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
-    "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track",
+    "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track", "ftk_dense_flow_params_default", "ftk_dense_flow_track",
 ]
 
 
@@ -66,6 +66,12 @@ class DirectParams(C.Structure):
     ]
 
 
+class DenseFlowParams(C.Structure):
+    """ftk_dense_flow_params (include/ftk_c.h) == DenseOpticalFlow::Options of the reference."""
+
+    _fields_ = [("max_iteration", C.c_int32), ("half_patch_size", C.c_int32), ("max_converge_step", C.c_float), ("max_delta_flow_step", C.c_float)]
+
+
 def load_library():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -97,6 +103,8 @@ def load_library():
         "ftk_match_hamming_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_dense_flow_params_default": (None, [P(DenseFlowParams)]),
+        "ftk_dense_flow_track": (C.c_int, [vp, P(DenseFlowParams), vp, vp, i32, i32, vp, vp, u32]),
         "ftk_direct_params_default": (None, [P(DirectParams)]),
         "ftk_direct_method_track": (C.c_int, [vp, P(DirectParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]),
         "ftk_match_mutual_scores": (C.c_int, [vp, vp, i32, i32, f32, vp, u32]),

@@ -630,3 +630,51 @@ class DirectMethod:
             return False, cur, np.asarray(cur_q_wc, np.float32).reshape(4), np.asarray(cur_p_wc, np.float32).reshape(3), st
         return True, cur, quat.multiply(ref_q_wc, q_rc), quat.rotate(ref_q_wc, p_rc) + ref_p_wc, st
 
+
+class DenseOpticalFlowOptions:
+    """dense_optical_flow.h:15-20"""
+
+    def __init__(self):
+        self.kMaxIteration = 10
+        self.kHalfPatchSize = 2
+        self.kMaxConvergeStep = 1e-6
+        self.kMaxDeltaFlowStep = 1.0
+
+
+class DenseOpticalFlow:
+    """DenseOpticalFlow (src/dense_optical_flow_tracker/dense_optical_flow.h:12-65), Gunnar Farneback's method."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = DenseOpticalFlowOptions()
+
+    def OpticalFlowMethodName(self):
+        return "Gunnar Farneback"
+
+    def options(self):
+        return self._options
+
+    def _params(self):
+        o = self._options
+        p = _capi.DenseFlowParams()
+        p.max_iteration, p.half_patch_size = int(o.kMaxIteration), int(o.kHalfPatchSize)
+        p.max_converge_step, p.max_delta_flow_step = float(o.kMaxConvergeStep), float(o.kMaxDeltaFlowStep)
+        return p
+
+    def Track(self, ref_pyramid, cur_pyramid, flow_rc=None, single_level=False, ref_image=0, cur_image=0):
+        """dense_optical_flow.cpp:35-85 (pyramids) or, with single_level=True, :7-33 (the GrayImage overload on level 0, where flow_rc
+        = (flow_row, flow_col) of the image's size is the initial flow).  Returns (ok, flow_row, flow_col)."""
+        rows, cols = ref_pyramid.rows, ref_pyramid.cols
+        fr = np.zeros((rows, cols), np.float32)
+        fc = np.zeros((rows, cols), np.float32)
+        flags = _capi.FLAG_SINGLE_LEVEL if single_level else 0
+        if single_level and flow_rc is not None and np.asarray(flow_rc[0]).shape == (rows, cols) and np.asarray(flow_rc[1]).shape == (rows, cols):
+            fr[:] = flow_rc[0]
+            fc[:] = flow_rc[1]
+        else:
+            flags |= _capi.FLAG_NO_PREDICTION
+        prm = self._params()
+        rc = lib().ftk_dense_flow_track(self.ctx._h, C.byref(prm), ref_pyramid._h, cur_pyramid._h, int(ref_image), int(cur_image), _ptr(fr), _ptr(fc), flags)
+        ok = self.ctx.check(rc, soft=(_capi.ERR_LEVEL_MISMATCH,))
+        return ok, fr, fc
+

@@ -96,6 +96,14 @@ void ftk_klt_params_default(ftk_klt_params *p) {
     p->forward_backward_max_error = 0.0f;
 }
 
+void ftk_dense_flow_params_default(ftk_dense_flow_params *p) {
+    if (!p) return;
+    p->max_iteration = 10;  // dense_optical_flow.h:15-20
+    p->half_patch_size = 2;
+    p->max_converge_step = 1e-6f;
+    p->max_delta_flow_step = 1.0f;
+}
+
 void ftk_direct_params_default(ftk_direct_params *p) {
     if (!p) return;
     p->max_track_points = 500;  // direct_method_tracker.h:20-28
@@ -139,7 +147,7 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < 2; ++b) {
@@ -643,6 +651,38 @@ int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, c
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, d_status, n, cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(q_rc, d_q, sizeof(float) * 4 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(p_rc, d_p, sizeof(float) * 3 * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FTK_OK;
+}
+
+int ftk_dense_flow_track(ftk_context *ctx, const ftk_dense_flow_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t ref_image,
+                         int32_t cur_image, float *flow_row, float *flow_col, uint32_t flags) {
+    if (!ctx || !params || !ref || !cur || !flow_row || !flow_col) return FTK_ERR_INVALID_ARGUMENT;
+    if (ref->view.levels != cur->view.levels)  // dense_optical_flow.cpp:40
+        return SetError(ctx, FTK_ERR_LEVEL_MISMATCH, "ref has %d levels, cur has %d", ref->view.levels, cur->view.levels);
+    if (ref->view.rows[0] != cur->view.rows[0] || ref->view.cols[0] != cur->view.cols[0])
+        return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "ref and cur pyramids differ in image size");
+    if (ref_image < 0 || ref_image >= ref->view.n_images || cur_image < 0 || cur_image >= cur->view.n_images)
+        return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image %d/%d outside the pyramid batches", ref_image, cur_image);
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS, single = flags & FTK_FLAG_SINGLE_LEVEL;
+    const bool initial = single && !(flags & FTK_FLAG_NO_PREDICTION);
+    const size_t n0 = static_cast<size_t>(ref->view.rows[0]) * ref->view.cols[0];
+    float *d_r = flow_row, *d_c = flow_col;
+    if (!on_device) {
+        if (int rc = EnsureDevice(ctx, ctx->d_flow, sizeof(float) * 2 * n0)) return rc;
+        d_r = static_cast<float *>(ctx->d_flow.ptr);
+        d_c = d_r + n0;
+        if (initial) {
+            FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_r, flow_row, sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->stream));
+            FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_c, flow_col, sizeof(float) * n0, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    if (int rc = ftk::LaunchDenseFlow(ctx, *params, ref->view, cur->view, ref_image, cur_image, single, initial, d_r, d_c)) return rc;
+    if (!on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(flow_row, d_r, sizeof(float) * n0, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(flow_col, d_c, sizeof(float) * n0, cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return FTK_OK;

@@ -61,6 +61,7 @@ struct ftk_context {
     FtkBuffer d_chunk_offsets, d_chunk_curmap;
     FtkBuffer d_back_uv, d_back_status;  // forward-backward pass scratch
     FtkBuffer d_dm_K, d_dm_points, d_dm_q, d_dm_p;  // direct-method staging
+    FtkBuffer d_flow;  // dense-flow staging (2 planes)
     FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
 };
 
@@ -112,6 +113,10 @@ int LaunchKltBasicPooled(ftk_context *ctx, const KltLaunch &launch);
 int LaunchDirectMethod(ftk_context *ctx, const ftk_direct_params &p, const PyramidView &ref, const PyramidView &cur, int n_pairs, const int *d_ref_image,
                        const int *d_cur_image, const int *d_offsets, const float *d_K, const float *d_points, const float2 *d_ref_uv, float2 *d_cur_uv,
                        float *d_q_rc, float *d_p_rc, uint8_t *d_status, int n_features, bool has_prediction, bool has_status);
+
+// dense_flow.cu
+int LaunchDenseFlow(ftk_context *ctx, const ftk_dense_flow_params &p, const PyramidView &ref, const PyramidView &cur, int ref_image, int cur_image,
+                    bool single_level, bool use_initial_flow, float *d_flow_r, float *d_flow_c);
 
 // match.cu
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);

@@ -173,6 +173,23 @@ int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, c
                             const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *K, const float *p_c_in_ref,
                             const float *ref_uv, float *cur_uv, float *q_rc, float *p_rc, uint8_t *status, uint32_t flags);
 
+/* ---- dense optical flow (SURVEY 8(f) "next" row; replaces DenseOpticalFlow::Track, both overloads,
+ *      src/dense_optical_flow_tracker/dense_optical_flow.cpp:7-85) ---------------------------------------------------------
+ * DenseOpticalFlow::Options (dense_optical_flow.h:15-20). */
+typedef struct ftk_dense_flow_params {
+    int32_t max_iteration;     /* kMaxIteration */
+    int32_t half_patch_size;   /* kHalfPatchSize (<= 7 in this build) */
+    float max_converge_step;   /* kMaxConvergeStep */
+    float max_delta_flow_step; /* kMaxDeltaFlowStep */
+} ftk_dense_flow_params;
+void ftk_dense_flow_params_default(ftk_dense_flow_params *params);
+/* Flow from image ref_image of `ref` to image cur_image of `cur`: flow_row / flow_col = rows x cols tightly packed floats (the
+ * reference's flow_rc[0] / flow_rc[1]).  Default: the pyramid overload (coarse to fine over all levels; the flow is an output
+ * only).  FTK_FLAG_SINGLE_LEVEL: the GrayImage overload on level 0; flow_* then are in/out unless FTK_FLAG_NO_PREDICTION says
+ * the caller's matrices have the wrong size (:18-23: start from zero). */
+int ftk_dense_flow_track(ftk_context *ctx, const ftk_dense_flow_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t ref_image,
+                         int32_t cur_image, float *flow_row, float *flow_col, uint32_t flags);
+
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of
  *      test/test_descriptor_matcher_brief.cpp:33-45 and test/test_descriptor_matcher_superpoint.cpp:32-34) --------

@@ -1263,3 +1263,223 @@ int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, c
     for (int32_t l = 0; l < 2 * levels; ++l) free(store[l]);
     return 1;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense optical flow, Gunnar Farneback: src/dense_optical_flow_tracker/dense_optical_flow.cpp.
+ * External: slam_utility::Utility::Interpolate (frozen in oracle/shim/slam_basic_math.h), Eigen 2x2 inverse (basic_type.h).
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    float w[32 * 32]; /* normalised Gaussian kernel, (2h+1)^2 entries */
+    float k2, k4, k22;
+    int32_t half, size;
+} dof_kernel_t;
+
+static void dof_init_kernel(dof_kernel_t *g, int32_t half) { /* :87-137 */
+    g->half = half;
+    g->size = 2 * half + 1;
+    g->k2 = g->k4 = g->k22 = 0.0f;
+    for (int32_t i = 0; i < g->size * g->size; ++i) g->w[i] = 0.0f;
+    if (half == 0) {
+        g->w[0] = 1.0f;
+        return; /* the moments stay 0 */
+    }
+    const float sigma = 1.0f;
+    const float sigma2 = sigma * sigma;
+    float sum = 0.0f;
+    for (int32_t row = 0; row < g->size; ++row)
+        for (int32_t col = 0; col < g->size; ++col) {
+            const int32_t dr = row - half, dc = col - half;
+            g->w[row * g->size + col] = expf(-0.5f * (float)(dr * dr + dc * dc) / sigma2);
+            sum += g->w[row * g->size + col];
+        }
+    for (int32_t i = 0; i < g->size * g->size; ++i) g->w[i] = g->w[i] / sum;
+    for (int32_t row = 0; row < g->size; ++row)
+        for (int32_t col = 0; col < g->size; ++col) {
+            const int32_t dr = row - half, dc = col - half;
+            const float w = g->w[row * g->size + col];
+            g->k2 += w * (float)dr * (float)dr;
+            g->k4 += w * (float)dr * (float)dr * (float)dr * (float)dr;
+            g->k22 += w * (float)dr * (float)dr * (float)dc * (float)dc;
+        }
+}
+
+/* :139-195: six Gaussian-weighted moment maps, planes S0, Srow, Scol, Srowcol, Srowrow, Scolcol of rows*cols floats */
+static void dof_moments(const dof_kernel_t *g, const image_t *im, float *S) {
+    const int32_t rows = im->rows, cols = im->cols, h = g->half;
+    const size_t n = (size_t)rows * cols;
+    for (int32_t row = 0; row < rows; ++row)
+        for (int32_t col = 0; col < cols; ++col) {
+            float s0 = 0.0f, sr = 0.0f, sc = 0.0f, src = 0.0f, srr = 0.0f, scc = 0.0f;
+            for (int32_t dr = -h; dr <= h; ++dr)
+                for (int32_t dc = -h; dc <= h; ++dc) {
+                    int32_t r = row + dr, c = col + dc;
+                    if (r < 0) r = 0;
+                    else if (r >= rows) r = rows - 1;
+                    if (c < 0) c = 0;
+                    else if (c >= cols) c = cols - 1;
+                    const float w = g->w[(dr + h) * g->size + dc + h];
+                    const float val = (float)im->d[r * cols + c];
+                    s0 += val * w;
+                    sr += (float)dr * val * w;
+                    sc += (float)dc * val * w;
+                    src += (float)(dr * dc) * val * w;
+                    srr += (float)(dr * dr) * val * w;
+                    scc += (float)(dc * dc) * val * w;
+                }
+            const size_t i = (size_t)row * cols + col;
+            S[i] = s0, S[n + i] = sr, S[2 * n + i] = sc, S[3 * n + i] = src, S[4 * n + i] = srr, S[5 * n + i] = scc;
+        }
+}
+
+static float dof_interpolate(const float *m, int32_t rows, int32_t cols, float row, float col) { /* shim slam_basic_math.h */
+    const float max_r = (float)(rows - 1), max_c = (float)(cols - 1);
+    const float r = row < 0.0f ? 0.0f : (row > max_r ? max_r : row);
+    const float c = col < 0.0f ? 0.0f : (col > max_c ? max_c : col);
+    const float fr = floorf(r), fc = floorf(c);
+    const int32_t r0 = (int32_t)fr, c0 = (int32_t)fc;
+    const int32_t r1 = r0 + 1 < rows ? r0 + 1 : rows - 1, c1 = c0 + 1 < cols ? c0 + 1 : cols - 1;
+    const float dr = r - fr, dc = c - fc;
+    const float ir = 1.0f - dr, ic = 1.0f - dc;
+    return ir * ic * m[r0 * cols + c0] + ir * dc * m[r0 * cols + c1] + dr * ic * m[r1 * cols + c0] + dr * dc * m[r1 * cols + c1];
+}
+
+/* :259-313 / :315-345: polynomial-expansion coefficients from the six moments */
+static void dof_coefficients(const dof_kernel_t *g, float S0, float Sr, float Sc, float Src, float Srr, float Scc, float *A, float *b) {
+    const float D = g->k4 - g->k2 * g->k2;
+    const float E = g->k22 - g->k2 * g->k2;
+    const float inv_D_plus_E = 1.0f / (D + E + 1e-6f);
+    const float inv_D_minus_E = 1.0f / (D - E + 1e-6f);
+    const float term1 = (Srr + Scc - 2.0f * g->k2 * S0) * inv_D_plus_E;
+    const float term2 = (Srr - Scc) * inv_D_minus_E;
+    const float a = 0.5f * (term1 + term2);
+    const float b_coeff = 0.5f * (term1 - term2);
+    const float c_coeff = Src / (g->k22 + 1e-6f);
+    A[0] = a;
+    A[1] = 0.5f * c_coeff;
+    A[2] = A[1];
+    A[3] = b_coeff;
+    b[0] = Sr / (g->k2 + 1e-6f);
+    b[1] = Sc / (g->k2 + 1e-6f);
+}
+
+/* :197-257 ComputeFlowByPixel */
+static void dof_flow_pixel(const ftko_dense_flow_params *o, const dof_kernel_t *g, const float *S_ref, const float *S_cur, int32_t rows, int32_t cols,
+                           int32_t row, int32_t col, float *flow_r, float *flow_c) {
+    const size_t n = (size_t)rows * cols, i = (size_t)row * cols + col;
+    float A1[4], b1[2];
+    dof_coefficients(g, S_ref[i], S_ref[n + i], S_ref[2 * n + i], S_ref[3 * n + i], S_ref[4 * n + i], S_ref[5 * n + i], A1, b1);
+    for (int32_t iter = 0; iter < o->max_iteration; ++iter) {
+        const float sample_r = (float)row + flow_r[i], sample_c = (float)col + flow_c[i];
+        float A2[4], b2[2];
+        dof_coefficients(g, dof_interpolate(S_cur, rows, cols, sample_r, sample_c), dof_interpolate(S_cur + n, rows, cols, sample_r, sample_c),
+                         dof_interpolate(S_cur + 2 * n, rows, cols, sample_r, sample_c), dof_interpolate(S_cur + 3 * n, rows, cols, sample_r, sample_c),
+                         dof_interpolate(S_cur + 4 * n, rows, cols, sample_r, sample_c), dof_interpolate(S_cur + 5 * n, rows, cols, sample_r, sample_c), A2,
+                         b2);
+        float M[4], bd[2];
+        for (int k = 0; k < 4; ++k) M[k] = ((A1[k] + A2[k]) * 0.5f) * 2.0f; /* A_avg = (A1 + A2) * 0.5; M = A_avg * 2 */
+        bd[0] = b1[0] - b2[0], bd[1] = b1[1] - b2[1];
+        /* MtM = M^T * M, Mtb = M^T * b_diff: r(i,j) = Mt(i,0) M(0,j) + Mt(i,1) M(1,j) */
+        const float m00 = M[0] * M[0] + M[2] * M[2], m01 = M[0] * M[1] + M[2] * M[3];
+        const float m10 = M[1] * M[0] + M[3] * M[2], m11 = M[1] * M[1] + M[3] * M[3];
+        const float t0 = M[0] * bd[0] + M[2] * bd[1], t1 = M[1] * bd[0] + M[3] * bd[1];
+        const float lambda = 0.1f * (m00 + m11) + 1.0f;
+        /* H = MtM + Identity * lambda */
+        const float h00 = m00 + 1.0f * lambda, h01 = m01 + 0.0f * lambda, h10 = m10 + 0.0f * lambda, h11 = m11 + 1.0f * lambda;
+        const float invdet = 1.0f / (h00 * h11 - h10 * h01);
+        const float i00 = h11 * invdet, i10 = -h10 * invdet, i01 = -h01 * invdet, i11 = h00 * invdet;
+        float d0 = i00 * t0 + i01 * t1, d1 = i10 * t0 + i11 * t1;
+        const float step_norm = sqrtf(d0 * d0 + d1 * d1);
+        if (step_norm > o->max_delta_flow_step) {
+            const float sc = o->max_delta_flow_step / step_norm;
+            d0 = d0 * sc, d1 = d1 * sc;
+        }
+        flow_r[i] += d0;
+        flow_c[i] += d1;
+        if (d0 * d0 + d1 * d1 < o->max_converge_step) break;
+    }
+}
+
+static int cmp_float(const void *a, const void *b) {
+    const float x = *(const float *)a, y = *(const float *)b;
+    return (x > y) - (x < y);
+}
+
+/* :347-371 SmoothFlow: 3x3 median with clamped borders */
+static void dof_median(float *flow, int32_t rows, int32_t cols) {
+    float *out = (float *)malloc(sizeof(float) * (size_t)rows * cols);
+    for (int32_t r = 0; r < rows; ++r)
+        for (int32_t c = 0; c < cols; ++c) {
+            float w[9];
+            int k = 0;
+            for (int32_t dr = -1; dr <= 1; ++dr)
+                for (int32_t dc = -1; dc <= 1; ++dc) {
+                    int32_t nr = r + dr, nc = c + dc;
+                    nr = nr < 0 ? 0 : (nr > rows - 1 ? rows - 1 : nr);
+                    nc = nc < 0 ? 0 : (nc > cols - 1 ? cols - 1 : nc);
+                    w[k++] = flow[nr * cols + nc];
+                }
+            qsort(w, 9, sizeof(float), cmp_float);
+            out[r * cols + c] = w[4];
+        }
+    memcpy(flow, out, sizeof(float) * (size_t)rows * cols);
+    free(out);
+}
+
+/* :7-33 Track(GrayImage, GrayImage, flow) */
+static void dof_track_level(const ftko_dense_flow_params *o, const dof_kernel_t *g, const image_t *ref, const image_t *cur, float *flow_r, float *flow_c) {
+    const int32_t rows = ref->rows, cols = ref->cols;
+    const size_t n = (size_t)rows * cols;
+    float *S_ref = (float *)malloc(sizeof(float) * 6 * n), *S_cur = (float *)malloc(sizeof(float) * 6 * n);
+    dof_moments(g, ref, S_ref);
+    dof_moments(g, cur, S_cur);
+    for (int32_t row = 0; row < rows; ++row)
+        for (int32_t col = 0; col < cols; ++col) dof_flow_pixel(o, g, S_ref, S_cur, rows, cols, row, col, flow_r, flow_c);
+    dof_median(flow_r, rows, cols);
+    dof_median(flow_c, rows, cols);
+    free(S_ref);
+    free(S_cur);
+}
+
+int ftko_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                          const int32_t *rows, const int32_t *cols, int32_t single_level, int32_t flow_valid, float *flow_row, float *flow_col) {
+    if (levels < 1 || levels > 16 || params->half_patch_size < 0 || params->half_patch_size > 15) return 0;
+    dof_kernel_t g;
+    dof_init_kernel(&g, params->half_patch_size);
+    image_t ref, cur;
+    if (single_level) { /* :7-33; the moment maps of `cur` must match `ref`: same size is implied by the shared rows / cols */
+        ref.d = ref_levels[0], ref.rows = rows[0], ref.cols = cols[0];
+        cur.d = cur_levels[0], cur.rows = rows[0], cur.cols = cols[0];
+        if (!flow_valid) {
+            memset(flow_row, 0, sizeof(float) * (size_t)rows[0] * cols[0]); /* :18-23 */
+            memset(flow_col, 0, sizeof(float) * (size_t)rows[0] * cols[0]);
+        }
+        dof_track_level(params, &g, &ref, &cur, flow_row, flow_col);
+        return 1;
+    }
+    /* :35-85 coarse to fine */
+    const int32_t top = levels - 1;
+    size_t n = (size_t)rows[top] * cols[top];
+    float *fr = (float *)calloc(n, sizeof(float)), *fc = (float *)calloc(n, sizeof(float));
+    for (int32_t l = top; l >= 0; --l) {
+        ref.d = ref_levels[l], ref.rows = rows[l], ref.cols = cols[l];
+        cur.d = cur_levels[l], cur.rows = rows[l], cur.cols = cols[l];
+        dof_track_level(params, &g, &ref, &cur, fr, fc);
+        if (l == 0) break;
+        const int32_t nr = rows[l - 1], nc = cols[l - 1];
+        float *ur = (float *)malloc(sizeof(float) * (size_t)nr * nc), *uc = (float *)malloc(sizeof(float) * (size_t)nr * nc);
+        for (int32_t r = 0; r < nr; ++r)
+            for (int32_t c = 0; c < nc; ++c) {
+                const float frow = (float)r * 0.5f, fcol = (float)c * 0.5f; /* :72-73 */
+                ur[(size_t)r * nc + c] = dof_interpolate(fr, rows[l], cols[l], frow, fcol) * 2.0f;
+                uc[(size_t)r * nc + c] = dof_interpolate(fc, rows[l], cols[l], frow, fcol) * 2.0f;
+            }
+        free(fr);
+        free(fc);
+        fr = ur, fc = uc;
+    }
+    memcpy(flow_row, fr, sizeof(float) * (size_t)rows[0] * cols[0]);
+    memcpy(flow_col, fc, sizeof(float) * (size_t)rows[0] * cols[0]);
+    free(fr);
+    free(fc);
+    return 1;
+}

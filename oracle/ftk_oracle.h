@@ -61,6 +61,10 @@ int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, c
                              const int32_t *rows, const int32_t *cols, const float *K, int32_t n, const float *p_c_in_ref, const float *ref_uv,
                              float *cur_uv, int32_t cur_uv_count, float *q_rc, float *p_rc, uint8_t *status, int32_t status_count);
 
+/* dense_optical_flow.cpp:7-85 DenseOpticalFlow::Track; flow_* = rows[0] x cols[0] floats (row / column flow component). */
+int ftko_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                          const int32_t *rows, const int32_t *cols, int32_t single_level, int32_t flow_valid, float *flow_row, float *flow_col);
+
 void ftko_ldlt_solve(int32_t n, const float *a, const float *b, float *x);
 
 #ifdef __cplusplus

@@ -34,4 +34,12 @@ typedef struct ftko_direct_params {
     int32_t method;              /* DirectMethodMethod: 0 kInverse, 1 kDirect (default), 2 kFast; only kDirect does work upstream */
 } ftko_direct_params;
 
+/* DenseOpticalFlow::Options (src/dense_optical_flow_tracker/dense_optical_flow.h:15-20); same layout as ftk_dense_flow_params. */
+typedef struct ftko_dense_flow_params {
+    int32_t max_iteration;     /* kMaxIteration = 10 */
+    int32_t half_patch_size;   /* kHalfPatchSize = 2 */
+    float max_converge_step;   /* kMaxConvergeStep = 1e-6 */
+    float max_delta_flow_step; /* kMaxDeltaFlowStep = 1.0 */
+} ftko_dense_flow_params;
+
 #endif

@@ -64,6 +64,18 @@ def make_direct_params(half=6, half_col=None, max_points=500, max_iter=15, conve
     return p
 
 
+class DenseFlowParams(C.Structure):
+    """ftko_dense_flow_params == DenseOpticalFlow::Options (src/dense_optical_flow_tracker/dense_optical_flow.h:15-20)."""
+
+    _fields_ = [("max_iteration", C.c_int32), ("half_patch_size", C.c_int32), ("max_converge_step", C.c_float), ("max_delta_flow_step", C.c_float)]
+
+
+def make_dense_flow_params(max_iter=10, half=2, converge=1e-6, max_step=1.0):
+    p = DenseFlowParams()
+    p.max_iteration, p.half_patch_size, p.max_converge_step, p.max_delta_flow_step = max_iter, half, converge, max_step
+    return p
+
+
 def make_params(variant="basic", method="fast", half=6, half_col=None, max_points=500, max_iter=15, max_large=3,
                 converge=4e-2, predict=(1.0, 0.0, 0.0, 1.0), luminance=False):
     """Defaults are the reference's OpticalFlowOptions defaults (optical_flow.h:20-28)."""
@@ -214,6 +226,28 @@ class _CpuChecker:
         ok = self._fn("direct_method_track")(C.byref(params), C.c_int32(levels), rp, cp, _i32p(rows), _i32p(cols), _f32p(Kc), C.c_int32(n), _f32p(pts),
                                               _f32p(ref_uv), _f32p(cur_buf), C.c_int32(cur_count), _f32p(q), _f32p(p), _u8p(st_buf), C.c_int32(st_count))
         return ok == 1, cur_buf[:n].copy(), q, p, st_buf[:n].copy()
+
+    def dense_flow_track(self, params, ref_levels, cur_levels, single_level=False, flow=None):
+        """DenseOpticalFlow::Track (dense_optical_flow.cpp:7-85).  flow = (flow_row, flow_col) initial content for the single-level
+        overload (None = matrices of the wrong size).  Returns (ok, flow_row, flow_col), each rows x cols float32."""
+        levels = len(ref_levels)
+        ref_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in ref_levels]
+        cur_levels = [np.ascontiguousarray(a, dtype=np.uint8) for a in cur_levels]
+        rows = np.array([a.shape[0] for a in ref_levels], dtype=np.int32)
+        cols = np.array([a.shape[1] for a in ref_levels], dtype=np.int32)
+        PtrArr = C.POINTER(C.c_uint8) * levels
+        rp = PtrArr(*[_u8p(a) for a in ref_levels])
+        cp = PtrArr(*[_u8p(a) for a in cur_levels])
+        fr = np.zeros((rows[0], cols[0]), np.float32)
+        fc = np.zeros((rows[0], cols[0]), np.float32)
+        valid = 0
+        if flow is not None:
+            fr[:] = flow[0]
+            fc[:] = flow[1]
+            valid = 1
+        ok = self._fn("dense_flow_track")(C.byref(params), C.c_int32(levels), rp, cp, _i32p(rows), _i32p(cols), C.c_int32(1 if single_level else 0),
+                                           C.c_int32(valid), _f32p(fr), _f32p(fc))
+        return ok == 1, fr, fc
 
     def pyramid_and_track(self, params, levels, ref_image, cur_image, ref_uv):
         ref_image = np.ascontiguousarray(ref_image, dtype=np.uint8)

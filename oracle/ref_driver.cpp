@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "descriptor_matcher.h"
+#include "dense_optical_flow.h"
 #include "direct_method_tracker.h"
 #include "optical_flow_affine_klt.h"
 #include "optical_flow_basic_klt.h"
@@ -346,6 +347,44 @@ int ftkref_direct_method_track_world(const ftko_direct_params *params, int32_t l
     }
     cur_q_wc[0] = q_cur.w(), cur_q_wc[1] = q_cur.x(), cur_q_wc[2] = q_cur.y(), cur_q_wc[3] = q_cur.z();
     cur_p_wc[0] = p_cur(0), cur_p_wc[1] = p_cur(1), cur_p_wc[2] = p_cur(2);
+    return 1;
+}
+
+// DenseOpticalFlow::Track (dense_optical_flow.cpp:7-85).  single_level != 0: the GrayImage overload on level 0, with
+// flow_row / flow_col as in/out (flow_valid == 0 = the caller's matrices have the wrong size, i.e. start from zero);
+// otherwise the pyramid overload (the flow is an output only).  flow_* are rows[0] x cols[0] row-major.
+int ftkref_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
+                            const int32_t *rows, const int32_t *cols, int32_t single_level, int32_t flow_valid, float *flow_row, float *flow_col) {
+    feature_tracker::DenseOpticalFlow solver;
+    solver.options().kMaxIteration = params->max_iteration;
+    solver.options().kHalfPatchSize = params->half_patch_size;
+    solver.options().kMaxConvergeStep = params->max_converge_step;
+    solver.options().kMaxDeltaFlowStep = params->max_delta_flow_step;
+    PaddedLevels ref_store, cur_store;
+    ref_store.Adopt(levels, ref_levels, rows, cols);
+    cur_store.Adopt(levels, cur_levels, rows, cols);
+    std::array<Mat, 2> flow;
+    const size_t n0 = static_cast<size_t>(rows[0]) * cols[0];
+    bool ok;
+    if (single_level) {
+        if (flow_valid) {
+            flow[0].resize(rows[0], cols[0]);
+            flow[1].resize(rows[0], cols[0]);
+            std::copy(flow_row, flow_row + n0, flow[0].v.begin());
+            std::copy(flow_col, flow_col + n0, flow[1].v.begin());
+        }
+        GrayImage ref_image(ref_store.ptr[0], rows[0], cols[0]);
+        GrayImage cur_image(cur_store.ptr[0], rows[0], cols[0]);
+        ok = solver.Track(ref_image, cur_image, flow);
+    } else {
+        ImagePyramid ref_pyr, cur_pyr;
+        ref_pyr.SetLevels(levels, ref_store.ptr.data(), rows, cols);
+        cur_pyr.SetLevels(levels, cur_store.ptr.data(), rows, cols);
+        ok = solver.Track(ref_pyr, cur_pyr, flow);
+    }
+    if (!ok) return 0;
+    std::copy(flow[0].v.begin(), flow[0].v.end(), flow_row);
+    std::copy(flow[1].v.begin(), flow[1].v.end(), flow_col);
     return 1;
 }
 

@@ -221,6 +221,25 @@ struct Mat {
 
     ArrayView<R, C> array() const { return ArrayView<R, C>{*this}; }
     Ldlt<R> ldlt() const;
+
+    // dense_optical_flow.cpp:216-218.  trace(): d00 + d11 + ...; inverse() of a 2x2 restates Eigen's
+    // compute_inverse_size2_helper: invdet = 1 / (a*d - b*c); [d, -b; -c, a] * invdet.
+    float trace() const {
+        static_assert(R == C, "trace needs a square matrix");
+        float s = d[0][0];
+        for (int i = 1; i < R; ++i) s = s + d[i][i];
+        return s;
+    }
+    Mat inverse() const {
+        static_assert(R == 2 && C == 2, "only the 2x2 inverse is used");
+        const float invdet = 1.0f / (d[0][0] * d[1][1] - d[1][0] * d[0][1]);
+        Mat r;
+        r.d[0][0] = d[1][1] * invdet;
+        r.d[1][0] = -d[1][0] * invdet;
+        r.d[0][1] = -d[0][1] * invdet;
+        r.d[1][1] = d[0][0] * invdet;
+        return r;
+    }
 };
 
 // Restatement of Eigen 3.3/3.4 LDLT<MatrixType, Lower>: in-place unblocked
@@ -378,6 +397,31 @@ struct Quat {
     }
 };
 
+// Dynamic float matrix (Slam_Utility's `Mat` = Eigen::MatrixXf; dense_optical_flow.cpp only): setZero / resize / element
+// access / rows / cols / scalar division.  Storage order does not matter to any result.
+struct MatDyn {
+    std::vector<float> v;
+    int r = 0, c = 0;
+    void setZero(int rows, int cols) {
+        r = rows;
+        c = cols;
+        v.assign(static_cast<size_t>(rows) * cols, 0.0f);
+    }
+    void resize(int rows, int cols) {
+        r = rows;
+        c = cols;
+        v.resize(static_cast<size_t>(rows) * cols);
+    }
+    int rows() const { return r; }
+    int cols() const { return c; }
+    float &operator()(int i, int j) { return v[static_cast<size_t>(i) * c + j]; }
+    const float &operator()(int i, int j) const { return v[static_cast<size_t>(i) * c + j]; }
+    MatDyn &operator/=(float s) {
+        for (float &x : v) x = x / s;
+        return *this;
+    }
+};
+
 // Dynamic int matrix (only setConstant + element access are used, lssd_klt.cpp:136-137).
 struct MatIntDyn {
     std::vector<int32_t> v;
@@ -418,5 +462,6 @@ using Quat = shim::Quat;
 // Slam_Utility's "treat as zero" threshold (direct_method_tracker.cpp:129,140 depth tests).  Frozen here, like the rest of the shim.
 constexpr float kZeroFloat = 1e-6f;
 using MatInt = shim::MatIntDyn;
+using Mat = shim::MatDyn;
 
 #endif

@@ -58,6 +58,7 @@ public:
     }
 
     uint32_t level() const { return level_; }
+    uint8_t *data() const { return images_[0].data(); }  // dense_optical_flow.cpp:38-39 only tests it against nullptr
     const GrayImage &GetImageConst(uint32_t i) const { return images_[i]; }
     GrayImage &GetImage(uint32_t i) { return images_[i]; }
 

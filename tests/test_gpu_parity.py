@@ -577,6 +577,34 @@ def test_direct_method_batch_of_pairs(ctx, oracle):
         assert_pose_same(f"pair {i}", (True, cur_uv[sl], q[i], p[i], st[sl]), exp)
 
 
+@pytest.mark.parametrize("shape,levels,single", [((96, 131), 3, False), ((120, 160), 1, True), ((240, 320), 4, False), ((37, 53), 2, False)])
+def test_dense_flow_vs_oracle(ctx, oracle, shape, levels, single):
+    """SURVEY 8(f) rank 4: ftk_dense_flow_track == DenseOpticalFlow::Track of the reference, bit for bit (both overloads, several
+    Gaussian windows, initial flow for the GrayImage overload)."""
+    rows, cols = shape
+    ref, cur, _, _ = S.make_pair(rows, cols, 10, pair_id=5 + levels)
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    rl, cl = oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels)
+    dof = ft.DenseOpticalFlow(ctx)
+    for half in (2, 1, 0, 3):
+        dof.options().kHalfPatchSize = half
+        prm = po.make_dense_flow_params(half=half)
+        flows = [None]
+        if single:
+            rng = np.random.default_rng(half)
+            flows.append((rng.normal(0, 1, ref.shape).astype(np.float32), rng.normal(0, 1, ref.shape).astype(np.float32)))
+        for flow in flows:
+            ok, fr, fc = dof.Track(pyr, pyr, flow_rc=flow, single_level=single, ref_image=0, cur_image=1)
+            eok, er, ec = oracle.dense_flow_track(prm, rl, cl, single_level=single, flow=flow)
+            assert ok and eok
+            for got, exp, name in ((fr, er, "row"), (fc, ec, "col")):
+                bad = np.argwhere(got.view(np.uint32) != exp.view(np.uint32))
+                assert bad.size == 0, f"half={half} {name} flow differs at {bad[:5].tolist()}: gpu {got[tuple(bad[0])]} oracle {exp[tuple(bad[0])]}"
+    assert np.abs(er).mean() > 0.2
+
+
 def lightglue_like_scores(n_ref, n_cur, seed):
     """Log-assignment-like matrix: a planted partial permutation of strong scores over weak background, ties, -inf, NaN."""
     rng = np.random.default_rng(seed)

@@ -286,3 +286,22 @@ def test_direct_method_world_frame_algebra(oracle, reflib):
     assert bits_equal(quat.multiply(ref_q, q), exp[2]) and bits_equal(quat.rotate(ref_q, p) + ref_p, exp[3])
     assert bits_equal(cu, exp[1]) and np.array_equal(st, exp[4])
 
+
+@pytest.mark.parametrize("levels,single", [(3, False), (1, True), (4, False)])
+def test_dense_flow_restatement_vs_reference_build(oracle, reflib, levels, single):
+    """SURVEY 8(f) rank 4: the C restatement of DenseOpticalFlow::Track equals the reference's own dense_optical_flow.cpp compiled in
+    place, bit for bit, for several Gaussian window sizes, both overloads, with and without an initial flow."""
+    ref, cur, _, _ = S.make_pair(96, 131, 10, pair_id=5)
+    rl, cl = oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels)
+    for half in (2, 1, 0, 3):
+        prm = po.make_dense_flow_params(half=half)
+        flows = [None]
+        if single:
+            rng = np.random.default_rng(half)
+            flows.append((rng.normal(0, 1, ref.shape).astype(np.float32), rng.normal(0, 1, ref.shape).astype(np.float32)))
+        for flow in flows:
+            a = oracle.dense_flow_track(prm, rl, cl, single_level=single, flow=flow)
+            b = reflib.dense_flow_track(prm, rl, cl, single_level=single, flow=flow)
+            assert a[0] and b[0] and bits_equal(a[1], b[1]) and bits_equal(a[2], b[2]), (half, flow is not None)
+    assert np.abs(a[1]).mean() > 0.3  # there is motion in the pair
+
