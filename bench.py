@@ -343,6 +343,19 @@ def run_extras(ctx, L, torch, local_rank, steps):
                                                      "pose_translation_of_pair_0": [float(x) for x in d_p[0].cpu().numpy()]}
     pyr_dm.close()
 
+    # ---- dense optical flow: Farneback, 752x480, 4 levels, reference defaults ----
+    pair0 = S.make_pair(ROWS, COLS, 10, pair_id=300)
+    pyr_df = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, 2)
+    pyr_df.SetRawImages(np.stack([pair0[0], pair0[1]]))
+    pyr_df.CreateImagePyramid()
+    d_fr = torch.empty((ROWS, COLS), dtype=torch.float32, device=dev)
+    d_fc = torch.empty_like(d_fr)
+    fprm = ft.DenseOpticalFlow(ctx)._params()
+    ms = timeit(lambda: ctx.check(L.ftk_dense_flow_track(ctx._h, C.byref(fprm), pyr_df._h, pyr_df._h, 0, 1, vp(d_fr.data_ptr()), vp(d_fc.data_ptr()),
+                                                         _capi.FLAG_DEVICE_POINTERS)), steps * 2)
+    out["dense_flow_752x480_4_levels"] = {"ms": ms, "pixels_per_s": ROWS * COLS / (ms * 1e-3), "mean_abs_flow_px": float(d_fr.abs().mean().item())}
+    pyr_df.close()
+
     # ---- score-matrix mutual arg-max (NNFeatureMatcher post-processing): HBM bound, 4 B per matrix element ----
     for n in (2048, 12288):  # LightGlue's usual size (16 MB, L2 resident) and a matrix far larger than L2 (604 MB)
         d_s = torch.randn((n, n), dtype=torch.float32, device=dev) * 2.0 - 6.0

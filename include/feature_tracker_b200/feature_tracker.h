@@ -460,6 +460,51 @@ private:
     DirectMethodOptions options_;
 };
 
+// src/dense_optical_flow_tracker/dense_optical_flow.h:12-65 (Gunnar Farneback).  The reference's flow type is Slam_Utility's
+// `Mat` (Eigen::MatrixXf, absent here): the facade hands the two flow components back as rows x cols row-major float vectors.
+class DenseOpticalFlow {
+public:
+    struct Options {
+        int32_t kMaxIteration = 10;
+        int32_t kHalfPatchSize = 2;
+        float kMaxConvergeStep = 1e-6f;
+        float kMaxDeltaFlowStep = 1.0f;
+    };
+    DenseOpticalFlow() = default;
+    virtual ~DenseOpticalFlow() = default;
+
+    // dense_optical_flow.cpp:35-85: coarse to fine over the pyramids; flow_rc[0] = row component, flow_rc[1] = column component
+    bool Track(const ImagePyramid &ref_pyramid, const ImagePyramid &cur_pyramid, std::array<std::vector<float>, 2> &flow_rc) {
+        return Run(ref_pyramid, cur_pyramid, flow_rc, 0u);
+    }
+    // dense_optical_flow.cpp:7-33 (the GrayImage overload): level 0 only; flow_rc of the image's size is the initial flow
+    bool TrackSingleLevel(const ImagePyramid &ref_image, const ImagePyramid &cur_image, std::array<std::vector<float>, 2> &flow_rc) {
+        return Run(ref_image, cur_image, flow_rc, FTK_FLAG_SINGLE_LEVEL);
+    }
+    std::string OpticalFlowMethodName() const { return "Gunnar Farneback"; }
+    Options &options() { return options_; }
+    const Options &options() const { return options_; }
+
+private:
+    bool Run(const ImagePyramid &ref, const ImagePyramid &cur, std::array<std::vector<float>, 2> &flow_rc, uint32_t flags) {
+        if (!ref.handle() || !cur.handle()) return false;  // :9-10, :38-39
+        if (ref.level() != cur.level()) return false;       // :40
+        const size_t n = static_cast<size_t>(ref.rows()) * ref.cols();
+        if (flow_rc[0].size() != n || flow_rc[1].size() != n) {  // :18-23
+            flow_rc[0].assign(n, 0.0f);
+            flow_rc[1].assign(n, 0.0f);
+            flags |= FTK_FLAG_NO_PREDICTION;
+        }
+        ftk_dense_flow_params p;
+        p.max_iteration = options_.kMaxIteration;
+        p.half_patch_size = options_.kHalfPatchSize;
+        p.max_converge_step = options_.kMaxConvergeStep;
+        p.max_delta_flow_step = options_.kMaxDeltaFlowStep;
+        return ftk_dense_flow_track(Device::Get(), &p, ref.handle(), cur.handle(), 0, 0, flow_rc[0].data(), flow_rc[1].data(), flags) == FTK_OK;
+    }
+    Options options_;
+};
+
 }  // namespace feature_tracker
 
 #endif

@@ -118,6 +118,15 @@ int main(int argc, char **argv) {
         }
         fwrite(st.data(), 1, n, out);
     }
+    // Dense optical flow, as in test_dense_optical_flow.cpp
+    {
+        DenseOpticalFlow dense;
+        std::array<std::vector<float>, 2> flow_rc;
+        okv = dense.Track(ref_pyramid, cur_pyramid, flow_rc) ? 1 : 0;
+        fwrite(&okv, sizeof(okv), 1, out);
+        fwrite(flow_rc[0].data(), sizeof(float), flow_rc[0].size(), out);
+        fwrite(flow_rc[1].data(), sizeof(float), flow_rc[1].size(), out);
+    }
     fclose(in);
     fclose(out);
     return 0;

@@ -27,7 +27,7 @@ def test_facade_compiles_and_links(tmp_path):
     text = open(os.path.join(ROOT, "include", "feature_tracker_b200", "feature_tracker.h")).read()
     for name in ["namespace feature_tracker", "enum class TrackStatus", "struct OpticalFlowOptions", "class OpticalFlowBasicKlt", "class OpticalFlowAffineKlt",
                  "class OpticalFlowLssdKlt", "class DescriptorMatcher", "predict_affine", "predict_R_cr", "consider_patch_luminance", "ForceMatch",
-                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber", "class DirectMethod", "struct DirectMethodOptions"]:
+                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber", "class DirectMethod", "struct DirectMethodOptions", "class DenseOpticalFlow"]:
         assert name in text, name
 
 
@@ -85,4 +85,10 @@ def test_facade_matches_oracle(tmp_path, oracle):
     assert ok == 1 and eok and (dst == est).all()
     assert (q.view(np.uint32) == eq.view(np.uint32)).all() and (pr.view(np.uint32) == ep.view(np.uint32)).all()
     assert (duv.view(np.uint32) == euv.view(np.uint32)).all()
+    # dense optical flow through the facade
+    ok = take(np.int32, 1)[0]
+    fr = take(np.float32, rows * cols).reshape(rows, cols)
+    fc = take(np.float32, rows * cols).reshape(rows, cols)
+    eok, er, ec = oracle.dense_flow_track(po.make_dense_flow_params(), rl, cl)
+    assert ok == 1 and eok and (fr.view(np.uint32) == er.view(np.uint32)).all() and (fc.view(np.uint32) == ec.view(np.uint32)).all()
 
