@@ -366,6 +366,36 @@ def run_extras(ctx, L, torch, local_rank, steps):
     return out
 
 
+def cpu_extras(out):
+    """Single-thread CPU figures of the reference (oracle/_ref; the C restatement for the mutual scores) on bounded samples of the
+    secondary workloads (2k x 2k sub-problems for the matchers), written next to the GPU figures."""
+    from feature_tracker_b200 import synthetic as S
+    from oracle import pyoracle as po
+    lib_cpu, kind = cpu_checker()
+
+    def clock(fn):
+        t0 = time.perf_counter()
+        fn()
+        return time.perf_counter() - t0
+
+    rb, cb, _, _, _ = S.make_brief_sets(2000, 2000, seed=99)
+    dt = clock(lambda: lib_cpu.match_brief_force(rb, cb, 60.0))
+    out["C4_brief256_force_10k_x_10k"]["cpu_reference"] = {"pairs_per_s": 4e6 / dt, "sample": "2000 x 2000, 1 thread", "kind": kind}
+    rf, cf = S.make_float_sets(2000, 2000, seed=5)
+    dt = clock(lambda: lib_cpu.match_cosine_force(rf, cf, 0.1))
+    out["C5_float256_force_20k_x_20k"]["cpu_reference"] = {"pairs_per_s": 4e6 / dt, "sample": "2000 x 2000, 1 thread", "kind": kind}
+    ref, cur, uv, K, pts = S.make_direct_method_scene(ROWS, COLS, 300, pair_id=200)
+    rl, cl = lib_cpu.pyramid_build(ref, LEVELS), lib_cpu.pyramid_build(cur, LEVELS)
+    dt = clock(lambda: lib_cpu.direct_method_track(po.make_direct_params(), rl, cl, K, pts, uv, [1, 0, 0, 0], [0, 0, 0]))
+    out["direct_method_600_pairs_x_300_features"]["cpu_reference"] = {"pairs_per_s": 1.0 / dt, "sample": "1 frame pair x 300 features, 1 thread", "kind": kind}
+    dt = clock(lambda: lib_cpu.dense_flow_track(po.make_dense_flow_params(), rl, cl))
+    out["dense_flow_752x480_4_levels"]["cpu_reference"] = {"pixels_per_s": ROWS * COLS / dt, "sample": "1 frame pair, 1 thread", "kind": kind}
+    scores = (np.random.default_rng(1).normal(-6, 2, (2048, 2048))).astype(np.float32)
+    oc = po.OracleLib()
+    dt = clock(lambda: oc.mutual_scores(scores, -3.0))
+    out["mutual_scores_2048x2048"]["cpu_reference"] = {"ms": dt * 1e3, "sample": "2048 x 2048, 1 thread", "kind": "port"}
+
+
 def oracle_trace(oracle, cparams, refs, curs, uvs, u, n_feat):
     """The oracle's results and per-feature patch-iteration counts (SURVEY 8(d) unit) for unique pair u."""
     rl, cl = oracle.pyramid_build(refs[u], LEVELS), oracle.pyramid_build(curs[u], LEVELS)
@@ -670,6 +700,8 @@ def run_b200(args):
     if not args.no_extras and world == 1:
         try:
             line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps)
+            if not args.no_cpu_baseline:
+                cpu_extras(line["other_workloads"])
         except Exception as e:  # the headline must survive a failure in the extras
             line["other_workloads"] = {"error": repr(e)}
     print(json.dumps(line))

@@ -107,6 +107,18 @@ def main():
         print(f"direct method frame {i}: q_rc = {q}, p_rc = {p}, inside = {int((st == 1).sum())}")
     np.savez_compressed(os.path.join(HERE, "direct_method_golden.npz"), **d)
 
+    # ---- dense optical flow on the reference's EuRoC fixture pair (the committed images of euroc_klt_golden.npz) ---------------
+    ok, fr, fc = R.dense_flow_track(po.make_dense_flow_params(), rl, cl)  # reference defaults, 4 levels (test_dense_optical_flow.cpp)
+    assert ok
+    import hashlib
+    df = {"flow_row_8": fr[::8, ::8].copy(), "flow_col_8": fc[::8, ::8].copy(),
+          "sha256": np.frombuffer(hashlib.sha256(fr.tobytes() + fc.tobytes()).digest(), np.uint8).copy()}
+    ok, fr1, fc1 = R.dense_flow_track(po.make_dense_flow_params(half=1, max_iter=4), rl[:1], cl[:1], single_level=True)
+    df["single_h1_row_8"], df["single_h1_col_8"] = fr1[::8, ::8].copy(), fc1[::8, ::8].copy()
+    df["single_h1_sha256"] = np.frombuffer(hashlib.sha256(fr1.tobytes() + fc1.tobytes()).digest(), np.uint8).copy()
+    np.savez_compressed(os.path.join(HERE, "dense_flow_golden.npz"), **df)
+    print("dense_flow_golden.npz: mean |flow| =", float(np.abs(fr).mean()), float(np.abs(fc).mean()))
+
 
 if __name__ == "__main__":
     main()

@@ -605,6 +605,21 @@ def test_dense_flow_vs_oracle(ctx, oracle, shape, levels, single):
     assert np.abs(er).mean() > 0.2
 
 
+def test_dense_flow_matches_golden(ctx, euroc_golden):
+    """The CUDA path against the committed outputs of the reference itself on its own EuRoC fixture pair (752x480, 4 levels)."""
+    import os
+    from conftest import GOLDEN
+    from test_oracle import _check_dense_flow_golden
+    g = dict(np.load(os.path.join(GOLDEN, "dense_flow_golden.npz")))
+
+    def track(rl, cl, prm, single):
+        pyr = upload_levels(ctx, [rl, cl])
+        dof = ft.DenseOpticalFlow(ctx)
+        dof.options().kHalfPatchSize, dof.options().kMaxIteration = prm.half_patch_size, prm.max_iteration
+        return dof.Track(pyr, pyr, single_level=single, ref_image=0, cur_image=1)
+    _check_dense_flow_golden(track, g, euroc_golden)
+
+
 def lightglue_like_scores(n_ref, n_cur, seed):
     """Log-assignment-like matrix: a planted partial permutation of strong scores over weak background, ties, -inf, NaN."""
     rng = np.random.default_rng(seed)

@@ -305,3 +305,25 @@ def test_dense_flow_restatement_vs_reference_build(oracle, reflib, levels, singl
             assert a[0] and b[0] and bits_equal(a[1], b[1]) and bits_equal(a[2], b[2]), (half, flow is not None)
     assert np.abs(a[1]).mean() > 0.3  # there is motion in the pair
 
+
+def _check_dense_flow_golden(track, g_flow, g_img):
+    """`track(levels_ref, levels_cur, params, single)` -> (ok, flow_row, flow_col); compared with the reference's committed outputs."""
+    import hashlib
+    levels = int(g_img["levels"])
+    rl = [g_img["ref"]] + [g_img[f"ref_l{l}"] for l in range(1, levels)]
+    cl = [g_img["cur"]] + [g_img[f"cur_l{l}"] for l in range(1, levels)]
+    for prm, single, key in ((po.make_dense_flow_params(), False, ""), (po.make_dense_flow_params(half=1, max_iter=4), True, "single_h1_")):
+        ok, fr, fc = track(rl[:1] if single else rl, cl[:1] if single else cl, prm, single)
+        assert ok
+        row_key, col_key = ("flow_row_8", "flow_col_8") if not single else ("single_h1_row_8", "single_h1_col_8")
+        assert bits_equal(fr[::8, ::8], g_flow[row_key]) and bits_equal(fc[::8, ::8], g_flow[col_key])
+        digest = np.frombuffer(hashlib.sha256(fr.tobytes() + fc.tobytes()).digest(), np.uint8)
+        assert np.array_equal(digest, g_flow[key + "sha256"])
+
+
+def test_dense_flow_matches_golden(oracle, euroc_golden):
+    """The restatement against outputs of the reference itself on its own EuRoC fixture pair (every 8th flow vector + a SHA-256 of
+    the full field)."""
+    g = dict(np.load(os.path.join(GOLDEN, "dense_flow_golden.npz")))
+    _check_dense_flow_golden(lambda rl, cl, prm, single: oracle.dense_flow_track(prm, rl, cl, single_level=single), g, euroc_golden)
+
