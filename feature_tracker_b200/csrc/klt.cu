@@ -947,7 +947,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
                     ok = PxChecked(cur, row_j, col_j, &value);
                     if (!ok) value = 0.0f;
                 } else {
-                    value = PxF(cur, row_j, col_j);
+                    value = PxFUnchecked(cur, row_j, col_j);
                     ok = true;
                 }
                 c.s.curp[k] = value;

@@ -70,6 +70,31 @@ __device__ __forceinline__ float PxF(const Img &im, float row, float col) {
     return fadd(fadd(fadd(fmul(fmul(ic, ir), p00), fmul(fmul(sc, ir), p01)), fmul(fmul(ic, sr), p10)), fmul(fmul(sc, sr), p11));
 }
 
+// GrayImage::GetPixelValueNoCheck(float, float) at a position that nobody bounds-checked (lssd_klt_fast.cpp:182-193: the
+// "patch totally inside" test looks at the un-rotated bounding box only, so a diverged R_cr sends samples anywhere).  The
+// reference then reads data[(int)row * cols + (int)col + {0, 1, cols, cols + 1}] from its tightly packed image: inside the
+// image that wraps into neighbouring rows, outside it is undefined behaviour (garbage or a crash).  Here: positions whose 2x2
+// footprint is inside take the normal path; the others reproduce the linear addressing for indices inside the image and read
+// 0 elsewhere -- never an address outside the pyramid.
+__device__ __forceinline__ float PxFUnchecked(const Img &im, float row, float col) {
+    const int r = __float2int_rz(row), c = __float2int_rz(col);  // static_cast<int32_t>: truncation
+    if (row >= 0.0f && col >= 0.0f && r < im.rows - 1 && c < im.cols - 1) return PxF(im, row, col);
+    const float sr = fsub(row, floorf(row)), sc = fsub(col, floorf(col));
+    const float ir = fsub(1.0f, sr), ic = fsub(1.0f, sc);
+    const long long n = static_cast<long long>(im.rows) * im.cols, base = static_cast<long long>(r) * im.cols + c;
+    float p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const long long l = base + (q & 1) + (q >> 1) * im.cols;
+        p[q] = 0.0f;
+        if (l >= 0 && l < n) {
+            const int rr = static_cast<int>(l / im.cols), cc = static_cast<int>(l - static_cast<long long>(rr) * im.cols);
+            p[q] = PxToFloat(im.p + rr * im.pitch + cc);
+        }
+    }
+    return fadd(fadd(fadd(fmul(fmul(ic, ir), p[0]), fmul(fmul(sc, ir), p[1])), fmul(fmul(ic, sr), p[2])), fmul(fmul(sc, sr), p[3]));
+}
+
 // GrayImage::GetPixelValue(float,float,float*): fails iff outside [0, cols-1] x [0, rows-1].
 __device__ __forceinline__ bool PxInside(const Img &im, float row, float col) {
     return !(col < 0.0f || row < 0.0f || col > static_cast<float>(im.cols - 1) || row > static_cast<float>(im.rows - 1));
