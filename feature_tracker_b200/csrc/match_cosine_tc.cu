@@ -96,6 +96,7 @@ __device__ __forceinline__ void UmmaCommit(uint64_t *bar) {
 __device__ __forceinline__ void TcFenceBefore() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void TcFenceAfter() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Asynchronous: pair with TmemLoadWait() before the registers are read.
 __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -106,7 +107,17 @@ __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
           "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// The registers of every tcgen05.ld issued before this point are valid afterwards.  `r` is threaded through the statement as
+// in/out operands so that no use of the loaded values can be scheduled ahead of the wait.
+__device__ __forceinline__ void TmemLoadWait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]),
+                   "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]),
+                   "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]),
+                   "+r"(r[31])
+                 :
+                 : "memory");
 }
 
 // Shared-memory matrix descriptor for a K-major, 128B-swizzled operand tile ([rows][64 bf16], 8-row groups 1024 B
@@ -131,21 +142,25 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 // unit-normalised BF16 copy.  32 descriptors per block: rows are staged through shared memory so global reads and writes are
 // coalesced while each row's sum of squares is still accumulated by one thread in ascending k.
 constexpr int kPrepRows = 32;
-constexpr int kPrepThreads = 128;
+constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *desc, int n, int dim, int k_pad, float *norm, __nv_bfloat16 *unit) {
     extern __shared__ float prep_smem[];  // [kPrepRows][dim + 1] + [kPrepRows]
     const int stride = dim + 1;
     float *s_norm = prep_smem + kPrepRows * stride;
     const int row0 = blockIdx.x * kPrepRows;
     const int rows = min(kPrepRows, n - row0);
-    for (int t = threadIdx.x; t < rows * dim; t += kPrepThreads) {
-        const int r = t / dim, k = t - r * dim;
-        prep_smem[r * stride + k] = __ldg(desc + static_cast<size_t>(row0) * dim + t);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp w moves rows w, w + 8, ...; lane = column within a 32-wide group (coalesced, no index arithmetic beyond adds)
+    for (int r = warp; r < rows; r += kPrepThreads / 32) {
+        const float *src = desc + static_cast<size_t>(row0 + r) * dim;
+        float *dst = prep_smem + r * stride;
+        for (int k = lane; k < dim; k += 32) dst[k] = __ldg(src + k);
     }
     __syncthreads();
     if (threadIdx.x < rows) {
         const float *a = prep_smem + threadIdx.x * stride;
         float s = __fmul_rn(a[0], a[0]);
+#pragma unroll 8
         for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
         const float nrm = __fsqrt_rn(s);
         norm[row0 + threadIdx.x] = nrm;
@@ -153,16 +168,17 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *desc
         s_norm[threadIdx.x] = (nrm > 0.0f && isfinite(nrm)) ? nrm : __int_as_float(0x7FC00000);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < rows * k_pad; t += kPrepThreads) {
-        const int r = t / k_pad, k = t - r * k_pad;
-        const float v = k < dim ? prep_smem[r * stride + k] / s_norm[r] : 0.0f;  // x / NaN = NaN
-        unit[static_cast<size_t>(row0) * k_pad + t] = __float2bfloat16_rn(v);
+    for (int r = warp; r < rows; r += kPrepThreads / 32) {
+        const float *src = prep_smem + r * stride;
+        const float nr = s_norm[r];
+        __nv_bfloat16 *dst = unit + static_cast<size_t>(row0 + r) * k_pad;
+        for (int k = lane; k < k_pad; k += 32) dst[k] = __float2bfloat16_rn(k < dim ? src[k] / nr : 0.0f);  // x / NaN = NaN
     }
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks,
-               int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad) {
+               int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *smem_a = smem;
@@ -257,7 +273,11 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         // ===================== epilogue: running top-2 per reference row =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int row = m_tile * kTileM + quarter * 32 + lane;
-        float b1 = -INFINITY, b2 = -INFINITY;
+        // A match needs distance < max_dist, i.e. a cosine above 1 - 2 * max_dist; approximate dots below `floor_dot` (that bound
+        // minus the BF16 error margin) cannot belong to a match and never enter the top-2.  With the usual tight thresholds the
+        // costly "new best in this chunk" path (taken by the whole warp when any of its 32 rows sees a new maximum) then runs
+        // for real candidates only instead of for every running maximum of the random background.
+        float b1 = floor_dot, b2 = -INFINITY;
         int j1 = -1;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -266,11 +286,9 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
             TcFenceAfter();
             const int n0 = t * kTileN;
             const bool partial = n0 + kTileN > n_cur;
-#pragma unroll 1
-            for (int chunk = 0; chunk < kTileN / 32; ++chunk) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN + chunk * 32);
-                TmemLoad32(taddr, r);
+            // The TMEM read of chunk c + 1 is in flight while chunk c is reduced (two register buffers).
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN);
+            auto reduce_chunk = [&](uint32_t (&r)[32], int chunk) {
                 const int c0 = n0 + chunk * 32;
                 if (partial) {
 #pragma unroll
@@ -306,6 +324,18 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
                 } else {
                     b2 = fmaxf(b2, m);  // m <= b1: the chunk can only improve the second place
                 }
+            };
+            uint32_t ra[32], rb[32];
+            TmemLoad32(tbase, ra);
+            TmemLoadWait(ra);
+#pragma unroll 1
+            for (int chunk = 0; chunk < kTileN / 32; chunk += 2) {
+                TmemLoad32(tbase + static_cast<uint32_t>((chunk + 1) * 32), rb);  // in flight while ra is reduced
+                reduce_chunk(ra, chunk);
+                TmemLoadWait(rb);
+                if (chunk + 2 < kTileN / 32) TmemLoad32(tbase + static_cast<uint32_t>((chunk + 2) * 32), ra);  // in flight while rb is reduced
+                reduce_chunk(rb, chunk + 1);
+                if (chunk + 2 < kTileN / 32) TmemLoadWait(ra);
             }
             TcFenceBefore();
             __syncwarp();
@@ -315,7 +345,8 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         }
         if (row < n_ref) {
             Top2 o;
-            o.b1 = b1, o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;  // j2 only says whether a second candidate exists
+            o.b1 = j1 >= 0 ? b1 : -INFINITY;  // no candidate above the floor in this split
+            o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;  // j2 only says whether a second candidate exists
             out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
         }
     }
@@ -339,6 +370,7 @@ __device__ __forceinline__ float KeyFloat(unsigned k) { return __uint_as_float((
 // The reference's distance, bit for bit: sequential dot (k ascending, no FMA), 0.5 - dot / |a| / |b| * 0.5.
 __device__ __forceinline__ float ExactDistance(const float *a, const float *b, int dim, float na, float nb) {
     float s = __fmul_rn(__ldg(a), __ldg(b));
+#pragma unroll 8
     for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(__ldg(a + k), __ldg(b + k)));
     return __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
 }
@@ -353,7 +385,8 @@ __device__ __forceinline__ float WarpExactDistance(const float *a, const float *
     float d = 0.0f;
     if (lane == 0) {
         float s = prod[0];
-        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);
+#pragma unroll 16
+        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);  // unrolled: the shared-memory loads run ahead of the dependent adds
         d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
     }
     __syncwarp();
@@ -369,8 +402,12 @@ __global__ void __launch_bounds__(kRerankWarps * 32) RerankKernel(const float *r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float *prod = rerank_smem + warp * dim;
     for (int i = blockIdx.x * kRerankWarps + warp; i < n_ref; i += gridDim.x * kRerankWarps) {
-        float gmax = -INFINITY;
-        for (int s = lane; s < n_splits; s += 32) gmax = fmaxf(gmax, top[static_cast<size_t>(s) * n_ref_pad + i].b1);
+        // lane s holds the top-2 of column split s (n_splits <= 32: the launch picks at most 16): one round of independent loads
+        // instead of a dependent load per split
+        Top2 mine;
+        mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
+        if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
+        float gmax = mine.b1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
         if (!(gmax > -INFINITY)) continue;
@@ -378,17 +415,22 @@ __global__ void __launch_bounds__(kRerankWarps * 32) RerankKernel(const float *r
         const float *a = ref + static_cast<size_t>(i) * dim;
         const float na = ref_norm[i];
         unsigned long long key = kNoKey64;
-        for (int s = 0; s < n_splits; ++s) {  // warp-uniform loop
-            const Top2 t = top[static_cast<size_t>(s) * n_ref_pad + i];
-            if (t.j1 < 0 || !(t.b1 >= thr)) continue;
-            if (t.j2 >= 0 && t.b2 >= thr) {
-                // both of this split's best are inside the margin: a third candidate could hide behind them
-                if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, s);
-                continue;
-            }
-            const float d = WarpExactDistance(a, cur + static_cast<size_t>(t.j1) * dim, dim, na, cur_norm[t.j1], prod);
+        const bool cand = mine.j1 >= 0 && mine.b1 >= thr;
+        const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;  // both of the split's best inside the margin: a third could hide
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
+        unsigned scan = __ballot_sync(0xFFFFFFFFu, crowded);
+        while (scan) {
+            const int sp = __ffs(scan) - 1;
+            scan &= scan - 1;
+            if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, sp);
+        }
+        while (todo) {  // warp-uniform
+            const int sp = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int j = __shfl_sync(0xFFFFFFFFu, mine.j1, sp);
+            const float d = WarpExactDistance(a, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j], prod);
             if (d == d) {
-                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(t.j1);
+                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
                 key = k < key ? k : key;
             }
         }
@@ -529,7 +571,11 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
         attr_set = true;
     }
-    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad);
+    // cos > 1 - 2 * max_dist is necessary for distance < max_dist; 3 * kEpsDot covers the BF16 dot error and the fp32 rounding of the
+    // distance formula.  NaN / huge thresholds give NaN / -inf floors: nothing or everything passes, as in the reference.
+    const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
+    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
+                                                                          floor_dot);
     RerankKernel<<<ctx->sm_count * 8, kRerankWarps * 32, sizeof(float) * kRerankWarps * dim, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
                                                                                                   n_ref_pad, best, work, n_work);
     ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
