@@ -576,7 +576,9 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
     CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
                                                                           floor_dot);
-    RerankKernel<<<ctx->sm_count * 8, kRerankWarps * 32, sizeof(float) * kRerankWarps * dim, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
+    // one reference row per warp: each row is a chain of dependent latencies (top-2 -> candidate row -> sequential sum), so the more rows
+    // are in flight the better
+    RerankKernel<<<Blocks(n_ref, kRerankWarps), kRerankWarps * 32, sizeof(float) * kRerankWarps * dim, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
                                                                                                   n_ref_pad, best, work, n_work);
     ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
     FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
