@@ -375,67 +375,84 @@ __device__ __forceinline__ float ExactDistance(const float *a, const float *b, i
     return __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
 }
 
-// Exact distance evaluated by a warp: the lanes load both descriptors coalesced and form the 256 products in parallel (each
-// product is one correctly rounded operation, exactly the reference's), lane 0 then adds them in ascending k -- the
-// reference's summation order -- so the value is bit-identical to ExactDistance().  `prod` = dim floats of shared memory.
-__device__ __forceinline__ float WarpExactDistance(const float *a, const float *b, int dim, float na, float nb, float *prod) {
-    const int lane = threadIdx.x & 31;
-    for (int k = lane; k < dim; k += 32) prod[k] = __fmul_rn(__ldg(a + k), __ldg(b + k));
-    __syncwarp();
-    float d = 0.0f;
-    if (lane == 0) {
-        float s = prod[0];
-#pragma unroll 16
-        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);  // unrolled: the shared-memory loads run ahead of the dependent adds
-        d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
-    }
-    __syncwarp();
-    return __shfl_sync(0xFFFFFFFFu, d, 0);
-}
-
-// One warp per reference row: exact re-evaluation of the candidates inside the error margin.
-constexpr int kRerankWarps = 4;
-__global__ void __launch_bounds__(kRerankWarps * 32) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
-                                                                 const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
-                                                                 unsigned long long *best, int2 *work, int *n_work) {
-    extern __shared__ float rerank_smem[];  // [kRerankWarps][dim]
+// Exact re-evaluation of the candidates inside the error margin.  A block owns 32 consecutive reference rows:
+//   1. each warp screens 8 rows: lane s reads the top-2 of column split s, the warp forms the row's best approximate dot, flags the
+//      splits whose best lies inside the margin (candidates) and hands "crowded" splits (both of its top-2 inside the margin: a
+//      third candidate could hide) to the exact scan;
+//   2. per round, every row with a candidate left gets its 256 products a[k] * b[k] written to shared memory by its warp
+//      (coalesced loads, each product one correctly rounded multiply -- the reference's), then LANE r OF WARP 0 ADDS ROW r's
+//      PRODUCTS in ascending k: 32 of the reference's sequential sums advance per instruction instead of one.
+// Rounds repeat while any row of the block has another candidate (almost always exactly one round).
+constexpr int kRerankRows = 32;
+constexpr int kRerankThreads = 128;
+constexpr int kMaxSplits = 16;
+__global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
+                                                              const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
+                                                              unsigned long long *best, int2 *work, int *n_work) {
+    extern __shared__ float rerank_smem[];  // [kRerankRows][dim + 1] products
+    __shared__ int s_cand[kRerankRows][kMaxSplits];  // candidate columns of each row, in split order
+    __shared__ int s_count[kRerankRows];
+    const int stride = dim + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float *prod = rerank_smem + warp * dim;
-    for (int i = blockIdx.x * kRerankWarps + warp; i < n_ref; i += gridDim.x * kRerankWarps) {
-        // lane s holds the top-2 of column split s (n_splits <= 32: the launch picks at most 16): one round of independent loads
-        // instead of a dependent load per split
-        Top2 mine;
-        mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
-        if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
-        float gmax = mine.b1;
+    const int row0 = blockIdx.x * kRerankRows;
+
+    // ---- 1. screening ----
+    for (int r = warp; r < kRerankRows; r += kRerankThreads / 32) {
+        const int i = row0 + r;
+        int count = 0;
+        if (i < n_ref) {
+            Top2 mine;
+            mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
+            if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
+            float gmax = mine.b1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
-        if (!(gmax > -INFINITY)) continue;
-        const float thr = gmax - 2.0f * kEpsDot;
-        const float *a = ref + static_cast<size_t>(i) * dim;
-        const float na = ref_norm[i];
-        unsigned long long key = kNoKey64;
-        const bool cand = mine.j1 >= 0 && mine.b1 >= thr;
-        const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;  // both of the split's best inside the margin: a third could hide
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
-        unsigned scan = __ballot_sync(0xFFFFFFFFu, crowded);
-        while (scan) {
-            const int sp = __ffs(scan) - 1;
-            scan &= scan - 1;
-            if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, sp);
+            for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+            const float thr = gmax - 2.0f * kEpsDot;
+            const bool cand = gmax > -INFINITY && mine.j1 >= 0 && mine.b1 >= thr;
+            const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;
+            const unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
+            unsigned scan = __ballot_sync(0xFFFFFFFFu, crowded);
+            while (scan) {
+                const int sp = __ffs(scan) - 1;
+                scan &= scan - 1;
+                if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, sp);
+            }
+            if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine.j1;
+            count = __popc(todo);
         }
-        while (todo) {  // warp-uniform
-            const int sp = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int j = __shfl_sync(0xFFFFFFFFu, mine.j1, sp);
-            const float d = WarpExactDistance(a, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j], prod);
-            if (d == d) {
-                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
-                key = k < key ? k : key;
+        if (lane == 0) s_count[r] = count;
+    }
+    __syncthreads();
+
+    // ---- 2. rounds of exact distances ----
+    unsigned long long key = kNoKey64;  // lane r of warp 0: row r
+    for (int round = 0; round < kMaxSplits; ++round) {
+        bool any = false;
+        for (int r = warp; r < kRerankRows; r += kRerankThreads / 32) {
+            if (round < s_count[r]) {
+                any = true;
+                const float *a = ref + static_cast<size_t>(row0 + r) * dim;
+                const float *b = cur + static_cast<size_t>(s_cand[r][round]) * dim;
+                float *prod = rerank_smem + r * stride;
+                for (int k = lane; k < dim; k += 32) prod[k] = __fmul_rn(__ldg(a + k), __ldg(b + k));
             }
         }
-        if (lane == 0 && key != kNoKey64) atomicMin(&best[i], key);
+        if (!__syncthreads_or(any)) break;
+        if (warp == 0 && round < s_count[lane]) {
+            const int i = row0 + lane, j = s_cand[lane][round];
+            const float *prod = rerank_smem + lane * stride;
+            float s = prod[0];
+#pragma unroll 8
+            for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);
+            const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, ref_norm[i]), cur_norm[j]), 0.5f));
+            if (d == d) {
+                const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+                key = k64 < key ? k64 : key;
+            }
+        }
+        __syncthreads();
     }
+    if (warp == 0 && row0 + lane < n_ref && key != kNoKey64) atomicMin(&best[row0 + lane], key);
 }
 
 // One block per flagged (row, split): exact scan of the split's column range.
@@ -523,7 +540,7 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     int splits = 1;
     {
         double best_eff = -1.0;
-        const int max_splits = n_tiles < 16 ? n_tiles : 16;
+        const int max_splits = n_tiles < kMaxSplits ? n_tiles : kMaxSplits;
         for (int sp = 1; sp <= max_splits; ++sp) {
             const int per = (n_tiles + sp - 1) / sp, real = (n_tiles + per - 1) / per;
             const long long ctas = static_cast<long long>(m_tiles) * real;
@@ -576,10 +593,8 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
     CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
                                                                           floor_dot);
-    // one reference row per warp: each row is a chain of dependent latencies (top-2 -> candidate row -> sequential sum), so the more rows
-    // are in flight the better
-    RerankKernel<<<Blocks(n_ref, kRerankWarps), kRerankWarps * 32, sizeof(float) * kRerankWarps * dim, st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
-                                                                                                  n_ref_pad, best, work, n_work);
+    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
+                                                                                                            n_ref_pad, best, work, n_work);
     ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
     FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
     ctx->launches += 7;
