@@ -26,8 +26,18 @@ typedef struct {
 
 static inline float px_i(const image_t *im, int32_t row, int32_t col) { return (float)im->d[row * im->cols + col]; }
 
+/* Diagnostics only (tools/fuzz_parity.py): how many unchecked samples addressed a base pixel outside the image.  The
+ * reference has undefined behaviour there (lssd_klt_fast.cpp:182-193 once a track diverges); results are untouched. */
+static long long g_outside_reads = 0;
+long long ftko_outside_reads(int32_t reset) {
+    const long long n = g_outside_reads;
+    if (reset) g_outside_reads = 0;
+    return n;
+}
+
 /* Unchecked bilinear sample: base pixel by truncation, fractions by floor, 4 weighted terms left to right. */
 static inline float px_f(const image_t *im, float row, float col) {
+    if (!(row >= 0.0f && col >= 0.0f && (int32_t)row <= im->rows - 1 && (int32_t)col <= im->cols - 1)) ++g_outside_reads;
     const uint8_t *v = &im->d[(int32_t)row * im->cols + (int32_t)col];
     const float sr = row - floorf(row);
     const float sc = col - floorf(col);

@@ -65,6 +65,9 @@ int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, c
 int ftko_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
                           const int32_t *rows, const int32_t *cols, int32_t single_level, int32_t flow_valid, float *flow_row, float *flow_col);
 
+/* Diagnostics: number of unchecked samples whose base pixel lay outside the image since the last reset (reference UB). */
+long long ftko_outside_reads(int32_t reset);
+
 void ftko_ldlt_solve(int32_t n, const float *a, const float *b, float *x);
 
 #ifdef __cplusplus

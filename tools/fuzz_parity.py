@@ -3,6 +3,7 @@
 with border and far-outside features, predictions and entry statuses.  Not part of the test-suite (minutes of CPU time);
     python tools/fuzz_parity.py [n_cases] [seed]
 prints one line per mismatching case and a summary."""
+import ctypes as C
 import os
 import sys
 
@@ -46,7 +47,7 @@ def main():
     rng = np.random.default_rng(seed)
     ctx = ft.Context(0)
     oracle = po.OracleLib()
-    bad = crashed = 0
+    bad = crashed = undefined = 0
     for case in range(n_cases):
         if os.environ.get("FUZZ_VERBOSE"):
             print("case", case, flush=True)
@@ -83,8 +84,12 @@ def main():
         prm = po.make_params(variant, method, half=hr, half_col=hc, max_points=max_points, luminance=lum)
         # The reference (and so the oracle) reads out of bounds when a tracker diverges to NaN positions (e.g. LSSD kFast with 3x3
         # patches): evaluate it in a forked child so that such a crash only skips the case.  The GPU result above is still computed.
-        exp = in_child(lambda: oracle.klt_track(prm, oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels), uv, cur_uv=pred, status=st_in,
-                                                single_level=single))
+        def run_oracle():
+            oracle.lib.ftko_outside_reads.restype = C.c_longlong
+            oracle.lib.ftko_outside_reads(C.c_int32(1))
+            r = oracle.klt_track(prm, oracle.pyramid_build(ref, levels), oracle.pyramid_build(cur, levels), uv, cur_uv=pred, status=st_in, single_level=single)
+            return r + (int(oracle.lib.ftko_outside_reads(C.c_int32(0))),)
+        exp = in_child(run_oracle)
         if exp is None:
             crashed += 1
             print(f"reference crashed (undefined behaviour) on case {case}: {variant}/{method} {2 * hr + 1}x{2 * hc + 1}; GPU returned normally")
@@ -93,12 +98,18 @@ def main():
         same_st = np.array_equal(got[2], exp[2])
         same_uv = np.array_equal(got[1].view(np.uint32), exp[1].view(np.uint32)) or np.array_equal(np.nan_to_num(got[1]), np.nan_to_num(exp[1]))
         if not (got[0] == exp[0] and same_st and same_uv):
+            if exp[3] > 0:  # the reference sampled outside the image without a bounds test: its result is undefined there
+                undefined += 1
+                print(f"reference read outside the image ({exp[3]} unchecked samples) on case {case}: {variant}/{method} {2 * hr + 1}x{2 * hc + 1}; results differ")
+                pyr.close()
+                continue
             bad += 1
             d = np.abs(got[1].astype(np.float64) - exp[1].astype(np.float64))
             print(f"MISMATCH case {case}: {variant}/{method} {2 * hr + 1}x{2 * hc + 1} {rows}x{cols} L{levels} single={single} n={uv.shape[0]} "
                   f"status_diff={int((got[2] != exp[2]).sum())} max_pos_diff={np.nanmax(d) if d.size else 0}")
         pyr.close()
-    print(f"fuzz: {n_cases} cases, {bad} mismatching, {crashed} where the reference itself crashed")
+    print(f"fuzz: {n_cases} cases, {bad} mismatching, {crashed} where the reference itself crashed, "
+          f"{undefined} differing where the reference read outside the image (undefined behaviour)")
     return 1 if bad else 0
 
 
