@@ -16,6 +16,8 @@
 //                        both inside the margin (a third candidate could hide) go to an exact scan (ExactScanKernel).
 // Warp roles in CosineTcKernel (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
 // epilogue (one TMEM lane quarter each).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -359,6 +361,240 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     }
 }
 
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- execute ONE 256 x 256 x 16 tcgen05.mma per
+// issue.  Each CTA keeps its own 128 reference rows (A) and loads only HALF of every current-set tile (128 of the 256 B rows);
+// the tensor cores of both SMs read both halves.  Per SM that halves the TMA traffic and the shared-memory operand reads of
+// B, which is what caps the single-CTA kernel (its MMA thread never starves, yet the tensor pipe is busy only ~65 %).
+//   * barriers: the LEADER (cluster rank 0) owns bar_a / bar_full[]: both CTAs' TMA loads complete_tx on the leader's barrier
+//     (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address), the leader's MMA thread waits there;
+//     tcgen05.commit ... multicast::cluster arrives on bar_empty[] / bar_acc_full[] of BOTH CTAs; the follower's epilogue warps
+//     arrive remotely on the leader's bar_acc_empty[] (8 arrivals per accumulator).
+//   * TMEM: allocated / freed with cta_group::2 by warp 1 of both CTAs; each CTA's epilogue reads its own 128 lanes.
+// =====================================================================================================================
+constexpr int kStages2 = 8;                          // 16 KiB stages: one K block of this CTA's half of a current-set tile
+constexpr int kHalfN = kTileN / 2;                   // B rows per CTA
+constexpr int kBoxBytesB2 = kHalfN * kKBlock * 2;    // 16 KiB
+constexpr size_t kTc2SmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytesA + static_cast<size_t>(kStages2) * kBoxBytesB2 + 512;
+constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) | (static_cast<uint32_t>((2 * kTileM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t ClusterCtaRank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void ClusterSync() {
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t MapToCta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void MbarArriveCluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void TmaLoad2DPair(void *smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     SmemU32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void UmmaBf16Pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in both CTAs of the pair once all MMAs issued so far have retired
+__device__ __forceinline__ void UmmaCommitPair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(SmemU32(bar)),
+                 "h"(static_cast<uint16_t>(3))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+CosineTcPairKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur_half, int n_ref, int n_cur, int k_blocks,
+                   int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *smem_a = smem;
+    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytesA;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages2 * kBoxBytesB2);
+    uint64_t *bar_a = &bars[0];
+    uint64_t *bar_full = &bars[1];                      // [kStages2]   (the leader's are used)
+    uint64_t *bar_empty = &bars[1 + kStages2];          // [kStages2]   (each CTA its own)
+    uint64_t *bar_acc_full = &bars[1 + 2 * kStages2];   // [2]          (each CTA its own)
+    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages2];  // [2]          (the leader's are used)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages2]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ClusterCtaRank();
+    const bool leader = rank == 0;
+    const int m_tile = blockIdx.x;  // the two CTAs of a cluster are neighbours in x: rows m_tile * 128 ...
+    const int t_begin = blockIdx.y * tiles_per_split;
+    const int t_end = min(n_tiles, t_begin + tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        MbarInit(bar_a, 1);
+        for (int s = 0; s < kStages2; ++s) {
+            MbarInit(&bar_full[s], 1);
+            MbarInit(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            MbarInit(&bar_acc_full[a], 1);
+            MbarInit(&bar_acc_empty[a], 8);  // four epilogue warps of each CTA
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    TcFenceBefore();
+    ClusterSync();  // barriers and TMEM of both CTAs exist
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; transaction bytes go to the leader's barriers) =====================
+        if (lane == 0) {
+            const uint32_t lead_bar_a = MapToCta(SmemU32(bar_a), 0);
+            if (leader) MbarExpectTx(bar_a, 2u * static_cast<uint32_t>(k_blocks) * kBoxBytesA);
+            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2DPair(smem_a + kb * kBoxBytesA, &map_ref, lead_bar_a, kb * kKBlock, m_tile * kTileM);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    MbarWait(&bar_empty[stage], phase ^ 1u);
+                    if (leader) MbarExpectTx(&bar_full[stage], 2u * kBoxBytesB2);
+                    TmaLoad2DPair(smem_b + stage * kBoxBytesB2, &map_cur_half, MapToCta(SmemU32(&bar_full[stage]), 0), kb * kKBlock,
+                                  t * kTileN + static_cast<int>(rank) * kHalfN);
+                    if (++stage == kStages2) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the leader CTA =====================
+        if (leader && lane == 0) {
+            MbarWait(bar_a, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
+                TcFenceAfter();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    MbarWait(&bar_full[stage], phase);
+                    TcFenceAfter();
+                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytesA);
+                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB2);
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k)
+                        UmmaBf16Pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc2, (kb | k) != 0 ? 1u : 0u);
+                    UmmaCommitPair(&bar_empty[stage]);
+                    if (++stage == kStages2) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                UmmaCommitPair(&bar_acc_full[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (both CTAs): running top-2 per reference row =====================
+        const int quarter = warp & 3;
+        const int row = m_tile * kTileM + quarter * 32 + lane;
+        float b1 = floor_dot, b2 = -INFINITY;
+        int j1 = -1;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t lead_acc_empty0 = MapToCta(SmemU32(&bar_acc_empty[0]), 0), lead_acc_empty1 = MapToCta(SmemU32(&bar_acc_empty[1]), 0);
+        for (int t = t_begin; t < t_end; ++t) {
+            MbarWait(&bar_acc_full[acc], acc_phase);
+            TcFenceAfter();
+            const int n0 = t * kTileN;
+            const bool partial = n0 + kTileN > n_cur;
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN);
+            auto reduce_chunk = [&](uint32_t (&r)[32], int chunk) {
+                const int c0 = n0 + chunk * 32;
+                if (partial) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c0 + c >= n_cur) r[c] = 0xFF800000u;
+                }
+                float m4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    m4[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                if (m > b1) {
+                    float cb1 = -INFINITY, cb2 = -INFINITY;
+                    int cj = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = __uint_as_float(r[c]);
+                        if (v > cb1) {
+                            cb2 = cb1;
+                            cb1 = v;
+                            cj = c;
+                        } else {
+                            cb2 = fmaxf(cb2, v);
+                        }
+                    }
+                    b2 = fmaxf(b1, cb2);
+                    b1 = cb1;
+                    j1 = c0 + cj;
+                } else {
+                    b2 = fmaxf(b2, m);
+                }
+            };
+            uint32_t ra[32], rb[32];
+            TmemLoad32(tbase, ra);
+            TmemLoadWait(ra);
+#pragma unroll 1
+            for (int chunk = 0; chunk < kTileN / 32; chunk += 2) {
+                TmemLoad32(tbase + static_cast<uint32_t>((chunk + 1) * 32), rb);
+                reduce_chunk(ra, chunk);
+                TmemLoadWait(rb);
+                if (chunk + 2 < kTileN / 32) TmemLoad32(tbase + static_cast<uint32_t>((chunk + 2) * 32), ra);
+                reduce_chunk(rb, chunk + 1);
+                if (chunk + 2 < kTileN / 32) TmemLoadWait(ra);
+            }
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArriveCluster(acc == 0 ? lead_acc_empty0 : lead_acc_empty1);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (row < n_ref) {
+            Top2 o;
+            o.b1 = j1 >= 0 ? b1 : -INFINITY;
+            o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;
+            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
+        }
+    }
+
+    TcFenceBefore();
+    ClusterSync();  // nobody leaves while the peer may still signal its barriers or read its shared memory
+    if (warp == 1) {
+        TcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // Order-preserving key for a non-NaN float distance (with -0 canonicalised to +0).
 __device__ __forceinline__ unsigned FloatKey(float d) {
     d = d + 0.0f;
@@ -583,16 +819,45 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     NormPrepKernel<<<Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_cur, n_cur, dim, k_pad, cur_norm, cur_unit);
     FillKeysKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, n_work);
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
-        attr_set = true;
-    }
     // cos > 1 - 2 * max_dist is necessary for distance < max_dist; 3 * kEpsDot covers the BF16 dot error and the fp32 rounding of the
     // distance formula.  NaN / huge thresholds give NaN / -inf floors: nothing or everything passes, as in the reference.
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
-    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
-                                                                          floor_dot);
+    // The CTA-pair kernel (cta_group::2) is bit-identical but measured slower than the single-CTA one (203 us vs 166 us for
+    // 20k x 20k x 256): opt-in with FTK_COSINE_2CTA=1, see DESIGN.md.
+    const char *pair_env = getenv("FTK_COSINE_2CTA");
+    const bool single_cta = !(pair_env && pair_env[0] == '1');
+    if (single_cta) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
+            attr_set = true;
+        }
+        CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
+                                                                              floor_dot);
+    } else {
+        // CTA pairs: clusters of two neighbouring m-tiles (an odd last tile gets an idle partner whose rows are zero-filled by TMA)
+        static bool attr_set = false;
+        if (!attr_set) {
+            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcPairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTc2SmemBytes)));
+            attr_set = true;
+        }
+        CUtensorMap map_cur_half;
+        if (!MakeMap(&map_cur_half, cur_unit, n_cur, k_pad, kHalfN)) return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((m_tiles + 1) / 2 * 2, splits);
+        cfg.blockDim = dim3(kTcThreads);
+        cfg.dynamicSmemBytes = kTc2SmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        FTK_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, CosineTcPairKernel, map_ref, map_cur_half, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
+                                               floor_dot));
+    }
     RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
                                                                                                             n_ref_pad, best, work, n_work);
     ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);

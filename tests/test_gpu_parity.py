@@ -456,6 +456,20 @@ def test_cosine_tensor_path_decides_without_fallback(ctx, oracle):
         assert (got == oracle.match_cosine_force(a, b, 0.1)[1]).all(), (n_ref, n_cur, dim)
 
 
+def test_cosine_cta_pair_kernel_opt_in(ctx, oracle, monkeypatch):
+    """The cta_group::2 (CTA pair) tensor-core kernel, FTK_COSINE_2CTA=1, stays exact although it is not the default: odd and even
+    numbers of 128-row tiles, partial column tiles, several K."""
+    monkeypatch.setenv("FTK_COSINE_2CTA", "1")
+    for n_ref, n_cur, dim in [(130, 170, 256), (400, 333, 256), (1000, 2100, 128), (257, 700, 64), (33, 40, 100)]:
+        ref, cur = S.make_float_sets(n_ref, n_cur, dim=dim, seed=n_ref + dim)
+        m = ft.CosineMatcher(ctx)
+        m.options().kMaxValidDescriptorDistance = 0.1
+        ok, idx = m.ForceMatch(ref, cur)
+        _, exp = oracle.match_cosine_force(ref, cur, 0.1)
+        assert ok and np.array_equal(idx, exp), (n_ref, n_cur, dim)
+        assert (exp >= 0).sum() > n_ref // 2
+
+
 def test_cosine_nearby_vs_oracle(ctx, oracle):
     rf, cf = S.make_float_sets(300, 350, dim=256, seed=31)
     rng = np.random.default_rng(8)
