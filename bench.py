@@ -520,6 +520,8 @@ def run_b200(args):
             self.params = [klt_params(t) for t in tracker_list]
             self.d_cur = [torch.empty_like(d_ref_uv) for _ in tracker_list]
             self.d_st = [torch.empty((n_total,), dtype=torch.uint8, device=dev) for _ in tracker_list]
+            self.h_cur = torch.empty((len(tracker_list), n_total, 2), dtype=torch.float32).pin_memory()
+            self.h_st = torch.empty((len(tracker_list), n_total), dtype=torch.uint8).pin_memory()
 
         def klt_only(self, i):
             flags = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
@@ -532,13 +534,13 @@ def run_b200(args):
                 self.klt_only(i)
 
         def step_e2e(self):
-            # the user-facing call, once per tracker: host images + host features in, host results out (H2D of chunk k+1 overlaps
-            # compute of chunk k)
+            # the user-facing call: host images + host features in, host results of every tracker out (H2D of chunk k+1 overlaps
+            # compute of chunk k; the images cross PCIe once for all trackers of the workload)
             flags = _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS
-            for prm in self.params:
-                ctx.check(L.ftk_track_image_pairs(ctx._h, C.byref(prm), ROWS, COLS, LEVELS, n_pairs, vp(host_images.data_ptr()),
-                                                  vp(host_images.data_ptr() + n_pairs * plane), vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()),
-                                                  vp(host_cur_uv.data_ptr()), vp(host_status.data_ptr()), flags))
+            arr = (_capi.KltParams * len(self.params))(*self.params)
+            ctx.check(L.ftk_track_image_pairs_multi(ctx._h, arr, len(self.params), ROWS, COLS, LEVELS, n_pairs, vp(host_images.data_ptr()),
+                                                    vp(host_images.data_ptr() + n_pairs * plane), vp(offsets.ctypes.data), vp(host_ref_uv.data_ptr()),
+                                                    vp(self.h_cur.data_ptr()), vp(self.h_st.data_ptr()), flags))
 
         def measure(self, steps, warmup, sample_clocks):
             n_track = len(self.trackers)
@@ -560,12 +562,12 @@ def run_b200(args):
             for _ in range(2):
                 self.step_e2e()
             ms_e2e, _ = timed(self.step_e2e, steps)
-            h2d = n_track * (2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4)
+            h2d = 2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4
             d2h = n_track * n_total * 9
             res["e2e"] = {"value": per_step * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                           "ms_per_step": ms_e2e / steps,
-                          "api": "ftk_track_image_pairs, one call per tracker (pinned host images + features in, host results out; H2D of chunk k+1 "
-                                 "overlaps compute of chunk k)"}
+                          "api": "ftk_track_image_pairs_multi: one call for all trackers of the workload (pinned host images + features in, host results "
+                                 "of every tracker out; H2D of chunk k+1 overlaps compute of chunk k)"}
             return res
 
         def rooflines(self, res, oracle):

@@ -269,6 +269,26 @@ class OpticalFlow:
         ok = self.ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
         return ok, cur[:n], st[:n]
 
+    @staticmethod
+    def TrackImagePairsMulti(trackers, levels, ref_images, cur_images, feat_offsets, ref_pixel_uv):
+        """Several trackers (any variants / methods / patch sizes, one context) over the same batch of host frame pairs in one pipelined
+        call: the images are uploaded and their pyramids built once (ftk_track_image_pairs_multi).  No prediction / status input.
+        Returns (ok, cur_pixel_uv [n_trackers, n, 2], status [n_trackers, n])."""
+        ctx = trackers[0].ctx
+        ref_images = np.ascontiguousarray(ref_images, dtype=np.uint8)
+        cur_images = np.ascontiguousarray(cur_images, dtype=np.uint8)
+        n_pairs, rows, cols = ref_images.shape
+        ref_uv = np.ascontiguousarray(ref_pixel_uv, dtype=np.float32).reshape(-1, 2)
+        n = ref_uv.shape[0]
+        feat_offsets = np.ascontiguousarray(feat_offsets, dtype=np.int32)
+        params = (_capi.KltParams * len(trackers))(*[t._params() for t in trackers])
+        cur = np.zeros((len(trackers), max(n, 1), 2), np.float32)
+        st = np.zeros((len(trackers), max(n, 1)), np.uint8)
+        rc = lib().ftk_track_image_pairs_multi(ctx._h, params, len(trackers), rows, cols, int(levels), n_pairs, _ptr(ref_images), _ptr(cur_images),
+                                               _ptr(feat_offsets), _ptr(ref_uv), _ptr(cur), _ptr(st), _capi.FLAG_NO_PREDICTION | _capi.FLAG_NO_STATUS)
+        ok = ctx.check(rc, soft=(_capi.ERR_EMPTY_INPUT,))
+        return ok, cur[:, :n], st[:, :n]
+
     def TrackImageSequence(self, levels, frames, feat_offsets, ref_pixel_uv, cur_pixel_uv=None, status=None):
         """Temporal form of TrackImagePairs: host frames [n_frames, rows, cols]; pair k tracks features
         feat_offsets[k]:feat_offsets[k+1] from frame k to frame k+1; every frame is uploaded and its pyramid built once

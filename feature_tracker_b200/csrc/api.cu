@@ -375,19 +375,26 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
 
 // The chunked two-stream pipeline behind ftk_track_image_pairs (cur_images != nullptr: pair p = ref_images[p] -> cur_images[p])
 // and ftk_track_image_sequence (cur_images == nullptr: ref_images holds n_pairs + 1 frames, pair p = frame p -> frame p + 1).
-static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_pairs,
-                                const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
-                                uint8_t *status, uint32_t flags) {
+// n_trackers parameter sets run on every chunk while its images are resident: tracker k reads / writes cur_uv + k * 2 * n_features and
+// status + k * n_features, exactly as n_trackers separate calls would, but the images cross PCIe once.
+static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
+                                int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
+                                float *cur_uv, uint8_t *status, uint32_t flags) {
     const bool sequence = cur_images == nullptr;
-    if (!ctx || !params || !ref_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
+    if (!ctx || !params || n_trackers < 1 || !ref_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
     if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
     if (flags & (FTK_FLAG_DEVICE_POINTERS | FTK_FLAG_SINGLE_LEVEL)) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "host images, multi-level only");
-    if (params->variant < 0 || params->variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params->variant);
+    bool any_fb = false;
+    for (int k = 0; k < n_trackers; ++k) {
+        if (params[k].variant < 0 || params[k].variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params[k].variant);
+        any_fb = any_fb || params[k].forward_backward_max_error > 0.0f;
+    }
     if (feat_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
     for (int p = 0; p < n_pairs; ++p)
         if (feat_offsets[p + 1] < feat_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
     const int n_features = feat_offsets[n_pairs];
     if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");  // optical_flow.cpp:8
+    const size_t n_all = static_cast<size_t>(n_trackers) * n_features;
     DeviceGuard guard(ctx->device);
 
     // chunking: about 8 chunks per call, double-buffered staging pyramids (2 * chunk_pairs images each: refs then curs; a
@@ -416,12 +423,12 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
 
     // features up front (small), chunk-local offset tables, the "cur image = stage_pairs + p" map
     if (int rc = EnsureDevice(ctx, ctx->d_ref_uv, sizeof(float2) * n_features)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_features)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_status, n_features)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_all)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_status, n_all)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * n_features)) return rc;
-    if (params->forward_backward_max_error > 0.0f) {  // backward-pass scratch for the whole batch, so no chunk reallocates it
-        if (int rc = EnsureDevice(ctx, ctx->d_back_uv, sizeof(float2) * n_features)) return rc;
-        if (int rc = EnsureDevice(ctx, ctx->d_back_status, n_features)) return rc;
+    if (any_fb) {  // backward-pass scratch for the whole batch, so no chunk reallocates it
+        if (int rc = EnsureDevice(ctx, ctx->d_back_uv, sizeof(float2) * n_all)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_back_status, n_all)) return rc;
     }
     std::vector<int32_t> h_offsets;
     h_offsets.reserve(n_pairs + n_chunks);
@@ -438,8 +445,8 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
     const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);
     cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
     FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_uv.ptr, ref_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ks));
-    if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_cur_uv.ptr, cur_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ks));
-    if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_status.ptr, status, n_features, cudaMemcpyHostToDevice, ks));
+    if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_cur_uv.ptr, cur_uv, sizeof(float2) * n_all, cudaMemcpyHostToDevice, ks));
+    if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_status.ptr, status, n_all, cudaMemcpyHostToDevice, ks));
     FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_offsets.ptr, h_offsets.data(), sizeof(int32_t) * h_offsets.size(), cudaMemcpyHostToDevice, ks));
     FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_curmap.ptr, h_curmap.data(), sizeof(int32_t) * h_curmap.size(), cudaMemcpyHostToDevice, ks));
     FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));  // the host vectors above go out of scope; the copy stream may start
@@ -476,30 +483,34 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
             if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, stage_pairs, np)) return rc;
         const int f_lo = feat_offsets[p_lo], f_hi = feat_offsets[p_hi];
         if (f_hi > f_lo) {
-            ftk::KltLaunch a{};
-            a.p = *params;
-            a.ref = v;
-            a.cur = v;
-            a.n_pairs = np;
-            a.n_features = f_hi - f_lo;
-            a.has_prediction = has_prediction ? 1 : 0;
-            a.has_status = has_status ? 1 : 0;
-            a.single_level = 0;
-            a.ref_uv = static_cast<const float2 *>(ctx->d_ref_uv.ptr) + f_lo;
-            a.cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr) + f_lo;
-            a.status = static_cast<uint8_t *>(ctx->d_status.ptr) + f_lo;
-            a.feat_offsets = static_cast<const int *>(ctx->d_chunk_offsets.ptr) + chunk_table_start[c];
-            a.ref_image = nullptr;  // image p of the staging batch
-            a.cur_image = static_cast<const int *>(ctx->d_chunk_curmap.ptr);
             int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr) + f_lo;
-            if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, np, a.n_features, d_feat_pair)) return rc;
-            a.feat_pair = d_feat_pair;
-            if (int rc = ftk::LaunchKltTrackChecked(ctx, a, f_lo)) return rc;
+            const int *chunk_offsets = static_cast<const int *>(ctx->d_chunk_offsets.ptr) + chunk_table_start[c];
+            if (int rc = ftk::LaunchFeaturePairs(ctx, chunk_offsets, np, f_hi - f_lo, d_feat_pair)) return rc;
+            for (int k = 0; k < n_trackers; ++k) {
+                const size_t base = static_cast<size_t>(k) * n_features + f_lo;
+                ftk::KltLaunch a{};
+                a.p = params[k];
+                a.ref = v;
+                a.cur = v;
+                a.n_pairs = np;
+                a.n_features = f_hi - f_lo;
+                a.has_prediction = has_prediction ? 1 : 0;
+                a.has_status = has_status ? 1 : 0;
+                a.single_level = 0;
+                a.ref_uv = static_cast<const float2 *>(ctx->d_ref_uv.ptr) + f_lo;
+                a.cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr) + base;
+                a.status = static_cast<uint8_t *>(ctx->d_status.ptr) + base;
+                a.feat_offsets = chunk_offsets;
+                a.ref_image = nullptr;  // image p of the staging batch
+                a.cur_image = static_cast<const int *>(ctx->d_chunk_curmap.ptr);
+                a.feat_pair = d_feat_pair;
+                if (int rc = ftk::LaunchKltTrackChecked(ctx, a, base)) return rc;
+            }
         }
         FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_computed[b], ks));
     }
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, ctx->d_cur_uv.ptr, sizeof(float2) * n_features, cudaMemcpyDeviceToHost, ks));
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, ctx->d_status.ptr, n_features, cudaMemcpyDeviceToHost, ks));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, ctx->d_cur_uv.ptr, sizeof(float2) * n_all, cudaMemcpyDeviceToHost, ks));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, ctx->d_status.ptr, n_all, cudaMemcpyDeviceToHost, ks));
     FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));
     return FTK_OK;
 }
@@ -508,13 +519,20 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
                           const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
                           uint8_t *status, uint32_t flags) {
     if (!cur_images) return FTK_ERR_INVALID_ARGUMENT;
-    return TrackImagesPipelined(ctx, params, rows, cols, levels, n_pairs, ref_images, cur_images, feat_offsets, ref_uv, cur_uv, status, flags);
+    return TrackImagesPipelined(ctx, params, 1, rows, cols, levels, n_pairs, ref_images, cur_images, feat_offsets, ref_uv, cur_uv, status, flags);
+}
+
+int ftk_track_image_pairs_multi(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
+                                int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
+                                float *cur_uv, uint8_t *status, uint32_t flags) {
+    if (!cur_images) return FTK_ERR_INVALID_ARGUMENT;
+    return TrackImagesPipelined(ctx, params, n_trackers, rows, cols, levels, n_pairs, ref_images, cur_images, feat_offsets, ref_uv, cur_uv, status, flags);
 }
 
 int ftk_track_image_sequence(ftk_context *ctx, const ftk_klt_params *params, int32_t rows, int32_t cols, int32_t levels, int32_t n_frames,
                              const uint8_t *frames, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv, uint8_t *status, uint32_t flags) {
     if (ctx && n_frames < 2) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "a sequence needs at least two frames");
-    return TrackImagesPipelined(ctx, params, rows, cols, levels, n_frames - 1, frames, nullptr, feat_offsets, ref_uv, cur_uv, status, flags);
+    return TrackImagesPipelined(ctx, params, 1, rows, cols, levels, n_frames - 1, frames, nullptr, feat_offsets, ref_uv, cur_uv, status, flags);
 }
 
 // ---- matching -------------------------------------------------------------------------------------------------

@@ -136,6 +136,14 @@ int ftk_track_image_pairs(ftk_context *ctx, const ftk_klt_params *params, int32_
                           const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv, float *cur_uv,
                           uint8_t *status, uint32_t flags);
 
+/* The same for several parameter sets at once (e.g. kDirect and kFast of one tracker, as BASELINE configs[1] runs them): every
+ * tracker k runs on each chunk while its images are resident, reading / writing cur_uv + k * 2 * n_features and
+ * status + k * n_features (n_features = feat_offsets[n_pairs]), so the result equals n_trackers separate calls while the images
+ * cross the host link once. */
+int ftk_track_image_pairs_multi(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
+                                int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
+                                float *cur_uv, uint8_t *status, uint32_t flags);
+
 /* The temporal form of the same pipeline (SURVEY 8(f) "next" row: the current frame of pair k is the reference frame of pair
  * k+1, but the reference's callers rebuild both pyramids for every pair, test/test_optical_flow.cpp:70-71).  `frames` holds
  * n_frames >= 2 tightly packed HOST images; pair k = (frame k -> frame k+1), k = 0 .. n_frames-2, owns features

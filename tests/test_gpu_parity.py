@@ -210,6 +210,28 @@ def test_track_image_pairs_pipelined(ctx, oracle):
     assert not ok
 
 
+def test_track_image_pairs_multi(ctx, oracle):
+    """ftk_track_image_pairs_multi: several trackers per upload; every tracker's slice equals its own ftk_track_image_pairs call."""
+    n_pairs, rows, cols, levels = 20, 96, 128, 3
+    uniq = [S.make_pair(rows, cols, 20, pair_id=180 + p, border=8) for p in range(4)]
+    refs = np.stack([uniq[p % 4][0] for p in range(n_pairs)])
+    curs = np.stack([uniq[p % 4][1] for p in range(n_pairs)])
+    uvs = [uniq[p % 4][2] for p in range(n_pairs)]
+    offsets = np.concatenate([[0], np.cumsum([u.shape[0] for u in uvs])]).astype(np.int32)
+    all_uv = np.concatenate(uvs)
+    trackers = [make_tracker(ctx, "affine", "direct", 6), make_tracker(ctx, "affine", "fast", 6), make_tracker(ctx, "basic", "inverse", 7)]
+    trackers[2].forward_backward_max_error = 0.5
+    ok, cur_uv, st = ft.OpticalFlow.TrackImagePairsMulti(trackers, levels, refs, curs, offsets, all_uv)
+    assert ok and cur_uv.shape == (3, all_uv.shape[0], 2)
+    for k, t in enumerate(trackers):
+        ok1, uv1, st1 = t.TrackImagePairs(levels, refs, curs, offsets, all_uv)
+        assert ok1 and bits_equal(cur_uv[k], uv1) and np.array_equal(st[k], st1), k
+    prm = po.make_params("affine", "direct", half=6)
+    exp = oracle.klt_track(prm, oracle.pyramid_build(uniq[1][0], levels), oracle.pyramid_build(uniq[1][1], levels), uvs[1])
+    sl = slice(offsets[1], offsets[2])
+    assert_same("multi affine direct pair 1", (True, cur_uv[0][sl], st[0][sl]), exp)
+
+
 def test_klt_temporal_sequence_shares_pyramids(ctx, oracle):
     """in a sequence the cur frame of pair k is the ref frame of pair k+1.  One pyramid per frame, pairs
     (k, k+1) addressed through the ref_image / cur_image maps; results equal tracking each pair on its own."""
