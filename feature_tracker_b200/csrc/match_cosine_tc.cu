@@ -362,6 +362,233 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
 }
 
 // =====================================================================================================================
+// A-from-TMEM variant.  tcgen05.mma reads ~64 B/clk of operands from shared memory: with both operands there, a 128 x 256 x 16
+// MMA needs 12 KB (A 4 KB + B 8 KB) = 192 clk against 135 clk of math -- the ~70 % ceiling measured above.  The reference tile
+// A (128 rows x K) never changes while a CTA streams the current set past it, so it is written ONCE into tensor memory
+// (tcgen05.st: TMEM lane = row, one 32-bit column = two consecutive BF16 of the row) and every MMA takes A from TMEM
+// (tcgen05.mma [d], [a], b_desc, ...).  Shared memory then only feeds B: tiles are 192 columns wide (2 x 192 accumulator
+// columns + 128 columns of A fill the 512 TMEM columns), 6 KB per 128 x 192 x 16 MMA = 96 clk < 101 clk of math, and all of
+// shared memory becomes an 8-stage B pipeline.
+// =====================================================================================================================
+constexpr int kTileN3 = 192;
+constexpr int kStages3 = 8;
+constexpr int kBoxBytesB3 = kTileN3 * kKBlock * 2;  // 24 KiB
+constexpr int kTmemColA = 2 * kTileN3;              // A lives behind the two accumulators
+constexpr size_t kTc3SmemBytes = 1024 + static_cast<size_t>(kStages3) * kBoxBytesB3 + 512;
+constexpr uint32_t kInstrDesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN3 >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+
+__device__ __forceinline__ void UmmaBf16ATmem(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void TmemStore32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+CosineTcATmemKernel(const __nv_bfloat16 *__restrict__ ref_unit, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks, int k_pad,
+                    int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *smem_b = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages3 * kBoxBytesB3);
+    uint64_t *bar_a = &bars[0];                          // A is in tensor memory (4 epilogue warps arrive)
+    uint64_t *bar_full = &bars[1];                       // [kStages3]
+    uint64_t *bar_empty = &bars[1 + kStages3];           // [kStages3]
+    uint64_t *bar_acc_full = &bars[1 + 2 * kStages3];    // [2]
+    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages3];   // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages3]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+    const int t_begin = blockIdx.y * tiles_per_split;
+    const int t_end = min(n_tiles, t_begin + tiles_per_split);
+
+    if (threadIdx.x == 0) {
+        MbarInit(bar_a, 4);
+        for (int s = 0; s < kStages3; ++s) {
+            MbarInit(&bar_full[s], 1);
+            MbarInit(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            MbarInit(&bar_acc_full[a], 1);
+            MbarInit(&bar_acc_empty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    TcFenceBefore();
+    __syncthreads();
+    TcFenceAfter();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: B only =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    MbarWait(&bar_empty[stage], phase ^ 1u);
+                    MbarExpectTx(&bar_full[stage], kBoxBytesB3);
+                    TmaLoad2D(smem_b + stage * kBoxBytesB3, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN3);
+                    if (++stage == kStages3) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            MbarWait(bar_a, 0);
+            TcFenceAfter();
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
+                TcFenceAfter();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN3);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    MbarWait(&bar_full[stage], phase);
+                    TcFenceAfter();
+                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB3);
+#pragma unroll
+                    for (int k = 0; k < kKBlock / 16; ++k) {
+                        // A: 16 BF16 of every row = 8 TMEM columns per MMA
+                        const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(kTmemColA + (kb * (kKBlock / 16) + k) * 8);
+                        UmmaBf16ATmem(tmem_d, tmem_a, bdesc + static_cast<uint64_t>(2 * k), kInstrDesc3, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    UmmaCommit(&bar_empty[stage]);
+                    if (++stage == kStages3) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                UmmaCommit(&bar_acc_full[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue warps: first park A in tensor memory, then the running top-2 =====================
+        const int quarter = warp & 3;
+        const int row = m_tile * kTileM + quarter * 32 + lane;
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(ref_unit + static_cast<size_t>(row) * k_pad);  // 2 BF16 per word, k ascending
+            const uint32_t tbase_a = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(kTmemColA);
+            for (int c0 = 0; c0 < k_pad / 2; c0 += 32) {
+                uint32_t r[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (row < n_ref) v = __ldg(reinterpret_cast<const uint4 *>(src + c0) + q);
+                    r[4 * q] = v.x, r[4 * q + 1] = v.y, r[4 * q + 2] = v.z, r[4 * q + 3] = v.w;
+                }
+                TmemStore32(tbase_a + static_cast<uint32_t>(c0), r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArrive(bar_a);
+        }
+        float b1 = floor_dot, b2 = -INFINITY;
+        int j1 = -1;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+            MbarWait(&bar_acc_full[acc], acc_phase);
+            TcFenceAfter();
+            const int n0 = t * kTileN3;
+            const bool partial = n0 + kTileN3 > n_cur;
+            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN3);
+            auto reduce_chunk = [&](uint32_t (&r)[32], int chunk) {
+                const int c0 = n0 + chunk * 32;
+                if (partial) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (c0 + c >= n_cur) r[c] = 0xFF800000u;
+                }
+                float m4[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    m4[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+                const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
+                if (m > b1) {
+                    float cb1 = -INFINITY, cb2 = -INFINITY;
+                    int cj = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = __uint_as_float(r[c]);
+                        if (v > cb1) {
+                            cb2 = cb1;
+                            cb1 = v;
+                            cj = c;
+                        } else {
+                            cb2 = fmaxf(cb2, v);
+                        }
+                    }
+                    b2 = fmaxf(b1, cb2);
+                    b1 = cb1;
+                    j1 = c0 + cj;
+                } else {
+                    b2 = fmaxf(b2, m);
+                }
+            };
+            uint32_t ra[32], rb[32];
+            TmemLoad32(tbase, ra);
+            TmemLoadWait(ra);
+#pragma unroll 1
+            for (int chunk = 0; chunk < kTileN3 / 32; chunk += 2) {
+                TmemLoad32(tbase + static_cast<uint32_t>((chunk + 1) * 32), rb);
+                reduce_chunk(ra, chunk);
+                TmemLoadWait(rb);
+                if (chunk + 2 < kTileN3 / 32) TmemLoad32(tbase + static_cast<uint32_t>((chunk + 2) * 32), ra);
+                reduce_chunk(rb, chunk + 1);
+                if (chunk + 2 < kTileN3 / 32) TmemLoadWait(ra);
+            }
+            TcFenceBefore();
+            __syncwarp();
+            if (lane == 0) MbarArrive(&bar_acc_empty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+        if (row < n_ref) {
+            Top2 o;
+            o.b1 = j1 >= 0 ? b1 : -INFINITY;
+            o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;
+            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
+        }
+    }
+
+    TcFenceBefore();
+    __syncthreads();
+    if (warp == 1) {
+        TcFenceAfter();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// =====================================================================================================================
 // CTA-pair variant (cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- execute ONE 256 x 256 x 16 tcgen05.mma per
 // issue.  Each CTA keeps its own 128 reference rows (A) and loads only HALF of every current-set tile (128 of the 256 B rows);
 // the tensor cores of both SMs read both halves.  Per SM that halves the TMA traffic and the shared-memory operand reads of
@@ -770,7 +997,11 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     if (n_ref == 0) return FTK_OK;
     cudaStream_t st = ctx->stream;
     const int k_blocks = (dim + kKBlock - 1) / kKBlock, k_pad = k_blocks * kKBlock;
-    const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + kTileN - 1) / kTileN;
+    // kernel variant: A from tensor memory (192-column tiles) when FTK_COSINE_ATMEM=1, else both operands from shared memory
+    const char *atmem_env = getenv("FTK_COSINE_ATMEM");
+    const bool a_in_tmem = atmem_env && atmem_env[0] == '1';
+    const int tile_n = a_in_tmem ? kTileN3 : kTileN;
+    const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + tile_n - 1) / tile_n;
     // Split the current set across CTAs: one CTA per SM at a time (192 KB of shared memory), so pick the split count whose
     // grid fills whole waves best (ties: fewer splits = more reuse of the resident reference tile).
     int splits = 1;
@@ -811,7 +1042,7 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     int2 *work = reinterpret_cast<int2 *>(n_work + 2);
 
     CUtensorMap map_ref, map_cur;
-    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, kTileN))
+    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, tile_n))
         return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
 
     const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * (dim + 1) + kPrepRows);
@@ -826,7 +1057,15 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     // 20k x 20k x 256): opt-in with FTK_COSINE_2CTA=1, see DESIGN.md.
     const char *pair_env = getenv("FTK_COSINE_2CTA");
     const bool single_cta = !(pair_env && pair_env[0] == '1');
-    if (single_cta) {
+    if (a_in_tmem) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcATmemKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTc3SmemBytes)));
+            attr_set = true;
+        }
+        CosineTcATmemKernel<<<dim3(m_tiles, splits), kTcThreads, kTc3SmemBytes, st>>>(ref_unit, map_cur, n_ref, n_cur, k_blocks, k_pad, tiles_per_split, n_tiles,
+                                                                                    top, n_ref_pad, floor_dot);
+    } else if (single_cta) {
         static bool attr_set = false;
         if (!attr_set) {
             FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
@@ -860,7 +1099,7 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     }
     RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
                                                                                                             n_ref_pad, best, work, n_work);
-    ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * kTileN, best);
+    ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * tile_n, best);
     FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
     ctx->launches += 7;
     ctx->d_last_scan_items = n_work;

@@ -478,10 +478,11 @@ def test_cosine_tensor_path_decides_without_fallback(ctx, oracle):
         assert (got == oracle.match_cosine_force(a, b, 0.1)[1]).all(), (n_ref, n_cur, dim)
 
 
-def test_cosine_cta_pair_kernel_opt_in(ctx, oracle, monkeypatch):
-    """The cta_group::2 (CTA pair) tensor-core kernel, FTK_COSINE_2CTA=1, stays exact although it is not the default: odd and even
-    numbers of 128-row tiles, partial column tiles, several K."""
-    monkeypatch.setenv("FTK_COSINE_2CTA", "1")
+@pytest.mark.parametrize("env", ["FTK_COSINE_2CTA", "FTK_COSINE_ATMEM"])
+def test_cosine_experimental_kernels_opt_in(ctx, oracle, monkeypatch, env):
+    """The two opt-in tensor-core variants -- cta_group::2 (CTA pair) and A-operand-from-TMEM -- stay exact although neither is the
+    default: odd and even numbers of 128-row tiles, partial column tiles, several K."""
+    monkeypatch.setenv(env, "1")
     for n_ref, n_cur, dim in [(130, 170, 256), (400, 333, 256), (1000, 2100, 128), (257, 700, 64), (33, 40, 100)]:
         ref, cur = S.make_float_sets(n_ref, n_cur, dim=dim, seed=n_ref + dim)
         m = ft.CosineMatcher(ctx)
