@@ -356,6 +356,33 @@ def run_extras(ctx, L, torch, local_rank, steps):
     out["dense_flow_752x480_4_levels"] = {"ms": ms, "pixels_per_s": ROWS * COLS / (ms * 1e-3), "mean_abs_flow_px": float(d_fr.abs().mean().item())}
     pyr_df.close()
 
+    # ---- front end (parity unpinned): detect 300 Harris corners (demo options) on the device pyramid + BRIEF-256 ----
+    img0 = S.make_pair(ROWS, COLS, 10, pair_id=301)[0]
+    pyr_det = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, 1)
+    pyr_det.SetRawImages(img0[None])
+    pyr_det.CreateImagePyramid()
+    det = ft.FeaturePointHarrisDetector(ctx)
+    d_duv = torch.zeros((300, 2), dtype=torch.float32, device=dev)
+    d_dresp = torch.zeros((300,), dtype=torch.float32, device=dev)
+    n_found = C.c_int32(0)
+    for thr, tag in ((40.0, "demo_threshold_40"), (1e5, "threshold_1e5")):
+        det.options().kMinValidResponse = thr
+        dprm2 = det._params()
+        ms = timeit(lambda: ctx.check(L.ftk_detect_features(ctx._h, C.byref(dprm2), pyr_det._h, 0, None, 0, 300, vp(d_duv.data_ptr()), vp(d_dresp.data_ptr()),
+                                                            C.byref(n_found), _capi.FLAG_DEVICE_POINTERS)), max(2, steps // 2))
+        out[f"detect_300_harris_752x480_{tag}"] = {"ms": ms, "found": int(n_found.value), "pixels_per_s": ROWS * COLS / (ms * 1e-3)}
+    d_resp_map = torch.empty((ROWS, COLS), dtype=torch.float32, device=dev)
+    ms = timeit(lambda: ctx.check(L.ftk_detect_response(ctx._h, C.byref(dprm2), pyr_det._h, 0, vp(d_resp_map.data_ptr()), _capi.FLAG_DEVICE_POINTERS)), steps * 2)
+    out["harris_response_752x480"] = {"ms": ms, "gb_per_s": 5.0 * ROWS * COLS / (ms * 1e-3) / 1e9, "algorithmic_bytes": 5 * ROWS * COLS}
+    pattern = ft.brief_pattern(256, 8, 0)
+    uv_many = np.tile(d_duv.cpu().numpy(), (200, 1))  # 60 000 features
+    d_many = torch.from_numpy(uv_many).to(dev)
+    d_desc = torch.empty((len(uv_many), 8), dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ctx.check(L.ftk_describe_brief(ctx._h, pyr_det._h, 0, vp(d_many.data_ptr()), len(uv_many), vp(pattern.ctypes.data), 256, 8,
+                                                       vp(d_desc.data_ptr()), None, _capi.FLAG_DEVICE_POINTERS)), steps * 2)
+    out["brief256_60k_features"] = {"ms": ms, "descriptors_per_s": len(uv_many) / (ms * 1e-3)}
+    pyr_det.close()
+
     # ---- score-matrix mutual arg-max (NNFeatureMatcher post-processing): HBM bound, 4 B per matrix element ----
     for n in (2048, 12288):  # LightGlue's usual size (16 MB, L2 resident) and a matrix far larger than L2 (604 MB)
         d_s = torch.randn((n, n), dtype=torch.float32, device=dev) * 2.0 - 6.0
@@ -390,8 +417,11 @@ def cpu_extras(out):
     out["direct_method_600_pairs_x_300_features"]["cpu_reference"] = {"pairs_per_s": 1.0 / dt, "sample": "1 frame pair x 300 features, 1 thread", "kind": kind}
     dt = clock(lambda: lib_cpu.dense_flow_track(po.make_dense_flow_params(), rl, cl))
     out["dense_flow_752x480_4_levels"]["cpu_reference"] = {"pixels_per_s": ROWS * COLS / dt, "sample": "1 frame pair, 1 thread", "kind": kind}
-    scores = (np.random.default_rng(1).normal(-6, 2, (2048, 2048))).astype(np.float32)
     oc = po.OracleLib()
+    img0 = S.make_pair(ROWS, COLS, 10, pair_id=301)[0]
+    dt = clock(lambda: oc.detect_features(po.make_detector_params("harris", 1, 0.04, 40.0, 20), img0, 300))
+    out["detect_300_harris_752x480_demo_threshold_40"]["cpu_reference"] = {"ms": dt * 1e3, "sample": "1 image, 1 thread", "kind": "port (parity unpinned)"}
+    scores = (np.random.default_rng(1).normal(-6, 2, (2048, 2048))).astype(np.float32)
     dt = clock(lambda: oc.mutual_scores(scores, -3.0))
     out["mutual_scores_2048x2048"]["cpu_reference"] = {"ms": dt * 1e3, "sample": "2048 x 2048, 1 thread", "kind": "port"}
 

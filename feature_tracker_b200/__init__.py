@@ -5,7 +5,7 @@ thin host-side mirror of the reference's C++ interface used by the tests and the
 """
 from . import _capi  # noqa: F401
 from .api import (  # noqa: F401
-    BriefMatcher, Context, CosineMatcher, DenseOpticalFlow, DescriptorMatcher, DirectMethod, DirectMethodMethod, DirectMethodOptions, DiskMatcher, FtkError, ImagePyramidBatch, MatcherOptions, NNFeatureMatcher, OpticalFlow,
+    BriefDescriptor, BriefMatcher, Context, CosineMatcher, DenseOpticalFlow, DescriptorMatcher, DirectMethod, DirectMethodMethod, DirectMethodOptions, DiskMatcher, FeaturePointHarrisDetector, FeaturePointShiTomasDetector, FtkError, ImagePyramidBatch, MatcherOptions, NNFeatureMatcher, OpticalFlow,
     OpticalFlowAffineKlt, OpticalFlowBasicKlt, OpticalFlowLssdKlt, OpticalFlowMethod, OpticalFlowOptions, SuperpointMatcher, TrackStatus,
-    default_context, pack_brief,
+    brief_pattern, default_context, pack_brief,
 )

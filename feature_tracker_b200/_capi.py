@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "ftk_track_image_pairs", "ftk_track_image_pairs_multi", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
     "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track", "ftk_dense_flow_params_default", "ftk_dense_flow_track",
+    "ftk_detector_params_default", "ftk_detect_features", "ftk_detect_response", "ftk_brief_pattern_default", "ftk_describe_brief",
 ]
 
 
@@ -72,6 +73,12 @@ class DenseFlowParams(C.Structure):
     _fields_ = [("max_iteration", C.c_int32), ("half_patch_size", C.c_int32), ("max_converge_step", C.c_float), ("max_delta_flow_step", C.c_float)]
 
 
+class DetectorParams(C.Structure):
+    """ftk_detector_params (include/ftk_c.h): FeaturePointDetector options by the names the reference's call sites use."""
+
+    _fields_ = [("kind", C.c_int32), ("half_patch", C.c_int32), ("harris_k", C.c_float), ("min_response", C.c_float), ("min_distance", C.c_int32)]
+
+
 def load_library():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -106,6 +113,11 @@ def load_library():
         "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_dense_flow_params_default": (None, [P(DenseFlowParams)]),
         "ftk_dense_flow_track": (C.c_int, [vp, P(DenseFlowParams), vp, vp, i32, i32, vp, vp, u32]),
+        "ftk_detector_params_default": (None, [P(DetectorParams)]),
+        "ftk_detect_features": (C.c_int, [vp, P(DetectorParams), vp, i32, vp, i32, i32, vp, vp, P(i32), u32]),
+        "ftk_detect_response": (C.c_int, [vp, P(DetectorParams), vp, i32, vp, u32]),
+        "ftk_brief_pattern_default": (None, [i32, i32, u32, vp]),
+        "ftk_describe_brief": (C.c_int, [vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, u32]),
         "ftk_direct_params_default": (None, [P(DirectParams)]),
         "ftk_direct_method_track": (C.c_int, [vp, P(DirectParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]),
         "ftk_match_mutual_scores": (C.c_int, [vp, vp, i32, i32, f32, vp, u32]),

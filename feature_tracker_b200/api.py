@@ -698,3 +698,115 @@ class DenseOpticalFlow:
         ok = self.ctx.check(rc, soft=(_capi.ERR_LEVEL_MISMATCH,))
         return ok, fr, fc
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Feature detection + BRIEF description.  Class / option names follow the reference's call sites
+# (test/test_descriptor_matcher_brief.cpp:59-76, test/test_optical_flow.cpp:60-66); the classes themselves belong to the absent
+# sibling repository Feature_Detector, so parity is unpinned: the checker is oracle/ftk_oracle.c's restatement of the published
+# algorithm (see include/ftk_c.h).
+# ---------------------------------------------------------------------------------------------------------------------------
+class FeaturePointDetectorOptions:
+    def __init__(self):
+        self.kMinValidResponse = 40.0
+        self.kMinFeatureDistance = 20
+        self.kHalfPatchSize = 1
+        self.kHarrisK = 0.04
+
+
+class FeaturePointHarrisDetector:
+    """feature_detector::FeaturePointHarrisDetector as the reference uses it: options().kMinFeatureDistance / kMinValidResponse and
+    DetectGoodFeatures(image, needed, features)."""
+
+    KIND = 0
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._options = FeaturePointDetectorOptions()
+
+    def options(self):
+        return self._options
+
+    def _params(self):
+        o = self._options
+        p = _capi.DetectorParams()
+        p.kind, p.half_patch, p.harris_k = self.KIND, int(o.kHalfPatchSize), float(o.kHarrisK)
+        p.min_response, p.min_distance = float(o.kMinValidResponse), int(o.kMinFeatureDistance)
+        return p
+
+    def DetectGoodFeatures(self, image, needed_feature_num, features=None, image_index=0, return_response=False):
+        """`image` is an ImagePyramid (level 0 is searched; the trackers then reuse it).  `features` already held by the caller block
+        their neighbourhood and are kept: returns (ok, features) with the new ones appended, so that at most `needed_feature_num`
+        are held afterwards (the reference's in/out vector)."""
+        existing = np.zeros((0, 2), np.float32) if features is None else np.ascontiguousarray(features, np.float32).reshape(-1, 2)
+        want = max(0, int(needed_feature_num) - len(existing))
+        out = np.zeros((max(want, 1), 2), np.float32)
+        resp = np.zeros(max(want, 1), np.float32)
+        n_out = C.c_int32(0)
+        prm = self._params()
+        rc = lib().ftk_detect_features(self.ctx._h, C.byref(prm), image._h, int(image_index), _ptr(existing) if len(existing) else None, len(existing),
+                                       want, _ptr(out), _ptr(resp), C.byref(n_out), 0)
+        ok = self.ctx.check(rc)
+        merged = np.concatenate([existing, out[:n_out.value]], axis=0)
+        if return_response:
+            return ok, merged, resp[:n_out.value]
+        return ok, merged
+
+    def ComputeResponse(self, image, image_index=0):
+        """The response map of level 0 (rows x cols float32, -inf where the window leaves the image)."""
+        out = np.zeros((image.rows, image.cols), np.float32)
+        prm = self._params()
+        self.ctx.check(lib().ftk_detect_response(self.ctx._h, C.byref(prm), image._h, int(image_index), _ptr(out), 0))
+        return out
+
+
+class FeaturePointShiTomasDetector(FeaturePointHarrisDetector):
+    """Same selection, response = smaller eigenvalue of the structure tensor."""
+
+    KIND = 1
+
+
+class BriefDescriptorOptions:
+    def __init__(self):
+        self.kLength = 256
+        self.kHalfPatchSize = 8
+        self.kPatternSeed = 0
+
+
+def brief_pattern(length, half_patch, seed=0):
+    """The library's default pair list, int8 [length][4] = (drow_a, dcol_a, drow_b, dcol_b)."""
+    pattern = np.zeros((int(length), 4), np.int8)
+    lib().ftk_brief_pattern_default(int(length), int(half_patch), int(seed) & 0xFFFFFFFF, _ptr(pattern))
+    return pattern
+
+
+class BriefDescriptor:
+    """feature_detector::BriefDescriptor as the reference uses it: options().kLength / kHalfPatchSize and Compute(image, features,
+    descriptors).  Descriptors come back packed (uint32 [n][kLength / 32]), the layout the Hamming matchers take."""
+
+    def __init__(self, ctx=None, pattern=None):
+        self.ctx = ctx or default_context()
+        self._options = BriefDescriptorOptions()
+        self._pattern = None if pattern is None else np.ascontiguousarray(pattern, np.int8).reshape(-1, 4)
+
+    def options(self):
+        return self._options
+
+    def pattern(self):
+        o = self._options
+        if self._pattern is not None:
+            return self._pattern
+        return brief_pattern(o.kLength, o.kHalfPatchSize, o.kPatternSeed)
+
+    def Compute(self, image, features, image_index=0):
+        """Returns (ok, descriptors, valid)."""
+        o = self._options
+        uv = np.ascontiguousarray(features, np.float32).reshape(-1, 2)
+        pattern = self.pattern()
+        n_bits = len(pattern)
+        desc = np.zeros((len(uv), max(n_bits // 32, 1)), np.uint32)
+        valid = np.zeros(len(uv), np.uint8)
+        rc = lib().ftk_describe_brief(self.ctx._h, image._h, int(image_index), _ptr(uv) if len(uv) else None, len(uv), _ptr(pattern), n_bits,
+                                      int(o.kHalfPatchSize), _ptr(desc) if len(uv) else None, _ptr(valid) if len(uv) else None, 0)
+        ok = self.ctx.check(rc)
+        return ok, desc, valid

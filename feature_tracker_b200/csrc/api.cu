@@ -104,6 +104,33 @@ void ftk_dense_flow_params_default(ftk_dense_flow_params *p) {
     p->max_delta_flow_step = 1.0f;
 }
 
+void ftk_detector_params_default(ftk_detector_params *p) {
+    if (!p) return;
+    p->kind = FTK_DETECTOR_HARRIS;
+    p->half_patch = 1;
+    p->harris_k = 0.04f;
+    p->min_response = 40.0f;  // the values test/test_descriptor_matcher_brief.cpp:60-61 sets
+    p->min_distance = 20;
+}
+
+// xorshift32 (13, 17, 5); coordinate = draw % (2 half + 1) - half in the order (drow_a, dcol_a, drow_b, dcol_b); a pair with
+// a == b is redrawn.  oracle/ftk_oracle.c holds the checker's own copy of this definition.
+void ftk_brief_pattern_default(int32_t n_bits, int32_t half_patch, uint32_t seed, int8_t *pattern) {
+    if (!pattern || half_patch < 0 || half_patch > 127) return;
+    uint32_t x = seed ? seed : 0x9E3779B9u;
+    const uint32_t span = static_cast<uint32_t>(2 * half_patch + 1);
+    for (int32_t k = 0; k < n_bits; ++k) {
+        int8_t v[4];
+        do {
+            for (int j = 0; j < 4; ++j) {
+                x ^= x << 13, x ^= x >> 17, x ^= x << 5;
+                v[j] = static_cast<int8_t>(static_cast<int32_t>(x % span) - half_patch);
+            }
+        } while (half_patch > 0 && v[0] == v[2] && v[1] == v[3]);
+        for (int j = 0; j < 4; ++j) pattern[4 * k + j] = v[j];
+    }
+}
+
 void ftk_direct_params_default(ftk_direct_params *p) {
     if (!p) return;
     p->max_track_points = 500;  // direct_method_tracker.h:20-28
@@ -147,7 +174,7 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < 2; ++b) {
@@ -701,6 +728,82 @@ int ftk_dense_flow_track(ftk_context *ctx, const ftk_dense_flow_params *params, 
     if (!on_device) {
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(flow_row, d_r, sizeof(float) * n0, cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(flow_col, d_c, sizeof(float) * n0, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FTK_OK;
+}
+
+int ftk_detect_response(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, float *response, uint32_t flags) {
+    if (!ctx || !params || !pyr || !response) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const size_t n = static_cast<size_t>(pyr->view.rows[0]) * pyr->view.cols[0];
+    float *d_response = response;
+    if (!on_device) {
+        if (int rc = EnsureDevice(ctx, ctx->d_det_response, sizeof(float) * n)) return rc;
+        d_response = static_cast<float *>(ctx->d_det_response.ptr);
+    }
+    if (int rc = ftk::LaunchDetectResponse(ctx, *params, pyr->view, image, d_response)) return rc;
+    if (!on_device) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(response, d_response, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return FTK_OK;
+}
+
+int ftk_detect_features(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, const float *existing_uv,
+                        int32_t n_existing, int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags) {
+    if (!ctx || !params || !pyr || !n_out || n_existing < 0 || needed < 0 || (n_existing > 0 && !existing_uv) || (needed > 0 && !out_uv))
+        return FTK_ERR_INVALID_ARGUMENT;
+    *n_out = 0;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const float2 *d_existing = nullptr;
+    if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(existing_uv), static_cast<size_t>(n_existing), on_device, &d_existing)) return rc;
+    float2 *d_uv = reinterpret_cast<float2 *>(out_uv);
+    float *d_resp = out_response;
+    if (!on_device) {
+        if (int rc = EnsureDevice(ctx, ctx->d_det_out, sizeof(float) * 3 * static_cast<size_t>(needed ? needed : 1))) return rc;
+        d_uv = static_cast<float2 *>(ctx->d_det_out.ptr);
+        d_resp = reinterpret_cast<float *>(d_uv + needed);
+    }
+    int n = 0;
+    if (int rc = ftk::LaunchDetectFeatures(ctx, *params, pyr->view, image, d_existing, n_existing, needed, d_uv, d_resp, &n)) return rc;
+    if (!on_device && n > 0) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_uv, d_uv, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_response) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_response, d_resp, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    return FTK_OK;
+}
+
+int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
+                       int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags) {
+    if (!ctx || !pyr || !pattern || n < 0 || (n > 0 && (!uv || !desc))) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_bits <= 0 || n_bits % 32 != 0 || n_bits > 1024) return SetError(ctx, FTK_ERR_UNSUPPORTED, "BRIEF length %d is not a multiple of 32 in 32..1024", n_bits);
+    if (half_patch < 0 || half_patch > 127) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "BRIEF half patch %d", half_patch);
+    for (int32_t k = 0; k < 4 * n_bits; ++k)
+        if (pattern[k] < -half_patch || pattern[k] > half_patch) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "BRIEF pair %d leaves the +-%d patch", k / 4, half_patch);
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const int words = n_bits / 32;
+    const char4 *d_pattern = nullptr;
+    if (int rc = Stage(ctx, ctx->d_det_pattern, reinterpret_cast<const char4 *>(pattern), static_cast<size_t>(n_bits), false, &d_pattern)) return rc;
+    const float2 *d_uv = nullptr;
+    if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(uv), static_cast<size_t>(n), on_device, &d_uv)) return rc;
+    uint32_t *d_desc = desc;
+    uint8_t *d_valid = valid;
+    if (!on_device) {
+        if (int rc = EnsureDevice(ctx, ctx->d_desc_ref, sizeof(uint32_t) * static_cast<size_t>(n ? n : 1) * words)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_status, static_cast<size_t>(n ? n : 1))) return rc;
+        d_desc = static_cast<uint32_t *>(ctx->d_desc_ref.ptr);
+        d_valid = static_cast<uint8_t *>(ctx->d_status.ptr);
+    }
+    if (int rc = ftk::LaunchDescribeBrief(ctx, pyr->view, image, d_uv, n, d_pattern, n_bits, half_patch, d_desc, d_valid)) return rc;
+    if (!on_device && n > 0) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(desc, d_desc, sizeof(uint32_t) * static_cast<size_t>(n) * words, cudaMemcpyDeviceToHost, ctx->stream));
+        if (valid) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(valid, d_valid, static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return FTK_OK;

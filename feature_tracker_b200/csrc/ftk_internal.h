@@ -62,6 +62,7 @@ struct ftk_context {
     FtkBuffer d_back_uv, d_back_status;  // forward-backward pass scratch
     FtkBuffer d_dm_K, d_dm_points, d_dm_q, d_dm_p;  // direct-method staging
     FtkBuffer d_flow;  // dense-flow staging (2 planes)
+    FtkBuffer d_det_response, d_det_state, d_det_cand, d_det_keys, d_det_tmp, d_det_out, d_det_pattern;  // detector / BRIEF scratch
     FtkBuffer d_desc_ref, d_desc_cur, d_idx, d_pred_uv, d_pos_cur, d_work0, d_work1, d_work2, d_work3;
 };
 
@@ -117,6 +118,13 @@ int LaunchDirectMethod(ftk_context *ctx, const ftk_direct_params &p, const Pyram
 // dense_flow.cu
 int LaunchDenseFlow(ftk_context *ctx, const ftk_dense_flow_params &p, const PyramidView &ref, const PyramidView &cur, int ref_image, int cur_image,
                     bool single_level, bool use_initial_flow, float *d_flow_r, float *d_flow_c);
+
+// detect.cu: corner response, greedy min-distance selection, BRIEF bits (level 0 of one pyramid image)
+int LaunchDetectResponse(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int image, float *d_response);
+int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int image, const float2 *d_existing, int n_existing,
+                         int needed, float2 *d_out_uv, float *d_out_response, int *n_out);
+int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int image, const float2 *d_uv, int n, const char4 *d_pattern, int n_bits,
+                        int half_patch, uint32_t *d_desc, uint8_t *d_valid);
 
 // match.cu
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);

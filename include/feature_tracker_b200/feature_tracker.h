@@ -507,4 +507,89 @@ private:
 
 }  // namespace feature_tracker
 
+// The callers' upstream step (test/test_descriptor_matcher_brief.cpp:59-76, test/test_optical_flow.cpp:60-66).  The reference takes
+// these classes from the sibling repository Feature_Detector, which is not in its tree: names and option names follow the call
+// sites, the arithmetic is the published algorithm documented in ftk_c.h (parity unpinned).  `image` is the device pyramid the
+// trackers use (its level 0 is searched), so detection costs no second upload.
+namespace feature_detector {
+
+using Vec2 = ::feature_tracker::Vec2;
+using BriefType = std::vector<uint8_t>;  // element-wise boolean container, as DescriptorMatcher<BriefType> expects
+
+template <int Kind>
+class FeaturePointDetector {
+public:
+    struct Options {
+        float kMinValidResponse = 40.0f;
+        int32_t kMinFeatureDistance = 20;
+        int32_t kHalfPatchSize = 1;
+        float kHarrisK = 0.04f;
+    };
+    // `features` is in/out like the reference's: what it holds on entry is kept and blocks its neighbourhood; new features are
+    // appended in falling response order until `needed_feature_num` are held.
+    bool DetectGoodFeatures(const ::feature_tracker::ImagePyramid &image, const uint32_t needed_feature_num, std::vector<Vec2> &features) {
+        if (!image.handle()) return false;
+        const size_t n_old = features.size();
+        if (n_old >= needed_feature_num) return true;
+        const int32_t want = static_cast<int32_t>(needed_feature_num - n_old);
+        std::vector<float> existing(2 * n_old), found(2 * static_cast<size_t>(want));
+        for (size_t i = 0; i < n_old; ++i) existing[2 * i] = features[i].x(), existing[2 * i + 1] = features[i].y();
+        ftk_detector_params p;
+        p.kind = Kind;
+        p.half_patch = options_.kHalfPatchSize;
+        p.harris_k = options_.kHarrisK;
+        p.min_response = options_.kMinValidResponse;
+        p.min_distance = options_.kMinFeatureDistance;
+        int32_t n_new = 0;
+        if (ftk_detect_features(::feature_tracker::Device::Get(), &p, image.handle(), 0, n_old ? existing.data() : nullptr, static_cast<int32_t>(n_old), want,
+                                found.data(), nullptr, &n_new, 0u) != FTK_OK)
+            return false;
+        for (int32_t i = 0; i < n_new; ++i) features.emplace_back(found[2 * i], found[2 * i + 1]);
+        return true;
+    }
+    Options &options() { return options_; }
+    const Options &options() const { return options_; }
+
+private:
+    Options options_;
+};
+using FeaturePointHarrisDetector = FeaturePointDetector<FTK_DETECTOR_HARRIS>;
+using FeaturePointShiTomasDetector = FeaturePointDetector<FTK_DETECTOR_SHI_TOMASI>;
+
+class BriefDescriptor {
+public:
+    struct Options {
+        int32_t kLength = 256;
+        int32_t kHalfPatchSize = 8;
+        uint32_t kPatternSeed = 0;
+    };
+    // descriptors[i][k] = bit k of feature i; a feature whose patch leaves the image gets an all-zero descriptor (the C ABI's
+    // convention; ftk_describe_brief also reports a validity flag).
+    bool Compute(const ::feature_tracker::ImagePyramid &image, const std::vector<Vec2> &features, std::vector<BriefType> &descriptors) {
+        descriptors.clear();
+        if (!image.handle() || options_.kLength <= 0 || options_.kLength % 32 != 0) return false;
+        const size_t n = features.size(), words = static_cast<size_t>(options_.kLength / 32);
+        std::vector<int8_t> pattern(4 * static_cast<size_t>(options_.kLength));
+        ftk_brief_pattern_default(options_.kLength, options_.kHalfPatchSize, options_.kPatternSeed, pattern.data());
+        std::vector<float> uv(2 * n);
+        for (size_t i = 0; i < n; ++i) uv[2 * i] = features[i].x(), uv[2 * i + 1] = features[i].y();
+        std::vector<uint32_t> packed(n * words);
+        if (ftk_describe_brief(::feature_tracker::Device::Get(), image.handle(), 0, uv.data(), static_cast<int32_t>(n), pattern.data(), options_.kLength,
+                               options_.kHalfPatchSize, packed.data(), nullptr, 0u) != FTK_OK)
+            return false;
+        descriptors.assign(n, BriefType(static_cast<size_t>(options_.kLength), 0));
+        for (size_t i = 0; i < n; ++i) {
+            for (int32_t k = 0; k < options_.kLength; ++k) descriptors[i][k] = (packed[i * words + (k >> 5)] >> (k & 31)) & 1u;
+        }
+        return true;
+    }
+    Options &options() { return options_; }
+    const Options &options() const { return options_; }
+
+private:
+    Options options_;
+};
+
+}  // namespace feature_detector
+
 #endif

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTK_ABI_VERSION 2
+#define FTK_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------------------------ */
 #define FTK_OK 0
@@ -197,6 +197,41 @@ void ftk_dense_flow_params_default(ftk_dense_flow_params *params);
  * the caller's matrices have the wrong size (:18-23: start from zero). */
 int ftk_dense_flow_track(ftk_context *ctx, const ftk_dense_flow_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t ref_image,
                          int32_t cur_image, float *flow_row, float *flow_col, uint32_t flags);
+
+/* ---- feature detection + BRIEF description (the callers' upstream step
+ *      feature_detector::FeaturePointHarrisDetector::DetectGoodFeatures / feature_detector::BriefDescriptor::Compute,
+ *      test/test_descriptor_matcher_brief.cpp:59-76, test/test_optical_flow.cpp:60-66) -------------------------------------
+ * PARITY UNPINNED: those classes live in the sibling repository Feature_Detector, which is absent from the reference tree
+ * (CMakeLists.txt:24-29) and unpinned.  The option names follow the call sites; the arithmetic is the published algorithm as
+ * frozen in the detector section of oracle/ftk_oracle.c, to which these entry points are bit-exact. */
+#define FTK_DETECTOR_HARRIS 0
+#define FTK_DETECTOR_SHI_TOMASI 1
+typedef struct ftk_detector_params {
+    int32_t kind;         /* FTK_DETECTOR_* */
+    int32_t half_patch;   /* structure-tensor window half size, 1..3 */
+    float harris_k;       /* 0.04; 0 <= k <= 1 */
+    float min_response;   /* kMinValidResponse (finite) */
+    int32_t min_distance; /* kMinFeatureDistance: a taken feature blocks |drow| < d and |dcol| < d */
+} ftk_detector_params;
+void ftk_detector_params_default(ftk_detector_params *params);
+/* Detects up to `needed` features on level 0 of image `image` of `pyr` (the pyramid the trackers use: no second upload).
+ * existing_uv [n_existing][2] (x, y; may be NULL when n_existing == 0) are features the caller already tracks: they block
+ * their neighbourhood and are not returned.  out_uv [needed][2] receives (x = col, y = row) in falling response order,
+ * out_response [needed] the responses (may be NULL), *n_out (HOST pointer, always) the count.  FTK_FLAG_DEVICE_POINTERS
+ * applies to existing_uv / out_uv / out_response.  The call synchronises the context. */
+int ftk_detect_features(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, const float *existing_uv,
+                        int32_t n_existing, int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags);
+/* The response map alone: rows x cols tightly packed floats, -inf where the window leaves the image. */
+int ftk_detect_response(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, float *response, uint32_t flags);
+/* Default BRIEF pair list (HOST memory): pattern [n_bits][4] = (drow_a, dcol_a, drow_b, dcol_b) inside +-half_patch, from
+ * xorshift32 seeded with `seed`. */
+void ftk_brief_pattern_default(int32_t n_bits, int32_t half_patch, uint32_t seed, int8_t *pattern);
+/* BRIEF descriptors of n features on level 0 of image `image`: bit k = I(p + a_k) < I(p + b_k) at the truncated position p;
+ * desc [n][n_bits / 32] in the packed layout ftk_match_hamming_* takes (n_bits a multiple of 32, <= 1024); a feature whose
+ * +-half_patch patch leaves the image gets zeros and valid[i] = 0 (valid may be NULL).  `pattern` is always a HOST pointer;
+ * FTK_FLAG_DEVICE_POINTERS applies to uv / desc / valid. */
+int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
+                       int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags);
 
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of

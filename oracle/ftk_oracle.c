@@ -1493,3 +1493,147 @@ int ftko_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, 
     free(fc);
     return 1;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Feature detection + BRIEF description -- PARITY UNPINNED.
+ * The reference calls feature_detector::FeaturePointHarrisDetector::DetectGoodFeatures and feature_detector::BriefDescriptor::
+ * Compute (test/test_descriptor_matcher_brief.cpp:59-76, test/test_optical_flow.cpp:60-66), which live in the sibling
+ * repository Feature_Detector (CMakeLists.txt:24-29); that repository is not vendored, not pinned and not present, and the
+ * reference holds no fixtures of detector output.  What is frozen here is the published algorithm behind those names, under
+ * the option names the call sites use:
+ *   response  Harris & Stephens 1988 / Shi & Tomasi 1994 on the (2h+1)^2 box-summed structure tensor of central differences
+ *             (gx = I(r,c+1)-I(r,c-1), gy = I(r+1,c)-I(r-1,c); integer sums, then a = Sxx/(4n), b = Sxy/(4n), c = Syy/(4n));
+ *             Harris = a c - b b - k (a+c)^2, Shi-Tomasi = ((a+c) - sqrt((a-c)^2 + 4 b b)) / 2, fp32, no contraction;
+ *             defined where the whole window and its gradients are inside the image, -inf elsewhere.
+ *   selection candidates = pixels with response >= kMinValidResponse, visited by falling response (ties: row-major index);
+ *             a candidate is taken unless an already taken or pre-existing feature lies within |drow| < kMinFeatureDistance
+ *             and |dcol| < kMinFeatureDistance (pre-existing features count at their truncated pixel, and only when inside
+ *             the image); stops after `needed` features.  Output (x = col, y = row).
+ *   BRIEF     Calonder et al. 2010: bit k = I(p + a_k) < I(p + b_k) for a fixed list of offset pairs inside +-kHalfPatchSize,
+ *             on the raw image at the truncated feature position; a feature whose patch leaves the image gets an all-zero
+ *             descriptor and valid = 0.  Word w holds pairs 32w .. 32w+31, least significant bit first (the packed layout of
+ *             ftko_match_brief_* / ftk_match_hamming256).  The pair list is an INPUT, so a caller that owns the upstream list
+ *             can pass it; ftko_brief_pattern is the default list (xorshift32, documented below).
+ * ---------------------------------------------------------------------------------------------------------- */
+static float detector_response_at(const ftko_detector_params *p, const uint8_t *image, int32_t cols, int32_t r, int32_t c) {
+    const int32_t h = p->half_patch;
+    int32_t sxx = 0, syy = 0, sxy = 0;
+    for (int32_t dr = -h; dr <= h; ++dr) {
+        for (int32_t dc = -h; dc <= h; ++dc) {
+            const uint8_t *q = image + (size_t)(r + dr) * cols + (c + dc);
+            const int32_t gx = (int32_t)q[1] - (int32_t)q[-1], gy = (int32_t)q[cols] - (int32_t)q[-cols];
+            sxx += gx * gx, syy += gy * gy, sxy += gx * gy;
+        }
+    }
+    const float inv = 1.0f / (float)(4 * (2 * h + 1) * (2 * h + 1));
+    const float a = (float)sxx * inv, b = (float)sxy * inv, cc = (float)syy * inv;
+    if (p->kind == 0) {
+        const float det = a * cc - b * b, tr = a + cc;
+        return det - p->harris_k * (tr * tr);
+    }
+    const float d = a - cc;
+    const float disc = d * d + 4.0f * (b * b);
+    return 0.5f * ((a + cc) - sqrtf(disc));
+}
+
+int ftko_detect_response(const ftko_detector_params *params, const uint8_t *image, int32_t rows, int32_t cols, float *response) {
+    if (params->half_patch < 1 || params->half_patch > 3 || rows <= 0 || cols <= 0) return 0;
+    const int32_t m = params->half_patch + 1;
+    for (int32_t r = 0; r < rows; ++r)
+        for (int32_t c = 0; c < cols; ++c)
+            response[(size_t)r * cols + c] =
+                (r >= m && r < rows - m && c >= m && c < cols - m) ? detector_response_at(params, image, cols, r, c) : -INFINITY;
+    return 1;
+}
+
+typedef struct {
+    float response;
+    int32_t index;
+} detector_candidate_t;
+
+static int detector_candidate_cmp(const void *pa, const void *pb) {
+    const detector_candidate_t *a = (const detector_candidate_t *)pa, *b = (const detector_candidate_t *)pb;
+    if (a->response != b->response) return a->response > b->response ? -1 : 1;
+    return a->index < b->index ? -1 : (a->index > b->index ? 1 : 0);
+}
+
+static void detector_mask(uint8_t *mask, int32_t rows, int32_t cols, int32_t r, int32_t c, int32_t dist) {
+    for (int32_t rr = r - (dist - 1); rr <= r + (dist - 1); ++rr)
+        for (int32_t qc = c - (dist - 1); qc <= c + (dist - 1); ++qc)
+            if (rr >= 0 && rr < rows && qc >= 0 && qc < cols) mask[(size_t)rr * cols + qc] = 1;
+}
+
+/* Returns the number of features written (<= needed), -1 on bad parameters. */
+int ftko_detect_features(const ftko_detector_params *params, const uint8_t *image, int32_t rows, int32_t cols, const float *existing_uv,
+                         int32_t n_existing, int32_t needed, float *out_uv, float *out_response) {
+    const size_t n = (size_t)rows * cols;
+    float *response = (float *)malloc(sizeof(float) * (n ? n : 1));
+    if (!ftko_detect_response(params, image, rows, cols, response)) {
+        free(response);
+        return -1;
+    }
+    uint8_t *mask = (uint8_t *)calloc(n, 1);
+    detector_candidate_t *cand = (detector_candidate_t *)malloc(sizeof(detector_candidate_t) * n);
+    const int32_t dist = params->min_distance;
+    for (int32_t i = 0; i < n_existing; ++i) { /* (int) casts truncate, like the reference's pixel look-ups */
+        const float x = existing_uv[2 * i], y = existing_uv[2 * i + 1];
+        if (!(x >= 0.0f && y >= 0.0f && x < (float)cols && y < (float)rows)) continue; /* outside the image (or NaN): masks nothing */
+        if (dist > 0) detector_mask(mask, rows, cols, (int32_t)y, (int32_t)x, dist);
+    }
+    size_t n_cand = 0;
+    for (size_t i = 0; i < n; ++i)
+        if (response[i] >= params->min_response) cand[n_cand].response = response[i], cand[n_cand].index = (int32_t)i, ++n_cand;
+    qsort(cand, n_cand, sizeof(detector_candidate_t), detector_candidate_cmp);
+    int32_t n_out = 0;
+    for (size_t k = 0; k < n_cand && n_out < needed; ++k) {
+        if (mask[cand[k].index]) continue;
+        const int32_t r = cand[k].index / cols, c = cand[k].index % cols;
+        out_uv[2 * n_out] = (float)c, out_uv[2 * n_out + 1] = (float)r;
+        if (out_response) out_response[n_out] = cand[k].response;
+        ++n_out;
+        if (dist > 0) detector_mask(mask, rows, cols, r, c, dist);
+    }
+    free(cand);
+    free(mask);
+    free(response);
+    return n_out;
+}
+
+/* Default pair list: xorshift32 (13, 17, 5) seeded with `seed` (0 -> 0x9E3779B9); every coordinate = draw % (2 half + 1) - half,
+ * in the order (drow_a, dcol_a, drow_b, dcol_b) per pair; a pair with a == b is redrawn. */
+void ftko_brief_pattern(int32_t n_bits, int32_t half_patch, uint32_t seed, int8_t *pattern) {
+    uint32_t x = seed ? seed : 0x9E3779B9u;
+    const uint32_t span = (uint32_t)(2 * half_patch + 1);
+    for (int32_t k = 0; k < n_bits; ++k) {
+        int8_t v[4];
+        do {
+            for (int j = 0; j < 4; ++j) {
+                x ^= x << 13, x ^= x >> 17, x ^= x << 5;
+                v[j] = (int8_t)((int32_t)(x % span) - half_patch);
+            }
+        } while (half_patch > 0 && v[0] == v[2] && v[1] == v[3]);
+        for (int j = 0; j < 4; ++j) pattern[4 * k + j] = v[j];
+    }
+}
+
+int ftko_describe_brief(const uint8_t *image, int32_t rows, int32_t cols, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
+                        int32_t half_patch, uint32_t *desc, uint8_t *valid) {
+    if (n_bits <= 0 || n_bits % 32 != 0 || half_patch < 0) return 0;
+    const int32_t words = n_bits / 32;
+    for (int32_t i = 0; i < n; ++i) {
+        uint32_t *d = desc + (size_t)i * words;
+        for (int32_t w = 0; w < words; ++w) d[w] = 0;
+        const float x = uv[2 * i], y = uv[2 * i + 1];
+        /* the float tests keep NaN and out-of-range positions away from the int casts */
+        const int ok = x >= (float)half_patch && y >= (float)half_patch && x < (float)(cols - half_patch) && y < (float)(rows - half_patch);
+        if (valid) valid[i] = (uint8_t)ok;
+        if (!ok) continue;
+        const int32_t c = (int32_t)x, r = (int32_t)y;
+        for (int32_t k = 0; k < n_bits; ++k) {
+            const int8_t *q = pattern + 4 * k;
+            const uint8_t va = image[(size_t)(r + q[0]) * cols + (c + q[1])], vb = image[(size_t)(r + q[2]) * cols + (c + q[3])];
+            if (va < vb) d[k >> 5] |= 1u << (k & 31);
+        }
+    }
+    return 1;
+}

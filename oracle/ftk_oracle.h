@@ -65,6 +65,15 @@ int ftko_direct_method_track(const ftko_direct_params *params, int32_t levels, c
 int ftko_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels, const uint8_t *const *ref_levels, const uint8_t *const *cur_levels,
                           const int32_t *rows, const int32_t *cols, int32_t single_level, int32_t flow_valid, float *flow_row, float *flow_col);
 
+/* SURVEY 8(f) rank 1 -- PARITY UNPINNED (Feature_Detector's sources are absent; see the block comment in ftk_oracle.c).
+ * Response map (rows x cols floats, -inf where undefined), greedy min-distance selection in response order, BRIEF bits. */
+int ftko_detect_response(const ftko_detector_params *params, const uint8_t *image, int32_t rows, int32_t cols, float *response);
+int ftko_detect_features(const ftko_detector_params *params, const uint8_t *image, int32_t rows, int32_t cols, const float *existing_uv,
+                         int32_t n_existing, int32_t needed, float *out_uv, float *out_response);
+void ftko_brief_pattern(int32_t n_bits, int32_t half_patch, uint32_t seed, int8_t *pattern);
+int ftko_describe_brief(const uint8_t *image, int32_t rows, int32_t cols, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
+                        int32_t half_patch, uint32_t *desc, uint8_t *valid);
+
 /* Diagnostics: number of unchecked samples whose base pixel lay outside the image since the last reset (reference UB). */
 long long ftko_outside_reads(int32_t reset);
 

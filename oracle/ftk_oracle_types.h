@@ -42,4 +42,15 @@ typedef struct ftko_dense_flow_params {
     float max_delta_flow_step; /* kMaxDeltaFlowStep = 1.0 */
 } ftko_dense_flow_params;
 
+/* Feature detector options.  Feature_Detector (the sibling repository that owns FeaturePointHarrisDetector / BriefDescriptor) is
+ * absent from /root/reference: the option NAMES come from the call sites (test/test_descriptor_matcher_brief.cpp:59-71), the
+ * arithmetic is the published Harris / Shi-Tomasi definition frozen in oracle/ftk_oracle.c.  Same layout as ftk_detector_params. */
+typedef struct ftko_detector_params {
+    int32_t kind;         /* 0 Harris (det - k trace^2), 1 Shi-Tomasi (smaller eigenvalue) */
+    int32_t half_patch;   /* structure-tensor window half size, 1..3 */
+    float harris_k;       /* 0.04 */
+    float min_response;   /* kMinValidResponse */
+    int32_t min_distance; /* kMinFeatureDistance */
+} ftko_detector_params;
+
 #endif

@@ -70,6 +70,19 @@ class DenseFlowParams(C.Structure):
     _fields_ = [("max_iteration", C.c_int32), ("half_patch_size", C.c_int32), ("max_converge_step", C.c_float), ("max_delta_flow_step", C.c_float)]
 
 
+class DetectorParams(C.Structure):
+    """ftko_detector_params (parity unpinned: Feature_Detector is absent; see oracle/ftk_oracle.c)."""
+
+    _fields_ = [("kind", C.c_int32), ("half_patch", C.c_int32), ("harris_k", C.c_float), ("min_response", C.c_float), ("min_distance", C.c_int32)]
+
+
+def make_detector_params(kind="harris", half=1, k=0.04, min_response=40.0, min_distance=20):
+    p = DetectorParams()
+    p.kind = {"harris": 0, "shi_tomasi": 1}[kind] if isinstance(kind, str) else int(kind)
+    p.half_patch, p.harris_k, p.min_response, p.min_distance = half, k, min_response, min_distance
+    return p
+
+
 def make_dense_flow_params(max_iter=10, half=2, converge=1e-6, max_step=1.0):
     p = DenseFlowParams()
     p.max_iteration, p.half_patch_size, p.max_converge_step, p.max_delta_flow_step = max_iter, half, converge, max_step
@@ -400,6 +413,42 @@ class OracleLib(_CpuChecker):
         idx = np.full(max(n_ref, 1), -1, np.int32)
         ok = self._fn("mutual_scores")(_f32p(scores), C.c_int32(n_ref), C.c_int32(n_cur), C.c_float(min_score), _i32p(idx))
         return ok == 1, idx[:n_ref].copy()
+
+    # -- feature detection + BRIEF (restatement of the published algorithm; Feature_Detector's sources are absent) --------------
+    def detect_response(self, params, image):
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        out = np.zeros(image.shape, np.float32)
+        ok = self._fn("detect_response")(C.byref(params), _u8p(image), C.c_int32(image.shape[0]), C.c_int32(image.shape[1]), _f32p(out))
+        return ok == 1, out
+
+    def detect_features(self, params, image, needed, existing=None):
+        """Returns (ok, uv [n][2], response [n])."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        existing = np.zeros((0, 2), np.float32) if existing is None else np.ascontiguousarray(existing, np.float32).reshape(-1, 2)
+        uv = np.zeros((max(needed, 1), 2), np.float32)
+        resp = np.zeros(max(needed, 1), np.float32)
+        n = self._fn("detect_features")(C.byref(params), _u8p(image), C.c_int32(image.shape[0]), C.c_int32(image.shape[1]),
+                                        _f32p(existing) if len(existing) else None, C.c_int32(len(existing)), C.c_int32(needed), _f32p(uv), _f32p(resp))
+        return n >= 0, uv[:max(n, 0)].copy(), resp[:max(n, 0)].copy()
+
+    def brief_pattern(self, n_bits, half_patch, seed=0):
+        pattern = np.zeros((n_bits, 4), np.int8)
+        f = getattr(self.lib, self.prefix + "brief_pattern")
+        f.restype = None
+        f(C.c_int32(n_bits), C.c_int32(half_patch), C.c_uint32(seed), pattern.ctypes.data_as(C.c_void_p))
+        return pattern
+
+    def describe_brief(self, image, uv, pattern, half_patch):
+        """Returns (ok, desc uint32 [n][n_bits / 32], valid uint8 [n])."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        pattern = np.ascontiguousarray(pattern, np.int8).reshape(-1, 4)
+        n_bits = len(pattern)
+        desc = np.zeros((max(len(uv), 1), max(n_bits // 32, 1)), np.uint32)
+        valid = np.zeros(max(len(uv), 1), np.uint8)
+        ok = self._fn("describe_brief")(_u8p(image), C.c_int32(image.shape[0]), C.c_int32(image.shape[1]), _f32p(uv), C.c_int32(len(uv)),
+                                        pattern.ctypes.data_as(C.c_void_p), C.c_int32(n_bits), C.c_int32(half_patch), desc.ctypes.data_as(C.c_void_p), _u8p(valid))
+        return ok == 1, desc[:len(uv)].copy(), valid[:len(uv)].copy()
 
 
 def have_ref():

@@ -127,6 +127,34 @@ int main(int argc, char **argv) {
         fwrite(flow_rc[0].data(), sizeof(float), flow_rc[0].size(), out);
         fwrite(flow_rc[1].data(), sizeof(float), flow_rc[1].size(), out);
     }
+    // Detect -> describe -> match on the same device pyramids, as in test_descriptor_matcher_brief.cpp:57-95
+    {
+        feature_detector::FeaturePointHarrisDetector detector;
+        detector.options().kMinFeatureDistance = 20;
+        detector.options().kMinValidResponse = 40.0f;
+        std::vector<Vec2> ref_features, cur_features;
+        okv = (detector.DetectGoodFeatures(ref_pyramid, 150, ref_features) && detector.DetectGoodFeatures(cur_pyramid, 150, cur_features)) ? 1 : 0;
+        feature_detector::BriefDescriptor descriptor;
+        descriptor.options().kLength = 256;
+        descriptor.options().kHalfPatchSize = 8;
+        std::vector<feature_detector::BriefType> rd, cd;
+        okv = (okv && descriptor.Compute(ref_pyramid, ref_features, rd) && descriptor.Compute(cur_pyramid, cur_features, cd)) ? 1 : 0;
+        class DemoMatcher : public DescriptorMatcher<feature_detector::BriefType> {} demo;
+        demo.options().kMaxValidPredictRowDistance = 50;
+        demo.options().kMaxValidPredictColDistance = 50;
+        demo.options().kMaxValidDescriptorDistance = 60;
+        std::vector<int32_t> pairs;
+        okv = (okv && demo.NearbyMatch(rd, cd, ref_features, cur_features, pairs)) ? 1 : 0;
+        fwrite(&okv, sizeof(okv), 1, out);
+        const int32_t counts[2] = {static_cast<int32_t>(ref_features.size()), static_cast<int32_t>(cur_features.size())};
+        fwrite(counts, sizeof(int32_t), 2, out);
+        for (const auto *set : {&ref_features, &cur_features})
+            for (const Vec2 &f : *set) {
+                const float xy[2] = {f.x(), f.y()};
+                fwrite(xy, sizeof(float), 2, out);
+            }
+        fwrite(pairs.data(), sizeof(int32_t), pairs.size(), out);
+    }
     fclose(in);
     fclose(out);
     return 0;

@@ -1,0 +1,148 @@
+"""CPU checks of the detector / BRIEF checker.  PARITY UNPINNED: feature_detector::FeaturePointHarrisDetector
+and feature_detector::BriefDescriptor (called at test/test_descriptor_matcher_brief.cpp:59-76) live in the absent sibling
+repository Feature_Detector, so there is nothing of the reference's to compile or compare with.  These tests pin oracle/ftk_oracle.c's
+restatement of the published algorithm against an independent numpy restatement, against the properties the sequential selection
+must have, and against the committed regression fixture."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, bits_equal
+from feature_tracker_b200 import synthetic as S
+from oracle import pyoracle as po
+
+
+def numpy_response(img, kind, h, k):
+    """Same arithmetic in numpy float32: integer tensor sums, then one rounding per operation."""
+    f = np.float32
+    I = img.astype(np.int64)
+    rows, cols = I.shape
+    gx = np.zeros_like(I)
+    gy = np.zeros_like(I)
+    gx[:, 1:-1] = I[:, 2:] - I[:, :-2]
+    gy[1:-1, :] = I[2:, :] - I[:-2, :]
+    out = np.full((rows, cols), -np.inf, np.float32)
+    m = h + 1
+    if rows <= 2 * m or cols <= 2 * m:
+        return out
+    def box(a):
+        s = np.zeros((rows - 2 * m, cols - 2 * m), np.int64)
+        for dr in range(-h, h + 1):
+            for dc in range(-h, h + 1):
+                s += a[m + dr:rows - m + dr, m + dc:cols - m + dc]
+        return s.astype(np.float32)
+    inv = f(1.0) / f(4 * (2 * h + 1) ** 2)
+    a, b, c = box(gx * gx) * inv, box(gx * gy) * inv, box(gy * gy) * inv
+    if kind == "harris":
+        tr = a + c
+        r = (a * c - b * b) - f(k) * (tr * tr)
+    else:
+        d = a - c
+        r = f(0.5) * ((a + c) - np.sqrt(d * d + f(4.0) * (b * b)))
+    out[m:rows - m, m:cols - m] = r
+    return out
+
+
+@pytest.mark.parametrize("kind", ["harris", "shi_tomasi"])
+@pytest.mark.parametrize("half", [1, 2, 3])
+def test_response_restatement_vs_numpy(oracle, kind, half):
+    for shape, seed in (((97, 131), 5), ((480, 752), 6), ((9, 9), 7), ((4, 40), 8)):
+        img = S.make_image(*shape, seed=seed) if min(shape) >= 32 else np.random.default_rng(seed).integers(0, 256, shape, dtype=np.uint8)
+        ok, r = oracle.detect_response(po.make_detector_params(kind, half, 0.04, 40.0, 20), img)
+        assert ok
+        assert bits_equal(r, numpy_response(img, kind, half, 0.04)), (kind, half, shape)
+
+
+def python_selection(response, min_response, dist, needed, existing=()):
+    """The sequential loop, literally: order by (response desc, index asc), take unless a taken / existing feature is near."""
+    rows, cols = response.shape
+    idx = np.nonzero(response.ravel() >= np.float32(min_response))[0]
+    order = idx[np.lexsort((idx, -response.ravel()[idx].astype(np.float64)))]
+    taken = []
+    blockers = [(int(y), int(x)) for x, y in existing if 0 <= x < cols and 0 <= y < rows]
+    for p in order:
+        if len(taken) >= needed:
+            break
+        r, c = divmod(int(p), cols)
+        if dist > 0 and any(abs(r - br) < dist and abs(c - bc) < dist for br, bc in blockers):
+            continue
+        taken.append((c, r))
+        blockers.append((r, c))
+    return np.array(taken, np.float32).reshape(-1, 2)
+
+
+@pytest.mark.parametrize("kind,thr,dist,needed", [("harris", 1e5, 9, 60), ("shi_tomasi", 300.0, 5, 1000), ("harris", 40.0, 20, 25), ("shi_tomasi", 1e9, 4, 10),
+                                                  ("harris", 5e5, 0, 40), ("harris", 5e5, 1, 40)])
+def test_selection_restatement_vs_python(oracle, kind, thr, dist, needed):
+    img = S.make_image(120, 160, seed=11)
+    prm = po.make_detector_params(kind, 1, 0.04, thr, dist)
+    _, resp = oracle.detect_response(prm, img)
+    existing = np.array([[40.5, 30.2], [500.0, 3.0], [np.nan, 4.0], [159.9, 119.9], [-0.5, 10.0]], np.float32)
+    for ex in (None, existing):
+        ok, uv, r = oracle.detect_features(prm, img, needed, existing=ex)
+        assert ok
+        exp = python_selection(resp, thr, dist, needed, () if ex is None else ex)
+        assert np.array_equal(uv, exp), (kind, thr, dist, needed, ex is not None)
+        assert bits_equal(r, resp[uv[:, 1].astype(int), uv[:, 0].astype(int)])
+        assert (np.diff(r) <= 0).all() and (r >= np.float32(thr)).all()
+        if dist > 0 and len(uv) > 1:
+            d = np.abs(uv[:, None, :] - uv[None, :, :]).max(axis=2) + np.eye(len(uv)) * 1e9
+            assert d.min() >= dist
+
+
+def test_detector_rejects_bad_parameters(oracle):
+    img = S.make_image(64, 64, seed=1)
+    ok, _, _ = oracle.detect_features(po.make_detector_params("harris", 0, 0.04, 40.0, 20), img, 10)
+    assert not ok
+    ok, _, _ = oracle.detect_features(po.make_detector_params("harris", 4, 0.04, 40.0, 20), img, 10)
+    assert not ok
+
+
+def test_brief_restatement_vs_numpy(oracle):
+    img = S.make_image(90, 120, seed=21)
+    rng = np.random.default_rng(3)
+    uv = np.concatenate([rng.uniform(-5, 125, (200, 2)).astype(np.float32), np.array([[8.0, 8.0], [111.99, 81.99], [112.0, 40.0], [np.nan, 10], [7.99, 30.0]], np.float32)])
+    for n_bits, half, seed in ((256, 8, 0), (128, 4, 77), (32, 15, 1)):
+        pattern = oracle.brief_pattern(n_bits, half, seed)
+        assert pattern.min() >= -half and pattern.max() <= half
+        assert not ((pattern[:, 0] == pattern[:, 2]) & (pattern[:, 1] == pattern[:, 3])).any()
+        assert np.array_equal(pattern, oracle.brief_pattern(n_bits, half, seed))
+        ok, desc, valid = oracle.describe_brief(img, uv, pattern, half)
+        assert ok
+        exp_valid = (uv[:, 0] >= half) & (uv[:, 1] >= half) & (uv[:, 0] < 120 - half) & (uv[:, 1] < 90 - half)
+        assert np.array_equal(valid.astype(bool), exp_valid)
+        assert valid[200] == (1 if half <= 8 else 0) and valid[203] == 0
+        for i in range(len(uv)):
+            bits = np.zeros(n_bits, np.uint8)
+            if exp_valid[i]:
+                r, c = int(uv[i, 1]), int(uv[i, 0])
+                bits = (img[r + pattern[:, 0], c + pattern[:, 1]] < img[r + pattern[:, 2], c + pattern[:, 3]]).astype(np.uint8)
+            words = np.packbits(bits.reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+            assert np.array_equal(desc[i], words), (n_bits, i)
+
+
+def test_detector_matches_regression_fixture(oracle, euroc_golden):
+    g = dict(np.load(os.path.join(GOLDEN, "detector_golden.npz")))
+    assert np.array_equal(oracle.brief_pattern(256, 8, 0), g["pattern"])
+    for name in ("ref", "cur"):
+        img = euroc_golden[name]
+        for kind in ("harris", "shi_tomasi"):
+            ok, uv, resp = oracle.detect_features(po.make_detector_params(kind, 1, 0.04, 40.0, 20), img, 300)
+            assert ok and np.array_equal(uv, g[f"{name}_{kind}_uv"]) and bits_equal(resp, g[f"{name}_{kind}_response"])
+        ok, desc, valid = oracle.describe_brief(img, g[f"{name}_harris_uv"], g["pattern"], 8)
+        assert ok and np.array_equal(desc, g[f"{name}_brief"]) and np.array_equal(valid, g[f"{name}_brief_valid"])
+
+
+def test_detected_features_match_across_the_euroc_pair(oracle, euroc_golden):
+    """End-to-end sanity of the restated front end, the reference's own demo flow (test_descriptor_matcher_brief.cpp:57-95): detect
+    in both images, describe, NearbyMatch with the demo's thresholds -- a sizeable share of the corners must pair up."""
+    g = dict(np.load(os.path.join(GOLDEN, "detector_golden.npz")))
+    def unpack(d):
+        return np.unpackbits(d.view(np.uint8).reshape(len(d), -1), axis=1, bitorder="little")
+    ok, idx = oracle.match_brief_nearby(unpack(g["ref_brief"]), unpack(g["cur_brief"]), g["ref_harris_uv"], g["cur_harris_uv"], 50, 50, 60.0)
+    assert ok
+    matched = idx >= 0
+    assert matched.sum() >= 100, matched.sum()
+    shift = g["cur_harris_uv"][idx[matched]] - g["ref_harris_uv"][matched]
+    assert np.abs(shift - np.median(shift, axis=0)).max(axis=1).__lt__(12).mean() > 0.6  # the scene has parallax: the shift is not one vector

@@ -27,7 +27,8 @@ def test_facade_compiles_and_links(tmp_path):
     text = open(os.path.join(ROOT, "include", "feature_tracker_b200", "feature_tracker.h")).read()
     for name in ["namespace feature_tracker", "enum class TrackStatus", "struct OpticalFlowOptions", "class OpticalFlowBasicKlt", "class OpticalFlowAffineKlt",
                  "class OpticalFlowLssdKlt", "class DescriptorMatcher", "predict_affine", "predict_R_cr", "consider_patch_luminance", "ForceMatch",
-                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber", "class DirectMethod", "struct DirectMethodOptions", "class DenseOpticalFlow"]:
+                 "NearbyMatch", "kMaxValidDescriptorDistance", "kMaxTrackPointsNumber", "class DirectMethod", "struct DirectMethodOptions", "class DenseOpticalFlow",
+                 "namespace feature_detector", "FeaturePointHarrisDetector", "class BriefDescriptor", "kMinFeatureDistance", "kMinValidResponse"]:
         assert name in text, name
 
 
@@ -92,3 +93,17 @@ def test_facade_matches_oracle(tmp_path, oracle):
     eok, er, ec = oracle.dense_flow_track(po.make_dense_flow_params(), rl, cl)
     assert ok == 1 and eok and (fr.view(np.uint32) == er.view(np.uint32)).all() and (fc.view(np.uint32) == ec.view(np.uint32)).all()
 
+    # detect -> describe -> match through the facade (parity unpinned: the checker is the oracle's restatement of the published algorithm)
+    ok = take(np.int32, 1)[0]
+    n_r, n_c = take(np.int32, 2)
+    f_ref = take(np.float32, 2 * n_r).reshape(-1, 2)
+    f_cur = take(np.float32, 2 * n_c).reshape(-1, 2)
+    pairs = take(np.int32, n_r)
+    prm = po.make_detector_params("harris", 1, 0.04, 40.0, 20)
+    assert ok == 1 and np.array_equal(f_ref, oracle.detect_features(prm, ref, 150)[1]) and np.array_equal(f_cur, oracle.detect_features(prm, cur, 150)[1])
+    pattern = oracle.brief_pattern(256, 8, 0)
+    _, rd, _ = oracle.describe_brief(ref, f_ref, pattern, 8)
+    _, cd, _ = oracle.describe_brief(cur, f_cur, pattern, 8)
+    unpack = lambda d: np.unpackbits(d.view(np.uint8).reshape(len(d), -1), axis=1, bitorder="little")
+    _, exp = oracle.match_brief_nearby(unpack(rd), unpack(cd), f_ref, f_cur, 50, 50, 60.0)
+    assert np.array_equal(pairs, exp) and (pairs >= 0).sum() > 20

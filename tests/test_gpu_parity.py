@@ -803,3 +803,120 @@ def test_cosine_c5_full_size_properties(ctx):
     sample = np.random.default_rng(1).integers(0, 20000, 128)
     d = 0.5 - 0.5 * (rf[sample].astype(np.float64) @ cf.astype(np.float64).T)
     assert (d.argmin(1) == idx[sample]).all() and (d.min(1) < 0.1).all()
+
+
+# ---- feature detection + BRIEF (parity unpinned -- the checker is the oracle's restatement) ---------------
+def make_detector(ctx, kind, half, thr, dist):
+    det = (ft.FeaturePointHarrisDetector if kind == "harris" else ft.FeaturePointShiTomasDetector)(ctx)
+    o = det.options()
+    o.kHalfPatchSize, o.kMinValidResponse, o.kMinFeatureDistance = half, thr, dist
+    return det
+
+
+def single_image_pyramid(ctx, img, levels=1):
+    pyr = ft.ImagePyramidBatch(ctx, img.shape[0], img.shape[1], levels, 1)
+    pyr.SetRawImages(img[None])
+    pyr.CreateImagePyramid()
+    return pyr
+
+
+@pytest.mark.parametrize("kind", ["harris", "shi_tomasi"])
+@pytest.mark.parametrize("half", [1, 2, 3])
+def test_detector_response_bit_exact(ctx, oracle, kind, half):
+    for shape, seed in (((480, 752), 31), ((97, 131), 32), ((33, 65), 33), ((9, 9), 34), ((4, 40), 35)):
+        img = S.make_image(*shape, seed=seed) if min(shape) >= 32 else np.random.default_rng(seed).integers(0, 256, shape, dtype=np.uint8)
+        ok, exp = oracle.detect_response(po.make_detector_params(kind, half, 0.04, 40.0, 20), img)
+        got = make_detector(ctx, kind, half, 40.0, 20).ComputeResponse(single_image_pyramid(ctx, img))
+        assert ok and bits_equal(got, exp), (kind, half, shape)
+
+
+@pytest.mark.parametrize("kind,thr,dist,needed,shape", [
+    ("harris", 40.0, 20, 300, (480, 752)),       # the demo's values (test_descriptor_matcher_brief.cpp:60-61): every pixel is a candidate
+    ("shi_tomasi", 40.0, 20, 300, (480, 752)),
+    ("harris", 1e5, 9, 5000, (480, 752)),        # more wanted than exist: the full maximal set
+    ("shi_tomasi", 300.0, 5, 1000, (240, 376)),
+    ("harris", 5e5, 1, 4000, (97, 131)),         # d = 1: nothing blocks anything
+    ("harris", 5e5, 0, 4000, (97, 131)),
+    ("shi_tomasi", 100.0, 64, 50, (97, 131)),    # windows wider than two warps' worth of columns
+    ("harris", 1e12, 20, 10, (97, 131)),         # no candidate at all
+    ("harris", -1e30, 3, 100000, (61, 83)),      # every defined pixel, plateaus of equal response included
+])
+def test_detector_selection_vs_oracle(ctx, oracle, kind, thr, dist, needed, shape):
+    img = S.make_image(*shape, seed=41 + dist)
+    if thr < 0:
+        img[:, : shape[1] // 2] = 77  # flat half: thousands of exactly equal responses, resolved by index
+    pyr = single_image_pyramid(ctx, img, levels=3 if min(shape) >= 64 else 1)
+    det = make_detector(ctx, kind, 1, thr, dist)
+    rng = np.random.default_rng(5)
+    existing = np.concatenate([rng.uniform(0, 1, (40, 2)) * [shape[1], shape[0]], [[np.nan, 3.0], [-2.0, 5.0], [shape[1], 1.0], [shape[1] - 0.5, shape[0] - 0.5]]]).astype(np.float32)
+    for ex in (None, existing):
+        ok_e, uv_e, resp_e = oracle.detect_features(po.make_detector_params(kind, 1, 0.04, thr, dist), img, needed, existing=ex)
+        want = needed + (0 if ex is None else len(ex))
+        ok_g, uv_g, resp_g = det.DetectGoodFeatures(pyr, want, ex, return_response=True)
+        n0 = 0 if ex is None else len(ex)
+        assert ok_g and ok_e
+        assert np.array_equal(uv_g[n0:], uv_e), (kind, thr, dist, needed, len(uv_g) - n0, len(uv_e))
+        assert bits_equal(resp_g, resp_e)
+        if ex is not None:
+            assert bits_equal(uv_g[:n0], ex)
+
+
+def test_detector_matches_regression_fixture(ctx, euroc_golden):
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "detector_golden.npz")))
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([euroc_golden["ref"], euroc_golden["cur"]]))
+    pyr.CreateImagePyramid()
+    assert np.array_equal(ft.brief_pattern(256, 8, 0), g["pattern"])
+    for i, name in enumerate(("ref", "cur")):
+        for kind in ("harris", "shi_tomasi"):
+            ok, uv, resp = make_detector(ctx, kind, 1, 40.0, 20).DetectGoodFeatures(pyr, 300, image_index=i, return_response=True)
+            assert ok and np.array_equal(uv, g[f"{name}_{kind}_uv"]) and bits_equal(resp, g[f"{name}_{kind}_response"]), (name, kind)
+        ok, desc, valid = ft.BriefDescriptor(ctx).Compute(pyr, g[f"{name}_harris_uv"], image_index=i)
+        assert ok and np.array_equal(desc, g[f"{name}_brief"]) and np.array_equal(valid, g[f"{name}_brief_valid"]), name
+
+
+def test_brief_vs_oracle(ctx, oracle):
+    img = S.make_image(90, 120, seed=21)
+    pyr = single_image_pyramid(ctx, img)
+    rng = np.random.default_rng(3)
+    uv = np.concatenate([rng.uniform(-5, 125, (3000, 2)).astype(np.float32),
+                         np.array([[8.0, 8.0], [111.99, 81.99], [112.0, 40.0], [np.nan, 10], [7.99, 30.0], [1e30, 1e30], [-1e30, 5]], np.float32)])
+    for n_bits, half, seed in ((256, 8, 0), (128, 4, 77), (32, 15, 1), (1024, 20, 9)):
+        d = ft.BriefDescriptor(ctx)
+        d.options().kLength, d.options().kHalfPatchSize, d.options().kPatternSeed = n_bits, half, seed
+        assert np.array_equal(d.pattern(), oracle.brief_pattern(n_bits, half, seed))
+        ok_g, desc_g, valid_g = d.Compute(pyr, uv)
+        ok_e, desc_e, valid_e = oracle.describe_brief(img, uv, d.pattern(), half)
+        assert ok_g and ok_e and np.array_equal(valid_g, valid_e) and np.array_equal(desc_g, desc_e), (n_bits, half)
+    ok, desc, valid = ft.BriefDescriptor(ctx).Compute(pyr, np.zeros((0, 2), np.float32))
+    assert ok and desc.shape[0] == 0
+    with pytest.raises(ft.FtkError):  # a pair outside the stated patch
+        ft.BriefDescriptor(ctx, pattern=np.full((32, 4), 9, np.int8)).Compute(pyr, uv[:4])
+
+
+def test_front_end_detect_describe_match_track(ctx, oracle, euroc_golden):
+    """The reference demo's flow (test_descriptor_matcher_brief.cpp:57-95) on one device pyramid batch, each stage against the oracle
+    fed with the previous stage's oracle output: detect in both frames -> BRIEF -> NearbyMatch, then KLT from the same pyramids."""
+    ref, cur = euroc_golden["ref"], euroc_golden["cur"]
+    pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    det = make_detector(ctx, "harris", 1, 40.0, 20)
+    _, ref_uv = det.DetectGoodFeatures(pyr, 300, image_index=0)
+    _, cur_uv = det.DetectGoodFeatures(pyr, 300, image_index=1)
+    prm = po.make_detector_params("harris", 1, 0.04, 40.0, 20)
+    assert np.array_equal(ref_uv, oracle.detect_features(prm, ref, 300)[1]) and np.array_equal(cur_uv, oracle.detect_features(prm, cur, 300)[1])
+    brief = ft.BriefDescriptor(ctx)
+    _, ref_desc, _ = brief.Compute(pyr, ref_uv, image_index=0)
+    _, cur_desc, _ = brief.Compute(pyr, cur_uv, image_index=1)
+    m = brief_matcher(ctx, 60.0, 50, 50)
+    ok, idx = m.NearbyMatch(ref_desc, cur_desc, ref_uv, cur_uv)
+    unpack = lambda d: np.unpackbits(d.view(np.uint8).reshape(len(d), -1), axis=1, bitorder="little")
+    ok_e, idx_e = oracle.match_brief_nearby(unpack(ref_desc), unpack(cur_desc), ref_uv, cur_uv, 50, 50, 60.0)
+    assert ok and ok_e and np.array_equal(idx, idx_e) and (idx >= 0).sum() >= 100
+    klt = make_tracker(ctx, "basic", "fast", 6)
+    got = klt.TrackFeatures(pyr, pyr, ref_uv, ref_image=0, cur_image=1)
+    levels = [[ref] + [euroc_golden[f"ref_l{l}"] for l in range(1, 4)], [cur] + [euroc_golden[f"cur_l{l}"] for l in range(1, 4)]]
+    assert_same("front end klt", got, oracle.klt_track(po.make_params("basic", "fast", 6), levels[0], levels[1], ref_uv))

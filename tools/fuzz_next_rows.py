@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Randomised parity sweep of the SURVEY 8(f) kernels (direct-method pose tracker, dense flow, forward-backward pass, sequence
-pipeline) against the C oracle.
+pipeline, detector + BRIEF) against the C oracle.
     python tools/fuzz_next_rows.py [n_cases] [seed]"""
 import os
 import sys
@@ -28,7 +28,7 @@ def main():
     oracle = po.OracleLib()
     bad = 0
     for case in range(n_cases):
-        kind = rng.choice(["direct_method", "dense_flow"])
+        kind = rng.choice(["direct_method", "dense_flow", "detector"])
         rows, cols = int(rng.integers(40, 200)), int(rng.integers(40, 260))
         levels = int(rng.integers(1, 5))
         while (min(rows, cols) >> (levels - 1)) < 8:
@@ -59,6 +59,33 @@ def main():
                                              status=st_in)
             ok = got[0] == exp[0] and all(same(g, e) for g, e in zip(got[1:], exp[1:]))
             desc = f"{2 * hr + 1}x{2 * hc + 1} n={uv.shape[0]}"
+            pyr.close()
+        elif kind == "detector":
+            img = S.make_image(rows, cols, seed=4000 + case)
+            if rng.random() < 0.3:  # quantise: plateaus of exactly equal responses
+                img = (img // int(rng.choice([16, 64]))).astype(np.uint8) * 3
+            dkind = str(rng.choice(["harris", "shi_tomasi"]))
+            half, dist, needed = int(rng.integers(1, 4)), int(rng.choice([0, 1, 2, 5, 12, 20, 33, 70])), int(rng.choice([1, 30, 300, 100000]))
+            thr = float(rng.choice([-1e20, 0.0, 40.0, 1e3, 1e5, 1e7]))
+            existing = (rng.uniform(-0.1, 1.1, (int(rng.integers(1, 40)), 2)) * [cols, rows]).astype(np.float32) if rng.random() < 0.5 else None
+            det = (ft.FeaturePointHarrisDetector if dkind == "harris" else ft.FeaturePointShiTomasDetector)(ctx)
+            o = det.options()
+            o.kHalfPatchSize, o.kMinValidResponse, o.kMinFeatureDistance = half, thr, dist
+            pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 1)
+            pyr.SetRawImages(img[None])
+            pyr.CreateImagePyramid()
+            n0 = 0 if existing is None else len(existing)
+            g_ok, g_uv, g_resp = det.DetectGoodFeatures(pyr, needed + n0, existing, return_response=True)
+            e_ok, e_uv, e_resp = oracle.detect_features(po.make_detector_params(dkind, half, 0.04, thr, dist), img, needed, existing=existing)
+            ok = g_ok == e_ok and same(g_uv[n0:], e_uv) and same(g_resp, e_resp)
+            n_bits, bh = int(rng.choice([32, 128, 256, 512])), int(rng.integers(0, 12))
+            uv = np.concatenate([e_uv[:200], (rng.uniform(-0.2, 1.2, (20, 2)) * [cols, rows]).astype(np.float32)])
+            bd = ft.BriefDescriptor(ctx)
+            bd.options().kLength, bd.options().kHalfPatchSize, bd.options().kPatternSeed = n_bits, bh, int(rng.integers(0, 1 << 31))
+            g_ok, g_desc, g_valid = bd.Compute(pyr, uv)
+            e_ok, e_desc, e_valid = oracle.describe_brief(img, uv, bd.pattern(), bh)
+            ok = ok and g_ok == e_ok and same(g_desc, e_desc) and same(g_valid, e_valid)
+            desc = f"{dkind} h={half} d={dist} thr={thr} needed={needed} existing={n0} found={len(e_uv)} brief={n_bits}/{bh}"
             pyr.close()
         else:
             ref, cur, _, _ = S.make_pair(rows, cols, 5, pair_id=3000 + case)
