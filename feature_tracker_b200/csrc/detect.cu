@@ -6,17 +6,21 @@
 // published algorithm as frozen in the detector section of oracle/ftk_oracle.c, and
 // these kernels are bit-exact against that restatement.
 //
-// K9a ResponseKernel   one pass over the image (HBM bound: 1 B read + 8 B written per pixel): integer structure-tensor sums from a
-//                      shared-memory tile, fp32 response with explicit rounding, candidate list by warp-aggregated append.
-// K9b SelectRoundKernel  the sequential "visit by falling response, take unless a taken feature is near" loop as a parallel fixed
-//                      point: a candidate is TAKEN once no undecided or taken candidate of higher priority is left in its
-//                      window, DROPPED once a taken one is; every decision is final and equals the sequential loop's, rounds
-//                      repeat until no candidate is undecided.  Priority = (response, then lower row-major index).
-// K9c CollectKernel + sort + EmitKernel   the taken set ordered by priority; the first `needed` are the sequential loop's output.
+// K9a ResponseKernel   one pass over the image (HBM bound: 1 B read + 12 B written per pixel): integer structure-tensor sums from a
+//                      shared-memory tile, fp32 response with explicit rounding, 64-bit priority key per candidate pixel.
+// K9b RowMaxKernel + DecideKernel   the sequential "visit by falling response, take unless a taken feature is near" loop as a
+//                      parallel fixed point over the key image: per round, the maximum key of every pixel's window (separable:
+//                      rows, then columns); a candidate whose window holds a TAKEN pixel is dropped, one that is its window's
+//                      maximum is taken, the others wait.  Every decision is final and equals the sequential loop's; rounds
+//                      repeat until no candidate is undecided.  Key = (response, then lower row-major index).
+//                      SelectRoundTileKernel fuses both passes and the decision for windows that fit in shared memory.
+// K9c CollectKernel + sort + EmitKernel   the taken set ordered by key; the first `needed` are the sequential loop's output.
 // K10 BriefKernel      one warp per feature, one pair per lane, a ballot per 32-bit descriptor word.
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "ftk_internal.h"
 
@@ -34,9 +38,18 @@ __device__ __forceinline__ unsigned DetOrderMap(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// Pixel states of the selection: 0 = not a candidate / dropped, kTaken = taken, anything else = the undecided candidate's key.
+using Key = unsigned long long;
+constexpr Key kTaken = ~0ull;
+constexpr int kRowMaxThreads = 256;
+
+__device__ __forceinline__ Key MakeKey(float response, unsigned pixel) {
+    // -0 + 0 = +0: one key for both zeros, like the float comparison of the sequential loop.  Index part < 2^32 - 1, so no key is kTaken.
+    return (static_cast<Key>(DetOrderMap(__fadd_rn(response, 0.0f))) << 32) | (0xFFFFFFFFu - pixel);
+}
+
 __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, ftk_detector_params p,
-                                                      float *__restrict__ response, float *__restrict__ state, unsigned *__restrict__ cand,
-                                                      unsigned *__restrict__ n_cand) {
+                                                      float *__restrict__ response, Key *__restrict__ state) {
     __shared__ uint8_t tile[kDetTile + 2 * kDetMaxMargin][kDetTile + 2 * kDetMaxMargin + 8];
     const int h = p.half_patch, m = h + 1, edge = kDetTile + 2 * m;
     const int r0 = blockIdx.y * kDetTile, c0 = blockIdx.x * kDetTile;
@@ -52,6 +65,7 @@ __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict_
     for (int q = 0; q < kDetTile / 8; ++q) {
         const int lr = threadIdx.y + 8 * q, lc = threadIdx.x;
         const int r = r0 + lr, c = c0 + lc;
+        if (r >= rows || c >= cols) continue;
         float resp = -INFINITY;
         if (r >= m && r < rows - m && c >= m && c < cols - m) {
             int sxx = 0, syy = 0, sxy = 0;
@@ -73,79 +87,156 @@ __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict_
                 resp = __fmul_rn(0.5f, __fsub_rn(__fadd_rn(a, cc), __fsqrt_rn(disc)));
             }
         }
-        const bool inside = r < rows && c < cols;
-        const bool is_cand = inside && resp >= p.min_response;
-        if (inside) {
-            const size_t i = static_cast<size_t>(r) * cols + c;
-            response[i] = resp;
-            if (state) state[i] = is_cand ? resp : -INFINITY;
-        }
-        if (cand) {  // warp-aggregated append; the list's order does not matter
-            const unsigned vote = __ballot_sync(0xFFFFFFFFu, is_cand);
-            if (vote) {
-                unsigned base = 0;
-                const int leader = __ffs(vote) - 1;
-                if (threadIdx.x == leader) base = atomicAdd(n_cand, __popc(vote));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (is_cand) cand[base + __popc(vote & ((1u << threadIdx.x) - 1u))] = static_cast<unsigned>(r) * cols + c;
-            }
-        }
+        const unsigned i = static_cast<unsigned>(r) * cols + c;
+        response[i] = resp;
+        if (state) state[i] = resp >= p.min_response ? MakeKey(resp, i) : 0ull;
     }
 }
 
 // Features the caller already holds block their window (they are not candidates themselves).
-__global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows, int cols, int dist, float *__restrict__ state) {
+__global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows, int cols, int dist, Key *__restrict__ state) {
     const float2 f = existing[blockIdx.x];
     if (!(f.x >= 0.0f && f.y >= 0.0f && f.x < static_cast<float>(cols) && f.y < static_cast<float>(rows))) return;
     const int r = static_cast<int>(f.y), c = static_cast<int>(f.x), w = 2 * dist - 1;
     for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
         const int rr = r - (dist - 1) + k / w, qc = c - (dist - 1) + k % w;
-        if (rr >= 0 && rr < rows && qc >= 0 && qc < cols) state[static_cast<size_t>(rr) * cols + qc] = -INFINITY;
+        if (rr >= 0 && rr < rows && qc >= 0 && qc < cols) state[static_cast<size_t>(rr) * cols + qc] = 0ull;
     }
 }
 
-// state[pixel]: the response while the candidate is undecided, +inf once taken, -inf when dropped / never a candidate.
-// One warp per candidate.  counters[round] = candidates still undecided after this round.
-__global__ void __launch_bounds__(256) SelectRoundKernel(const unsigned *__restrict__ cand, const unsigned *__restrict__ n_cand, float *state, int rows,
-                                                         int cols, int dist, unsigned *__restrict__ counters, int round) {
+// rowmax[r][c] = max of state[r][c - (dist-1) .. c + (dist-1)].  One block per 256-column segment of a row, staged through shared memory.
+__global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__restrict__ state, int cols, int dist, Key *__restrict__ rowmax,
+                                                               const unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
-    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= *n_cand) return;
-    const unsigned p = cand[w];
-    const float s = __ldcg(state + p);
-    if (s == INFINITY || s == -INFINITY) return;
-    const int r = p / cols, c = p - r * cols;
-    const int ra = max(0, r - (dist - 1)), rb = min(rows - 1, r + (dist - 1)), ca = max(0, c - (dist - 1)), cb = min(cols - 1, c + (dist - 1));
-    bool taken_near = false, higher_near = false;
-    for (int rr = ra; rr <= rb; ++rr) {
-        const float *row = state + static_cast<size_t>(rr) * cols;
-        for (int qc = ca + lane; qc <= cb; qc += 32) {
-            const float v = __ldcg(row + qc);
-            const unsigned q = static_cast<unsigned>(rr) * cols + qc;
-            taken_near |= v == INFINITY;
-            higher_near |= v > s || (v == s && q < p);
+    extern __shared__ Key seg[];
+    const int c0 = blockIdx.x * kRowMaxThreads, halo = dist - 1, width = kRowMaxThreads + 2 * halo;
+    const Key *row = state + static_cast<size_t>(blockIdx.y) * cols;
+    for (int k = threadIdx.x; k < width; k += kRowMaxThreads) {
+        const int c = c0 - halo + k;
+        seg[k] = (c >= 0 && c < cols) ? row[c] : 0ull;
+    }
+    __syncthreads();
+    const int c = c0 + threadIdx.x;
+    if (c >= cols) return;
+    Key best = 0ull;
+    for (int k = 0; k <= 2 * halo; ++k) best = max(best, seg[threadIdx.x + k]);
+    rowmax[static_cast<size_t>(blockIdx.y) * cols + c] = best;
+}
+
+// Window maximum = column maximum of the row maxima; then the decision for every undecided candidate.  counters[round] = candidates
+// still undecided after this round.  Reads only the snapshot in `rowmax` and the pixel's own state: no ordering between threads.
+__global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowmax, Key *__restrict__ state, int rows, int cols, int dist,
+                                                    unsigned *__restrict__ counters, int round) {
+    if (round > 0 && counters[round - 1] == 0) return;
+    const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
+    bool waits = false;
+    if (c < cols && r < rows) {
+        const size_t i = static_cast<size_t>(r) * cols + c;
+        const Key s = state[i];
+        if (s != 0ull && s != kTaken) {
+            const int ra = max(0, r - (dist - 1)), rb = min(rows - 1, r + (dist - 1));
+            Key best = 0ull;
+            for (int rr = ra; rr <= rb; ++rr) best = max(best, __ldg(rowmax + static_cast<size_t>(rr) * cols + c));
+            if (best == kTaken) state[i] = 0ull;
+            else if (best == s) state[i] = kTaken;
+            else waits = true;
         }
     }
-    taken_near = __any_sync(0xFFFFFFFFu, taken_near);
-    higher_near = __any_sync(0xFFFFFFFFu, higher_near);
-    if (lane == 0) {
-        if (taken_near) __stcg(state + p, -INFINITY);
-        else if (!higher_near) __stcg(state + p, INFINITY);
-        else atomicAdd(counters + round, 1u);
+    const int n_waiting = __syncthreads_count(waits);
+    if (n_waiting && threadIdx.x == 0 && threadIdx.y == 0) atomicAdd(counters + round, static_cast<unsigned>(n_waiting));
+}
+
+// out[k] = max of in[k * 1 .. k + W - 1] (elements `stride` apart), k = 0 .. G-1: the G windows share elements G-1 .. W-1, window k
+// adds the suffix k .. G-2 on the left and the prefix W .. W+k-1 on the right -- W + G - 1 reads instead of G * W.
+template <int G>
+__device__ __forceinline__ void WindowMax(const Key *in, int stride, int W, Key (&out)[G]) {
+    if (W < G) {
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            Key best = 0ull;
+            for (int j = 0; j < W; ++j) best = max(best, in[(k + j) * stride]);
+            out[k] = best;
+        }
+        return;
+    }
+    Key common = 0ull;
+    for (int j = G - 1; j < W; ++j) common = max(common, in[j * stride]);
+    out[G - 1] = common;
+#pragma unroll
+    for (int k = G - 2; k >= 0; --k) out[k] = max(out[k + 1], in[k * stride]);  // common + left suffix
+    Key prefix = 0ull;
+#pragma unroll
+    for (int k = 1; k < G; ++k) {
+        prefix = max(prefix, in[(W + k - 1) * stride]);
+        out[k] = max(out[k], prefix);
     }
 }
 
-__global__ void CollectKernel(const unsigned *__restrict__ cand, const unsigned *__restrict__ n_cand, const float *__restrict__ state,
-                              const float *__restrict__ response, unsigned long long *__restrict__ keys, unsigned *__restrict__ n_keys) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_cand) return;
-    const unsigned p = cand[i];
-    if (state[p] != INFINITY) return;
-    // -0 + 0 = +0: one key for both zeros, like the float comparison of the sequential loop
-    keys[atomicAdd(n_keys, 1u)] = (static_cast<unsigned long long>(DetOrderMap(__fadd_rn(response[p], 0.0f))) << 32) | (0xFFFFFFFFu - p);
+// One round in one kernel for windows that fit in shared memory: a CTA stages its 32 x 32 tile plus the halo, takes row maxima, then
+// column maxima, and decides its own pixels IN PLACE.  Neighbouring CTAs may read a pixel before or after its decision; both
+// readings lead to decisions the sequential loop also makes (a state only ever moves from undecided to its final value, "taken"
+// needs every higher key of the window finally dropped, "dropped" needs a finally taken key in the window), so the fixed point is
+// the same -- only the number of rounds can differ.
+constexpr int kGroup = 8;
+__global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
+    if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
+    extern __shared__ Key sm[];
+    const int h = dist - 1, edge = kDetTile + 2 * h, stride = edge | 1, W = 2 * h + 1;
+    Key *A = sm, *B = sm + edge * stride;  // A: states of tile + halo; B[row][32]: row maxima for the tile's columns
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int r_tile = blockIdx.y * kDetTile, c_tile = blockIdx.x * kDetTile;
+    bool undecided = false;
+#pragma unroll
+    for (int q = 0; q < kDetTile / 8; ++q) {
+        const int r = r_tile + threadIdx.y + 8 * q, c = c_tile + threadIdx.x;
+        if (r < rows && c < cols) {
+            const Key v = __ldcg(state + static_cast<size_t>(r) * cols + c);
+            undecided |= v != 0ull && v != kTaken;
+        }
+    }
+    if (!__syncthreads_or(undecided)) return;
+    for (int k = tid; k < edge * edge; k += 256) {
+        const int tr = k / edge, tc = k - tr * edge;
+        const int r = r_tile - h + tr, c = c_tile - h + tc;
+        A[tr * stride + tc] = (r >= 0 && r < rows && c >= 0 && c < cols) ? __ldcg(state + static_cast<size_t>(r) * cols + c) : 0ull;
+    }
+    __syncthreads();
+    for (int item = tid; item < edge * (kDetTile / kGroup); item += 256) {
+        const int row = item / (kDetTile / kGroup), g = item % (kDetTile / kGroup);
+        Key out[kGroup];
+        WindowMax<kGroup>(A + row * stride + g * kGroup, 1, W, out);
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) B[row * kDetTile + g * kGroup + k] = out[k];
+    }
+    __syncthreads();
+    if (tid < 32 * (kDetTile / kGroup)) {
+        const int col = tid & 31, g = tid >> 5;
+        Key out[kGroup];
+        WindowMax<kGroup>(B + g * kGroup * kDetTile + col, kDetTile, W, out);
+        unsigned waiting = 0;
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) {
+            const int lr = g * kGroup + k;
+            const Key s = A[(lr + h) * stride + h + col];
+            if (s == 0ull || s == kTaken) continue;  // also every pixel outside the image
+            Key *mine = state + static_cast<size_t>(r_tile + lr) * cols + c_tile + col;
+            if (out[k] == kTaken) __stcg(mine, 0ull);
+            else if (out[k] == s) __stcg(mine, kTaken);
+            else ++waiting;
+        }
+        waiting = __reduce_add_sync(0xFFFFFFFFu, waiting);
+        if (col == 0 && waiting) atomicAdd(counters + round, waiting);
+    }
 }
 
-__global__ void EmitKernel(const unsigned long long *__restrict__ keys, int n, int cols, const float *__restrict__ response, float2 *__restrict__ uv,
+__global__ void CollectKernel(const Key *__restrict__ state, unsigned n_pixels, const float *__restrict__ response, Key *__restrict__ keys,
+                              unsigned *__restrict__ n_keys) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels || state[i] != kTaken) return;
+    keys[atomicAdd(n_keys, 1u)] = MakeKey(response[i], i);
+}
+
+__global__ void EmitKernel(const Key *__restrict__ keys, int n, int cols, const float *__restrict__ response, float2 *__restrict__ uv,
                            float *__restrict__ out_response) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -192,7 +283,7 @@ int LaunchDetectResponse(ftk_context *ctx, const ftk_detector_params &p, const P
     const int rows = pyr.rows[0], cols = pyr.cols[0];
     const uint8_t *img = pyr.base[0] + image * pyr.image_stride[0];
     const dim3 grid((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile);
-    ResponseKernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(img, rows, cols, pyr.pitch[0], p, d_response, nullptr, nullptr, nullptr);
+    ResponseKernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(img, rows, cols, pyr.pitch[0], p, d_response, nullptr);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
@@ -208,53 +299,68 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
     if (needed <= 0) return FTK_OK;
     const uint8_t *img = pyr.base[0] + image * pyr.image_stride[0];
     cudaStream_t st = ctx->stream;
-    // counters: [0] candidates, [1] taken, [2 ..] undecided per round of the current batch
-    const size_t n_counters = 2 + kRoundsPerBatch;
+    // a feature blocks |drow| < dist and |dcol| < dist; dist <= 1 blocks nothing but its own pixel, and no window is wider than the image
+    const int dist = std::min(std::max(p.min_distance, 1), std::max(rows, cols));
+    // taken features are >= dist apart: at most ceil(rows / dist) * ceil(cols / dist) of them
+    const size_t max_taken = static_cast<size_t>((rows + dist - 1) / dist) * ((cols + dist - 1) / dist);
+    // counters: [0] taken, [1 ..] undecided per round of the current batch
+    const size_t n_counters = 1 + kRoundsPerBatch;
     if (int rc = EnsureDevice(ctx, ctx->d_det_response, sizeof(float) * n)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_state, sizeof(float) * n)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_cand, sizeof(unsigned) * (n + n_counters))) return rc;
-    float *response = static_cast<float *>(ctx->d_det_response.ptr), *state = static_cast<float *>(ctx->d_det_state.ptr);
-    unsigned *cand = static_cast<unsigned *>(ctx->d_det_cand.ptr), *counters = cand + n;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_state, sizeof(Key) * 2 * n)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_keys, sizeof(Key) * 2 * max_taken)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_cand, sizeof(unsigned) * n_counters)) return rc;
+    float *response = static_cast<float *>(ctx->d_det_response.ptr);
+    Key *state = static_cast<Key *>(ctx->d_det_state.ptr), *rowmax = state + n;
+    Key *keys = static_cast<Key *>(ctx->d_det_keys.ptr), *sorted = keys + max_taken;
+    unsigned *counters = static_cast<unsigned *>(ctx->d_det_cand.ptr);
     FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, sizeof(unsigned) * n_counters, st));
-    const dim3 grid((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile);
-    ResponseKernel<<<grid, dim3(32, 8), 0, st>>>(img, rows, cols, pyr.pitch[0], p, response, state, cand, counters);
+    const dim3 tiles((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile);
+    ResponseKernel<<<tiles, dim3(32, 8), 0, st>>>(img, rows, cols, pyr.pitch[0], p, response, state);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
-    const int dist = p.min_distance > 0 ? p.min_distance : 1;  // d <= 1: a feature blocks nothing but its own pixel
     if (n_existing > 0 && p.min_distance > 0) {
         ExistingMaskKernel<<<n_existing, 128, 0, st>>>(d_existing, rows, cols, dist, state);
         ++ctx->launches;
         FTK_CUDA_CHECK(ctx, cudaGetLastError());
     }
-    unsigned n_cand = 0;
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_cand, counters, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    if (n_cand == 0) return FTK_OK;
-    const unsigned round_blocks = (n_cand + 7) / 8;
+    const dim3 row_grid((cols + kRowMaxThreads - 1) / kRowMaxThreads, rows), decide_grid((cols + 31) / 32, (rows + 7) / 8);
+    const size_t row_smem = sizeof(Key) * (kRowMaxThreads + 2 * (dist - 1));
+    if (row_smem > 48 * 1024) FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(RowMaxKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(row_smem)));
+    // one fused kernel per round while tile + halo fit in shared memory with two CTAs per SM; two kernels per round beyond that
+    const int edge = kDetTile + 2 * (dist - 1);
+    const size_t tile_smem = sizeof(Key) * (static_cast<size_t>(edge) * (edge | 1) + static_cast<size_t>(edge) * kDetTile);
+    const bool fused = tile_smem <= 100 * 1024 && !getenv("FTK_DETECT_TWO_PASS");
+    if (fused && tile_smem > 48 * 1024)
+        FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(SelectRoundTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
     for (int done = 0;; done += kRoundsPerBatch) {
         if (done >= kMaxRounds) return SetError(ctx, FTK_ERR_CUDA, "feature selection did not converge in %d rounds", kMaxRounds);
-        if (done) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 2, 0, sizeof(unsigned) * kRoundsPerBatch, st));
+        if (done) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned) * kRoundsPerBatch, st));
         for (int k = 0; k < kRoundsPerBatch; ++k) {
-            SelectRoundKernel<<<round_blocks, 256, 0, st>>>(cand, counters, state, rows, cols, dist, counters + 2, k);
-            ++ctx->launches;
+            if (fused) {
+                SelectRoundTileKernel<<<tiles, dim3(32, 8), tile_smem, st>>>(state, rows, cols, dist, counters + 1, k);
+                ++ctx->launches;
+            } else {
+                RowMaxKernel<<<row_grid, kRowMaxThreads, row_smem, st>>>(state, cols, dist, rowmax, counters + 1, k);
+                DecideKernel<<<decide_grid, dim3(32, 8), 0, st>>>(rowmax, state, rows, cols, dist, counters + 1, k);
+                ctx->launches += 2;
+            }
         }
         FTK_CUDA_CHECK(ctx, cudaGetLastError());
         unsigned undecided[kRoundsPerBatch];
-        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(undecided, counters + 2, sizeof(undecided), cudaMemcpyDeviceToHost, st));
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(undecided, counters + 1, sizeof(undecided), cudaMemcpyDeviceToHost, st));
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
         bool converged = false;
         for (int k = 0; k < kRoundsPerBatch; ++k) converged |= undecided[k] == 0;
         if (converged) break;
     }
-    if (int rc = EnsureDevice(ctx, ctx->d_det_keys, sizeof(unsigned long long) * 2 * n_cand)) return rc;
-    unsigned long long *keys = static_cast<unsigned long long *>(ctx->d_det_keys.ptr), *sorted = keys + n_cand;
-    CollectKernel<<<(n_cand + 255) / 256, 256, 0, st>>>(cand, counters, state, response, keys, counters + 1);
+    CollectKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(state, static_cast<unsigned>(n), response, keys, counters);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     unsigned n_taken = 0;
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_taken, counters + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_taken, counters, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     if (n_taken == 0) return FTK_OK;
+    if (n_taken > max_taken) return SetError(ctx, FTK_ERR_CUDA, "feature selection took %u features, more than the %zu that fit", n_taken, max_taken);
     size_t tmp_bytes = 0;
     FTK_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, keys, sorted, static_cast<int>(n_taken), 0, 64, st));
     if (int rc = EnsureDevice(ctx, ctx->d_det_tmp, tmp_bytes ? tmp_bytes : 1)) return rc;

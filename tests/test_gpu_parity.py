@@ -861,8 +861,12 @@ def test_detector_selection_vs_oracle(ctx, oracle, kind, thr, dist, needed, shap
             assert bits_equal(uv_g[:n0], ex)
 
 
-def test_detector_matches_regression_fixture(ctx, euroc_golden):
+@pytest.mark.parametrize("two_pass", [False, True])
+def test_detector_matches_regression_fixture(ctx, euroc_golden, monkeypatch, two_pass):
+    """Both selection paths: the fused shared-memory round kernel (default for windows that fit) and the two-kernel rounds."""
     import os
+    if two_pass:
+        monkeypatch.setenv("FTK_DETECT_TWO_PASS", "1")
     from conftest import GOLDEN
     g = dict(np.load(os.path.join(GOLDEN, "detector_golden.npz")))
     pyr = ft.ImagePyramidBatch(ctx, 480, 752, 4, 2)
