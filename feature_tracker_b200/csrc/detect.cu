@@ -97,11 +97,10 @@ __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict_
 __global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows, int cols, int dist, Key *__restrict__ state) {
     const float2 f = existing[blockIdx.x];
     if (!(f.x >= 0.0f && f.y >= 0.0f && f.x < static_cast<float>(cols) && f.y < static_cast<float>(rows))) return;
-    const int r = static_cast<int>(f.y), c = static_cast<int>(f.x), w = 2 * dist - 1;
-    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
-        const int rr = r - (dist - 1) + k / w, qc = c - (dist - 1) + k % w;
-        if (rr >= 0 && rr < rows && qc >= 0 && qc < cols) state[static_cast<size_t>(rr) * cols + qc] = 0ull;
-    }
+    const int r = static_cast<int>(f.y), c = static_cast<int>(f.x);
+    const int ra = max(0, r - (dist - 1)), rb = min(rows - 1, r + (dist - 1)), ca = max(0, c - (dist - 1)), cb = min(cols - 1, c + (dist - 1));
+    const unsigned w = cb - ca + 1, count = w * (rb - ra + 1);  // <= rows * cols < 2^32
+    for (unsigned k = threadIdx.x; k < count; k += blockDim.x) state[static_cast<size_t>(ra + k / w) * cols + ca + k % w] = 0ull;
 }
 
 // rowmax[r][c] = max of state[r][c - (dist-1) .. c + (dist-1)].  One block per 256-column segment of a row, staged through shared memory.
