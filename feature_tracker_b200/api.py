@@ -752,6 +752,19 @@ class FeaturePointHarrisDetector:
             return ok, merged, resp[:n_out.value]
         return ok, merged
 
+    def DetectGoodFeaturesBatch(self, images, needed_feature_num, first=0, count=None):
+        """Every image of a pyramid batch in one call (ftk_detect_features_batch).  Returns (ok, [features of image first, first + 1, ...],
+        [responses ...])."""
+        count = images.n_images - first if count is None else int(count)
+        needed = max(0, int(needed_feature_num))
+        out = np.zeros((count, max(needed, 1), 2), np.float32)
+        resp = np.zeros((count, max(needed, 1)), np.float32)
+        n_out = np.zeros(count, np.int32)
+        prm = self._params()
+        rc = lib().ftk_detect_features_batch(self.ctx._h, C.byref(prm), images._h, int(first), count, needed, _ptr(out), _ptr(resp), _ptr(n_out), 0)
+        ok = self.ctx.check(rc)
+        return ok, [out[i, :n_out[i]].copy() for i in range(count)], [resp[i, :n_out[i]].copy() for i in range(count)]
+
     def ComputeResponse(self, image, image_index=0):
         """The response map of level 0 (rows x cols float32, -inf where the window leaves the image)."""
         out = np.zeros((image.rows, image.cols), np.float32)

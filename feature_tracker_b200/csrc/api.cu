@@ -751,31 +751,48 @@ int ftk_detect_response(ftk_context *ctx, const ftk_detector_params *params, con
     return FTK_OK;
 }
 
-int ftk_detect_features(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, const float *existing_uv,
+// Shared body of ftk_detect_features / ftk_detect_features_batch: out_uv [count][needed][2], out_response [count][needed], n_out [count] (host).
+static int DetectImages(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t first, int32_t count, const float *existing_uv,
                         int32_t n_existing, int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags) {
-    if (!ctx || !params || !pyr || !n_out || n_existing < 0 || needed < 0 || (n_existing > 0 && !existing_uv) || (needed > 0 && !out_uv))
+    if (!ctx || !params || !pyr || !n_out || count < 1 || n_existing < 0 || needed < 0 || (n_existing > 0 && !existing_uv) || (needed > 0 && !out_uv))
         return FTK_ERR_INVALID_ARGUMENT;
-    *n_out = 0;
+    for (int32_t i = 0; i < count; ++i) n_out[i] = 0;
     DeviceGuard guard(ctx->device);
     const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
     const float2 *d_existing = nullptr;
     if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(existing_uv), static_cast<size_t>(n_existing), on_device, &d_existing)) return rc;
+    const size_t slots = static_cast<size_t>(count) * static_cast<size_t>(needed);
+    // staging: [n_out (count ints)] then, for host callers, [uv (slots float2)] [response (slots floats)]
+    const size_t head = (sizeof(int32_t) * count + 15) / 16 * 16;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_out, head + (on_device ? 0 : sizeof(float) * 3 * slots) + 16)) return rc;
+    int32_t *d_n_out = static_cast<int32_t *>(ctx->d_det_out.ptr);
     float2 *d_uv = reinterpret_cast<float2 *>(out_uv);
     float *d_resp = out_response;
     if (!on_device) {
-        if (int rc = EnsureDevice(ctx, ctx->d_det_out, sizeof(float) * 3 * static_cast<size_t>(needed ? needed : 1))) return rc;
-        d_uv = static_cast<float2 *>(ctx->d_det_out.ptr);
-        d_resp = reinterpret_cast<float *>(d_uv + needed);
+        d_uv = reinterpret_cast<float2 *>(static_cast<char *>(ctx->d_det_out.ptr) + head);
+        d_resp = reinterpret_cast<float *>(d_uv + slots);
+        if (slots) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_uv, 0, sizeof(float) * 3 * slots, ctx->stream));  // slots past n_out[i] read as zeros
     }
-    int n = 0;
-    if (int rc = ftk::LaunchDetectFeatures(ctx, *params, pyr->view, image, d_existing, n_existing, needed, d_uv, d_resp, &n)) return rc;
-    if (!on_device && n > 0) {
-        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_uv, d_uv, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_response) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_response, d_resp, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (int rc = ftk::LaunchDetectFeatures(ctx, *params, pyr->view, first, count, d_existing, n_existing, needed, d_uv, d_resp, d_n_out)) return rc;
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(n_out, d_n_out, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!on_device && slots) {
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_uv, d_uv, sizeof(float2) * slots, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_response) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(out_response, d_resp, sizeof(float) * slots, cudaMemcpyDeviceToHost, ctx->stream));
     }
     FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    *n_out = n;
+    for (int32_t i = 0; i < count; ++i)
+        if (n_out[i] < 0) return SetError(ctx, FTK_ERR_CUDA, "feature selection of image %d took more features than can exist", first + i);
     return FTK_OK;
+}
+
+int ftk_detect_features(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, const float *existing_uv,
+                        int32_t n_existing, int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags) {
+    return DetectImages(ctx, params, pyr, image, 1, existing_uv, n_existing, needed, out_uv, out_response, n_out, flags);
+}
+
+int ftk_detect_features_batch(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t first_image, int32_t n_images,
+                              int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags) {
+    return DetectImages(ctx, params, pyr, first_image, n_images, nullptr, 0, needed, out_uv, out_response, n_out, flags);
 }
 
 int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,

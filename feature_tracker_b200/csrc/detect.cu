@@ -16,7 +16,7 @@
 //                      SelectRoundTileKernel fuses both passes and the decision for windows that fit in shared memory.
 // K9c CollectKernel + sort + EmitKernel   the taken set ordered by key; the first `needed` are the sequential loop's output.
 // K10 BriefKernel      one warp per feature, one pair per lane, a ballot per 32-bit descriptor word.
-#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -48,9 +48,15 @@ __device__ __forceinline__ Key MakeKey(float response, unsigned pixel) {
     return (static_cast<Key>(DetOrderMap(__fadd_rn(response, 0.0f))) << 32) | (0xFFFFFFFFu - pixel);
 }
 
-__global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, ftk_detector_params p,
-                                                      float *__restrict__ response, Key *__restrict__ state) {
+// blockIdx.z = image of the batch in every selection kernel: image z owns pixels [z * rows * cols, (z + 1) * rows * cols) of the
+// response / state planes and the source plane img + z * image_stride.
+__global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict__ img, long long image_stride, int rows, int cols, int pitch,
+                                                      ftk_detector_params p, float *__restrict__ response, Key *__restrict__ state) {
     __shared__ uint8_t tile[kDetTile + 2 * kDetMaxMargin][kDetTile + 2 * kDetMaxMargin + 8];
+    img += blockIdx.z * image_stride;
+    const size_t plane = static_cast<size_t>(blockIdx.z) * rows * cols;
+    response += plane;
+    if (state) state += plane;
     const int h = p.half_patch, m = h + 1, edge = kDetTile + 2 * m;
     const int r0 = blockIdx.y * kDetTile, c0 = blockIdx.x * kDetTile;
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -104,10 +110,12 @@ __global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows
 }
 
 // rowmax[r][c] = max of state[r][c - (dist-1) .. c + (dist-1)].  One block per 256-column segment of a row, staged through shared memory.
-__global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__restrict__ state, int cols, int dist, Key *__restrict__ rowmax,
+__global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__restrict__ state, int rows, int cols, int dist, Key *__restrict__ rowmax,
                                                                const unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ Key seg[];
+    state += static_cast<size_t>(blockIdx.z) * rows * cols;
+    rowmax += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int c0 = blockIdx.x * kRowMaxThreads, halo = dist - 1, width = kRowMaxThreads + 2 * halo;
     const Key *row = state + static_cast<size_t>(blockIdx.y) * cols;
     for (int k = threadIdx.x; k < width; k += kRowMaxThreads) {
@@ -127,6 +135,8 @@ __global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__rest
 __global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowmax, Key *__restrict__ state, int rows, int cols, int dist,
                                                     unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;
+    rowmax += static_cast<size_t>(blockIdx.z) * rows * cols;
+    state += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 8 + threadIdx.y;
     bool waits = false;
     if (c < cols && r < rows) {
@@ -180,6 +190,7 @@ constexpr int kGroup = 8;
 __global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ Key sm[];
+    state += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int h = dist - 1, edge = kDetTile + 2 * h, stride = edge | 1, W = 2 * h + 1;
     Key *A = sm, *B = sm + edge * stride;  // A: states of tile + halo; B[row][32]: row maxima for the tile's columns
     const int tid = threadIdx.y * 32 + threadIdx.x;
@@ -228,20 +239,33 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int row
     }
 }
 
+// taken[z] counts image z's taken pixels; its keys go to keys + z * max_taken.
 __global__ void CollectKernel(const Key *__restrict__ state, unsigned n_pixels, const float *__restrict__ response, Key *__restrict__ keys,
-                              unsigned *__restrict__ n_keys) {
+                              unsigned max_taken, unsigned *__restrict__ taken) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pixels || state[i] != kTaken) return;
-    keys[atomicAdd(n_keys, 1u)] = MakeKey(response[i], i);
+    const size_t plane = static_cast<size_t>(blockIdx.z) * n_pixels;
+    if (i >= n_pixels || state[plane + i] != kTaken) return;
+    const unsigned slot = atomicAdd(taken + blockIdx.z, 1u);
+    if (slot < max_taken) keys[static_cast<size_t>(blockIdx.z) * max_taken + slot] = MakeKey(response[plane + i], i);
 }
 
-__global__ void EmitKernel(const Key *__restrict__ keys, int n, int cols, const float *__restrict__ response, float2 *__restrict__ uv,
-                           float *__restrict__ out_response) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Segment bounds of the per-image key lists for the segmented sort.
+__global__ void SegmentsKernel(const unsigned *__restrict__ taken, int n_images, unsigned max_taken, int *__restrict__ seg_begin, int *__restrict__ seg_end) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    if (z >= n_images) return;
+    seg_begin[z] = z * static_cast<int>(max_taken);
+    seg_end[z] = seg_begin[z] + static_cast<int>(min(taken[z], max_taken));
+}
+
+__global__ void EmitKernel(const Key *__restrict__ sorted, const unsigned *__restrict__ taken, unsigned max_taken, int needed, int rows, int cols,
+                           const float *__restrict__ response, float2 *__restrict__ uv, float *__restrict__ out_response, int *__restrict__ n_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, z = blockIdx.z;
+    const int n = min(static_cast<int>(min(taken[z], max_taken)), needed);
+    if (i == 0) n_out[z] = taken[z] > max_taken ? -1 : n;  // -1: more taken features than can exist (never happens; checked by the host)
     if (i >= n) return;
-    const unsigned p = 0xFFFFFFFFu - static_cast<unsigned>(keys[i] & 0xFFFFFFFFull);
-    uv[i] = make_float2(static_cast<float>(p % cols), static_cast<float>(p / cols));
-    if (out_response) out_response[i] = response[p];
+    const unsigned p = 0xFFFFFFFFu - static_cast<unsigned>(sorted[static_cast<size_t>(z) * max_taken + i] & 0xFFFFFFFFull);
+    uv[static_cast<size_t>(z) * needed + i] = make_float2(static_cast<float>(p % cols), static_cast<float>(p / cols));
+    if (out_response) out_response[static_cast<size_t>(z) * needed + i] = response[static_cast<size_t>(z) * rows * cols + p];
 }
 
 __global__ void __launch_bounds__(256) BriefKernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, const float2 *__restrict__ uv, int n,
@@ -282,94 +306,115 @@ int LaunchDetectResponse(ftk_context *ctx, const ftk_detector_params &p, const P
     const int rows = pyr.rows[0], cols = pyr.cols[0];
     const uint8_t *img = pyr.base[0] + image * pyr.image_stride[0];
     const dim3 grid((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile);
-    ResponseKernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(img, rows, cols, pyr.pitch[0], p, d_response, nullptr);
+    ResponseKernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(img, 0, rows, cols, pyr.pitch[0], p, d_response, nullptr);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
 }
 
-int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int image, const float2 *d_existing, int n_existing,
-                         int needed, float2 *d_out_uv, float *d_out_response, int *n_out) {
-    *n_out = 0;
-    if (int rc = CheckDetector(ctx, p, pyr, image)) return rc;
+// Images first .. first + count - 1 of the batch, `needed` features each: d_out_uv [count][needed], d_out_response [count][needed] (or
+// null), d_n_out [count] (device).  The images are processed in chunks sized to the scratch budget; every kernel of a chunk covers all
+// its images (blockIdx.z), so the launch count per chunk does not depend on the number of images.  Pre-existing features (count == 1
+// only) block their windows.  The stream is synchronised once per batch of rounds (convergence test), not per image.
+int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int first, int count, const float2 *d_existing,
+                         int n_existing, int needed, float2 *d_out_uv, float *d_out_response, int *d_n_out) {
+    if (int rc = CheckDetector(ctx, p, pyr, first)) return rc;
+    if (count < 1 || first + count > pyr.n_images) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "images %d..%d outside the pyramid batch", first, first + count - 1);
+    if (n_existing > 0 && count != 1) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pre-existing features need a single-image call");
     const int rows = pyr.rows[0], cols = pyr.cols[0];
     const size_t n = static_cast<size_t>(rows) * cols;
-    if (n >= 0xFFFFFFFFull) return SetError(ctx, FTK_ERR_UNSUPPORTED, "image too large for 32-bit pixel indices");
-    if (needed <= 0) return FTK_OK;
-    const uint8_t *img = pyr.base[0] + image * pyr.image_stride[0];
+    if (n >= 0x7FFFFFFFull) return SetError(ctx, FTK_ERR_UNSUPPORTED, "image too large for 32-bit pixel indices");
     cudaStream_t st = ctx->stream;
+    if (needed <= 0) {
+        FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_n_out, 0, sizeof(int) * count, st));
+        return FTK_OK;
+    }
     // a feature blocks |drow| < dist and |dcol| < dist; dist <= 1 blocks nothing but its own pixel, and no window is wider than the image
     const int dist = std::min(std::max(p.min_distance, 1), std::max(rows, cols));
     // taken features are >= dist apart: at most ceil(rows / dist) * ceil(cols / dist) of them
     const size_t max_taken = static_cast<size_t>((rows + dist - 1) / dist) * ((cols + dist - 1) / dist);
-    // counters: [0] taken, [1 ..] undecided per round of the current batch
-    const size_t n_counters = 1 + kRoundsPerBatch;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_response, sizeof(float) * n)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_state, sizeof(Key) * 2 * n)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_keys, sizeof(Key) * 2 * max_taken)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_cand, sizeof(unsigned) * n_counters)) return rc;
-    float *response = static_cast<float *>(ctx->d_det_response.ptr);
-    Key *state = static_cast<Key *>(ctx->d_det_state.ptr), *rowmax = state + n;
-    Key *keys = static_cast<Key *>(ctx->d_det_keys.ptr), *sorted = keys + max_taken;
-    unsigned *counters = static_cast<unsigned *>(ctx->d_det_cand.ptr);
-    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, sizeof(unsigned) * n_counters, st));
-    const dim3 tiles((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile);
-    ResponseKernel<<<tiles, dim3(32, 8), 0, st>>>(img, rows, cols, pyr.pitch[0], p, response, state);
-    ++ctx->launches;
-    FTK_CUDA_CHECK(ctx, cudaGetLastError());
-    if (n_existing > 0 && p.min_distance > 0) {
-        ExistingMaskKernel<<<n_existing, 128, 0, st>>>(d_existing, rows, cols, dist, state);
-        ++ctx->launches;
-        FTK_CUDA_CHECK(ctx, cudaGetLastError());
-    }
-    const dim3 row_grid((cols + kRowMaxThreads - 1) / kRowMaxThreads, rows), decide_grid((cols + 31) / 32, (rows + 7) / 8);
-    const size_t row_smem = sizeof(Key) * (kRowMaxThreads + 2 * (dist - 1));
-    if (row_smem > 48 * 1024) FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(RowMaxKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(row_smem)));
     // one fused kernel per round while tile + halo fit in shared memory with two CTAs per SM; two kernels per round beyond that
     const int edge = kDetTile + 2 * (dist - 1);
     const size_t tile_smem = sizeof(Key) * (static_cast<size_t>(edge) * (edge | 1) + static_cast<size_t>(edge) * kDetTile);
     const bool fused = tile_smem <= 100 * 1024 && !getenv("FTK_DETECT_TWO_PASS");
+    const size_t row_smem = sizeof(Key) * (kRowMaxThreads + 2 * (dist - 1));
     if (fused && tile_smem > 48 * 1024)
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(SelectRoundTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
-    for (int done = 0;; done += kRoundsPerBatch) {
-        if (done >= kMaxRounds) return SetError(ctx, FTK_ERR_CUDA, "feature selection did not converge in %d rounds", kMaxRounds);
-        if (done) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 1, 0, sizeof(unsigned) * kRoundsPerBatch, st));
-        for (int k = 0; k < kRoundsPerBatch; ++k) {
-            if (fused) {
-                SelectRoundTileKernel<<<tiles, dim3(32, 8), tile_smem, st>>>(state, rows, cols, dist, counters + 1, k);
-                ++ctx->launches;
-            } else {
-                RowMaxKernel<<<row_grid, kRowMaxThreads, row_smem, st>>>(state, cols, dist, rowmax, counters + 1, k);
-                DecideKernel<<<decide_grid, dim3(32, 8), 0, st>>>(rowmax, state, rows, cols, dist, counters + 1, k);
-                ctx->launches += 2;
-            }
-        }
-        FTK_CUDA_CHECK(ctx, cudaGetLastError());
-        unsigned undecided[kRoundsPerBatch];
-        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(undecided, counters + 1, sizeof(undecided), cudaMemcpyDeviceToHost, st));
-        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-        bool converged = false;
-        for (int k = 0; k < kRoundsPerBatch; ++k) converged |= undecided[k] == 0;
-        if (converged) break;
-    }
-    CollectKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(state, static_cast<unsigned>(n), response, keys, counters);
-    ++ctx->launches;
-    FTK_CUDA_CHECK(ctx, cudaGetLastError());
-    unsigned n_taken = 0;
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(&n_taken, counters, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-    if (n_taken == 0) return FTK_OK;
-    if (n_taken > max_taken) return SetError(ctx, FTK_ERR_CUDA, "feature selection took %u features, more than the %zu that fit", n_taken, max_taken);
+    if (!fused && row_smem > 48 * 1024)
+        FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(RowMaxKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(row_smem)));
+    // scratch per image: response (4 B / pixel), state (8), row maxima (8, two-kernel rounds only), two key lists
+    const size_t per_image = n * (fused ? 12 : 20) + 2 * sizeof(Key) * max_taken;
+    size_t budget = 1ull << 30;
+    if (const char *e = getenv("FTK_DETECT_SCRATCH_BYTES")) budget = static_cast<size_t>(atoll(e));
+    int chunk = static_cast<int>(std::min<size_t>(std::max<size_t>(budget / per_image, 1), static_cast<size_t>(count)));
+    chunk = std::min({chunk, 65535, static_cast<int>(0x7FFFFFFFull / std::max<size_t>(max_taken, 1))});
+    chunk = std::max(chunk, 1);
+    if (int rc = EnsureDevice(ctx, ctx->d_det_response, sizeof(float) * n * chunk)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_state, sizeof(Key) * n * chunk * (fused ? 1 : 2))) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_keys, sizeof(Key) * 2 * max_taken * chunk)) return rc;
+    // counters: undecided per round of the current batch of rounds | taken per image | segment begin | segment end
+    if (int rc = EnsureDevice(ctx, ctx->d_det_cand, sizeof(unsigned) * (kRoundsPerBatch + 3 * static_cast<size_t>(chunk)))) return rc;
+    float *response = static_cast<float *>(ctx->d_det_response.ptr);
+    Key *state = static_cast<Key *>(ctx->d_det_state.ptr), *rowmax = state + n * chunk;
+    Key *keys = static_cast<Key *>(ctx->d_det_keys.ptr), *sorted = keys + max_taken * chunk;
+    unsigned *undecided_dev = static_cast<unsigned *>(ctx->d_det_cand.ptr), *taken = undecided_dev + kRoundsPerBatch;
+    int *seg_begin = reinterpret_cast<int *>(taken + chunk), *seg_end = seg_begin + chunk;
     size_t tmp_bytes = 0;
-    FTK_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, keys, sorted, static_cast<int>(n_taken), 0, 64, st));
+    FTK_CUDA_CHECK(ctx, cub::DeviceSegmentedRadixSort::SortKeysDescending(nullptr, tmp_bytes, keys, sorted, static_cast<int>(max_taken * chunk), chunk,
+                                                                          seg_begin, seg_end, 0, 64, st));
     if (int rc = EnsureDevice(ctx, ctx->d_det_tmp, tmp_bytes ? tmp_bytes : 1)) return rc;
-    FTK_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortKeysDescending(ctx->d_det_tmp.ptr, tmp_bytes, keys, sorted, static_cast<int>(n_taken), 0, 64, st));
-    ++ctx->launches;
-    const int n_emit = static_cast<int>(n_taken) < needed ? static_cast<int>(n_taken) : needed;
-    EmitKernel<<<(n_emit + 255) / 256, 256, 0, st>>>(sorted, n_emit, cols, response, d_out_uv, d_out_response);
-    ++ctx->launches;
-    FTK_CUDA_CHECK(ctx, cudaGetLastError());
-    *n_out = n_emit;
+
+    for (int c0 = 0; c0 < count; c0 += chunk) {
+        const int m = std::min(chunk, count - c0);
+        const uint8_t *img = pyr.base[0] + static_cast<long long>(first + c0) * pyr.image_stride[0];
+        FTK_CUDA_CHECK(ctx, cudaMemsetAsync(undecided_dev, 0, sizeof(unsigned) * (kRoundsPerBatch + static_cast<size_t>(chunk)), st));
+        const dim3 tiles((cols + kDetTile - 1) / kDetTile, (rows + kDetTile - 1) / kDetTile, m);
+        ResponseKernel<<<tiles, dim3(32, 8), 0, st>>>(img, pyr.image_stride[0], rows, cols, pyr.pitch[0], p, response, state);
+        ++ctx->launches;
+        FTK_CUDA_CHECK(ctx, cudaGetLastError());
+        if (n_existing > 0 && p.min_distance > 0) {
+            ExistingMaskKernel<<<n_existing, 128, 0, st>>>(d_existing, rows, cols, dist, state);
+            ++ctx->launches;
+            FTK_CUDA_CHECK(ctx, cudaGetLastError());
+        }
+        const dim3 row_grid((cols + kRowMaxThreads - 1) / kRowMaxThreads, rows, m), decide_grid((cols + 31) / 32, (rows + 7) / 8, m);
+        for (int done = 0;; done += kRoundsPerBatch) {
+            if (done >= kMaxRounds) return SetError(ctx, FTK_ERR_CUDA, "feature selection did not converge in %d rounds", kMaxRounds);
+            if (done) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(undecided_dev, 0, sizeof(unsigned) * kRoundsPerBatch, st));
+            for (int k = 0; k < kRoundsPerBatch; ++k) {
+                if (fused) {
+                    SelectRoundTileKernel<<<tiles, dim3(32, 8), tile_smem, st>>>(state, rows, cols, dist, undecided_dev, k);
+                    ++ctx->launches;
+                } else {
+                    RowMaxKernel<<<row_grid, kRowMaxThreads, row_smem, st>>>(state, rows, cols, dist, rowmax, undecided_dev, k);
+                    DecideKernel<<<decide_grid, dim3(32, 8), 0, st>>>(rowmax, state, rows, cols, dist, undecided_dev, k);
+                    ctx->launches += 2;
+                }
+            }
+            FTK_CUDA_CHECK(ctx, cudaGetLastError());
+            unsigned undecided[kRoundsPerBatch];
+            FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(undecided, undecided_dev, sizeof(undecided), cudaMemcpyDeviceToHost, st));
+            FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            bool converged = false;
+            for (int k = 0; k < kRoundsPerBatch; ++k) converged |= undecided[k] == 0;
+            if (converged) break;
+        }
+        CollectKernel<<<dim3(static_cast<unsigned>((n + 255) / 256), 1, m), 256, 0, st>>>(state, static_cast<unsigned>(n), response, keys,
+                                                                                         static_cast<unsigned>(max_taken), taken);
+        SegmentsKernel<<<(m + 127) / 128, 128, 0, st>>>(taken, m, static_cast<unsigned>(max_taken), seg_begin, seg_end);
+        ctx->launches += 2;
+        FTK_CUDA_CHECK(ctx, cudaGetLastError());
+        FTK_CUDA_CHECK(ctx, cub::DeviceSegmentedRadixSort::SortKeysDescending(ctx->d_det_tmp.ptr, tmp_bytes, keys, sorted, static_cast<int>(max_taken * m), m,
+                                                                              seg_begin, seg_end, 0, 64, st));
+        ++ctx->launches;
+        const int n_emit_max = static_cast<int>(std::min<size_t>(max_taken, static_cast<size_t>(needed)));
+        EmitKernel<<<dim3((n_emit_max + 255) / 256, 1, m), 256, 0, st>>>(sorted, taken, static_cast<unsigned>(max_taken), needed, rows, cols, response,
+                                                                        d_out_uv + static_cast<size_t>(c0) * needed,
+                                                                        d_out_response ? d_out_response + static_cast<size_t>(c0) * needed : nullptr,
+                                                                        d_n_out + c0);
+        ++ctx->launches;
+        FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    }
     return FTK_OK;
 }
 

@@ -221,6 +221,11 @@ void ftk_detector_params_default(ftk_detector_params *params);
  * applies to existing_uv / out_uv / out_response.  The call synchronises the context. */
 int ftk_detect_features(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, const float *existing_uv,
                         int32_t n_existing, int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags);
+/* The same for images first_image .. first_image + n_images - 1 of the batch in one call (every kernel covers all images, so the
+ * launch count does not grow with the batch): out_uv [n_images][needed][2], out_response [n_images][needed] (may be NULL), n_out
+ * [n_images] (HOST).  Slots past n_out[i] are zero for host callers and untouched for device callers. */
+int ftk_detect_features_batch(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t first_image, int32_t n_images,
+                              int32_t needed, float *out_uv, float *out_response, int32_t *n_out, uint32_t flags);
 /* The response map alone: rows x cols tightly packed floats, -inf where the window leaves the image. */
 int ftk_detect_response(ftk_context *ctx, const ftk_detector_params *params, const ftk_pyramid *pyr, int32_t image, float *response, uint32_t flags);
 /* Default BRIEF pair list (HOST memory): pattern [n_bits][4] = (drow_a, dcol_a, drow_b, dcol_b) inside +-half_patch, from

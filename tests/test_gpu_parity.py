@@ -881,6 +881,28 @@ def test_detector_matches_regression_fixture(ctx, euroc_golden, monkeypatch, two
         assert ok and np.array_equal(desc, g[f"{name}_brief"]) and np.array_equal(valid, g[f"{name}_brief_valid"]), name
 
 
+@pytest.mark.parametrize("scratch_bytes", [None, "3000000", "1"])
+def test_detector_batch_vs_oracle(ctx, oracle, monkeypatch, scratch_bytes):
+    """ftk_detect_features_batch: all images of a batch in one call equal the per-image results, also when the scratch budget forces the
+    batch through in chunks (two images per chunk / one image per chunk)."""
+    if scratch_bytes is not None:
+        monkeypatch.setenv("FTK_DETECT_SCRATCH_BYTES", scratch_bytes)
+    rows, cols, n_img = 150, 200, 7
+    imgs = np.stack([S.make_image(rows, cols, seed=60 + i) for i in range(n_img)])
+    imgs[3] = 128          # no corner at all
+    imgs[5, :, :100] = 9   # a flat half
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, 2, n_img)
+    pyr.SetRawImages(imgs)
+    pyr.CreateImagePyramid()
+    for kind, thr, dist, needed, first, count in (("harris", 1e4, 12, 40, 0, n_img), ("shi_tomasi", 50.0, 7, 1000, 2, 4), ("harris", 40.0, 40, 5, 0, n_img)):
+        det = make_detector(ctx, kind, 1, thr, dist)
+        ok, uvs, resps = det.DetectGoodFeaturesBatch(pyr, needed, first=first, count=count)
+        assert ok and len(uvs) == count
+        for i in range(count):
+            ok_e, uv_e, resp_e = oracle.detect_features(po.make_detector_params(kind, 1, 0.04, thr, dist), imgs[first + i], needed)
+            assert ok_e and np.array_equal(uvs[i], uv_e) and bits_equal(resps[i], resp_e), (kind, first + i, len(uvs[i]), len(uv_e))
+
+
 def test_brief_vs_oracle(ctx, oracle):
     img = S.make_image(90, 120, seed=21)
     pyr = single_image_pyramid(ctx, img)

@@ -48,6 +48,28 @@ def main():
     e1.record(stream)
     ctx.synchronize()
     print(f"detect thr={thr} dist={dist}: {e0.elapsed_time(e1) / reps:.3f} ms per call, {n.value} features, {launches} launches per call")
+    n_img = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    if n_img:
+        imgs = np.stack([S.make_pair(480, 752, 10, pair_id=301 + (i % 8))[0] for i in range(8)])
+        big = ft.ImagePyramidBatch(ctx, 480, 752, 4, n_img)
+        big.SetRawImages(imgs[np.arange(n_img) % 8])
+        big.CreateImagePyramid()
+        d_buv = torch.zeros((n_img, 300, 2), dtype=torch.float32, device=dev)
+        counts = np.zeros(n_img, np.int32)
+
+        def run_batch():
+            ctx.check(L.ftk_detect_features_batch(ctx._h, C.byref(prm), big._h, 0, n_img, 300, vp(d_buv.data_ptr()), None, vp(counts.ctypes.data), _capi.FLAG_DEVICE_POINTERS))
+
+        run_batch()
+        l0 = L.ftk_kernel_launches(ctx._h)
+        e0.record(stream)
+        for _ in range(3):
+            run_batch()
+        e1.record(stream)
+        ctx.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(f"batch of {n_img} images: {ms:.3f} ms per call = {ms / n_img * 1e3:.1f} us per image, {(L.ftk_kernel_launches(ctx._h) - l0) // 3} launches per call, "
+              f"{int(counts.sum())} features")
 
 
 if __name__ == "__main__":
