@@ -371,6 +371,17 @@ def run_extras(ctx, L, torch, local_rank, steps):
         ms = timeit(lambda: ctx.check(L.ftk_detect_features(ctx._h, C.byref(dprm2), pyr_det._h, 0, None, 0, 300, vp(d_duv.data_ptr()), vp(d_dresp.data_ptr()),
                                                             C.byref(n_found), _capi.FLAG_DEVICE_POINTERS)), max(2, steps // 2))
         out[f"detect_300_harris_752x480_{tag}"] = {"ms": ms, "found": int(n_found.value), "pixels_per_s": ROWS * COLS / (ms * 1e-3)}
+    n_batch = 256  # the same detector over a batch of frames in one call: every kernel covers all images
+    imgs8 = np.stack([S.make_pair(ROWS, COLS, 10, pair_id=301 + i)[0] for i in range(8)])
+    pyr_batch = ft.ImagePyramidBatch(ctx, ROWS, COLS, LEVELS, n_batch)
+    pyr_batch.SetRawImages(imgs8[np.arange(n_batch) % 8])
+    pyr_batch.CreateImagePyramid()
+    d_buv = torch.zeros((n_batch, 300, 2), dtype=torch.float32, device=dev)
+    counts = np.zeros(n_batch, np.int32)
+    ms = timeit(lambda: ctx.check(L.ftk_detect_features_batch(ctx._h, C.byref(dprm2), pyr_batch._h, 0, n_batch, 300, vp(d_buv.data_ptr()), None,
+                                                              vp(counts.ctypes.data), _capi.FLAG_DEVICE_POINTERS)), 3)
+    out["detect_300_harris_batch_of_256_frames"] = {"ms": ms, "us_per_frame": ms / n_batch * 1e3, "frames_per_s": n_batch / (ms * 1e-3), "found": int(counts.sum())}
+    pyr_batch.close()
     d_resp_map = torch.empty((ROWS, COLS), dtype=torch.float32, device=dev)
     ms = timeit(lambda: ctx.check(L.ftk_detect_response(ctx._h, C.byref(dprm2), pyr_det._h, 0, vp(d_resp_map.data_ptr()), _capi.FLAG_DEVICE_POINTERS)), steps * 2)
     out["harris_response_752x480"] = {"ms": ms, "gb_per_s": 5.0 * ROWS * COLS / (ms * 1e-3) / 1e9, "algorithmic_bytes": 5 * ROWS * COLS}

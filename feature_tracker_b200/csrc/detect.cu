@@ -6,15 +6,16 @@
 // published algorithm as frozen in the detector section of oracle/ftk_oracle.c, and
 // these kernels are bit-exact against that restatement.
 //
-// K9a ResponseKernel   one pass over the image (HBM bound: 1 B read + 12 B written per pixel): integer structure-tensor sums from a
-//                      shared-memory tile, fp32 response with explicit rounding, 64-bit priority key per candidate pixel.
+// K9a ResponseKernel   one pass over the image (HBM bound: 1 B read + 8 B written per pixel): integer structure-tensor sums from a
+//                      shared-memory tile, fp32 response with explicit rounding, 32-bit ordered state per candidate pixel.
 // K9b RowMaxKernel + DecideKernel   the sequential "visit by falling response, take unless a taken feature is near" loop as a
 //                      parallel fixed point over the key image: per round, the maximum key of every pixel's window (separable:
 //                      rows, then columns); a candidate whose window holds a TAKEN pixel is dropped, one that is its window's
 //                      maximum is taken, the others wait.  Every decision is final and equals the sequential loop's; rounds
 //                      repeat until no candidate is undecided.  Key = (response, then lower row-major index).
 //                      SelectRoundTileKernel fuses both passes and the decision for windows that fit in shared memory.
-// K9c CollectKernel + sort + EmitKernel   the taken set ordered by key; the first `needed` are the sequential loop's output.
+// K9c CollectKernel + SortEmitKernel   the taken set ordered by key (bitonic sort in shared memory; CUB segmented radix sort +
+//                      EmitKernel for lists beyond 4096 keys); the first `needed` are the sequential loop's output.
 // K10 BriefKernel      one warp per feature, one pair per lane, a ballot per 32-bit descriptor word.
 #include <cub/device/device_segmented_radix_sort.cuh>
 
@@ -38,20 +39,25 @@ __device__ __forceinline__ unsigned DetOrderMap(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// Pixel states of the selection: 0 = not a candidate / dropped, kTaken = taken, anything else = the undecided candidate's key.
+// Pixel states of the selection, one 32-bit word per pixel in HBM: 0 = not a candidate / dropped, kTaken32 = taken, anything else =
+// the ordered response bits of an undecided candidate.  Comparisons run on 64-bit keys (state << 32 | ~pixel index), built when a
+// state is loaded, so that equal responses resolve towards the lower index; 0 and kTaken keep their meaning as keys.
 using Key = unsigned long long;
+using State = unsigned;
 constexpr Key kTaken = ~0ull;
+constexpr State kTaken32 = ~0u;
+__device__ __forceinline__ Key StateKey(State v, unsigned pixel) {
+    return v == 0u ? 0ull : (v == kTaken32 ? kTaken : ((static_cast<Key>(v) << 32) | (0xFFFFFFFFu - pixel)));
+}
+// -0 + 0 = +0: one state for both zeros, like the float comparison of the sequential loop; finite responses never map to 0 or kTaken32.
+__device__ __forceinline__ State MakeState(float response) { return DetOrderMap(__fadd_rn(response, 0.0f)); }
 constexpr int kRowMaxThreads = 256;
 
-__device__ __forceinline__ Key MakeKey(float response, unsigned pixel) {
-    // -0 + 0 = +0: one key for both zeros, like the float comparison of the sequential loop.  Index part < 2^32 - 1, so no key is kTaken.
-    return (static_cast<Key>(DetOrderMap(__fadd_rn(response, 0.0f))) << 32) | (0xFFFFFFFFu - pixel);
-}
 
 // blockIdx.z = image of the batch in every selection kernel: image z owns pixels [z * rows * cols, (z + 1) * rows * cols) of the
 // response / state planes and the source plane img + z * image_stride.
 __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict__ img, long long image_stride, int rows, int cols, int pitch,
-                                                      ftk_detector_params p, float *__restrict__ response, Key *__restrict__ state) {
+                                                      ftk_detector_params p, float *__restrict__ response, State *__restrict__ state) {
     __shared__ uint8_t tile[kDetTile + 2 * kDetMaxMargin][kDetTile + 2 * kDetMaxMargin + 8];
     img += blockIdx.z * image_stride;
     const size_t plane = static_cast<size_t>(blockIdx.z) * rows * cols;
@@ -59,11 +65,12 @@ __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict_
     if (state) state += plane;
     const int h = p.half_patch, m = h + 1, edge = kDetTile + 2 * m;
     const int r0 = blockIdx.y * kDetTile, c0 = blockIdx.x * kDetTile;
-    const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int k = tid; k < edge * edge; k += 256) {
-        const int tr = k / edge, tc = k - tr * edge;
-        const int r = r0 - m + tr, c = c0 - m + tc;
-        tile[tr][tc] = (r >= 0 && r < rows && c >= 0 && c < cols) ? img[static_cast<size_t>(r) * pitch + c] : 0;
+    for (int tr = threadIdx.y; tr < edge; tr += 8) {
+        const int r = r0 - m + tr;
+        for (int tc = threadIdx.x; tc < edge; tc += 32) {
+            const int c = c0 - m + tc;
+            tile[tr][tc] = (r >= 0 && r < rows && c >= 0 && c < cols) ? img[static_cast<size_t>(r) * pitch + c] : 0;
+        }
     }
     __syncthreads();
     const float inv = __fdiv_rn(1.0f, static_cast<float>(4 * (2 * h + 1) * (2 * h + 1)));
@@ -95,32 +102,32 @@ __global__ void __launch_bounds__(256) ResponseKernel(const uint8_t *__restrict_
         }
         const unsigned i = static_cast<unsigned>(r) * cols + c;
         response[i] = resp;
-        if (state) state[i] = resp >= p.min_response ? MakeKey(resp, i) : 0ull;
+        if (state) state[i] = resp >= p.min_response ? MakeState(resp) : 0u;
     }
 }
 
 // Features the caller already holds block their window (they are not candidates themselves).
-__global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows, int cols, int dist, Key *__restrict__ state) {
+__global__ void ExistingMaskKernel(const float2 *__restrict__ existing, int rows, int cols, int dist, State *__restrict__ state) {
     const float2 f = existing[blockIdx.x];
     if (!(f.x >= 0.0f && f.y >= 0.0f && f.x < static_cast<float>(cols) && f.y < static_cast<float>(rows))) return;
     const int r = static_cast<int>(f.y), c = static_cast<int>(f.x);
     const int ra = max(0, r - (dist - 1)), rb = min(rows - 1, r + (dist - 1)), ca = max(0, c - (dist - 1)), cb = min(cols - 1, c + (dist - 1));
     const unsigned w = cb - ca + 1, count = w * (rb - ra + 1);  // <= rows * cols < 2^32
-    for (unsigned k = threadIdx.x; k < count; k += blockDim.x) state[static_cast<size_t>(ra + k / w) * cols + ca + k % w] = 0ull;
+    for (unsigned k = threadIdx.x; k < count; k += blockDim.x) state[static_cast<size_t>(ra + k / w) * cols + ca + k % w] = 0u;
 }
 
 // rowmax[r][c] = max of state[r][c - (dist-1) .. c + (dist-1)].  One block per 256-column segment of a row, staged through shared memory.
-__global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__restrict__ state, int rows, int cols, int dist, Key *__restrict__ rowmax,
+__global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const State *__restrict__ state, int rows, int cols, int dist, Key *__restrict__ rowmax,
                                                                const unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ Key seg[];
     state += static_cast<size_t>(blockIdx.z) * rows * cols;
     rowmax += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int c0 = blockIdx.x * kRowMaxThreads, halo = dist - 1, width = kRowMaxThreads + 2 * halo;
-    const Key *row = state + static_cast<size_t>(blockIdx.y) * cols;
+    const State *row = state + static_cast<size_t>(blockIdx.y) * cols;
     for (int k = threadIdx.x; k < width; k += kRowMaxThreads) {
         const int c = c0 - halo + k;
-        seg[k] = (c >= 0 && c < cols) ? row[c] : 0ull;
+        seg[k] = (c >= 0 && c < cols) ? StateKey(row[c], blockIdx.y * cols + c) : 0ull;
     }
     __syncthreads();
     const int c = c0 + threadIdx.x;
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(kRowMaxThreads) RowMaxKernel(const Key *__rest
 
 // Window maximum = column maximum of the row maxima; then the decision for every undecided candidate.  counters[round] = candidates
 // still undecided after this round.  Reads only the snapshot in `rowmax` and the pixel's own state: no ordering between threads.
-__global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowmax, Key *__restrict__ state, int rows, int cols, int dist,
+__global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowmax, State *__restrict__ state, int rows, int cols, int dist,
                                                     unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;
     rowmax += static_cast<size_t>(blockIdx.z) * rows * cols;
@@ -141,13 +148,13 @@ __global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowm
     bool waits = false;
     if (c < cols && r < rows) {
         const size_t i = static_cast<size_t>(r) * cols + c;
-        const Key s = state[i];
+        const Key s = StateKey(state[i], static_cast<unsigned>(i));
         if (s != 0ull && s != kTaken) {
             const int ra = max(0, r - (dist - 1)), rb = min(rows - 1, r + (dist - 1));
             Key best = 0ull;
             for (int rr = ra; rr <= rb; ++rr) best = max(best, __ldg(rowmax + static_cast<size_t>(rr) * cols + c));
-            if (best == kTaken) state[i] = 0ull;
-            else if (best == s) state[i] = kTaken;
+            if (best == kTaken) state[i] = 0u;
+            else if (best == s) state[i] = kTaken32;
             else waits = true;
         }
     }
@@ -187,7 +194,7 @@ __device__ __forceinline__ void WindowMax(const Key *in, int stride, int W, Key 
 // needs every higher key of the window finally dropped, "dropped" needs a finally taken key in the window), so the fixed point is
 // the same -- only the number of rounds can differ.
 constexpr int kGroup = 8;
-__global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
+__global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ Key sm[];
     state += static_cast<size_t>(blockIdx.z) * rows * cols;
@@ -200,15 +207,19 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int row
     for (int q = 0; q < kDetTile / 8; ++q) {
         const int r = r_tile + threadIdx.y + 8 * q, c = c_tile + threadIdx.x;
         if (r < rows && c < cols) {
-            const Key v = __ldcg(state + static_cast<size_t>(r) * cols + c);
-            undecided |= v != 0ull && v != kTaken;
+            const State v = __ldcg(state + static_cast<size_t>(r) * cols + c);
+            undecided |= v != 0u && v != kTaken32;
         }
     }
     if (!__syncthreads_or(undecided)) return;
-    for (int k = tid; k < edge * edge; k += 256) {
-        const int tr = k / edge, tc = k - tr * edge;
-        const int r = r_tile - h + tr, c = c_tile - h + tc;
-        A[tr * stride + tc] = (r >= 0 && r < rows && c >= 0 && c < cols) ? __ldcg(state + static_cast<size_t>(r) * cols + c) : 0ull;
+    for (int tr = threadIdx.y; tr < edge; tr += 8) {  // warp = row of the staged region: no index division, coalesced 128 B requests
+        const int r = r_tile - h + tr;
+        const bool row_inside = r >= 0 && r < rows;
+        const State *row = state + static_cast<size_t>(row_inside ? r : 0) * cols;
+        for (int tc = threadIdx.x; tc < edge; tc += 32) {
+            const int c = c_tile - h + tc;
+            A[tr * stride + tc] = (row_inside && c >= 0 && c < cols) ? StateKey(__ldcg(row + c), r * cols + c) : 0ull;
+        }
     }
     __syncthreads();
     for (int item = tid; item < edge * (kDetTile / kGroup); item += 256) {
@@ -229,9 +240,9 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int row
             const int lr = g * kGroup + k;
             const Key s = A[(lr + h) * stride + h + col];
             if (s == 0ull || s == kTaken) continue;  // also every pixel outside the image
-            Key *mine = state + static_cast<size_t>(r_tile + lr) * cols + c_tile + col;
-            if (out[k] == kTaken) __stcg(mine, 0ull);
-            else if (out[k] == s) __stcg(mine, kTaken);
+            State *mine = state + static_cast<size_t>(r_tile + lr) * cols + c_tile + col;
+            if (out[k] == kTaken) __stcg(mine, 0u);
+            else if (out[k] == s) __stcg(mine, kTaken32);
             else ++waiting;
         }
         waiting = __reduce_add_sync(0xFFFFFFFFu, waiting);
@@ -240,13 +251,50 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(Key *state, int row
 }
 
 // taken[z] counts image z's taken pixels; its keys go to keys + z * max_taken.
-__global__ void CollectKernel(const Key *__restrict__ state, unsigned n_pixels, const float *__restrict__ response, Key *__restrict__ keys,
+__global__ void CollectKernel(const State *__restrict__ state, unsigned n_pixels, const float *__restrict__ response, Key *__restrict__ keys,
                               unsigned max_taken, unsigned *__restrict__ taken) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const size_t plane = static_cast<size_t>(blockIdx.z) * n_pixels;
-    if (i >= n_pixels || state[plane + i] != kTaken) return;
+    if (i >= n_pixels || state[plane + i] != kTaken32) return;
     const unsigned slot = atomicAdd(taken + blockIdx.z, 1u);
-    if (slot < max_taken) keys[static_cast<size_t>(blockIdx.z) * max_taken + slot] = MakeKey(response[plane + i], i);
+    if (slot < max_taken) keys[static_cast<size_t>(blockIdx.z) * max_taken + slot] = StateKey(MakeState(response[plane + i]), i);
+}
+
+// Per-image key lists of at most kSortMax keys: one CTA sorts image z's list in shared memory (bitonic, descending) and writes the
+// first `needed` features straight away -- no sorted copy in HBM, no separate emit pass.
+constexpr int kSortMax = 4096;
+__global__ void __launch_bounds__(256) SortEmitKernel(const Key *__restrict__ keys, const unsigned *__restrict__ taken, unsigned max_taken, int needed, int rows,
+                                                      int cols, const float *__restrict__ response, float2 *__restrict__ uv, float *__restrict__ out_response,
+                                                      int *__restrict__ n_out) {
+    extern __shared__ Key list[];
+    const int z = blockIdx.x;
+    const unsigned count = taken[z];
+    if (count > max_taken) {  // more taken features than can exist (never happens; the host reports it)
+        if (threadIdx.x == 0) n_out[z] = -1;
+        return;
+    }
+    int padded = 1;
+    while (padded < static_cast<int>(count)) padded <<= 1;
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) list[i] = i < static_cast<int>(count) ? keys[static_cast<size_t>(z) * max_taken + i] : 0ull;
+    __syncthreads();
+    for (int size = 2; size <= padded; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < padded / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;  // lo has bit `stride` clear
+                const bool descending = (lo & size) == 0;
+                const Key a = list[lo], b = list[hi];
+                if ((a < b) == descending) list[lo] = b, list[hi] = a;
+            }
+            __syncthreads();
+        }
+    }
+    const int n = min(static_cast<int>(count), needed);
+    if (threadIdx.x == 0) n_out[z] = n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned p = 0xFFFFFFFFu - static_cast<unsigned>(list[i] & 0xFFFFFFFFull);
+        uv[static_cast<size_t>(z) * needed + i] = make_float2(static_cast<float>(p % cols), static_cast<float>(p / cols));
+        if (out_response) out_response[static_cast<size_t>(z) * needed + i] = response[static_cast<size_t>(z) * rows * cols + p];
+    }
 }
 
 // Segment bounds of the per-image key lists for the segmented sort.
@@ -342,20 +390,21 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(SelectRoundTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
     if (!fused && row_smem > 48 * 1024)
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(RowMaxKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(row_smem)));
-    // scratch per image: response (4 B / pixel), state (8), row maxima (8, two-kernel rounds only), two key lists
-    const size_t per_image = n * (fused ? 12 : 20) + 2 * sizeof(Key) * max_taken;
+    // scratch per image: response (4 B / pixel), state (4), row maxima (8, two-kernel rounds only), two key lists
+    const size_t per_image = n * (fused ? 8 : 16) + 2 * sizeof(Key) * max_taken;
     size_t budget = 1ull << 30;
     if (const char *e = getenv("FTK_DETECT_SCRATCH_BYTES")) budget = static_cast<size_t>(atoll(e));
     int chunk = static_cast<int>(std::min<size_t>(std::max<size_t>(budget / per_image, 1), static_cast<size_t>(count)));
     chunk = std::min({chunk, 65535, static_cast<int>(0x7FFFFFFFull / std::max<size_t>(max_taken, 1))});
     chunk = std::max(chunk, 1);
     if (int rc = EnsureDevice(ctx, ctx->d_det_response, sizeof(float) * n * chunk)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_det_state, sizeof(Key) * n * chunk * (fused ? 1 : 2))) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_det_state, (sizeof(State) + (fused ? 0 : sizeof(Key))) * n * chunk + 16)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_det_keys, sizeof(Key) * 2 * max_taken * chunk)) return rc;
     // counters: undecided per round of the current batch of rounds | taken per image | segment begin | segment end
     if (int rc = EnsureDevice(ctx, ctx->d_det_cand, sizeof(unsigned) * (kRoundsPerBatch + 3 * static_cast<size_t>(chunk)))) return rc;
     float *response = static_cast<float *>(ctx->d_det_response.ptr);
-    Key *state = static_cast<Key *>(ctx->d_det_state.ptr), *rowmax = state + n * chunk;
+    Key *rowmax = static_cast<Key *>(ctx->d_det_state.ptr);  // two-kernel rounds only
+    State *state = reinterpret_cast<State *>(fused ? rowmax : rowmax + n * chunk);
     Key *keys = static_cast<Key *>(ctx->d_det_keys.ptr), *sorted = keys + max_taken * chunk;
     unsigned *undecided_dev = static_cast<unsigned *>(ctx->d_det_cand.ptr), *taken = undecided_dev + kRoundsPerBatch;
     int *seg_begin = reinterpret_cast<int *>(taken + chunk), *seg_end = seg_begin + chunk;
@@ -401,17 +450,28 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
         }
         CollectKernel<<<dim3(static_cast<unsigned>((n + 255) / 256), 1, m), 256, 0, st>>>(state, static_cast<unsigned>(n), response, keys,
                                                                                          static_cast<unsigned>(max_taken), taken);
+        ++ctx->launches;
+        FTK_CUDA_CHECK(ctx, cudaGetLastError());
+        float2 *uv_out = d_out_uv + static_cast<size_t>(c0) * needed;
+        float *resp_out = d_out_response ? d_out_response + static_cast<size_t>(c0) * needed : nullptr;
+        if (max_taken <= kSortMax) {  // the usual case: a few hundred features per image
+            int padded = 1;
+            while (padded < static_cast<int>(max_taken)) padded <<= 1;
+            SortEmitKernel<<<m, 256, sizeof(Key) * padded, st>>>(keys, taken, static_cast<unsigned>(max_taken), needed, rows, cols, response, uv_out, resp_out,
+                                                                d_n_out + c0);
+            ++ctx->launches;
+            FTK_CUDA_CHECK(ctx, cudaGetLastError());
+            continue;
+        }
         SegmentsKernel<<<(m + 127) / 128, 128, 0, st>>>(taken, m, static_cast<unsigned>(max_taken), seg_begin, seg_end);
-        ctx->launches += 2;
+        ++ctx->launches;
         FTK_CUDA_CHECK(ctx, cudaGetLastError());
         FTK_CUDA_CHECK(ctx, cub::DeviceSegmentedRadixSort::SortKeysDescending(ctx->d_det_tmp.ptr, tmp_bytes, keys, sorted, static_cast<int>(max_taken * m), m,
                                                                               seg_begin, seg_end, 0, 64, st));
         ++ctx->launches;
         const int n_emit_max = static_cast<int>(std::min<size_t>(max_taken, static_cast<size_t>(needed)));
         EmitKernel<<<dim3((n_emit_max + 255) / 256, 1, m), 256, 0, st>>>(sorted, taken, static_cast<unsigned>(max_taken), needed, rows, cols, response,
-                                                                        d_out_uv + static_cast<size_t>(c0) * needed,
-                                                                        d_out_response ? d_out_response + static_cast<size_t>(c0) * needed : nullptr,
-                                                                        d_n_out + c0);
+                                                                        uv_out, resp_out, d_n_out + c0);
         ++ctx->launches;
         FTK_CUDA_CHECK(ctx, cudaGetLastError());
     }
