@@ -162,44 +162,47 @@ __global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowm
     if (n_waiting && threadIdx.x == 0 && threadIdx.y == 0) atomicAdd(counters + round, static_cast<unsigned>(n_waiting));
 }
 
-// out[k] = max of in[k * 1 .. k + W - 1] (elements `stride` apart), k = 0 .. G-1: the G windows share elements G-1 .. W-1, window k
-// adds the suffix k .. G-2 on the left and the prefix W .. W+k-1 on the right -- W + G - 1 reads instead of G * W.
-template <int G>
-__device__ __forceinline__ void WindowMax(const Key *in, int stride, int W, Key (&out)[G]) {
+// out[k] = max of element(k) .. element(k + W - 1), k = 0 .. G-1: the G windows share elements G-1 .. W-1, window k adds the suffix
+// k .. G-2 on the left and the prefix W .. W+k-1 on the right -- W + G - 1 reads instead of G * W.
+template <int G, typename Element>
+__device__ __forceinline__ void WindowMax(Element element, int W, Key (&out)[G]) {
     if (W < G) {
 #pragma unroll
         for (int k = 0; k < G; ++k) {
             Key best = 0ull;
-            for (int j = 0; j < W; ++j) best = max(best, in[(k + j) * stride]);
+            for (int j = 0; j < W; ++j) best = max(best, element(k + j));
             out[k] = best;
         }
         return;
     }
     Key common = 0ull;
-    for (int j = G - 1; j < W; ++j) common = max(common, in[j * stride]);
+    for (int j = G - 1; j < W; ++j) common = max(common, element(j));
     out[G - 1] = common;
 #pragma unroll
-    for (int k = G - 2; k >= 0; --k) out[k] = max(out[k + 1], in[k * stride]);  // common + left suffix
+    for (int k = G - 2; k >= 0; --k) out[k] = max(out[k + 1], element(k));  // common + left suffix
     Key prefix = 0ull;
 #pragma unroll
     for (int k = 1; k < G; ++k) {
-        prefix = max(prefix, in[(W + k - 1) * stride]);
+        prefix = max(prefix, element(W + k - 1));
         out[k] = max(out[k], prefix);
     }
 }
 
-// One round in one kernel for windows that fit in shared memory: a CTA stages its 32 x 32 tile plus the halo, takes row maxima, then
-// column maxima, and decides its own pixels IN PLACE.  Neighbouring CTAs may read a pixel before or after its decision; both
-// readings lead to decisions the sequential loop also makes (a state only ever moves from undecided to its final value, "taken"
-// needs every higher key of the window finally dropped, "dropped" needs a finally taken key in the window), so the fixed point is
-// the same -- only the number of rounds can differ.
+// One round in one kernel for windows that fit in shared memory: a CTA stages the 32-bit states of its 32 x 32 tile plus the halo,
+// takes row maxima of the keys (state << 32 | ~pixel; built on the fly: a pixel that is no candidate has a key below every
+// candidate's, a taken one a key above), then column maxima, and decides its own pixels IN PLACE.  Neighbouring CTAs may read a
+// pixel before or after its decision; both readings lead to decisions the sequential loop also makes (a state only ever moves from
+// undecided to its final value, "taken" needs every higher key of the window finally dropped, "dropped" needs a finally taken key
+// in the window), so the fixed point is the same -- only the number of rounds can differ.
 constexpr int kGroup = 8;
+constexpr int kStageCols = 4;  // column slots per lane while staging: edge <= 32 * kStageCols
 __global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ Key sm[];
     state += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int h = dist - 1, edge = kDetTile + 2 * h, stride = edge | 1, W = 2 * h + 1;
-    Key *A = sm, *B = sm + edge * stride;  // A: states of tile + halo; B[row][32]: row maxima for the tile's columns
+    Key *B = sm;                                                      // B[row][32]: row maxima for the tile's columns
+    State *A = reinterpret_cast<State *>(sm + edge * kDetTile);       // A: states of tile + halo, `stride` words per row
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int r_tile = blockIdx.y * kDetTile, c_tile = blockIdx.x * kDetTile;
     bool undecided = false;
@@ -212,37 +215,53 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int r
         }
     }
     if (!__syncthreads_or(undecided)) return;
-    for (int tr = threadIdx.y; tr < edge; tr += 8) {  // warp = row of the staged region: no index division, coalesced 128 B requests
-        const int r = r_tile - h + tr;
-        const bool row_inside = r >= 0 && r < rows;
-        const State *row = state + static_cast<size_t>(row_inside ? r : 0) * cols;
-        for (int tc = threadIdx.x; tc < edge; tc += 32) {
-            const int c = c_tile - h + tc;
-            A[tr * stride + tc] = (row_inside && c >= 0 && c < cols) ? StateKey(__ldcg(row + c), r * cols + c) : 0ull;
+    {  // staging: warp = row of the region, lane = column slot; everything column-dependent is computed once
+        int offset[kStageCols];
+        bool inside[kStageCols];
+#pragma unroll
+        for (int q = 0; q < kStageCols; ++q) {
+            const int tc = threadIdx.x + 32 * q, c = c_tile - h + tc;
+            inside[q] = tc < edge && c >= 0 && c < cols;
+            offset[q] = inside[q] ? c : 0;
+        }
+        for (int tr = threadIdx.y; tr < edge; tr += 8) {
+            const int r = r_tile - h + tr;
+            const bool row_inside = r >= 0 && r < rows;
+            const State *row = state + static_cast<size_t>(row_inside ? r : 0) * cols;
+            State v[kStageCols];
+#pragma unroll
+            for (int q = 0; q < kStageCols; ++q) v[q] = (row_inside && inside[q]) ? __ldcg(row + offset[q]) : 0u;
+#pragma unroll
+            for (int q = 0; q < kStageCols; ++q)
+                if (threadIdx.x + 32 * q < edge) A[tr * stride + threadIdx.x + 32 * q] = v[q];
         }
     }
     __syncthreads();
     for (int item = tid; item < edge * (kDetTile / kGroup); item += 256) {
         const int row = item / (kDetTile / kGroup), g = item % (kDetTile / kGroup);
+        const State *in = A + row * stride + g * kGroup;
+        // ~pixel of element 0; elements to the right have lower "~pixel".  Outside the image the index is meaningless and the state 0.
+        const unsigned low0 = 0xFFFFFFFFu - static_cast<unsigned>((r_tile - h + row) * cols + (c_tile - h + g * kGroup));
         Key out[kGroup];
-        WindowMax<kGroup>(A + row * stride + g * kGroup, 1, W, out);
+        WindowMax<kGroup>([&](int j) { return (static_cast<Key>(in[j]) << 32) | (low0 - static_cast<unsigned>(j)); }, W, out);
 #pragma unroll
         for (int k = 0; k < kGroup; ++k) B[row * kDetTile + g * kGroup + k] = out[k];
     }
     __syncthreads();
     if (tid < 32 * (kDetTile / kGroup)) {
         const int col = tid & 31, g = tid >> 5;
+        const Key *in = B + g * kGroup * kDetTile + col;
         Key out[kGroup];
-        WindowMax<kGroup>(B + g * kGroup * kDetTile + col, kDetTile, W, out);
+        WindowMax<kGroup>([&](int j) { return in[j * kDetTile]; }, W, out);
         unsigned waiting = 0;
 #pragma unroll
         for (int k = 0; k < kGroup; ++k) {
             const int lr = g * kGroup + k;
-            const Key s = A[(lr + h) * stride + h + col];
-            if (s == 0ull || s == kTaken) continue;  // also every pixel outside the image
-            State *mine = state + static_cast<size_t>(r_tile + lr) * cols + c_tile + col;
-            if (out[k] == kTaken) __stcg(mine, 0u);
-            else if (out[k] == s) __stcg(mine, kTaken32);
+            const State s = A[(lr + h) * stride + h + col];
+            if (s == 0u || s == kTaken32) continue;  // also every pixel outside the image
+            const unsigned pixel = static_cast<unsigned>((r_tile + lr) * cols + c_tile + col);
+            if (static_cast<State>(out[k] >> 32) == kTaken32) __stcg(state + pixel, 0u);
+            else if (out[k] == ((static_cast<Key>(s) << 32) | (0xFFFFFFFFu - pixel))) __stcg(state + pixel, kTaken32);
             else ++waiting;
         }
         waiting = __reduce_add_sync(0xFFFFFFFFu, waiting);
@@ -383,8 +402,8 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
     const size_t max_taken = static_cast<size_t>((rows + dist - 1) / dist) * ((cols + dist - 1) / dist);
     // one fused kernel per round while tile + halo fit in shared memory with two CTAs per SM; two kernels per round beyond that
     const int edge = kDetTile + 2 * (dist - 1);
-    const size_t tile_smem = sizeof(Key) * (static_cast<size_t>(edge) * (edge | 1) + static_cast<size_t>(edge) * kDetTile);
-    const bool fused = tile_smem <= 100 * 1024 && !getenv("FTK_DETECT_TWO_PASS");
+    const size_t tile_smem = sizeof(Key) * static_cast<size_t>(edge) * kDetTile + sizeof(State) * static_cast<size_t>(edge) * (edge | 1);
+    const bool fused = edge <= 32 * kStageCols && !getenv("FTK_DETECT_TWO_PASS");  // <= 96 KB: at least two CTAs per SM
     const size_t row_smem = sizeof(Key) * (kRowMaxThreads + 2 * (dist - 1));
     if (fused && tile_smem > 48 * 1024)
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(SelectRoundTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
