@@ -165,22 +165,22 @@ __global__ void __launch_bounds__(256) DecideKernel(const Key *__restrict__ rowm
 // out[k] = max of element(k) .. element(k + W - 1), k = 0 .. G-1: the G windows share elements G-1 .. W-1, window k adds the suffix
 // k .. G-2 on the left and the prefix W .. W+k-1 on the right -- W + G - 1 reads instead of G * W.
 template <int G, typename Element>
-__device__ __forceinline__ void WindowMax(Element element, int W, Key (&out)[G]) {
+__device__ __forceinline__ void WindowMax(Element element, int W, State (&out)[G]) {
     if (W < G) {
 #pragma unroll
         for (int k = 0; k < G; ++k) {
-            Key best = 0ull;
+            State best = 0u;
             for (int j = 0; j < W; ++j) best = max(best, element(k + j));
             out[k] = best;
         }
         return;
     }
-    Key common = 0ull;
+    State common = 0u;
     for (int j = G - 1; j < W; ++j) common = max(common, element(j));
     out[G - 1] = common;
 #pragma unroll
     for (int k = G - 2; k >= 0; --k) out[k] = max(out[k + 1], element(k));  // common + left suffix
-    Key prefix = 0ull;
+    State prefix = 0u;
 #pragma unroll
     for (int k = 1; k < G; ++k) {
         prefix = max(prefix, element(W + k - 1));
@@ -189,20 +189,21 @@ __device__ __forceinline__ void WindowMax(Element element, int W, Key (&out)[G])
 }
 
 // One round in one kernel for windows that fit in shared memory: a CTA stages the 32-bit states of its 32 x 32 tile plus the halo,
-// takes row maxima of the keys (state << 32 | ~pixel; built on the fly: a pixel that is no candidate has a key below every
-// candidate's, a taken one a key above), then column maxima, and decides its own pixels IN PLACE.  Neighbouring CTAs may read a
-// pixel before or after its decision; both readings lead to decisions the sequential loop also makes (a state only ever moves from
-// undecided to its final value, "taken" needs every higher key of the window finally dropped, "dropped" needs a finally taken key
-// in the window), so the fixed point is the same -- only the number of rounds can differ.
+// takes row maxima, then column maxima (one integer max per element: 0 < any response < kTaken32), and decides its own pixels IN
+// PLACE: a taken state in the window drops the pixel, a larger state makes it wait, and a pixel that holds the window's maximum is
+// taken unless an equal state with a lower index is in the window (checked explicitly, in index order, for those few pixels only).
+// Neighbouring CTAs may read a pixel before or after its decision; both readings lead to decisions the sequential loop also makes
+// (a state only ever moves from undecided to its final value, "taken" needs every higher key of the window finally dropped,
+// "dropped" needs a finally taken key in the window), so the fixed point is the same -- only the number of rounds can differ.
 constexpr int kGroup = 8;
 constexpr int kStageCols = 4;  // column slots per lane while staging: edge <= 32 * kStageCols
 __global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
-    extern __shared__ Key sm[];
+    extern __shared__ State sm32[];
     state += static_cast<size_t>(blockIdx.z) * rows * cols;
     const int h = dist - 1, edge = kDetTile + 2 * h, stride = edge | 1, W = 2 * h + 1;
-    Key *B = sm;                                                      // B[row][32]: row maxima for the tile's columns
-    State *A = reinterpret_cast<State *>(sm + edge * kDetTile);       // A: states of tile + halo, `stride` words per row
+    State *B = sm32;                    // B[row][32]: row maxima for the tile's columns
+    State *A = sm32 + edge * kDetTile;  // A: states of tile + halo, `stride` words per row
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int r_tile = blockIdx.y * kDetTile, c_tile = blockIdx.x * kDetTile;
     bool undecided = false;
@@ -240,29 +241,47 @@ __global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int r
     for (int item = tid; item < edge * (kDetTile / kGroup); item += 256) {
         const int row = item / (kDetTile / kGroup), g = item % (kDetTile / kGroup);
         const State *in = A + row * stride + g * kGroup;
-        // ~pixel of element 0; elements to the right have lower "~pixel".  Outside the image the index is meaningless and the state 0.
-        const unsigned low0 = 0xFFFFFFFFu - static_cast<unsigned>((r_tile - h + row) * cols + (c_tile - h + g * kGroup));
-        Key out[kGroup];
-        WindowMax<kGroup>([&](int j) { return (static_cast<Key>(in[j]) << 32) | (low0 - static_cast<unsigned>(j)); }, W, out);
+        State out[kGroup];
+        WindowMax<kGroup>([&](int j) { return in[j]; }, W, out);
 #pragma unroll
         for (int k = 0; k < kGroup; ++k) B[row * kDetTile + g * kGroup + k] = out[k];
     }
     __syncthreads();
     if (tid < 32 * (kDetTile / kGroup)) {
         const int col = tid & 31, g = tid >> 5;
-        const Key *in = B + g * kGroup * kDetTile + col;
-        Key out[kGroup];
+        const State *in = B + g * kGroup * kDetTile + col;
+        State out[kGroup];
         WindowMax<kGroup>([&](int j) { return in[j * kDetTile]; }, W, out);
         unsigned waiting = 0;
 #pragma unroll
         for (int k = 0; k < kGroup; ++k) {
-            const int lr = g * kGroup + k;
-            const State s = A[(lr + h) * stride + h + col];
-            if (s == 0u || s == kTaken32) continue;  // also every pixel outside the image
-            const unsigned pixel = static_cast<unsigned>((r_tile + lr) * cols + c_tile + col);
-            if (static_cast<State>(out[k] >> 32) == kTaken32) __stcg(state + pixel, 0u);
-            else if (out[k] == ((static_cast<Key>(s) << 32) | (0xFFFFFFFFu - pixel))) __stcg(state + pixel, kTaken32);
-            else ++waiting;
+            const int lr = g * kGroup + k;  // the same tile row for the whole warp
+            const State *centre = A + (lr + h) * stride + h + col;
+            const State s = *centre;
+            const bool live = s != 0u && s != kTaken32;  // false for every pixel outside the image
+            State *mine = state + static_cast<size_t>(r_tile + lr) * cols + c_tile + col;
+            if (live && out[k] == kTaken32) __stcg(mine, 0u);
+            if (live && out[k] != kTaken32 && out[k] > s) ++waiting;
+            // The window's maximum response is mine; an equal one at a lower index (rows above, or left in my row) goes first.  Few
+            // pixels get here, so the warp checks them one after the other, all lanes scanning one pixel's window part.
+            bool holds = live && out[k] == s;
+            if (holds && h > 0 && (centre[-1] == s || centre[-stride] == s)) holds = false, ++waiting;  // plateaus: the neighbour goes first
+            unsigned holders = __ballot_sync(0xFFFFFFFFu, holds);
+            while (holders) {
+                const int src = __ffs(holders) - 1;
+                holders &= holders - 1;
+                const State want = __shfl_sync(0xFFFFFFFFu, s, src);
+                const State *c0 = A + (lr + h) * stride + h + src;
+                bool lower_tie = static_cast<int>(threadIdx.x) < h && c0[static_cast<int>(threadIdx.x) - h] == want;  // h <= 48: two rounds at most
+                if (static_cast<int>(threadIdx.x) + 32 < h) lower_tie |= c0[static_cast<int>(threadIdx.x) + 32 - h] == want;
+                for (int dr = -h; dr < 0; ++dr)
+                    for (int dc = -h + static_cast<int>(threadIdx.x); dc <= h; dc += 32) lower_tie |= c0[dr * stride + dc] == want;
+                lower_tie = __any_sync(0xFFFFFFFFu, lower_tie);
+                if (col == src) {
+                    if (lower_tie) ++waiting;
+                    else __stcg(mine, kTaken32);
+                }
+            }
         }
         waiting = __reduce_add_sync(0xFFFFFFFFu, waiting);
         if (col == 0 && waiting) atomicAdd(counters + round, waiting);
@@ -402,8 +421,8 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
     const size_t max_taken = static_cast<size_t>((rows + dist - 1) / dist) * ((cols + dist - 1) / dist);
     // one fused kernel per round while tile + halo fit in shared memory with two CTAs per SM; two kernels per round beyond that
     const int edge = kDetTile + 2 * (dist - 1);
-    const size_t tile_smem = sizeof(Key) * static_cast<size_t>(edge) * kDetTile + sizeof(State) * static_cast<size_t>(edge) * (edge | 1);
-    const bool fused = edge <= 32 * kStageCols && !getenv("FTK_DETECT_TWO_PASS");  // <= 96 KB: at least two CTAs per SM
+    const size_t tile_smem = sizeof(State) * (static_cast<size_t>(edge) * kDetTile + static_cast<size_t>(edge) * (edge | 1));
+    const bool fused = edge <= 32 * kStageCols && !getenv("FTK_DETECT_TWO_PASS");  // <= 82 KB: at least two CTAs per SM
     const size_t row_smem = sizeof(Key) * (kRowMaxThreads + 2 * (dist - 1));
     if (fused && tile_smem > 48 * 1024)
         FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(SelectRoundTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tile_smem)));
