@@ -197,7 +197,7 @@ __device__ __forceinline__ void WindowMax(Element element, int W, State (&out)[G
 // "dropped" needs a finally taken key in the window), so the fixed point is the same -- only the number of rounds can differ.
 constexpr int kGroup = 8;
 constexpr int kStageCols = 4;  // column slots per lane while staging: edge <= 32 * kStageCols
-__global__ void __launch_bounds__(256) SelectRoundTileKernel(State *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
+__global__ void __launch_bounds__(256, 6) SelectRoundTileKernel(State *state, int rows, int cols, int dist, unsigned *__restrict__ counters, int round) {
     if (round > 0 && counters[round - 1] == 0) return;  // converged earlier in this batch
     extern __shared__ State sm32[];
     state += static_cast<size_t>(blockIdx.z) * rows * cols;
