@@ -8,12 +8,12 @@
 //
 // K9a ResponseKernel   one pass over the image (HBM bound: 1 B read + 8 B written per pixel): integer structure-tensor sums from a
 //                      shared-memory tile, fp32 response with explicit rounding, 32-bit ordered state per candidate pixel.
-// K9b RowMaxKernel + DecideKernel   the sequential "visit by falling response, take unless a taken feature is near" loop as a
-//                      parallel fixed point over the key image: per round, the maximum key of every pixel's window (separable:
-//                      rows, then columns); a candidate whose window holds a TAKEN pixel is dropped, one that is its window's
-//                      maximum is taken, the others wait.  Every decision is final and equals the sequential loop's; rounds
-//                      repeat until no candidate is undecided.  Key = (response, then lower row-major index).
-//                      SelectRoundTileKernel fuses both passes and the decision for windows that fit in shared memory.
+// K9b SelectRoundTileKernel   the sequential "visit by falling response, take unless a taken feature is near" loop as a parallel
+//                      fixed point over the state plane: per round, the maximum of every pixel's window (separable: rows, then
+//                      columns, in shared memory); a candidate whose window holds a taken pixel is dropped, one that holds its
+//                      window's maximum (ties: the lower row-major index) is taken, the others wait.  Every decision is final and
+//                      equals the sequential loop's; rounds repeat until no candidate is undecided.  Windows too wide for
+//                      shared memory use RowMaxKernel + DecideKernel (two kernels per round, 64-bit keys through HBM).
 // K9c CollectKernel + SortEmitKernel   the taken set ordered by key (bitonic sort in shared memory; CUB segmented radix sort +
 //                      EmitKernel for lists beyond 4096 keys); the first `needed` are the sequential loop's output.
 // K10 BriefKernel      one warp per feature, one pair per lane, a ballot per 32-bit descriptor word.
@@ -40,8 +40,8 @@ __device__ __forceinline__ unsigned DetOrderMap(float v) {
 }
 
 // Pixel states of the selection, one 32-bit word per pixel in HBM: 0 = not a candidate / dropped, kTaken32 = taken, anything else =
-// the ordered response bits of an undecided candidate.  Comparisons run on 64-bit keys (state << 32 | ~pixel index), built when a
-// state is loaded, so that equal responses resolve towards the lower index; 0 and kTaken keep their meaning as keys.
+// the ordered response bits of an undecided candidate.  The two-kernel rounds compare 64-bit keys (state << 32 | ~pixel index),
+// built when a state is loaded, so that equal responses resolve towards the lower index; 0 and kTaken keep their meaning as keys.
 using Key = unsigned long long;
 using State = unsigned;
 constexpr Key kTaken = ~0ull;
@@ -52,7 +52,6 @@ __device__ __forceinline__ Key StateKey(State v, unsigned pixel) {
 // -0 + 0 = +0: one state for both zeros, like the float comparison of the sequential loop; finite responses never map to 0 or kTaken32.
 __device__ __forceinline__ State MakeState(float response) { return DetOrderMap(__fadd_rn(response, 0.0f)); }
 constexpr int kRowMaxThreads = 256;
-
 
 // blockIdx.z = image of the batch in every selection kernel: image z owns pixels [z * rows * cols, (z + 1) * rows * cols) of the
 // response / state planes and the source plane img + z * image_stride.
