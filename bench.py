@@ -300,6 +300,20 @@ def run_extras(ctx, L, torch, local_rank, steps):
                                                              vp(d_pos.data_ptr()), 50, 50, 60.0, vp(d_idx.data_ptr()), fl)), steps * 4)
     out["C4_brief256_nearby_10k_window50"] = {"ref_rows_per_s": 1e4 / (ms * 1e-3), "ms": ms}
 
+    # ---- 1000 frame pairs x (300 x 300) BRIEF-256 NearbyMatch in one call (the KLT batch's counterpart for descriptor tracking) ----
+    n_mp, per = 1000, 300
+    rb1, cb1, pred1, pos1, _ = S.make_brief_sets(per, per, seed=9)
+    d_rp = torch.from_numpy(np.tile(ft.pack_brief(rb1), (n_mp, 1)).astype(np.int32)).to(dev)
+    d_cp = torch.from_numpy(np.tile(ft.pack_brief(cb1), (n_mp, 1)).astype(np.int32)).to(dev)
+    d_predp = torch.from_numpy(np.tile(pred1, (n_mp, 1))).to(dev)
+    d_posp = torch.from_numpy(np.tile(pos1, (n_mp, 1))).to(dev)
+    offs = (np.arange(n_mp + 1) * per).astype(np.int32)
+    d_idxp = torch.full((n_mp * per,), -1, dtype=torch.int32, device=dev)
+    ms = timeit(lambda: ctx.check(L.ftk_match_hamming_pairs(ctx._h, vp(d_rp.data_ptr()), vp(d_cp.data_ptr()), 8, n_mp, vp(offs.ctypes.data), vp(offs.ctypes.data),
+                                                            vp(d_predp.data_ptr()), vp(d_posp.data_ptr()), 50, 50, 60.0, vp(d_idxp.data_ptr()), fl)), steps * 2)
+    out["brief256_nearby_1000_pairs_x_300x300"] = {"ms": ms, "pairs_of_frames_per_s": n_mp / (ms * 1e-3), "ref_rows_per_s": n_mp * per / (ms * 1e-3),
+                                                   "matched": int((d_idxp.cpu().numpy() >= 0).sum())}
+
     # ---- C5: float-256 force 20k x 20k ----
     rf, cf = S.make_float_sets(20000, 20000, seed=5)
     d_rf = torch.from_numpy(rf).to(dev)

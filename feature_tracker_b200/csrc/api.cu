@@ -629,6 +629,40 @@ int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_re
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 
+int ftk_match_hamming_pairs(ftk_context *ctx, const uint32_t *ref, const uint32_t *cur, int32_t words, int32_t n_pairs, const int32_t *ref_offsets,
+                            const int32_t *cur_offsets, const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist,
+                            int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_pairs < 0 || words < 0 || words > 64 || !ref_offsets || !cur_offsets || (pred_uv && !cur_uv)) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs == 0) return FTK_OK;
+    for (int32_t p = 0; p < n_pairs; ++p)
+        if (ref_offsets[p + 1] < ref_offsets[p] || cur_offsets[p + 1] < cur_offsets[p] || ref_offsets[0] != 0 || cur_offsets[0] != 0)
+            return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "descriptor offsets must start at 0 and not decrease (pair %d)", p);
+    const int32_t n_ref = ref_offsets[n_pairs], n_cur = cur_offsets[n_pairs];
+    if ((n_ref > 0 && !ref) || (n_cur > 0 && !cur)) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const uint32_t *d_ref = nullptr, *d_cur = nullptr;
+    const float2 *d_pred = nullptr, *d_pos = nullptr;
+    const int32_t *d_ref_off = nullptr, *d_cur_off = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * words, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * words, on_device, &d_cur)) return rc;
+    if (pred_uv) {
+        if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
+        if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
+    }
+    if (int rc = Stage(ctx, ctx->d_offsets, ref_offsets, static_cast<size_t>(n_pairs) + 1, false, &d_ref_off)) return rc;
+    if (int rc = Stage(ctx, ctx->d_chunk_offsets, cur_offsets, static_cast<size_t>(n_pairs) + 1, false, &d_cur_off)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * static_cast<size_t>(n_ref ? n_ref : 1))) return rc;
+    int *d_ref_pair = static_cast<int *>(ctx->d_feat_pair.ptr);
+    if (n_ref > 0)
+        if (int rc = ftk::LaunchFeaturePairs(ctx, d_ref_off, n_pairs, n_ref, d_ref_pair)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (int rc = ftk::LaunchHammingPairs(ctx, d_ref, d_cur, words, n_ref, d_ref_pair, d_ref_off, d_cur_off, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx))
+        return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
 int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, const ftk_pyramid *ref, const ftk_pyramid *cur, int32_t n_pairs,
                             const int32_t *ref_image, const int32_t *cur_image, const int32_t *feat_offsets, const float *K, const float *p_c_in_ref,
                             const float *ref_uv, float *cur_uv, float *q_rc, float *p_rc, uint8_t *status, uint32_t flags) {

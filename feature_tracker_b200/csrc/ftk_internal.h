@@ -130,6 +130,9 @@ int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int image, con
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);
 int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
                         const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
+int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *d_cur, int words, int n_ref_total, const int *d_ref_pair,
+                       const int *d_ref_off, const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist,
+                       int *d_idx);
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
 // match_mutual.cu: mutual arg-max of a score matrix; cross-check filter
 int LaunchMutualScores(ftk_context *ctx, const float *d_scores, int n_ref, int n_cur, float min_score, int *d_idx);

@@ -362,6 +362,40 @@ __global__ void __launch_bounds__(128) NearbyKernel(Dist dist, int n_ref, const 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Many small matching problems in one launch (one frame pair each: a few hundred descriptors per side).  One warp per ref
+// descriptor; its lanes stride over the cur descriptors of the same pair, apply the reference's window gate when positions are
+// given (descriptor_matcher.h:108-111) and reduce (distance, j) lexicographically.  The d == 0 break (:119) cannot change an
+// integer-distance result: a later candidate never beats distance 0 at a lower index.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) HammingPairsKernel(const uint32_t *__restrict__ ref, const uint32_t *__restrict__ cur, int words, int n_ref_total,
+                                                          const int *__restrict__ ref_pair, const int *__restrict__ ref_off, const int *__restrict__ cur_off,
+                                                          const float2 *__restrict__ pred, const float2 *__restrict__ pos, float max_dcol, float max_drow,
+                                                          float max_dist, int *__restrict__ idx) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n_ref_total) return;
+    const int p = ref_pair[i];
+    const int c0 = cur_off[p], c1 = cur_off[p + 1];
+    (void)ref_off;
+    const uint32_t *r = ref + static_cast<size_t>(i) * words;
+    float2 pr = make_float2(0.0f, 0.0f);
+    if (pred) pr = pred[i];
+    unsigned long long best = kNoKey64;
+    for (int j = c0 + lane; j < c1; j += 32) {
+        if (pred) {
+            const float2 q = pos[j];
+            if (fabsf(__fsub_rn(pr.x, q.x)) > max_dcol || fabsf(__fsub_rn(pr.y, q.y)) > max_drow) continue;
+        }
+        const uint32_t *c = cur + static_cast<size_t>(j) * words;
+        unsigned d = 0;
+        for (int w = 0; w < words; ++w) d += __popc(__ldg(r + w) ^ __ldg(c + w));
+        const unsigned long long key = (static_cast<unsigned long long>(d) << 32) | static_cast<unsigned>(j - c0);
+        best = key < best ? key : best;
+    }
+    best = WarpMin64(best);
+    if (lane == 0 && best != kNoKey64 && static_cast<float>(static_cast<unsigned>(best >> 32)) < max_dist) idx[i] = static_cast<int>(best & 0xFFFFFFFFull);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Exact fp32 cosine force matching
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kCosThreads = 128;  // ref rows per CTA (one per thread)
@@ -528,6 +562,18 @@ int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const
         HammingFinalize64Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, max_dist, d_idx);
     }
     ctx->launches += 3;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+// d_pred / d_pos null: ForceMatch per pair; otherwise NearbyMatch per pair.  d_ref_pair [n_ref_total] = pair of every ref descriptor.
+int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *d_cur, int words, int n_ref_total, const int *d_ref_pair,
+                       const int *d_ref_off, const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist,
+                       int *d_idx) {
+    if (n_ref_total == 0 || words == 0) return FTK_OK;
+    HammingPairsKernel<<<Blocks(n_ref_total, 8), 256, 0, ctx->stream>>>(d_ref, d_cur, words, n_ref_total, d_ref_pair, d_ref_off, d_cur_off, d_pred, d_pos,
+                                                                       static_cast<float>(max_dcol), static_cast<float>(max_drow), max_dist, d_idx);
+    ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
 }

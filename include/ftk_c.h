@@ -249,6 +249,14 @@ int ftk_match_hamming_force(ftk_context *ctx, const uint32_t *ref, int32_t n_ref
 int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_ref, const uint32_t *cur, int32_t n_cur, int32_t words,
                              const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
                              uint32_t flags);
+/* Many independent ForceMatch / NearbyMatch problems in one call (one per frame pair, like the pair batches of ftk_klt_track): pair p
+ * matches ref descriptors ref_offsets[p] .. ref_offsets[p+1]-1 against cur descriptors cur_offsets[p] .. cur_offsets[p+1]-1 (offsets
+ * are HOST arrays of n_pairs + 1 entries starting at 0).  pred_uv == NULL: ForceMatch; otherwise NearbyMatch with pred_uv [n_ref_total][2]
+ * and cur_uv [n_cur_total][2].  idx [n_ref_total] is in/out like the single-pair calls; a match is the index INSIDE the pair's cur set.
+ * A pair without cur descriptors leaves its idx entries untouched (the reference returns false for it, descriptor_matcher.h:58). */
+int ftk_match_hamming_pairs(ftk_context *ctx, const uint32_t *ref, const uint32_t *cur, int32_t words, int32_t n_pairs, const int32_t *ref_offsets,
+                            const int32_t *cur_offsets, const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist,
+                            int32_t *idx, uint32_t flags);
 /* Float descriptors, row-major n x dim, distance 0.5 - 0.5 * cos(ref, cur). */
 int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist,
                            int32_t *idx, uint32_t flags);

@@ -425,6 +425,42 @@ def test_hamming_semantics(ctx, oracle):
     assert not ok  # descriptor_matcher.h:95
 
 
+@pytest.mark.parametrize("bits", [256, 96])
+def test_hamming_pairs_batch_vs_oracle(ctx, oracle, bits):
+    """ftk_match_hamming_pairs: many small Force / NearbyMatch problems in one launch equal the per-pair reference loop, including empty
+    pairs, duplicates (ties -> lowest index) and pre-filled index vectors."""
+    rng = np.random.default_rng(bits)
+    sizes = [(40, 50), (0, 30), (25, 0), (300, 280), (1, 1), (70, 33), (64, 64)]
+    refs, curs, preds, poss = [], [], [], []
+    for k, (nr, nc) in enumerate(sizes):
+        rb, cb, pred, pos, _ = S.make_brief_sets(max(nr, 1), max(nc, 1), seed=70 + k, bits=bits)
+        rb, cb, pred, pos = rb[:nr], cb[:nc], pred[:nr], pos[:nc]
+        if nc > 4:
+            cb[3] = cb[1]  # exact duplicates: the lower index must win
+        refs.append(rb), curs.append(cb), preds.append(pred), poss.append(pos)
+    ro = np.concatenate([[0], np.cumsum([len(r) for r in refs])]).astype(np.int32)
+    co = np.concatenate([[0], np.cumsum([len(c) for c in curs])]).astype(np.int32)
+    pack = lambda blocks: np.concatenate([ft.pack_brief(b) if len(b) else np.zeros((0, bits // 32), np.uint32) for b in blocks])
+    R, Cc = pack(refs), pack(curs)
+    P, Q = np.concatenate(preds), np.concatenate(poss)
+    m = brief_matcher(ctx, 60.0 if bits == 256 else 30.0, 45, 55)
+    prefill = rng.integers(-1, 5, ro[-1]).astype(np.int32)
+    for nearby in (False, True):
+        for pre in (None, prefill):
+            ok, idx = m.MatchPairs(R, ro, Cc, co, P if nearby else None, Q if nearby else None, index_pairs_in_cur=pre)
+            assert ok
+            for k, (nr, nc) in enumerate(sizes):
+                got = idx[ro[k]:ro[k + 1]]
+                start = None if pre is None else pre[ro[k]:ro[k + 1]]
+                if nc == 0 or nr == 0:  # the reference returns false and leaves the vector as it came
+                    exp = np.full(nr, -1, np.int32) if start is None else start
+                elif nearby:
+                    exp = oracle.match_brief_nearby(refs[k], curs[k], preds[k], poss[k], 45, 55, m.options().kMaxValidDescriptorDistance, idx=start)[1]
+                else:
+                    exp = oracle.match_brief_force(refs[k], curs[k], m.options().kMaxValidDescriptorDistance, idx=start)[1]
+                assert np.array_equal(got, exp), (bits, nearby, pre is not None, k)
+
+
 @pytest.mark.parametrize("n_ref,n_cur,win", [(500, 600, (50, 50)), (1500, 1400, (30, 45)), (200, 3000, (5, 80)), (300, 300, (1000, 1000)), (100, 120, (0, 0))])
 def test_hamming_nearby_vs_oracle(ctx, oracle, n_ref, n_cur, win):
     rb, cb, pred, pos, _ = S.make_brief_sets(n_ref, n_cur, seed=3 * n_ref + n_cur)
