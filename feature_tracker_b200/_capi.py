@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "ftk_track_image_pairs", "ftk_track_image_pairs_multi", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_hamming_pairs", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
     "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track", "ftk_dense_flow_params_default", "ftk_dense_flow_track",
-    "ftk_detector_params_default", "ftk_detect_features", "ftk_detect_features_batch", "ftk_detect_response", "ftk_brief_pattern_default", "ftk_describe_brief",
+    "ftk_detector_params_default", "ftk_detect_features", "ftk_detect_features_batch", "ftk_detect_response", "ftk_brief_pattern_default", "ftk_describe_brief", "ftk_describe_brief_batch",
 ]
 
 
@@ -120,6 +120,7 @@ def load_library():
         "ftk_detect_response": (C.c_int, [vp, P(DetectorParams), vp, i32, vp, u32]),
         "ftk_brief_pattern_default": (None, [i32, i32, u32, vp]),
         "ftk_describe_brief": (C.c_int, [vp, vp, i32, vp, i32, vp, i32, i32, vp, vp, u32]),
+        "ftk_describe_brief_batch": (C.c_int, [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, u32]),
         "ftk_direct_params_default": (None, [P(DirectParams)]),
         "ftk_direct_method_track": (C.c_int, [vp, P(DirectParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]),
         "ftk_match_mutual_scores": (C.c_int, [vp, vp, i32, i32, f32, vp, u32]),

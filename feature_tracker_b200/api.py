@@ -844,3 +844,19 @@ class BriefDescriptor:
                                       int(o.kHalfPatchSize), _ptr(desc) if len(uv) else None, _ptr(valid) if len(uv) else None, 0)
         ok = self.ctx.check(rc)
         return ok, desc, valid
+
+    def ComputeBatch(self, images, feature_lists, first=0):
+        """Descriptors of several images of a pyramid batch in one launch (ftk_describe_brief_batch): feature_lists[i] belongs to image
+        first + i.  Returns (ok, [descriptors ...], [valid ...])."""
+        o = self._options
+        lists = [np.ascontiguousarray(f, np.float32).reshape(-1, 2) for f in feature_lists]
+        offsets = np.concatenate([[0], np.cumsum([len(f) for f in lists])]).astype(np.int32)
+        uv = np.concatenate(lists) if lists else np.zeros((0, 2), np.float32)
+        pattern = self.pattern()
+        n_bits = len(pattern)
+        desc = np.zeros((len(uv), max(n_bits // 32, 1)), np.uint32)
+        valid = np.zeros(len(uv), np.uint8)
+        rc = lib().ftk_describe_brief_batch(self.ctx._h, images._h, int(first), len(lists), _ptr(offsets), _ptr(uv) if len(uv) else None, _ptr(pattern), n_bits,
+                                            int(o.kHalfPatchSize), _ptr(desc) if len(uv) else None, _ptr(valid) if len(uv) else None, 0)
+        ok = self.ctx.check(rc)
+        return ok, [desc[offsets[i]:offsets[i + 1]] for i in range(len(lists))], [valid[offsets[i]:offsets[i + 1]] for i in range(len(lists))]

@@ -829,8 +829,9 @@ int ftk_detect_features_batch(ftk_context *ctx, const ftk_detector_params *param
     return DetectImages(ctx, params, pyr, first_image, n_images, nullptr, 0, needed, out_uv, out_response, n_out, flags);
 }
 
-int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
-                       int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags) {
+// Shared body of ftk_describe_brief / ftk_describe_brief_batch; feat_offsets (HOST, count + 1 entries) null = one image.
+static int DescribeImages(ftk_context *ctx, const ftk_pyramid *pyr, int32_t first, int32_t count, const int32_t *feat_offsets, const float *uv, int32_t n,
+                          const int8_t *pattern, int32_t n_bits, int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags) {
     if (!ctx || !pyr || !pattern || n < 0 || (n > 0 && (!uv || !desc))) return FTK_ERR_INVALID_ARGUMENT;
     if (n_bits <= 0 || n_bits % 32 != 0 || n_bits > 1024) return SetError(ctx, FTK_ERR_UNSUPPORTED, "BRIEF length %d is not a multiple of 32 in 32..1024", n_bits);
     if (half_patch < 0 || half_patch > 127) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "BRIEF half patch %d", half_patch);
@@ -843,6 +844,14 @@ int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, 
     if (int rc = Stage(ctx, ctx->d_det_pattern, reinterpret_cast<const char4 *>(pattern), static_cast<size_t>(n_bits), false, &d_pattern)) return rc;
     const float2 *d_uv = nullptr;
     if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(uv), static_cast<size_t>(n), on_device, &d_uv)) return rc;
+    int *d_feat_image = nullptr;
+    if (feat_offsets && n > 0) {
+        const int32_t *d_off = nullptr;
+        if (int rc = Stage(ctx, ctx->d_offsets, feat_offsets, static_cast<size_t>(count) + 1, false, &d_off)) return rc;
+        if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * static_cast<size_t>(n))) return rc;
+        d_feat_image = static_cast<int *>(ctx->d_feat_pair.ptr);
+        if (int rc = ftk::LaunchFeaturePairs(ctx, d_off, count, n, d_feat_image)) return rc;
+    }
     uint32_t *d_desc = desc;
     uint8_t *d_valid = valid;
     if (!on_device) {
@@ -851,13 +860,26 @@ int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, 
         d_desc = static_cast<uint32_t *>(ctx->d_desc_ref.ptr);
         d_valid = static_cast<uint8_t *>(ctx->d_status.ptr);
     }
-    if (int rc = ftk::LaunchDescribeBrief(ctx, pyr->view, image, d_uv, n, d_pattern, n_bits, half_patch, d_desc, d_valid)) return rc;
+    if (int rc = ftk::LaunchDescribeBrief(ctx, pyr->view, first, count, d_feat_image, d_uv, n, d_pattern, n_bits, half_patch, d_desc, d_valid)) return rc;
     if (!on_device && n > 0) {
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(desc, d_desc, sizeof(uint32_t) * static_cast<size_t>(n) * words, cudaMemcpyDeviceToHost, ctx->stream));
         if (valid) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(valid, d_valid, static_cast<size_t>(n), cudaMemcpyDeviceToHost, ctx->stream));
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return FTK_OK;
+}
+
+int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
+                       int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags) {
+    return DescribeImages(ctx, pyr, image, 1, nullptr, uv, n, pattern, n_bits, half_patch, desc, valid, flags);
+}
+
+int ftk_describe_brief_batch(ftk_context *ctx, const ftk_pyramid *pyr, int32_t first_image, int32_t n_images, const int32_t *feat_offsets, const float *uv,
+                             const int8_t *pattern, int32_t n_bits, int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags) {
+    if (!feat_offsets || n_images < 1) return FTK_ERR_INVALID_ARGUMENT;
+    for (int32_t i = 0; i < n_images; ++i)
+        if (feat_offsets[i + 1] < feat_offsets[i] || feat_offsets[0] != 0) return ctx ? SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feature offsets must start at 0 and not decrease") : FTK_ERR_INVALID_ARGUMENT;
+    return DescribeImages(ctx, pyr, first_image, n_images, feat_offsets, uv, feat_offsets[n_images], pattern, n_bits, half_patch, desc, valid, flags);
 }
 
 int ftk_match_mutual_scores(ftk_context *ctx, const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx, uint32_t flags) {

@@ -353,11 +353,13 @@ __global__ void EmitKernel(const Key *__restrict__ sorted, const unsigned *__res
     if (out_response) out_response[static_cast<size_t>(z) * needed + i] = response[static_cast<size_t>(z) * rows * cols + p];
 }
 
-__global__ void __launch_bounds__(256) BriefKernel(const uint8_t *__restrict__ img, int rows, int cols, int pitch, const float2 *__restrict__ uv, int n,
-                                                   const char4 *__restrict__ pattern, int words, int half, uint32_t *__restrict__ desc,
-                                                   uint8_t *__restrict__ valid) {
+// feat_image (may be null: every feature belongs to the plane `img`) = image of the batch, relative to `img`, of every feature.
+__global__ void __launch_bounds__(256) BriefKernel(const uint8_t *__restrict__ img, long long image_stride, const int *__restrict__ feat_image, int rows,
+                                                   int cols, int pitch, const float2 *__restrict__ uv, int n, const char4 *__restrict__ pattern, int words,
+                                                   int half, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (f >= n) return;
+    if (feat_image) img += feat_image[f] * image_stride;
     const float2 p = uv[f];
     const bool ok = p.x >= static_cast<float>(half) && p.y >= static_cast<float>(half) && p.x < static_cast<float>(cols - half) &&
                     p.y < static_cast<float>(rows - half);
@@ -515,12 +517,15 @@ int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const P
     return FTK_OK;
 }
 
-int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int image, const float2 *d_uv, int n, const char4 *d_pattern, int n_bits,
-                        int half_patch, uint32_t *d_desc, uint8_t *d_valid) {
-    if (image < 0 || image >= pyr.n_images) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "image %d outside the pyramid batch", image);
+// d_feat_image null: all n features lie on image `first`; otherwise feature f lies on image first + d_feat_image[f].
+int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int first, int count, const int *d_feat_image, const float2 *d_uv, int n,
+                        const char4 *d_pattern, int n_bits, int half_patch, uint32_t *d_desc, uint8_t *d_valid) {
+    if (first < 0 || count < 1 || first + count > pyr.n_images)
+        return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "images %d..%d outside the pyramid batch", first, first + count - 1);
     if (n == 0) return FTK_OK;
-    const uint8_t *img = pyr.base[0] + image * pyr.image_stride[0];
-    BriefKernel<<<(n + 7) / 8, 256, 0, ctx->stream>>>(img, pyr.rows[0], pyr.cols[0], pyr.pitch[0], d_uv, n, d_pattern, n_bits / 32, half_patch, d_desc, d_valid);
+    const uint8_t *img = pyr.base[0] + first * pyr.image_stride[0];
+    BriefKernel<<<(n + 7) / 8, 256, 0, ctx->stream>>>(img, pyr.image_stride[0], d_feat_image, pyr.rows[0], pyr.cols[0], pyr.pitch[0], d_uv, n, d_pattern,
+                                                     n_bits / 32, half_patch, d_desc, d_valid);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;

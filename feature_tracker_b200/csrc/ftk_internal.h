@@ -123,8 +123,8 @@ int LaunchDenseFlow(ftk_context *ctx, const ftk_dense_flow_params &p, const Pyra
 int LaunchDetectResponse(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int image, float *d_response);
 int LaunchDetectFeatures(ftk_context *ctx, const ftk_detector_params &p, const PyramidView &pyr, int first, int count, const float2 *d_existing,
                          int n_existing, int needed, float2 *d_out_uv, float *d_out_response, int *d_n_out);
-int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int image, const float2 *d_uv, int n, const char4 *d_pattern, int n_bits,
-                        int half_patch, uint32_t *d_desc, uint8_t *d_valid);
+int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int first, int count, const int *d_feat_image, const float2 *d_uv, int n,
+                        const char4 *d_pattern, int n_bits, int half_patch, uint32_t *d_desc, uint8_t *d_valid);
 
 // match.cu
 int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);

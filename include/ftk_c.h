@@ -238,6 +238,11 @@ void ftk_brief_pattern_default(int32_t n_bits, int32_t half_patch, uint32_t seed
 int ftk_describe_brief(ftk_context *ctx, const ftk_pyramid *pyr, int32_t image, const float *uv, int32_t n, const int8_t *pattern, int32_t n_bits,
                        int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags);
 
+/* The same for images first_image .. first_image + n_images - 1 in one launch: the features of image first_image + i are
+ * uv[feat_offsets[i] .. feat_offsets[i+1]-1] (feat_offsets: HOST, n_images + 1 entries starting at 0); desc / valid are indexed like uv. */
+int ftk_describe_brief_batch(ftk_context *ctx, const ftk_pyramid *pyr, int32_t first_image, int32_t n_images, const int32_t *feat_offsets, const float *uv,
+                             const int8_t *pattern, int32_t n_bits, int32_t half_patch, uint32_t *desc, uint8_t *valid, uint32_t flags);
+
 /* ---- descriptor matching (replaces DescriptorMatcher<T>::ForceMatch / NearbyMatch,
  *      src/descriptor_matcher/descriptor_matcher.h:55-79,90-124, with the ComputeDistance bodies of
  *      test/test_descriptor_matcher_brief.cpp:33-45 and test/test_descriptor_matcher_superpoint.cpp:32-34) --------

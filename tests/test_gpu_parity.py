@@ -958,6 +958,41 @@ def test_brief_vs_oracle(ctx, oracle):
         ft.BriefDescriptor(ctx, pattern=np.full((32, 4), 9, np.int8)).Compute(pyr, uv[:4])
 
 
+def test_front_end_batched_detect_describe_match(ctx, oracle):
+    """The batched front end -- ftk_detect_features_batch -> ftk_describe_brief_batch -> ftk_match_hamming_pairs: a handful of launches
+    for many frame pairs -- equals the per-image / per-pair oracle calls stage by stage."""
+    rows, cols, n_pairs = 160, 208, 5
+    pairs = [S.make_pair(rows, cols, 5, pair_id=500 + p) for p in range(n_pairs)]
+    imgs = np.stack([pr[0] for pr in pairs] + [pr[1] for pr in pairs])  # refs then curs
+    imgs[2] = 200  # a frame without corners: an empty ref set
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, 3, 2 * n_pairs)
+    pyr.SetRawImages(imgs)
+    pyr.CreateImagePyramid()
+    det = make_detector(ctx, "harris", 1, 2e4, 9)
+    ok, feats, _ = det.DetectGoodFeaturesBatch(pyr, 120)
+    prm = po.make_detector_params("harris", 1, 0.04, 2e4, 9)
+    assert ok and all(np.array_equal(feats[i], oracle.detect_features(prm, imgs[i], 120)[1]) for i in range(2 * n_pairs))
+    brief = ft.BriefDescriptor(ctx)
+    ok, descs, valids = brief.ComputeBatch(pyr, feats)
+    assert ok
+    unpack = lambda d: np.unpackbits(np.ascontiguousarray(d).view(np.uint8).reshape(len(d), -1), axis=1, bitorder="little") if len(d) else np.zeros((0, 256), np.uint8)
+    for i in range(2 * n_pairs):
+        _, d_e, v_e = oracle.describe_brief(imgs[i], feats[i], brief.pattern(), 8)
+        assert np.array_equal(descs[i], d_e[:len(feats[i])]) and np.array_equal(valids[i], v_e[:len(feats[i])]), i
+    ro = np.concatenate([[0], np.cumsum([len(feats[p]) for p in range(n_pairs)])]).astype(np.int32)
+    co = np.concatenate([[0], np.cumsum([len(feats[n_pairs + p]) for p in range(n_pairs)])]).astype(np.int32)
+    m = brief_matcher(ctx, 70.0, 30, 30)
+    ok, idx = m.MatchPairs(np.concatenate(descs[:n_pairs]), ro, np.concatenate(descs[n_pairs:]), co, np.concatenate(feats[:n_pairs]), np.concatenate(feats[n_pairs:]))
+    assert ok and (idx >= 0).sum() > 50
+    for p in range(n_pairs):
+        got = idx[ro[p]:ro[p + 1]]
+        if len(feats[p]) == 0 or len(feats[n_pairs + p]) == 0:
+            assert (got == -1).all()
+            continue
+        exp = oracle.match_brief_nearby(unpack(descs[p]), unpack(descs[n_pairs + p]), feats[p], feats[n_pairs + p], 30, 30, 70.0)[1]
+        assert np.array_equal(got, exp), p
+
+
 def test_front_end_detect_describe_match_track(ctx, oracle, euroc_golden):
     """The reference demo's flow (test_descriptor_matcher_brief.cpp:57-95) on one device pyramid batch, each stage against the oracle
     fed with the previous stage's oracle output: detect in both frames -> BRIEF -> NearbyMatch, then KLT from the same pyramids."""
