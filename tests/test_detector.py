@@ -146,3 +146,17 @@ def test_detected_features_match_across_the_euroc_pair(oracle, euroc_golden):
     assert matched.sum() >= 100, matched.sum()
     shift = g["cur_harris_uv"][idx[matched]] - g["ref_harris_uv"][matched]
     assert np.abs(shift - np.median(shift, axis=0)).max(axis=1).__lt__(12).mean() > 0.6  # the scene has parallax: the shift is not one vector
+
+
+def test_product_pattern_and_defaults_match_the_checker(oracle):
+    """Host-only entry points of the product library (no GPU needed): the default BRIEF pair list is the checker's, the detector
+    defaults are the values the reference's demo sets (test/test_descriptor_matcher_brief.cpp:60-61)."""
+    import ctypes as C
+    import feature_tracker_b200 as ft
+    from feature_tracker_b200 import _capi
+    from feature_tracker_b200.api import lib
+    for n_bits, half, seed in ((256, 8, 0), (128, 4, 77), (32, 15, 1), (1024, 20, 9), (64, 0, 5), (96, 1, 0xFFFFFFFF)):
+        assert np.array_equal(ft.brief_pattern(n_bits, half, seed), oracle.brief_pattern(n_bits, half, seed)), (n_bits, half, seed)
+    prm = _capi.DetectorParams()
+    lib().ftk_detector_params_default(C.byref(prm))
+    assert (prm.kind, prm.half_patch, prm.min_distance) == (0, 1, 20) and prm.min_response == 40.0 and abs(prm.harris_k - 0.04) < 1e-7
