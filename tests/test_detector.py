@@ -160,3 +160,26 @@ def test_product_pattern_and_defaults_match_the_checker(oracle):
     prm = _capi.DetectorParams()
     lib().ftk_detector_params_default(C.byref(prm))
     assert (prm.kind, prm.half_patch, prm.min_distance) == (0, 1, 20) and prm.min_response == 40.0 and abs(prm.harris_k - 0.04) < 1e-7
+
+
+def test_selection_is_maximal_when_not_capped(oracle):
+    """Size-independent property at the full image size: with more features wanted than exist, every candidate that was not taken has a
+    taken feature of higher priority inside its window, and no two taken features block each other."""
+    img = S.make_image(480, 752, seed=91)
+    thr, dist = 3e4, 15
+    prm = po.make_detector_params("harris", 1, 0.04, thr, dist)
+    ok, uv, resp = oracle.detect_features(prm, img, 100000)
+    _, rmap = oracle.detect_response(prm, img)
+    assert ok and 100 < len(uv) < 100000
+    taken = np.zeros(img.shape, bool)
+    cols_i, rows_i = uv[:, 0].astype(int), uv[:, 1].astype(int)
+    taken[rows_i, cols_i] = True
+    d = np.abs(uv[:, None, :] - uv[None, :, :]).max(axis=2) + np.eye(len(uv)) * 1e9
+    assert d.min() >= dist
+    # best taken response within the window of every pixel (dilation by brute force over the taken list)
+    best = np.full(img.shape, -np.inf, np.float32)
+    for r, c, v in zip(rows_i, cols_i, resp):
+        ra, rb, ca, cb = max(0, r - dist + 1), min(479, r + dist - 1), max(0, c - dist + 1), min(751, c + dist - 1)
+        np.maximum(best[ra:rb + 1, ca:cb + 1], v, out=best[ra:rb + 1, ca:cb + 1])
+    cand = (rmap >= np.float32(thr)) & ~taken
+    assert (best[cand] >= rmap[cand]).all()
