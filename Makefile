@@ -5,7 +5,7 @@ OUT := feature_tracker_b200/libftk_b200.so
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: the KLT / matching numerics reproduce the reference's un-fused fp32 arithmetic bit for bit.
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Iinclude -I$(CSRC) --expt-relaxed-constexpr
-SRCS := $(CSRC)/api.cu $(CSRC)/pyramid.cu $(CSRC)/klt.cu $(CSRC)/klt_basic_fastpath.cu $(CSRC)/klt_basic_pooled.cu $(CSRC)/direct_method.cu $(CSRC)/dense_flow.cu $(CSRC)/detect.cu $(CSRC)/match.cu $(CSRC)/match_mutual.cu $(CSRC)/match_cosine_tc.cu
+SRCS := $(CSRC)/api.cu $(CSRC)/pyramid.cu $(CSRC)/klt.cu $(CSRC)/klt_basic_fastpath.cu $(CSRC)/direct_method.cu $(CSRC)/dense_flow.cu $(CSRC)/detect.cu $(CSRC)/match.cu $(CSRC)/match_mutual.cu $(CSRC)/match_cosine_tc.cu
 OBJS := $(SRCS:.cu=.o)
 HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/ftk_c.h
 

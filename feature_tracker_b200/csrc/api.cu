@@ -157,8 +157,6 @@ int ftk_create(int device, ftk_context **out) {
     {
         const char *e = getenv("FTK_DISABLE_FASTPATH");
         ctx->use_fast_paths = !(e && e[0] == '1');
-        const char *e2 = getenv("FTK_ENABLE_POOLED");
-        ctx->use_pooled = e2 && e2[0] == '1';
     }
     DeviceGuard guard(device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -177,13 +175,14 @@ void ftk_destroy(ftk_context *ctx) {
                         &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < ftk_context::kStageBuffers; ++b) {
         if (ctx->stage_pyr[b]) {
             if (ctx->stage_pyr[b]->storage) cudaFree(ctx->stage_pyr[b]->storage);
             delete ctx->stage_pyr[b];
         }
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
         if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
+        if (ctx->chunk_stream[b]) cudaStreamDestroy(ctx->chunk_stream[b]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
@@ -339,9 +338,25 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
     const int n_features = h_offsets[n_pairs];
     // optical_flow.cpp:8: RETURN_FALSE_IF(ref_pixel_uv.empty())
     if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");
-    if (!on_device) {
+    {
+        // pair -> image maps index device memory inside the kernels: validated on the host for device callers too (two small copies
+        // next to the feat_offsets one above)
+        std::vector<int32_t> h_ri, h_ci;
+        if (on_device) {
+            if (ref_image) {
+                h_ri.resize(n_pairs);
+                FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_ri.data(), ref_image, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (cur_image) {
+                h_ci.resize(n_pairs);
+                FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_ci.data(), cur_image, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            if (ref_image || cur_image) FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        const int32_t *ri_map = on_device ? (ref_image ? h_ri.data() : nullptr) : ref_image;
+        const int32_t *ci_map = on_device ? (cur_image ? h_ci.data() : nullptr) : cur_image;
         for (int p = 0; p < n_pairs; ++p) {
-            const int ri = ref_image ? ref_image[p] : p, ci = cur_image ? cur_image[p] : p;
+            const int ri = ri_map ? ri_map[p] : p, ci = ci_map ? ci_map[p] : p;
             if (ri < 0 || ri >= ref->view.n_images || ci < 0 || ci >= cur->view.n_images)
                 return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pair %d references image %d/%d outside the pyramid batches", p, ri, ci);
         }
@@ -400,55 +415,57 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
     return FTK_OK;
 }
 
-// The chunked two-stream pipeline behind ftk_track_image_pairs (cur_images != nullptr: pair p = ref_images[p] -> cur_images[p])
-// and ftk_track_image_sequence (cur_images == nullptr: ref_images holds n_pairs + 1 frames, pair p = frame p -> frame p + 1).
+// The chunked pipeline behind ftk_track_image_pairs (cur_images != nullptr: pair p = ref_images[p] -> cur_images[p]) and
+// ftk_track_image_sequence (cur_images == nullptr: ref_images holds n_pairs + 1 frames, pair p = frame p -> frame p + 1).
 // n_trackers parameter sets run on every chunk while its images are resident: tracker k reads / writes cur_uv + k * 2 * n_features and
 // status + k * n_features, exactly as n_trackers separate calls would, but the images cross PCIe once.
-static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
-                                int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
-                                float *cur_uv, uint8_t *status, uint32_t flags) {
+//
+// Streams: one copy stream carries every host-to-device byte (a chunk's features, then its images); kStageBuffers staging pyramids
+// rotate, each with its own compute stream, so the tail of chunk c's kernels overlaps the head of chunk c + 1's (different streams)
+// and chunk c's results travel back (device-to-host engine) while later chunks are uploaded and computed.  Nothing is copied up
+// front and nothing is left for the end but the last chunk's results.
+static int TrackImagesPipelinedBody(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
+                                    int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
+                                    float *cur_uv, uint8_t *status, uint32_t flags, bool any_fb) {
     const bool sequence = cur_images == nullptr;
-    if (!ctx || !params || n_trackers < 1 || !ref_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
-    if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
-    if (flags & (FTK_FLAG_DEVICE_POINTERS | FTK_FLAG_SINGLE_LEVEL)) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "host images, multi-level only");
-    bool any_fb = false;
-    for (int k = 0; k < n_trackers; ++k) {
-        if (params[k].variant < 0 || params[k].variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params[k].variant);
-        any_fb = any_fb || params[k].forward_backward_max_error > 0.0f;
-    }
-    if (feat_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
-    for (int p = 0; p < n_pairs; ++p)
-        if (feat_offsets[p + 1] < feat_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
     const int n_features = feat_offsets[n_pairs];
-    if (n_features == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");  // optical_flow.cpp:8
     const size_t n_all = static_cast<size_t>(n_trackers) * n_features;
-    DeviceGuard guard(ctx->device);
+    constexpr int kB = ftk_context::kStageBuffers;
 
-    // chunking: about 8 chunks per call, double-buffered staging pyramids (2 * chunk_pairs images each: refs then curs; a
-    // sequence chunk uses the first chunk_pairs + 1 of them and re-uploads the frame it shares with the previous chunk)
-    const int chunk_pairs = n_pairs < 16 ? n_pairs : (n_pairs + 7) / 8;
+    // chunking: ~24 chunks per call (small enough that filling / draining the pipeline costs a few percent, large enough that a
+    // chunk's kernels still fill the GPU for several waves)
+    int chunk_pairs = (n_pairs + 23) / 24;
+    if (chunk_pairs < 8) chunk_pairs = n_pairs < 8 ? n_pairs : 8;
     const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
     if (!ctx->copy_stream) {
         FTK_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kB; ++b) {
+            FTK_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->chunk_stream[b], cudaStreamNonBlocking));
             FTK_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
             FTK_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming));
         }
     }
+    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // earlier asynchronous calls on the context may still use the scratch buffers
     if (ctx->stage_rows != rows || ctx->stage_cols != cols || ctx->stage_levels != levels || ctx->stage_pairs < chunk_pairs) {
-        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < kB; ++b) {
             if (ctx->stage_pyr[b]) ftk_pyramid_destroy(ctx, ctx->stage_pyr[b]);
             ctx->stage_pyr[b] = nullptr;
-            if (int rc = ftk_pyramid_create(ctx, rows, cols, levels, 2 * chunk_pairs, &ctx->stage_pyr[b])) return rc;
+        }
+        ctx->stage_rows = ctx->stage_cols = ctx->stage_levels = ctx->stage_pairs = 0;
+        for (int b = 0; b < kB; ++b) {
+            if (int rc = ftk_pyramid_create(ctx, rows, cols, levels, 2 * chunk_pairs, &ctx->stage_pyr[b])) {
+                for (int q = 0; q < kB; ++q) {  // all or nothing: a later call must not find half of the staging set
+                    if (ctx->stage_pyr[q]) ftk_pyramid_destroy(ctx, ctx->stage_pyr[q]);
+                    ctx->stage_pyr[q] = nullptr;
+                }
+                return rc;
+            }
         }
         ctx->stage_rows = rows, ctx->stage_cols = cols, ctx->stage_levels = levels, ctx->stage_pairs = chunk_pairs;
         FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));  // the pyramids' memset
     }
     const int stage_pairs = ctx->stage_pairs;
 
-    // features up front (small), chunk-local offset tables, the "cur image = stage_pairs + p" map
     if (int rc = EnsureDevice(ctx, ctx->d_ref_uv, sizeof(float2) * n_features)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_cur_uv, sizeof(float2) * n_all)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_status, n_all)) return rc;
@@ -457,6 +474,7 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
         if (int rc = EnsureDevice(ctx, ctx->d_back_uv, sizeof(float2) * n_all)) return rc;
         if (int rc = EnsureDevice(ctx, ctx->d_back_status, n_all)) return rc;
     }
+    // chunk-local offset tables and the "cur image = stage_pairs + p" map (small; first thing on the copy stream)
     std::vector<int32_t> h_offsets;
     h_offsets.reserve(n_pairs + n_chunks);
     std::vector<int> chunk_table_start(n_chunks);
@@ -470,23 +488,30 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
     if (int rc = EnsureDevice(ctx, ctx->d_chunk_offsets, sizeof(int32_t) * h_offsets.size())) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_chunk_curmap, sizeof(int32_t) * h_curmap.size())) return rc;
     const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);
-    cudaStream_t cs = ctx->copy_stream, ks = ctx->stream;
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_ref_uv.ptr, ref_uv, sizeof(float2) * n_features, cudaMemcpyHostToDevice, ks));
-    if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_cur_uv.ptr, cur_uv, sizeof(float2) * n_all, cudaMemcpyHostToDevice, ks));
-    if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_status.ptr, status, n_all, cudaMemcpyHostToDevice, ks));
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_offsets.ptr, h_offsets.data(), sizeof(int32_t) * h_offsets.size(), cudaMemcpyHostToDevice, ks));
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_curmap.ptr, h_curmap.data(), sizeof(int32_t) * h_curmap.size(), cudaMemcpyHostToDevice, ks));
-    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));  // the host vectors above go out of scope; the copy stream may start
+    cudaStream_t cs = ctx->copy_stream;
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_offsets.ptr, h_offsets.data(), sizeof(int32_t) * h_offsets.size(), cudaMemcpyHostToDevice, cs));
+    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->d_chunk_curmap.ptr, h_curmap.data(), sizeof(int32_t) * h_curmap.size(), cudaMemcpyHostToDevice, cs));
 
     const size_t plane = static_cast<size_t>(rows) * cols;
+    float2 *d_ref_uv = static_cast<float2 *>(ctx->d_ref_uv.ptr), *d_cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr);
+    uint8_t *d_status = static_cast<uint8_t *>(ctx->d_status.ptr);
     for (int c = 0; c < n_chunks; ++c) {
-        const int b = c & 1;
+        const int b = c % kB;
         const int p_lo = c * chunk_pairs, p_hi = p_lo + chunk_pairs < n_pairs ? p_lo + chunk_pairs : n_pairs;
         const int np = p_hi - p_lo;
+        const int f_lo = feat_offsets[p_lo], f_hi = feat_offsets[p_hi], nf = f_hi - f_lo;
         ftk_pyramid *pyr = ctx->stage_pyr[b];
         const ftk::PyramidView &v = pyr->view;
-        // ---- copy stream: images of this chunk into staging buffer b (after its previous user finished computing)
-        if (c >= 2) FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(cs, ctx->ev_computed[b], 0));
+        // ---- copy stream: this chunk's features and images into staging buffer b (after its previous user finished computing)
+        if (c >= kB) FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(cs, ctx->ev_computed[b], 0));
+        if (nf > 0) {
+            FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_ref_uv + f_lo, ref_uv + 2 * static_cast<size_t>(f_lo), sizeof(float2) * nf, cudaMemcpyHostToDevice, cs));
+            for (int k = 0; k < n_trackers; ++k) {
+                const size_t base = static_cast<size_t>(k) * n_features + f_lo;
+                if (has_prediction) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cur_uv + base, cur_uv + 2 * base, sizeof(float2) * nf, cudaMemcpyHostToDevice, cs));
+                if (has_status) FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d_status + base, status + base, nf, cudaMemcpyHostToDevice, cs));
+            }
+        }
         uint8_t *dst_ref = const_cast<uint8_t *>(v.base[0]);
         uint8_t *dst_cur = dst_ref + static_cast<size_t>(stage_pairs) * v.image_stride[0];
         const int n_first = sequence ? np + 1 : np;  // images copied into staging slots [0, n_first)
@@ -503,16 +528,17 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
                                                       cudaMemcpyHostToDevice, cs));
         }
         FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
-        // ---- compute stream: pyramids of the 2 * np images, then the chunk's features
+        // ---- compute stream of buffer b: pyramids of the chunk's images, its features, its results back to the host
+        cudaStream_t ks = ctx->chunk_stream[b];
+        ctx->stream = ks;  // every Launch* helper issues on ctx->stream (restored by the caller, also on error)
         FTK_CUDA_CHECK(ctx, cudaStreamWaitEvent(ks, ctx->ev_copied[b], 0));
         if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, 0, n_first)) return rc;
         if (!sequence)
             if (int rc = ftk::LaunchPyramidBuild(ctx, pyr, stage_pairs, np)) return rc;
-        const int f_lo = feat_offsets[p_lo], f_hi = feat_offsets[p_hi];
-        if (f_hi > f_lo) {
+        if (nf > 0) {
             int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr) + f_lo;
             const int *chunk_offsets = static_cast<const int *>(ctx->d_chunk_offsets.ptr) + chunk_table_start[c];
-            if (int rc = ftk::LaunchFeaturePairs(ctx, chunk_offsets, np, f_hi - f_lo, d_feat_pair)) return rc;
+            if (int rc = ftk::LaunchFeaturePairs(ctx, chunk_offsets, np, nf, d_feat_pair)) return rc;
             for (int k = 0; k < n_trackers; ++k) {
                 const size_t base = static_cast<size_t>(k) * n_features + f_lo;
                 ftk::KltLaunch a{};
@@ -520,25 +546,60 @@ static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, 
                 a.ref = v;
                 a.cur = v;
                 a.n_pairs = np;
-                a.n_features = f_hi - f_lo;
+                a.n_features = nf;
                 a.has_prediction = has_prediction ? 1 : 0;
                 a.has_status = has_status ? 1 : 0;
                 a.single_level = 0;
-                a.ref_uv = static_cast<const float2 *>(ctx->d_ref_uv.ptr) + f_lo;
-                a.cur_uv = static_cast<float2 *>(ctx->d_cur_uv.ptr) + base;
-                a.status = static_cast<uint8_t *>(ctx->d_status.ptr) + base;
+                a.ref_uv = d_ref_uv + f_lo;
+                a.cur_uv = d_cur_uv + base;
+                a.status = d_status + base;
                 a.feat_offsets = chunk_offsets;
                 a.ref_image = nullptr;  // image p of the staging batch
                 a.cur_image = static_cast<const int *>(ctx->d_chunk_curmap.ptr);
                 a.feat_pair = d_feat_pair;
                 if (int rc = ftk::LaunchKltTrackChecked(ctx, a, base)) return rc;
+                FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv + 2 * base, d_cur_uv + base, sizeof(float2) * nf, cudaMemcpyDeviceToHost, ks));
+                FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status + base, d_status + base, nf, cudaMemcpyDeviceToHost, ks));
             }
         }
         FTK_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_computed[b], ks));
     }
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(cur_uv, ctx->d_cur_uv.ptr, sizeof(float2) * n_all, cudaMemcpyDeviceToHost, ks));
-    FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(status, ctx->d_status.ptr, n_all, cudaMemcpyDeviceToHost, ks));
-    FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ks));
+    return FTK_OK;
+}
+
+static int TrackImagesPipelined(ftk_context *ctx, const ftk_klt_params *params, int32_t n_trackers, int32_t rows, int32_t cols, int32_t levels,
+                                int32_t n_pairs, const uint8_t *ref_images, const uint8_t *cur_images, const int32_t *feat_offsets, const float *ref_uv,
+                                float *cur_uv, uint8_t *status, uint32_t flags) {
+    if (!ctx || !params || n_trackers < 1 || !ref_images || !feat_offsets || !ref_uv || !cur_uv || !status) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs <= 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no frame pairs");
+    if (flags & (FTK_FLAG_DEVICE_POINTERS | FTK_FLAG_SINGLE_LEVEL)) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "host images, multi-level only");
+    bool any_fb = false;
+    for (int k = 0; k < n_trackers; ++k) {
+        if (params[k].variant < 0 || params[k].variant > 2) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "unknown tracker variant %d", params[k].variant);
+        any_fb = any_fb || params[k].forward_backward_max_error > 0.0f;
+    }
+    if (feat_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
+    for (int p = 0; p < n_pairs; ++p)
+        if (feat_offsets[p + 1] < feat_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
+    if (feat_offsets[n_pairs] == 0) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "no features");  // optical_flow.cpp:8
+    DeviceGuard guard(ctx->device);
+    cudaStream_t user_stream = ctx->stream;
+    const int rc = TrackImagesPipelinedBody(ctx, params, n_trackers, rows, cols, levels, n_pairs, ref_images, cur_images, feat_offsets, ref_uv, cur_uv, status,
+                                            flags, any_fb);
+    ctx->stream = user_stream;
+    // Success or not, nothing of this call may stay in flight: the copies read and write the caller's host arrays.
+    cudaError_t err = cudaSuccess;
+    if (ctx->copy_stream) {
+        cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+        if (e != cudaSuccess) err = e;
+        for (int b = 0; b < ftk_context::kStageBuffers; ++b) {
+            if (!ctx->chunk_stream[b]) continue;
+            e = cudaStreamSynchronize(ctx->chunk_stream[b]);
+            if (e != cudaSuccess) err = e;
+        }
+    }
+    if (rc != FTK_OK) return rc;
+    if (err != cudaSuccess) return SetError(ctx, FTK_ERR_CUDA, "pipelined tracking failed: %s", cudaGetErrorString(err));
     return FTK_OK;
 }
 
@@ -683,14 +744,24 @@ int ftk_direct_method_track(ftk_context *ctx, const ftk_direct_params *params, c
         memcpy(h_offsets.data(), feat_offsets, sizeof(int32_t) * (n_pairs + 1));
     }
     if (h_offsets[0] != 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets[0] must be 0");
+    std::vector<int32_t> h_ri, h_ci;  // the pair -> image maps index device memory inside the kernel: validated for device callers too
+    if (on_device && ref_image) {
+        h_ri.resize(n_pairs);
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_ri.data(), ref_image, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (on_device && cur_image) {
+        h_ci.resize(n_pairs);
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h_ci.data(), cur_image, sizeof(int32_t) * n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (on_device && (ref_image || cur_image)) FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const int32_t *ri_map = on_device ? (ref_image ? h_ri.data() : nullptr) : ref_image;
+    const int32_t *ci_map = on_device ? (cur_image ? h_ci.data() : nullptr) : cur_image;
     for (int p = 0; p < n_pairs; ++p) {
         if (h_offsets[p + 1] < h_offsets[p]) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "feat_offsets must be non-decreasing");
         if (h_offsets[p + 1] == h_offsets[p]) return SetError(ctx, FTK_ERR_EMPTY_INPUT, "pair %d has no features", p);  // :44
-        if (!on_device) {
-            const int ri = ref_image ? ref_image[p] : p, ci = cur_image ? cur_image[p] : p;
-            if (ri < 0 || ri >= ref->view.n_images || ci < 0 || ci >= cur->view.n_images)
-                return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pair %d references image %d/%d outside the pyramid batches", p, ri, ci);
-        }
+        const int ri = ri_map ? ri_map[p] : p, ci = ci_map ? ci_map[p] : p;
+        if (ri < 0 || ri >= ref->view.n_images || ci < 0 || ci >= cur->view.n_images)
+            return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "pair %d references image %d/%d outside the pyramid batches", p, ri, ci);
     }
     const int n = h_offsets[n_pairs];
     const bool has_prediction = !(flags & FTK_FLAG_NO_PREDICTION), has_status = !(flags & FTK_FLAG_NO_STATUS);

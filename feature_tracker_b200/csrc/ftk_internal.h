@@ -45,16 +45,19 @@ struct FtkBuffer {
 struct ftk_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;           // H2D of the next chunk while the current one computes (ftk_track_image_pairs)
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-    cudaEvent_t ev_computed[2] = {nullptr, nullptr};
-    ftk_pyramid *stage_pyr[2] = {nullptr, nullptr};  // double-buffered pyramid storage for the pipelined entry point
+    // the pipelined entry points (ftk_track_image_pairs*, ftk_track_image_sequence): one copy stream for every host-to-device byte,
+    // kStageBuffers rotating staging pyramids with one compute stream each
+    static constexpr int kStageBuffers = 3;
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t chunk_stream[kStageBuffers] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_copied[kStageBuffers] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_computed[kStageBuffers] = {nullptr, nullptr, nullptr};
+    ftk_pyramid *stage_pyr[kStageBuffers] = {nullptr, nullptr, nullptr};
     int stage_rows = 0, stage_cols = 0, stage_levels = 0, stage_pairs = 0;
     std::string error;
     uint64_t launches = 0;
     int sm_count = 0;
     const int *d_last_scan_items = nullptr;  // device counter of the last tensor-core cosine match (nullptr: path not used)
-    bool use_pooled = false;     // FTK_ENABLE_POOLED=1 routes basic kInverse to the CTA-pooled-fold kernel (experiment; slower)
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
@@ -107,8 +110,6 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &launch);
 int LaunchKltTrackChecked(ftk_context *ctx, const KltLaunch &launch, size_t scratch_offset = 0);
 // klt_basic_fastpath.cu: FTK_ERR_UNSUPPORTED when no specialisation covers the configuration
 int LaunchKltBasicFastPath(ftk_context *ctx, const KltLaunch &launch);
-// klt_basic_pooled.cu: basic kInverse with CTA-pooled folds; FTK_ERR_UNSUPPORTED when not covered
-int LaunchKltBasicPooled(ftk_context *ctx, const KltLaunch &launch);
 
 // direct_method.cu: one CTA per frame pair
 int LaunchDirectMethod(ftk_context *ctx, const ftk_direct_params &p, const PyramidView &ref, const PyramidView &cur, int n_pairs, const int *d_ref_image,

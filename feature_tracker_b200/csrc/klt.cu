@@ -1194,10 +1194,6 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
     geo.ec = geo.pc + 2;
     geo.esize = geo.er * geo.ec;
     if (geo.hr < 0 || geo.hc < 0) return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "negative patch half size");
-    if (ctx->use_fast_paths && ctx->use_pooled) {
-        const int rc = LaunchKltBasicPooled(ctx, a);
-        if (rc != FTK_ERR_UNSUPPORTED) return rc;
-    }
     if (ctx->use_fast_paths) {
         const int rc = LaunchKltBasicFastPath(ctx, a);
         if (rc != FTK_ERR_UNSUPPORTED) return rc;

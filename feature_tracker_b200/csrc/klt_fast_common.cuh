@@ -1,4 +1,4 @@
-// Helpers shared by the 16-lanes-per-feature basic-KLT kernels (klt_basic_fastpath.cu, klt_basic_pooled.cu).
+// Helpers shared by the 16-lanes-per-feature basic-KLT kernels (klt_basic_fastpath.cu).
 #ifndef FTK_KLT_FAST_COMMON_CUH_
 #define FTK_KLT_FAST_COMMON_CUH_
 

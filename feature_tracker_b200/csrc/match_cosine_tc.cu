@@ -140,16 +140,31 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 
 // ---- kernels -----------------------------------------------------------------------------------------------------
 
+// A descriptor whose norm is zero, not finite or far outside the range in which the unit-normalised BF16 copy bounds the dot-product
+// error (kEpsDot) cannot be screened by the tensor-core pass.  The reference still assigns such pairs a distance (e.g. a sum of
+// squares that overflows gives dot / inf = 0, i.e. d = 0.5; an underflowed norm gives +-inf): they are evaluated with the exact
+// kernel arithmetic instead -- an abnormal CURRENT descriptor becomes an extra exact candidate of every reference row (list
+// `abn_cur`), an abnormal REFERENCE row is scanned exactly against the whole current set.  Their BF16 rows are zero.
+__device__ __forceinline__ bool AbnormalNorm(float nrm) { return !(nrm >= 1e-12f && nrm <= 1e12f); }
+
 // norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA) -- and the
-// unit-normalised BF16 copy.  32 descriptors per block: rows are staged through shared memory so global reads and writes are
-// coalesced while each row's sum of squares is still accumulated by one thread in ascending k.
+// unit-normalised BF16 copy, for BOTH descriptor sets in one launch (blocks [0, ref_blocks) = reference rows, the rest = current
+// rows).  32 descriptors per block: rows are staged through shared memory so global reads and writes are coalesced while each
+// row's sum of squares is still accumulated by one thread in ascending k.
 constexpr int kPrepRows = 32;
 constexpr int kPrepThreads = 256;
-__global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *desc, int n, int dim, int k_pad, float *norm, __nv_bfloat16 *unit) {
+__global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref, int n_ref, const float *cur, int n_cur, int ref_blocks, int dim, int k_pad,
+                                                              float *ref_norm, float *cur_norm, __nv_bfloat16 *ref_unit, __nv_bfloat16 *cur_unit,
+                                                              int *counters, int *abn_cur) {
     extern __shared__ float prep_smem[];  // [kPrepRows][dim + 1] + [kPrepRows]
+    const bool is_cur = static_cast<int>(blockIdx.x) >= ref_blocks;
+    const float *desc = is_cur ? cur : ref;
+    const int n = is_cur ? n_cur : n_ref;
+    float *norm = is_cur ? cur_norm : ref_norm;
+    __nv_bfloat16 *unit = is_cur ? cur_unit : ref_unit;
     const int stride = dim + 1;
     float *s_norm = prep_smem + kPrepRows * stride;
-    const int row0 = blockIdx.x * kPrepRows;
+    const int row0 = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows;
     const int rows = min(kPrepRows, n - row0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // warp w moves rows w, w + 8, ...; lane = column within a 32-wide group (coalesced, no index arithmetic beyond adds)
@@ -166,15 +181,16 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *desc
         for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
         const float nrm = __fsqrt_rn(s);
         norm[row0 + threadIdx.x] = nrm;
-        // A descriptor without a usable norm has NaN distances to everything in the reference: NaN rows keep it out of every top-2.
-        s_norm[threadIdx.x] = (nrm > 0.0f && isfinite(nrm)) ? nrm : __int_as_float(0x7FC00000);
+        const bool abnormal = AbnormalNorm(nrm);
+        s_norm[threadIdx.x] = abnormal ? 0.0f : nrm;  // 0 marks "zero BF16 row"
+        if (abnormal && is_cur) abn_cur[atomicAdd(&counters[1], 1)] = row0 + threadIdx.x;
     }
     __syncthreads();
     for (int r = warp; r < rows; r += kPrepThreads / 32) {
         const float *src = prep_smem + r * stride;
         const float nr = s_norm[r];
         __nv_bfloat16 *dst = unit + static_cast<size_t>(row0 + r) * k_pad;
-        for (int k = lane; k < k_pad; k += 32) dst[k] = __float2bfloat16_rn(k < dim ? src[k] / nr : 0.0f);  // x / NaN = NaN
+        for (int k = lane; k < k_pad; k += 32) dst[k] = __float2bfloat16_rn((k < dim && nr > 0.0f) ? src[k] / nr : 0.0f);
     }
 }
 
@@ -361,467 +377,6 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     }
 }
 
-// =====================================================================================================================
-// A-from-TMEM variant.  tcgen05.mma reads ~64 B/clk of operands from shared memory: with both operands there, a 128 x 256 x 16
-// MMA needs 12 KB (A 4 KB + B 8 KB) = 192 clk against 135 clk of math -- the ~70 % ceiling measured above.  The reference tile
-// A (128 rows x K) never changes while a CTA streams the current set past it, so it is written ONCE into tensor memory
-// (tcgen05.st: TMEM lane = row, one 32-bit column = two consecutive BF16 of the row) and every MMA takes A from TMEM
-// (tcgen05.mma [d], [a], b_desc, ...).  Shared memory then only feeds B: tiles are 192 columns wide (2 x 192 accumulator
-// columns + 128 columns of A fill the 512 TMEM columns), 6 KB per 128 x 192 x 16 MMA = 96 clk < 101 clk of math, and all of
-// shared memory becomes an 8-stage B pipeline.
-// =====================================================================================================================
-constexpr int kTileN3 = 192;
-constexpr int kStages3 = 8;
-constexpr int kBoxBytesB3 = kTileN3 * kKBlock * 2;  // 24 KiB
-constexpr int kTmemColA = 2 * kTileN3;              // A lives behind the two accumulators
-constexpr size_t kTc3SmemBytes = 1024 + static_cast<size_t>(kStages3) * kBoxBytesB3 + 512;
-constexpr uint32_t kInstrDesc3 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN3 >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
-
-__device__ __forceinline__ void UmmaBf16ATmem(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void TmemStore32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
-        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
-        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
-        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-CosineTcATmemKernel(const __nv_bfloat16 *__restrict__ ref_unit, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks, int k_pad,
-                    int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t *smem_b = smem;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages3 * kBoxBytesB3);
-    uint64_t *bar_a = &bars[0];                          // A is in tensor memory (4 epilogue warps arrive)
-    uint64_t *bar_full = &bars[1];                       // [kStages3]
-    uint64_t *bar_empty = &bars[1 + kStages3];           // [kStages3]
-    uint64_t *bar_acc_full = &bars[1 + 2 * kStages3];    // [2]
-    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages3];   // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages3]);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
-    const int t_begin = blockIdx.y * tiles_per_split;
-    const int t_end = min(n_tiles, t_begin + tiles_per_split);
-
-    if (threadIdx.x == 0) {
-        MbarInit(bar_a, 4);
-        for (int s = 0; s < kStages3; ++s) {
-            MbarInit(&bar_full[s], 1);
-            MbarInit(&bar_empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            MbarInit(&bar_acc_full[a], 1);
-            MbarInit(&bar_acc_empty[a], 4);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    TcFenceBefore();
-    __syncthreads();
-    TcFenceAfter();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== TMA producer: B only =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_empty[stage], phase ^ 1u);
-                    MbarExpectTx(&bar_full[stage], kBoxBytesB3);
-                    TmaLoad2D(smem_b + stage * kBoxBytesB3, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN3);
-                    if (++stage == kStages3) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            MbarWait(bar_a, 0);
-            TcFenceAfter();
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
-                TcFenceAfter();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN3);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_full[stage], phase);
-                    TcFenceAfter();
-                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB3);
-#pragma unroll
-                    for (int k = 0; k < kKBlock / 16; ++k) {
-                        // A: 16 BF16 of every row = 8 TMEM columns per MMA
-                        const uint32_t tmem_a = tmem_base + static_cast<uint32_t>(kTmemColA + (kb * (kKBlock / 16) + k) * 8);
-                        UmmaBf16ATmem(tmem_d, tmem_a, bdesc + static_cast<uint64_t>(2 * k), kInstrDesc3, (kb | k) != 0 ? 1u : 0u);
-                    }
-                    UmmaCommit(&bar_empty[stage]);
-                    if (++stage == kStages3) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-                UmmaCommit(&bar_acc_full[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===================== epilogue warps: first park A in tensor memory, then the running top-2 =====================
-        const int quarter = warp & 3;
-        const int row = m_tile * kTileM + quarter * 32 + lane;
-        {
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(ref_unit + static_cast<size_t>(row) * k_pad);  // 2 BF16 per word, k ascending
-            const uint32_t tbase_a = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(kTmemColA);
-            for (int c0 = 0; c0 < k_pad / 2; c0 += 32) {
-                uint32_t r[32];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (row < n_ref) v = __ldg(reinterpret_cast<const uint4 *>(src + c0) + q);
-                    r[4 * q] = v.x, r[4 * q + 1] = v.y, r[4 * q + 2] = v.z, r[4 * q + 3] = v.w;
-                }
-                TmemStore32(tbase_a + static_cast<uint32_t>(c0), r);
-            }
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            TcFenceBefore();
-            __syncwarp();
-            if (lane == 0) MbarArrive(bar_a);
-        }
-        float b1 = floor_dot, b2 = -INFINITY;
-        int j1 = -1;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-            MbarWait(&bar_acc_full[acc], acc_phase);
-            TcFenceAfter();
-            const int n0 = t * kTileN3;
-            const bool partial = n0 + kTileN3 > n_cur;
-            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN3);
-            auto reduce_chunk = [&](uint32_t (&r)[32], int chunk) {
-                const int c0 = n0 + chunk * 32;
-                if (partial) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (c0 + c >= n_cur) r[c] = 0xFF800000u;
-                }
-                float m4[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    m4[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
-                const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-                if (m > b1) {
-                    float cb1 = -INFINITY, cb2 = -INFINITY;
-                    int cj = 0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = __uint_as_float(r[c]);
-                        if (v > cb1) {
-                            cb2 = cb1;
-                            cb1 = v;
-                            cj = c;
-                        } else {
-                            cb2 = fmaxf(cb2, v);
-                        }
-                    }
-                    b2 = fmaxf(b1, cb2);
-                    b1 = cb1;
-                    j1 = c0 + cj;
-                } else {
-                    b2 = fmaxf(b2, m);
-                }
-            };
-            uint32_t ra[32], rb[32];
-            TmemLoad32(tbase, ra);
-            TmemLoadWait(ra);
-#pragma unroll 1
-            for (int chunk = 0; chunk < kTileN3 / 32; chunk += 2) {
-                TmemLoad32(tbase + static_cast<uint32_t>((chunk + 1) * 32), rb);
-                reduce_chunk(ra, chunk);
-                TmemLoadWait(rb);
-                if (chunk + 2 < kTileN3 / 32) TmemLoad32(tbase + static_cast<uint32_t>((chunk + 2) * 32), ra);
-                reduce_chunk(rb, chunk + 1);
-                if (chunk + 2 < kTileN3 / 32) TmemLoadWait(ra);
-            }
-            TcFenceBefore();
-            __syncwarp();
-            if (lane == 0) MbarArrive(&bar_acc_empty[acc]);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
-        }
-        if (row < n_ref) {
-            Top2 o;
-            o.b1 = j1 >= 0 ? b1 : -INFINITY;
-            o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;
-            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
-        }
-    }
-
-    TcFenceBefore();
-    __syncthreads();
-    if (warp == 1) {
-        TcFenceAfter();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
-// =====================================================================================================================
-// CTA-pair variant (cta_group::2): two CTAs of a cluster -- two SMs of one TPC -- execute ONE 256 x 256 x 16 tcgen05.mma per
-// issue.  Each CTA keeps its own 128 reference rows (A) and loads only HALF of every current-set tile (128 of the 256 B rows);
-// the tensor cores of both SMs read both halves.  Per SM that halves the TMA traffic and the shared-memory operand reads of
-// B, which is what caps the single-CTA kernel (its MMA thread never starves, yet the tensor pipe is busy only ~65 %).
-//   * barriers: the LEADER (cluster rank 0) owns bar_a / bar_full[]: both CTAs' TMA loads complete_tx on the leader's barrier
-//     (cp.async.bulk.tensor ... cta_group::2 with the leader's barrier address), the leader's MMA thread waits there;
-//     tcgen05.commit ... multicast::cluster arrives on bar_empty[] / bar_acc_full[] of BOTH CTAs; the follower's epilogue warps
-//     arrive remotely on the leader's bar_acc_empty[] (8 arrivals per accumulator).
-//   * TMEM: allocated / freed with cta_group::2 by warp 1 of both CTAs; each CTA's epilogue reads its own 128 lanes.
-// =====================================================================================================================
-constexpr int kStages2 = 8;                          // 16 KiB stages: one K block of this CTA's half of a current-set tile
-constexpr int kHalfN = kTileN / 2;                   // B rows per CTA
-constexpr int kBoxBytesB2 = kHalfN * kKBlock * 2;    // 16 KiB
-constexpr size_t kTc2SmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytesA + static_cast<size_t>(kStages2) * kBoxBytesB2 + 512;
-constexpr uint32_t kInstrDesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(kTileN >> 3) << 17) | (static_cast<uint32_t>((2 * kTileM) >> 4) << 24);
-
-__device__ __forceinline__ uint32_t ClusterCtaRank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void ClusterSync() {
-    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-}
-// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t MapToCta(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void MbarArriveCluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void TmaLoad2DPair(void *smem_dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                     SmemU32(smem_dst)),
-                 "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void UmmaBf16Pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on the barrier at this shared-memory offset in both CTAs of the pair once all MMAs issued so far have retired
-__device__ __forceinline__ void UmmaCommitPair(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(SmemU32(bar)),
-                 "h"(static_cast<uint16_t>(3))
-                 : "memory");
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-CosineTcPairKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur_half, int n_ref, int n_cur, int k_blocks,
-                   int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytesA;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages2 * kBoxBytesB2);
-    uint64_t *bar_a = &bars[0];
-    uint64_t *bar_full = &bars[1];                      // [kStages2]   (the leader's are used)
-    uint64_t *bar_empty = &bars[1 + kStages2];          // [kStages2]   (each CTA its own)
-    uint64_t *bar_acc_full = &bars[1 + 2 * kStages2];   // [2]          (each CTA its own)
-    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages2];  // [2]          (the leader's are used)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages2]);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = ClusterCtaRank();
-    const bool leader = rank == 0;
-    const int m_tile = blockIdx.x;  // the two CTAs of a cluster are neighbours in x: rows m_tile * 128 ...
-    const int t_begin = blockIdx.y * tiles_per_split;
-    const int t_end = min(n_tiles, t_begin + tiles_per_split);
-
-    if (threadIdx.x == 0) {
-        MbarInit(bar_a, 1);
-        for (int s = 0; s < kStages2; ++s) {
-            MbarInit(&bar_full[s], 1);
-            MbarInit(&bar_empty[s], 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            MbarInit(&bar_acc_full[a], 1);
-            MbarInit(&bar_acc_empty[a], 8);  // four epilogue warps of each CTA
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemU32(tmem_slot)), "r"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-    TcFenceBefore();
-    ClusterSync();  // barriers and TMEM of both CTAs exist
-    TcFenceAfter();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== TMA producer (both CTAs; transaction bytes go to the leader's barriers) =====================
-        if (lane == 0) {
-            const uint32_t lead_bar_a = MapToCta(SmemU32(bar_a), 0);
-            if (leader) MbarExpectTx(bar_a, 2u * static_cast<uint32_t>(k_blocks) * kBoxBytesA);
-            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2DPair(smem_a + kb * kBoxBytesA, &map_ref, lead_bar_a, kb * kKBlock, m_tile * kTileM);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_empty[stage], phase ^ 1u);
-                    if (leader) MbarExpectTx(&bar_full[stage], 2u * kBoxBytesB2);
-                    TmaLoad2DPair(smem_b + stage * kBoxBytesB2, &map_cur_half, MapToCta(SmemU32(&bar_full[stage]), 0), kb * kKBlock,
-                                  t * kTileN + static_cast<int>(rank) * kHalfN);
-                    if (++stage == kStages2) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer: one thread of the leader CTA =====================
-        if (leader && lane == 0) {
-            MbarWait(bar_a, 0);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
-                TcFenceAfter();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_full[stage], phase);
-                    TcFenceAfter();
-                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytesA);
-                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB2);
-#pragma unroll
-                    for (int k = 0; k < kKBlock / 16; ++k)
-                        UmmaBf16Pair(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc2, (kb | k) != 0 ? 1u : 0u);
-                    UmmaCommitPair(&bar_empty[stage]);
-                    if (++stage == kStages2) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-                UmmaCommitPair(&bar_acc_full[acc]);
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
-            }
-        }
-        __syncwarp();
-    } else {
-        // ===================== epilogue (both CTAs): running top-2 per reference row =====================
-        const int quarter = warp & 3;
-        const int row = m_tile * kTileM + quarter * 32 + lane;
-        float b1 = floor_dot, b2 = -INFINITY;
-        int j1 = -1;
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        const uint32_t lead_acc_empty0 = MapToCta(SmemU32(&bar_acc_empty[0]), 0), lead_acc_empty1 = MapToCta(SmemU32(&bar_acc_empty[1]), 0);
-        for (int t = t_begin; t < t_end; ++t) {
-            MbarWait(&bar_acc_full[acc], acc_phase);
-            TcFenceAfter();
-            const int n0 = t * kTileN;
-            const bool partial = n0 + kTileN > n_cur;
-            const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kTileN);
-            auto reduce_chunk = [&](uint32_t (&r)[32], int chunk) {
-                const int c0 = n0 + chunk * 32;
-                if (partial) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (c0 + c >= n_cur) r[c] = 0xFF800000u;
-                }
-                float m4[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    m4[q] = fmaxf(fmaxf(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1])), fmaxf(__uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
-                const float m = fmaxf(fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])), fmaxf(fmaxf(m4[4], m4[5]), fmaxf(m4[6], m4[7])));
-                if (m > b1) {
-                    float cb1 = -INFINITY, cb2 = -INFINITY;
-                    int cj = 0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = __uint_as_float(r[c]);
-                        if (v > cb1) {
-                            cb2 = cb1;
-                            cb1 = v;
-                            cj = c;
-                        } else {
-                            cb2 = fmaxf(cb2, v);
-                        }
-                    }
-                    b2 = fmaxf(b1, cb2);
-                    b1 = cb1;
-                    j1 = c0 + cj;
-                } else {
-                    b2 = fmaxf(b2, m);
-                }
-            };
-            uint32_t ra[32], rb[32];
-            TmemLoad32(tbase, ra);
-            TmemLoadWait(ra);
-#pragma unroll 1
-            for (int chunk = 0; chunk < kTileN / 32; chunk += 2) {
-                TmemLoad32(tbase + static_cast<uint32_t>((chunk + 1) * 32), rb);
-                reduce_chunk(ra, chunk);
-                TmemLoadWait(rb);
-                if (chunk + 2 < kTileN / 32) TmemLoad32(tbase + static_cast<uint32_t>((chunk + 2) * 32), ra);
-                reduce_chunk(rb, chunk + 1);
-                if (chunk + 2 < kTileN / 32) TmemLoadWait(ra);
-            }
-            TcFenceBefore();
-            __syncwarp();
-            if (lane == 0) MbarArriveCluster(acc == 0 ? lead_acc_empty0 : lead_acc_empty1);
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
-        }
-        if (row < n_ref) {
-            Top2 o;
-            o.b1 = j1 >= 0 ? b1 : -INFINITY;
-            o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;
-            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
-        }
-    }
-
-    TcFenceBefore();
-    ClusterSync();  // nobody leaves while the peer may still signal its barriers or read its shared memory
-    if (warp == 1) {
-        TcFenceAfter();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
-    }
-}
-
 // Order-preserving key for a non-NaN float distance (with -0 canonicalised to +0).
 __device__ __forceinline__ unsigned FloatKey(float d) {
     d = d + 0.0f;
@@ -840,50 +395,56 @@ __device__ __forceinline__ float ExactDistance(const float *a, const float *b, i
 
 // Exact re-evaluation of the candidates inside the error margin.  A block owns 32 consecutive reference rows:
 //   1. each warp screens 8 rows: lane s reads the top-2 of column split s, the warp forms the row's best approximate dot, flags the
-//      splits whose best lies inside the margin (candidates) and hands "crowded" splits (both of its top-2 inside the margin: a
-//      third candidate could hide) to the exact scan;
+//      splits whose best lies inside the margin (candidates) and marks "crowded" splits (both of its top-2 inside the margin: a
+//      third candidate could hide) for the exact scan;
 //   2. per round, every row with a candidate left gets its 256 products a[k] * b[k] written to shared memory by its warp
 //      (coalesced loads, each product one correctly rounded multiply -- the reference's), then LANE r OF WARP 0 ADDS ROW r's
 //      PRODUCTS in ascending k: 32 of the reference's sequential sums advance per instruction instead of one.
-// Rounds repeat while any row of the block has another candidate (almost always exactly one round).
+//      Rounds repeat while any row of the block has another candidate (almost always exactly one round);
+//   3. abnormal current descriptors (see AbnormalNorm) are exact candidates of every row;
+//   4. a row without scan work is FINISHED here (idx written when its best distance < max_dist); a row with crowded splits, or an
+//      abnormal reference row, parks its key in best[] and queues (row, split mask) for ExactScanKernel, which finishes it.
 constexpr int kRerankRows = 32;
 constexpr int kRerankThreads = 128;
 constexpr int kMaxSplits = 16;
 __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
                                                               const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
-                                                              unsigned long long *best, int2 *work, int *n_work) {
+                                                              unsigned long long *best, int2 *work, int *counters, const int *abn_cur, float max_dist,
+                                                              int *idx) {
     extern __shared__ float rerank_smem[];  // [kRerankRows][dim + 1] products
     __shared__ int s_cand[kRerankRows][kMaxSplits];  // candidate columns of each row, in split order
     __shared__ int s_count[kRerankRows];
+    __shared__ unsigned s_scan[kRerankRows];  // split mask the exact scan has to cover
     const int stride = dim + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRerankRows;
+    const unsigned all_splits = (1u << n_splits) - 1u;  // n_splits <= kMaxSplits = 16
 
     // ---- 1. screening ----
     for (int r = warp; r < kRerankRows; r += kRerankThreads / 32) {
         const int i = row0 + r;
         int count = 0;
+        unsigned scan = 0u;
         if (i < n_ref) {
-            Top2 mine;
-            mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
-            if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
-            float gmax = mine.b1;
+            if (AbnormalNorm(ref_norm[i])) {
+                scan = all_splits;  // nothing the tensor-core pass said about this row can be trusted
+            } else {
+                Top2 mine;
+                mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
+                if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
+                float gmax = mine.b1;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
-            const float thr = gmax - 2.0f * kEpsDot;
-            const bool cand = gmax > -INFINITY && mine.j1 >= 0 && mine.b1 >= thr;
-            const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;
-            const unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
-            unsigned scan = __ballot_sync(0xFFFFFFFFu, crowded);
-            while (scan) {
-                const int sp = __ffs(scan) - 1;
-                scan &= scan - 1;
-                if (lane == 0) work[atomicAdd(n_work, 1)] = make_int2(i, sp);
+                for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+                const float thr = gmax - 2.0f * kEpsDot;
+                const bool cand = gmax > -INFINITY && mine.j1 >= 0 && mine.b1 >= thr;
+                const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;
+                const unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
+                scan = __ballot_sync(0xFFFFFFFFu, crowded);
+                if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine.j1;
+                count = __popc(todo);
             }
-            if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine.j1;
-            count = __popc(todo);
         }
-        if (lane == 0) s_count[r] = count;
+        if (lane == 0) s_count[r] = count, s_scan[r] = scan;
     }
     __syncthreads();
 
@@ -915,24 +476,49 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
         }
         __syncthreads();
     }
-    if (warp == 0 && row0 + lane < n_ref && key != kNoKey64) atomicMin(&best[row0 + lane], key);
+    if (warp != 0 || row0 + lane >= n_ref) return;
+    const int i = row0 + lane;
+    // ---- 3. abnormal current descriptors: exact candidates of every row (normally none) ----
+    const unsigned scan = s_scan[lane];
+    const int n_abn = scan == all_splits ? 0 : counters[1];  // a full scan covers them anyway
+    for (int q = 0; q < n_abn; ++q) {
+        const int j = abn_cur[q];
+        const float d = ExactDistance(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim, ref_norm[i], cur_norm[j]);
+        if (d == d) {
+            const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+            key = k64 < key ? k64 : key;
+        }
+    }
+    // ---- 4. finish the row, or hand it to the exact scan ----
+    if (scan != 0u) {
+        best[i] = key;
+        work[atomicAdd(&counters[0], 1)] = make_int2(i, static_cast<int>(scan));
+    } else if (key != kNoKey64 && KeyFloat(static_cast<unsigned>(key >> 32)) < max_dist) {
+        idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+    }
 }
 
-// One block per flagged (row, split): exact scan of the split's column range.
+// One block per queued row: exact scan of the column ranges of the flagged splits, merged with the row's parked key; writes idx.
 __global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const float *cur, int n_cur, int dim, const float *ref_norm, const float *cur_norm,
-                                                      const int2 *work, const int *n_work, int cols_per_split, unsigned long long *best) {
-    const int n = *n_work;
+                                                      const int2 *work, const int *counters, int cols_per_split, int n_splits,
+                                                      const unsigned long long *best, float max_dist, int *idx) {
+    __shared__ unsigned long long s_key[4];
+    const int n = counters[0];
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
-        const int i = work[w].x, s = work[w].y;
-        const int j_begin = s * cols_per_split, j_end = min(n_cur, j_begin + cols_per_split);
+        const int i = work[w].x;
+        const unsigned mask = static_cast<unsigned>(work[w].y);
         const float *a = ref + static_cast<size_t>(i) * dim;
         const float na = ref_norm[i];
         unsigned long long key = kNoKey64;
-        for (int j = j_begin + threadIdx.x; j < j_end; j += blockDim.x) {
-            const float d = ExactDistance(a, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j]);
-            if (d == d) {
-                const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
-                key = k < key ? k : key;
+        for (int s = 0; s < n_splits; ++s) {
+            if (!((mask >> s) & 1u)) continue;
+            const int j_begin = s * cols_per_split, j_end = min(n_cur, j_begin + cols_per_split);
+            for (int j = j_begin + threadIdx.x; j < j_end; j += blockDim.x) {
+                const float d = ExactDistance(a, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j]);
+                if (d == d) {
+                    const unsigned long long k = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+                    key = k < key ? k : key;
+                }
             }
         }
 #pragma unroll
@@ -940,23 +526,15 @@ __global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const f
             const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
             key = other < key ? other : key;
         }
-        if ((threadIdx.x & 31) == 0 && key != kNoKey64) atomicMin(&best[i], key);
+        if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            key = best[i];
+            for (int q = 0; q < 4; ++q) key = s_key[q] < key ? s_key[q] : key;
+            if (key != kNoKey64 && KeyFloat(static_cast<unsigned>(key >> 32)) < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+        }
+        __syncthreads();
     }
-}
-
-__global__ void FinalizeKernel(const unsigned long long *best, int n_ref, float max_dist, int *idx) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_ref) return;
-    const unsigned long long key = best[i];
-    if (key == kNoKey64) return;
-    const float d = KeyFloat(static_cast<unsigned>(key >> 32));
-    if (d < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
-}
-
-__global__ void FillKeysKernel(unsigned long long *p, int n, int *counter) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = kNoKey64;
-    if (i == 0) *counter = 0;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda).
@@ -991,17 +569,14 @@ int Blocks(int n, int threads) { return (n + threads - 1) / threads; }
 }  // namespace
 
 // Returns FTK_ERR_UNSUPPORTED when the tensor-core path does not cover the shape (dim > 256): the caller then runs the
-// exact CUDA-core kernel of match.cu.
+// exact CUDA-core kernel of match.cu.  Four launches: NormPrepKernel (both sets) -> CosineTcKernel -> RerankKernel (finishes the
+// rows) -> ExactScanKernel (finishes the few rows the screening could not decide; its blocks exit at once when there are none).
 int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
     if (dim > kMaxKBlocks * kKBlock) return FTK_ERR_UNSUPPORTED;
     if (n_ref == 0) return FTK_OK;
     cudaStream_t st = ctx->stream;
     const int k_blocks = (dim + kKBlock - 1) / kKBlock, k_pad = k_blocks * kKBlock;
-    // kernel variant: A from tensor memory (192-column tiles) when FTK_COSINE_ATMEM=1, else both operands from shared memory
-    const char *atmem_env = getenv("FTK_COSINE_ATMEM");
-    const bool a_in_tmem = atmem_env && atmem_env[0] == '1';
-    const int tile_n = a_in_tmem ? kTileN3 : kTileN;
-    const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + tile_n - 1) / tile_n;
+    const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + kTileN - 1) / kTileN;
     // Split the current set across CTAs: one CTA per SM at a time (192 KB of shared memory), so pick the split count whose
     // grid fills whole waves best (ties: fewer splits = more reuse of the resident reference tile).
     int splits = 1;
@@ -1025,84 +600,47 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
     const int n_ref_pad = m_tiles * kTileM;
 
-    // scratch: norms | unit bf16 copies | top-2 | best keys | work list
+    // scratch: norms | unit bf16 copies | top-2 | counters, parked keys, work list, abnormal-column list
     const size_t bytes_norm = sizeof(float) * (static_cast<size_t>(n_ref) + n_cur);
     const size_t bytes_unit = sizeof(__nv_bfloat16) * static_cast<size_t>(k_pad) * (static_cast<size_t>(n_ref) + n_cur);
     if (int rc = EnsureDevice(ctx, ctx->d_work3, bytes_norm + 256)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work1, bytes_unit + 1024)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work2, sizeof(Top2) * static_cast<size_t>(splits) * n_ref_pad + 256)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref) + sizeof(int2) * static_cast<size_t>(n_ref) * splits + 256))
+    if (int rc = EnsureDevice(ctx, ctx->d_work0,
+                              16 + (sizeof(unsigned long long) + sizeof(int2)) * static_cast<size_t>(n_ref) + sizeof(int) * static_cast<size_t>(n_cur) + 256))
         return rc;
     float *ref_norm = static_cast<float *>(ctx->d_work3.ptr), *cur_norm = ref_norm + n_ref;
     __nv_bfloat16 *ref_unit = static_cast<__nv_bfloat16 *>(ctx->d_work1.ptr);
     __nv_bfloat16 *cur_unit = ref_unit + static_cast<size_t>(n_ref) * k_pad;
     Top2 *top = static_cast<Top2 *>(ctx->d_work2.ptr);
-    unsigned long long *best = static_cast<unsigned long long *>(ctx->d_work0.ptr);
-    int *n_work = reinterpret_cast<int *>(best + n_ref);
-    int2 *work = reinterpret_cast<int2 *>(n_work + 2);
+    int *counters = static_cast<int *>(ctx->d_work0.ptr);  // [0] rows queued for the exact scan, [1] abnormal current descriptors
+    unsigned long long *best = reinterpret_cast<unsigned long long *>(counters + 4);
+    int2 *work = reinterpret_cast<int2 *>(best + n_ref);
+    int *abn_cur = reinterpret_cast<int *>(work + n_ref);
 
     CUtensorMap map_ref, map_cur;
-    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, tile_n))
+    if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, kTileN))
         return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
 
+    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, 16, st));
     const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * (dim + 1) + kPrepRows);
-    NormPrepKernel<<<Blocks(n_ref, kPrepRows), kPrepThreads, prep_smem, st>>>(d_ref, n_ref, dim, k_pad, ref_norm, ref_unit);
-    NormPrepKernel<<<Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_cur, n_cur, dim, k_pad, cur_norm, cur_unit);
-    FillKeysKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, n_work);
+    const int ref_blocks = Blocks(n_ref, kPrepRows);
+    NormPrepKernel<<<ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_ref, n_ref, d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm,
+                                                                                          ref_unit, cur_unit, counters, abn_cur);
 
     // cos > 1 - 2 * max_dist is necessary for distance < max_dist; 3 * kEpsDot covers the BF16 dot error and the fp32 rounding of the
     // distance formula.  NaN / huge thresholds give NaN / -inf floors: nothing or everything passes, as in the reference.
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
-    // The CTA-pair kernel (cta_group::2) is bit-identical but measured slower than the single-CTA one (203 us vs 166 us for
-    // 20k x 20k x 256): opt-in with FTK_COSINE_2CTA=1, see DESIGN.md.
-    const char *pair_env = getenv("FTK_COSINE_2CTA");
-    const bool single_cta = !(pair_env && pair_env[0] == '1');
-    if (a_in_tmem) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcATmemKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTc3SmemBytes)));
-            attr_set = true;
-        }
-        CosineTcATmemKernel<<<dim3(m_tiles, splits), kTcThreads, kTc3SmemBytes, st>>>(ref_unit, map_cur, n_ref, n_cur, k_blocks, k_pad, tiles_per_split, n_tiles,
-                                                                                    top, n_ref_pad, floor_dot);
-    } else if (single_cta) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
-            attr_set = true;
-        }
-        CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
-                                                                              floor_dot);
-    } else {
-        // CTA pairs: clusters of two neighbouring m-tiles (an odd last tile gets an idle partner whose rows are zero-filled by TMA)
-        static bool attr_set = false;
-        if (!attr_set) {
-            FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcPairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTc2SmemBytes)));
-            attr_set = true;
-        }
-        CUtensorMap map_cur_half;
-        if (!MakeMap(&map_cur_half, cur_unit, n_cur, k_pad, kHalfN)) return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((m_tiles + 1) / 2 * 2, splits);
-        cfg.blockDim = dim3(kTcThreads);
-        cfg.dynamicSmemBytes = kTc2SmemBytes;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        FTK_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, CosineTcPairKernel, map_ref, map_cur_half, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
-                                               floor_dot));
-    }
-    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits,
-                                                                                                            n_ref_pad, best, work, n_work);
-    ExactScanKernel<<<ctx->sm_count * 4, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, n_work, tiles_per_split * tile_n, best);
-    FinalizeKernel<<<Blocks(n_ref, 256), 256, 0, st>>>(best, n_ref, max_dist, d_idx);
-    ctx->launches += 7;
-    ctx->d_last_scan_items = n_work;
+    // The opt-in is per device and the ABI allows one process to hold contexts on several GPUs: set it before every launch (cheap).
+    FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
+    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
+                                                                          floor_dot);
+    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(
+        d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx);
+    ExactScanKernel<<<ctx->sm_count * 2, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters, tiles_per_split * kTileN, splits, best, max_dist,
+                                                       d_idx);
+    ctx->launches += 4;
+    ctx->d_last_scan_items = counters;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
 }

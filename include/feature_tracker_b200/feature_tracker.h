@@ -5,9 +5,12 @@
 //
 // Differences a maintainer has to know about (all dictated by where the data lives):
 //   * ImagePyramid is device resident: SetRawImage() + CreateImagePyramid() upload level 0 and build the levels on the GPU.
-//   * DescriptorMatcher<T> no longer calls a per-pair virtual ComputeDistance (one virtual call per pair cannot feed a GPU);
-//     the distance is selected by DescriptorTraits<T>: Hamming for element-wise boolean containers (BriefType), the
-//     0.5 - 0.5 * cos distance for float vectors (Superpoint / Disk descriptors), exactly the demos' ComputeDistance bodies.
+//   * DescriptorMatcher<T> keeps the private virtual ComputeDistance (descriptor_matcher.h:45), so the reference's subclasses
+//     (test/test_descriptor_matcher_brief.cpp:27-46) compile unchanged, but it is NOT called per pair (one virtual call per pair
+//     cannot feed a GPU): the distance the GPU evaluates is selected by DescriptorTraits<T> -- Hamming for element-wise boolean
+//     containers (BriefType), 0.5 - 0.5 * cos for float vectors (Superpoint / Disk descriptors), exactly the demos' bodies.  Every
+//     match call evaluates the subclass's override on a few (ref, cur) pairs and FAILS LOUDLY (std::logic_error) when it
+//     disagrees with that metric, so a custom distance can never be silently replaced.
 //   * Vec2 is any type with x() / y() accessors and a (float, float) constructor (Eigen::Vector2f qualifies); define
 //     FTK_VEC2_TYPE before including this header to use the application's own type.
 // Header only; link with libftk_b200.so.
@@ -16,11 +19,13 @@
 
 #include <array>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "ftk_c.h"
@@ -71,6 +76,23 @@ private:
     ftk_context *ctx_ = nullptr;
 };
 
+// Host image view with the accessors of Slam_Utility's GrayImage the reference's call sites use (data / rows / cols;
+// test/test_optical_flow.cpp:45-52).  The GrayImage overloads below are templates over any type with these three accessors,
+// so an application passes its own Slam_Utility GrayImage directly; this class only serves applications that have none.
+class GrayImage {
+public:
+    GrayImage() = default;
+    GrayImage(uint8_t *data, int32_t rows, int32_t cols) : data_(data), rows_(rows), cols_(cols) {}
+    void SetImage(uint8_t *data, int32_t rows, int32_t cols) { data_ = data, rows_ = rows, cols_ = cols; }
+    uint8_t *data() const { return data_; }
+    int32_t rows() const { return rows_; }
+    int32_t cols() const { return cols_; }
+
+private:
+    uint8_t *data_ = nullptr;
+    int32_t rows_ = 0, cols_ = 0;
+};
+
 // Device-resident stand-in for Slam_Utility's ImagePyramid (call sites: test/test_optical_flow.cpp:49-53,70-71).
 class ImagePyramid {
 public:
@@ -94,6 +116,7 @@ public:
             built_rows_ = rows_;
             built_cols_ = cols_;
         }
+        for (auto &h : host_levels_) h.clear();
         if (ftk_pyramid_set_images(ctx, pyr_, 0, 1, raw_, 0) != FTK_OK) return false;
         return ftk_pyramid_build(ctx, pyr_, 0, 1) == FTK_OK && ftk_synchronize(ctx) == FTK_OK;
     }
@@ -101,12 +124,30 @@ public:
     int32_t rows() const { return rows_; }
     int32_t cols() const { return cols_; }
     const ftk_pyramid *handle() const { return pyr_; }
+    // ImagePyramid::GetImageConst(i) of Slam_Utility (callers: basic_klt.cpp:22-23): level i as a host image.  The levels live in
+    // HBM; level i is copied back on first use after each CreateImagePyramid and cached (level 0 is the caller's own buffer).
+    const GrayImage &GetImageConst(uint32_t i) const {
+        if (i >= kPyramidMaxLevel || pyr_ == nullptr || i >= level()) throw std::out_of_range("ImagePyramid::GetImageConst: no such level");
+        if (i == 0) {
+            views_[0].SetImage(const_cast<uint8_t *>(raw_), rows_, cols_);
+        } else if (host_levels_[i].empty()) {
+            const int32_t r = rows_ >> i, c = cols_ >> i;
+            host_levels_[i].resize(static_cast<size_t>(r) * c);
+            if (ftk_pyramid_get_level(Device::Get(), pyr_, 0, static_cast<int32_t>(i), host_levels_[i].data()) != FTK_OK)
+                throw std::runtime_error("ImagePyramid::GetImageConst: device read failed");
+            views_[i].SetImage(host_levels_[i].data(), r, c);
+        }
+        return views_[i];
+    }
+    static constexpr uint32_t kPyramidMaxLevel = 10;
 
 private:
     void Release() {
         if (pyr_) ftk_pyramid_destroy(Device::Get(), pyr_);
         pyr_ = nullptr;
     }
+    mutable std::array<std::vector<uint8_t>, kPyramidMaxLevel> host_levels_;
+    mutable std::array<GrayImage, kPyramidMaxLevel> views_;
     const uint8_t *raw_ = nullptr;
     int32_t rows_ = 0, cols_ = 0, built_rows_ = 0, built_cols_ = 0;
     ftk_pyramid *pyr_ = nullptr;
@@ -146,7 +187,20 @@ public:
         if (cur_pyramid.level() != ref_pyramid.level()) return false;
         return Track(ref_pyramid, cur_pyramid, ref_pixel_uv, cur_pixel_uv, status, 0u);
     }
-    // optical_flow.cpp:28-47 (the GrayImage overload): level 0 of the two pyramids, TrackSingleLevel semantics.
+    // optical_flow.cpp:28-47, optical_flow.h:41-42: TrackFeatures(const GrayImage &, const GrayImage &, ...) -- TrackSingleLevel on
+    // two host images.  A template over the image type (data() / rows() / cols()), so Slam_Utility's GrayImage is accepted as is.
+    template <typename GrayImageT, typename = decltype(std::declval<const GrayImageT &>().data()), typename = decltype(std::declval<const GrayImageT &>().rows())>
+    bool TrackFeatures(const GrayImageT &ref_image, const GrayImageT &cur_image, const std::vector<Vec2> &ref_pixel_uv, std::vector<Vec2> &cur_pixel_uv,
+                       std::vector<uint8_t> &status) {
+        if (ref_pixel_uv.empty()) return false;                                       // :30
+        if (ref_image.data() == nullptr || cur_image.data() == nullptr) return false;  // :31-32
+        if (ref_image.rows() != cur_image.rows() || ref_image.cols() != cur_image.cols()) return false;  // one device batch holds equal-sized images
+        single_ref_.SetRawImage(ref_image.data(), ref_image.rows(), ref_image.cols());
+        single_cur_.SetRawImage(cur_image.data(), cur_image.rows(), cur_image.cols());
+        if (!single_ref_.CreateImagePyramid(1) || !single_cur_.CreateImagePyramid(1)) return false;
+        return Track(single_ref_, single_cur_, ref_pixel_uv, cur_pixel_uv, status, FTK_FLAG_SINGLE_LEVEL);
+    }
+    // The same on level 0 of two device pyramids (no upload).
     bool TrackFeaturesSingleLevel(const ImagePyramid &ref_image, const ImagePyramid &cur_image, const std::vector<Vec2> &ref_pixel_uv,
                                   std::vector<Vec2> &cur_pixel_uv, std::vector<uint8_t> &status) {
         if (ref_pixel_uv.empty()) return false;
@@ -200,6 +254,7 @@ private:
     }
     OpticalFlowOptions options_;
     float forward_backward_max_error_ = 0.0f;
+    ImagePyramid single_ref_, single_cur_;  // 1-level device images of the GrayImage overload
 };
 
 // basic_klt/optical_flow_basic_klt.h:9-41
@@ -323,6 +378,45 @@ public:
     const Options &options() const { return options_; }
 
 private:
+    // descriptor_matcher.h:45 declares `virtual float ComputeDistance(ref, cur) = 0` and the reference's subclasses override it
+    // (test/test_descriptor_matcher_brief.cpp:33, test_descriptor_matcher_superpoint.cpp:32).  Kept so those subclasses compile
+    // unchanged; the default is the metric the GPU evaluates.  It is never called per pair: Run() spot-checks the override.
+    virtual float ComputeDistance(const DescriptorType &descriptor_ref, const DescriptorType &descriptor_cur) {
+        return TraitsDistance(descriptor_ref, descriptor_cur);
+    }
+    // The metric of DescriptorTraits<T> on the host, in the arithmetic of the demos' ComputeDistance bodies.
+    static float TraitsDistance(const DescriptorType &a, const DescriptorType &b) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        const size_t n = Traits::Size(a);
+        if constexpr (Traits::kBinary) {
+            if (n == 0 || Traits::Size(b) == 0) return 2147483647.0f;  // kMaxInt32 (test_descriptor_matcher_brief.cpp:34-36)
+            int32_t d = 0;
+            for (size_t k = 0; k < n; ++k) d += Traits::At(a, k) != Traits::At(b, k) ? 1 : 0;
+            return static_cast<float>(d);
+        } else {
+            float dot = 0.0f, na = 0.0f, nb = 0.0f;
+            for (size_t k = 0; k < n; ++k) {
+                dot += Traits::At(a, k) * Traits::At(b, k);
+                na += Traits::At(a, k) * Traits::At(a, k);
+                nb += Traits::At(b, k) * Traits::At(b, k);
+            }
+            return 0.5f - dot / std::sqrt(na) / std::sqrt(nb) * 0.5f;  // test_descriptor_matcher_superpoint.cpp:33
+        }
+    }
+    // A subclass's ComputeDistance must be the metric the kernels implement: checked on a few pairs of every call.
+    void CheckOverride(const std::vector<DescriptorType> &ref, const std::vector<DescriptorType> &cur) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        const size_t probes = 4;
+        for (size_t q = 0; q < probes && !ref.empty(); ++q) {
+            const DescriptorType &a = ref[(q * 7919u) % ref.size()], &b = cur[(q * 104729u + q) % cur.size()];
+            const float user = ComputeDistance(a, b), gpu = TraitsDistance(a, b);
+            const bool same = Traits::kBinary ? user == gpu : (std::fabs(user - gpu) <= 1e-4f || (user != user && gpu != gpu));
+            if (!same)
+                throw std::logic_error("feature_tracker_b200: the ComputeDistance override of this DescriptorMatcher subclass is not the metric the GPU "
+                                       "kernels evaluate for its descriptor type (Hamming for boolean containers, 0.5 - 0.5*cos for float vectors); "
+                                       "got " + std::to_string(user) + ", GPU metric gives " + std::to_string(gpu));
+        }
+    }
     static uint32_t PrepareIndex(size_t n_ref, std::vector<int32_t> &idx) {
         if (idx.size() == n_ref) return 0u;
         idx.assign(n_ref, -1);  // descriptor_matcher.h:60-62, 98-100
@@ -339,6 +433,14 @@ private:
         ftk_context *ctx = Device::Get();
         const int32_t n_ref = static_cast<int32_t>(ref.size()), n_cur = static_cast<int32_t>(cur.size());
         const size_t len = Traits::Size(cur[0]);
+        // every descriptor must have the length of cur[0]: the reference's distances index element k of both operands
+        // (test_descriptor_matcher_brief.cpp:39-41), which is undefined for ragged sets -- refused here instead.
+        for (const auto &d : ref)
+            if (Traits::Size(d) != len) return false;
+        for (const auto &d : cur)
+            if (Traits::Size(d) != len) return false;
+        if (len == 0) return false;
+        CheckOverride(ref, cur);
         std::vector<float> pred_flat, pos_flat;
         if (pred) pred_flat = Flatten(*pred), pos_flat = Flatten(*pos);
         int rc;
@@ -346,10 +448,10 @@ private:
             const int32_t words = static_cast<int32_t>((len + 31) / 32);
             std::vector<uint32_t> r(static_cast<size_t>(n_ref) * words, 0u), c(static_cast<size_t>(n_cur) * words, 0u);
             for (int32_t i = 0; i < n_ref; ++i)
-                for (size_t k = 0; k < len && k < Traits::Size(ref[i]); ++k)
+                for (size_t k = 0; k < len; ++k)
                     if (Traits::At(ref[i], k)) r[static_cast<size_t>(i) * words + k / 32] |= 1u << (k % 32);
             for (int32_t j = 0; j < n_cur; ++j)
-                for (size_t k = 0; k < len && k < Traits::Size(cur[j]); ++k)
+                for (size_t k = 0; k < len; ++k)
                     if (Traits::At(cur[j], k)) c[static_cast<size_t>(j) * words + k / 32] |= 1u << (k % 32);
             rc = pred ? ftk_match_hamming_nearby(ctx, r.data(), n_ref, c.data(), n_cur, words, pred_flat.data(), pos_flat.data(),
                                                  options_.kMaxValidPredictRowDistance, options_.kMaxValidPredictColDistance,

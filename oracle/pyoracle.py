@@ -330,6 +330,40 @@ class _CpuChecker:
                                               C.c_int32(max_drow), C.c_int32(max_dcol), C.c_float(max_dist), _i32p(buf), C.c_int32(cnt))
         return ok == 1, buf[:n_ref].copy()
 
+    def match_rows_threaded(self, kind, ref, cur, max_dist, threads=None, pred_uv=None, cur_uv=None, max_drow=0, max_dcol=0):
+        """A full ForceMatch / NearbyMatch of `kind` in {"brief_force", "brief_nearby", "cosine_force", "cosine_nearby"} with the ref rows
+        split over host threads (rows are independent: descriptor_matcher.h:67-76, :103-121, and ctypes drops the GIL), every slice
+        computed by the checker's own single-threaded entry point with an empty index vector on entry.  Returns (ok, idx[n_ref])."""
+        import threading
+        n_ref = len(ref)
+        threads = max(1, min(threads or (os.cpu_count() or 1), n_ref))
+        bounds = [n_ref * t // threads for t in range(threads + 1)]
+        out, oks = np.full(n_ref, -1, np.int32), [True] * threads
+
+        def work(t):
+            a, b = bounds[t], bounds[t + 1]
+            if a == b:
+                return
+            if kind == "brief_force":
+                ok, idx = self.match_brief_force(ref[a:b], cur, max_dist)
+            elif kind == "brief_nearby":
+                ok, idx = self.match_brief_nearby(ref[a:b], cur, pred_uv[a:b], cur_uv, max_drow, max_dcol, max_dist)
+            elif kind == "cosine_force":
+                ok, idx = self.match_cosine_force(ref[a:b], cur, max_dist)
+            elif kind == "cosine_nearby":
+                ok, idx = self.match_cosine_nearby(ref[a:b], cur, pred_uv[a:b], cur_uv, max_drow, max_dcol, max_dist)
+            else:
+                raise ValueError(kind)
+            oks[t] = ok
+            out[a:b] = idx
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return all(oks), out
+
     def match_brief_nearby_uv(self, ref_bits, cur_bits, pred_uv, cur_uv, max_drow, max_dcol, max_dist, status=None):
         ref_bits = np.ascontiguousarray(ref_bits, dtype=np.uint8)
         cur_bits = np.ascontiguousarray(cur_bits, dtype=np.uint8)

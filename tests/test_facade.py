@@ -11,13 +11,84 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def build_facade_test(tmp_path):
-    exe = str(tmp_path / "facade_test")
+def build_cpp(tmp_path, source, name):
+    exe = str(tmp_path / name)
     libdir = os.path.join(ROOT, "feature_tracker_b200")
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"),
-           "-o", exe, "-L" + libdir, "-lftk_b200", "-Wl,-rpath," + libdir]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), source, "-o", exe, "-L" + libdir, "-lftk_b200",
+           "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
     return exe
+
+
+def build_facade_test(tmp_path):
+    return build_cpp(tmp_path, os.path.join(ROOT, "tests", "cpp", "facade_test.cpp"), "facade_test")
+
+
+def build_boundary_test(tmp_path):
+    return build_cpp(tmp_path, os.path.join(ROOT, "tests", "cpp", "boundary_test.cpp"), "boundary_test")
+
+
+def test_boundary_program_compiles(tmp_path):
+    """A DescriptorMatcher<T> subclass overriding the private virtual ComputeDistance (descriptor_matcher.h:45), the GrayImage
+    overload of TrackFeatures (optical_flow.h:41-42) and ImagePyramid::GetImageConst all compile against the facade."""
+    assert os.path.exists(build_boundary_test(tmp_path))
+
+
+REF_BRIEF_TEST = "/root/reference/test/test_descriptor_matcher_brief.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BRIEF_TEST), reason="needs the reference tree (only in the build container)")
+def test_reference_brief_matcher_subclass_compiles_unchanged(tmp_path):
+    """The reference demo's own `class BriefMatcher` (test/test_descriptor_matcher_brief.cpp:27-46, read from the reference tree at
+    test time, never copied into the repo) compiles against the facade header without a change."""
+    lines = open(REF_BRIEF_TEST).read().splitlines()[26:46]
+    assert lines[0].startswith("class BriefMatcher") and "ComputeDistance" in "\n".join(lines) and "override" in "\n".join(lines)
+    src = tmp_path / "ref_subclass.cpp"
+    src.write_text('#include "feature_tracker_b200/feature_tracker.h"\n'
+                   "constexpr int32_t kMaxInt32 = 2147483647;  // Slam_Utility basic_type.h\n"
+                   + "\n".join(lines) + "\n"
+                   "int main() { BriefMatcher m; m.options().kMaxValidDescriptorDistance = 60; return m.options().kMaxValidPredictRowDistance == 40 ? 0 : 1; }\n")
+    exe = build_cpp(tmp_path, str(src), "ref_subclass")
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_boundary_program_matches_oracle(tmp_path, oracle):
+    from feature_tracker_b200 import synthetic as S
+    from oracle import pyoracle as po
+    exe = build_boundary_test(tmp_path)
+    rows, cols, levels, n = 240, 320, 4, 100
+    ref, cur, uv, _ = S.make_pair(rows, cols, n, pair_id=23, border=12)
+    rb, cb, _, _, _ = S.make_brief_sets(180, 210, seed=11, rows=rows, cols=cols)
+    rf, cf = S.make_float_sets(180, 210, seed=12, dim=64)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        f.write(struct.pack("8i", rows, cols, levels, n, rb.shape[0], cb.shape[0], rb.shape[1], rf.shape[1]))
+        for a in (ref, cur, uv, rb, cb, rf, cf):
+            f.write(np.ascontiguousarray(a).tobytes())
+    subprocess.check_call([exe, fin, fout], timeout=120)
+    data = open(fout, "rb").read()
+    off = 0
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(data, dtype=dtype, count=count, offset=off)
+        off += a.nbytes
+        return a
+
+    assert take(np.int32, 1)[0] == 1 and (take(np.int32, rb.shape[0]) == oracle.match_brief_force(rb, cb, 60.0)[1]).all()
+    assert take(np.int32, 1)[0] == 1 and (take(np.int32, rf.shape[0]) == oracle.match_cosine_force(rf, cf, 0.1)[1]).all()
+    assert take(np.int32, 1)[0] == 1, "an override that is not the GPU metric must be refused with std::logic_error"
+    assert take(np.int32, 1)[0] == 0, "ragged descriptor sets must return false"
+    # TrackFeatures(const GrayImage &, const GrayImage &, ...): TrackSingleLevel on level 0 (optical_flow.cpp:28-47)
+    ok = take(np.int32, 1)[0]
+    got_uv, got_st = take(np.float32, 2 * n).reshape(n, 2), take(np.uint8, n)
+    _, exp_uv, exp_st = oracle.klt_track(po.make_params("basic", "inverse", half=6), [ref], [cur], uv, single_level=True)
+    assert ok == 1 and (got_st == exp_st).all() and (got_uv.view(np.uint32) == exp_uv.view(np.uint32)).all()
+    for l, lv in enumerate(oracle.pyramid_build(ref, levels)):
+        r, c = take(np.int32, 2)
+        assert (r, c) == lv.shape and (take(np.uint8, r * c).reshape(r, c) == lv).all(), l
+    assert off == len(data)
 
 
 def test_facade_compiles_and_links(tmp_path):

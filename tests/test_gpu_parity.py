@@ -340,21 +340,6 @@ def test_klt_north_star_config(ctx, oracle):
     assert good.mean() > 0.9 and np.median(np.linalg.norm(got[1][good] - fwd(uv)[good], axis=1)) < 0.3
 
 
-def test_klt_pooled_fold_kernel_opt_in(oracle, monkeypatch):
-    """The CTA-pooled-fold kernel (FTK_ENABLE_POOLED=1, read by ftk_create) stays bit-identical although it is not the default."""
-    monkeypatch.setenv("FTK_ENABLE_POOLED", "1")
-    pooled_ctx = ft.Context(0)
-    ref, cur, uv, _ = S.make_pair(480, 752, 700, pair_id=5)
-    pyr = ft.ImagePyramidBatch(pooled_ctx, 480, 752, 4, 2)
-    pyr.SetRawImages(np.stack([ref, cur]))
-    pyr.CreateImagePyramid()
-    for half in (7, 6):
-        klt = make_tracker(pooled_ctx, "basic", "inverse", half, max_points=1000)
-        got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
-        exp = oracle.klt_track(po.make_params("basic", "inverse", half=half, max_points=1000), oracle.pyramid_build(ref, 4), oracle.pyramid_build(cur, 4), uv)
-        assert_same(f"pooled h={half}", got, exp)
-
-
 def test_klt_lssd_c3_shape(ctx, oracle):
     """BASELINE configs[2] at reduced count: LSSD inverse, 21x21 patches, 1280x720."""
     ref, cur, uv, _ = S.make_pair(720, 1280, 300, pair_id=2)
@@ -514,19 +499,42 @@ def test_cosine_tensor_path_decides_without_fallback(ctx, oracle):
         assert (got == oracle.match_cosine_force(a, b, 0.1)[1]).all(), (n_ref, n_cur, dim)
 
 
-@pytest.mark.parametrize("env", ["FTK_COSINE_2CTA", "FTK_COSINE_ATMEM"])
-def test_cosine_experimental_kernels_opt_in(ctx, oracle, monkeypatch, env):
-    """The two opt-in tensor-core variants -- cta_group::2 (CTA pair) and A-operand-from-TMEM -- stay exact although neither is the
-    default: odd and even numbers of 128-row tiles, partial column tiles, several K."""
-    monkeypatch.setenv(env, "1")
-    for n_ref, n_cur, dim in [(130, 170, 256), (400, 333, 256), (1000, 2100, 128), (257, 700, 64), (33, 40, 100)]:
-        ref, cur = S.make_float_sets(n_ref, n_cur, dim=dim, seed=n_ref + dim)
-        m = ft.CosineMatcher(ctx)
-        m.options().kMaxValidDescriptorDistance = 0.1
-        ok, idx = m.ForceMatch(ref, cur)
-        _, exp = oracle.match_cosine_force(ref, cur, 0.1)
-        assert ok and np.array_equal(idx, exp), (n_ref, n_cur, dim)
-        assert (exp >= 0).sum() > n_ref // 2
+def test_cosine_abnormal_norms_follow_the_reference(ctx, oracle):
+    """Descriptors whose fp32 sum of squares overflows (norm = inf => dot / inf = 0 => d = 0.5), underflows (norm = 0 => NaN or +-inf)
+    or is NaN: the tensor-core path must give the reference's answer for them too (they are evaluated exactly)."""
+    rf, cf = S.make_float_sets(300, 400, dim=256, seed=77)
+    rf, cf = rf.copy(), cf.copy()
+    rf[5] *= np.float32(1e20)     # reference row with an infinite norm
+    cf[7] *= np.float32(1e20)     # current column with an infinite norm: d = 0.5 to every finite row
+    cf[9] *= np.float32(1e-30)    # squares underflow: norm 0
+    rf[11] = 0.0                  # zero descriptor: NaN distances
+    cf[13, 4] = np.nan
+    rf[17] *= np.float32(1e-25)   # tiny but exactly representable scale: norm ~1e-25 (abnormal range, still a well-defined distance)
+    c = ft.CosineMatcher(ctx)
+    for max_dist in (0.1, 0.45, 0.6, 2.0):
+        c.options().kMaxValidDescriptorDistance = max_dist
+        ok, idx = c.ForceMatch(rf, cf)
+        ok_e, exp = oracle.match_cosine_force(rf, cf, max_dist)
+        assert ok == ok_e and np.array_equal(idx, exp), (max_dist, np.nonzero(idx != exp)[0][:10], idx[idx != exp][:10], exp[idx != exp][:10])
+        assert c.last_exact_scan_items() >= 2  # rows 5, 11 and 17 went through the exact scan
+
+
+def test_cosine_two_devices_in_one_process(oracle):
+    """One process, contexts on two GPUs: the tensor-core kernel's shared-memory opt-in is per device.  Skipped on a
+    single-GPU box."""
+    import ctypes as C
+    from feature_tracker_b200.api import lib as ftk_lib
+    try:
+        other = ft.Context(1)
+    except Exception:
+        pytest.skip("needs a second GPU")
+    rf, cf = S.make_float_sets(500, 700, dim=256, seed=78)
+    exp = oracle.match_cosine_force(rf, cf, 0.1)[1]
+    for context in (ft.Context(0), other, ft.Context(0)):
+        c = ft.CosineMatcher(context)
+        c.options().kMaxValidDescriptorDistance = 0.1
+        ok, idx = c.ForceMatch(rf, cf)
+        assert ok and np.array_equal(idx, exp)
 
 
 def test_cosine_nearby_vs_oracle(ctx, oracle):
@@ -839,6 +847,67 @@ def test_cosine_c5_full_size_properties(ctx):
     sample = np.random.default_rng(1).integers(0, 20000, 128)
     d = 0.5 - 0.5 * (rf[sample].astype(np.float64) @ cf.astype(np.float64).T)
     assert (d.argmin(1) == idx[sample]).all() and (d.min(1) < 0.1).all()
+
+
+# ---- BASELINE configs[3] / configs[4] at FULL size, every index against the reference's own code (oracle/_ref) ------------------
+def test_hamming_c4_full_size_bit_exact_vs_reference(ctx, reflib):
+    """BASELINE configs[3]: BRIEF-256 ForceMatch 10k x 10k and NearbyMatch (window 50 / 50), ALL 10 000 indices of each against
+    descriptor_matcher.h:55-79 / :90-124 with the ComputeDistance of test/test_descriptor_matcher_brief.cpp:33-45, compiled in place
+    (ref rows split over the host threads; every slice is the reference's own single-threaded loop)."""
+    rb, cb, pred, pos, _ = S.make_brief_sets(10000, 10000, seed=99)
+    pr, pc = ft.pack_brief(rb), ft.pack_brief(cb)
+    m = brief_matcher(ctx, 60.0, 50, 50)
+    ok, idx = m.ForceMatch(pr, pc)
+    ok_e, exp = reflib.match_rows_threaded("brief_force", rb, cb, 60.0)
+    assert ok and ok_e and (exp >= 0).sum() > 5000
+    assert int((idx != exp).sum()) == 0
+    ok, nidx = m.NearbyMatch(pr, pc, pred, pos)
+    ok_e, nexp = reflib.match_rows_threaded("brief_nearby", rb, cb, 60.0, pred_uv=pred, cur_uv=pos, max_drow=50, max_dcol=50)
+    assert ok and ok_e and (nexp >= 0).sum() > 5000
+    assert int((nidx != nexp).sum()) == 0
+
+
+def test_cosine_c5_full_size_bit_exact_vs_reference(ctx, reflib):
+    """BASELINE configs[4]: float-256 ForceMatch 20k x 20k, ALL 20 000 indices against descriptor_matcher.h:55-79 with the
+    ComputeDistance of test/test_descriptor_matcher_superpoint.cpp:32-34 (sequential fp32 dot / norms), compiled in place."""
+    rf, cf = S.make_float_sets(20000, 20000, seed=5)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.1
+    ok, idx = c.ForceMatch(rf, cf)
+    ok_e, exp = reflib.match_rows_threaded("cosine_force", rf, cf, 0.1)
+    assert ok and ok_e and (exp >= 0).sum() > 10000
+    assert int((idx != exp).sum()) == 0
+
+
+@pytest.mark.parametrize("variant,method", [(v, m) for v in ("basic", "affine", "lssd") for m in ("inverse", "direct", "fast")])
+def test_klt_vs_reference_direct(ctx, reflib, variant, method):
+    """Every tracker family straight against oracle/_ref (the reference's .cpp compiled in place), not via the C restatement:
+    pyramid from the reference's CreateImagePyramid, bit-identical positions, identical status."""
+    ref, cur, uv, _ = S.make_pair(240, 320, 150, pair_id=40, border=10)
+    rl, cl = reflib.pyramid_build(ref, 4), reflib.pyramid_build(cur, 4)
+    klt = make_tracker(ctx, variant, method, 6)
+    pyr = ft.ImagePyramidBatch(ctx, 240, 320, 4, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    for l in range(4):
+        assert (pyr.GetLevel(0, l) == rl[l]).all() and (pyr.GetLevel(1, l) == cl[l]).all()
+    got = klt.TrackFeatures(pyr, pyr, uv, ref_image=0, cur_image=1)
+    exp = reflib.klt_track(po.make_params(variant, method, half=6), rl, cl, uv)
+    assert_same(f"{variant}/{method} vs _ref", got, exp)
+
+
+def test_matchers_vs_reference_direct(ctx, reflib):
+    """ForceMatch / NearbyMatch of both descriptor types straight against oracle/_ref on mid-sized sets."""
+    rb, cb, pred, pos, _ = S.make_brief_sets(1500, 1700, seed=41)
+    m = brief_matcher(ctx, 60.0, 50, 50)
+    assert (m.ForceMatch(ft.pack_brief(rb), ft.pack_brief(cb))[1] == reflib.match_brief_force(rb, cb, 60.0)[1]).all()
+    assert (m.NearbyMatch(ft.pack_brief(rb), ft.pack_brief(cb), pred, pos)[1] == reflib.match_brief_nearby(rb, cb, pred, pos, 50, 50, 60.0)[1]).all()
+    rf, cf = S.make_float_sets(1200, 1300, seed=42)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.1
+    c.options().kMaxValidPredictRowDistance = c.options().kMaxValidPredictColDistance = 50
+    assert (c.ForceMatch(rf, cf)[1] == reflib.match_cosine_force(rf, cf, 0.1)[1]).all()
+    assert (c.NearbyMatch(rf, cf, pred[:1200], pos[:1300])[1] == reflib.match_cosine_nearby(rf, cf, pred[:1200], pos[:1300], 50, 50, 0.1)[1]).all()
 
 
 # ---- feature detection + BRIEF (SURVEY 8(f) rank 1; parity unpinned -- the checker is the oracle's restatement) ---------------
