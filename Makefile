@@ -10,7 +10,13 @@ OBJS := $(SRCS:.cu=.o)
 HDRS := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/ftk_c.h
 
 .PHONY: all clean oracle ref
-all: $(OUT)
+all: $(OUT) tools/microbench tools/c1_latency
+
+# measurement helpers (not part of the product library): pipe-rate microbenchmark for the roofline denominators, C1 latency probe
+tools/microbench: tools/microbench.cu
+	$(NVCC) $(ARCH) -O3 -o $@ $< -lcudart_static -lpthread -ldl -lrt
+tools/c1_latency: tools/c1_latency.cpp include/ftk_c.h include/feature_tracker_b200/feature_tracker.h $(OUT)
+	g++ -std=c++17 -O2 -Wall -Iinclude -o $@ $< -Lfeature_tracker_b200 -lftk_b200 -Wl,-rpath,'$$ORIGIN/../feature_tracker_b200'
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)

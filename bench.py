@@ -34,7 +34,8 @@ sys.path.insert(0, ROOT)
 ROWS, COLS, LEVELS = 480, 752, 4
 PAIRS_PER_GPU = 1000
 FEATURES_PER_PAIR = 2000
-UNIQUE_PAIRS = 8  # synthetic pairs generated; the batch tiles them (distinct HBM addresses, identical content)
+UNIQUE_PAIRS = 32  # distinct synthetic pairs generated (seeded); the batch of 1000 cycles over them (distinct HBM addresses)
+TRAFFIC_JSON = "r2_ncu_traffic.json"  # dram bytes per launch from `ncu --set full` captures of this round's kernels (tools/ncu_summary.py)
 METRIC = "tracked features/sec (4-lvl KLT, 752x480)"
 UNIT = "features/s"
 WORKLOADS = {
@@ -225,14 +226,16 @@ class ClockSampler:
 
 
 
-def run_extras(ctx, L, torch, local_rank, steps):
-    """Secondary workloads of BASELINE.json configs[1..4] (device-resident, CUDA-event timed).  Not the headline."""
+def run_extras(ctx, L, torch, local_rank, steps, peaks, keep):
+    """Secondary workloads of BASELINE.json configs[1..4] (device-resident, CUDA-event timed).  Not the headline.
+    `keep` receives the full-size C4 / C5 results (and their inputs) for the parity check against the reference in cpu_extras."""
     import feature_tracker_b200 as ft
     from feature_tracker_b200 import _capi, synthetic as S
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     vp = C.c_void_p
     out = {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
 
     def timeit(fn, n):
         fn()
@@ -246,7 +249,7 @@ def run_extras(ctx, L, torch, local_rank, steps):
         return e0.elapsed_time(e1) / n
 
     # ---- KLT variants on a reduced batch (100 pairs x 2000 features; 8 pairs for the heavy LSSD shape) ----
-    def klt_case(name, variant, method, half, rows, cols, n_pairs, n_feat, unique=4):
+    def klt_case(name, variant, method, half, rows, cols, n_pairs, n_feat, unique=4, keep_key=None):
         pairs = [S.make_pair(rows, cols, n_feat, pair_id=100 + p) for p in range(unique)]
         imgs = np.stack([pairs[p % unique][0] for p in range(n_pairs)] + [pairs[p % unique][1] for p in range(n_pairs)])
         pyr = ft.ImagePyramidBatch(ctx, rows, cols, LEVELS, 2 * n_pairs)
@@ -273,6 +276,9 @@ def run_extras(ctx, L, torch, local_rank, steps):
         ms = timeit(fn, steps)
         out[name] = {"features_per_s": uv.shape[0] / (ms * 1e-3), "ms": ms, "pairs": n_pairs, "features_per_pair": n_feat,
                      "tracked_fraction": float((d_st.cpu().numpy() == 1).mean())}
+        if keep_key:
+            keep[keep_key] = {"tracker": (variant, method, half), "pairs": pairs, "n_pairs": n_pairs, "n_feat": n_feat, "unique": unique, "ms": ms,
+                              "uv": d_cur.cpu().numpy(), "st": d_st.cpu().numpy()}
         pyr.close()
 
     klt_case("C2_affine_direct_13x13", "affine", "direct", 6, ROWS, COLS, 100, 2000)
@@ -280,7 +286,8 @@ def run_extras(ctx, L, torch, local_rank, steps):
     klt_case("basic_fast_13x13_reference_default", "basic", "fast", 6, ROWS, COLS, 100, 2000)
     klt_case("basic_direct_15x15", "basic", "direct", 7, ROWS, COLS, 100, 2000)
     klt_case("basic_inverse_15x15_100pairs", "basic", "inverse", 7, ROWS, COLS, 100, 2000)
-    klt_case("C3_lssd_inverse_21x21_1280x720", "lssd", "inverse", 10, 720, 1280, 4, 10000, unique=2)
+    # BASELINE configs[2]: 10k features per 1280x720 frame; 20 frame pairs = 200 000 features per launch (~50 waves of feature groups)
+    klt_case("C3_lssd_inverse_21x21_1280x720", "lssd", "inverse", 10, 720, 1280, 20, 10000, unique=2, keep_key="c3")
 
     # ---- C4: BRIEF-256 force 10k x 10k + nearby ----
     rb, cb, pred, pos, truth = S.make_brief_sets(10000, 10000, seed=99)
@@ -295,10 +302,25 @@ def run_extras(ctx, L, torch, local_rank, steps):
     has = truth >= 0
     popc_peak_pairs = 148 * 16 * 1.965e9 / 8  # measured POPC rate: 16 lanes/clk/SM (profiles/r1_microbench_pipe_rates.txt), 8 POPC per 256-bit pair
     out["C4_brief256_force_10k_x_10k"] = {"pairs_per_s": 1e8 / (ms * 1e-3), "ms": ms, "recovered_planted_matches": float((idx[has] == truth[has]).mean()),
-                                          "popc_peak_pairs_per_s": popc_peak_pairs, "frac_of_popc_peak": 1e8 / (ms * 1e-3) / popc_peak_pairs}
+                                          "popc_peak_pairs_per_s": popc_peak_pairs, "frac_of_popc_peak": 1e8 / (ms * 1e-3) / popc_peak_pairs,
+                                          "roofline": {"bound": "integer pipe (POPC)", "achieved": 8e8 / (ms * 1e-3) / 1e12, "peak": popc_peak_pairs * 8 / 1e12,
+                                                       "unit": "T POPC32/s", "frac": 1e8 / (ms * 1e-3) / popc_peak_pairs, "traffic": None,
+                                                       "peak_source": "measured POPC issue rate 16 lanes/clk/SM (tools/microbench.cu, profiles/r1_microbench_pipe_rates.txt) x 148 SM x 1.965 GHz",
+                                                       "algorithmic_work": "8 POPC32 per 256-bit pair x 1e8 pairs (SURVEY 8(d))", "scope": "whole call (all launches)"}}
+    keep["c4_force_idx"] = idx.copy()
+    keep["c4_inputs"] = (rb, cb, pred, pos)
     ms = timeit(lambda: ctx.check(L.ftk_match_hamming_nearby(ctx._h, vp(d_r.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, vp(d_pred.data_ptr()),
                                                              vp(d_pos.data_ptr()), 50, 50, 60.0, vp(d_idx.data_ptr()), fl)), steps * 4)
-    out["C4_brief256_nearby_10k_window50"] = {"ref_rows_per_s": 1e4 / (ms * 1e-3), "ms": ms}
+    keep["c4_nearby_idx"] = d_idx.cpu().numpy().copy()
+    # algorithmic bytes of the candidate search: every cur descriptor inside a ref row's window is read once (32 B descriptor + 8 B position)
+    in_window = int(((np.abs(pos[None, :, 0] - pred[:, None, 0]) <= 50) & (np.abs(pos[None, :, 1] - pred[:, None, 1]) <= 50)).sum())
+    nb_bytes = in_window * 40.0 + 10000 * (32 + 8 + 4)
+    out["C4_brief256_nearby_10k_window50"] = {"ref_rows_per_s": 1e4 / (ms * 1e-3), "ms": ms, "candidate_pairs": in_window,
+                                              "roofline": {"bound": "hbm", "achieved": nb_bytes / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                                           "frac": nb_bytes / (ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                                                           "algorithmic_bytes_per_launch": nb_bytes,
+                                                           "note": "gather latency bound: the whole working set (400 KB) is L2 resident, so HBM is the nominal "
+                                                                   "roofline only; candidates in window x 40 B + 44 B per ref row; whole call (grid build + search)"}}
 
     # ---- 1000 frame pairs x (300 x 300) BRIEF-256 NearbyMatch in one call (the KLT batch's counterpart for descriptor tracking) ----
     n_mp, per = 1000, 300
@@ -321,8 +343,27 @@ def run_extras(ctx, L, torch, local_rank, steps):
     d_idx2 = torch.full((20000,), -1, dtype=torch.int32, device=dev)
     ms = timeit(lambda: ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_rf.data_ptr()), 20000, vp(d_cf.data_ptr()), 20000, 256, 0.1, vp(d_idx2.data_ptr()), fl)), max(2, steps // 2))
     flop = 2.0 * 20000 * 20000 * 256
-    out["C5_float256_force_20k_x_20k"] = {"pairs_per_s": 4e8 / (ms * 1e-3), "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12,
-                                          "matched": int((d_idx2.cpu().numpy() >= 0).sum())}
+    keep["c5_idx"] = d_idx2.cpu().numpy().copy()
+    keep["c5_inputs"] = (rf, cf)
+    bf16_peak = peaks.get("bf16_tflops", 1650.0)
+    c5 = {"pairs_per_s": 4e8 / (ms * 1e-3), "ms": ms, "tflops": flop / (ms * 1e-3) / 1e12, "matched": int((keep["c5_idx"] >= 0).sum()),
+          "exact_scan_rows": int(L.ftk_last_cosine_exact_scan_items(ctx._h)),
+          "roofline_call": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / bf16_peak,
+                            "traffic": None, "scope": "whole ftk_match_cosine_force call: normalise + BF16 copies, tcgen05 GEMM with top-2 epilogue, exact re-rank",
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "fallback"}}
+    if hasattr(L, "ftk_set_profiling"):
+        L.ftk_set_profiling(ctx._h, 1)
+        kms = []
+        for _ in range(max(3, steps // 2)):
+            ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_rf.data_ptr()), 20000, vp(d_cf.data_ptr()), 20000, 256, 0.1, vp(d_idx2.data_ptr()), fl))
+            ctx.synchronize()
+            kms.append(float(L.ftk_last_kernel_ms(ctx._h)))
+        L.ftk_set_profiling(ctx._h, 0)
+        k_ms = statistics.median(kms)
+        c5["roofline"] = {"bound": "tensor", "achieved": flop / (k_ms * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": flop / (k_ms * 1e-3) / 1e12 / bf16_peak,
+                          "traffic": None, "kernel": "CosineTcKernel (tcgen05.mma BF16, TMEM accumulators, TMA operands)", "launch_ms": k_ms,
+                          "algorithmic_flops_per_launch": flop, "scope": "dominant kernel alone, CUDA events around its launch on the library's stream"}
+    out["C5_float256_force_20k_x_20k"] = c5
 
     # ---- direct-method pose tracker: one 6-DoF pose per frame pair from 300 features, 13x13 patches, 4 levels ----
     n_dm, f_dm = 600, 300
@@ -418,12 +459,60 @@ def run_extras(ctx, L, torch, local_rank, steps):
     return out
 
 
-def cpu_extras(out):
+def cpu_extras(out, keep, fp32_peak):
     """Single-thread CPU figures of the reference (oracle/_ref; the C restatement for the mutual scores) on bounded samples of the
-    secondary workloads (2k x 2k sub-problems for the matchers), written next to the GPU figures."""
+    secondary workloads (2k x 2k sub-problems for the matchers), written next to the GPU figures; FULL-SIZE parity of
+    the C4 / C5 results of the timed runs against the reference (ref rows split over the host threads); C3's roofline."""
     from feature_tracker_b200 import synthetic as S
     from oracle import pyoracle as po
     lib_cpu, kind = cpu_checker()
+    cores = os.cpu_count() or 1
+
+    if "c4_inputs" in keep:
+        rb, cb, pred, pos = keep["c4_inputs"]
+        t0 = time.perf_counter()
+        ok, exp = lib_cpu.match_rows_threaded("brief_force", rb, cb, 60.0)
+        dt = time.perf_counter() - t0
+        out["C4_brief256_force_10k_x_10k"]["parity"] = {"checked_rows": 10000, "index_mismatch": int((exp != keep["c4_force_idx"]).sum()), "matched": int((exp >= 0).sum()),
+                                                        "checker": f"oracle/_ref ForceMatch, full 10k x 10k, {cores} host threads, {dt:.1f} s", "kind": kind}
+        ok, exp = lib_cpu.match_rows_threaded("brief_nearby", rb, cb, 60.0, pred_uv=pred, cur_uv=pos, max_drow=50, max_dcol=50)
+        out["C4_brief256_nearby_10k_window50"]["parity"] = {"checked_rows": 10000, "index_mismatch": int((exp != keep["c4_nearby_idx"]).sum()),
+                                                            "matched": int((exp >= 0).sum()), "checker": "oracle/_ref NearbyMatch, full size", "kind": kind}
+    if "c5_inputs" in keep:
+        rf, cf = keep["c5_inputs"]
+        t0 = time.perf_counter()
+        ok, exp = lib_cpu.match_rows_threaded("cosine_force", rf, cf, 0.1)
+        dt = time.perf_counter() - t0
+        out["C5_float256_force_20k_x_20k"]["parity"] = {"checked_rows": 20000, "index_mismatch": int((exp != keep["c5_idx"]).sum()), "matched": int((exp >= 0).sum()),
+                                                        "checker": f"oracle/_ref ForceMatch (sequential fp32 cosine), full 20k x 20k, {cores} host threads, {dt:.1f} s",
+                                                        "kind": kind}
+        out["C5_float256_force_20k_x_20k"]["cpu_reference_all_cores"] = {"pairs_per_s": 4e8 / dt, "cores": cores, "sample": "full 20k x 20k", "kind": kind}
+    if "c3" in keep:
+        c3 = keep["c3"]
+        v, m, h = c3["tracker"]
+        oc = po.OracleLib()
+        params = po.make_params(v, m, half=h, max_points=max(500, c3["n_feat"]))
+        sub = 1500  # oracle iteration trace + parity on the first `sub` features of each unique pair (LSSD 21x21 costs ~1 ms per feature on one core)
+        iters, mism = 0, 0
+        for u in range(c3["unique"]):
+            ref, cur, uv, _ = c3["pairs"][u]
+            cu, st, it = oracle_trace(oc, params, [ref], [cur], [uv[:sub]], 0, sub)
+            iters += int(it.sum())
+            got_uv, got_st = c3["uv"][u * c3["n_feat"]:u * c3["n_feat"] + sub], c3["st"][u * c3["n_feat"]:u * c3["n_feat"] + sub]
+            same = (got_uv.view(np.uint32) == cu.view(np.uint32)) | (np.isnan(got_uv) & np.isnan(cu))
+            mism += int((~same).any(1).sum()) + int((got_st != st).sum())
+        n_total = c3["n_pairs"] * c3["n_feat"]
+        per_feature = iters / (sub * c3["unique"])
+        flops, formula = algorithmic_flops(c3["tracker"], per_feature * n_total, n_total)
+        tfs = flops / (c3["ms"] * 1e-3) / 1e12
+        o = out["C3_lssd_inverse_21x21_1280x720"]
+        o["roofline"] = {"bound": "fp32", "bound_note": "FP32 CUDA-core issue (no FMA: bit-exact arithmetic) + L1/shared bandwidth; neither HBM nor tensor",
+                         "achieved": tfs, "peak": fp32_peak["tflops"], "unit": "TFLOP/s", "frac": tfs / fp32_peak["tflops"], "traffic": None,
+                         "peak_source": fp32_peak["source"], "algorithmic_flops_per_launch": flops, "algorithmic_flops_formula": formula,
+                         "patch_iterations_per_feature": per_feature, "launch_ms": c3["ms"], "features_per_launch": n_total}
+        o["parity"] = {"checked_features": sub * c3["unique"], "mismatch": mism, "checker": "oracle C restatement (bit-identical to oracle/_ref)"}
+        dt1 = clock_once(lambda: lib_cpu.pyramid_and_track(params, LEVELS, c3["pairs"][0][0], c3["pairs"][0][1], c3["pairs"][0][2][:sub]))
+        o["cpu_reference"] = {"features_per_s": sub / dt1, "sample": f"1 frame pair x {sub} features incl. both pyramids, 1 thread", "kind": kind}
 
     def clock(fn):
         t0 = time.perf_counter()
@@ -451,6 +540,54 @@ def cpu_extras(out):
     out["mutual_scores_2048x2048"]["cpu_reference"] = {"ms": dt * 1e3, "sample": "2048 x 2048, 1 thread", "kind": "port"}
 
 
+def pyramid_traffic(n_images):
+    """dram bytes per launch of the pyramid kernel from this round's `ncu --set full` capture at bench scale (2 000 images, far larger
+    than L2), scaled by the image count when the launch differs; None when no capture is committed."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_JSON)))["PyramidKernel"]
+        return (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["images_per_launch"] * n_images
+    except Exception:
+        return None
+
+
+def c1_latency(cpu_lib, kind):
+    """BASELINE configs[0]: one 752x480 frame pair, 200 features, 4 levels, basic KLT kInverse 15x15 -- latency of the reference-facing
+    routes (tools/c1_latency: the C++ facade on ordinary host memory, and the fused C-ABI call on pinned memory; host clock, median of
+    300 calls), the reference's own time for the same pair beside it (test/test_optical_flow.cpp:69-73: pyramids x2 + TrackFeatures)."""
+    import struct
+    import tempfile
+    from feature_tracker_b200 import synthetic as S
+    from oracle import pyoracle as po
+    ref, cur, uv, _ = S.make_pair(ROWS, COLS, 200, pair_id=7)
+    exe = os.path.join(ROOT, "tools", "c1_latency")
+    os.chmod(exe, os.stat(exe).st_mode | 0o111)
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        f.write(struct.pack("5i", ROWS, COLS, LEVELS, len(uv), 7))
+        for a in (ref, cur, uv):
+            f.write(np.ascontiguousarray(a).tobytes())
+        path = f.name
+    try:
+        res = json.loads(subprocess.run([exe, path, "300"], capture_output=True, text=True, timeout=300).stdout.strip().splitlines()[-1])
+    finally:
+        os.unlink(path)
+    out = {"config": "BASELINE configs[0]: 1 frame pair 752x480, 200 features, 4 levels, basic KLT kInverse 15x15; per call: pyramid x2 + TrackFeatures, host buffers in "
+                     "and out; host steady_clock, median of 300 calls after 20 warm-up calls", "gpu": res}
+    if cpu_lib is not None:
+        params = po.make_params("basic", "inverse", half=7, max_points=500)
+        cpu_lib.pyramid_and_track(params, LEVELS, ref, cur, uv)
+        ts = sorted(clock_once(lambda: cpu_lib.pyramid_and_track(params, LEVELS, ref, cur, uv)) for _ in range(15))
+        out["cpu_reference"] = {"ms": ts[len(ts) // 2] * 1e3, "kind": kind, "cores": 1, "sample": "the same pair, median of 15 calls, 1 thread (the reference is single-threaded)"}
+        out["speedup_facade"] = out["cpu_reference"]["ms"] * 1e3 / res["facade_us"]["median"]
+        out["speedup_one_call"] = out["cpu_reference"]["ms"] * 1e3 / res["one_call_us"]["median"]
+    return out
+
+
+def clock_once(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
+
+
 def oracle_trace(oracle, cparams, refs, curs, uvs, u, n_feat):
     """The oracle's results and per-feature patch-iteration counts (SURVEY 8(d) unit) for unique pair u."""
     rl, cl = oracle.pyramid_build(refs[u], LEVELS), oracle.pyramid_build(curs[u], LEVELS)
@@ -469,6 +606,26 @@ def oracle_trace(oracle, cparams, refs, curs, uvs, u, n_feat):
       uvs[u].ctypes.data_as(C.c_void_p), cu.ctypes.data_as(C.c_void_p), C.c_int32(0), st.ctypes.data_as(C.c_void_p), C.c_int32(0), C.c_int32(0),
       it.ctypes.data_as(C.c_void_p))
     return cu, st, it
+
+
+def measured_fp32_peak(device):
+    """The FP32 roofline denominator of the KLT kernels.  They are compiled without FMA contraction (bit-exact arithmetic), so the
+    reachable ceiling is the FADD / FMUL issue rate, measured live by tools/microbench (built by `make`; dependent-free FADD and FMUL
+    streams, 8 independent chains per thread): warp-instructions/clk/SM x 32 lanes x SMs x clock = flop/s (1 flop per instruction)."""
+    exe = os.path.join(ROOT, "tools", "microbench")
+    derived = 148 * 128 * 1.965e9 / 1e12
+    try:
+        os.chmod(exe, os.stat(exe).st_mode | 0o111)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ""))
+        res = json.loads(subprocess.run([exe, "--json", str(device)], capture_output=True, text=True, timeout=120, env=env).stdout.strip().splitlines()[-1])
+        rate = 0.5 * (res["fadd"]["flops_per_s"] + res["fmul"]["flops_per_s"]) / 1e12
+        return {"tflops": rate, "source": f"measured live by tools/microbench: FADD {res['fadd']['warp_instr_per_clk_sm']:.2f} / FMUL "
+                                          f"{res['fmul']['warp_instr_per_clk_sm']:.2f} warp-instr/clk/SM x 32 lanes x {res['sm_count']} SMs (timed, no clock assumed); 1 flop per "
+                                          "instruction because the kernels run without FMA (bit-exact fp32); the nominal FMA peak would be "
+                                          f"{2 * derived:.1f} TFLOP/s", "popc_per_s": res["popc"]["ops_per_s"], "raw": res}
+    except Exception as e:  # noqa: BLE001
+        return {"tflops": derived * 3.75 / 4.0, "source": f"fallback: 3.75 of 4 warp-instr/clk/SM (profiles/r1_microbench_pipe_rates.txt) x 148 SMs x 1.965 GHz; "
+                                                          f"live microbench failed ({e!r})", "popc_per_s": None, "raw": None}
 
 
 def algorithmic_flops(tracker, iters, n_total):
@@ -631,16 +788,15 @@ def run_b200(args):
             h2d = 2 * n_pairs * plane + n_total * 8 + (n_pairs + 1) * 4 + 2 * n_pairs * 4
             d2h = n_track * n_total * 9
             res["e2e"] = {"value": per_step * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                          "ms_per_step": ms_e2e / steps,
+                          "ms_per_step": ms_e2e / steps, "h2d_gbs_per_rank": h2d / (ms_e2e / steps * 1e-3) / 1e9,
                           "api": "ftk_track_image_pairs_multi: one call for all trackers of the workload (pinned host images + features in, host results "
                                  "of every tracker out; H2D of chunk k+1 overlaps compute of chunk k)"}
             return res
 
-        def rooflines(self, res, oracle):
+        def rooflines(self, res, oracle, fp32_peak):
             """Per tracker: algorithmic flops (oracle iteration trace) / kernel time, against the derived fp32 issue peak; plus the
             at-scale parity spot check of the timed run's outputs against the oracle."""
             from oracle import pyoracle as po
-            fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
             out, parity = {}, {"pairs": 0, "status_mismatch": 0, "position_bits_mismatch": 0}
             for i, t in enumerate(self.trackers):
                 cparams = po.make_params(t[0], t[1], half=t[2], max_points=max(500, n_feat))
@@ -663,15 +819,15 @@ def run_b200(args):
                 try:  # dram bytes of one ncu --set full capture of this kernel, scaled from its 200 000-feature launch to this launch
                     key = {("basic", "inverse"): "BasicInverseFastKernel", ("affine", "direct"): "KltKernel_affine_direct",
                            ("affine", "fast"): "KltKernel_affine_fast"}[(t[0], t[1])]
-                    tr = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))[key]
+                    tr = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_JSON)))[key]
                     traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["features_per_launch"] * n_total
                 except Exception:
                     pass
                 ms_k = res["kernel_ms"][f"klt_{t[0]}_{t[1]}"]
                 tfs = flops / (ms_k * 1e-3) / 1e12
-                out[f"{t[0]}_{t[1]}"] = {"bound": "fp32", "bound_note": "FP32 CUDA-core issue + L1/shared bandwidth; neither HBM nor tensor (SURVEY 8(d))", "achieved": tfs, "peak": fp32_peak, "unit": "TFLOP/s",
-                                         "frac": tfs / fp32_peak, "traffic": traffic,
-                                         "peak_source": "derived 148 SM x 128 lanes x 2 x 1.965 GHz (no measured fp32 figure in MEASURED_PEAKS.json)",
+                out[f"{t[0]}_{t[1]}"] = {"bound": "fp32", "bound_note": "FP32 CUDA-core issue + L1/shared bandwidth; neither HBM nor tensor (SURVEY 8(d))", "achieved": tfs,
+                                         "peak": fp32_peak["tflops"], "unit": "TFLOP/s", "frac": tfs / fp32_peak["tflops"], "traffic": traffic,
+                                         "peak_source": fp32_peak["source"],
                                          "algorithmic_flops_per_launch": flops, "algorithmic_flops_formula": formula,
                                          "patch_iterations_per_feature": iters / n_total, "launch_ms": ms_k,
                                          "kernel": "BasicInverseFastKernel<15,15>" if t == ("basic", "inverse", 7) else f"KltKernel ({tracker_name(t)})"}
@@ -700,7 +856,8 @@ def run_b200(args):
             step_e2e_sequence()
         ms_seq, _ = timed(step_e2e_sequence, args.steps)
         north_res["e2e_sequence"] = {"value": n_total * world * args.steps / (ms_seq * 1e-3), "unit": UNIT, "ms_per_step": ms_seq / args.steps,
-                                     "h2d_bytes_per_step": ((n_pairs + 1) * plane + n_total * 8) * world,
+                                     "h2d_bytes_per_step": ((n_pairs + 1) * plane + n_total * 8) * world, "d2h_bytes_per_step": n_total * 9 * world,
+                                     "h2d_gbs_per_rank": ((n_pairs + 1) * plane + n_total * 8) / (ms_seq / args.steps * 1e-3) / 1e9,
                                      "tracked_fraction": float((host_status.numpy() == 1).mean()),
                                      "api": "ftk_track_image_sequence (n_pairs + 1 host frames, pair k = frame k -> k+1; every frame uploaded and its pyramid "
                                             "built once)"}
@@ -730,9 +887,10 @@ def run_b200(args):
         "tracked_fraction": res["tracked_fraction"],
         "kernel_ms": res["kernel_ms"],
         "roofline_pyramid": {"bound": "hbm", "achieved": pyr_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pyr_gbs / hbm_peak,
-                             "traffic": (72.85e6 + 6.28e6) / 200 * 2 * n_pairs,  # ncu dram bytes per image (profiles/r1_ncu_traffic.json) x images
-                             "peak_source": hbm_src, "algorithmic_bytes_per_launch": pyr_bytes},
+                             "traffic": pyramid_traffic(2 * n_pairs), "peak_source": hbm_src, "algorithmic_bytes_per_launch": pyr_bytes},
     }
+    fp32_peak = measured_fp32_peak(local_rank)
+    line["fp32_issue_peak"] = {"tflops": fp32_peak["tflops"], "source": fp32_peak["source"]}
 
     if not args.no_cpu_baseline:
         from oracle import pyoracle as po
@@ -748,14 +906,14 @@ def run_b200(args):
                                           "tracker object per host thread",
                                 "single_thread_value": nf1 / dt1}
         oracle = po.OracleLib()
-        roofs, parity = head.rooflines(res, oracle)
+        roofs, parity = head.rooflines(res, oracle, fp32_peak)
         # the dominant kernel of the step = the tracker kernel with the longest launch
         dominant = max(roofs, key=lambda k: roofs[k]["launch_ms"])
         line["roofline"] = roofs[dominant]
         line["roofline_by_tracker"] = roofs
         line["parity_check"] = parity
         if north is not None:
-            nroofs, nparity = north.rooflines(north_res, oracle)
+            nroofs, nparity = north.rooflines(north_res, oracle, fp32_peak)
             dt, nf = cpu_track_sample(lib_cpu, cpu_params(WORKLOADS["north_star"], n_feat), refs, curs, uvs, sample_pairs, cores)
             north_res["roofline"] = nroofs["basic_inverse"]
             north_res["parity_check"] = nparity
@@ -765,13 +923,26 @@ def run_b200(args):
         north_res["config"] = "BASELINE north_star target: basic KLT kInverse 15x15, 4 levels, the same 1000 x 2000 batch; target >= 1e8 features/s/GPU"
         north_res["unit"] = UNIT
         line["north_star"] = north_res
+        # a compact copy inside `e2e` (the scaling harness keeps that object whole): whole-job north-star throughput at this N
+        line["e2e"]["north_star"] = {
+            "tracker": "basic KLT kInverse 15x15", "device_resident_value": north_res["value"],
+            "e2e_sequence_value": north_res["e2e_sequence"]["value"], "e2e_sequence_h2d_gbs_per_rank": north_res["e2e_sequence"]["h2d_gbs_per_rank"],
+            "e2e_pairs_value": north_res["e2e"]["value"], "e2e_pairs_h2d_gbs_per_rank": north_res["e2e"]["h2d_gbs_per_rank"], "unit": UNIT,
+            "note": "sequence = ftk_track_image_sequence (every frame uploaded once: the VIO use); pairs = ftk_track_image_pairs_multi (both frames of every pair uploaded)"}
     if not args.no_extras and world == 1:
         try:
-            line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps)
+            ctx.synchronize()
+            line["c1_latency"] = c1_latency(*(cpu_checker() if not args.no_cpu_baseline else (None, None)))
+        except Exception as e:  # noqa: BLE001
+            line["c1_latency"] = {"error": repr(e)}
+        try:
+            keep = {}
+            line["other_workloads"] = run_extras(ctx, L, torch, local_rank, args.steps, peaks, keep)
             if not args.no_cpu_baseline:
-                cpu_extras(line["other_workloads"])
+                cpu_extras(line["other_workloads"], keep, fp32_peak)
         except Exception as e:  # the headline must survive a failure in the extras
-            line["other_workloads"] = {"error": repr(e)}
+            import traceback
+            line["other_workloads"] = {"error": repr(e), "traceback": traceback.format_exc()[-1500:]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libftk_b200.so")
+# FTK_LIB_PATH: A/B measurements of alternative builds of the same library (never a different implementation)
+LIB_PATH = os.environ.get("FTK_LIB_PATH") or os.path.join(_HERE, "libftk_b200.so")
 
 OK = 0
 ERR_INVALID_ARGUMENT = -1
@@ -26,7 +27,7 @@ FLAG_NO_INDEX_INPUT = 16
 # Every symbol include/ftk_c.h declares (tests check that the library exports all of them).
 EXPORTED_SYMBOLS = [
     "ftk_abi_version", "ftk_klt_params_default", "ftk_create", "ftk_destroy", "ftk_last_error", "ftk_synchronize", "ftk_stream",
-    "ftk_kernel_launches", "ftk_pyramid_create", "ftk_pyramid_destroy", "ftk_pyramid_set_images", "ftk_pyramid_build",
+    "ftk_kernel_launches", "ftk_alloc_pinned", "ftk_free_pinned", "ftk_set_profiling", "ftk_last_kernel_ms", "ftk_pyramid_create", "ftk_pyramid_destroy", "ftk_pyramid_set_images", "ftk_pyramid_build",
     "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
     "ftk_track_image_pairs", "ftk_track_image_pairs_multi", "ftk_track_image_sequence",
     "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_hamming_pairs", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
@@ -95,6 +96,10 @@ def load_library():
         "ftk_synchronize": (C.c_int, [vp]),
         "ftk_stream": (vp, [vp]),
         "ftk_kernel_launches": (C.c_uint64, [vp]),
+        "ftk_alloc_pinned": (C.c_int, [C.c_size_t, P(vp)]),
+        "ftk_free_pinned": (None, [vp]),
+        "ftk_set_profiling": (C.c_int, [vp, C.c_int]),
+        "ftk_last_kernel_ms": (C.c_float, [vp]),
         "ftk_pyramid_create": (C.c_int, [vp, i32, i32, i32, i32, P(vp)]),
         "ftk_pyramid_destroy": (None, [vp, vp]),
         "ftk_pyramid_set_images": (C.c_int, [vp, vp, i32, i32, vp, u32]),

@@ -527,6 +527,18 @@ SuperpointMatcher = CosineMatcher
 DiskMatcher = CosineMatcher
 
 
+def nn_match_pairs_host(matches, n_ref, n_cur):
+    """The fused-model branch of NNFeatureMatcher::Match (nn_feature_matcher.cpp:160-178): matches [n, 2] int64 (idx_ref, idx_cur)
+    -> index_pairs_in_cur [n_ref]; pairs with an index outside either set are ignored, later pairs overwrite earlier ones.  Host
+    code, as in the reference: the network already produced at most kMaxNumberOfMatches pairs."""
+    idx = np.full(n_ref, -1, np.int32)
+    for i_ref, i_cur in np.asarray(matches, np.int64).reshape(-1, 2):
+        # :169 bounds idx_ref by matched_pixel_uv_cur.size(), which is pixel_uv_cur.size() (:158)
+        if 0 <= i_ref < min(n_ref, n_cur) and 0 <= i_cur < n_cur:
+            idx[i_ref] = i_cur
+    return idx
+
+
 class NNFeatureMatcherOptions:
     """nn_feature_matcher.h:23-27 (the fields the score-matrix post-processing uses)."""
 

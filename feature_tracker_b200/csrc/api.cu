@@ -185,6 +185,8 @@ void ftk_destroy(ftk_context *ctx) {
         if (ctx->chunk_stream[b]) cudaStreamDestroy(ctx->chunk_stream[b]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int q = 0; q < 2; ++q)
+        if (ctx->ev_prof[q]) cudaEventDestroy(ctx->ev_prof[q]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -199,6 +201,37 @@ int ftk_synchronize(ftk_context *ctx) {
 }
 
 void *ftk_stream(ftk_context *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+int ftk_alloc_pinned(size_t bytes, void **out) {
+    if (!out) return FTK_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? FTK_OK : FTK_ERR_CUDA;
+}
+
+void ftk_free_pinned(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+int ftk_set_profiling(ftk_context *ctx, int enabled) {
+    if (!ctx) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    if (enabled && !ctx->ev_prof[0]) {
+        FTK_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev_prof[0]));
+        FTK_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev_prof[1]));
+    }
+    ctx->profiling = enabled != 0;
+    ctx->prof_recorded = false;
+    return FTK_OK;
+}
+
+float ftk_last_kernel_ms(ftk_context *ctx) {
+    if (!ctx || !ctx->prof_recorded) return -1.0f;
+    DeviceGuard guard(ctx->device);
+    float ms = -1.0f;
+    if (cudaEventSynchronize(ctx->ev_prof[1]) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_prof[0], ctx->ev_prof[1]) != cudaSuccess) return -1.0f;
+    return ms;
+}
 
 uint64_t ftk_kernel_launches(const ftk_context *ctx) { return ctx ? ctx->launches : 0; }
 

@@ -56,6 +56,9 @@ struct ftk_context {
     int stage_rows = 0, stage_cols = 0, stage_levels = 0, stage_pairs = 0;
     std::string error;
     uint64_t launches = 0;
+    bool profiling = false;                        // ftk_set_profiling: events around the dominant kernel of a call
+    cudaEvent_t ev_prof[2] = {nullptr, nullptr};
+    bool prof_recorded = false;
     int sm_count = 0;
     const int *d_last_scan_items = nullptr;  // device counter of the last tensor-core cosine match (nullptr: path not used)
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
@@ -72,6 +75,16 @@ struct ftk_context {
 namespace ftk {
 
 int SetError(ftk_context *ctx, int code, const char *fmt, ...);
+// ftk_set_profiling: bracket the dominant kernel of a call (no-ops unless profiling is enabled)
+inline void ProfBegin(ftk_context *ctx) {
+    if (ctx->profiling && ctx->ev_prof[0]) cudaEventRecord(ctx->ev_prof[0], ctx->stream);
+}
+inline void ProfEnd(ftk_context *ctx) {
+    if (ctx->profiling && ctx->ev_prof[1]) {
+        cudaEventRecord(ctx->ev_prof[1], ctx->stream);
+        ctx->prof_recorded = true;
+    }
+}
 int EnsureDevice(ftk_context *ctx, FtkBuffer &buf, size_t bytes);
 
 #define FTK_CUDA_CHECK(ctx, expr)                                                                              \

@@ -15,6 +15,8 @@
 // sequential CPU loops while K accumulators x (32/G) features advance per warp instruction.
 // This file is the generic ("literal") implementation for every variant/method and any patch size; the
 // specialised kernels for the head-line configurations live in klt_basic_fastpath.cu.
+#include <cstdlib>
+
 #include "klt_device.cuh"
 
 namespace ftk {
@@ -39,12 +41,14 @@ struct Scratch {
     float *dx, *dy;    // ref gradients (fast methods)
     float *curp;       // cur patch (lssd fast)
     float *hoist;      // lssd inverse: per-level reference gradients / samples + this iteration's cur samples: 4 x p_floats
+    Ldlt6Shared *ldlt; // affine: normal equations + factors of the cooperative 6x6 LDLT
+    LdltShared<3> *ldlt3;  // lssd: the same for its 3x3 system (aliases the same scratch region)
     uint8_t *exv;      // ex patch validity
     uint8_t *curv;     // cur patch validity (lssd fast)
 };
 
 struct SmemLayout {
-    int term_floats, ex_floats, p_floats, curp_floats, hoist_floats, exv_bytes, curv_bytes, total_bytes;
+    int term_floats, ex_floats, p_floats, curp_floats, hoist_floats, ldlt_floats, exv_bytes, curv_bytes, total_bytes;
 };
 
 __host__ __device__ inline int RoundUp(int v, int m) { return (v + m - 1) / m * m; }
@@ -69,7 +73,8 @@ __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G,
         pair_floats = 0;
         l.hoist_floats = (method == kInverse ? 3 : 1) * RoundUp(geo.psize, 4);  // per level: [fx, fy,] reference centre sample
     }
-    l.total_bytes = 4 * (l.term_floats + l.ex_floats + pair_floats + l.curp_floats + l.hoist_floats) + l.exv_bytes + l.curv_bytes;
+    l.ldlt_floats = variant == FTK_VARIANT_AFFINE ? RoundUp(kLdlt6Floats, 4) : (variant == FTK_VARIANT_LSSD ? RoundUp(kLdlt3Floats, 4) : 0);
+    l.total_bytes = 4 * (l.term_floats + l.ex_floats + pair_floats + l.curp_floats + l.hoist_floats + l.ldlt_floats) + l.exv_bytes + l.curv_bytes;
     l.total_bytes = RoundUp(l.total_bytes, 16);
     // Groups of one warp must start on different banks: make the group stride (in words) congruent to G modulo 32.
     if (G < 32)
@@ -92,6 +97,9 @@ __device__ __forceinline__ Scratch CarveScratch(unsigned char *base, const SmemL
     f += l.curp_floats;
     s.hoist = f;
     f += l.hoist_floats;
+    s.ldlt = reinterpret_cast<Ldlt6Shared *>(f);
+    s.ldlt3 = reinterpret_cast<LdltShared<3> *>(f);
+    f += l.ldlt_floats;
     uint8_t *b = reinterpret_cast<uint8_t *>(f);
     s.exv = b;
     b += l.exv_bytes;
@@ -120,6 +128,7 @@ struct Ctx {
     Scratch s;
     Geometry geo;
     const ftk_klt_params *p;
+    int ldlt_dst0, ldlt_dst1;  // affine: float offsets inside Ldlt6Shared of chain `lane` and chain `G + lane` (-1: none)
 };
 
 // ---- shared pieces of the fast methods ---------------------------------------------------------------------------
@@ -425,14 +434,26 @@ __device__ __forceinline__ void AffineBiasTerms(float x, float y, float dx, floa
     t[5] = -fmul(dt, dy);
 }
 
+// Where chain q of the affine normal equations goes inside Ldlt6Shared (as a float offset): Hessian entry (row, col) with
+// row <= col is stored at the lower-triangle position a[col][row]; chains 21..26 are the right-hand side b[0..5].
+__device__ __forceinline__ int AffineChainSlot(int q) {
+    if (q < 0 || q >= 27) return -1;
+    if (q >= 21) return 36 + 8 + (q - 21);
+    return kAffCol[q] * 6 + kAffRow[q];
+}
+
+// Chain lanes store their accumulators into the LDLT scratch (n_chains = 27: Hessian + bias, 21: Hessian, 6: bias only, which then
+// sit in chains 0..5).
 template <int G>
-__device__ __forceinline__ void AffineGatherHessian(const Ctx<G> &c, float (&H)[6][6]) {
-#pragma unroll
-    for (int q = 0; q < 21; ++q) {
-        const float v = c.ch.value(c.g, q);
-        H[kAffRow[q]][kAffCol[q]] = v;
-        H[kAffCol[q]][kAffRow[q]] = v;
+__device__ __forceinline__ void AffineScatterChains(Ctx<G> &c, int n_chains) {
+    float *dst = reinterpret_cast<float *>(c.s.ldlt);
+    if (n_chains == 6) {
+        if (c.g.lane < 6) c.s.ldlt->b[c.g.lane] = c.ch.acc;
+    } else {
+        if (c.g.lane < n_chains && c.ldlt_dst0 >= 0) dst[c.ldlt_dst0] = c.ch.acc;
+        if (G + c.g.lane < n_chains && c.ldlt_dst1 >= 0) dst[c.ldlt_dst1] = c.ch.acc_hi;
     }
+    c.g.sync();
 }
 
 // The reference samples of affine_klt.cpp:131-273 do not depend on the iteration: the centre sample I_ref(row_i, col_i)
@@ -473,7 +494,7 @@ __device__ unsigned long long AffineHoistRef(Ctx<G> &c, const Img &ref, float re
 
 // affine_klt.cpp:131-273 ConstructIncrementalFunction: 21 Hessian + 6 bias chains, on top of the hoisted reference samples.
 template <int METHOD, int G>
-__device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, unsigned long long ref_bits, float (&H)[6][6], float (&b)[6]) {
+__device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, unsigned long long ref_bits) {
     static_assert(2 * G >= 27, "affine needs 27 chains, at most two per lane");
     const int pf = RoundUp(c.geo.psize, 4);
     const float *hv4 = c.s.hoist, *hfx = c.s.hoist + pf, *hfy = c.s.hoist + 2 * pf;
@@ -510,9 +531,7 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
         c.ch.template fold_wide<27>(c.g);
         w.next();
     }
-    AffineGatherHessian(c, H);
-#pragma unroll
-    for (int q = 0; q < 6; ++q) b[q] = c.ch.value(c.g, 21 + q);
+    AffineScatterChains(c, 27);  // Hessian (lower triangle) and bias -> the LDLT scratch
     return valid;
 }
 
@@ -530,9 +549,10 @@ template <int METHOD, int G>
 __device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
     const unsigned long long ref_bits = AffineHoistRef<METHOD, G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
-        float H[6][6], b[6], z[6];
-        if (AffineConstruct<METHOD, G>(c, cur, s, ref_bits, H, b) == 0) break;
-        LdltSolve<6>(H, b, z);
+        float z[6];
+        if (AffineConstruct<METHOD, G>(c, cur, s, ref_bits) == 0) break;
+        Ldlt6FactorShared(c.g, *c.s.ldlt);  // hessian.ldlt().solve(bias), affine_klt.cpp:103
+        Ldlt6SolveShared(c.g, *c.s.ldlt, z);
         const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
         const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);
         if (IsNan(v0) || IsNan(v1)) {
@@ -581,13 +601,16 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
         c.ch.template fold_wide<21>(c.g);
         w.next();
     }
-    float H[6][6];
-    AffineGatherHessian(c, H);
-    H[1][2] = H[2][1] = H[0][3];
-    H[1][4] = H[4][1] = H[0][5];
-    H[3][4] = H[4][3] = H[2][3];
-    LdltFactors<6> factors;  // the Hessian is fixed for the level: factorise once (identical factors every iteration)
-    LdltFactor<6>(H, factors);
+    AffineScatterChains(c, 21);
+    if (c.g.lane == 0) {
+        // affine_klt_fast.cpp:127-135: (1,2), (1,4), (3,4) are copies of (0,3), (0,5), (2,3); lower-triangle positions a[col][row]
+        float *a = c.s.ldlt->a;
+        a[2 * 6 + 1] = a[3 * 6 + 0];
+        a[4 * 6 + 1] = a[5 * 6 + 0];
+        a[4 * 6 + 3] = a[3 * 6 + 2];
+    }
+    c.g.sync();
+    Ldlt6FactorShared(c.g, *c.s.ldlt);  // the Hessian is fixed for the level: factorise once (identical factors every iteration)
 
     float last_squared_step = INFINITY;
     uint32_t large_step_cnt = 0;
@@ -623,10 +646,9 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
             w.next();
         }
         if (valid == 0) break;
-        float b[6], z[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) b[q] = c.g.get(c.ch.acc, q);
-        LdltSolveFactored<6>(factors, b, z);
+        float z[6];
+        AffineScatterChains(c, 6);
+        Ldlt6SolveShared(c.g, *c.s.ldlt, z);
         bool any_nan = false;
 #pragma unroll
         for (int q = 0; q < 6; ++q) any_nan = any_nan || IsNan(z[q]);
@@ -684,21 +706,26 @@ __device__ __forceinline__ void LssdTerms(const float (&J)[3], float residual, f
     t[8] = -fmul(J[2], residual);
 }
 
+// Chains 0..5 = Hessian (0,0) (0,1) (0,2) (1,1) (1,2) (2,2), chains 6..8 = bias: the owning lanes store them into the LDLT scratch
+// (lower-triangle position a[col][row]), then the 3 x 3 system is solved cooperatively (hessian.ldlt().solve(bias)).
 template <int G>
-__device__ __forceinline__ void LssdGather(const Ctx<G> &c, float (&H)[3][3], float (&b)[3]) {
-    const float h00 = c.g.get(c.ch.acc, 0), h01 = c.g.get(c.ch.acc, 1), h02 = c.g.get(c.ch.acc, 2);
-    const float h11 = c.g.get(c.ch.acc, 3), h12 = c.g.get(c.ch.acc, 4), h22 = c.g.get(c.ch.acc, 5);
-    H[0][0] = h00, H[0][1] = h01, H[0][2] = h02;
-    H[1][0] = h01, H[1][1] = h11, H[1][2] = h12;
-    H[2][0] = h02, H[2][1] = h12, H[2][2] = h22;
-    b[0] = c.g.get(c.ch.acc, 6);
-    b[1] = c.g.get(c.ch.acc, 7);
-    b[2] = c.g.get(c.ch.acc, 8);
+__device__ __forceinline__ void LssdSolve(Ctx<G> &c, float (&v)[3]) {
+    LdltShared<3> &s = *c.s.ldlt3;
+    const int lane = c.g.lane;
+    if (lane < 6) {
+        const int slot = lane == 0 ? 0 : (lane == 1 ? 3 : (lane == 2 ? 6 : (lane == 3 ? 4 : (lane == 4 ? 7 : 8))));
+        s.a[slot] = c.ch.acc;
+    } else if (lane < 9) {
+        s.b[lane - 6] = c.ch.acc;
+    }
+    c.g.sync();
+    LdltFactorShared<3, G>(c.g, s);
+    LdltSolveShared<3, G>(c.g, s, v);
 }
 
 // lssd_klt.cpp:127-250 ConstructIncrementalFunction: pass 1 = validity + patch means (2 chains), pass 2 = 9 chains.
 template <int METHOD, int G>
-__device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const LssdState &s, float (&H)[3][3], float (&b)[3]) {
+__device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const LssdState &s) {
     int valid = 0;
     unsigned long long ok_bits = 0ull;  // bit q: this lane's pixel of chunk q is valid (psize <= 64 * G, checked on the host)
     c.ch.reset();
@@ -770,7 +797,6 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
         c.ch.template fold<9>(c.g);
         w.next();
     }
-    LssdGather(c, H, b);
     return valid;
 }
 
@@ -805,8 +831,7 @@ __device__ unsigned long long LssdHoistRef(Ctx<G> &c, const Img &ref, float ref_
 
 // lssd_klt.cpp:127-250 ConstructIncrementalFunction, kInverse, on top of the hoisted reference samples.
 template <int G>
-__device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ref_bits,
-                                    float (&H)[3][3], float (&b)[3]) {
+__device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ref_bits) {
     const int pf = RoundUp(c.geo.psize, 4);
     const float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf;
     float *hv5 = c.s.hoist + 3 * pf;
@@ -867,7 +892,6 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
         c.ch.template fold<9>(c.g);
         w.next();
     }
-    LssdGather(c, H, b);
     return valid;
 }
 
@@ -877,12 +901,12 @@ __device__ void LssdTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float re
     unsigned long long ref_bits = 0ull;
     if constexpr (METHOD == kInverse) ref_bits = LssdHoistRef<G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
-        float H[3][3], b[3], v[3];
+        float v[3];
         int valid;
-        if constexpr (METHOD == kInverse) valid = LssdConstructHoisted<G>(c, cur, ref_x, ref_y, s, ref_bits, H, b);
-        else valid = LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s, H, b);
+        if constexpr (METHOD == kInverse) valid = LssdConstructHoisted<G>(c, cur, ref_x, ref_y, s, ref_bits);
+        else valid = LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s);
         if (valid == 0) break;
-        LdltSolve<3>(H, b, v);
+        LssdSolve(c, v);
         if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
             status = FTK_STATUS_NUMERIC_ERROR;
             break;
@@ -997,9 +1021,8 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
             w.next();
         }
         if (valid == 0) break;
-        float H[3][3], b[3], v[3];
-        LssdGather(c, H, b);
-        LdltSolve<3>(H, b, v);
+        float v[3];
+        LssdSolve(c, v);
         if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
             status = FTK_STATUS_NUMERIC_ERROR;
             break;
@@ -1038,6 +1061,11 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE ? 6 : 7) Kl
     c.walk.col = c.g.lane - c.walk.row * c.geo.pc;
     c.walk.step_row = G / c.geo.pc;
     c.walk.step_col = G - c.walk.step_row * c.geo.pc;
+    c.ldlt_dst0 = c.ldlt_dst1 = -1;
+    if constexpr (VARIANT == FTK_VARIANT_AFFINE) {
+        c.ldlt_dst0 = AffineChainSlot(c.g.lane);
+        c.ldlt_dst1 = AffineChainSlot(G + c.g.lane);
+    }
 
     const int pair = a.feat_pair[f];
     const int local = f - a.feat_offsets[pair];
@@ -1183,7 +1211,16 @@ int LaunchFeaturePairs(ftk_context *ctx, const int *d_offsets, int n_pairs, int 
     return FTK_OK;
 }
 
+static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a);
+
 int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
+    ProfBegin(ctx);
+    const int rc = LaunchKltTrackImpl(ctx, a);
+    ProfEnd(ctx);
+    return rc;
+}
+
+static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
     Geometry geo;
     geo.hr = a.p.patch_row_half;
     geo.hc = a.p.patch_col_half;
@@ -1207,6 +1244,7 @@ int LaunchKltTrack(ftk_context *ctx, const KltLaunch &a) {
             // kDirect with 16 lanes per feature: two features share a warp's 6x6 LDLT instructions and 13x13 patches fill 11 chunks of
             // 16 to 96 % (measured 47.4 ms vs 50.9 ms per 2 M features; kFast is slower that way, 49.4 ms vs 43.9 ms)
             if (geo.psize <= 16 * 64 && a.p.method == kDirect) return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo);
+            if (geo.psize <= 16 * 64 && getenv("FTK_TMP_AFFINE_G16")) return LaunchMethod<FTK_VARIANT_AFFINE, 16>(ctx, a, geo);  // TEMPORARY measurement switch
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_LSSD:

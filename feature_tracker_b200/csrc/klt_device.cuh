@@ -332,6 +332,132 @@ __device__ __forceinline__ void LdltSolveFactored(const LdltFactors<N> &f, const
     }
 }
 
+// ---- cooperative LDLT<N> in shared memory (affine: N = 6, LSSD: N = 3) ------------------------------------------------
+// The register version above indexes its arrays with the data-dependent pivot, which puts them in local memory (the affine
+// kernels carried ~780 LDL/STL) and makes every lane of a group repeat ~1300 instructions per 6 x 6 solve.  Here the lower
+// triangle lives in the group's shared scratch and lane i owns row i: pivot search, symmetric swap, column update and scaling of
+// one elimination step run on N lanes at once.  Every matrix element goes through exactly the operations of LdltFactor, in the
+// same order, so factors, transpositions and solutions are bit-identical to it (tests: the trackers against the oracle).
+template <int N>
+struct LdltShared {
+    float a[N * N];  // row-major, lower triangle + diagonal used
+    int perm[8];     // x_permuted[i] = b[perm[i]] (the forward transpositions applied to the identity)
+    float b[8];      // right-hand side, written by the lanes that own the bias chains
+    float z[8];      // solution after the backward transpositions
+};
+using Ldlt6Shared = LdltShared<6>;
+constexpr int kLdlt6Floats = 36 + 8 + 8 + 8;
+constexpr int kLdlt3Floats = 9 + 8 + 8 + 8;
+
+// Factorises s.a in place; fills s.perm.  All lanes of the group call (uniform control flow inside the group).
+template <int N, int G>
+__device__ __forceinline__ void LdltFactorShared(const Group<G> &g, LdltShared<N> &s) {
+    float *a = s.a;
+    const int lane = g.lane;
+    int tr[N];
+    bool zero_diag = false;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        if (zero_diag) {
+            tr[k] = k;
+            continue;
+        }
+        int p = k;
+        float best = fabsf(a[k * N + k]);
+#pragma unroll
+        for (int i = k + 1; i < N; ++i) {
+            const float v = fabsf(a[i * N + i]);
+            if (v > best) {
+                best = v;
+                p = i;
+            }
+        }
+        tr[k] = p;
+        g.sync();  // every lane has read the diagonal
+        {
+            // symmetric exchange of rows / columns k and p of the lower triangle: one element pair per lane (p == k: no-ops)
+            int ia = -1, ib = -1;
+            if (lane < k) ia = k * N + lane, ib = p * N + lane;
+            else if (lane == k) ia = k * N + k, ib = p * N + p;
+            else if (lane < p) ia = lane * N + k, ib = p * N + lane;
+            else if (lane > p && lane < N) ia = lane * N + k, ib = lane * N + p;
+            if (ia >= 0) {
+                const float t = a[ia];
+                a[ia] = a[ib];
+                a[ib] = t;
+            }
+        }
+        g.sync();
+        if (k > 0) {
+            if (lane >= k && lane < N) {
+                // lane == k: a[k][k] -= sum_j a[k][j] * temp[j]; lane > k: a[i][k] -= sum_j a[i][j] * temp[j]; temp[j] = a[j][j] * a[k][j]
+                float sum = fmul(a[lane * N + 0], fmul(a[0 * N + 0], a[k * N + 0]));
+#pragma unroll
+                for (int j = 1; j < k; ++j) sum = fadd(sum, fmul(a[lane * N + j], fmul(a[j * N + j], a[k * N + j])));
+                a[lane * N + k] = fsub(a[lane * N + k], sum);
+            }
+            g.sync();
+        }
+        const float akk = a[k * N + k];
+        const bool pivot_ok = fabsf(akk) > 0.0f;
+        if (k == 0 && !pivot_ok) {
+            tr[0] = 0;
+            zero_diag = true;
+        } else if (pivot_ok) {
+            if (lane > k && lane < N) a[lane * N + k] = fdiv(a[lane * N + k], akk);
+        }
+        g.sync();
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) s.perm[i] = i;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const int t = s.perm[k];
+            s.perm[k] = s.perm[tr[k]];
+            s.perm[tr[k]] = t;
+        }
+    }
+    g.sync();
+}
+
+// Solves with the factors of LdltFactorShared and the right-hand side s.b; every lane gets the solution.
+template <int N, int G>
+__device__ __forceinline__ void LdltSolveShared(const Group<G> &g, LdltShared<N> &s, float (&z)[N]) {
+    const float *a = s.a;
+    float x[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = s.b[s.perm[i]];
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        float sum = fmul(a[i * N + 0], x[0]);
+#pragma unroll
+        for (int j = 1; j < i; ++j) sum = fadd(sum, fmul(a[i * N + j], x[j]));
+        x[i] = fsub(x[i], sum);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) x[i] = (fabsf(a[i * N + i]) > FLT_MIN) ? fdiv(x[i], a[i * N + i]) : 0.0f;
+#pragma unroll
+    for (int i = N - 2; i >= 0; --i) {
+        float sum = fmul(a[(i + 1) * N + i], x[i + 1]);
+#pragma unroll
+        for (int j = i + 2; j < N; ++j) sum = fadd(sum, fmul(a[j * N + i], x[j]));
+        x[i] = fsub(x[i], sum);
+    }
+    // backward transpositions = the inverse permutation (every lane writes the same values)
+#pragma unroll
+    for (int i = 0; i < N; ++i) s.z[s.perm[i]] = x[i];
+    g.sync();
+#pragma unroll
+    for (int i = 0; i < N; ++i) z[i] = s.z[i];
+    g.sync();
+}
+
+template <int G>
+__device__ __forceinline__ void Ldlt6FactorShared(const Group<G> &g, Ldlt6Shared &s) { LdltFactorShared<6, G>(g, s); }
+template <int G>
+__device__ __forceinline__ void Ldlt6SolveShared(const Group<G> &g, Ldlt6Shared &s, float (&z)[6]) { LdltSolveShared<6, G>(g, s, z); }
+
 template <int N>
 __device__ __forceinline__ void LdltSolve(const float (&A)[N][N], const float (&b)[N], float (&x)[N]) {
     LdltFactors<N> f;

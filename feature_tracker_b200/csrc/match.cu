@@ -547,9 +547,11 @@ int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const
         const int splits = CurSplits(ctx, ref_blocks, n_cur, kHamTile);
         const int per = ((n_cur + splits - 1) / splits + kHamTile - 1) / kHamTile * kHamTile;
         const dim3 grid(ref_blocks, (n_cur + per - 1) / per);
+        ProfBegin(ctx);
         if (words == 8) HammingForceKernel<8><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
         else if (words == 4) HammingForceKernel<4><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
         else HammingForceKernel<16><<<grid, kHamThreads, 0, st>>>(d_ref, n_ref, d_cur, n_cur, per, d_best);
+        ProfEnd(ctx);
         HammingFinalize32Kernel<<<Blocks(n_ref, 256), 256, 0, st>>>(d_best, n_ref, max_dist, d_idx);
     } else {
         if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref))) return rc;

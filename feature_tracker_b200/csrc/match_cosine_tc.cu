@@ -167,11 +167,28 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
     const int row0 = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows;
     const int rows = min(kPrepRows, n - row0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // warp w moves rows w, w + 8, ...; lane = column within a 32-wide group (coalesced, no index arithmetic beyond adds)
-    for (int r = warp; r < rows; r += kPrepThreads / 32) {
-        const float *src = desc + static_cast<size_t>(row0 + r) * dim;
-        float *dst = prep_smem + r * stride;
-        for (int k = lane; k < dim; k += 32) dst[k] = __ldg(src + k);
+    // warp w moves rows w, w + 8, w + 16, w + 24; lane = column within a 32-wide group.  All 32 loads of a thread are issued before
+    // the first use (dim <= 256 = 8 x 32), and the values stay in registers for the BF16 pass: global memory is read once.
+    constexpr int kRowsPerWarp = kPrepRows / (kPrepThreads / 32), kColsPerLane = kMaxKBlocks * kKBlock / 32;
+    float v[kRowsPerWarp][kColsPerLane];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp + rr * (kPrepThreads / 32);
+        const float *src = desc + static_cast<size_t>(row0 + min(r, rows - 1)) * dim;
+#pragma unroll
+        for (int q = 0; q < kColsPerLane; ++q) {
+            const int k = lane + 32 * q;
+            v[rr][q] = k < dim ? __ldg(src + k) : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        float *dst = prep_smem + (warp + rr * (kPrepThreads / 32)) * stride;
+#pragma unroll
+        for (int q = 0; q < kColsPerLane; ++q) {
+            const int k = lane + 32 * q;
+            if (k < dim) dst[k] = v[rr][q];
+        }
     }
     __syncthreads();
     if (threadIdx.x < rows) {
@@ -182,15 +199,23 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
         const float nrm = __fsqrt_rn(s);
         norm[row0 + threadIdx.x] = nrm;
         const bool abnormal = AbnormalNorm(nrm);
-        s_norm[threadIdx.x] = abnormal ? 0.0f : nrm;  // 0 marks "zero BF16 row"
+        // The BF16 copy only feeds the screening GEMM, whose error margin (kEpsDot) has room for the 1-ulp difference between
+        // x * (1 / norm) and x / norm: one multiply per element instead of a division.  0 marks "zero BF16 row".
+        s_norm[threadIdx.x] = abnormal ? 0.0f : 1.0f / nrm;
         if (abnormal && is_cur) abn_cur[atomicAdd(&counters[1], 1)] = row0 + threadIdx.x;
     }
     __syncthreads();
-    for (int r = warp; r < rows; r += kPrepThreads / 32) {
-        const float *src = prep_smem + r * stride;
-        const float nr = s_norm[r];
+#pragma unroll
+    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
+        const int r = warp + rr * (kPrepThreads / 32);
+        if (r >= rows) continue;
+        const float inv = s_norm[r];
         __nv_bfloat16 *dst = unit + static_cast<size_t>(row0 + r) * k_pad;
-        for (int k = lane; k < k_pad; k += 32) dst[k] = __float2bfloat16_rn((k < dim && nr > 0.0f) ? src[k] / nr : 0.0f);
+#pragma unroll
+        for (int q = 0; q < kColsPerLane; ++q) {
+            const int k = lane + 32 * q;
+            if (k < k_pad) dst[k] = __float2bfloat16_rn(v[rr][q] * inv);  // columns past dim hold 0
+        }
     }
 }
 
@@ -452,13 +477,37 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
     unsigned long long key = kNoKey64;  // lane r of warp 0: row r
     for (int round = 0; round < kMaxSplits; ++round) {
         bool any = false;
-        for (int r = warp; r < kRerankRows; r += kRerankThreads / 32) {
-            if (round < s_count[r]) {
-                any = true;
-                const float *a = ref + static_cast<size_t>(row0 + r) * dim;
-                const float *b = cur + static_cast<size_t>(s_cand[r][round]) * dim;
-                float *prod = rerank_smem + r * stride;
-                for (int k = lane; k < dim; k += 32) prod[k] = __fmul_rn(__ldg(a + k), __ldg(b + k));
+        // warp w owns rows w, w + 4, ..., w + 28; four rows at a time, all their loads (2 x 8 per row and lane) issued before the first
+        // product, so a block waits for global memory twice per round instead of once per row
+        constexpr int kBatch = 4, kColsPerLane = kMaxKBlocks * kKBlock / 32;
+#pragma unroll
+        for (int half = 0; half < kRerankRows / (kRerankThreads / 32) / kBatch; ++half) {
+            float va[kBatch][kColsPerLane], vb[kBatch][kColsPerLane];
+            bool live[kBatch];
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                const int r = warp + (half * kBatch + q) * (kRerankThreads / 32);
+                live[q] = round < s_count[r];
+                any = any || live[q];
+                const float *a = ref + static_cast<size_t>(live[q] ? row0 + r : 0) * dim;
+                const float *b = cur + static_cast<size_t>(live[q] ? s_cand[r][round] : 0) * dim;
+#pragma unroll
+                for (int c = 0; c < kColsPerLane; ++c) {
+                    const int k = lane + 32 * c;
+                    const bool in = live[q] && k < dim;
+                    va[q][c] = in ? __ldg(a + k) : 0.0f;
+                    vb[q][c] = in ? __ldg(b + k) : 0.0f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kBatch; ++q) {
+                if (!live[q]) continue;
+                float *prod = rerank_smem + (warp + (half * kBatch + q) * (kRerankThreads / 32)) * stride;
+#pragma unroll
+                for (int c = 0; c < kColsPerLane; ++c) {
+                    const int k = lane + 32 * c;
+                    if (k < dim) prod[k] = __fmul_rn(va[q][c], vb[q][c]);
+                }
             }
         }
         if (!__syncthreads_or(any)) break;
@@ -633,8 +682,10 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
     // The opt-in is per device and the ABI allows one process to hold contexts on several GPUs: set it before every launch (cheap).
     FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
+    ProfBegin(ctx);
     CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
                                                                           floor_dot);
+    ProfEnd(ctx);
     RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(
         d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx);
     ExactScanKernel<<<ctx->sm_count * 2, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters, tiles_per_split * kTileN, splits, best, max_dist,

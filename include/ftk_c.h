@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTK_ABI_VERSION 3
+#define FTK_ABI_VERSION 4
 
 /* ---- error codes ------------------------------------------------------------------------------------------ */
 #define FTK_OK 0
@@ -97,6 +97,17 @@ int ftk_synchronize(ftk_context *ctx);
 void *ftk_stream(ftk_context *ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 uint64_t ftk_kernel_launches(const ftk_context *ctx);
+
+/* Page-locked host memory for the host-pointer entry points: copies from / to it are asynchronous DMA transfers (what "pinned memory
+ * recommended" means below); ordinary memory works everywhere but is staged by the driver.  Not tied to a context. */
+int ftk_alloc_pinned(size_t bytes, void **out);
+void ftk_free_pinned(void *ptr);
+/* Measurement hook (bench.py's per-kernel roofline figures): while enabled, the entry points that have one dominant kernel
+ * (ftk_match_cosine_force: the tcgen05 GEMM; ftk_match_hamming_force: the POPC kernel; ftk_klt_track: the tracker kernel) record
+ * CUDA events around that kernel's launch on the context's stream.  ftk_last_kernel_ms synchronises and returns the duration of the
+ * last such launch in milliseconds (negative when none was recorded).  Off by default: no events are recorded. */
+int ftk_set_profiling(ftk_context *ctx, int enabled);
+float ftk_last_kernel_ms(ftk_context *ctx);
 
 /* ---- image pyramids (replaces ImagePyramid::SetRawImage / CreateImagePyramid, call sites
  *      test/test_optical_flow.cpp:49-53,70-71; semantics: oracle/shim/datatype_image_pyramid.h) -------------------
@@ -268,9 +279,11 @@ int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, co
 int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim,
                             const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist, int32_t *idx,
                             uint32_t flags);
-/* Diagnostics: number of (reference row, column split) items the last ftk_match_cosine_force call had to hand to the exact
- * fall-back scan because the tensor-core pass could not separate the candidates (0 when the fast path decided every row;
- * -1 when the call did not use the tensor-core path).  Synchronises the context. */
+/* Diagnostics: number of reference rows the last ftk_match_cosine_force call had to hand to the exact scan because the tensor-core
+ * pass could not separate their candidates or their norm is abnormal (0 when the screening decided every row; -1 when the call did
+ * not use the tensor-core path).  Synchronises the context.
+ * Bit-exactness contract: indices equal the reference's sequential fp32 evaluation for ALL inputs, including descriptors whose sum of
+ * squares overflows, underflows or is NaN (those rows / columns are evaluated with the exact arithmetic only). */
 int ftk_last_cosine_exact_scan_items(ftk_context *ctx);
 /* ---- mutual arg-max of a score matrix (SURVEY 8(f) "next" row; replaces the score-matrix post-processing of
  *      NNFeatureMatcher::Match, src/nn_feature_matcher/nn_feature_matcher.cpp:180-216) ---------------------------------

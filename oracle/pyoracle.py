@@ -433,6 +433,23 @@ class RefLib(_CpuChecker):
         return ok == 1, cur_buf, q, p, st_buf
 
 
+    def nn_match_scores(self, scores, min_score):
+        """NNFeatureMatcher::Match, score-matrix branch (nn_feature_matcher.cpp:180-216), by the reference's own code compiled in place
+        against the ONNX Runtime stub of oracle/shim/onnx_run_time.h.  Needs n_ref <= n_cur.  Returns (ok, idx[n_ref])."""
+        scores = np.ascontiguousarray(scores, dtype=np.float32)
+        n_ref, n_cur = scores.shape
+        idx = np.full(max(n_ref, 1), -1, np.int32)
+        ok = self._fn("nn_match_scores")(_f32p(scores), C.c_int32(n_ref), C.c_int32(n_cur), C.c_float(min_score), _i32p(idx))
+        return ok == 1, idx[:n_ref].copy()
+
+    def nn_match_pairs(self, matches, n_ref, n_cur):
+        """The "matches" branch (nn_feature_matcher.cpp:160-178): matches = [n, 2] int64 (idx_ref, idx_cur).  Returns (ok, idx[n_ref])."""
+        matches = np.ascontiguousarray(matches, dtype=np.int64).reshape(-1, 2)
+        idx = np.full(max(n_ref, 1), -1, np.int32)
+        ok = self._fn("nn_match_pairs")(matches.ctypes.data_as(C.c_void_p), C.c_int32(len(matches)), C.c_int32(n_ref), C.c_int32(n_cur), _i32p(idx))
+        return ok == 1, idx[:n_ref].copy()
+
+
 class OracleLib(_CpuChecker):
     prefix = "ftko_"
 
@@ -441,7 +458,8 @@ class OracleLib(_CpuChecker):
         super().__init__(ORACLE_SO)
 
     def mutual_scores(self, scores, min_score):
-        """nn_feature_matcher.cpp:180-216 (C restatement only: the reference file needs ONNX Runtime to compile)."""
+        """nn_feature_matcher.cpp:180-216 (C restatement; pinned against the reference's own Match() -- RefLib.nn_match_scores -- by
+        tests/test_oracle.py)."""
         scores = np.ascontiguousarray(scores, dtype=np.float32)
         n_ref, n_cur = scores.shape
         idx = np.full(max(n_ref, 1), -1, np.int32)

@@ -9,6 +9,7 @@
 #include "descriptor_matcher.h"
 #include "dense_optical_flow.h"
 #include "direct_method_tracker.h"
+#include "nn_feature_matcher.h"
 #include "optical_flow_affine_klt.h"
 #include "optical_flow_basic_klt.h"
 #include "optical_flow_lssd_klt.h"
@@ -385,6 +386,59 @@ int ftkref_dense_flow_track(const ftko_dense_flow_params *params, int32_t levels
     if (!ok) return 0;
     std::copy(flow[0].v.begin(), flow[0].v.end(), flow_row);
     std::copy(flow[1].v.begin(), flow[1].v.end(), flow_col);
+    return 1;
+}
+
+// NNFeatureMatcher::Match, score-matrix branch (nn_feature_matcher.cpp:150-219), run by the reference's own code on an injected
+// network output: `scores` (n_ref x n_cur row-major) is handed to the stub session of oracle/shim/onnx_run_time.h, Match() then does
+// its column / row arg-max, kMinValidMatchScore gate and mutual check.  idx[i] = the current index Match() assigned to reference
+// feature i (recovered from matched_pixel_uv_cur: current feature j sits at pixel (j, j)), -1 where status stayed kLargeResidual.
+// n_ref <= n_cur is required (the reference sizes matched_pixel_uv_cur by pixel_uv_cur and indexes it by idx_ref, :158,215).
+int ftkref_nn_match_scores(const float *scores, int32_t n_ref, int32_t n_cur, float min_score, int32_t *idx) {
+    if (n_ref <= 0 || n_cur <= 0 || n_ref > n_cur) return 0;
+    feature_tracker::NNFeatureMatcher matcher;
+    matcher.options().kMinValidMatchScore = min_score;
+    matcher.options().kMaxNumberOfMatches = 4;
+    matcher.options().kModelType = feature_tracker::NNFeatureMatcher::ModelType::kLightglueForSuperpointScoreMat;
+    shim::NextOutputs().clear();
+    if (!matcher.Initialize()) return 0;
+    Ort::Value out;
+    out.rows = n_ref;
+    out.cols = n_cur;
+    out.f.assign(scores, scores + static_cast<size_t>(n_ref) * n_cur);
+    shim::NextOutputs().clear();
+    shim::NextOutputs().push_back(out);
+    std::vector<SuperpointDescriptorType> desc_ref(n_ref), desc_cur(n_cur);
+    std::vector<Vec2> uv_ref(n_ref), uv_cur(n_cur), matched;
+    for (int32_t j = 0; j < n_cur; ++j) uv_cur[j] = Vec2(static_cast<float>(j), static_cast<float>(j));
+    std::vector<uint8_t> status;
+    if (!matcher.Match(desc_ref, desc_cur, uv_ref, uv_cur, matched, status)) return 0;
+    for (int32_t i = 0; i < n_ref; ++i)
+        idx[i] = status[i] == static_cast<uint8_t>(feature_tracker::TrackStatus::kTracked) ? static_cast<int32_t>(matched[i].x()) : -1;
+    return 1;
+}
+
+// The "matches" branch of the same function (:160-178; the fused LightGlue models return index pairs + scores): matches = n x 2
+// int64 (idx_ref, idx_cur).  Outputs as above.
+int ftkref_nn_match_pairs(const int64_t *matches, int32_t n_matches, int32_t n_ref, int32_t n_cur, int32_t *idx) {
+    if (n_ref <= 0 || n_cur <= 0 || n_ref > n_cur) return 0;
+    feature_tracker::NNFeatureMatcher matcher;
+    matcher.options().kMaxNumberOfMatches = 4;
+    shim::NextOutputs().clear();
+    if (!matcher.Initialize()) return 0;
+    Ort::Value pairs, mscores;
+    pairs.rows = n_matches, pairs.cols = 2;
+    pairs.i64.assign(matches, matches + static_cast<size_t>(n_matches) * 2);
+    mscores.rows = n_matches, mscores.cols = 1;
+    mscores.f.assign(static_cast<size_t>(n_matches), 1.0f);
+    shim::NextOutputs() = {pairs, mscores};
+    std::vector<SuperpointDescriptorType> desc_ref(n_ref), desc_cur(n_cur);
+    std::vector<Vec2> uv_ref(n_ref), uv_cur(n_cur), matched;
+    for (int32_t j = 0; j < n_cur; ++j) uv_cur[j] = Vec2(static_cast<float>(j), static_cast<float>(j));
+    std::vector<uint8_t> status;
+    if (!matcher.Match(desc_ref, desc_cur, uv_ref, uv_cur, matched, status)) return 0;
+    for (int32_t i = 0; i < n_ref; ++i)
+        idx[i] = status[i] == static_cast<uint8_t>(feature_tracker::TrackStatus::kTracked) ? static_cast<int32_t>(matched[i].x()) : -1;
     return 1;
 }
 

@@ -110,6 +110,8 @@ struct Mat {
             for (int j = 0; j < C; ++j) d[i][j] = 0.0f;
     }
 
+    static constexpr int rows() { return R; }  // nn_feature_matcher.cpp:98-101 sizes its input tensors with them
+    static constexpr int cols() { return C; }
     float &operator()(int i, int j) { return d[i][j]; }
     const float &operator()(int i, int j) const { return d[i][j]; }
     float &operator()(int i) { return (&d[0][0])[i]; }

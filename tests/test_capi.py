@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
     assert sorted(_capi.EXPORTED_SYMBOLS) == names
-    assert lib.ftk_abi_version() == 3
+    assert lib.ftk_abi_version() == 4
 
 
 def test_default_params_are_the_reference_defaults():

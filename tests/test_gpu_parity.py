@@ -744,6 +744,20 @@ def test_mutual_scores_vs_oracle(ctx, oracle, n_ref, n_cur):
     assert not ok
 
 
+@pytest.mark.parametrize("n_ref,n_cur", [(300, 300), (257, 1031), (2048, 2048)])
+def test_mutual_scores_vs_reference_match(ctx, reflib, n_ref, n_cur):
+    """ftk_match_mutual_scores against the reference's OWN NNFeatureMatcher::Match (nn_feature_matcher.cpp:150-219 compiled in place with
+    the ONNX Runtime stub; the session returns the injected score matrix), index for index."""
+    s = lightglue_like_scores(n_ref, n_cur, seed=n_ref * 11 + n_cur)
+    m = ft.NNFeatureMatcher(ctx)
+    for thr in (-3.0, -1.0, -100.0):
+        m.options().kMinValidMatchScore = thr
+        ok, idx = m.MatchScores(s)
+        ok_e, exp = reflib.nn_match_scores(s, thr)
+        assert ok and ok_e and np.array_equal(idx, exp), (thr, np.nonzero(idx != exp)[0][:10])
+    assert (exp >= 0).sum() > min(n_ref, n_cur) // 4
+
+
 def test_cross_check_force_match(ctx, oracle):
     """Cross-check matching = two ForceMatch calls (reference semantics each) + the mutual filter."""
     rng = np.random.default_rng(9)

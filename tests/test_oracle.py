@@ -222,6 +222,38 @@ def test_mutual_scores_restatement(oracle):
     assert not ok
 
 
+def test_mutual_scores_restatement_pinned_to_reference_match(oracle, reflib):
+    """The restatement against the REFERENCE's own NNFeatureMatcher::Match (nn_feature_matcher.cpp:150-219 compiled in place; ONNX
+    Runtime replaced by the stub of oracle/shim/onnx_run_time.h, whose session returns the injected score matrix): ties, NaN, -inf,
+    every threshold.  This pins the mutual-score row of SURVEY 8(f) to the reference."""
+    rng = np.random.default_rng(78)
+    for n_ref, n_cur in [(1, 1), (5, 7), (40, 61), (64, 64), (300, 300), (257, 1031)]:
+        s = rng.normal(-4, 3, (n_ref, n_cur)).astype(np.float32)
+        s[rng.random(s.shape) < 0.1] = np.float32(-1.5)  # ties
+        for i in range(min(n_ref, n_cur) // 2):  # planted mutual maxima
+            s[i, (i * 7) % n_cur] = np.float32(1.0 + 0.01 * i)
+        if n_ref > 5:
+            s[2, :] = -np.inf
+            s[3, 0] = np.nan
+            s[0, 2] = np.nan
+            s[5, 3] = np.nan
+            s[4, 4], s[4, 6] = -0.0, 0.0
+        for thr in (-3.0, -1.0, -100.0, 0.5):
+            ok_r, exp = reflib.nn_match_scores(s, thr)
+            ok_o, got = oracle.mutual_scores(s, thr)
+            assert ok_r and ok_o and np.array_equal(got, exp), (n_ref, n_cur, thr, np.nonzero(got != exp)[0][:10])
+        assert (exp >= 0).sum() >= min(1, n_ref // 8)
+
+
+def test_reference_match_pairs_branch(reflib):
+    """The fused-model branch of Match (nn_feature_matcher.cpp:160-178): index pairs scattered with bounds checks -- what the python
+    NNFeatureMatcher.MatchPairs mirrors on the host (no kernel: n <= a few hundred pairs)."""
+    import feature_tracker_b200.api as api
+    pairs = np.array([[0, 3], [2, 1], [5, 9], [-1, 2], [3, 40], [99, 1], [4, -2], [2, 7]], np.int64)
+    ok, exp = reflib.nn_match_pairs(pairs, 8, 10)
+    assert ok and np.array_equal(exp, api.nn_match_pairs_host(pairs, 8, 10))
+
+
 @pytest.mark.parametrize("levels,half,max_points", [(4, 6, 500), (3, 4, 40), (1, 7, 500), (5, 6, 25)])
 def test_direct_method_restatement_vs_reference_build(oracle, reflib, levels, half, max_points):
     """SURVEY 8(f) rank 3: the C restatement of DirectMethod::TrackFeatures equals the reference's own
