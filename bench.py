@@ -52,7 +52,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="configs1", choices=sorted(WORKLOADS) + ["match_sharded"],
+                    help="match_sharded: BASELINE configs[3] / configs[4] with the reference rows split over the ranks (strong scaling, SURVEY 8(e))")
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU)
     ap.add_argument("--features", type=int, default=FEATURES_PER_PAIR)
     ap.add_argument("--variant", default=None, help="with --method / --half: time one tracker instead of a named workload (profiling)")
@@ -65,6 +66,8 @@ def parse():
 
 
 def trackers_of(args):
+    if args.workload == "match_sharded":
+        return WORKLOADS["configs1"]
     if args.variant or args.method or args.half is not None:
         return [(args.variant or "basic", args.method or "inverse", 7 if args.half is None else args.half)]
     return WORKLOADS[args.workload]
@@ -948,10 +951,131 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_match_sharded(args):
+    """SURVEY 8(e), matching: the reference rows of BASELINE configs[3] (BRIEF-256 10k x 10k force + nearby) and configs[4] (float-256
+    20k x 20k force) are split into contiguous blocks over the ranks, the current set is replicated on every GPU, no collective on
+    the data path; the index vectors are gathered on rank 0 (NCCL) and compared with the whole problem solved on rank 0's GPU.  Strong
+    scaling: the total work is fixed.  Timing: CUDA events per rank, barrier on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import feature_tracker_b200 as ft
+    from feature_tracker_b200 import _capi, sharding, synthetic as S
+    from feature_tracker_b200.api import lib as ftk_lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    ctx = ft.Context(local_rank)
+    L = ftk_lib()
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    vp = C.c_void_p
+    fl = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_INDEX_INPUT
+    steps = max(args.steps, 5)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    out = {}
+    # ---- C4 ----
+    rb, cb, pred, pos, _ = S.make_brief_sets(10000, 10000, seed=99)
+    lo, hi = sharding.shard_bounds(10000, world, rank)
+    d_c = torch.from_numpy(ft.pack_brief(cb).view(np.int32)).to(dev)
+    d_pos = torch.from_numpy(pos).to(dev)
+    d_r = torch.from_numpy(ft.pack_brief(rb[lo:hi]).view(np.int32)).to(dev)
+    d_pred = torch.from_numpy(pred[lo:hi]).to(dev)
+    d_idx = torch.full((hi - lo,), -1, dtype=torch.int32, device=dev)
+    full = {}
+    if rank == 0:
+        d_rf_all = torch.from_numpy(ft.pack_brief(rb).view(np.int32)).to(dev)
+        d_pred_all = torch.from_numpy(pred).to(dev)
+        d_all = torch.full((10000,), -1, dtype=torch.int32, device=dev)
+        ctx.check(L.ftk_match_hamming_force(ctx._h, vp(d_rf_all.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, 60.0, vp(d_all.data_ptr()), fl))
+        ctx.synchronize()
+        full["c4_force"] = d_all.cpu().numpy().copy()
+        ctx.check(L.ftk_match_hamming_nearby(ctx._h, vp(d_rf_all.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, vp(d_pred_all.data_ptr()), vp(d_pos.data_ptr()), 50, 50,
+                                             60.0, vp(d_all.data_ptr()), fl))
+        ctx.synchronize()
+        full["c4_nearby"] = d_all.cpu().numpy().copy()
+    ms = timed(lambda: ctx.check(L.ftk_match_hamming_force(ctx._h, vp(d_r.data_ptr()), hi - lo, vp(d_c.data_ptr()), 10000, 8, 60.0, vp(d_idx.data_ptr()), fl)))
+    ctx.synchronize()
+    got = sharding.match_sharded(lambda a, b: d_idx.cpu().numpy(), 10000, world, rank)
+    out["C4_brief256_force_10k_x_10k"] = {"ms": ms, "pairs_per_s": 1e8 / (ms * 1e-3), "rows_per_rank": hi - lo}
+    if rank == 0:
+        out["C4_brief256_force_10k_x_10k"]["index_mismatch_vs_single_gpu"] = int((got != full["c4_force"]).sum())
+    ms = timed(lambda: ctx.check(L.ftk_match_hamming_nearby(ctx._h, vp(d_r.data_ptr()), hi - lo, vp(d_c.data_ptr()), 10000, 8, vp(d_pred.data_ptr()), vp(d_pos.data_ptr()),
+                                                            50, 50, 60.0, vp(d_idx.data_ptr()), fl)))
+    ctx.synchronize()
+    got = sharding.match_sharded(lambda a, b: d_idx.cpu().numpy(), 10000, world, rank)
+    out["C4_brief256_nearby_10k_window50"] = {"ms": ms, "ref_rows_per_s": 1e4 / (ms * 1e-3)}
+    if rank == 0:
+        out["C4_brief256_nearby_10k_window50"]["index_mismatch_vs_single_gpu"] = int((got != full["c4_nearby"]).sum())
+    # ---- C5 ----
+    rf, cf = S.make_float_sets(20000, 20000, seed=5)
+    lo, hi = sharding.shard_bounds(20000, world, rank)
+    d_cf = torch.from_numpy(cf).to(dev)
+    d_rf = torch.from_numpy(np.ascontiguousarray(rf[lo:hi])).to(dev)
+    d_idx2 = torch.full((hi - lo,), -1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        d_rf_all = torch.from_numpy(rf).to(dev)
+        d_all = torch.full((20000,), -1, dtype=torch.int32, device=dev)
+        ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_rf_all.data_ptr()), 20000, vp(d_cf.data_ptr()), 20000, 256, 0.1, vp(d_all.data_ptr()), fl))
+        ctx.synchronize()
+        full["c5"] = d_all.cpu().numpy().copy()
+    ms5 = timed(lambda: ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_rf.data_ptr()), hi - lo, vp(d_cf.data_ptr()), 20000, 256, 0.1, vp(d_idx2.data_ptr()), fl)))
+    ctx.synchronize()
+    got = sharding.match_sharded(lambda a, b: d_idx2.cpu().numpy(), 20000, world, rank)
+    flop = 2.0 * 20000 * 20000 * 256
+    out["C5_float256_force_20k_x_20k"] = {"ms": ms5, "pairs_per_s": 4e8 / (ms5 * 1e-3), "tflops_whole_job": flop / (ms5 * 1e-3) / 1e12, "rows_per_rank": hi - lo}
+    if rank == 0:
+        out["C5_float256_force_20k_x_20k"]["index_mismatch_vs_single_gpu"] = int((got != full["c5"]).sum())
+        line = {"metric": "descriptor pairs/sec (float-256 force match 20k x 20k, ref rows sharded)", "value": 4e8 / (ms5 * 1e-3), "unit": "pairs/s", "n_gpus": world,
+                "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms5, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16 screen + f32 exact",
+                "data": "synthetic", "config": {"workload": "BASELINE configs[3] + configs[4], reference rows split over the ranks, current set replicated, no collective on "
+                                                             "the data path; results gathered on rank 0 and compared with the single-GPU result",
+                                                "sharding": "ref rows, contiguous blocks"}, "workloads": out}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "match_sharded":
+        run_match_sharded(args)
     else:
         run_b200(args)
 

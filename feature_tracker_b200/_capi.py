@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "ftk_kernel_launches", "ftk_alloc_pinned", "ftk_free_pinned", "ftk_set_profiling", "ftk_last_kernel_ms", "ftk_pyramid_create", "ftk_pyramid_destroy", "ftk_pyramid_set_images", "ftk_pyramid_build",
     "ftk_pyramid_set_level", "ftk_pyramid_get_level", "ftk_pyramid_levels", "ftk_pyramid_images", "ftk_klt_track",
     "ftk_track_image_pairs", "ftk_track_image_pairs_multi", "ftk_track_image_sequence",
-    "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_hamming_pairs", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
+    "ftk_match_hamming_force", "ftk_match_hamming_nearby", "ftk_match_hamming_pairs", "ftk_match_cosine_pairs", "ftk_match_cosine_force", "ftk_match_cosine_nearby", "ftk_fill_matched", "ftk_last_cosine_exact_scan_items",
     "ftk_match_mutual_scores", "ftk_match_cross_check", "ftk_direct_params_default", "ftk_direct_method_track", "ftk_dense_flow_params_default", "ftk_dense_flow_track",
     "ftk_detector_params_default", "ftk_detect_features", "ftk_detect_features_batch", "ftk_detect_response", "ftk_brief_pattern_default", "ftk_describe_brief", "ftk_describe_brief_batch",
 ]
@@ -115,6 +115,7 @@ def load_library():
         "ftk_match_hamming_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
         "ftk_match_hamming_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_hamming_pairs": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, f32, vp, u32]),
+        "ftk_match_cosine_pairs": (C.c_int, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_force": (C.c_int, [vp, vp, i32, vp, i32, i32, f32, vp, u32]),
         "ftk_match_cosine_nearby": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, f32, vp, u32]),
         "ftk_dense_flow_params_default": (None, [P(DenseFlowParams)]),

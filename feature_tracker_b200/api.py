@@ -517,6 +517,25 @@ class CosineMatcher(DescriptorMatcher):
                                              int(o.kMaxValidPredictRowDistance), int(o.kMaxValidPredictColDistance),
                                              float(o.kMaxValidDescriptorDistance), _ptr(idx), flags)
 
+    def MatchPairs(self, descriptors_ref, ref_offsets, descriptors_cur, cur_offsets, pixel_uv_pred_in_cur=None, pixel_uv_cur=None, index_pairs_in_cur=None):
+        """Many frame pairs in one call (ftk_match_cosine_pairs), the float-descriptor twin of BriefMatcher.MatchPairs."""
+        ref, cur = self._prep(descriptors_ref), self._prep(descriptors_cur)
+        ro = np.ascontiguousarray(ref_offsets, dtype=np.int32)
+        co = np.ascontiguousarray(cur_offsets, dtype=np.int32)
+        n_ref = ref.shape[0]
+        assert ro[-1] == n_ref and co[-1] == cur.shape[0] and len(ro) == len(co) and ref.shape[1] == cur.shape[1]
+        idx, flags = self._idx(index_pairs_in_cur, n_ref)
+        pred = pos = None
+        if pixel_uv_pred_in_cur is not None:
+            pred = np.ascontiguousarray(pixel_uv_pred_in_cur, dtype=np.float32).reshape(-1, 2)
+            pos = np.ascontiguousarray(pixel_uv_cur, dtype=np.float32).reshape(-1, 2)
+            assert pred.shape[0] == n_ref and pos.shape[0] == cur.shape[0]
+        o = self._options
+        rc = lib().ftk_match_cosine_pairs(self.ctx._h, _ptr(ref), _ptr(cur), cur.shape[1], len(ro) - 1, _ptr(ro), _ptr(co), _ptr(pred), _ptr(pos),
+                                          int(o.kMaxValidPredictRowDistance), int(o.kMaxValidPredictColDistance), float(o.kMaxValidDescriptorDistance),
+                                          _ptr(idx), flags)
+        return self.ctx.check(rc), idx[:n_ref]
+
 
     def last_exact_scan_items(self):
         """Diagnostics: rows x splits the last ForceMatch re-scanned exactly (0 = the tensor-core pass decided everything)."""

@@ -172,7 +172,7 @@ void ftk_destroy(ftk_context *ctx) {
     DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
-                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
+                        &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_small, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
                         &ctx->d_work2, &ctx->d_work3};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < ftk_context::kStageBuffers; ++b) {
@@ -187,6 +187,7 @@ void ftk_destroy(ftk_context *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int q = 0; q < 2; ++q)
         if (ctx->ev_prof[q]) cudaEventDestroy(ctx->ev_prof[q]);
+    if (ctx->h_small) cudaFreeHost(ctx->h_small);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -404,6 +405,53 @@ int ftk_klt_track(ftk_context *ctx, const ftk_klt_params *params, const ftk_pyra
     a.has_prediction = (flags & FTK_FLAG_NO_PREDICTION) ? 0 : 1;
     a.has_status = (flags & FTK_FLAG_NO_STATUS) ? 0 : 1;
     a.single_level = (flags & FTK_FLAG_SINGLE_LEVEL) ? 1 : 0;
+
+    // Small host-pointer calls (the reference's own use: one frame pair, a few hundred features -- BASELINE configs[0]) are bound by
+    // the number of copies and launches, not by bytes: every array travels in ONE pinned block (one H2D, one D2H).
+    // Block layout: [cur_uv | status (padded to 16) | ref_uv | feat_offsets | ref_image | cur_image]; results = the first two.
+    const size_t sz_uv = sizeof(float2) * static_cast<size_t>(n_features), sz_st = (static_cast<size_t>(n_features) + 15) / 16 * 16;
+    const size_t sz_off = (sizeof(int32_t) * (static_cast<size_t>(n_pairs) + 1) + 15) / 16 * 16, sz_map = (sizeof(int32_t) * static_cast<size_t>(n_pairs) + 15) / 16 * 16;
+    const size_t small_bytes = 2 * sz_uv + sz_st + sz_off + 2 * sz_map;
+    if (!on_device && small_bytes <= 256 * 1024) {
+        if (int rc = EnsureDevice(ctx, ctx->d_small, small_bytes)) return rc;
+        if (ctx->h_small_bytes < small_bytes) {
+            if (ctx->h_small) cudaFreeHost(ctx->h_small);
+            ctx->h_small = nullptr, ctx->h_small_bytes = 0;
+            FTK_CUDA_CHECK(ctx, cudaHostAlloc(&ctx->h_small, 256 * 1024, cudaHostAllocDefault));
+            ctx->h_small_bytes = 256 * 1024;
+        }
+        uint8_t *h = static_cast<uint8_t *>(ctx->h_small), *d = static_cast<uint8_t *>(ctx->d_small.ptr);
+        const size_t o_st = sz_uv, o_ref = o_st + sz_st, o_off = o_ref + sz_uv, o_ri = o_off + sz_off, o_ci = o_ri + sz_map;
+        if (a.has_prediction) memcpy(h, cur_uv, sz_uv);
+        if (a.has_status) memcpy(h + o_st, status, n_features);
+        memcpy(h + o_ref, ref_uv, sz_uv);
+        memcpy(h + o_off, feat_offsets, sizeof(int32_t) * (n_pairs + 1));
+        if (ref_image) memcpy(h + o_ri, ref_image, sizeof(int32_t) * n_pairs);
+        if (cur_image) memcpy(h + o_ci, cur_image, sizeof(int32_t) * n_pairs);
+        // inputs only: when neither a prediction nor a status comes in, the upload starts at ref_uv
+        const size_t up_from = (a.has_prediction || a.has_status) ? 0 : o_ref;
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(d + up_from, h + up_from, small_bytes - up_from, cudaMemcpyHostToDevice, ctx->stream));
+        a.cur_uv = reinterpret_cast<float2 *>(d);
+        a.status = d + o_st;
+        a.ref_uv = reinterpret_cast<const float2 *>(d + o_ref);
+        a.feat_offsets = reinterpret_cast<const int *>(d + o_off);
+        a.ref_image = ref_image ? reinterpret_cast<const int *>(d + o_ri) : nullptr;
+        a.cur_image = cur_image ? reinterpret_cast<const int *>(d + o_ci) : nullptr;
+        if (n_pairs == 1) {
+            a.feat_pair = nullptr;  // every feature belongs to pair 0
+        } else {
+            if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * n_features)) return rc;
+            int *d_feat_pair = static_cast<int *>(ctx->d_feat_pair.ptr);
+            if (int rc = ftk::LaunchFeaturePairs(ctx, a.feat_offsets, n_pairs, n_features, d_feat_pair)) return rc;
+            a.feat_pair = d_feat_pair;
+        }
+        if (int rc = ftk::LaunchKltTrackChecked(ctx, a)) return rc;
+        FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(h, d, o_st + n_features, cudaMemcpyDeviceToHost, ctx->stream));
+        FTK_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(cur_uv, h, sz_uv);
+        memcpy(status, h + o_st, n_features);
+        return FTK_OK;
+    }
 
     const float2 *d_ref_uv = nullptr;
     if (int rc = Stage(ctx, ctx->d_ref_uv, reinterpret_cast<const float2 *>(ref_uv), n_features, on_device, &d_ref_uv)) return rc;
@@ -754,6 +802,40 @@ int ftk_match_hamming_pairs(ftk_context *ctx, const uint32_t *ref, const uint32_
     if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
     if (int rc = ftk::LaunchHammingPairs(ctx, d_ref, d_cur, words, n_ref, d_ref_pair, d_ref_off, d_cur_off, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx))
         return rc;
+    return FinishIndex(ctx, idx, n_ref, flags, d_idx);
+}
+
+int ftk_match_cosine_pairs(ftk_context *ctx, const float *ref, const float *cur, int32_t dim, int32_t n_pairs, const int32_t *ref_offsets,
+                           const int32_t *cur_offsets, const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist,
+                           int32_t *idx, uint32_t flags) {
+    if (!ctx || !idx || n_pairs < 0 || dim <= 0 || dim > 1024 || !ref_offsets || !cur_offsets || (pred_uv && !cur_uv)) return FTK_ERR_INVALID_ARGUMENT;
+    if (n_pairs == 0) return FTK_OK;
+    for (int32_t p = 0; p < n_pairs; ++p)
+        if (ref_offsets[p + 1] < ref_offsets[p] || cur_offsets[p + 1] < cur_offsets[p] || ref_offsets[0] != 0 || cur_offsets[0] != 0)
+            return SetError(ctx, FTK_ERR_INVALID_ARGUMENT, "descriptor offsets must start at 0 and not decrease (pair %d)", p);
+    const int32_t n_ref = ref_offsets[n_pairs], n_cur = cur_offsets[n_pairs];
+    if ((n_ref > 0 && !ref) || (n_cur > 0 && !cur)) return FTK_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
+    const float *d_ref = nullptr, *d_cur = nullptr;
+    const float2 *d_pred = nullptr, *d_pos = nullptr;
+    const int32_t *d_ref_off = nullptr, *d_cur_off = nullptr;
+    if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * dim, on_device, &d_ref)) return rc;
+    if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * dim, on_device, &d_cur)) return rc;
+    if (pred_uv) {
+        if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
+        if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
+    }
+    if (int rc = Stage(ctx, ctx->d_offsets, ref_offsets, static_cast<size_t>(n_pairs) + 1, false, &d_ref_off)) return rc;
+    if (int rc = Stage(ctx, ctx->d_chunk_offsets, cur_offsets, static_cast<size_t>(n_pairs) + 1, false, &d_cur_off)) return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_feat_pair, sizeof(int) * static_cast<size_t>(n_ref ? n_ref : 1))) return rc;
+    int *d_ref_pair = static_cast<int *>(ctx->d_feat_pair.ptr);
+    if (n_ref > 0)
+        if (int rc = ftk::LaunchFeaturePairs(ctx, d_ref_off, n_pairs, n_ref, d_ref_pair)) return rc;
+    int *d_idx = nullptr;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
+    if (n_cur > 0)
+        if (int rc = ftk::LaunchCosinePairs(ctx, d_ref, d_cur, dim, n_ref, n_cur, d_ref_pair, d_cur_off, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 

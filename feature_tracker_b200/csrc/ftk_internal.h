@@ -66,6 +66,9 @@ struct ftk_context {
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
     FtkBuffer d_chunk_offsets, d_chunk_curmap;
     FtkBuffer d_back_uv, d_back_status;  // forward-backward pass scratch
+    FtkBuffer d_small;                   // small host-pointer calls: every input / output array in one device block ...
+    void *h_small = nullptr;             // ... mirrored by one pinned host block (one H2D + one D2H per call)
+    size_t h_small_bytes = 0;
     FtkBuffer d_dm_K, d_dm_points, d_dm_q, d_dm_p;  // direct-method staging
     FtkBuffer d_flow;  // dense-flow staging (2 planes)
     FtkBuffer d_det_response, d_det_state, d_det_cand, d_det_keys, d_det_tmp, d_det_out, d_det_pattern;  // detector / BRIEF scratch
@@ -147,6 +150,8 @@ int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, cons
 int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *d_cur, int words, int n_ref_total, const int *d_ref_pair,
                        const int *d_ref_off, const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist,
                        int *d_idx);
+int LaunchCosinePairs(ftk_context *ctx, const float *d_ref, const float *d_cur, int dim, int n_ref_total, int n_cur_total, const int *d_ref_pair,
+                      const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
 // match_mutual.cu: mutual arg-max of a score matrix; cross-check filter
 int LaunchMutualScores(ftk_context *ctx, const float *d_scores, int n_ref, int n_cur, float min_score, int *d_idx);

@@ -15,8 +15,6 @@
 // sequential CPU loops while K accumulators x (32/G) features advance per warp instruction.
 // This file is the generic ("literal") implementation for every variant/method and any patch size; the
 // specialised kernels for the head-line configurations live in klt_basic_fastpath.cu.
-#include <cstdlib>
-
 #include "klt_device.cuh"
 
 namespace ftk {
@@ -759,6 +757,7 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
     }
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
+    const SharedDivisor by_ref = MakeSharedDivisor(ref_avg), by_cur = MakeSharedDivisor(cur_avg);  // every division below is by one of the two patch means
 
     c.ch.reset();
     chunk = 0;
@@ -781,15 +780,15 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
             const float v3 = PxF(gi, fadd(gr, 1.0f), gc);
             const float v4 = PxF(ref, row_i, col_i);
             const float v5 = PxF(cur, row_j, col_j);
-            const float avg = METHOD == kInverse ? ref_avg : cur_avg;
-            const float jp0 = fdiv(fsub(v1, v0), avg), jp1 = fdiv(fsub(v3, v2), avg);
+            const SharedDivisor &by_avg = METHOD == kInverse ? by_ref : by_cur;
+            const float jp0 = DivideBy(by_avg, fsub(v1, v0)), jp1 = DivideBy(by_avg, fsub(v3, v2));
             const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
             const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
             float J[3];
             J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
             J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
             J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
-            const float residual = fsub(fdiv(v5, cur_avg), fdiv(v4, ref_avg));
+            const float residual = fsub(DivideBy(by_cur, v5), DivideBy(by_ref, v4));
             LssdTerms(J, residual, t);
         }
 #pragma unroll
@@ -865,6 +864,7 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
     }
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
+    const SharedDivisor by_ref = MakeSharedDivisor(ref_avg), by_cur = MakeSharedDivisor(cur_avg);  // every division below is by one of the two patch means
 
     c.ch.reset();
     chunk = 0;
@@ -877,14 +877,14 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
         if ((ok_bits >> chunk) & 1ull) {
             const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
             const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
-            const float jp0 = fdiv(hfx[k], ref_avg), jp1 = fdiv(hfy[k], ref_avg);
+            const float jp0 = DivideBy(by_ref, hfx[k]), jp1 = DivideBy(by_ref, hfy[k]);
             const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
             const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
             float J[3];
             J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
             J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
             J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
-            const float residual = fsub(fdiv(hv5[k], cur_avg), fdiv(hv4[k], ref_avg));
+            const float residual = fsub(DivideBy(by_cur, hv5[k]), DivideBy(by_ref, hv4[k]));
             LssdTerms(J, residual, t);
         }
 #pragma unroll
@@ -1037,7 +1037,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
 // Kernel: one group per feature; TrackMultipleLevel / TrackSingleLevel of the three subclasses.
 // ===================================================================================================================
 template <int VARIANT, int METHOD, int G>
-__global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE ? 6 : 7) KltKernel(KltLaunch a, SmemLayout layout) {
+__global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE ? (METHOD == FTK_METHOD_FAST ? 8 : 6) : 7) KltKernel(KltLaunch a, SmemLayout layout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<G> c;
     const int groups_per_block = blockDim.x / G;
@@ -1067,7 +1067,7 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE ? 6 : 7) Kl
         c.ldlt_dst1 = AffineChainSlot(G + c.g.lane);
     }
 
-    const int pair = a.feat_pair[f];
+    const int pair = a.feat_pair ? a.feat_pair[f] : 0;  // null: a single frame pair
     const int local = f - a.feat_offsets[pair];
     const float2 ref_uv = a.ref_uv[f];
     float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;  // optical_flow.cpp:12-14
@@ -1244,7 +1244,6 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             // kDirect with 16 lanes per feature: two features share a warp's 6x6 LDLT instructions and 13x13 patches fill 11 chunks of
             // 16 to 96 % (measured 47.4 ms vs 50.9 ms per 2 M features; kFast is slower that way, 49.4 ms vs 43.9 ms)
             if (geo.psize <= 16 * 64 && a.p.method == kDirect) return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo);
-            if (geo.psize <= 16 * 64 && getenv("FTK_TMP_AFFINE_G16")) return LaunchMethod<FTK_VARIANT_AFFINE, 16>(ctx, a, geo);  // TEMPORARY measurement switch
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_LSSD:

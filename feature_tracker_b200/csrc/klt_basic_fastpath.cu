@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) BasicInverseFastKernel(KltLaunch a) 
     const float dcol = static_cast<float>(lane - HC);
     constexpr unsigned kRowMask = (1u << PR) - 1u;
 
-    const int pair = a.feat_pair[f];
+    const int pair = a.feat_pair ? a.feat_pair[f] : 0;  // null: a single frame pair
     const int local = f - a.feat_offsets[pair];
     const float2 ref_uv = a.ref_uv[f];
     float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) BasicDirectFastKernel(KltLaunch a) {
     const float dcol = static_cast<float>(lane - HC);
     constexpr unsigned kRowMask = (1u << PR) - 1u;
 
-    const int pair = a.feat_pair[f];
+    const int pair = a.feat_pair ? a.feat_pair[f] : 0;  // null: a single frame pair
     const int local = f - a.feat_offsets[pair];
     const float2 ref_uv = a.ref_uv[f];
     float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(kThreads) BasicFastMethodKernel(KltLaunch a) {
     float *term = sm.term;
     const int lane = g.lane;
 
-    const int pair = a.feat_pair[f];
+    const int pair = a.feat_pair ? a.feat_pair[f] : 0;  // null: a single frame pair
     const int local = f - a.feat_offsets[pair];
     const float2 ref_uv = a.ref_uv[f];
     float2 cur_uv = a.has_prediction ? a.cur_uv[f] : ref_uv;

@@ -395,6 +395,57 @@ __global__ void __launch_bounds__(256) HammingPairsKernel(const uint32_t *__rest
     if (lane == 0 && best != kNoKey64 && static_cast<float>(static_cast<unsigned>(best >> 32)) < max_dist) idx[i] = static_cast<int>(best & 0xFFFFFFFFull);
 }
 
+// The same for float descriptors (0.5 - 0.5 * cos): the warp's reference row is staged in shared memory, each lane evaluates one current
+// descriptor of the pair at a time with the reference's own arithmetic (sequential fp32 dot, k ascending, no FMA, two divisions).
+// Float distances can be negative, so the d == 0 break of NearbyMatch (descriptor_matcher.h:119) matters: when a candidate behind
+// the first exact zero wins, the row is rescanned up to that zero only -- as NearbyKernel does.  ForceMatch has no break (:67-76).
+constexpr int kCosPairsWarps = 8;
+__global__ void __launch_bounds__(32 * kCosPairsWarps) CosinePairsKernel(const float *__restrict__ ref, const float *__restrict__ cur, int dim, int n_ref_total,
+                                                                         const int *__restrict__ ref_pair, const int *__restrict__ cur_off,
+                                                                         const float *__restrict__ ref_norm, const float *__restrict__ cur_norm,
+                                                                         const float2 *__restrict__ pred, const float2 *__restrict__ pos, float max_dcol,
+                                                                         float max_drow, float max_dist, int *__restrict__ idx) {
+    extern __shared__ float s_rows[];  // [kCosPairsWarps][dim]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kCosPairsWarps + warp;
+    if (i >= n_ref_total) return;
+    float *row = s_rows + warp * dim;
+    for (int k = lane; k < dim; k += 32) row[k] = __ldg(ref + static_cast<size_t>(i) * dim + k);
+    __syncwarp();
+    const int p = ref_pair[i];
+    const int c0 = cur_off[p], c1 = cur_off[p + 1];
+    const float rn = ref_norm[i];
+    float2 pr = make_float2(0.0f, 0.0f);
+    if (pred) pr = pred[i];
+    unsigned limit = 0xFFFFFFFFu;
+    unsigned long long best = kNoKey64;
+    for (int pass = 0; pass < 2; ++pass) {
+        best = kNoKey64;
+        unsigned first_zero = 0xFFFFFFFFu;
+        for (int j = c0 + lane; j < c1; j += 32) {
+            if (static_cast<unsigned>(j - c0) > limit) break;
+            if (pred) {
+                const float2 q = pos[j];
+                if (fabsf(__fsub_rn(pr.x, q.x)) > max_dcol || fabsf(__fsub_rn(pr.y, q.y)) > max_drow) continue;
+            }
+            const float *c = cur + static_cast<size_t>(j) * dim;
+            float dot = __fmul_rn(row[0], __ldg(c));
+            for (int k = 1; k < dim; ++k) dot = __fadd_rn(dot, __fmul_rn(row[k], __ldg(c + k)));
+            const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(dot, rn), cur_norm[j]), 0.5f));
+            if (d != d) continue;  // NaN never compares below anything in the reference
+            const unsigned long long key = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j - c0);
+            best = key < best ? key : best;
+            if (d == 0.0f) first_zero = min(first_zero, static_cast<unsigned>(j - c0));
+        }
+        best = WarpMin64(best);
+        first_zero = WarpMin32(first_zero);
+        // only NearbyMatch breaks at the first zero distance
+        if (!pred || first_zero == 0xFFFFFFFFu || static_cast<unsigned>(best & 0xFFFFFFFFull) <= first_zero) break;
+        limit = first_zero;
+    }
+    if (lane == 0 && best != kNoKey64 && KeyFloat(static_cast<unsigned>(best >> 32)) < max_dist) idx[i] = static_cast<int>(best & 0xFFFFFFFFull);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Exact fp32 cosine force matching
 // ---------------------------------------------------------------------------------------------------------------
@@ -575,6 +626,20 @@ int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *
     if (n_ref_total == 0 || words == 0) return FTK_OK;
     HammingPairsKernel<<<Blocks(n_ref_total, 8), 256, 0, ctx->stream>>>(d_ref, d_cur, words, n_ref_total, d_ref_pair, d_ref_off, d_cur_off, d_pred, d_pos,
                                                                        static_cast<float>(max_dcol), static_cast<float>(max_drow), max_dist, d_idx);
+    ++ctx->launches;
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    return FTK_OK;
+}
+
+int LaunchCosinePairs(ftk_context *ctx, const float *d_ref, const float *d_cur, int dim, int n_ref_total, int n_cur_total, const int *d_ref_pair,
+                      const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx) {
+    if (n_ref_total == 0) return FTK_OK;
+    float *ref_norm, *cur_norm;
+    if (int rc = ComputeNorms(ctx, d_ref, n_ref_total, d_cur, n_cur_total, dim, &ref_norm, &cur_norm)) return rc;
+    const size_t smem = sizeof(float) * static_cast<size_t>(kCosPairsWarps) * dim;
+    CosinePairsKernel<<<Blocks(n_ref_total, kCosPairsWarps), 32 * kCosPairsWarps, smem, ctx->stream>>>(d_ref, d_cur, dim, n_ref_total, d_ref_pair, d_cur_off, ref_norm,
+                                                                                                       cur_norm, d_pred, d_pos, static_cast<float>(max_dcol),
+                                                                                                       static_cast<float>(max_drow), max_dist, d_idx);
     ++ctx->launches;
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;

@@ -153,6 +153,40 @@ private:
     ftk_pyramid *pyr_ = nullptr;
 };
 
+// A batch of same-sized frames, device resident (not in the reference, whose callers loop over frame pairs: the batch entry points
+// below -- OpticalFlow::TrackFeaturesBatch, DescriptorMatcher<T>::MatchPairs -- are how the GPU is kept busy).
+class ImagePyramidBatch {
+public:
+    ImagePyramidBatch() = default;
+    ~ImagePyramidBatch() { Release(); }
+    ImagePyramidBatch(const ImagePyramidBatch &) = delete;
+    ImagePyramidBatch &operator=(const ImagePyramidBatch &) = delete;
+
+    // `images`: n_images tightly packed rows x cols frames in host memory (pinned memory makes the upload asynchronous).
+    bool CreateImagePyramids(const uint8_t *images, int32_t rows, int32_t cols, int32_t n_images, uint32_t level) {
+        if (images == nullptr || level == 0 || n_images <= 0) return false;
+        ftk_context *ctx = Device::Get();
+        if (pyr_ == nullptr || ftk_pyramid_levels(pyr_) != static_cast<int32_t>(level) || rows != rows_ || cols != cols_ || ftk_pyramid_images(pyr_) != n_images) {
+            Release();
+            if (ftk_pyramid_create(ctx, rows, cols, static_cast<int32_t>(level), n_images, &pyr_) != FTK_OK) return false;
+            rows_ = rows, cols_ = cols;
+        }
+        if (ftk_pyramid_set_images(ctx, pyr_, 0, n_images, images, 0) != FTK_OK) return false;
+        return ftk_pyramid_build(ctx, pyr_, 0, n_images) == FTK_OK && ftk_synchronize(ctx) == FTK_OK;
+    }
+    uint32_t level() const { return pyr_ ? static_cast<uint32_t>(ftk_pyramid_levels(pyr_)) : 0u; }
+    int32_t images() const { return pyr_ ? ftk_pyramid_images(pyr_) : 0; }
+    const ftk_pyramid *handle() const { return pyr_; }
+
+private:
+    void Release() {
+        if (pyr_) ftk_pyramid_destroy(Device::Get(), pyr_);
+        pyr_ = nullptr;
+    }
+    int32_t rows_ = 0, cols_ = 0;
+    ftk_pyramid *pyr_ = nullptr;
+};
+
 // src/optical_flow_tracker/optical_flow.h:12-18
 enum class OpticalFlowMethod : uint8_t {
     kInverse = 0,
@@ -207,6 +241,37 @@ public:
         return Track(ref_image, cur_image, ref_pixel_uv, cur_pixel_uv, status, FTK_FLAG_SINGLE_LEVEL);
     }
 
+    // Many frame pairs in one call (ftk_klt_track): pair p tracks features [feat_offsets[p], feat_offsets[p + 1]) from frame
+    // ref_image[p] to frame cur_image[p] of the batch, each with exactly the semantics of TrackFeatures above (kMaxTrackPointsNumber
+    // applies per pair).  Equal to looping over the pairs; one launch instead of one call per pair.
+    bool TrackFeaturesBatch(const ImagePyramidBatch &pyramids, const std::vector<int32_t> &ref_image, const std::vector<int32_t> &cur_image,
+                            const std::vector<int32_t> &feat_offsets, const std::vector<Vec2> &ref_pixel_uv, std::vector<Vec2> &cur_pixel_uv,
+                            std::vector<uint8_t> &status) {
+        if (ref_pixel_uv.empty() || !pyramids.handle()) return false;
+        const size_t n_pairs = ref_image.size();
+        if (n_pairs == 0 || cur_image.size() != n_pairs || feat_offsets.size() != n_pairs + 1 || static_cast<size_t>(feat_offsets.back()) != ref_pixel_uv.size()) return false;
+        ftk_klt_params p = Params();
+        uint32_t flags = 0;
+        const size_t n = ref_pixel_uv.size();
+        std::vector<float> ref_flat(2 * n), cur_flat(2 * n, 0.0f);
+        for (size_t i = 0; i < n; ++i) ref_flat[2 * i] = ref_pixel_uv[i].x(), ref_flat[2 * i + 1] = ref_pixel_uv[i].y();
+        if (cur_pixel_uv.size() == n) {
+            for (size_t i = 0; i < n; ++i) cur_flat[2 * i] = cur_pixel_uv[i].x(), cur_flat[2 * i + 1] = cur_pixel_uv[i].y();
+        } else {
+            flags |= FTK_FLAG_NO_PREDICTION;
+        }
+        if (status.size() != n) {
+            flags |= FTK_FLAG_NO_STATUS;
+            status.assign(n, static_cast<uint8_t>(TrackStatus::kNotTracked));
+        }
+        if (ftk_klt_track(Device::Get(), &p, pyramids.handle(), pyramids.handle(), static_cast<int32_t>(n_pairs), ref_image.data(), cur_image.data(), feat_offsets.data(),
+                          ref_flat.data(), cur_flat.data(), status.data(), flags) != FTK_OK)
+            return false;
+        cur_pixel_uv.resize(n);
+        for (size_t i = 0; i < n; ++i) cur_pixel_uv[i] = Vec2(cur_flat[2 * i], cur_flat[2 * i + 1]);
+        return true;
+    }
+
     OpticalFlowOptions &options() { return options_; }
     const OpticalFlowOptions &options() const { return options_; }
 
@@ -218,10 +283,7 @@ protected:
     virtual void FillParams(ftk_klt_params &p) const = 0;
 
 private:
-    bool Track(const ImagePyramid &ref, const ImagePyramid &cur, const std::vector<Vec2> &ref_uv, std::vector<Vec2> &cur_uv, std::vector<uint8_t> &status,
-               uint32_t flags) {
-        if (!ref.handle() || !cur.handle()) return false;
-        const int32_t n = static_cast<int32_t>(ref_uv.size());
+    ftk_klt_params Params() const {
         ftk_klt_params p;
         ftk_klt_params_default(&p);
         p.max_track_points = options_.kMaxTrackPointsNumber;
@@ -233,6 +295,13 @@ private:
         p.method = static_cast<int32_t>(options_.kMethod);
         p.forward_backward_max_error = forward_backward_max_error_;
         FillParams(p);
+        return p;
+    }
+    bool Track(const ImagePyramid &ref, const ImagePyramid &cur, const std::vector<Vec2> &ref_uv, std::vector<Vec2> &cur_uv, std::vector<uint8_t> &status,
+               uint32_t flags) {
+        if (!ref.handle() || !cur.handle()) return false;
+        const int32_t n = static_cast<int32_t>(ref_uv.size());
+        ftk_klt_params p = Params();
         std::vector<float> ref_flat(2 * static_cast<size_t>(n)), cur_flat(2 * static_cast<size_t>(n), 0.0f);
         for (int32_t i = 0; i < n; ++i) ref_flat[2 * i] = ref_uv[i].x(), ref_flat[2 * i + 1] = ref_uv[i].y();
         if (cur_uv.size() == ref_uv.size()) {
@@ -374,10 +443,62 @@ public:
         return FillMatchedPixelByPairIndices(index_pairs_in_cur, pixel_uv_cur, matched_pixel_uv_cur, status);
     }
 
+    // Many independent ForceMatch (pixel_uv_* == nullptr) or NearbyMatch problems in one call (ftk_match_hamming_pairs /
+    // ftk_match_cosine_pairs): pair p matches descriptors_ref[ref_offsets[p] .. ref_offsets[p + 1]) against
+    // descriptors_cur[cur_offsets[p] .. cur_offsets[p + 1]); index_pairs_in_cur[i] is the index INSIDE the pair's current block.
+    bool MatchPairs(const std::vector<DescriptorType> &descriptors_ref, const std::vector<int32_t> &ref_offsets, const std::vector<DescriptorType> &descriptors_cur,
+                    const std::vector<int32_t> &cur_offsets, const std::vector<Vec2> *pixel_uv_pred_in_cur, const std::vector<Vec2> *pixel_uv_cur,
+                    std::vector<int32_t> &index_pairs_in_cur) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        if (descriptors_cur.empty() || ref_offsets.size() < 2 || ref_offsets.size() != cur_offsets.size()) return false;
+        if (static_cast<size_t>(ref_offsets.back()) != descriptors_ref.size() || static_cast<size_t>(cur_offsets.back()) != descriptors_cur.size()) return false;
+        if ((pixel_uv_pred_in_cur == nullptr) != (pixel_uv_cur == nullptr)) return false;
+        if (pixel_uv_pred_in_cur && (pixel_uv_pred_in_cur->size() != descriptors_ref.size() || pixel_uv_cur->size() != descriptors_cur.size())) return false;
+        const size_t len = Traits::Size(descriptors_cur[0]);
+        for (const auto &d : descriptors_ref)
+            if (Traits::Size(d) != len) return false;
+        for (const auto &d : descriptors_cur)
+            if (Traits::Size(d) != len) return false;
+        if (len == 0) return false;
+        CheckOverride(descriptors_ref, descriptors_cur);
+        const uint32_t flags = PrepareIndex(descriptors_ref.size(), index_pairs_in_cur);
+        std::vector<float> pred_flat, pos_flat;
+        if (pixel_uv_pred_in_cur) pred_flat = Flatten(*pixel_uv_pred_in_cur), pos_flat = Flatten(*pixel_uv_cur);
+        const float *pred = pixel_uv_pred_in_cur ? pred_flat.data() : nullptr, *pos = pixel_uv_pred_in_cur ? pos_flat.data() : nullptr;
+        const int32_t n_pairs = static_cast<int32_t>(ref_offsets.size()) - 1;
+        ftk_context *ctx = Device::Get();
+        if constexpr (Traits::kBinary) {
+            const int32_t words = static_cast<int32_t>((len + 31) / 32);
+            const std::vector<uint32_t> r = PackBits(descriptors_ref, len, words), c = PackBits(descriptors_cur, len, words);
+            return ftk_match_hamming_pairs(ctx, r.data(), c.data(), words, n_pairs, ref_offsets.data(), cur_offsets.data(), pred, pos, options_.kMaxValidPredictRowDistance,
+                                           options_.kMaxValidPredictColDistance, options_.kMaxValidDescriptorDistance, index_pairs_in_cur.data(), flags) == FTK_OK;
+        } else {
+            const int32_t dim = static_cast<int32_t>(len);
+            const std::vector<float> r = PackFloats(descriptors_ref, dim), c = PackFloats(descriptors_cur, dim);
+            return ftk_match_cosine_pairs(ctx, r.data(), c.data(), dim, n_pairs, ref_offsets.data(), cur_offsets.data(), pred, pos, options_.kMaxValidPredictRowDistance,
+                                          options_.kMaxValidPredictColDistance, options_.kMaxValidDescriptorDistance, index_pairs_in_cur.data(), flags) == FTK_OK;
+        }
+    }
+
     Options &options() { return options_; }
     const Options &options() const { return options_; }
 
 private:
+    static std::vector<uint32_t> PackBits(const std::vector<DescriptorType> &set, size_t len, int32_t words) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        std::vector<uint32_t> out(set.size() * static_cast<size_t>(words), 0u);
+        for (size_t i = 0; i < set.size(); ++i)
+            for (size_t k = 0; k < len; ++k)
+                if (Traits::At(set[i], k)) out[i * words + k / 32] |= 1u << (k % 32);
+        return out;
+    }
+    static std::vector<float> PackFloats(const std::vector<DescriptorType> &set, int32_t dim) {
+        using Traits = DescriptorTraits<DescriptorType>;
+        std::vector<float> out(set.size() * static_cast<size_t>(dim));
+        for (size_t i = 0; i < set.size(); ++i)
+            for (int32_t k = 0; k < dim; ++k) out[i * dim + k] = static_cast<float>(Traits::At(set[i], k));
+        return out;
+    }
     // descriptor_matcher.h:45 declares `virtual float ComputeDistance(ref, cur) = 0` and the reference's subclasses override it
     // (test/test_descriptor_matcher_brief.cpp:33, test_descriptor_matcher_superpoint.cpp:32).  Kept so those subclasses compile
     // unchanged; the default is the metric the GPU evaluates.  It is never called per pair: Run() spot-checks the override.
@@ -446,24 +567,14 @@ private:
         int rc;
         if constexpr (Traits::kBinary) {
             const int32_t words = static_cast<int32_t>((len + 31) / 32);
-            std::vector<uint32_t> r(static_cast<size_t>(n_ref) * words, 0u), c(static_cast<size_t>(n_cur) * words, 0u);
-            for (int32_t i = 0; i < n_ref; ++i)
-                for (size_t k = 0; k < len; ++k)
-                    if (Traits::At(ref[i], k)) r[static_cast<size_t>(i) * words + k / 32] |= 1u << (k % 32);
-            for (int32_t j = 0; j < n_cur; ++j)
-                for (size_t k = 0; k < len; ++k)
-                    if (Traits::At(cur[j], k)) c[static_cast<size_t>(j) * words + k / 32] |= 1u << (k % 32);
+            const std::vector<uint32_t> r = PackBits(ref, len, words), c = PackBits(cur, len, words);
             rc = pred ? ftk_match_hamming_nearby(ctx, r.data(), n_ref, c.data(), n_cur, words, pred_flat.data(), pos_flat.data(),
                                                  options_.kMaxValidPredictRowDistance, options_.kMaxValidPredictColDistance,
                                                  options_.kMaxValidDescriptorDistance, idx.data(), flags)
                       : ftk_match_hamming_force(ctx, r.data(), n_ref, c.data(), n_cur, words, options_.kMaxValidDescriptorDistance, idx.data(), flags);
         } else {
             const int32_t dim = static_cast<int32_t>(len);
-            std::vector<float> r(static_cast<size_t>(n_ref) * dim), c(static_cast<size_t>(n_cur) * dim);
-            for (int32_t i = 0; i < n_ref; ++i)
-                for (int32_t k = 0; k < dim; ++k) r[static_cast<size_t>(i) * dim + k] = Traits::At(ref[i], k);
-            for (int32_t j = 0; j < n_cur; ++j)
-                for (int32_t k = 0; k < dim; ++k) c[static_cast<size_t>(j) * dim + k] = Traits::At(cur[j], k);
+            const std::vector<float> r = PackFloats(ref, dim), c = PackFloats(cur, dim);
             rc = pred ? ftk_match_cosine_nearby(ctx, r.data(), n_ref, c.data(), n_cur, dim, pred_flat.data(), pos_flat.data(),
                                                 options_.kMaxValidPredictRowDistance, options_.kMaxValidPredictColDistance,
                                                 options_.kMaxValidDescriptorDistance, idx.data(), flags)

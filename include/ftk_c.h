@@ -273,6 +273,11 @@ int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_re
 int ftk_match_hamming_pairs(ftk_context *ctx, const uint32_t *ref, const uint32_t *cur, int32_t words, int32_t n_pairs, const int32_t *ref_offsets,
                             const int32_t *cur_offsets, const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist,
                             int32_t *idx, uint32_t flags);
+/* The same for float descriptors (row-major n x dim, dim <= 1024; distance 0.5 - 0.5 * cos as in ftk_match_cosine_*): every pair is an
+ * independent ForceMatch (pred_uv == NULL) or NearbyMatch of the reference, evaluated with its own sequential fp32 arithmetic. */
+int ftk_match_cosine_pairs(ftk_context *ctx, const float *ref, const float *cur, int32_t dim, int32_t n_pairs, const int32_t *ref_offsets,
+                           const int32_t *cur_offsets, const float *pred_uv, const float *cur_uv, int32_t max_drow, int32_t max_dcol, float max_dist,
+                           int32_t *idx, uint32_t flags);
 /* Float descriptors, row-major n x dim, distance 0.5 - 0.5 * cos(ref, cur). */
 int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, const float *cur, int32_t n_cur, int32_t dim, float max_dist,
                            int32_t *idx, uint32_t flags);

@@ -8,6 +8,7 @@
 //   boundary_test <in.bin> <out.bin>      (fixture layout: see tests/test_facade.py)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 
@@ -131,6 +132,53 @@ int main(int argc, char **argv) {
         const int32_t shape[2] = {im.rows(), im.cols()};
         fwrite(shape, sizeof(int32_t), 2, out);
         fwrite(im.data(), 1, size_t(im.rows()) * im.cols(), out);
+    }
+    // ---- batch entry points == loops over the single-pair calls ----
+    {
+        std::vector<uint8_t> frames(4 * size_t(rows) * cols);  // frames 0, 1 = ref, cur; 2, 3 = cur, ref (the reverse pair)
+        const size_t plane = size_t(rows) * cols;
+        memcpy(&frames[0], ref_img.data(), plane), memcpy(&frames[plane], cur_img.data(), plane);
+        memcpy(&frames[2 * plane], cur_img.data(), plane), memcpy(&frames[3 * plane], ref_img.data(), plane);
+        ImagePyramidBatch batch;
+        if (!batch.CreateImagePyramids(frames.data(), rows, cols, 4, levels)) return 5;
+        const int half_n = n / 2;
+        std::vector<Vec2> uv2(ref_pixel_uv.begin(), ref_pixel_uv.end());
+        uv2.insert(uv2.end(), ref_pixel_uv.begin(), ref_pixel_uv.begin() + half_n);
+        const std::vector<int32_t> ref_idx = {0, 2}, cur_idx = {1, 3}, offsets = {0, n, n + half_n};
+        std::vector<Vec2> batch_uv;
+        std::vector<uint8_t> batch_st;
+        OpticalFlowAffineKlt affine;
+        int32_t batch_ok = affine.TrackFeaturesBatch(batch, ref_idx, cur_idx, offsets, uv2, batch_uv, batch_st) ? 1 : 0;
+        ImagePyramid pa, pb;
+        pa.SetRawImage(ref_img.data(), rows, cols), pb.SetRawImage(cur_img.data(), rows, cols);
+        pa.CreateImagePyramid(levels), pb.CreateImagePyramid(levels);
+        std::vector<Vec2> uv_fwd, uv_bwd, first_half(ref_pixel_uv.begin(), ref_pixel_uv.begin() + half_n);
+        std::vector<uint8_t> st_fwd, st_bwd;
+        affine.TrackFeatures(pa, pb, ref_pixel_uv, uv_fwd, st_fwd);
+        affine.TrackFeatures(pb, pa, first_half, uv_bwd, st_bwd);
+        int32_t differ = 0;
+        for (int i = 0; i < n; ++i) differ += memcmp(&batch_uv[i], &uv_fwd[i], sizeof(Vec2)) != 0 || batch_st[i] != st_fwd[i];
+        for (int i = 0; i < half_n; ++i) differ += memcmp(&batch_uv[n + i], &uv_bwd[i], sizeof(Vec2)) != 0 || batch_st[n + i] != st_bwd[i];
+        fwrite(&batch_ok, sizeof(batch_ok), 1, out);
+        fwrite(&differ, sizeof(differ), 1, out);
+
+        // MatchPairs (binary and float) against per-pair ForceMatch
+        const int r_split = n_ref / 3, c_split = n_cur / 2;
+        const std::vector<int32_t> ro = {0, r_split, n_ref}, co = {0, c_split, n_cur};
+        std::vector<int32_t> pairs_idx, fpairs_idx;
+        int32_t pairs_ok = brief.MatchPairs(rb, ro, cb, co, nullptr, nullptr, pairs_idx) ? 1 : 0;
+        pairs_ok = (pairs_ok && cosine.MatchPairs(rf, ro, cf, co, nullptr, nullptr, fpairs_idx)) ? 1 : 0;
+        int32_t pairs_differ = 0;
+        for (int q = 0; q < 2; ++q) {
+            std::vector<BriefType> r1(rb.begin() + ro[q], rb.begin() + ro[q + 1]), c1(cb.begin() + co[q], cb.begin() + co[q + 1]);
+            std::vector<FloatDescriptor> r2(rf.begin() + ro[q], rf.begin() + ro[q + 1]), c2(cf.begin() + co[q], cf.begin() + co[q + 1]);
+            std::vector<int32_t> i1, i2;
+            brief.ForceMatch(r1, c1, i1);
+            cosine.ForceMatch(r2, c2, i2);
+            for (size_t i = 0; i < i1.size(); ++i) pairs_differ += i1[i] != pairs_idx[ro[q] + i] || i2[i] != fpairs_idx[ro[q] + i];
+        }
+        fwrite(&pairs_ok, sizeof(pairs_ok), 1, out);
+        fwrite(&pairs_differ, sizeof(pairs_differ), 1, out);
     }
     fclose(in);
     fclose(out);

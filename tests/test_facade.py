@@ -88,6 +88,9 @@ def test_boundary_program_matches_oracle(tmp_path, oracle):
     for l, lv in enumerate(oracle.pyramid_build(ref, levels)):
         r, c = take(np.int32, 2)
         assert (r, c) == lv.shape and (take(np.uint8, r * c).reshape(r, c) == lv).all(), l
+    # batch entry points of the facade == loops over its single-pair calls (TrackFeaturesBatch; MatchPairs binary + float)
+    assert list(take(np.int32, 2)) == [1, 0]
+    assert list(take(np.int32, 2)) == [1, 0]
     assert off == len(data)
 
 

@@ -537,6 +537,47 @@ def test_cosine_two_devices_in_one_process(oracle):
         assert ok and np.array_equal(idx, exp)
 
 
+def test_cosine_pair_batches_vs_oracle(ctx, oracle):
+    """ftk_match_cosine_pairs: many independent ForceMatch / NearbyMatch problems (ragged sizes, an empty ref set, an empty cur set,
+    exact duplicates whose distance rounds to 0 -> NearbyMatch's break) == the reference's per-pair calls."""
+    rng = np.random.default_rng(91)
+    sizes = [(40, 55), (0, 10), (33, 1), (7, 0), (120, 90), (64, 64)]
+    refs, curs, preds, poss = [], [], [], []
+    for q, (nr, nc) in enumerate(sizes):
+        a, b = S.make_float_sets(max(nr, 1), max(nc, 1), dim=128, seed=200 + q)
+        a, b = a[:nr].copy(), b[:nc].copy()
+        if nr > 5 and nc > 9:
+            a[3] = b[8]  # exact duplicate
+        refs.append(a), curs.append(b)
+        poss.append(np.stack([rng.uniform(0, 751, nc), rng.uniform(0, 479, nc)], 1).astype(np.float32))
+        preds.append(np.stack([rng.uniform(0, 751, nr), rng.uniform(0, 479, nr)], 1).astype(np.float32))
+        if nr > 5 and nc > 9:
+            preds[-1][3] = poss[-1][8]
+    ro = np.concatenate([[0], np.cumsum([x[0] for x in sizes])]).astype(np.int32)
+    co = np.concatenate([[0], np.cumsum([x[1] for x in sizes])]).astype(np.int32)
+    R, Cc = np.concatenate(refs), np.concatenate(curs)
+    c = ft.CosineMatcher(ctx)
+    c.options().kMaxValidDescriptorDistance = 0.45
+    c.options().kMaxValidPredictRowDistance, c.options().kMaxValidPredictColDistance = 200, 300
+    ok, idx = c.MatchPairs(R, ro, Cc, co)
+    ok2, nidx = c.MatchPairs(R, ro, Cc, co, np.concatenate(preds), np.concatenate(poss))
+    assert ok and ok2
+    matched = 0
+    for q, (nr, nc) in enumerate(sizes):
+        got, ngot = idx[ro[q]:ro[q + 1]], nidx[ro[q]:ro[q + 1]]
+        if nr == 0:
+            continue
+        if nc == 0:  # the reference returns false and touches nothing: the entries keep their initial -1
+            assert (got == -1).all() and (ngot == -1).all()
+            continue
+        exp = oracle.match_cosine_force(refs[q], curs[q], 0.45)[1]
+        nexp = oracle.match_cosine_nearby(refs[q], curs[q], preds[q], poss[q], 200, 300, 0.45)[1]
+        assert np.array_equal(got, exp), (q, np.nonzero(got != exp)[0][:5])
+        assert np.array_equal(ngot, nexp), (q, np.nonzero(ngot != nexp)[0][:5])
+        matched += int((exp >= 0).sum())
+    assert matched > 100
+
+
 def test_cosine_nearby_vs_oracle(ctx, oracle):
     rf, cf = S.make_float_sets(300, 350, dim=256, seed=31)
     rng = np.random.default_rng(8)
