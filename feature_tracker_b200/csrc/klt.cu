@@ -756,6 +756,49 @@ __device__ __forceinline__ void LssdSolve(Ctx<G> &c, float (&v)[3]) {
     LdltSolveShared<3, G>(c.g, s, v);
 }
 
+// Second pass of lssd_klt.cpp:127-250 (Jacobians, residuals, 9 chains) over the pixels of `ok_bits`.  FAST: both patch means are
+// in the shared-divisor range (always, for real images), so every division is the 3-instruction form.
+template <int METHOD, int G, bool FAST>
+__device__ __forceinline__ void LssdSecondPass(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ok_bits,
+                                               const SharedDivisor &by_ref, const SharedDivisor &by_cur) {
+    c.ch.reset();
+    int chunk = 0;
+    PatchWalk w = c.walk;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        float t[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
+        if ((ok_bits >> chunk) & 1ull) {
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            float row_j, col_j;
+            LssdWarp(s, col_i, row_i, &col_j, &row_j);
+            const Img &gi = METHOD == kInverse ? ref : cur;
+            const float gr = METHOD == kInverse ? row_i : row_j, gc = METHOD == kInverse ? col_i : col_j;
+            const float v0 = PxF(gi, gr, fsub(gc, 1.0f));
+            const float v1 = PxF(gi, gr, fadd(gc, 1.0f));
+            const float v2 = PxF(gi, fsub(gr, 1.0f), gc);
+            const float v3 = PxF(gi, fadd(gr, 1.0f), gc);
+            const float v4 = PxF(ref, row_i, col_i);
+            const float v5 = PxF(cur, row_j, col_j);
+            const SharedDivisor &by_avg = METHOD == kInverse ? by_ref : by_cur;
+            const float jp0 = DivideBy<FAST>(by_avg, fsub(v1, v0)), jp1 = DivideBy<FAST>(by_avg, fsub(v3, v2));
+            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
+            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
+            float J[3];
+            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
+            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
+            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
+            const float residual = fsub(DivideBy<FAST>(by_cur, v5), DivideBy<FAST>(by_ref, v4));
+            LssdTerms(J, residual, t);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
+        c.ch.template fold<9>(c.g);
+        w.next();
+    }
+}
+
 // lssd_klt.cpp:127-250 ConstructIncrementalFunction: pass 1 = validity + patch means (2 chains), pass 2 = 9 chains.
 template <int METHOD, int G>
 __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, const LssdState &s) {
@@ -793,44 +836,8 @@ __device__ int LssdConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float re
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
     const SharedDivisor by_ref = MakeSharedDivisor(ref_avg), by_cur = MakeSharedDivisor(cur_avg);  // every division below is by one of the two patch means
-
-    c.ch.reset();
-    chunk = 0;
-    w = c.walk;
-    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
-        const int k = base + c.g.lane;
-        float t[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
-        if ((ok_bits >> chunk) & 1ull) {
-            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
-            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
-            float row_j, col_j;
-            LssdWarp(s, col_i, row_i, &col_j, &row_j);
-            const Img &gi = METHOD == kInverse ? ref : cur;
-            const float gr = METHOD == kInverse ? row_i : row_j, gc = METHOD == kInverse ? col_i : col_j;
-            const float v0 = PxF(gi, gr, fsub(gc, 1.0f));
-            const float v1 = PxF(gi, gr, fadd(gc, 1.0f));
-            const float v2 = PxF(gi, fsub(gr, 1.0f), gc);
-            const float v3 = PxF(gi, fadd(gr, 1.0f), gc);
-            const float v4 = PxF(ref, row_i, col_i);
-            const float v5 = PxF(cur, row_j, col_j);
-            const SharedDivisor &by_avg = METHOD == kInverse ? by_ref : by_cur;
-            const float jp0 = DivideBy(by_avg, fsub(v1, v0)), jp1 = DivideBy(by_avg, fsub(v3, v2));
-            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
-            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
-            float J[3];
-            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
-            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
-            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
-            const float residual = fsub(DivideBy(by_cur, v5), DivideBy(by_ref, v4));
-            LssdTerms(J, residual, t);
-        }
-#pragma unroll
-        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
-        c.ch.template fold<9>(c.g);
-        w.next();
-    }
+    if (by_ref.fast && by_cur.fast) LssdSecondPass<METHOD, G, true>(c, ref, cur, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
+    else LssdSecondPass<METHOD, G, false>(c, ref, cur, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
     return valid;
 }
 
@@ -861,6 +868,40 @@ __device__ unsigned long long LssdHoistRef(Ctx<G> &c, const Img &ref, float ref_
         w.next();
     }
     return ref_bits;
+}
+
+// Second pass of the hoisted kInverse form: Jacobians and residuals from the per-level fx / fy / v4 and this iteration's v5.
+template <int G, bool FAST>
+__device__ __forceinline__ void LssdSecondPassHoisted(Ctx<G> &c, float ref_x, float ref_y, const LssdState &s, unsigned long long ok_bits,
+                                                      const SharedDivisor &by_ref, const SharedDivisor &by_cur) {
+    const int pf = RoundUp(c.geo.psize, 4);
+    const float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf, *hv5 = c.s.hoist + 3 * pf;
+    c.ch.reset();
+    int chunk = 0;
+    PatchWalk w = c.walk;
+    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
+        const int k = base + c.g.lane;
+        float t[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
+        if ((ok_bits >> chunk) & 1ull) {
+            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
+            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
+            const float jp0 = DivideBy<FAST>(by_ref, hfx[k]), jp1 = DivideBy<FAST>(by_ref, hfy[k]);
+            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
+            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
+            float J[3];
+            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
+            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
+            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
+            const float residual = fsub(DivideBy<FAST>(by_cur, hv5[k]), DivideBy<FAST>(by_ref, hv4[k]));
+            LssdTerms(J, residual, t);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
+        c.ch.template fold<9>(c.g);
+        w.next();
+    }
 }
 
 // lssd_klt.cpp:127-250 ConstructIncrementalFunction, kInverse, on top of the hoisted reference samples.
@@ -900,33 +941,8 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
     const SharedDivisor by_ref = MakeSharedDivisor(ref_avg), by_cur = MakeSharedDivisor(cur_avg);  // every division below is by one of the two patch means
-
-    c.ch.reset();
-    chunk = 0;
-    w = c.walk;
-    for (int base = 0; base < c.geo.psize; base += G, ++chunk) {
-        const int k = base + c.g.lane;
-        float t[9];
-#pragma unroll
-        for (int q = 0; q < 9; ++q) t[q] = 0.0f;
-        if ((ok_bits >> chunk) & 1ull) {
-            const int drow = w.row - c.geo.hr, dcol = w.col - c.geo.hc;
-            const float row_i = fadd(static_cast<float>(drow), ref_y), col_i = fadd(static_cast<float>(dcol), ref_x);
-            const float jp0 = DivideBy(by_ref, hfx[k]), jp1 = DivideBy(by_ref, hfy[k]);
-            const float s00 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
-            const float s10 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
-            float J[3];
-            J[0] = fadd(fmul(jp0, s00), fmul(jp1, s10));
-            J[1] = fadd(fmul(jp0, 1.0f), fmul(jp1, 0.0f));
-            J[2] = fadd(fmul(jp0, 0.0f), fmul(jp1, 1.0f));
-            const float residual = fsub(DivideBy(by_cur, hv5[k]), DivideBy(by_ref, hv4[k]));
-            LssdTerms(J, residual, t);
-        }
-#pragma unroll
-        for (int q = 0; q < 9; ++q) c.ch.put(c.g.lane, q, t[q]);
-        c.ch.template fold<9>(c.g);
-        w.next();
-    }
+    if (by_ref.fast && by_cur.fast) LssdSecondPassHoisted<G, true>(c, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
+    else LssdSecondPassHoisted<G, false>(c, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
     return valid;
 }
 

@@ -40,9 +40,11 @@ __device__ __forceinline__ SharedDivisor MakeSharedDivisor(float divisor) {
     d.fast = divisor >= 9.5367431640625e-07f && divisor <= 1048576.0f;
     return d;
 }
-// |a| is 0 or in [2^-100, 2^100] for every caller (bilinear samples of 8-bit pixels and their differences)
+// |a| is 0 or in [2^-100, 2^100] for every caller (bilinear samples of 8-bit pixels and their differences).  FAST is hoisted out of
+// the pixel loops by the callers (both divisors in range), so the loop bodies carry no branch and no general-division slow path.
+template <bool FAST>
 __device__ __forceinline__ float DivideBy(const SharedDivisor &d, float a) {
-    if (!d.fast) return __fdiv_rn(a, d.b);
+    if (!FAST) return __fdiv_rn(a, d.b);
     const float q0 = __fmul_rn(a, d.y);
     const float r = __fmaf_rn(-d.b, q0, a);
     return __fmaf_rn(r, d.y, q0);

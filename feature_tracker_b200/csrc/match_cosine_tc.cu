@@ -147,6 +147,46 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 // `abn_cur`), an abnormal REFERENCE row is scanned exactly against the whole current set.  Their BF16 rows are zero.
 __device__ __forceinline__ bool AbnormalNorm(float nrm) { return !(nrm >= 1e-12f && nrm <= 1e12f); }
 
+// Row stride (floats) of the staged descriptor / product rows: a multiple of 4 that is 4 (mod 32), so that 32 threads reading float4s
+// at the same offset of 32 different rows touch all banks exactly once per quarter-warp (no conflicts), and rows stay 16-byte aligned.
+__host__ __device__ inline int StagedStride(int dim) {
+    int s = (dim + 3) / 4 * 4;
+    while (s % 32 != 4) s += 4;
+    return s;
+}
+
+// s = (..((f(p[0]) + f(p[1])) + f(p[2])) + ...) in ascending k -- the reference's scalar order -- over a 16-byte aligned shared row.  The
+// adds form one dependent chain (4 cycles each); the loads do not depend on it, so they are issued as float4s two groups ahead: the
+// chain, not the shared-memory latency, sets the pace (a scalar load per add made this loop ~30 cycles per element).
+template <bool SQUARE>
+__device__ __forceinline__ float SequentialRowSum(const float *row, int dim) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    const int n4 = dim >> 2;
+    auto f = [](float v) { return SQUARE ? __fmul_rn(v, v) : v; };
+    float s;
+    int k4 = 0;
+    if (n4 == 0) {
+        s = f(row[0]);
+        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, f(row[k]));
+        return s;
+    }
+    float4 a = r4[0], b = n4 > 1 ? r4[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s = f(a.x);
+    s = __fadd_rn(s, f(a.y));
+    s = __fadd_rn(s, f(a.z));
+    s = __fadd_rn(s, f(a.w));
+    for (k4 = 1; k4 < n4; ++k4) {
+        const float4 cur = b;
+        if (k4 + 1 < n4) b = r4[k4 + 1];
+        s = __fadd_rn(s, f(cur.x));
+        s = __fadd_rn(s, f(cur.y));
+        s = __fadd_rn(s, f(cur.z));
+        s = __fadd_rn(s, f(cur.w));
+    }
+    for (int k = n4 << 2; k < dim; ++k) s = __fadd_rn(s, f(row[k]));
+    return s;
+}
+
 // norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA) -- and the
 // unit-normalised BF16 copy, for BOTH descriptor sets in one launch (blocks [0, ref_blocks) = reference rows, the rest = current
 // rows).  32 descriptors per block: rows are staged through shared memory so global reads and writes are coalesced while each
@@ -156,13 +196,13 @@ constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref, int n_ref, const float *cur, int n_cur, int ref_blocks, int dim, int k_pad,
                                                               float *ref_norm, float *cur_norm, __nv_bfloat16 *ref_unit, __nv_bfloat16 *cur_unit,
                                                               int *counters, int *abn_cur) {
-    extern __shared__ float prep_smem[];  // [kPrepRows][dim + 1] + [kPrepRows]
+    extern __shared__ __align__(16) float prep_smem[];  // [kPrepRows][StagedStride(dim)] + [kPrepRows]
     const bool is_cur = static_cast<int>(blockIdx.x) >= ref_blocks;
     const float *desc = is_cur ? cur : ref;
     const int n = is_cur ? n_cur : n_ref;
     float *norm = is_cur ? cur_norm : ref_norm;
     __nv_bfloat16 *unit = is_cur ? cur_unit : ref_unit;
-    const int stride = dim + 1;
+    const int stride = StagedStride(dim);
     float *s_norm = prep_smem + kPrepRows * stride;
     const int row0 = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows;
     const int rows = min(kPrepRows, n - row0);
@@ -192,11 +232,7 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
     }
     __syncthreads();
     if (threadIdx.x < rows) {
-        const float *a = prep_smem + threadIdx.x * stride;
-        float s = __fmul_rn(a[0], a[0]);
-#pragma unroll 8
-        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, __fmul_rn(a[k], a[k]));
-        const float nrm = __fsqrt_rn(s);
+        const float nrm = __fsqrt_rn(SequentialRowSum<true>(prep_smem + threadIdx.x * stride, dim));
         norm[row0 + threadIdx.x] = nrm;
         const bool abnormal = AbnormalNorm(nrm);
         // The BF16 copy only feeds the screening GEMM, whose error margin (kEpsDot) has room for the 1-ulp difference between
@@ -436,36 +472,50 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
                                                               const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
                                                               unsigned long long *best, int2 *work, int *counters, const int *abn_cur, float max_dist,
                                                               int *idx) {
-    extern __shared__ float rerank_smem[];  // [kRerankRows][dim + 1] products
+    extern __shared__ __align__(16) float rerank_smem[];  // [kRerankRows][StagedStride(dim)] products
     __shared__ int s_cand[kRerankRows][kMaxSplits];  // candidate columns of each row, in split order
     __shared__ int s_count[kRerankRows];
     __shared__ unsigned s_scan[kRerankRows];  // split mask the exact scan has to cover
-    const int stride = dim + 1;
+    const int stride = StagedStride(dim);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRerankRows;
     const unsigned all_splits = (1u << n_splits) - 1u;  // n_splits <= kMaxSplits = 16
 
     // ---- 1. screening ----
-    for (int r = warp; r < kRerankRows; r += kRerankThreads / 32) {
+    // warp w owns rows w, w + 4, ..., w + 28; lane s < n_splits holds column split s.  All eight top-2 records of a lane are loaded
+    // before the first reduction, so the warp waits for global memory once instead of once per row.
+    constexpr int kRowsPerWarp = kRerankRows / (kRerankThreads / 32);
+    Top2 mine[kRowsPerWarp];
+    float rnorm[kRowsPerWarp];
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int i = row0 + warp + q * (kRerankThreads / 32);
+        mine[q].b1 = -INFINITY, mine[q].j1 = -1, mine[q].b2 = -INFINITY, mine[q].j2 = -1;
+        rnorm[q] = 1.0f;
+        if (i < n_ref) {
+            if (lane < n_splits) mine[q] = top[static_cast<size_t>(lane) * n_ref_pad + i];
+            rnorm[q] = ref_norm[i];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kRowsPerWarp; ++q) {
+        const int r = warp + q * (kRerankThreads / 32);
         const int i = row0 + r;
         int count = 0;
         unsigned scan = 0u;
         if (i < n_ref) {
-            if (AbnormalNorm(ref_norm[i])) {
+            if (AbnormalNorm(rnorm[q])) {
                 scan = all_splits;  // nothing the tensor-core pass said about this row can be trusted
             } else {
-                Top2 mine;
-                mine.b1 = -INFINITY, mine.j1 = -1, mine.b2 = -INFINITY, mine.j2 = -1;
-                if (lane < n_splits) mine = top[static_cast<size_t>(lane) * n_ref_pad + i];
-                float gmax = mine.b1;
+                float gmax = mine[q].b1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
                 const float thr = gmax - 2.0f * kEpsDot;
-                const bool cand = gmax > -INFINITY && mine.j1 >= 0 && mine.b1 >= thr;
-                const bool crowded = cand && mine.j2 >= 0 && mine.b2 >= thr;
+                const bool cand = gmax > -INFINITY && mine[q].j1 >= 0 && mine[q].b1 >= thr;
+                const bool crowded = cand && mine[q].j2 >= 0 && mine[q].b2 >= thr;
                 const unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
                 scan = __ballot_sync(0xFFFFFFFFu, crowded);
-                if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine.j1;
+                if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine[q].j1;
                 count = __popc(todo);
             }
         }
@@ -513,10 +563,7 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
         if (!__syncthreads_or(any)) break;
         if (warp == 0 && round < s_count[lane]) {
             const int i = row0 + lane, j = s_cand[lane][round];
-            const float *prod = rerank_smem + lane * stride;
-            float s = prod[0];
-#pragma unroll 8
-            for (int k = 1; k < dim; ++k) s = __fadd_rn(s, prod[k]);
+            const float s = SequentialRowSum<false>(rerank_smem + lane * stride, dim);
             const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, ref_norm[i]), cur_norm[j]), 0.5f));
             if (d == d) {
                 const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
@@ -672,7 +719,7 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
         return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
 
     FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, 16, st));
-    const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * (dim + 1) + kPrepRows);
+    const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * StagedStride(dim) + kPrepRows);
     const int ref_blocks = Blocks(n_ref, kPrepRows);
     NormPrepKernel<<<ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_ref, n_ref, d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm,
                                                                                           ref_unit, cur_unit, counters, abn_cur);
@@ -686,7 +733,7 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
                                                                           floor_dot);
     ProfEnd(ctx);
-    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * (dim + 1), st>>>(
+    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * StagedStride(dim), st>>>(
         d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx);
     ExactScanKernel<<<ctx->sm_count * 2, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters, tiles_per_split * kTileN, splits, best, max_dist,
                                                        d_idx);
