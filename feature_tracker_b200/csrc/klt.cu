@@ -55,6 +55,7 @@ __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G,
     SmemLayout l{};
     const int kmax = variant == FTK_VARIANT_BASIC ? 5 : (variant == FTK_VARIANT_AFFINE ? 27 : 9);
     l.term_floats = RoundUp(kmax * (G + 4), 4);
+    if (variant == FTK_VARIANT_AFFINE && G == 16) l.term_floats = RoundUp(G * (2 * G + 4), 4) > l.term_floats ? RoundUp(G * (2 * G + 4), 4) : l.term_floats;  // paired chain layout
     if (method == kFast) {
         l.ex_floats = RoundUp(geo.esize, 4);
         l.p_floats = RoundUp(geo.psize, 4);
@@ -557,10 +558,17 @@ __device__ int AffineConstruct(Ctx<G> &c, const Img &cur, const AffineState &s, 
         }
         AffineHessianTerms(tx, ty, tdx, tdy, t);
         AffineBiasTerms(tx, ty, tdx, tdy, tdt, &t[21]);
-#pragma unroll
-        for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
         valid += c.g.count(ok);
-        c.ch.template fold_wide<27>(c.g);
+        if constexpr (G == 16) {
+            // 27 chains on 16 lanes: chain k and chain 16 + k as one 64-bit term, one packed add per pixel (see Chain::fold_pairs)
+#pragma unroll
+            for (int q = 0; q < 16; ++q) c.ch.put_pair(c.g.lane, q, t[q], q + 16 < 27 ? t[q + 16] : 0.0f);
+            c.ch.fold_pairs(c.g);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 27; ++q) c.ch.put(c.g.lane, q, t[q]);
+            c.ch.template fold_wide<27>(c.g);
+        }
         w.next();
     }
     AffineScatterChains(c, 27);  // Hessian (lower triangle) and bias -> the LDLT scratch

@@ -217,6 +217,35 @@ struct Chain {
         }
         g.sync();
     }
+    // ---- paired layout: chain k and chain G + k travel together (affine kDirect / kInverse on 16 lanes: 27 chains) ----------------
+    // term2[k * kPairStride + 2 * pixel + {0, 1}] = term of chain k / chain G + k.  A pixel lane writes one 64-bit store per chain pair
+    // (16 instead of 27 stores), a chain lane reads its row as float4s = two pixels of both chains, and advances both accumulators with
+    // ONE packed add per pixel (Blackwell FADD2, add.rn.f32x2: two independent IEEE round-to-nearest adds, so each chain still sees
+    // exactly its own sequence of sums).  Row stride 2 G + 4 floats: the float4 reads of lanes 0..7 fall on distinct banks.
+    static constexpr int kPairStride = 2 * G + 4;
+    __device__ __forceinline__ void put_pair(int lane, int k, float lo, float hi) const {
+        *reinterpret_cast<float2 *>(term + k * kPairStride + 2 * lane) = make_float2(lo, hi);
+    }
+    // All lanes call; chain pairs 0..G-1 (chains G + k beyond the real count accumulate the zeros the pixel lanes stored for them).
+    __device__ __forceinline__ void fold_pairs(const Group<G> &g) {
+        g.sync();
+        {
+            const float4 *t4 = reinterpret_cast<const float4 *>(term + g.lane * kPairStride);
+            unsigned long long a2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "f"(acc), "f"(acc_hi));
+#pragma unroll
+            for (int q = 0; q < G / 2; ++q) {
+                const float4 v = t4[q];  // pixel 2q: (chain lane, chain G + lane), pixel 2q + 1: the same two chains
+                unsigned long long p0, p1;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(p0) : "f"(v.x), "f"(v.y));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(p1) : "f"(v.z), "f"(v.w));
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a2) : "l"(p0));
+                asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a2) : "l"(p1));
+            }
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc), "=f"(acc_hi) : "l"(a2));
+        }
+        g.sync();
+    }
     // K chains with G < K <= 2 G: lanes fold chains 0..G-1, then lanes 0..K-G-1 fold chains G..K-1.
     template <int K>
     __device__ __forceinline__ void fold_wide(const Group<G> &g) {
