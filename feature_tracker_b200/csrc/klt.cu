@@ -1096,7 +1096,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
 // Kernel: one group per feature; TrackMultipleLevel / TrackSingleLevel of the three subclasses.
 // ===================================================================================================================
 template <int VARIANT, int METHOD, int G>
-__global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE ? (METHOD == FTK_METHOD_FAST ? 8 : 6) : 7) KltKernel(KltLaunch a, SmemLayout layout) {
+__global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD == FTK_METHOD_FAST ? 8 : 7) KltKernel(KltLaunch a, SmemLayout layout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Ctx<G> c;
     const int groups_per_block = blockDim.x / G;
