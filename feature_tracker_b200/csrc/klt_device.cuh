@@ -59,6 +59,9 @@ struct Img {
 __device__ __forceinline__ Img LevelImage(const PyramidView &v, int image, int level) {
     Img im;
     im.p = v.base[level] + image * v.image_stride[level];
+    // Opaque to the optimiser: otherwise ptxas re-derives this 64-bit base from the kernel parameters inside every pixel loop
+    // (~20 integer instructions per chunk) instead of keeping two registers live.
+    asm("" : "+l"(im.p));
     im.rows = v.rows[level];
     im.cols = v.cols[level];
     im.pitch = v.pitch[level];
@@ -140,7 +143,11 @@ __device__ __forceinline__ bool PxChecked(const Img &im, float row, float col, f
 // rounded operations, ((ic*ir)*p00 + (sc*ir)*p01) + (ic*sr)*p10) + (sc*sr)*p11; only the common sub-expressions are shared.
 __device__ __forceinline__ bool PxStencil5(const Img &im, float row, float col, float *left, float *right, float *up, float *down, float *centre) {
     const float cm = fsub(col, 1.0f), cp = fadd(col, 1.0f), rm = fsub(row, 1.0f), rp = fadd(row, 1.0f);
-    if (!(PxInside(im, row, cm) && PxInside(im, row, cp) && PxInside(im, rm, col) && PxInside(im, rp, col) && PxInside(im, row, col))) return false;
+    // The five GetPixelValue bounds tests (each !(col < 0 || row < 0 || col > cols - 1 || row > rows - 1)) in four comparisons:
+    // cm <= col <= cp and rm <= row <= rp for every float (rounding is monotonic), so the extreme coordinates decide -- cm < 0 covers
+    // col < 0 and cp < 0, cp > cols - 1 covers col > and cm >, likewise for the rows; with a NaN coordinate every comparison of either
+    // form is false and both forms say "inside", as the reference does.
+    if (cm < 0.0f || cp > static_cast<float>(im.cols - 1) || rm < 0.0f || rp > static_cast<float>(im.rows - 1)) return false;
     const int r = __float2int_rd(row), c = __float2int_rd(col);
     float fr, fc;
     asm("cvt.rn.f32.s32 %0, %1;" : "=f"(fr) : "r"(r));
