@@ -309,7 +309,9 @@ def run_extras(ctx, L, torch, local_rank, steps, peaks, keep):
                                           "roofline": {"bound": "integer pipe (POPC)", "achieved": 8e8 / (ms * 1e-3) / 1e12, "peak": popc_peak_pairs * 8 / 1e12,
                                                        "unit": "T POPC32/s", "frac": 1e8 / (ms * 1e-3) / popc_peak_pairs, "traffic": None,
                                                        "peak_source": "measured POPC issue rate 16 lanes/clk/SM (tools/microbench.cu, profiles/r1_microbench_pipe_rates.txt) x 148 SM x 1.965 GHz",
-                                                       "algorithmic_work": "8 POPC32 per 256-bit pair x 1e8 pairs (SURVEY 8(d))", "scope": "whole call (all launches)"}}
+                                                       "algorithmic_work": "8 POPC32 per 256-bit pair x 1e8 pairs (SURVEY 8(d)); the kernel ISSUES 5 per pair (carry-save adders on the ALU "
+                                                                           "pipe fold three words into two before counting), so this fraction can pass the naive XU-pipe bound",
+                                                       "scope": "whole call (all launches)"}}
     keep["c4_force_idx"] = idx.copy()
     keep["c4_inputs"] = (rb, cb, pred, pos)
     ms = timeit(lambda: ctx.check(L.ftk_match_hamming_nearby(ctx._h, vp(d_r.data_ptr()), 10000, vp(d_c.data_ptr()), 10000, 8, vp(d_pred.data_ptr()),

@@ -1236,9 +1236,8 @@ __global__ void FeaturePairKernel(const int *offsets, int n_pairs, int n_feature
 }
 
 template <int VARIANT, int METHOD, int G>
-int LaunchOne(ftk_context *ctx, const KltLaunch &a, const Geometry &geo) {
+int LaunchOne(ftk_context *ctx, const KltLaunch &a, const Geometry &geo, int threads = 128) {
     const SmemLayout layout = MakeLayout(VARIANT, METHOD, G, geo);
-    const int threads = 128;
     const int groups_per_block = threads / G;
     const size_t smem = static_cast<size_t>(layout.total_bytes) * groups_per_block;
     if (smem > 227 * 1024) return SetError(ctx, FTK_ERR_UNSUPPORTED, "patch %dx%d needs %zu bytes of shared memory per block", geo.pr, geo.pc, smem);
@@ -1300,8 +1299,9 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_AFFINE:
-            // kDirect with 16 lanes per feature: two features share a warp's 6x6 LDLT instructions and 13x13 patches fill 11 chunks of
-            // 16 to 96 % (measured 47.4 ms vs 50.9 ms per 2 M features; kFast is slower that way, 49.4 ms vs 43.9 ms)
+            // kDirect with 16 lanes per feature: two features share a warp's fold / LDLT instructions and 13x13 patches fill 11 chunks of
+            // 16 to 96 % (round 2, paired FADD2 folds: 41.5 ms vs 42.8 ms per 2 M features with 32 lanes; kFast is much slower that way,
+            // 43.8 ms vs 35.9 ms: two features of a warp run max(iterations) of every level)
             if (geo.psize <= 16 * 64 && a.p.method == kDirect) return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo);
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;

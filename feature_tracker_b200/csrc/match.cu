@@ -48,6 +48,22 @@ __global__ void FillU64Kernel(unsigned long long *p, int n, unsigned long long v
 constexpr int kHamThreads = 256;
 constexpr int kHamTile = 256;  // cur descriptors per shared-memory tile
 
+// Population count of several words with fewer POPC instructions.  POPC runs on the XU pipe (16 lanes/clk/SM), LOP3 on the ALU pipe
+// (64 lanes/clk/SM, profiles/r2_microbench_pipe_rates.txt), and the force kernel was XU bound (93.5 % busy): a carry-save adder
+// (sum = a ^ b ^ c, carry = majority(a, b, c): one LOP3 each) turns three words of weight 1 into one of weight 1 and one of weight 2,
+// so popc(x0..x7) = popc(s3) + popc(x7) + 2 * (popc(c1) + popc(c2) + popc(c3)) needs 5 POPC + 6 LOP3 instead of 8 POPC -- the point
+// where both pipes take about the same time.  Integer arithmetic: the distance is the same number.
+__device__ __forceinline__ unsigned Maj3(unsigned a, unsigned b, unsigned c) { return (a & b) | (c & (a ^ b)); }
+__device__ __forceinline__ unsigned Popc8(unsigned x0, unsigned x1, unsigned x2, unsigned x3, unsigned x4, unsigned x5, unsigned x6, unsigned x7) {
+    const unsigned s1 = x0 ^ x1 ^ x2, c1 = Maj3(x0, x1, x2);
+    const unsigned s2 = x3 ^ x4 ^ x5, c2 = Maj3(x3, x4, x5);
+    const unsigned s3 = s1 ^ s2 ^ x6, c3 = Maj3(s1, s2, x6);
+    return __popc(s3) + __popc(x7) + 2u * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+__device__ __forceinline__ unsigned Popc4(unsigned x0, unsigned x1, unsigned x2, unsigned x3) {
+    return __popc(x0 ^ x1 ^ x2) + __popc(x3) + 2u * __popc(Maj3(x0, x1, x2));
+}
+
 template <int W>
 __global__ void __launch_bounds__(kHamThreads) HammingForceKernel(const uint32_t *__restrict__ ref, int n_ref, const uint32_t *__restrict__ cur, int n_cur,
                                                                  int cur_per_split, unsigned *__restrict__ best) {
@@ -74,11 +90,17 @@ __global__ void __launch_bounds__(kHamThreads) HammingForceKernel(const uint32_t
 #pragma unroll 4
         for (int t = 0; t < n_tile; ++t) {
             unsigned d = 0;
-            if constexpr (W % 4 == 0) {
+            if constexpr (W % 8 == 0) {
+#pragma unroll
+                for (int w = 0; w < W; w += 8) {
+                    const uint4 c = *reinterpret_cast<const uint4 *>(&tile[t * W + w]), e = *reinterpret_cast<const uint4 *>(&tile[t * W + w + 4]);
+                    d += Popc8(r[w] ^ c.x, r[w + 1] ^ c.y, r[w + 2] ^ c.z, r[w + 3] ^ c.w, r[w + 4] ^ e.x, r[w + 5] ^ e.y, r[w + 6] ^ e.z, r[w + 7] ^ e.w);
+                }
+            } else if constexpr (W % 4 == 0) {
 #pragma unroll
                 for (int w = 0; w < W; w += 4) {
                     const uint4 c = *reinterpret_cast<const uint4 *>(&tile[t * W + w]);
-                    d += __popc(r[w] ^ c.x) + __popc(r[w + 1] ^ c.y) + __popc(r[w + 2] ^ c.z) + __popc(r[w + 3] ^ c.w);
+                    d += Popc4(r[w] ^ c.x, r[w + 1] ^ c.y, r[w + 2] ^ c.z, r[w + 3] ^ c.w);
                 }
             } else {
 #pragma unroll

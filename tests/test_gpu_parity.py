@@ -727,6 +727,27 @@ def test_dense_flow_vs_oracle(ctx, oracle, shape, levels, single):
     assert np.abs(er).mean() > 0.2
 
 
+def test_dense_flow_and_direct_method_vs_reference_direct(ctx, reflib):
+    """The two 8(f) trackers straight against oracle/_ref (dense_optical_flow.cpp and direct_method_tracker.cpp compiled in place), not via
+    the C restatement."""
+    rows, cols, levels = 120, 160, 3
+    ref, cur, _, _ = S.make_pair(rows, cols, 10, pair_id=55)
+    pyr = ft.ImagePyramidBatch(ctx, rows, cols, levels, 2)
+    pyr.SetRawImages(np.stack([ref, cur]))
+    pyr.CreateImagePyramid()
+    rl, cl = reflib.pyramid_build(ref, levels), reflib.pyramid_build(cur, levels)
+    ok, fr, fc = ft.DenseOpticalFlow(ctx).Track(pyr, pyr, ref_image=0, cur_image=1)
+    eok, er, ec = reflib.dense_flow_track(po.make_dense_flow_params(), rl, cl)
+    assert ok and eok and bits_equal(fr, er) and bits_equal(fc, ec)
+    sref, scur, suv, K, pts = S.make_direct_method_scene(240, 320, 80, pair_id=56)
+    pyr2 = ft.ImagePyramidBatch(ctx, 240, 320, 4, 2)
+    pyr2.SetRawImages(np.stack([sref, scur]))
+    pyr2.CreateImagePyramid()
+    got = ft.DirectMethod(ctx).TrackFeatures(pyr2, pyr2, K, pts, suv, [1, 0, 0, 0], [0, 0, 0], ref_image=0, cur_image=1)
+    exp = reflib.direct_method_track(po.make_direct_params(), reflib.pyramid_build(sref, 4), reflib.pyramid_build(scur, 4), K, pts, suv, [1, 0, 0, 0], [0, 0, 0])
+    assert_pose_same("direct method vs _ref", got, exp)
+
+
 def test_dense_flow_matches_golden(ctx, euroc_golden):
     """The CUDA path against the committed outputs of the reference itself on its own EuRoC fixture pair (752x480, 4 levels)."""
     import os
