@@ -274,14 +274,35 @@ __device__ __forceinline__ unsigned FloatKey(float d) {
 }
 __device__ __forceinline__ float KeyFloat(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k); }
 
+// A distance functor gives the scan a `Row` (what a warp keeps of its reference descriptor while it walks the candidates) and the distance
+// of that row to current descriptor j.
 struct HammingDist {
     const uint32_t *ref, *cur;
     int words;
+    struct Row {
+        int i;
+    };
+    __device__ __forceinline__ Row load(int i) const { return Row{i}; }
     // returns false when the distance is not comparable (never for Hamming)
-    __device__ __forceinline__ bool operator()(int i, int j, float *d) const {
+    __device__ __forceinline__ bool operator()(const Row &r, int j, float *d) const {
         unsigned s = 0;
-        for (int w = 0; w < words; ++w) s += __popc(__ldg(ref + static_cast<size_t>(i) * words + w) ^ __ldg(cur + static_cast<size_t>(j) * words + w));
+        for (int w = 0; w < words; ++w) s += __popc(__ldg(ref + static_cast<size_t>(r.i) * words + w) ^ __ldg(cur + static_cast<size_t>(j) * words + w));
         *d = words > 0 ? static_cast<float>(s) : 2147483647.0f;  // brief.cpp:34-36: empty descriptors -> kMaxInt32
+        return true;
+    }
+};
+
+// 256-bit descriptors in 16-byte aligned arrays (BRIEF-256, the usual case): the reference row lives in registers, a candidate costs two
+// 128-bit loads and the carry-save popcount instead of 16 scalar loads and 8 POPC.
+struct HammingDist256 {
+    const uint4 *ref, *cur;
+    struct Row {
+        uint4 a, b;
+    };
+    __device__ __forceinline__ Row load(int i) const { return Row{__ldg(ref + 2 * static_cast<size_t>(i)), __ldg(ref + 2 * static_cast<size_t>(i) + 1)}; }
+    __device__ __forceinline__ bool operator()(const Row &r, int j, float *d) const {
+        const uint4 c = __ldg(cur + 2 * static_cast<size_t>(j)), e = __ldg(cur + 2 * static_cast<size_t>(j) + 1);
+        *d = static_cast<float>(Popc8(r.a.x ^ c.x, r.a.y ^ c.y, r.a.z ^ c.z, r.a.w ^ c.w, r.b.x ^ e.x, r.b.y ^ e.y, r.b.z ^ e.z, r.b.w ^ e.w));
         return true;
     }
 };
@@ -297,7 +318,12 @@ struct CosineDist {
     const float *ref, *cur;
     const float *ref_norm, *cur_norm;
     int dim;
-    __device__ __forceinline__ bool operator()(int i, int j, float *d) const {
+    struct Row {
+        int i;
+    };
+    __device__ __forceinline__ Row load(int i) const { return Row{i}; }
+    __device__ __forceinline__ bool operator()(const Row &r, int j, float *d) const {
+        const int i = r.i;
         const float dot = SeqDot(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim);
         const float v = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(dot, ref_norm[i]), cur_norm[j]), 0.5f));
         *d = v;
@@ -324,7 +350,7 @@ __device__ __forceinline__ unsigned WarpMin32(unsigned v) { return __reduce_min_
 
 // One warp per ref descriptor.  `limit_j`: candidates with j > limit_j are ignored (used for the d == 0 break).
 template <typename Dist>
-__device__ void NearbyScan(const Dist &dist, int i, float2 pred, const float2 *pos, int n_cur, const GridDesc &g, const int *starts, const int *sorted,
+__device__ void NearbyScan(const Dist &dist, const typename Dist::Row &row, float2 pred, const float2 *pos, int n_cur, const GridDesc &g, const int *starts, const int *sorted,
                            const int *special, int n_special, float max_dcol, float max_drow, unsigned limit_j, unsigned long long *best_out,
                            unsigned *first_zero_out) {
     const int lane = threadIdx.x & 31;
@@ -337,7 +363,7 @@ __device__ void NearbyScan(const Dist &dist, int i, float2 pred, const float2 *p
         // descriptor_matcher.h:108-111 (exact fp32 gate)
         if (fabsf(__fsub_rn(pred.x, q.x)) > max_dcol || fabsf(__fsub_rn(pred.y, q.y)) > max_drow) return;
         float d;
-        if (!dist(i, j, &d)) return;
+        if (!dist(row, j, &d)) return;
         const unsigned long long key = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
         best = key < best ? key : best;
         if (d == 0.0f) first_zero = min(first_zero, static_cast<unsigned>(j));
@@ -371,11 +397,12 @@ __global__ void __launch_bounds__(128) NearbyKernel(Dist dist, int n_ref, const 
     const GridDesc g = *gp;
     unsigned long long best;
     unsigned first_zero;
-    NearbyScan(dist, i, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, 0xFFFFFFFFu, &best, &first_zero);
+    const typename Dist::Row row = dist.load(i);
+    NearbyScan(dist, row, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, 0xFFFFFFFFu, &best, &first_zero);
     if (first_zero != 0xFFFFFFFFu && static_cast<unsigned>(best & 0xFFFFFFFFull) > first_zero) {
         // A candidate after the reference's d == 0 break won: redo the scan over j <= first_zero only.
         unsigned dummy;
-        NearbyScan(dist, i, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, first_zero, &best, &dummy);
+        NearbyScan(dist, row, pred[i], pos, n_cur, g, starts, sorted, special, n_special, max_dcol, max_drow, first_zero, &best, &dummy);
     }
     if ((threadIdx.x & 31) == 0 && best != kNoKey64) {
         const float d = KeyFloat(static_cast<unsigned>(best >> 32));
@@ -402,16 +429,32 @@ __global__ void __launch_bounds__(256) HammingPairsKernel(const uint32_t *__rest
     float2 pr = make_float2(0.0f, 0.0f);
     if (pred) pr = pred[i];
     unsigned long long best = kNoKey64;
-    for (int j = c0 + lane; j < c1; j += 32) {
-        if (pred) {
-            const float2 q = pos[j];
-            if (fabsf(__fsub_rn(pr.x, q.x)) > max_dcol || fabsf(__fsub_rn(pr.y, q.y)) > max_drow) continue;
+    if (words == 8 && ((reinterpret_cast<uintptr_t>(ref) | reinterpret_cast<uintptr_t>(cur)) & 15) == 0) {
+        // 256-bit descriptors, aligned: reference row in registers, two 128-bit loads and the carry-save popcount per candidate
+        const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(r)), rb = __ldg(reinterpret_cast<const uint4 *>(r) + 1);
+        for (int j = c0 + lane; j < c1; j += 32) {
+            if (pred) {
+                const float2 q = pos[j];
+                if (fabsf(__fsub_rn(pr.x, q.x)) > max_dcol || fabsf(__fsub_rn(pr.y, q.y)) > max_drow) continue;
+            }
+            const uint4 *c = reinterpret_cast<const uint4 *>(cur) + 2 * static_cast<size_t>(j);
+            const uint4 ca = __ldg(c), cb = __ldg(c + 1);
+            const unsigned d = Popc8(ra.x ^ ca.x, ra.y ^ ca.y, ra.z ^ ca.z, ra.w ^ ca.w, rb.x ^ cb.x, rb.y ^ cb.y, rb.z ^ cb.z, rb.w ^ cb.w);
+            const unsigned long long key = (static_cast<unsigned long long>(d) << 32) | static_cast<unsigned>(j - c0);
+            best = key < best ? key : best;
         }
-        const uint32_t *c = cur + static_cast<size_t>(j) * words;
-        unsigned d = 0;
-        for (int w = 0; w < words; ++w) d += __popc(__ldg(r + w) ^ __ldg(c + w));
-        const unsigned long long key = (static_cast<unsigned long long>(d) << 32) | static_cast<unsigned>(j - c0);
-        best = key < best ? key : best;
+    } else {
+        for (int j = c0 + lane; j < c1; j += 32) {
+            if (pred) {
+                const float2 q = pos[j];
+                if (fabsf(__fsub_rn(pr.x, q.x)) > max_dcol || fabsf(__fsub_rn(pr.y, q.y)) > max_drow) continue;
+            }
+            const uint32_t *c = cur + static_cast<size_t>(j) * words;
+            unsigned d = 0;
+            for (int w = 0; w < words; ++w) d += __popc(__ldg(r + w) ^ __ldg(c + w));
+            const unsigned long long key = (static_cast<unsigned long long>(d) << 32) | static_cast<unsigned>(j - c0);
+            best = key < best ? key : best;
+        }
     }
     best = WarpMin64(best);
     if (lane == 0 && best != kNoKey64 && static_cast<float>(static_cast<unsigned>(best >> 32)) < max_dist) idx[i] = static_cast<int>(best & 0xFFFFFFFFull);
@@ -670,6 +713,10 @@ int LaunchCosinePairs(ftk_context *ctx, const float *d_ref, const float *d_cur, 
 int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
                         const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx) {
     if (n_ref == 0) return FTK_OK;
+    if (words == 8 && reinterpret_cast<uintptr_t>(d_ref) % 16 == 0 && reinterpret_cast<uintptr_t>(d_cur) % 16 == 0) {
+        const HammingDist256 dist{reinterpret_cast<const uint4 *>(d_ref), reinterpret_cast<const uint4 *>(d_cur)};
+        return RunNearby(ctx, dist, n_ref, n_cur, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx);
+    }
     const HammingDist dist{d_ref, d_cur, words};
     return RunNearby(ctx, dist, n_ref, n_cur, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx);
 }
