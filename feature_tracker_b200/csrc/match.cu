@@ -225,27 +225,35 @@ __global__ void CellCountKernel(const float2 *pos, int n, const GridDesc *gp, in
     atomicAdd(&counts[CellCoord(p.y, g.y0, g.inv_ch, g.gh) * g.gw + CellCoord(p.x, g.x0, g.inv_cw, g.gw)], 1);
 }
 
-// Exclusive scan of counts[0..n) into starts[0..n]; single block.
+// Exclusive scan of counts[0..n) into starts[0..n]; single block: per-thread range sums, then a shuffle scan over the 1024 partials.
 __global__ void __launch_bounds__(1024) ScanKernel(const int *counts, const GridDesc *gp, int *starts, int *cursor) {
     const int n = gp->gw * gp->gh;
-    __shared__ int partial[1024];
+    __shared__ int warp_total[32];
     const int per = (n + 1023) / 1024;
     const int begin = threadIdx.x * per, end = min(n, begin + per);
     int sum = 0;
     for (int i = begin; i < end; ++i) sum += counts[i];
-    partial[threadIdx.x] = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_total[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int t = 0; t < 1024; ++t) {
-            const int v = partial[t];
-            partial[t] = acc;
-            acc += v;
+    if (warp == 0) {
+        int w = warp_total[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xFFFFFFFFu, w, o);
+            if (lane >= o) w += up;
         }
-        starts[n] = acc;
+        warp_total[lane] = w;  // inclusive totals of the warps
     }
     __syncthreads();
-    int acc = partial[threadIdx.x];
+    int acc = incl - sum + (warp > 0 ? warp_total[warp - 1] : 0);
+    if (threadIdx.x == 1023) starts[n] = acc + sum;
     for (int i = begin; i < end; ++i) {
         starts[i] = acc;
         cursor[i] = acc;
