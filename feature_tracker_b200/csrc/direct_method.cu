@@ -71,6 +71,7 @@ struct DmShared {
     float q[4], q_inv[4], p[3];
     float K[4];  // this level's scaled intrinsics
     int stop;    // the level's iteration loop ends
+    LdltShared<6> ldlt;  // normal equations / factors of the cooperative 6 x 6 solve
 };
 
 __global__ void __launch_bounds__(kDmThreads) DirectMethodKernel(DmArgs a) {
@@ -234,19 +235,24 @@ __global__ void __launch_bounds__(kDmThreads) DirectMethodKernel(DmArgs a) {
 
             // ---- 3. solve + pose update (:178-187), warp 0 ----
             if (warp == 0) {
-                float H[6][6], b[6], dx[6];
-                int q = 0;
+                // chain lanes store the normal equations (lower-triangle position a[col][row], bias b) into the shared LDLT scratch;
+                // the 6 x 6 system is solved cooperatively (klt_device.cuh LdltFactorShared: lane i owns row i; no local memory)
+                float dx[6];
+                {
+                    int q = 0;
 #pragma unroll
-                for (int r = 0; r < 6; ++r)
+                    for (int r = 0; r < 6; ++r)
 #pragma unroll
-                    for (int c = r; c < 6; ++c) {
-                        const float v = __shfl_sync(0xFFFFFFFFu, acc, q++);
-                        H[r][c] = v;
-                        H[c][r] = v;
-                    }
-#pragma unroll
-                for (int r = 0; r < 6; ++r) b[r] = __shfl_sync(0xFFFFFFFFu, acc, 21 + r);
-                LdltSolve<6>(H, b, dx);
+                        for (int c = r; c < 6; ++c) {
+                            if (lane == q) sm.ldlt.a[c * 6 + r] = acc;
+                            ++q;
+                        }
+                    if (lane >= 21 && lane < 27) sm.ldlt.b[lane - 21] = acc;
+                    __syncwarp();
+                }
+                const Group<32> g32;
+                LdltFactorShared<6, 32>(g32, sm.ldlt);
+                LdltSolveShared<6, 32>(g32, sm.ldlt, dx);
                 if (lane == 0) {
                     bool any_nan = false;
 #pragma unroll

@@ -204,8 +204,6 @@ struct Chain {
     float acc;     // chain `lane`
     float acc_hi;  // chain `G + lane` when a pass has more chains than the group has lanes (fold_wide)
     __device__ __forceinline__ void reset() { acc = 0.0f, acc_hi = 0.0f; }
-    // value of chain q after the folds (any lane may ask)
-    __device__ __forceinline__ float value(const Group<G> &g, int q) const { return q < G ? g.get(acc, q) : g.get(acc_hi, q - G); }
     __device__ __forceinline__ void put(int lane, int k, float v) const { term[k * kStride + lane] = v; }
     // All lanes call; lanes >= K idle during the fold.
     template <int K>

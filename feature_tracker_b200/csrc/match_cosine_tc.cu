@@ -468,7 +468,7 @@ __device__ __forceinline__ float ExactDistance(const float *a, const float *b, i
 constexpr int kRerankRows = 32;
 constexpr int kRerankThreads = 128;
 constexpr int kMaxSplits = 16;
-__global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
+__global__ void __launch_bounds__(kRerankThreads, 5) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
                                                               const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
                                                               unsigned long long *best, int2 *work, int *counters, const int *abn_cur, float max_dist,
                                                               int *idx) {
@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row0 = blockIdx.x * kRerankRows;
     const unsigned all_splits = (1u << n_splits) - 1u;  // n_splits <= kMaxSplits = 16
+    const int n_abn_all = counters[1];  // read early: the block's only other dependent global accesses are the row loads
 
     // ---- 1. screening ----
     // warp w owns rows w, w + 4, ..., w + 28; lane s < n_splits holds column split s.  All eight top-2 records of a lane are loaded
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(kRerankThreads) RerankKernel(const float *ref,
     const int i = row0 + lane;
     // ---- 3. abnormal current descriptors: exact candidates of every row (normally none) ----
     const unsigned scan = s_scan[lane];
-    const int n_abn = scan == all_splits ? 0 : counters[1];  // a full scan covers them anyway
+    const int n_abn = scan == all_splits ? 0 : n_abn_all;  // a full scan covers them anyway
     for (int q = 0; q < n_abn; ++q) {
         const int j = abn_cur[q];
         const float d = ExactDistance(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim, ref_norm[i], cur_norm[j]);
