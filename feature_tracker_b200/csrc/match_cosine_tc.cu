@@ -32,12 +32,14 @@ constexpr int kTileN = 256;      // current descriptors per MMA tile (TMEM colum
                                  // UMMA) under the 128 B/clk shared-memory bandwidth, N = 128 would sit exactly on it
 constexpr int kKBlock = 64;      // BF16 elements per 128-byte swizzle row
 constexpr int kMaxKBlocks = 4;   // K <= 256
-constexpr int kStages = 4;       // pipeline stage = one K block (64 wide) of a 256-row tile of the current set
+constexpr int kStages = 3;       // pipeline stage = one K block (64 wide) of a 256-row tile of the current set
+constexpr int kSlotsA = 2;       // the persistent CTA loads the reference tile of its next work item while the current one is multiplied
 constexpr int kBoxBytesA = kTileM * kKBlock * 2;  // 16 KiB: one TMA box of the reference tile (128 rows x 128 B)
 constexpr int kBoxBytesB = kTileN * kKBlock * 2;  // 32 KiB: one TMA box of the current set (256 rows x 128 B)
 constexpr int kTcThreads = 192;
 constexpr int kTmemCols = 512;   // two 256-column fp32 accumulators (all of TMEM)
-constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kMaxKBlocks) * kBoxBytesA + static_cast<size_t>(kStages) * kBoxBytesB + 256;
+constexpr int kSlotBytesA = kMaxKBlocks * kBoxBytesA;  // 64 KiB
+constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kSlotsA) * kSlotBytesA + static_cast<size_t>(kStages) * kBoxBytesB + 256;
 
 // |dot(bf16(a_hat), bf16(b_hat)) - exact dot of the unit vectors| <= 2 * 2^-9 + 2^-18 (Cauchy-Schwarz), plus fp32
 // accumulation slack on both sides.
@@ -255,28 +257,33 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
     }
 }
 
+// Persistent: one CTA per SM walks the work items (reference tile m, split of the current set) item = blockIdx.x, + gridDim.x, ...
+// The three roles run the same item loop and carry their pipeline state (stage / accumulator / reference-slot parities) across
+// items, so the TMA stream, the MMA issue and the epilogue of consecutive items overlap: no per-item start-up bubble, and the
+// last wave is short because items are small (16 splits).
 __global__ void __launch_bounds__(kTcThreads, 1)
 CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks,
-               int tiles_per_split, int n_tiles, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
+               int tiles_per_split, int n_tiles, int m_tiles, int n_items, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem_a + kMaxKBlocks * kBoxBytesA;
+    uint8_t *smem_b = smem_a + kSlotsA * kSlotBytesA;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages * kBoxBytesB);
-    uint64_t *bar_a = &bars[0];
-    uint64_t *bar_full = &bars[1];                     // [kStages]
-    uint64_t *bar_empty = &bars[1 + kStages];          // [kStages]
-    uint64_t *bar_acc_full = &bars[1 + 2 * kStages];   // [2]
-    uint64_t *bar_acc_empty = &bars[3 + 2 * kStages];  // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(&bars[5 + 2 * kStages]);
+    uint64_t *bar_a_full = &bars[0];                   // [kSlotsA]
+    uint64_t *bar_a_empty = &bars[kSlotsA];            // [kSlotsA]
+    uint64_t *bar_full = &bars[2 * kSlotsA];           // [kStages]
+    uint64_t *bar_empty = bar_full + kStages;          // [kStages]
+    uint64_t *bar_acc_full = bar_empty + kStages;      // [2]
+    uint64_t *bar_acc_empty = bar_acc_full + 2;        // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x;
-    const int t_begin = blockIdx.y * tiles_per_split;
-    const int t_end = min(n_tiles, t_begin + tiles_per_split);
 
     if (threadIdx.x == 0) {
-        MbarInit(bar_a, 1);
+        for (int s = 0; s < kSlotsA; ++s) {
+            MbarInit(&bar_a_full[s], 1);
+            MbarInit(&bar_a_empty[s], 1);
+        }
         for (int s = 0; s < kStages; ++s) {
             MbarInit(&bar_full[s], 1);
             MbarInit(&bar_empty[s], 1);
@@ -299,19 +306,35 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            MbarExpectTx(bar_a, static_cast<uint32_t>(k_blocks) * kBoxBytesA);
-            for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2D(smem_a + kb * kBoxBytesA, &map_ref, bar_a, kb * kKBlock, m_tile * kTileM);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_empty[stage], phase ^ 1u);
-                    MbarExpectTx(&bar_full[stage], kBoxBytesB);
-                    TmaLoad2D(smem_b + stage * kBoxBytesB, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
+            int stage = 0, slot = 0;
+            uint32_t phase = 0, slot_phase = 0;
+            auto load_ref_tile = [&](int item) {
+                MbarWait(&bar_a_empty[slot], slot_phase ^ 1u);  // the MMAs of the item that used this slot have retired
+                MbarExpectTx(&bar_a_full[slot], static_cast<uint32_t>(k_blocks) * kBoxBytesA);
+                for (int kb = 0; kb < k_blocks; ++kb)
+                    TmaLoad2D(smem_a + slot * kSlotBytesA + kb * kBoxBytesA, &map_ref, &bar_a_full[slot], kb * kKBlock, (item % m_tiles) * kTileM);
+                if (++slot == kSlotsA) {
+                    slot = 0;
+                    slot_phase ^= 1u;
+                }
+            };
+            if (static_cast<int>(blockIdx.x) < n_items) load_ref_tile(blockIdx.x);
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int t_begin = (item / m_tiles) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+                for (int t = t_begin; t < t_end; ++t) {
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        MbarWait(&bar_empty[stage], phase ^ 1u);
+                        MbarExpectTx(&bar_full[stage], kBoxBytesB);
+                        TmaLoad2D(smem_b + stage * kBoxBytesB, &map_cur, &bar_full[stage], kb * kKBlock, t * kTileN);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
+                    // The next item's reference tile is requested once this item's first tile is on its way: by then the MMAs
+                    // of the previous item (the last users of that slot) have been issued, so the wait inside is short, and the
+                    // tile lands while the rest of this item streams.
+                    if (t == t_begin && item + static_cast<int>(gridDim.x) < n_items) load_ref_tile(item + gridDim.x);
                 }
             }
         }
@@ -319,47 +342,59 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            MbarWait(bar_a, 0);
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int t = t_begin; t < t_end; ++t) {
-                MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
+            int stage = 0, acc = 0, slot = 0;
+            uint32_t phase = 0, acc_phase = 0, slot_phase = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int t_begin = (item / m_tiles) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+                MbarWait(&bar_a_full[slot], slot_phase);
                 TcFenceAfter();
-                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    MbarWait(&bar_full[stage], phase);
+                const uint8_t *a_tile = smem_a + slot * kSlotBytesA;
+                for (int t = t_begin; t < t_end; ++t) {
+                    MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
                     TcFenceAfter();
-                    const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytesA);
-                    const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB);
+                    const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kTileN);
+                    for (int kb = 0; kb < k_blocks; ++kb) {
+                        MbarWait(&bar_full[stage], phase);
+                        TcFenceAfter();
+                        const uint64_t adesc = MakeSmemDesc(a_tile + kb * kBoxBytesA);
+                        const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB);
 #pragma unroll
-                    for (int k = 0; k < kKBlock / 16; ++k) {
-                        // each UMMA consumes K = 16 BF16 = 32 bytes of the 128-byte swizzle row: advance the start address by 32 B
-                        UmmaBf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kKBlock / 16; ++k) {
+                            // each UMMA consumes K = 16 BF16 = 32 bytes of the 128-byte swizzle row: advance the start address by 32 B
+                            UmmaBf16(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                        UmmaCommit(&bar_empty[stage]);  // the stage's operands may be overwritten once these MMAs retire
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
-                    UmmaCommit(&bar_empty[stage]);  // the stage's operands may be overwritten once these MMAs retire
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    UmmaCommit(&bar_acc_full[acc]);  // the accumulator is complete
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
                 }
-                UmmaCommit(&bar_acc_full[acc]);  // the accumulator is complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+                UmmaCommit(&bar_a_empty[slot]);  // the reference slot may be refilled once this item's MMAs retire
+                if (++slot == kSlotsA) {
+                    slot = 0;
+                    slot_phase ^= 1u;
+                }
             }
         }
         __syncwarp();
     } else {
         // ===================== epilogue: running top-2 per reference row =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int row = m_tile * kTileM + quarter * 32 + lane;
         // A match needs distance < max_dist, i.e. a cosine above 1 - 2 * max_dist; approximate dots below `floor_dot` (that bound
         // minus the BF16 error margin) cannot belong to a match and never enter the top-2.  With the usual tight thresholds the
         // costly "new best in this chunk" path (taken by the whole warp when any of its 32 rows sees a new maximum) then runs
         // for real candidates only instead of for every running maximum of the random background.
-        float b1 = floor_dot, b2 = -INFINITY;
-        int j1 = -1;
         int acc = 0;
         uint32_t acc_phase = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int split = item / m_tiles, row = (item % m_tiles) * kTileM + quarter * 32 + lane;
+        const int t_begin = split * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+        float b1 = floor_dot, b2 = -INFINITY;
+        int j1 = -1;
         for (int t = t_begin; t < t_end; ++t) {
             MbarWait(&bar_acc_full[acc], acc_phase);
             TcFenceAfter();
@@ -426,7 +461,8 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
             Top2 o;
             o.b1 = j1 >= 0 ? b1 : -INFINITY;  // no candidate above the floor in this split
             o.j1 = j1, o.b2 = b2, o.j2 = b2 > -INFINITY ? 0 : -1;  // j2 only says whether a second candidate exists
-            out[static_cast<size_t>(blockIdx.y) * n_ref_pad + row] = o;
+            out[static_cast<size_t>(split) * n_ref_pad + row] = o;
+        }
         }
     }
 
@@ -674,21 +710,20 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     cudaStream_t st = ctx->stream;
     const int k_blocks = (dim + kKBlock - 1) / kKBlock, k_pad = k_blocks * kKBlock;
     const int m_tiles = (n_ref + kTileM - 1) / kTileM, n_tiles = (n_cur + kTileN - 1) / kTileN;
-    // Split the current set across CTAs: one CTA per SM at a time (192 KB of shared memory), so pick the split count whose
-    // grid fills whole waves best (ties: fewer splits = more reuse of the resident reference tile).
+    // Work items = (reference tile, split of the current set), walked by one persistent CTA per SM.  Pick the split count that
+    // gives every CTA the fewest current-set tiles in total (ties: fewer splits = fewer partial top-2 records to merge).
     int splits = 1;
     {
-        double best_eff = -1.0;
+        double best_cost = 0.0;
         const int max_splits = n_tiles < kMaxSplits ? n_tiles : kMaxSplits;
         for (int sp = 1; sp <= max_splits; ++sp) {
             const int per = (n_tiles + sp - 1) / sp, real = (n_tiles + per - 1) / per;
-            const long long ctas = static_cast<long long>(m_tiles) * real;
-            const long long waves = (ctas + ctx->sm_count - 1) / ctx->sm_count;
-            // time ~ waves * tiles per CTA (+ one tile-equivalent for loading the reference tile)
-            const double cost = static_cast<double>(waves) * (per + 1.0);
-            const double eff = 1.0 / cost;
-            if (eff > best_eff * 1.02) {
-                best_eff = eff;
+            const long long items = static_cast<long long>(m_tiles) * real;
+            const long long per_cta = (items + ctx->sm_count - 1) / ctx->sm_count;
+            // time ~ items per CTA * (tiles per item + a fraction of a tile for the item switch)
+            const double cost = static_cast<double>(per_cta) * (per + 0.1);
+            if (sp == 1 || cost < best_cost * 0.99) {
+                best_cost = cost;
                 splits = real;
             }
         }
@@ -731,8 +766,9 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     // The opt-in is per device and the ABI allows one process to hold contexts on several GPUs: set it before every launch (cheap).
     FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
     ProfBegin(ctx);
-    CosineTcKernel<<<dim3(m_tiles, splits), kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split, n_tiles, top, n_ref_pad,
-                                                                          floor_dot);
+    const int n_items = m_tiles * splits;
+    CosineTcKernel<<<n_items < ctx->sm_count ? n_items : ctx->sm_count, kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split,
+                                                                                                       n_tiles, m_tiles, n_items, top, n_ref_pad, floor_dot);
     ProfEnd(ctx);
     RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * StagedStride(dim), st>>>(
         d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx);
