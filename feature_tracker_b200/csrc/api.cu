@@ -173,7 +173,7 @@ void ftk_destroy(ftk_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
                         &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_small, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
-                        &ctx->d_work2, &ctx->d_work3};
+                        &ctx->d_work2, &ctx->d_work3, &ctx->d_cos_counters};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < ftk_context::kStageBuffers; ++b) {
         if (ctx->stage_pyr[b]) {

@@ -61,6 +61,11 @@ struct ftk_context {
     bool prof_recorded = false;
     int sm_count = 0;
     const int *d_last_scan_items = nullptr;  // device counter of the last tensor-core cosine match (nullptr: path not used)
+    // tensor-core cosine match: two counter sets used alternately -- call n counts in set n & 1 while its first kernel zeroes the
+    // other set for call n + 1 (no memset launch per call); `clean` is false until a call has left both sets in that state
+    FtkBuffer d_cos_counters;
+    unsigned cos_calls = 0;
+    bool cos_counters_clean = false;
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;

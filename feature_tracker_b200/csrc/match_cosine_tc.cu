@@ -47,6 +47,12 @@ constexpr float kEpsDot = 0.0041f;
 
 constexpr unsigned long long kNoKey64 = 0xFFFFFFFFFFFFFFFFull;
 
+// Programmatic dependent launch: the four kernels of a call are launched with the stream-serialization attribute, so that the
+// launch latency and the prologue of kernel n + 1 overlap the tail of kernel n.  Every kernel announces its dependents at once and
+// waits for its predecessor (complete and flushed) right before its first dependent access.
+__device__ __forceinline__ void GridDepLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void GridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct __align__(16) Top2 {
     float b1;
     int j1;
@@ -149,110 +155,109 @@ constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cas
 // `abn_cur`), an abnormal REFERENCE row is scanned exactly against the whole current set.  Their BF16 rows are zero.
 __device__ __forceinline__ bool AbnormalNorm(float nrm) { return !(nrm >= 1e-12f && nrm <= 1e12f); }
 
-// Row stride (floats) of the staged descriptor / product rows: a multiple of 4 that is 4 (mod 32), so that 32 threads reading float4s
-// at the same offset of 32 different rows touch all banks exactly once per quarter-warp (no conflicts), and rows stay 16-byte aligned.
-__host__ __device__ inline int StagedStride(int dim) {
-    int s = (dim + 3) / 4 * 4;
-    while (s % 32 != 4) s += 4;
-    return s;
+// ---- eight lanes per descriptor row -------------------------------------------------------------------------------------------
+// NormPrepKernel and RerankKernel need fp32 sums in the reference's scalar order (k ascending, one rounding per add, no FMA): a
+// dependent chain of `dim` adds per row.  Eight lanes share a row: lane l of the group holds elements k = 64 q + 8 l + e
+// (q < 4, e < 8; dim <= 256), i.e. two adjacent float4s per 64-element block, so a group reads a row as whole 256-byte runs
+// and every load of a row is in flight at once.  The chain then walks the lanes: the owner of the next eight elements adds them to the
+// running sum, which is broadcast to the group (32 hand-overs for 256 elements).  No shared memory, no block-wide barrier; the other
+// warps of the SM hide the hand-over latency.
+constexpr int kRowLanes = 8;
+constexpr int kRowBlocks = kMaxKBlocks * kKBlock / 64;  // 64-element blocks of a row (4)
+
+// v[q][e] = row[64 q + 8 l + e] for indices below `bound` (0 elsewhere; bound = 0: nothing is read).  VEC: dim % 4 == 0 and a 16-byte
+// aligned base, i.e. every float4 of the row is aligned and lies wholly inside or outside the row.
+template <bool VEC>
+__device__ __forceinline__ void GroupLoadRow(const float *row, int bound, int l, float (&v)[kRowBlocks][8]) {
+#pragma unroll
+    for (int q = 0; q < kRowBlocks; ++q) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k0 = 64 * q + 8 * l + 4 * h;
+            if (VEC) {
+                const float4 t = k0 < bound ? __ldg(reinterpret_cast<const float4 *>(row + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[q][4 * h] = t.x, v[q][4 * h + 1] = t.y, v[q][4 * h + 2] = t.z, v[q][4 * h + 3] = t.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[q][4 * h + e] = k0 + e < bound ? __ldg(row + k0 + e) : 0.0f;
+            }
+        }
+    }
 }
 
-// s = (..((f(p[0]) + f(p[1])) + f(p[2])) + ...) in ascending k -- the reference's scalar order -- over a 16-byte aligned shared row.  The
-// adds form one dependent chain (4 cycles each); the loads do not depend on it, so they are issued as float4s two groups ahead: the
-// chain, not the shared-memory latency, sets the pace (a scalar load per add made this loop ~30 cycles per element).
-template <bool SQUARE>
-__device__ __forceinline__ float SequentialRowSum(const float *row, int dim) {
-    const float4 *r4 = reinterpret_cast<const float4 *>(row);
-    const int n4 = dim >> 2;
-    auto f = [](float v) { return SQUARE ? __fmul_rn(v, v) : v; };
-    float s;
-    int k4 = 0;
-    if (n4 == 0) {
-        s = f(row[0]);
-        for (int k = 1; k < dim; ++k) s = __fadd_rn(s, f(row[k]));
-        return s;
+// s = (..((x[0] + x[1]) + x[2]) + ...) over k < dim with x distributed as above; every lane of the group returns s.  dim >= 1.
+// EVERY lane adds its own eight elements to the running sum at every hand-over and the broadcast keeps the owner's result: no
+// divergent branch and no predicates around the adds (the other lanes' sums are discarded garbage), 9 instructions per hand-over.
+__device__ __forceinline__ float GroupChainSum(const float (&v)[kRowBlocks][8], int dim, int lane) {
+    const int base = lane & ~(kRowLanes - 1);
+    float s = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kRowBlocks; ++q) {
+#pragma unroll
+        for (int hop = 0; hop < kRowLanes; ++hop) {
+            const int k0 = 64 * q + 8 * hop;
+            if (k0 + 8 <= dim) {  // uniform: a whole run of eight
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = k0 + e == 0 ? v[q][e] : __fadd_rn(s, v[q][e]);
+                s = __shfl_sync(0xFFFFFFFFu, s, base | hop);
+            } else if (k0 < dim) {  // uniform: the row ends inside this run
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (k0 + e == 0)
+                        s = v[q][e];
+                    else if (k0 + e < dim)
+                        s = __fadd_rn(s, v[q][e]);
+                }
+                s = __shfl_sync(0xFFFFFFFFu, s, base | hop);
+            }
+        }
     }
-    float4 a = r4[0], b = n4 > 1 ? r4[1] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s = f(a.x);
-    s = __fadd_rn(s, f(a.y));
-    s = __fadd_rn(s, f(a.z));
-    s = __fadd_rn(s, f(a.w));
-    for (k4 = 1; k4 < n4; ++k4) {
-        const float4 cur = b;
-        if (k4 + 1 < n4) b = r4[k4 + 1];
-        s = __fadd_rn(s, f(cur.x));
-        s = __fadd_rn(s, f(cur.y));
-        s = __fadd_rn(s, f(cur.z));
-        s = __fadd_rn(s, f(cur.w));
-    }
-    for (int k = n4 << 2; k < dim; ++k) s = __fadd_rn(s, f(row[k]));
     return s;
 }
 
 // norm[i] = sqrt(sequential fp32 dot(a, a)) -- the reference's evaluation order (oracle/shim: k ascending, no FMA) -- and the
 // unit-normalised BF16 copy, for BOTH descriptor sets in one launch (blocks [0, ref_blocks) = reference rows, the rest = current
-// rows).  32 descriptors per block: rows are staged through shared memory so global reads and writes are coalesced while each
-// row's sum of squares is still accumulated by one thread in ascending k.
-constexpr int kPrepRows = 32;
-constexpr int kPrepThreads = 256;
+// rows).  Global memory is read once (the row stays in registers for the BF16 pass) and written in 16-byte pieces.
+constexpr int kPrepThreads = 128;
+constexpr int kPrepRows = kPrepThreads / kRowLanes;
+template <bool VEC>
 __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref, int n_ref, const float *cur, int n_cur, int ref_blocks, int dim, int k_pad,
                                                               float *ref_norm, float *cur_norm, __nv_bfloat16 *ref_unit, __nv_bfloat16 *cur_unit,
-                                                              int *counters, int *abn_cur) {
-    extern __shared__ __align__(16) float prep_smem[];  // [kPrepRows][StagedStride(dim)] + [kPrepRows]
+                                                              int *counters, int *next_counters, int *abn_cur) {
+    GridDepLaunchDependents();
+    if (blockIdx.x == 0 && threadIdx.x == 0) next_counters[0] = next_counters[1] = 0;  // the other set, for the next call
     const bool is_cur = static_cast<int>(blockIdx.x) >= ref_blocks;
     const float *desc = is_cur ? cur : ref;
     const int n = is_cur ? n_cur : n_ref;
-    float *norm = is_cur ? cur_norm : ref_norm;
-    __nv_bfloat16 *unit = is_cur ? cur_unit : ref_unit;
-    const int stride = StagedStride(dim);
-    float *s_norm = prep_smem + kPrepRows * stride;
-    const int row0 = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows;
-    const int rows = min(kPrepRows, n - row0);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // warp w moves rows w, w + 8, w + 16, w + 24; lane = column within a 32-wide group.  All 32 loads of a thread are issued before
-    // the first use (dim <= 256 = 8 x 32), and the values stay in registers for the BF16 pass: global memory is read once.
-    constexpr int kRowsPerWarp = kPrepRows / (kPrepThreads / 32), kColsPerLane = kMaxKBlocks * kKBlock / 32;
-    float v[kRowsPerWarp][kColsPerLane];
+    const int lane = threadIdx.x & 31, l = lane & (kRowLanes - 1);
+    const int row = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows + (threadIdx.x / kRowLanes);
+    const bool live = row < n;
+    float v[kRowBlocks][8];
+    GroupLoadRow<VEC>(desc + static_cast<size_t>(live ? row : 0) * dim, live ? dim : 0, l, v);
+    float sq[kRowBlocks][8];
 #pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const int r = warp + rr * (kPrepThreads / 32);
-        const float *src = desc + static_cast<size_t>(row0 + min(r, rows - 1)) * dim;
+    for (int q = 0; q < kRowBlocks; ++q)
 #pragma unroll
-        for (int q = 0; q < kColsPerLane; ++q) {
-            const int k = lane + 32 * q;
-            v[rr][q] = k < dim ? __ldg(src + k) : 0.0f;
-        }
+        for (int e = 0; e < 8; ++e) sq[q][e] = __fmul_rn(v[q][e], v[q][e]);
+    const float nrm = __fsqrt_rn(GroupChainSum(sq, dim, lane));
+    if (!live) return;
+    const bool abnormal = AbnormalNorm(nrm);
+    if (l == 0) {
+        (is_cur ? cur_norm : ref_norm)[row] = nrm;
+        if (abnormal && is_cur) abn_cur[atomicAdd(&counters[1], 1)] = row;
     }
+    // The BF16 copy only feeds the screening GEMM, whose error margin (kEpsDot) has room for the 1-ulp difference between
+    // x * (1 / norm) and x / norm: one multiply per element instead of a division.  Abnormal rows become zero BF16 rows.
+    const float inv = abnormal ? 0.0f : 1.0f / nrm;
+    __nv_bfloat16 *dst = (is_cur ? cur_unit : ref_unit) + static_cast<size_t>(row) * k_pad;
 #pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        float *dst = prep_smem + (warp + rr * (kPrepThreads / 32)) * stride;
+    for (int q = 0; q < kRowBlocks; ++q) {
+        const int k0 = 64 * q + 8 * l;
+        if (k0 < k_pad) {  // columns past dim hold 0 (loaded as 0)
+            __align__(16) __nv_bfloat162 o[4];
 #pragma unroll
-        for (int q = 0; q < kColsPerLane; ++q) {
-            const int k = lane + 32 * q;
-            if (k < dim) dst[k] = v[rr][q];
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < rows) {
-        const float nrm = __fsqrt_rn(SequentialRowSum<true>(prep_smem + threadIdx.x * stride, dim));
-        norm[row0 + threadIdx.x] = nrm;
-        const bool abnormal = AbnormalNorm(nrm);
-        // The BF16 copy only feeds the screening GEMM, whose error margin (kEpsDot) has room for the 1-ulp difference between
-        // x * (1 / norm) and x / norm: one multiply per element instead of a division.  0 marks "zero BF16 row".
-        s_norm[threadIdx.x] = abnormal ? 0.0f : 1.0f / nrm;
-        if (abnormal && is_cur) abn_cur[atomicAdd(&counters[1], 1)] = row0 + threadIdx.x;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-        const int r = warp + rr * (kPrepThreads / 32);
-        if (r >= rows) continue;
-        const float inv = s_norm[r];
-        __nv_bfloat16 *dst = unit + static_cast<size_t>(row0 + r) * k_pad;
-#pragma unroll
-        for (int q = 0; q < kColsPerLane; ++q) {
-            const int k = lane + 32 * q;
-            if (k < k_pad) dst[k] = __float2bfloat16_rn(v[rr][q] * inv);  // columns past dim hold 0
+            for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(abnormal ? 0.0f : v[q][2 * e] * inv, abnormal ? 0.0f : v[q][2 * e + 1] * inv);
+            *reinterpret_cast<uint4 *>(dst + k0) = *reinterpret_cast<const uint4 *>(o);
         }
     }
 }
@@ -302,10 +307,12 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     __syncthreads();
     TcFenceAfter();
     const uint32_t tmem_base = *tmem_slot;
+    GridDepLaunchDependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            GridDepWait();  // the BF16 unit descriptors come from NormPrepKernel; nothing else in this kernel reads its output
             int stage = 0, slot = 0;
             uint32_t phase = 0, slot_phase = 0;
             auto load_ref_tile = [&](int item) {
@@ -490,133 +497,82 @@ __device__ __forceinline__ float ExactDistance(const float *a, const float *b, i
     return __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, na), nb), 0.5f));
 }
 
-// Exact re-evaluation of the candidates inside the error margin.  A block owns 32 consecutive reference rows:
-//   1. each warp screens 8 rows: lane s reads the top-2 of column split s, the warp forms the row's best approximate dot, flags the
-//      splits whose best lies inside the margin (candidates) and marks "crowded" splits (both of its top-2 inside the margin: a
-//      third candidate could hide) for the exact scan;
-//   2. per round, every row with a candidate left gets its 256 products a[k] * b[k] written to shared memory by its warp
-//      (coalesced loads, each product one correctly rounded multiply -- the reference's), then LANE r OF WARP 0 ADDS ROW r's
-//      PRODUCTS in ascending k: 32 of the reference's sequential sums advance per instruction instead of one.
-//      Rounds repeat while any row of the block has another candidate (almost always exactly one round);
+// Exact re-evaluation of the candidates inside the error margin.  Eight lanes own a reference row (see GroupLoadRow):
+//   1. lane l reads the top-2 of column splits l and l + 8; the group forms the row's best approximate dot, flags the splits whose
+//      best lies inside the margin (candidates) and marks "crowded" splits (both of its top-2 inside the margin: a third candidate
+//      could hide) for the exact scan;
+//   2. per candidate (almost always exactly one) the group loads both descriptors, forms the 256 products a[k] * b[k] -- each one
+//      correctly rounded multiply, the reference's -- and adds them in ascending k (GroupChainSum);
 //   3. abnormal current descriptors (see AbnormalNorm) are exact candidates of every row;
 //   4. a row without scan work is FINISHED here (idx written when its best distance < max_dist); a row with crowded splits, or an
 //      abnormal reference row, parks its key in best[] and queues (row, split mask) for ExactScanKernel, which finishes it.
-constexpr int kRerankRows = 32;
 constexpr int kRerankThreads = 128;
-constexpr int kMaxSplits = 16;
+constexpr int kRerankRows = kRerankThreads / kRowLanes;
+constexpr int kMaxSplits = 2 * kRowLanes;
+template <bool VEC>
 __global__ void __launch_bounds__(kRerankThreads, 5) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
                                                               const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
                                                               unsigned long long *best, int2 *work, int *counters, const int *abn_cur, float max_dist,
                                                               int *idx) {
-    extern __shared__ __align__(16) float rerank_smem[];  // [kRerankRows][StagedStride(dim)] products
-    __shared__ int s_cand[kRerankRows][kMaxSplits];  // candidate columns of each row, in split order
-    __shared__ int s_count[kRerankRows];
-    __shared__ unsigned s_scan[kRerankRows];  // split mask the exact scan has to cover
-    const int stride = StagedStride(dim);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row0 = blockIdx.x * kRerankRows;
+    const int lane = threadIdx.x & 31, l = lane & (kRowLanes - 1), base = lane & ~(kRowLanes - 1);
+    const int i = blockIdx.x * kRerankRows + threadIdx.x / kRowLanes;
+    const bool live = i < n_ref;
     const unsigned all_splits = (1u << n_splits) - 1u;  // n_splits <= kMaxSplits = 16
-    const int n_abn_all = counters[1];  // read early: the block's only other dependent global accesses are the row loads
+    GridDepLaunchDependents();
+    GridDepWait();
+    const int n_abn_all = counters[1];
 
     // ---- 1. screening ----
-    // warp w owns rows w, w + 4, ..., w + 28; lane s < n_splits holds column split s.  All eight top-2 records of a lane are loaded
-    // before the first reduction, so the warp waits for global memory once instead of once per row.
-    constexpr int kRowsPerWarp = kRerankRows / (kRerankThreads / 32);
-    Top2 mine[kRowsPerWarp];
-    float rnorm[kRowsPerWarp];
-#pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) {
-        const int i = row0 + warp + q * (kRerankThreads / 32);
-        mine[q].b1 = -INFINITY, mine[q].j1 = -1, mine[q].b2 = -INFINITY, mine[q].j2 = -1;
-        rnorm[q] = 1.0f;
-        if (i < n_ref) {
-            if (lane < n_splits) mine[q] = top[static_cast<size_t>(lane) * n_ref_pad + i];
-            rnorm[q] = ref_norm[i];
-        }
+    Top2 t0, t1;
+    t0.b1 = t1.b1 = -INFINITY, t0.j1 = t1.j1 = -1, t0.b2 = t1.b2 = -INFINITY, t0.j2 = t1.j2 = -1;
+    float na = 1.0f;
+    if (live) {
+        if (l < n_splits) t0 = top[static_cast<size_t>(l) * n_ref_pad + i];
+        if (l + kRowLanes < n_splits) t1 = top[static_cast<size_t>(l + kRowLanes) * n_ref_pad + i];
+        na = ref_norm[i];
     }
+    float gmax = fmaxf(t0.b1, t1.b1);
 #pragma unroll
-    for (int q = 0; q < kRowsPerWarp; ++q) {
-        const int r = warp + q * (kRerankThreads / 32);
-        const int i = row0 + r;
-        int count = 0;
-        unsigned scan = 0u;
-        if (i < n_ref) {
-            if (AbnormalNorm(rnorm[q])) {
-                scan = all_splits;  // nothing the tensor-core pass said about this row can be trusted
-            } else {
-                float gmax = mine[q].b1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
-                const float thr = gmax - 2.0f * kEpsDot;
-                const bool cand = gmax > -INFINITY && mine[q].j1 >= 0 && mine[q].b1 >= thr;
-                const bool crowded = cand && mine[q].j2 >= 0 && mine[q].b2 >= thr;
-                const unsigned todo = __ballot_sync(0xFFFFFFFFu, cand && !crowded);
-                scan = __ballot_sync(0xFFFFFFFFu, crowded);
-                if (cand && !crowded) s_cand[r][__popc(todo & ((1u << lane) - 1u))] = mine[q].j1;
-                count = __popc(todo);
-            }
-        }
-        if (lane == 0) s_count[r] = count, s_scan[r] = scan;
-    }
-    __syncthreads();
+    for (int o = kRowLanes / 2; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, o));
+    const float thr = gmax - 2.0f * kEpsDot;
+    const bool trusted = live && !AbnormalNorm(na) && gmax > -INFINITY;  // an abnormal row: nothing the tensor-core pass said about it counts
+    const bool cand0 = trusted && t0.j1 >= 0 && t0.b1 >= thr, crowded0 = cand0 && t0.j2 >= 0 && t0.b2 >= thr;
+    const bool cand1 = trusted && t1.j1 >= 0 && t1.b1 >= thr, crowded1 = cand1 && t1.j2 >= 0 && t1.b2 >= thr;
+    const unsigned todo0 = __ballot_sync(0xFFFFFFFFu, cand0 && !crowded0), todo1 = __ballot_sync(0xFFFFFFFFu, cand1 && !crowded1);
+    const unsigned scan0 = __ballot_sync(0xFFFFFFFFu, crowded0), scan1 = __ballot_sync(0xFFFFFFFFu, crowded1);
+    unsigned todo = ((todo0 >> base) & 0xFFu) | (((todo1 >> base) & 0xFFu) << kRowLanes);  // the row's candidate splits
+    const unsigned scan = !live ? 0u : AbnormalNorm(na) ? all_splits : ((scan0 >> base) & 0xFFu) | (((scan1 >> base) & 0xFFu) << kRowLanes);
 
-    // ---- 2. rounds of exact distances ----
-    unsigned long long key = kNoKey64;  // lane r of warp 0: row r
-    for (int round = 0; round < kMaxSplits; ++round) {
-        bool any = false;
-        // warp w owns rows w, w + 4, ..., w + 28; four rows at a time, all their loads (2 x 8 per row and lane) issued before the first
-        // product, so a block waits for global memory twice per round instead of once per row
-        constexpr int kBatch = 4, kColsPerLane = kMaxKBlocks * kKBlock / 32;
+    // ---- 2. exact distances of the candidates ----
+    unsigned long long key = kNoKey64;
+    while (__any_sync(0xFFFFFFFFu, todo != 0u)) {
+        const bool has = todo != 0u;
+        const int split = has ? __ffs(static_cast<int>(todo)) - 1 : 0;
+        todo &= todo - 1u;
+        const int src = base | (split & (kRowLanes - 1));
+        const int j_lo = __shfl_sync(0xFFFFFFFFu, t0.j1, src), j_hi = __shfl_sync(0xFFFFFFFFu, t1.j1, src);
+        const int j = has ? (split < kRowLanes ? j_lo : j_hi) : 0;
+        float a[kRowBlocks][8], b[kRowBlocks][8];
+        GroupLoadRow<VEC>(ref + static_cast<size_t>(has ? i : 0) * dim, has ? dim : 0, l, a);
+        GroupLoadRow<VEC>(cur + static_cast<size_t>(j) * dim, has ? dim : 0, l, b);
+        const float nb = has ? cur_norm[j] : 1.0f;
 #pragma unroll
-        for (int half = 0; half < kRerankRows / (kRerankThreads / 32) / kBatch; ++half) {
-            float va[kBatch][kColsPerLane], vb[kBatch][kColsPerLane];
-            bool live[kBatch];
+        for (int q = 0; q < kRowBlocks; ++q)
 #pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                const int r = warp + (half * kBatch + q) * (kRerankThreads / 32);
-                live[q] = round < s_count[r];
-                any = any || live[q];
-                const float *a = ref + static_cast<size_t>(live[q] ? row0 + r : 0) * dim;
-                const float *b = cur + static_cast<size_t>(live[q] ? s_cand[r][round] : 0) * dim;
-#pragma unroll
-                for (int c = 0; c < kColsPerLane; ++c) {
-                    const int k = lane + 32 * c;
-                    const bool in = live[q] && k < dim;
-                    va[q][c] = in ? __ldg(a + k) : 0.0f;
-                    vb[q][c] = in ? __ldg(b + k) : 0.0f;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                if (!live[q]) continue;
-                float *prod = rerank_smem + (warp + (half * kBatch + q) * (kRerankThreads / 32)) * stride;
-#pragma unroll
-                for (int c = 0; c < kColsPerLane; ++c) {
-                    const int k = lane + 32 * c;
-                    if (k < dim) prod[k] = __fmul_rn(va[q][c], vb[q][c]);
-                }
-            }
+            for (int e = 0; e < 8; ++e) a[q][e] = __fmul_rn(a[q][e], b[q][e]);
+        const float dot = GroupChainSum(a, dim, lane);
+        const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(dot, na), nb), 0.5f));
+        if (has && d == d) {
+            const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
+            key = k64 < key ? k64 : key;
         }
-        if (!__syncthreads_or(any)) break;
-        if (warp == 0 && round < s_count[lane]) {
-            const int i = row0 + lane, j = s_cand[lane][round];
-            const float s = SequentialRowSum<false>(rerank_smem + lane * stride, dim);
-            const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(s, ref_norm[i]), cur_norm[j]), 0.5f));
-            if (d == d) {
-                const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
-                key = k64 < key ? k64 : key;
-            }
-        }
-        __syncthreads();
     }
-    if (warp != 0 || row0 + lane >= n_ref) return;
-    const int i = row0 + lane;
+    if (l != 0 || !live) return;
     // ---- 3. abnormal current descriptors: exact candidates of every row (normally none) ----
-    const unsigned scan = s_scan[lane];
     const int n_abn = scan == all_splits ? 0 : n_abn_all;  // a full scan covers them anyway
     for (int q = 0; q < n_abn; ++q) {
         const int j = abn_cur[q];
-        const float d = ExactDistance(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim, ref_norm[i], cur_norm[j]);
+        const float d = ExactDistance(ref + static_cast<size_t>(i) * dim, cur + static_cast<size_t>(j) * dim, dim, na, cur_norm[j]);
         if (d == d) {
             const unsigned long long k64 = (static_cast<unsigned long long>(FloatKey(d)) << 32) | static_cast<unsigned>(j);
             key = k64 < key ? k64 : key;
@@ -636,6 +592,7 @@ __global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const f
                                                       const int2 *work, const int *counters, int cols_per_split, int n_splits,
                                                       const unsigned long long *best, float max_dist, int *idx) {
     __shared__ unsigned long long s_key[4];
+    GridDepWait();
     const int n = counters[0];
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
         const int i = work[w].x;
@@ -699,6 +656,18 @@ bool MakeMap(CUtensorMap *map, const __nv_bfloat16 *base, int rows, int k_pad, i
 
 int Blocks(int n, int threads) { return (n + threads - 1) / threads; }
 
+// Launch with programmatic stream serialization (see GridDepWait).
+template <typename... Params, typename... Args>
+cudaError_t LaunchDependent(void (*kernel)(Params...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 }  // namespace
 
 // Returns FTK_ERR_UNSUPPORTED when the tensor-core path does not cover the shape (dim > 256): the caller then runs the
@@ -738,15 +707,20 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     if (int rc = EnsureDevice(ctx, ctx->d_work3, bytes_norm + 256)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work1, bytes_unit + 1024)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work2, sizeof(Top2) * static_cast<size_t>(splits) * n_ref_pad + 256)) return rc;
-    if (int rc = EnsureDevice(ctx, ctx->d_work0,
-                              16 + (sizeof(unsigned long long) + sizeof(int2)) * static_cast<size_t>(n_ref) + sizeof(int) * static_cast<size_t>(n_cur) + 256))
+    if (int rc = EnsureDevice(ctx, ctx->d_work0, (sizeof(unsigned long long) + sizeof(int2)) * static_cast<size_t>(n_ref) + sizeof(int) * static_cast<size_t>(n_cur) + 256))
         return rc;
+    if (int rc = EnsureDevice(ctx, ctx->d_cos_counters, 32)) return rc;
     float *ref_norm = static_cast<float *>(ctx->d_work3.ptr), *cur_norm = ref_norm + n_ref;
     __nv_bfloat16 *ref_unit = static_cast<__nv_bfloat16 *>(ctx->d_work1.ptr);
     __nv_bfloat16 *cur_unit = ref_unit + static_cast<size_t>(n_ref) * k_pad;
     Top2 *top = static_cast<Top2 *>(ctx->d_work2.ptr);
-    int *counters = static_cast<int *>(ctx->d_work0.ptr);  // [0] rows queued for the exact scan, [1] abnormal current descriptors
-    unsigned long long *best = reinterpret_cast<unsigned long long *>(counters + 4);
+    // [0] rows queued for the exact scan, [1] abnormal current descriptors; two sets, see ftk_context::d_cos_counters
+    if (!ctx->cos_counters_clean) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_cos_counters.ptr, 0, 32, st));
+    ctx->cos_counters_clean = false;  // until this call's launches are all queued
+    int *counters = static_cast<int *>(ctx->d_cos_counters.ptr) + 4 * (ctx->cos_calls & 1u);
+    int *next_counters = static_cast<int *>(ctx->d_cos_counters.ptr) + 4 * ((ctx->cos_calls + 1u) & 1u);
+    ++ctx->cos_calls;
+    unsigned long long *best = static_cast<unsigned long long *>(ctx->d_work0.ptr);
     int2 *work = reinterpret_cast<int2 *>(best + n_ref);
     int *abn_cur = reinterpret_cast<int *>(work + n_ref);
 
@@ -754,29 +728,30 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     if (!MakeMap(&map_ref, ref_unit, n_ref, k_pad, kTileM) || !MakeMap(&map_cur, cur_unit, n_cur, k_pad, kTileN))
         return SetError(ctx, FTK_ERR_CUDA, "cuTensorMapEncodeTiled failed for the descriptor matrices");
 
-    FTK_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, 16, st));
-    const size_t prep_smem = sizeof(float) * (static_cast<size_t>(kPrepRows) * StagedStride(dim) + kPrepRows);
+    // float4 row loads need 16-byte aligned rows: dim % 4 == 0 and aligned bases (device pointers may come from the caller)
+    const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ref) | reinterpret_cast<uintptr_t>(d_cur)) % 16 == 0;
     const int ref_blocks = Blocks(n_ref, kPrepRows);
-    NormPrepKernel<<<ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, prep_smem, st>>>(d_ref, n_ref, d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm,
-                                                                                          ref_unit, cur_unit, counters, abn_cur);
+    (vec ? NormPrepKernel<true> : NormPrepKernel<false>)<<<ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, 0, st>>>(
+        d_ref, n_ref, d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm, ref_unit, cur_unit, counters, next_counters, abn_cur);
 
     // cos > 1 - 2 * max_dist is necessary for distance < max_dist; 3 * kEpsDot covers the BF16 dot error and the fp32 rounding of the
     // distance formula.  NaN / huge thresholds give NaN / -inf floors: nothing or everything passes, as in the reference.
     const float floor_dot = 1.0f - 2.0f * max_dist - 3.0f * kEpsDot;
     // The opt-in is per device and the ABI allows one process to hold contexts on several GPUs: set it before every launch (cheap).
     FTK_CUDA_CHECK(ctx, cudaFuncSetAttribute(CosineTcKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kTcSmemBytes)));
-    ProfBegin(ctx);
     const int n_items = m_tiles * splits;
-    CosineTcKernel<<<n_items < ctx->sm_count ? n_items : ctx->sm_count, kTcThreads, kTcSmemBytes, st>>>(map_ref, map_cur, n_ref, n_cur, k_blocks, tiles_per_split,
-                                                                                                       n_tiles, m_tiles, n_items, top, n_ref_pad, floor_dot);
+    ProfBegin(ctx);
+    FTK_CUDA_CHECK(ctx, LaunchDependent(CosineTcKernel, n_items < ctx->sm_count ? n_items : ctx->sm_count, kTcThreads, kTcSmemBytes, st, map_ref, map_cur, n_ref,
+                                        n_cur, k_blocks, tiles_per_split, n_tiles, m_tiles, n_items, top, n_ref_pad, floor_dot));
     ProfEnd(ctx);
-    RerankKernel<<<Blocks(n_ref, kRerankRows), kRerankThreads, sizeof(float) * kRerankRows * StagedStride(dim), st>>>(
-        d_ref, n_ref, d_cur, dim, ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx);
-    ExactScanKernel<<<ctx->sm_count * 2, 128, 0, st>>>(d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters, tiles_per_split * kTileN, splits, best, max_dist,
-                                                       d_idx);
+    FTK_CUDA_CHECK(ctx, LaunchDependent(vec ? RerankKernel<true> : RerankKernel<false>, Blocks(n_ref, kRerankRows), kRerankThreads, 0, st, d_ref, n_ref, d_cur, dim,
+                                        ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx));
+    FTK_CUDA_CHECK(ctx, LaunchDependent(ExactScanKernel, ctx->sm_count * 2, 128, 0, st, d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters,
+                                        tiles_per_split * kTileN, splits, best, max_dist, d_idx));
+    FTK_CUDA_CHECK(ctx, cudaGetLastError());
+    ctx->cos_counters_clean = true;
     ctx->launches += 4;
     ctx->d_last_scan_items = counters;
-    FTK_CUDA_CHECK(ctx, cudaGetLastError());
     return FTK_OK;
 }
 

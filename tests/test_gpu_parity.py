@@ -519,6 +519,32 @@ def test_cosine_abnormal_norms_follow_the_reference(ctx, oracle):
         assert c.last_exact_scan_items() >= 2  # rows 5, 11 and 17 went through the exact scan
 
 
+def test_cosine_force_odd_dims_and_unaligned_device_pointers(ctx, oracle):
+    """The tensor-core path reads descriptor rows as float4s when it may (dim % 4 == 0, 16-byte aligned bases) and as scalars
+    otherwise: dims that are not multiples of 4, and device pointers that are only 4-byte aligned, give the reference's result too."""
+    import ctypes as C
+    import torch
+    from feature_tracker_b200 import _capi
+    from feature_tracker_b200.api import lib as ftk_lib
+    L = ftk_lib()
+    dev = torch.device("cuda", 0)
+    vp = C.c_void_p
+    fl = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_INDEX_INPUT
+    for dim, shift in ((1, 0), (3, 0), (37, 0), (101, 1), (250, 0), (256, 1), (256, 3), (128, 2), (64, 0)):
+        rf, cf = S.make_float_sets(700, 900, dim=dim, seed=90 + dim + shift)
+        exp = oracle.match_cosine_force(rf, cf, 0.1)[1]
+        buf_r = torch.zeros(rf.size + 8, dtype=torch.float32, device=dev)
+        buf_c = torch.zeros(cf.size + 8, dtype=torch.float32, device=dev)
+        d_r, d_c = buf_r[shift:shift + rf.size], buf_c[shift:shift + cf.size]
+        d_r.copy_(torch.from_numpy(rf.ravel()))
+        d_c.copy_(torch.from_numpy(cf.ravel()))
+        d_idx = torch.full((700,), -1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        ctx.check(L.ftk_match_cosine_force(ctx._h, vp(d_r.data_ptr()), 700, vp(d_c.data_ptr()), 900, dim, 0.1, vp(d_idx.data_ptr()), fl))
+        ctx.synchronize()
+        assert np.array_equal(d_idx.cpu().numpy(), exp), (dim, shift)
+
+
 def test_cosine_two_devices_in_one_process(oracle):
     """One process, contexts on two GPUs: the tensor-core kernel's shared-memory opt-in is per device.  Skipped on a
     single-GPU box."""

@@ -44,7 +44,7 @@ def main():
                 got = m.NearbyMatch(ft.pack_brief(ref), ft.pack_brief(cur), pred, pos, idx_in)
                 exp = oracle.match_brief_nearby(ref, cur, pred, pos, win[0], win[1], thr, idx=idx_in)
         elif kind.startswith("cos"):
-            dim = int(rng.choice([16, 64, 100, 128, 256]))
+            dim = int(rng.choice([1, 7, 16, 37, 64, 100, 128, 250, 256]))
             cur = rng.normal(0, 1, (n_cur, dim)).astype(np.float32)
             ref = (cur[rng.integers(0, n_cur, n_ref)] + rng.choice([0.0, 0.05, 0.3]) * rng.normal(0, 1, (n_ref, dim))).astype(np.float32)
             if rng.random() < 0.5:
