@@ -709,7 +709,8 @@ int ftk_track_image_sequence(ftk_context *ctx, const ftk_klt_params *params, int
 namespace {
 
 // Common index-vector handling (descriptor_matcher.h:60-62, 98-100): a missing index vector starts at -1.
-int PrepareIndex(ftk_context *ctx, int32_t *idx, int n_ref, uint32_t flags, int **d_idx) {
+// defer_fill: with FTK_FLAG_NO_INDEX_INPUT the launcher writes the -1 of unmatched rows itself (no memset here)
+int PrepareIndex(ftk_context *ctx, int32_t *idx, int n_ref, uint32_t flags, int **d_idx, bool defer_fill = false) {
     const bool on_device = flags & FTK_FLAG_DEVICE_POINTERS;
     if (on_device) {
         *d_idx = idx;
@@ -719,7 +720,7 @@ int PrepareIndex(ftk_context *ctx, int32_t *idx, int n_ref, uint32_t flags, int 
     }
     if (n_ref == 0) return FTK_OK;
     if (flags & FTK_FLAG_NO_INDEX_INPUT) {
-        FTK_CUDA_CHECK(ctx, cudaMemsetAsync(*d_idx, 0xFF, sizeof(int) * n_ref, ctx->stream));  // -1
+        if (!defer_fill) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(*d_idx, 0xFF, sizeof(int) * n_ref, ctx->stream));  // -1
     } else if (!on_device) {
         FTK_CUDA_CHECK(ctx, cudaMemcpyAsync(*d_idx, idx, sizeof(int) * n_ref, cudaMemcpyHostToDevice, ctx->stream));
     }
@@ -1105,8 +1106,8 @@ int ftk_match_cosine_force(ftk_context *ctx, const float *ref, int32_t n_ref, co
     if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * dim, on_device, &d_ref)) return rc;
     if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * dim, on_device, &d_cur)) return rc;
     int *d_idx = nullptr;
-    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
-    if (int rc = ftk::LaunchCosineForce(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx)) return rc;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx, true)) return rc;
+    if (int rc = ftk::LaunchCosineForce(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx, (flags & FTK_FLAG_NO_INDEX_INPUT) != 0)) return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 

@@ -157,12 +157,13 @@ int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *
                        int *d_idx);
 int LaunchCosinePairs(ftk_context *ctx, const float *d_ref, const float *d_cur, int dim, int n_ref_total, int n_cur_total, const int *d_ref_pair,
                       const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
-int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
+// fill_unmatched: d_idx holds no input -- rows without a match get -1 (the tensor-core path writes it with the results instead of a memset)
+int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx, bool fill_unmatched);
 // match_mutual.cu: mutual arg-max of a score matrix; cross-check filter
 int LaunchMutualScores(ftk_context *ctx, const float *d_scores, int n_ref, int n_cur, float min_score, int *d_idx);
 int LaunchCrossCheck(ftk_context *ctx, int *d_idx_fwd, int n_ref, const int *d_idx_bwd, int n_cur);
 // match_cosine_tc.cu: tcgen05 GEMM + exact re-rank; FTK_ERR_UNSUPPORTED for dim > 256
-int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx);
+int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx, bool fill_unmatched);
 int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,
                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
 

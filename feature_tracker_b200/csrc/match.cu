@@ -729,14 +729,15 @@ int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, cons
     return RunNearby(ctx, dist, n_ref, n_cur, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx);
 }
 
-int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
+int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx, bool fill_unmatched) {
     if (n_ref == 0) return FTK_OK;
     ctx->d_last_scan_items = nullptr;
     if (ctx->use_fast_paths) {
-        const int rc = LaunchCosineForceTensor(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx);
+        const int rc = LaunchCosineForceTensor(ctx, d_ref, n_ref, d_cur, n_cur, dim, max_dist, d_idx, fill_unmatched);
         if (rc != FTK_ERR_UNSUPPORTED) return rc;
     }
     cudaStream_t st = ctx->stream;
+    if (fill_unmatched) FTK_CUDA_CHECK(ctx, cudaMemsetAsync(d_idx, 0xFF, sizeof(int) * n_ref, st));  // -1
     float *ref_norm, *cur_norm;
     if (int rc = ComputeNorms(ctx, d_ref, n_ref, d_cur, n_cur, dim, &ref_norm, &cur_norm)) return rc;
     if (int rc = EnsureDevice(ctx, ctx->d_work0, sizeof(unsigned long long) * static_cast<size_t>(n_ref))) return rc;

@@ -32,14 +32,13 @@ constexpr int kTileN = 256;      // current descriptors per MMA tile (TMEM colum
                                  // UMMA) under the 128 B/clk shared-memory bandwidth, N = 128 would sit exactly on it
 constexpr int kKBlock = 64;      // BF16 elements per 128-byte swizzle row
 constexpr int kMaxKBlocks = 4;   // K <= 256
-constexpr int kStages = 3;       // pipeline stage = one K block (64 wide) of a 256-row tile of the current set
-constexpr int kSlotsA = 2;       // the persistent CTA loads the reference tile of its next work item while the current one is multiplied
+constexpr int kStages = 5;       // pipeline stage = one K block (64 wide) of a 256-row tile of the current set
 constexpr int kBoxBytesA = kTileM * kKBlock * 2;  // 16 KiB: one TMA box of the reference tile (128 rows x 128 B)
 constexpr int kBoxBytesB = kTileN * kKBlock * 2;  // 32 KiB: one TMA box of the current set (256 rows x 128 B)
 constexpr int kTcThreads = 192;
 constexpr int kTmemCols = 512;   // two 256-column fp32 accumulators (all of TMEM)
 constexpr int kSlotBytesA = kMaxKBlocks * kBoxBytesA;  // 64 KiB
-constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kSlotsA) * kSlotBytesA + static_cast<size_t>(kStages) * kBoxBytesB + 256;
+constexpr size_t kTcSmemBytes = 1024 + static_cast<size_t>(kSlotBytesA) + static_cast<size_t>(kStages) * kBoxBytesB + 256;
 
 // |dot(bf16(a_hat), bf16(b_hat)) - exact dot of the unit vectors| <= 2 * 2^-9 + 2^-18 (Cauchy-Schwarz), plus fp32
 // accumulation slack on both sides.
@@ -157,23 +156,23 @@ __device__ __forceinline__ bool AbnormalNorm(float nrm) { return !(nrm >= 1e-12f
 
 // ---- eight lanes per descriptor row -------------------------------------------------------------------------------------------
 // NormPrepKernel and RerankKernel need fp32 sums in the reference's scalar order (k ascending, one rounding per add, no FMA): a
-// dependent chain of `dim` adds per row.  Eight lanes share a row: lane l of the group holds elements k = 64 q + 8 l + e
-// (q < 4, e < 8; dim <= 256), i.e. two adjacent float4s per 64-element block, so a group reads a row as whole 256-byte runs
-// and every load of a row is in flight at once.  The chain then walks the lanes: the owner of the next eight elements adds them to the
-// running sum, which is broadcast to the group (32 hand-overs for 256 elements).  No shared memory, no block-wide barrier; the other
-// warps of the SM hide the hand-over latency.
+// dependent chain of `dim` adds per row.  Eight lanes share a row: lane l of the group holds the runs of kRun = 16 consecutive
+// elements k = 128 q + 16 l + e (q < 2, e < 16; dim <= 256), so a group reads a row as whole 512-byte pieces and every load of a row
+// is in flight at once.  The chain then walks the lanes: the owner of the next run adds it to the running sum, which is broadcast to
+// the group (16 hand-overs for 256 elements).  No shared memory, no block-wide barrier; the other warps of the SM hide the latency.
 constexpr int kRowLanes = 8;
-constexpr int kRowBlocks = kMaxKBlocks * kKBlock / 64;  // 64-element blocks of a row (4)
+constexpr int kRun = 16;
+constexpr int kRowBlocks = kMaxKBlocks * kKBlock / (kRowLanes * kRun);  // blocks of 128 elements per row (2)
 
-// v[q][e] = row[64 q + 8 l + e] for indices below `bound` (0 elsewhere; bound = 0: nothing is read).  VEC: dim % 4 == 0 and a 16-byte
-// aligned base, i.e. every float4 of the row is aligned and lies wholly inside or outside the row.
+// v[q][e] = row[128 q + 16 l + e] for indices below `bound` (0 elsewhere; bound = 0: nothing is read).  VEC: dim % 4 == 0 and a
+// 16-byte aligned base, i.e. every float4 of the row is aligned and lies wholly inside or outside the row.
 template <bool VEC>
-__device__ __forceinline__ void GroupLoadRow(const float *row, int bound, int l, float (&v)[kRowBlocks][8]) {
+__device__ __forceinline__ void GroupLoadRow(const float *row, int bound, int l, float (&v)[kRowBlocks][kRun]) {
 #pragma unroll
     for (int q = 0; q < kRowBlocks; ++q) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int k0 = 64 * q + 8 * l + 4 * h;
+        for (int h = 0; h < kRun / 4; ++h) {
+            const int k0 = kRowLanes * kRun * q + kRun * l + 4 * h;
             if (VEC) {
                 const float4 t = k0 < bound ? __ldg(reinterpret_cast<const float4 *>(row + k0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 v[q][4 * h] = t.x, v[q][4 * h + 1] = t.y, v[q][4 * h + 2] = t.z, v[q][4 * h + 3] = t.w;
@@ -186,23 +185,23 @@ __device__ __forceinline__ void GroupLoadRow(const float *row, int bound, int l,
 }
 
 // s = (..((x[0] + x[1]) + x[2]) + ...) over k < dim with x distributed as above; every lane of the group returns s.  dim >= 1.
-// EVERY lane adds its own eight elements to the running sum at every hand-over and the broadcast keeps the owner's result: no
-// divergent branch and no predicates around the adds (the other lanes' sums are discarded garbage), 9 instructions per hand-over.
-__device__ __forceinline__ float GroupChainSum(const float (&v)[kRowBlocks][8], int dim, int lane) {
+// EVERY lane adds its own run to the running sum at every hand-over and the broadcast keeps the owner's result: no divergent branch
+// and no predicates around the adds (the other lanes' sums are discarded garbage).
+__device__ __forceinline__ float GroupChainSum(const float (&v)[kRowBlocks][kRun], int dim, int lane) {
     const int base = lane & ~(kRowLanes - 1);
     float s = 0.0f;
 #pragma unroll
     for (int q = 0; q < kRowBlocks; ++q) {
 #pragma unroll
         for (int hop = 0; hop < kRowLanes; ++hop) {
-            const int k0 = 64 * q + 8 * hop;
-            if (k0 + 8 <= dim) {  // uniform: a whole run of eight
+            const int k0 = kRowLanes * kRun * q + kRun * hop;
+            if (k0 + kRun <= dim) {  // uniform: a whole run
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s = k0 + e == 0 ? v[q][e] : __fadd_rn(s, v[q][e]);
+                for (int e = 0; e < kRun; ++e) s = k0 + e == 0 ? v[q][e] : __fadd_rn(s, v[q][e]);
                 s = __shfl_sync(0xFFFFFFFFu, s, base | hop);
             } else if (k0 < dim) {  // uniform: the row ends inside this run
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
+                for (int e = 0; e < kRun; ++e) {
                     if (k0 + e == 0)
                         s = v[q][e];
                     else if (k0 + e < dim)
@@ -225,6 +224,7 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
                                                               float *ref_norm, float *cur_norm, __nv_bfloat16 *ref_unit, __nv_bfloat16 *cur_unit,
                                                               int *counters, int *next_counters, int *abn_cur) {
     GridDepLaunchDependents();
+    GridDepWait();  // launched with the stream-serialization attribute too: only its launch overlaps the kernel before it on the stream
     if (blockIdx.x == 0 && threadIdx.x == 0) next_counters[0] = next_counters[1] = 0;  // the other set, for the next call
     const bool is_cur = static_cast<int>(blockIdx.x) >= ref_blocks;
     const float *desc = is_cur ? cur : ref;
@@ -232,13 +232,13 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
     const int lane = threadIdx.x & 31, l = lane & (kRowLanes - 1);
     const int row = (static_cast<int>(blockIdx.x) - (is_cur ? ref_blocks : 0)) * kPrepRows + (threadIdx.x / kRowLanes);
     const bool live = row < n;
-    float v[kRowBlocks][8];
+    float v[kRowBlocks][kRun];
     GroupLoadRow<VEC>(desc + static_cast<size_t>(live ? row : 0) * dim, live ? dim : 0, l, v);
-    float sq[kRowBlocks][8];
+    float sq[kRowBlocks][kRun];
 #pragma unroll
     for (int q = 0; q < kRowBlocks; ++q)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sq[q][e] = __fmul_rn(v[q][e], v[q][e]);
+        for (int e = 0; e < kRun; ++e) sq[q][e] = __fmul_rn(v[q][e], v[q][e]);
     const float nrm = __fsqrt_rn(GroupChainSum(sq, dim, lane));
     if (!live) return;
     const bool abnormal = AbnormalNorm(nrm);
@@ -252,31 +252,33 @@ __global__ void __launch_bounds__(kPrepThreads) NormPrepKernel(const float *ref,
     __nv_bfloat16 *dst = (is_cur ? cur_unit : ref_unit) + static_cast<size_t>(row) * k_pad;
 #pragma unroll
     for (int q = 0; q < kRowBlocks; ++q) {
-        const int k0 = 64 * q + 8 * l;
-        if (k0 < k_pad) {  // columns past dim hold 0 (loaded as 0)
-            __align__(16) __nv_bfloat162 o[4];
+        const int k0 = kRowLanes * kRun * q + kRun * l;
+        if (k0 < k_pad) {  // columns past dim hold 0 (loaded as 0); k_pad is a multiple of 64, so the whole run lies inside the row
+            __align__(16) __nv_bfloat162 o[kRun / 2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = __floats2bfloat162_rn(abnormal ? 0.0f : v[q][2 * e] * inv, abnormal ? 0.0f : v[q][2 * e + 1] * inv);
-            *reinterpret_cast<uint4 *>(dst + k0) = *reinterpret_cast<const uint4 *>(o);
+            for (int e = 0; e < kRun / 2; ++e) o[e] = __floats2bfloat162_rn(abnormal ? 0.0f : v[q][2 * e] * inv, abnormal ? 0.0f : v[q][2 * e + 1] * inv);
+#pragma unroll
+            for (int h = 0; h < kRun / 8; ++h) reinterpret_cast<uint4 *>(dst + k0)[h] = reinterpret_cast<const uint4 *>(o)[h];
         }
     }
 }
 
-// Persistent: one CTA per SM walks the work items (reference tile m, split of the current set) item = blockIdx.x, + gridDim.x, ...
-// The three roles run the same item loop and carry their pipeline state (stage / accumulator / reference-slot parities) across
-// items, so the TMA stream, the MMA issue and the epilogue of consecutive items overlap: no per-item start-up bubble, and the
-// last wave is short because items are small (16 splits).
+// Persistent: one CTA per SM.  The work items (reference tile m, split of the current set), numbered m-major, are dealt out as one
+// contiguous range per CTA, so a CTA changes its reference tile at most a few times in the whole kernel and the rest of shared memory
+// can go to a deep pipeline of current-set stages.  The three roles run the same item loop and carry their pipeline state (stage /
+// accumulator / reference-tile parities) across items: the TMA stream, the MMA issue and the epilogue of consecutive items overlap, and
+// every CTA gets the same number of items to within one.
 __global__ void __launch_bounds__(kTcThreads, 1)
 CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constant__ CUtensorMap map_cur, int n_ref, int n_cur, int k_blocks,
-               int tiles_per_split, int n_tiles, int m_tiles, int n_items, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
+               int tiles_per_split, int n_tiles, int n_splits, int n_items, Top2 *__restrict__ out, int n_ref_pad, float floor_dot) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *smem_a = smem;
-    uint8_t *smem_b = smem_a + kSlotsA * kSlotBytesA;
+    uint8_t *smem_b = smem_a + kSlotBytesA;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + kStages * kBoxBytesB);
-    uint64_t *bar_a_full = &bars[0];                   // [kSlotsA]
-    uint64_t *bar_a_empty = &bars[kSlotsA];            // [kSlotsA]
-    uint64_t *bar_full = &bars[2 * kSlotsA];           // [kStages]
+    uint64_t *bar_a_full = &bars[0];
+    uint64_t *bar_a_empty = &bars[1];
+    uint64_t *bar_full = &bars[2];                     // [kStages]
     uint64_t *bar_empty = bar_full + kStages;          // [kStages]
     uint64_t *bar_acc_full = bar_empty + kStages;      // [2]
     uint64_t *bar_acc_empty = bar_acc_full + 2;        // [2]
@@ -284,11 +286,12 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    const int item_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * n_items / gridDim.x);
+    const int item_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * n_items / gridDim.x);
+
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlotsA; ++s) {
-            MbarInit(&bar_a_full[s], 1);
-            MbarInit(&bar_a_empty[s], 1);
-        }
+        MbarInit(bar_a_full, 1);
+        MbarInit(bar_a_empty, 1);
         for (int s = 0; s < kStages; ++s) {
             MbarInit(&bar_full[s], 1);
             MbarInit(&bar_empty[s], 1);
@@ -313,21 +316,18 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         // ===================== TMA producer =====================
         if (lane == 0) {
             GridDepWait();  // the BF16 unit descriptors come from NormPrepKernel; nothing else in this kernel reads its output
-            int stage = 0, slot = 0;
-            uint32_t phase = 0, slot_phase = 0;
-            auto load_ref_tile = [&](int item) {
-                MbarWait(&bar_a_empty[slot], slot_phase ^ 1u);  // the MMAs of the item that used this slot have retired
-                MbarExpectTx(&bar_a_full[slot], static_cast<uint32_t>(k_blocks) * kBoxBytesA);
-                for (int kb = 0; kb < k_blocks; ++kb)
-                    TmaLoad2D(smem_a + slot * kSlotBytesA + kb * kBoxBytesA, &map_ref, &bar_a_full[slot], kb * kKBlock, (item % m_tiles) * kTileM);
-                if (++slot == kSlotsA) {
-                    slot = 0;
-                    slot_phase ^= 1u;
+            int stage = 0, m_loaded = -1;
+            uint32_t phase = 0, ref_phase = 0;
+            for (int item = item_begin; item < item_end; ++item) {
+                const int m_tile = item / n_splits;
+                if (m_tile != m_loaded) {
+                    MbarWait(bar_a_empty, ref_phase ^ 1u);  // the MMAs on the previous reference tile have retired
+                    MbarExpectTx(bar_a_full, static_cast<uint32_t>(k_blocks) * kBoxBytesA);
+                    for (int kb = 0; kb < k_blocks; ++kb) TmaLoad2D(smem_a + kb * kBoxBytesA, &map_ref, bar_a_full, kb * kKBlock, m_tile * kTileM);
+                    ref_phase ^= 1u;
+                    m_loaded = m_tile;
                 }
-            };
-            if (static_cast<int>(blockIdx.x) < n_items) load_ref_tile(blockIdx.x);
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int t_begin = (item / m_tiles) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+                const int t_begin = (item % n_splits) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
                 for (int t = t_begin; t < t_end; ++t) {
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         MbarWait(&bar_empty[stage], phase ^ 1u);
@@ -338,10 +338,6 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
                             phase ^= 1u;
                         }
                     }
-                    // The next item's reference tile is requested once this item's first tile is on its way: by then the MMAs
-                    // of the previous item (the last users of that slot) have been issued, so the wait inside is short, and the
-                    // tile lands while the rest of this item streams.
-                    if (t == t_begin && item + static_cast<int>(gridDim.x) < n_items) load_ref_tile(item + gridDim.x);
                 }
             }
         }
@@ -349,13 +345,17 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            int stage = 0, acc = 0, slot = 0;
-            uint32_t phase = 0, acc_phase = 0, slot_phase = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-                const int t_begin = (item / m_tiles) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
-                MbarWait(&bar_a_full[slot], slot_phase);
-                TcFenceAfter();
-                const uint8_t *a_tile = smem_a + slot * kSlotBytesA;
+            int stage = 0, acc = 0, m_loaded = -1;
+            uint32_t phase = 0, acc_phase = 0, ref_phase = 0;
+            for (int item = item_begin; item < item_end; ++item) {
+                const int m_tile = item / n_splits;
+                const int t_begin = (item % n_splits) * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
+                if (m_tile != m_loaded) {
+                    MbarWait(bar_a_full, ref_phase);
+                    TcFenceAfter();
+                    ref_phase ^= 1u;
+                    m_loaded = m_tile;
+                }
                 for (int t = t_begin; t < t_end; ++t) {
                     MbarWait(&bar_acc_empty[acc], acc_phase ^ 1u);
                     TcFenceAfter();
@@ -363,7 +363,7 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
                     for (int kb = 0; kb < k_blocks; ++kb) {
                         MbarWait(&bar_full[stage], phase);
                         TcFenceAfter();
-                        const uint64_t adesc = MakeSmemDesc(a_tile + kb * kBoxBytesA);
+                        const uint64_t adesc = MakeSmemDesc(smem_a + kb * kBoxBytesA);
                         const uint64_t bdesc = MakeSmemDesc(smem_b + stage * kBoxBytesB);
 #pragma unroll
                         for (int k = 0; k < kKBlock / 16; ++k) {
@@ -380,11 +380,8 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1u;
                 }
-                UmmaCommit(&bar_a_empty[slot]);  // the reference slot may be refilled once this item's MMAs retire
-                if (++slot == kSlotsA) {
-                    slot = 0;
-                    slot_phase ^= 1u;
-                }
+                // the reference tile may be replaced once the MMAs of its last item retire
+                if (item + 1 < item_end && (item + 1) / n_splits != m_tile) UmmaCommit(bar_a_empty);
             }
         }
         __syncwarp();
@@ -397,8 +394,8 @@ CosineTcKernel(const __grid_constant__ CUtensorMap map_ref, const __grid_constan
         // for real candidates only instead of for every running maximum of the random background.
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int split = item / m_tiles, row = (item % m_tiles) * kTileM + quarter * 32 + lane;
+        for (int item = item_begin; item < item_end; ++item) {
+        const int split = item % n_splits, row = (item / n_splits) * kTileM + quarter * 32 + lane;
         const int t_begin = split * tiles_per_split, t_end = min(n_tiles, t_begin + tiles_per_split);
         float b1 = floor_dot, b2 = -INFINITY;
         int j1 = -1;
@@ -513,7 +510,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(kRerankThreads, 5) RerankKernel(const float *ref, int n_ref, const float *cur, int dim, const float *ref_norm,
                                                               const float *cur_norm, const Top2 *top, int n_splits, int n_ref_pad,
                                                               unsigned long long *best, int2 *work, int *counters, const int *abn_cur, float max_dist,
-                                                              int *idx) {
+                                                              int fill_unmatched, int *idx) {
     const int lane = threadIdx.x & 31, l = lane & (kRowLanes - 1), base = lane & ~(kRowLanes - 1);
     const int i = blockIdx.x * kRerankRows + threadIdx.x / kRowLanes;
     const bool live = i < n_ref;
@@ -552,14 +549,14 @@ __global__ void __launch_bounds__(kRerankThreads, 5) RerankKernel(const float *r
         const int src = base | (split & (kRowLanes - 1));
         const int j_lo = __shfl_sync(0xFFFFFFFFu, t0.j1, src), j_hi = __shfl_sync(0xFFFFFFFFu, t1.j1, src);
         const int j = has ? (split < kRowLanes ? j_lo : j_hi) : 0;
-        float a[kRowBlocks][8], b[kRowBlocks][8];
+        float a[kRowBlocks][kRun], b[kRowBlocks][kRun];
         GroupLoadRow<VEC>(ref + static_cast<size_t>(has ? i : 0) * dim, has ? dim : 0, l, a);
         GroupLoadRow<VEC>(cur + static_cast<size_t>(j) * dim, has ? dim : 0, l, b);
         const float nb = has ? cur_norm[j] : 1.0f;
 #pragma unroll
         for (int q = 0; q < kRowBlocks; ++q)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) a[q][e] = __fmul_rn(a[q][e], b[q][e]);
+            for (int e = 0; e < kRun; ++e) a[q][e] = __fmul_rn(a[q][e], b[q][e]);
         const float dot = GroupChainSum(a, dim, lane);
         const float d = __fsub_rn(0.5f, __fmul_rn(__fdiv_rn(__fdiv_rn(dot, na), nb), 0.5f));
         if (has && d == d) {
@@ -584,14 +581,17 @@ __global__ void __launch_bounds__(kRerankThreads, 5) RerankKernel(const float *r
         work[atomicAdd(&counters[0], 1)] = make_int2(i, static_cast<int>(scan));
     } else if (key != kNoKey64 && KeyFloat(static_cast<unsigned>(key >> 32)) < max_dist) {
         idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+    } else if (fill_unmatched) {
+        idx[i] = -1;  // otherwise the caller's entry stays (descriptor_matcher.h: only matched rows are assigned)
     }
 }
 
 // One block per queued row: exact scan of the column ranges of the flagged splits, merged with the row's parked key; writes idx.
 __global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const float *cur, int n_cur, int dim, const float *ref_norm, const float *cur_norm,
                                                       const int2 *work, const int *counters, int cols_per_split, int n_splits,
-                                                      const unsigned long long *best, float max_dist, int *idx) {
+                                                      const unsigned long long *best, float max_dist, int fill_unmatched, int *idx) {
     __shared__ unsigned long long s_key[4];
+    GridDepLaunchDependents();  // whatever follows on the stream may set itself up; it orders its own accesses (GridDepWait)
     GridDepWait();
     const int n = counters[0];
     for (int w = blockIdx.x; w < n; w += gridDim.x) {
@@ -621,7 +621,10 @@ __global__ void __launch_bounds__(128) ExactScanKernel(const float *ref, const f
         if (threadIdx.x == 0) {
             key = best[i];
             for (int q = 0; q < 4; ++q) key = s_key[q] < key ? s_key[q] : key;
-            if (key != kNoKey64 && KeyFloat(static_cast<unsigned>(key >> 32)) < max_dist) idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+            if (key != kNoKey64 && KeyFloat(static_cast<unsigned>(key >> 32)) < max_dist)
+                idx[i] = static_cast<int>(key & 0xFFFFFFFFull);
+            else if (fill_unmatched)
+                idx[i] = -1;
         }
         __syncthreads();
     }
@@ -673,7 +676,8 @@ cudaError_t LaunchDependent(void (*kernel)(Params...), int grid, int block, size
 // Returns FTK_ERR_UNSUPPORTED when the tensor-core path does not cover the shape (dim > 256): the caller then runs the
 // exact CUDA-core kernel of match.cu.  Four launches: NormPrepKernel (both sets) -> CosineTcKernel -> RerankKernel (finishes the
 // rows) -> ExactScanKernel (finishes the few rows the screening could not decide; its blocks exit at once when there are none).
-int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx) {
+int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx,
+                            bool fill_unmatched) {
     if (dim > kMaxKBlocks * kKBlock) return FTK_ERR_UNSUPPORTED;
     if (n_ref == 0) return FTK_OK;
     cudaStream_t st = ctx->stream;
@@ -731,8 +735,8 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     // float4 row loads need 16-byte aligned rows: dim % 4 == 0 and aligned bases (device pointers may come from the caller)
     const bool vec = dim % 4 == 0 && (reinterpret_cast<uintptr_t>(d_ref) | reinterpret_cast<uintptr_t>(d_cur)) % 16 == 0;
     const int ref_blocks = Blocks(n_ref, kPrepRows);
-    (vec ? NormPrepKernel<true> : NormPrepKernel<false>)<<<ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, 0, st>>>(
-        d_ref, n_ref, d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm, ref_unit, cur_unit, counters, next_counters, abn_cur);
+    FTK_CUDA_CHECK(ctx, LaunchDependent(vec ? NormPrepKernel<true> : NormPrepKernel<false>, ref_blocks + Blocks(n_cur, kPrepRows), kPrepThreads, 0, st, d_ref, n_ref,
+                                        d_cur, n_cur, ref_blocks, dim, k_pad, ref_norm, cur_norm, ref_unit, cur_unit, counters, next_counters, abn_cur));
 
     // cos > 1 - 2 * max_dist is necessary for distance < max_dist; 3 * kEpsDot covers the BF16 dot error and the fp32 rounding of the
     // distance formula.  NaN / huge thresholds give NaN / -inf floors: nothing or everything passes, as in the reference.
@@ -742,12 +746,12 @@ int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, con
     const int n_items = m_tiles * splits;
     ProfBegin(ctx);
     FTK_CUDA_CHECK(ctx, LaunchDependent(CosineTcKernel, n_items < ctx->sm_count ? n_items : ctx->sm_count, kTcThreads, kTcSmemBytes, st, map_ref, map_cur, n_ref,
-                                        n_cur, k_blocks, tiles_per_split, n_tiles, m_tiles, n_items, top, n_ref_pad, floor_dot));
+                                        n_cur, k_blocks, tiles_per_split, n_tiles, splits, n_items, top, n_ref_pad, floor_dot));
     ProfEnd(ctx);
     FTK_CUDA_CHECK(ctx, LaunchDependent(vec ? RerankKernel<true> : RerankKernel<false>, Blocks(n_ref, kRerankRows), kRerankThreads, 0, st, d_ref, n_ref, d_cur, dim,
-                                        ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, d_idx));
+                                        ref_norm, cur_norm, top, splits, n_ref_pad, best, work, counters, abn_cur, max_dist, fill_unmatched ? 1 : 0, d_idx));
     FTK_CUDA_CHECK(ctx, LaunchDependent(ExactScanKernel, ctx->sm_count * 2, 128, 0, st, d_ref, d_cur, n_cur, dim, ref_norm, cur_norm, work, counters,
-                                        tiles_per_split * kTileN, splits, best, max_dist, d_idx));
+                                        tiles_per_split * kTileN, splits, best, max_dist, fill_unmatched ? 1 : 0, d_idx));
     FTK_CUDA_CHECK(ctx, cudaGetLastError());
     ctx->cos_counters_clean = true;
     ctx->launches += 4;
