@@ -173,7 +173,7 @@ void ftk_destroy(ftk_context *ctx) {
     cudaStreamSynchronize(ctx->stream);
     FtkBuffer *all[] = {&ctx->d_ref_uv, &ctx->d_cur_uv, &ctx->d_status, &ctx->d_offsets, &ctx->d_ref_img, &ctx->d_cur_img, &ctx->d_feat_pair,
                         &ctx->d_chunk_offsets, &ctx->d_chunk_curmap, &ctx->d_back_uv, &ctx->d_back_status, &ctx->d_small, &ctx->d_dm_K, &ctx->d_dm_points, &ctx->d_dm_q, &ctx->d_dm_p, &ctx->d_flow, &ctx->d_det_response, &ctx->d_det_state, &ctx->d_det_cand, &ctx->d_det_keys, &ctx->d_det_tmp, &ctx->d_det_out, &ctx->d_det_pattern, &ctx->d_desc_ref, &ctx->d_desc_cur, &ctx->d_idx, &ctx->d_pred_uv, &ctx->d_pos_cur, &ctx->d_work0, &ctx->d_work1,
-                        &ctx->d_work2, &ctx->d_work3, &ctx->d_cos_counters};
+                        &ctx->d_work2, &ctx->d_work3, &ctx->d_cos_counters, &ctx->d_nearby_state};
     for (FtkBuffer *b : all) FreeBuffer(*b);
     for (int b = 0; b < ftk_context::kStageBuffers; ++b) {
         if (ctx->stage_pyr[b]) {
@@ -747,8 +747,8 @@ int ftk_match_hamming_force(ftk_context *ctx, const uint32_t *ref, int32_t n_ref
     if (int rc = Stage(ctx, ctx->d_desc_ref, ref, static_cast<size_t>(n_ref) * words, on_device, &d_ref)) return rc;
     if (int rc = Stage(ctx, ctx->d_desc_cur, cur, static_cast<size_t>(n_cur) * words, on_device, &d_cur)) return rc;
     int *d_idx = nullptr;
-    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
-    if (int rc = ftk::LaunchHammingForce(ctx, d_ref, n_ref, d_cur, n_cur, words, max_dist, d_idx)) return rc;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx, true)) return rc;
+    if (int rc = ftk::LaunchHammingForce(ctx, d_ref, n_ref, d_cur, n_cur, words, max_dist, d_idx, (flags & FTK_FLAG_NO_INDEX_INPUT) != 0)) return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 
@@ -767,8 +767,10 @@ int ftk_match_hamming_nearby(ftk_context *ctx, const uint32_t *ref, int32_t n_re
     if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
     if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
     int *d_idx = nullptr;
-    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
-    if (int rc = ftk::LaunchHammingNearby(ctx, d_ref, n_ref, d_cur, n_cur, words, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx, true)) return rc;
+    if (int rc = ftk::LaunchHammingNearby(ctx, d_ref, n_ref, d_cur, n_cur, words, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx,
+                                          (flags & FTK_FLAG_NO_INDEX_INPUT) != 0))
+        return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 
@@ -1125,8 +1127,10 @@ int ftk_match_cosine_nearby(ftk_context *ctx, const float *ref, int32_t n_ref, c
     if (int rc = Stage(ctx, ctx->d_pred_uv, reinterpret_cast<const float2 *>(pred_uv), n_ref, on_device, &d_pred)) return rc;
     if (int rc = Stage(ctx, ctx->d_pos_cur, reinterpret_cast<const float2 *>(cur_uv), n_cur, on_device, &d_pos)) return rc;
     int *d_idx = nullptr;
-    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx)) return rc;
-    if (int rc = ftk::LaunchCosineNearby(ctx, d_ref, n_ref, d_cur, n_cur, dim, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx)) return rc;
+    if (int rc = PrepareIndex(ctx, idx, n_ref, flags, &d_idx, true)) return rc;
+    if (int rc = ftk::LaunchCosineNearby(ctx, d_ref, n_ref, d_cur, n_cur, dim, d_pred, d_pos, max_drow, max_dcol, max_dist, d_idx,
+                                         (flags & FTK_FLAG_NO_INDEX_INPUT) != 0))
+        return rc;
     return FinishIndex(ctx, idx, n_ref, flags, d_idx);
 }
 

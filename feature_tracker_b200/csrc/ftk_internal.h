@@ -66,6 +66,10 @@ struct ftk_context {
     FtkBuffer d_cos_counters;
     unsigned cos_calls = 0;
     bool cos_counters_clean = false;
+    // NearbyMatch grid: bounds / ticket / grid descriptor / per-cell counts live in one buffer whose "between calls" state (bounds at
+    // their initial values, every count zero) is restored by the kernels themselves, so a call needs neither a memset nor a copy
+    FtkBuffer d_nearby_state;
+    bool nearby_state_clean = false;
     bool use_fast_paths = true;  // FTK_DISABLE_FASTPATH=1 forces the generic kernels (A/B testing)
     // device scratch
     FtkBuffer d_ref_uv, d_cur_uv, d_status, d_offsets, d_ref_img, d_cur_img, d_feat_pair;
@@ -94,6 +98,25 @@ inline void ProfEnd(ftk_context *ctx) {
     }
 }
 int EnsureDevice(ftk_context *ctx, FtkBuffer &buf, size_t bytes);
+
+#ifdef __CUDACC__
+// Programmatic dependent launch: the kernels of one call are launched with the stream-serialization attribute, so that the launch
+// latency and the prologue of kernel n + 1 overlap the tail of kernel n.  Every such kernel announces its dependents at once and waits
+// for its predecessor (complete and flushed) right before its first access to anything an earlier kernel of the stream may have written.
+__device__ __forceinline__ void GridDepLaunchDependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void GridDepWait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... Params, typename... Args>
+cudaError_t LaunchDependent(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cfg.attrs = &attr, cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+#endif
 
 #define FTK_CUDA_CHECK(ctx, expr)                                                                              \
     do {                                                                                                       \
@@ -149,15 +172,16 @@ int LaunchDescribeBrief(ftk_context *ctx, const PyramidView &pyr, int first, int
                         const char4 *d_pattern, int n_bits, int half_patch, uint32_t *d_desc, uint8_t *d_valid);
 
 // match.cu
-int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx);
+int LaunchHammingForce(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, float max_dist, int *d_idx,
+                       bool fill_unmatched);
+// fill_unmatched (here and below): d_idx holds no input -- rows without a match get -1, written with the results instead of a memset
 int LaunchHammingNearby(ftk_context *ctx, const uint32_t *d_ref, int n_ref, const uint32_t *d_cur, int n_cur, int words, const float2 *d_pred,
-                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
+                        const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx, bool fill_unmatched);
 int LaunchHammingPairs(ftk_context *ctx, const uint32_t *d_ref, const uint32_t *d_cur, int words, int n_ref_total, const int *d_ref_pair,
                        const int *d_ref_off, const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist,
                        int *d_idx);
 int LaunchCosinePairs(ftk_context *ctx, const float *d_ref, const float *d_cur, int dim, int n_ref_total, int n_cur_total, const int *d_ref_pair,
                       const int *d_cur_off, const float2 *d_pred, const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
-// fill_unmatched: d_idx holds no input -- rows without a match get -1 (the tensor-core path writes it with the results instead of a memset)
 int LaunchCosineForce(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx, bool fill_unmatched);
 // match_mutual.cu: mutual arg-max of a score matrix; cross-check filter
 int LaunchMutualScores(ftk_context *ctx, const float *d_scores, int n_ref, int n_cur, float min_score, int *d_idx);
@@ -165,7 +189,7 @@ int LaunchCrossCheck(ftk_context *ctx, int *d_idx_fwd, int n_ref, const int *d_i
 // match_cosine_tc.cu: tcgen05 GEMM + exact re-rank; FTK_ERR_UNSUPPORTED for dim > 256
 int LaunchCosineForceTensor(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, float max_dist, int *d_idx, bool fill_unmatched);
 int LaunchCosineNearby(ftk_context *ctx, const float *d_ref, int n_ref, const float *d_cur, int n_cur, int dim, const float2 *d_pred,
-                       const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx);
+                       const float2 *d_pos, int max_drow, int max_dcol, float max_dist, int *d_idx, bool fill_unmatched);
 
 }  // namespace ftk
 
