@@ -545,6 +545,42 @@ def test_cosine_force_odd_dims_and_unaligned_device_pointers(ctx, oracle):
         assert np.array_equal(d_idx.cpu().numpy(), exp), (dim, shift)
 
 
+def test_cosine_large_shapes_tensor_path_equals_exact_kernel(monkeypatch):
+    """Shapes far beyond BASELINE's: every persistent CTA of the tcgen05 kernel walks dozens of work items and changes its reference tile
+    many times (pipeline parities wrap repeatedly).  The checker here is the library's own exact CUDA-core kernel (a context created with
+    FTK_DISABLE_FASTPATH=1), which the smaller tests pin to the oracle; sizes the CPU oracle would need minutes for."""
+    import ctypes as C
+    import torch
+    from feature_tracker_b200 import _capi
+    from feature_tracker_b200.api import lib as ftk_lib
+    L = ftk_lib()
+    monkeypatch.delenv("FTK_DISABLE_FASTPATH", raising=False)
+    fast = ft.Context(0)
+    monkeypatch.setenv("FTK_DISABLE_FASTPATH", "1")
+    exact = ft.Context(0)
+    monkeypatch.delenv("FTK_DISABLE_FASTPATH", raising=False)
+    dev = torch.device("cuda", 0)
+    vp = C.c_void_p
+    fl = _capi.FLAG_DEVICE_POINTERS | _capi.FLAG_NO_INDEX_INPUT
+    for n_ref, n_cur, dim, max_dist in ((70001, 33000, 96, 0.1), (150000, 9000, 256, 0.1), (3000, 120000, 64, 0.6), (40000, 40000, 128, 0.05)):
+        g = torch.Generator(device=dev).manual_seed(n_ref + dim)
+        d_r = torch.randn((n_ref, dim), generator=g, device=dev, dtype=torch.float32)
+        d_c = torch.randn((n_cur, dim), generator=g, device=dev, dtype=torch.float32)
+        m = min(n_ref, n_cur)
+        perm = torch.randperm(n_cur, generator=g, device=dev)
+        d_c[perm[:m]] = d_r[:m] + 0.2 * torch.randn((m, dim), generator=g, device=dev, dtype=torch.float32)  # planted partners
+        d_c[perm[1]] = d_c[perm[0]]  # an exact duplicate column: ties resolve to the lower index in both paths
+        out = []
+        for context in (fast, exact):
+            d_idx = torch.full((n_ref,), -7, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            context.check(L.ftk_match_cosine_force(context._h, vp(d_r.data_ptr()), n_ref, vp(d_c.data_ptr()), n_cur, dim, max_dist, vp(d_idx.data_ptr()), fl))
+            context.synchronize()
+            out.append(d_idx.cpu().numpy())
+        assert np.array_equal(out[0], out[1]), (n_ref, n_cur, dim, int((out[0] != out[1]).sum()))
+        assert (out[0] >= -1).all() and (out[0][:m] >= 0).mean() > 0.9
+
+
 def test_cosine_two_devices_in_one_process(oracle):
     """One process, contexts on two GPUs: the tensor-core kernel's shared-memory opt-in is per device.  Skipped on a
     single-GPU box."""
