@@ -4,16 +4,19 @@
 // ComputeDistance of test/test_descriptor_matcher_superpoint.cpp:32-34 (d = 0.5 - dot / |a| / |b| * 0.5).
 //
 // The result is still EXACT (same indices as the reference's fp32 evaluation, lowest j on ties):
-//   1. PrepKernel      : unit-normalised BF16 copies of both descriptor sets (K padded to a multiple of 64).
+//   1. NormPrepKernel  : exact fp32 norms (the reference's sequential sum) and unit-normalised BF16 copies of both descriptor sets
+//                        (K padded to a multiple of 64); eight lanes per row, broadcast chain sum.
 //   2. CosineTcKernel  : C = A_hat * B_hat^T with tcgen05.mma (BF16 in, FP32 accumulate in TMEM); operands arrive by TMA
-//                        (128B-swizzled boxes), the 128 x K reference tile stays resident in shared memory while
-//                        128-column tiles of the current set stream through a 2-stage mbarrier pipeline; the score
+//                        (128B-swizzled boxes).  Persistent: one CTA per SM walks a contiguous range of (reference tile, split of
+//                        the current set) work items; the 128 x K reference tile stays resident in shared memory while 256-column
+//                        tiles of the current set stream through a 5-stage mbarrier pipeline; two TMEM accumulators.  The score
 //                        matrix is never written: the epilogue warps read the accumulator with tcgen05.ld and keep a
-//                        running top-2 (largest approximate dot, lowest j first) per reference row in registers.
+//                        running top-2 (largest approximate dot, lowest j first) per reference row and split in registers.
 //   3. RerankKernel    : |approximate dot - exact dot| <= kEpsDot for unit vectors, so only candidates within
 //                        2 * kEpsDot of the row's best approximate dot can be the exact arg-min.  Those (usually one)
 //                        are re-evaluated with the reference's own sequential fp32 arithmetic; rows whose top-2 are
 //                        both inside the margin (a third candidate could hide) go to an exact scan (ExactScanKernel).
+// Kernels 2-4 are launched with programmatic stream serialization (ftk_internal.h: GridDepWait); nothing else is queued per call.
 // Warp roles in CosineTcKernel (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
 // epilogue (one TMEM lane quarter each).
 #include <cstdlib>
