@@ -12,7 +12,9 @@
  *   - uv arrays are interleaved float32 (x = column, y = row), like std::vector<Vec2>.
  *   - status bytes are feature_tracker::TrackStatus values (src/feature_tracker.h:8-14).
  *   - Pointers are HOST pointers unless FTK_FLAG_DEVICE_POINTERS is given; host calls are synchronous (results are
- *     valid on return), device-pointer calls are asynchronous on the context's stream.
+ *     valid on return), device-pointer calls are asynchronous on the context's stream.  Inside a call the matcher kernels may
+ *     overlap each other's launch (programmatic dependent launch); the first kernel of every call is an ordinary launch, so work
+ *     the caller queued on ftk_stream() before the call is complete before the call's kernels read anything.
  *   - A context is bound to one GPU and one stream; it is not re-entrant (the reference objects are not either:
  *     src/optical_flow_tracker/optical_flow.h:94-103).  Use one context per host thread / per GPU.
  *   - There is no CPU fallback: every call fails with FTK_ERR_CUDA when no sm_100 device is usable.
