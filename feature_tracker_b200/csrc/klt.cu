@@ -208,14 +208,13 @@ template <int G>
 __device__ __forceinline__ bool ExGradient(const Ctx<G> &c, int row, int col, float *dx, float *dy) {
     const int e = (row + 1) * c.geo.ec + col + 1;
     const int l = e - 1, r = e + 1, u = e - c.geo.ec, d = e + c.geo.ec;
-    if (c.s.exv[l] && c.s.exv[r] && c.s.exv[u] && c.s.exv[d]) {
-        *dx = fsub(c.s.ex[r], c.s.ex[l]);
-        *dy = fsub(c.s.ex[d], c.s.ex[u]);
-        return true;
-    }
-    *dx = 0.0f;
-    *dy = 0.0f;
-    return false;
+    // The four 0 / 1 flags are read and combined unconditionally: `a && b && c && d` on shared-memory bytes costs a divergent branch per
+    // flag (29 instructions here instead of 8).  The samples of invalid neighbours are 0 and always addressable (interior e).
+    const unsigned ok = c.s.exv[l] & c.s.exv[r] & c.s.exv[u] & c.s.exv[d];
+    const float gx = fsub(c.s.ex[r], c.s.ex[l]), gy = fsub(c.s.ex[d], c.s.ex[u]);
+    *dx = ok ? gx : 0.0f;
+    *dy = ok ? gy : 0.0f;
+    return ok != 0u;
 }
 
 // Step bookkeeping shared by the fast trackers (basic_klt_fast.cpp:48-60, affine_klt_fast.cpp:55-67,
@@ -387,7 +386,7 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
                 const int prow = w.row, pcol = w.col;
                 const int row = min_row + prow, col = min_col + pcol;
                 const int e = (prow + 1) * c.geo.ec + pcol + 1;
-                ok = !(row < 0 || row > cur.rows - 2 || col < 0 || col > cur.cols - 2) && c.s.exv[e];
+                ok = !(row < 0 || row > cur.rows - 2 || col < 0 || col > cur.cols - 2) & (c.s.exv[e] != 0);  // flag read unconditionally: no branch
                 if (ok) {
                     const float cur_value = fadd(fadd(fadd(fmul(w_tl, PxI(cur, row, col)), fmul(w_tr, PxI(cur, row, col + 1))), fmul(w_bl, PxI(cur, row + 1, col))),
                                                  fmul(w_br, PxI(cur, row + 1, col + 1)));
@@ -672,7 +671,8 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
                 const float row_c = fadd(ay, s.cur_y), col_c = fadd(ax, s.cur_x);
                 const int e = (prow + 1) * c.geo.ec + pcol + 1;
                 float cur_value;
-                ok = PxChecked(cur, row_c, col_c, &cur_value) && c.s.exv[e];
+                const bool ref_ok = c.s.exv[e] != 0;  // read before the sample so that `&&` does not become a second branch
+                ok = PxChecked(cur, row_c, col_c, &cur_value) & ref_ok;
                 if (ok) {
                     bdt = fsub(cur_value, c.s.ex[e]);
                     bx = col_c, by = row_c, bdx = c.s.dx[k], bdy = c.s.dy[k];
@@ -1062,7 +1062,7 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
                 const int prow = w.row, pcol = w.col;
                 const float row_i = fadd(static_cast<float>(w.row - c.geo.hr), ref_y), col_i = fadd(static_cast<float>(w.col - c.geo.hc), ref_x);
                 const int e = (prow + 1) * c.geo.ec + pcol + 1;
-                ok = c.s.exv[e] && c.s.curv[k];
+                ok = (c.s.exv[e] & c.s.curv[k]) != 0;
                 if (ok) {
                     const float s0 = fadd(fmul(s.R[0], -row_i), fmul(s.R[1], col_i));
                     const float s1 = fadd(fmul(s.R[2], -row_i), fmul(s.R[3], col_i));
