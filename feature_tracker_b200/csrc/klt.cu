@@ -584,28 +584,36 @@ __device__ __forceinline__ void AffineApply(AffineState &s, const float (&z)[6],
 }
 
 // affine_klt.cpp:93-129 TrackOneFeature.
+// `done` on entry: this group only keeps its partner company (a feature that is not tracked, or a group without a feature).  The loop
+// runs until every group that shares the warp-level operations (Group::mask) has left it: a finished group keeps executing the same
+// instructions on its frozen state and discards the results, so barriers and votes stay warp-uniform.
 template <int METHOD, int G>
-__device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
+__device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status, bool done = false) {
     const unsigned long long ref_bits = AffineHoistRef<METHOD, G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        if (c.g.all(done)) break;
         float z[6];
-        if (AffineConstruct<METHOD, G>(c, cur, s, ref_bits) == 0) break;
+        if (AffineConstruct<METHOD, G>(c, cur, s, ref_bits) == 0) done = true;  // `break` in the reference
+        if (c.g.all(done)) break;
         Ldlt6FactorShared(c.g, *c.s.ldlt);  // hessian.ldlt().solve(bias), affine_klt.cpp:103
         Ldlt6SolveShared(c.g, *c.s.ldlt, z);
+        if (done) continue;
         const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
         const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);
         if (IsNan(v0) || IsNan(v1)) {
             status = FTK_STATUS_NUMERIC_ERROR;
-            break;
+            done = true;
+            continue;
         }
         AffineApply(s, z, v0, v1);
         if (IsOutside(cur, s.cur_x, s.cur_y)) {
             status = FTK_STATUS_OUTSIDE;
-            break;
+            done = true;
+            continue;
         }
         if (fadd(fmul(v0, v0), fmul(v1, v1)) < c.p->max_converge_step) {
             status = FTK_STATUS_TRACKED;
-            break;
+            done = true;
         }
     }
 }
@@ -1098,11 +1106,16 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
 template <int VARIANT, int METHOD, int G>
 __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD == FTK_METHOD_FAST ? 8 : 7) KltKernel(KltLaunch a, SmemLayout layout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Ctx<G> c;
+    // Affine kDirect on 16 lanes: both groups of a warp run one instruction stream (see Group / AffineTrackOne), so a group without a
+    // feature shadows the last one and writes nothing instead of leaving.
+    constexpr bool kWholeWarp = VARIANT == FTK_VARIANT_AFFINE && METHOD == kDirect && G == 16;
+    Ctx<G> c{PatchWalk{}, Group<G>(kWholeWarp)};
     const int groups_per_block = blockDim.x / G;
     const int group_in_block = threadIdx.x / G;
-    const int f = blockIdx.x * groups_per_block + group_in_block;
-    if (f >= a.n_features) return;
+    const int f_raw = blockIdx.x * groups_per_block + group_in_block;
+    const bool exists = f_raw < a.n_features;
+    if (!kWholeWarp && !exists) return;
+    const int f = exists ? f_raw : a.n_features - 1;
 
     c.s = CarveScratch(smem_raw + static_cast<size_t>(group_in_block) * layout.total_bytes, layout);
     c.ch.term = c.s.term;
@@ -1133,8 +1146,8 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
     uint8_t status = a.has_status ? a.status[f] : static_cast<uint8_t>(FTK_STATUS_NOT_TRACKED);  // :17-19
 
     // basic_klt.cpp:9,12,15: only the first kMaxTrackPointsNumber features, never re-track failed ones.
-    const bool tracked = static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
-    if (tracked) {
+    const bool tracked = exists && static_cast<uint32_t>(local) < a.p.max_track_points && status <= FTK_STATUS_TRACKED;
+    if (kWholeWarp ? !c.g.all(!tracked) : tracked) {
         const int ref_image = a.ref_image ? a.ref_image[pair] : pair;
         const int cur_image = a.cur_image ? a.cur_image[pair] : pair;
         const Img cur0 = LevelImage(a.cur, cur_image, 0);
@@ -1151,8 +1164,8 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                 {
                     AffineState s{cur_uv.x, cur_uv.y, {a.p.predict[0], a.p.predict[1], a.p.predict[2], a.p.predict[3]}};
                     if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
-                    else AffineTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
-                    cur_uv = make_float2(s.cur_x, s.cur_y);
+                    else AffineTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
+                    if (tracked) cur_uv = make_float2(s.cur_x, s.cur_y);
                 }
             } else {
                 // lssd_klt.cpp:63-94: the result is never written back to cur_pixel_uv (reference quirk, kept).
@@ -1188,12 +1201,12 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                     for (int l = levels - 1; l > -1; --l) {
                         const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
                         if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
-                        else AffineTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                        else AffineTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
                         if (l == 0) break;
                         sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
                         s.cur_x = fmul(s.cur_x, 2.0f), s.cur_y = fmul(s.cur_y, 2.0f);
                     }
-                    cur_uv = make_float2(s.cur_x, s.cur_y);
+                    if (tracked) cur_uv = make_float2(s.cur_x, s.cur_y);
                 }
             } else {
                 // lssd_klt.cpp:7-61
@@ -1215,9 +1228,9 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
             }
         }
         // final "outside" test on level-0 size (basic_klt.cpp:49-53 and twins)
-        if (IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;
+        if (tracked && IsOutside(cur0, cur_uv.x, cur_uv.y)) status = FTK_STATUS_OUTSIDE;
     }
-    if (c.g.lane == 0) {
+    if (c.g.lane == 0 && exists) {
         a.cur_uv[f] = cur_uv;
         a.status[f] = status;
     }

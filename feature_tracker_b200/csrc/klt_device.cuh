@@ -180,18 +180,26 @@ __device__ __forceinline__ bool IsOutside(const Img &im, float x, float y) {
 // ---- lane groups: G lanes of a warp cooperate on one feature ---------------------------------------------------
 template <int G>
 struct Group {
-    int lane;       // 0..G-1
-    int base;       // first lane of the group inside the warp
-    unsigned mask;  // member mask of the group
-    __device__ __forceinline__ Group() {
+    int lane;        // 0..G-1
+    int base;        // first lane of the group inside the warp
+    unsigned mask;   // mask of the warp-level operations: the group's lanes, or the whole warp (see `whole_warp`)
+    unsigned lanes;  // the group's lanes
+    // whole_warp: every group of the warp runs the same instruction stream (the kernel guarantees it: finished groups keep executing
+    // with their results discarded), so barriers / votes / shuffles may name the full warp.  ptxas then emits the plain instruction; a
+    // per-lane sub-warp mask costs a REDUX.OR + R2UR + BRA.DIV uniformity check around every one of them (3 % of the affine kDirect
+    // kernel's instructions).
+    __device__ __forceinline__ explicit Group(bool whole_warp = false) {
         const int l = threadIdx.x & 31;
         lane = l % G;
         base = l - lane;
-        mask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << base);
+        lanes = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << base);
+        mask = whole_warp ? 0xFFFFFFFFu : lanes;
     }
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-    __device__ __forceinline__ int count(bool pred) const { return __popc(__ballot_sync(mask, pred)); }
+    __device__ __forceinline__ int count(bool pred) const { return __popc(__ballot_sync(mask, pred) & lanes); }
     __device__ __forceinline__ float get(float v, int src) const { return __shfl_sync(mask, v, base + src); }
+    // true when `pred` holds on every group that takes part in the group's warp-level operations
+    __device__ __forceinline__ bool all(bool pred) const { return __all_sync(mask, pred); }
 };
 
 // ---- chains: K accumulators, one per lane, folded sequentially over the G terms of a chunk -----------------------
@@ -419,10 +427,8 @@ __device__ __forceinline__ void LdltFactorShared(const Group<G> &g, LdltShared<N
     bool zero_diag = false;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        if (zero_diag) {
-            tr[k] = k;
-            continue;
-        }
+        // After a zero first pivot (zero_diag) the reference stops: the remaining steps then change nothing, but still execute their
+        // barriers -- the groups of a warp may share them (Group::mask), so every group must pass the same number.
         int p = k;
         float best = fabsf(a[k * N + k]);
 #pragma unroll
@@ -433,6 +439,7 @@ __device__ __forceinline__ void LdltFactorShared(const Group<G> &g, LdltShared<N
                 p = i;
             }
         }
+        if (zero_diag) p = k;
         tr[k] = p;
         g.sync();  // every lane has read the diagonal
         {
@@ -450,7 +457,7 @@ __device__ __forceinline__ void LdltFactorShared(const Group<G> &g, LdltShared<N
         }
         g.sync();
         if (k > 0) {
-            if (lane >= k && lane < N) {
+            if (!zero_diag && lane >= k && lane < N) {
                 // lane == k: a[k][k] -= sum_j a[k][j] * temp[j]; lane > k: a[i][k] -= sum_j a[i][j] * temp[j]; temp[j] = a[j][j] * a[k][j]
                 float sum = fmul(a[lane * N + 0], fmul(a[0 * N + 0], a[k * N + 0]));
 #pragma unroll
@@ -464,7 +471,7 @@ __device__ __forceinline__ void LdltFactorShared(const Group<G> &g, LdltShared<N
         if (k == 0 && !pivot_ok) {
             tr[0] = 0;
             zero_diag = true;
-        } else if (pivot_ok) {
+        } else if (pivot_ok && !zero_diag) {
             if (lane > k && lane < N) a[lane * N + k] = fdiv(a[lane * N + k], akk);
         }
         g.sync();
