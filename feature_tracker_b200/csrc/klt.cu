@@ -620,11 +620,14 @@ __device__ void AffineTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float 
 
 // affine_klt_fast.cpp:7-69 TrackOneFeatureFast (+ :71-138 PrecomputeJacobianAndHessian, :140-188 ComputeBias).
 template <int G>
-__device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status) {
-    if (ExtractExRefPatch(c, ref, ref_x, ref_y) == 0) {
+__device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, AffineState &s, uint8_t &status,
+                                   bool done = false) {  // `done`: see AffineTrackOne
+    const int valid_ref = ExtractExRefPatch(c, ref, ref_x, ref_y);
+    if (!done && valid_ref == 0) {
         status = FTK_STATUS_OUTSIDE;
-        return;
+        done = true;  // `return` in the reference
     }
+    if (c.g.all(done)) return;
     // Hessian at the level-entry cur position: 21 chains of which (1,2), (1,4), (3,4) are overwritten by copies.
     c.ch.reset();
     PatchWalk w = c.walk;
@@ -661,8 +664,9 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
 
     float last_squared_step = INFINITY;
     uint32_t large_step_cnt = 0;
-    status = FTK_STATUS_LARGE_RESIDUAL;
+    if (!done) status = FTK_STATUS_LARGE_RESIDUAL;
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        if (c.g.all(done)) break;
         int valid = 0;
         c.ch.reset();
         PatchWalk w = c.walk;
@@ -693,22 +697,25 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
             c.ch.template fold<6>(c.g);
             w.next();
         }
-        if (valid == 0) break;
+        if (valid == 0) done = true;  // `break` in the reference
+        if (c.g.all(done)) break;
         float z[6];
         AffineScatterChains(c, 6);
         Ldlt6SolveShared(c.g, *c.s.ldlt, z);
+        if (done) continue;
         bool any_nan = false;
 #pragma unroll
         for (int q = 0; q < 6; ++q) any_nan = any_nan || IsNan(z[q]);
         if (any_nan) {
             status = FTK_STATUS_NUMERIC_ERROR;
-            break;
+            done = true;
+            continue;
         }
         const float v0 = fadd(fadd(fmul(z[0], s.cur_x), fmul(z[2], s.cur_y)), z[4]);
         const float v1 = fadd(fadd(fmul(z[1], s.cur_x), fmul(z[3], s.cur_y)), z[5]);
         AffineApply(s, z, v0, v1);
         const float squared_step = fadd(fmul(v0, v0), fmul(v1, v1));
-        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) break;
+        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) done = true;
     }
 }
 
@@ -1106,9 +1113,9 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
 template <int VARIANT, int METHOD, int G>
 __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD == FTK_METHOD_FAST ? 8 : 7) KltKernel(KltLaunch a, SmemLayout layout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Affine kDirect on 16 lanes: both groups of a warp run one instruction stream (see Group / AffineTrackOne), so a group without a
+    // Affine trackers on 16 lanes: both groups of a warp run one instruction stream (see Group / AffineTrackOne), so a group without a
     // feature shadows the last one and writes nothing instead of leaving.
-    constexpr bool kWholeWarp = VARIANT == FTK_VARIANT_AFFINE && METHOD == kDirect && G == 16;
+    constexpr bool kWholeWarp = VARIANT == FTK_VARIANT_AFFINE && G == 16;
     Ctx<G> c{PatchWalk{}, Group<G>(kWholeWarp)};
     const int groups_per_block = blockDim.x / G;
     const int group_in_block = threadIdx.x / G;
@@ -1163,7 +1170,7 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                 // affine_klt.cpp:61-91: starts from predict_affine_
                 {
                     AffineState s{cur_uv.x, cur_uv.y, {a.p.predict[0], a.p.predict[1], a.p.predict[2], a.p.predict[3]}};
-                    if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                    if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
                     else AffineTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
                     if (tracked) cur_uv = make_float2(s.cur_x, s.cur_y);
                 }
@@ -1200,7 +1207,7 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                     AffineState s{scur_x, scur_y, {1.0f, 0.0f, 0.0f, 1.0f}};
                     for (int l = levels - 1; l > -1; --l) {
                         const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
-                        if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
+                        if constexpr (METHOD == kFast) AffineTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
                         else AffineTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
                         if (l == 0) break;
                         sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
@@ -1312,10 +1319,20 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_BASIC, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_AFFINE:
-            // kDirect with 16 lanes per feature: two features share a warp's fold / LDLT instructions and 13x13 patches fill 11 chunks of
-            // 16 to 96 % (round 2, paired FADD2 folds: 41.5 ms vs 42.8 ms per 2 M features with 32 lanes; kFast is much slower that way,
-            // 43.8 ms vs 35.9 ms: two features of a warp run max(iterations) of every level)
-            if (geo.psize <= 16 * 64 && a.p.method == kDirect) return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo);
+            // 16 lanes per feature: two features share a warp's fold / LDLT instructions and 13x13 patches fill 11 chunks of 16 to 96 %.  Both
+            // groups run one instruction stream (Group whole-warp mode), which is what makes this pay: with per-group masks the uniformity
+            // checks around every barrier / vote made kFast and kInverse slower on 16 lanes than on 32 (43.8 vs 35.9 ms per 2 M features).
+            // Measured per 200 k features: kDirect (16 lanes before, per-group masks) 3.71 -> 3.33 ms; kFast 32 -> 16 lanes 3.37 -> 3.11 ms, kInverse
+            // 3.91 -> 3.41 ms.
+            // Small CTAs (kDirect 64 threads, kFast / kInverse one warp) balance best: 128 / 64 / 32 threads gave kDirect 3.36 / 3.33 / 3.45,
+            // kFast 3.27 / 3.19 / 3.11, kInverse 3.47 / 3.48 / 3.41 ms.
+            if (geo.psize <= 16 * 64) {
+                switch (a.p.method) {
+                    case kDirect: return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo, 64);
+                    case kInverse: return LaunchOne<FTK_VARIANT_AFFINE, kInverse, 16>(ctx, a, geo, 32);
+                    default: return LaunchOne<FTK_VARIANT_AFFINE, kFast, 16>(ctx, a, geo, 32);
+                }
+            }
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_LSSD:
