@@ -305,37 +305,45 @@ __device__ int BasicConstruct(Ctx<G> &c, const Img &ref, const Img &cur, float r
 
 // basic_klt.cpp:88-116 TrackOneFeature.
 template <int METHOD, int G>
-__device__ void BasicTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status) {
+__device__ void BasicTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status, bool done = false) {
+    // `done`: see AffineTrackOne
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        if (c.g.all(done)) break;
         float H[3], b[2];
-        if (BasicConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s.cur_x, s.cur_y, H, b) == 0) break;
+        if (BasicConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s.cur_x, s.cur_y, H, b) == 0) done = true;  // `break` in the reference
+        if (done) continue;
         const float A[2][2] = {{H[0], H[1]}, {H[1], H[2]}};
         float v[2];
         LdltSolve<2>(A, b, v);
         if (IsNan(v[0]) || IsNan(v[1])) {
             status = FTK_STATUS_NUMERIC_ERROR;
-            break;
+            done = true;
+            continue;
         }
         s.cur_x = fadd(s.cur_x, v[0]);
         s.cur_y = fadd(s.cur_y, v[1]);
         if (IsOutside(cur, s.cur_x, s.cur_y)) {
             status = FTK_STATUS_OUTSIDE;
-            break;
+            done = true;
+            continue;
         }
         if (fadd(fmul(v[0], v[0]), fmul(v[1], v[1])) < c.p->max_converge_step) {
             status = FTK_STATUS_TRACKED;
-            break;
+            done = true;
         }
     }
 }
 
 // basic_klt_fast.cpp:7-62 TrackOneFeatureFast (+ :64-99 PrecomputeJacobianAndHessian, :101-195 ComputeBias).
 template <int G>
-__device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status) {
-    if (ExtractExRefPatch(c, ref, ref_x, ref_y) == 0) {
+__device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, BasicState &s, uint8_t &status,
+                                  bool done = false) {  // `done`: see AffineTrackOne
+    const int valid_ref = ExtractExRefPatch(c, ref, ref_x, ref_y);
+    if (!done && valid_ref == 0) {
         status = FTK_STATUS_OUTSIDE;
-        return;
+        done = true;  // `return` in the reference
     }
+    if (c.g.all(done)) return;
     // gradients + Hessian (3 chains)
     c.ch.reset();
     PatchWalk wg = c.walk;
@@ -362,10 +370,11 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
     LdltFactors<2> factors;
     LdltFactor<2>(A, factors);
 
-    status = FTK_STATUS_LARGE_RESIDUAL;
+    if (!done) status = FTK_STATUS_LARGE_RESIDUAL;
     float last_squared_step = INFINITY;
     uint32_t large_step_cnt = 0;
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        if (c.g.all(done)) break;
         // ComputeBias: integer-aligned window at floor(cur), one weight set.
         const float int_row = floorf(s.cur_y), int_col = floorf(s.cur_x);
         const float dec_row = fsub(s.cur_y, int_row), dec_col = fsub(s.cur_x, int_col);
@@ -401,18 +410,20 @@ __device__ void BasicTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, flo
             c.ch.template fold<2>(c.g);
             w.next();
         }
-        if (valid == 0) break;
         const float b[2] = {c.g.get(c.ch.acc, 0), c.g.get(c.ch.acc, 1)};
+        if (valid == 0) done = true;  // `break` in the reference
+        if (done) continue;
         float v[2];
         LdltSolveFactored<2>(factors, b, v);
         if (IsNan(v[0]) || IsNan(v[1])) {
             status = FTK_STATUS_NUMERIC_ERROR;
-            break;
+            done = true;
+            continue;
         }
         s.cur_x = fadd(s.cur_x, v[0]);
         s.cur_y = fadd(s.cur_y, v[1]);
         const float squared_step = fadd(fmul(v[0], v[0]), fmul(v[1], v[1]));
-        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) break;
+        if (FastStepCheck(*c.p, squared_step, last_squared_step, large_step_cnt, status)) done = true;
     }
 }
 
@@ -929,7 +940,7 @@ __device__ __forceinline__ void LssdSecondPassHoisted(Ctx<G> &c, float ref_x, fl
 
 // lssd_klt.cpp:127-250 ConstructIncrementalFunction, kInverse, on top of the hoisted reference samples.
 template <int G>
-__device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ref_bits) {
+__device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, float ref_y, const LssdState &s, unsigned long long ref_bits, bool done) {
     const int pf = RoundUp(c.geo.psize, 4);
     const float *hfx = c.s.hoist, *hfy = c.s.hoist + pf, *hv4 = c.s.hoist + 2 * pf;
     float *hv5 = c.s.hoist + 3 * pf;
@@ -964,31 +975,37 @@ __device__ int LssdConstructHoisted(Ctx<G> &c, const Img &cur, float ref_x, floa
     const float ref_avg = fdiv(c.g.get(c.ch.acc, 0), static_cast<float>(valid));
     const float cur_avg = fdiv(c.g.get(c.ch.acc, 1), static_cast<float>(valid));
     const SharedDivisor by_ref = MakeSharedDivisor(ref_avg), by_cur = MakeSharedDivisor(cur_avg);  // every division below is by one of the two patch means
-    if (by_ref.fast && by_cur.fast) LssdSecondPassHoisted<G, true>(c, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
+    // One choice for every group that shares the warp-level operations; a finished group (results discarded) never forces the general form.
+    if (c.g.all(done || (by_ref.fast && by_cur.fast))) LssdSecondPassHoisted<G, true>(c, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
     else LssdSecondPassHoisted<G, false>(c, ref_x, ref_y, s, ok_bits, by_ref, by_cur);
     return valid;
 }
 
 // lssd_klt.cpp:96-125 TrackOneFeature.
 template <int METHOD, int G>
-__device__ void LssdTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, LssdState &s, uint8_t &status) {
+__device__ void LssdTrackOne(Ctx<G> &c, const Img &ref, const Img &cur, float ref_x, float ref_y, LssdState &s, uint8_t &status, bool done = false) {
+    // `done`: see AffineTrackOne
     unsigned long long ref_bits = 0ull;
     if constexpr (METHOD == kInverse) ref_bits = LssdHoistRef<G>(c, ref, ref_x, ref_y);
     for (uint32_t iter = 0; iter < c.p->max_iteration; ++iter) {
+        if (c.g.all(done)) break;
         float v[3];
         int valid;
-        if constexpr (METHOD == kInverse) valid = LssdConstructHoisted<G>(c, cur, ref_x, ref_y, s, ref_bits);
+        if constexpr (METHOD == kInverse) valid = LssdConstructHoisted<G>(c, cur, ref_x, ref_y, s, ref_bits, done);
         else valid = LssdConstruct<METHOD, G>(c, ref, cur, ref_x, ref_y, s);
-        if (valid == 0) break;
+        if (valid == 0) done = true;  // `break` in the reference
+        if (c.g.all(done)) break;
         LssdSolve(c, v);
+        if (done) continue;
         if (IsNan(v[0]) || IsNan(v[1]) || IsNan(v[2])) {
             status = FTK_STATUS_NUMERIC_ERROR;
-            break;
+            done = true;
+            continue;
         }
         LssdUpdate(s, v);
         if (fadd(fadd(fmul(v[0], v[0]), fmul(v[1], v[1])), fmul(v[2], v[2])) < c.p->max_converge_step) {
             status = FTK_STATUS_TRACKED;
-            break;
+            done = true;
         }
     }
 }
@@ -1113,9 +1130,10 @@ __device__ void LssdTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, floa
 template <int VARIANT, int METHOD, int G>
 __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD == FTK_METHOD_FAST ? 8 : 7) KltKernel(KltLaunch a, SmemLayout layout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // Affine trackers on 16 lanes: both groups of a warp run one instruction stream (see Group / AffineTrackOne), so a group without a
+    // Several features per warp (affine and small-patch LSSD kInverse on 16 lanes, basic on 8): the groups of a warp run one instruction stream (see Group / AffineTrackOne), so a group without a
     // feature shadows the last one and writes nothing instead of leaving.
-    constexpr bool kWholeWarp = VARIANT == FTK_VARIANT_AFFINE && G == 16;
+    constexpr bool kWholeWarp = ((VARIANT == FTK_VARIANT_AFFINE || (VARIANT == FTK_VARIANT_LSSD && METHOD == kInverse)) && G == 16) ||
+                                (VARIANT == FTK_VARIANT_BASIC && G == 8);
     Ctx<G> c{PatchWalk{}, Group<G>(kWholeWarp)};
     const int groups_per_block = blockDim.x / G;
     const int group_in_block = threadIdx.x / G;
@@ -1163,9 +1181,9 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
             if constexpr (VARIANT == FTK_VARIANT_BASIC) {
                 // basic_klt.cpp:59-86
                 BasicState s{cur_uv.x, cur_uv.y};
-                if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
-                else BasicTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
-                cur_uv = make_float2(s.cur_x, s.cur_y);
+                if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
+                else BasicTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
+                if (tracked) cur_uv = make_float2(s.cur_x, s.cur_y);
             } else if constexpr (VARIANT == FTK_VARIANT_AFFINE) {
                 // affine_klt.cpp:61-91: starts from predict_affine_
                 {
@@ -1182,7 +1200,7 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                 s.t[0] = fsub(cur_uv.x, fadd(fmul(P[0], ref_uv.x), fmul(P[1], ref_uv.y)));
                 s.t[1] = fsub(cur_uv.y, fadd(fmul(P[2], ref_uv.x), fmul(P[3], ref_uv.y)));
                 if constexpr (METHOD == kFast) LssdTrackOneFast<G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
-                else LssdTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status);
+                else LssdTrackOne<METHOD, G>(c, ref0, cur0, ref_uv.x, ref_uv.y, s, status, !tracked);
             }
         } else {
             const int levels = a.ref.levels;
@@ -1194,13 +1212,13 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                 BasicState s{scur_x, scur_y};
                 for (int l = levels - 1; l > -1; --l) {
                     const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
-                    if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
-                    else BasicTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                    if constexpr (METHOD == kFast) BasicTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
+                    else BasicTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
                     if (l == 0) break;
                     sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
                     s.cur_x = fmul(s.cur_x, 2.0f), s.cur_y = fmul(s.cur_y, 2.0f);
                 }
-                cur_uv = make_float2(s.cur_x, s.cur_y);
+                if (tracked) cur_uv = make_float2(s.cur_x, s.cur_y);
             } else if constexpr (VARIANT == FTK_VARIANT_AFFINE) {
                 // affine_klt.cpp:6-59: affine starts at identity and is carried across levels un-scaled.
                 {
@@ -1225,13 +1243,15 @@ __global__ void __launch_bounds__(128, VARIANT == FTK_VARIANT_AFFINE && METHOD =
                 for (int l = levels - 1; l > -1; --l) {
                     const Img ref = LevelImage(a.ref, ref_image, l), cur = LevelImage(a.cur, cur_image, l);
                     if constexpr (METHOD == kFast) LssdTrackOneFast<G>(c, ref, cur, sref_x, sref_y, s, status);
-                    else LssdTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status);
+                    else LssdTrackOne<METHOD, G>(c, ref, cur, sref_x, sref_y, s, status, !tracked);
                     if (l == 0) break;
                     sref_x = fmul(sref_x, 2.0f), sref_y = fmul(sref_y, 2.0f);
                     s.t[0] = fmul(s.t[0], 2.0f), s.t[1] = fmul(s.t[1], 2.0f);
                 }
-                cur_uv.x = fadd(fadd(fmul(s.R[0], ref_uv.x), fmul(s.R[1], ref_uv.y)), s.t[0]);
-                cur_uv.y = fadd(fadd(fmul(s.R[2], ref_uv.x), fmul(s.R[3], ref_uv.y)), s.t[1]);
+                if (tracked) {
+                    cur_uv.x = fadd(fadd(fmul(s.R[0], ref_uv.x), fmul(s.R[1], ref_uv.y)), s.t[0]);
+                    cur_uv.y = fadd(fadd(fmul(s.R[2], ref_uv.x), fmul(s.R[3], ref_uv.y)), s.t[1]);
+                }
             }
         }
         // final "outside" test on level-0 size (basic_klt.cpp:49-53 and twins)
@@ -1336,8 +1356,10 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);
             break;
         case FTK_VARIANT_LSSD:
-            // (16 lanes per feature, two features sharing every fold: 21.8 ms with 64-thread CTAs, 25.3 ms with 128, against 14.1 ms per 200 k
-            // features at 21x21 -- 7 KB of hoisted samples per feature leave too few warps per SM, and the pair runs max(iterations))
+            // kInverse on 16 lanes per feature (whole-warp mode, one warp per CTA) while the hoisted samples of two features per warp still
+            // leave enough warps on an SM: per 200 k features 13x13 6.15 -> 5.58 ms, 15x15 7.14 -> 6.88 ms, but 17x17 8.28 -> 8.75 ms and
+            // 21x21 (BASELINE configs[2]) 14.2 -> 18.2 ms (7 KB of hoisted samples per feature: 13 warps per SM)
+            if (a.p.method == kInverse && geo.psize <= 15 * 15) return LaunchOne<FTK_VARIANT_LSSD, kInverse, 16>(ctx, a, geo, 32);
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_LSSD, 32>(ctx, a, geo);
             break;
         default:
