@@ -53,9 +53,11 @@ __host__ __device__ inline int RoundUp(int v, int m) { return (v + m - 1) / m * 
 
 __host__ __device__ inline SmemLayout MakeLayout(int variant, int method, int G, const Geometry &geo) {
     SmemLayout l{};
-    const int kmax = variant == FTK_VARIANT_BASIC ? 5 : (variant == FTK_VARIANT_AFFINE ? 27 : 9);
+    int kmax = variant == FTK_VARIANT_BASIC ? 5 : (variant == FTK_VARIANT_AFFINE ? 27 : 9);
+    if (variant == FTK_VARIANT_AFFINE && method == kFast) kmax = G == 16 ? 8 : 21;  // 21 Hessian chains per level (in three parts on 16 lanes), 6 per iteration
     l.term_floats = RoundUp(kmax * (G + 4), 4);
-    if (variant == FTK_VARIANT_AFFINE && G == 16) l.term_floats = RoundUp(G * (2 * G + 4), 4) > l.term_floats ? RoundUp(G * (2 * G + 4), 4) : l.term_floats;  // paired chain layout
+    // paired chain layout of the 16-lane kDirect / kInverse trackers (kFast folds 21 + 6 plain chains: the smaller buffer buys two more CTAs per SM)
+    if (variant == FTK_VARIANT_AFFINE && G == 16 && method != kFast) l.term_floats = RoundUp(G * (2 * G + 4), 4) > l.term_floats ? RoundUp(G * (2 * G + 4), 4) : l.term_floats;
     if (method == kFast) {
         l.ex_floats = RoundUp(geo.esize, 4);
         l.p_floats = RoundUp(geo.psize, 4);
@@ -657,9 +659,23 @@ __device__ void AffineTrackOneFast(Ctx<G> &c, const Img &ref, const Img &cur, fl
             c.s.dy[k] = dy;
         }
         AffineHessianTerms(x, y, dx, dy, t);
+        if constexpr (G == 16) {
+            // 21 chains through an 8-chain buffer in three parts (chains 0..7, 8..15, 16..20): shared memory per feature decides how many
+            // warps an SM holds, and this pass runs once per level
 #pragma unroll
-        for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
-        c.ch.template fold_wide<21>(c.g);
+            for (int q = 0; q < 8; ++q) c.ch.put(c.g.lane, q, t[q]);
+            c.ch.template fold_at<8, 0>(c.g);
+#pragma unroll
+            for (int q = 8; q < 16; ++q) c.ch.put(c.g.lane, q - 8, t[q]);
+            c.ch.template fold_at<8, 8>(c.g);
+#pragma unroll
+            for (int q = 16; q < 21; ++q) c.ch.put(c.g.lane, q - 16, t[q]);
+            c.ch.template fold_hi<5>(c.g);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 21; ++q) c.ch.put(c.g.lane, q, t[q]);
+            c.ch.template fold_wide<21>(c.g);
+        }
         w.next();
     }
     AffineScatterChains(c, 21);
@@ -1344,13 +1360,15 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             // checks around every barrier / vote made kFast and kInverse slower on 16 lanes than on 32 (43.8 vs 35.9 ms per 2 M features).
             // Measured per 200 k features: kDirect (16 lanes before, per-group masks) 3.71 -> 3.33 ms; kFast 32 -> 16 lanes 3.37 -> 3.11 ms, kInverse
             // 3.91 -> 3.41 ms.
-            // Small CTAs (kDirect 64 threads, kFast / kInverse one warp) balance best: 128 / 64 / 32 threads gave kDirect 3.36 / 3.33 / 3.45,
-            // kFast 3.27 / 3.19 / 3.11, kInverse 3.47 / 3.48 / 3.41 ms.
+            // kFast was then limited by shared memory (5.2 KB per feature: 20 warps per SM): its term buffer now holds 8 chains instead of the 16
+            // pairs kDirect needs (the 21 Hessian chains of a level pass through it in three parts) = 3.4 KB per feature, 32 warps per SM with
+            // 128-thread CTAs: 3.11 -> 2.77 ms.  kDirect / kInverse are register limited; 64 / 32 threads per CTA balance best for them
+            // (128 / 64 / 32 threads: kDirect 3.36 / 3.33 / 3.45 ms, kInverse 3.47 / 3.48 / 3.41 ms).
             if (geo.psize <= 16 * 64) {
                 switch (a.p.method) {
                     case kDirect: return LaunchOne<FTK_VARIANT_AFFINE, kDirect, 16>(ctx, a, geo, 64);
                     case kInverse: return LaunchOne<FTK_VARIANT_AFFINE, kInverse, 16>(ctx, a, geo, 32);
-                    default: return LaunchOne<FTK_VARIANT_AFFINE, kFast, 16>(ctx, a, geo, 32);
+                    default: return LaunchOne<FTK_VARIANT_AFFINE, kFast, 16>(ctx, a, geo, 128);
                 }
             }
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_AFFINE, 32>(ctx, a, geo);

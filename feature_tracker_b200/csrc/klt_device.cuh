@@ -230,6 +230,43 @@ struct Chain {
         }
         g.sync();
     }
+    // fold<K> for chains FIRST .. FIRST + K - 1 whose terms were stored in slots 0 .. K - 1: lane FIRST + k folds slot k (a pass that sends its
+    // chains through a buffer of K chains in several parts)
+    template <int K, int FIRST>
+    __device__ __forceinline__ void fold_at(const Group<G> &g) {
+        static_assert(FIRST + K <= G, "one chain per lane");
+        g.sync();
+        if (g.lane >= FIRST && g.lane < FIRST + K) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(term + (g.lane - FIRST) * kStride);
+#pragma unroll
+            for (int q = 0; q < G / 4; ++q) {
+                const float4 v = t4[q];
+                acc = fadd(acc, v.x);
+                acc = fadd(acc, v.y);
+                acc = fadd(acc, v.z);
+                acc = fadd(acc, v.w);
+            }
+        }
+        g.sync();
+    }
+    // fold<K> into the second accumulator: chains G .. G + K - 1 of a pass whose terms were stored in slots 0 .. K - 1 (a pass with more
+    // chains than lanes that reuses a G-chain buffer instead of holding all of its terms at once)
+    template <int K>
+    __device__ __forceinline__ void fold_hi(const Group<G> &g) {
+        g.sync();
+        if (g.lane < K) {
+            const float4 *t4 = reinterpret_cast<const float4 *>(term + g.lane * kStride);
+#pragma unroll
+            for (int q = 0; q < G / 4; ++q) {
+                const float4 v = t4[q];
+                acc_hi = fadd(acc_hi, v.x);
+                acc_hi = fadd(acc_hi, v.y);
+                acc_hi = fadd(acc_hi, v.z);
+                acc_hi = fadd(acc_hi, v.w);
+            }
+        }
+        g.sync();
+    }
     // ---- paired layout: chain k and chain G + k travel together (affine kDirect / kInverse on 16 lanes: 27 chains) ----------------
     // term2[k * kPairStride + 2 * pixel + {0, 1}] = term of chain k / chain G + k.  A pixel lane writes one 64-bit store per chain pair
     // (16 instead of 27 stores), a chain lane reads its row as float4s = two pixels of both chains, and advances both accumulators with
