@@ -1378,6 +1378,9 @@ static int LaunchKltTrackImpl(ftk_context *ctx, const KltLaunch &a) {
             // leave enough warps on an SM: per 200 k features 13x13 6.15 -> 5.58 ms, 15x15 7.14 -> 6.88 ms, but 17x17 8.28 -> 8.75 ms and
             // 21x21 (BASELINE configs[2]) 14.2 -> 18.2 ms (7 KB of hoisted samples per feature: 13 warps per SM)
             if (a.p.method == kInverse && geo.psize <= 15 * 15) return LaunchOne<FTK_VARIANT_LSSD, kInverse, 16>(ctx, a, geo, 32);
+            // One warp per CTA: a CTA's shared memory is released when its slowest feature finishes, and iteration counts differ a lot between
+            // features (21x21, 200 k features: 128 / 96 / 64 / 32 threads per CTA = 14.15 / 13.84 / 13.44 / 12.93 ms)
+            if (a.p.method == kInverse && geo.psize <= 32 * 64) return LaunchOne<FTK_VARIANT_LSSD, kInverse, 32>(ctx, a, geo, 32);
             if (geo.psize <= 32 * 64) return LaunchMethod<FTK_VARIANT_LSSD, 32>(ctx, a, geo);
             break;
         default:
