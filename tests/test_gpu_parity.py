@@ -153,6 +153,34 @@ def test_klt_entry_semantics(ctx, oracle):
     assert not ok
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,method,half", [("basic", "inverse", 5), ("basic", "fast", 9), ("affine", "direct", 6), ("affine", "fast", 6),
+                                                  ("affine", "inverse", 4), ("lssd", "inverse", 6), ("lssd", "fast", 5)])
+def test_klt_untracked_neighbours_with_garbage_positions(ctx, oracle, variant, method, half):
+    """Several features share a warp and run one instruction stream: a feature that is not tracked (entry status above kTracked, or beyond
+    kMaxTrackPointsNumber) keeps its partner company with its results discarded.  Its positions may be anything -- NaN, infinities, 1e30 --
+    and must neither disturb the partner nor be touched themselves (basic_klt.cpp:9,12,15)."""
+    ref, cur, uv, _ = S.make_pair(150, 200, 61, pair_id=41, border=14)  # odd count: the last warp has a group without a feature
+    rl, cl = oracle.pyramid_build(ref, 3), oracle.pyramid_build(cur, 3)
+    pyr = upload_levels(ctx, [rl, cl])
+    uv = uv.copy()
+    pred = uv + np.float32(0.75)
+    st_in = np.zeros(61, np.uint8)
+    garbage = [np.nan, np.inf, -np.inf, 1e30, -1e30, 3e9, -7.5]
+    for i in range(1, 61, 2):
+        st_in[i] = 2 + (i // 2) % 3  # kLargeResidual / kOutside / kNumericError: never re-tracked
+        g = np.float32(garbage[(i // 2) % len(garbage)])
+        if i % 4 == 1:
+            pred[i] = (g, -g)
+        else:
+            uv[i] = (g, np.float32(12.0))
+            pred[i, 1] = g
+    klt = make_tracker(ctx, variant, method, half, max_points=57)  # features 57..60 are beyond the cap as well
+    p = po.make_params(variant, method, half=half, max_points=57)
+    assert_same(f"{variant}/{method}", klt.TrackFeatures(pyr, pyr, uv, cur_pixel_uv=pred, status=st_in, ref_image=0, cur_image=1),
+                oracle.klt_track(p, rl, cl, uv, cur_uv=pred, status=st_in))
+
+
 def test_klt_batch_of_pairs(ctx, oracle):
     """Many frame pairs in one call (the sharding unit): ragged feature counts incl. an empty pair, device-built pyramids."""
     n_pairs, rows, cols, levels = 5, 120, 160, 3
